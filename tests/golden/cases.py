@@ -1,0 +1,81 @@
+"""Case tables shared by make_golden.py (reference side) and the tests (oracle / CUDA side)."""
+import numpy as np
+import torch
+
+PRUNE_KS = (-1, 0, 1, 2, 3)
+SPLITS = ('train', 'dev', 'test')
+SYNTH_ADJ_SEEDS = tuple(range(100, 108))           # 8 batches x 50 sentences x len(PRUNE_KS)
+
+# name -> (opt overrides, batch source, weight seed).  Batch source: ('split', name) = bundled sample JSON,
+# ('synth', seed, batch_size) = gcn_over_pruned_trees_b200.synth.make_batch.
+SMALL_VOCAB = 400
+MODEL_CASES = {
+    'cfg1_train_json_k1':   (dict(prune_k=1), ('split', 'train'), 11),
+    'cfg2_synth_kfull':     (dict(prune_k=-1, vocab_size=SMALL_VOCAB), ('synth', 201, 50), 12),
+    'cfg2_synth_k0':        (dict(prune_k=0, vocab_size=SMALL_VOCAB), ('synth', 202, 50), 12),
+    'cfg2_synth_k1':        (dict(prune_k=1, vocab_size=SMALL_VOCAB), ('synth', 203, 50), 12),
+    'cfg2_synth_k2':        (dict(prune_k=2, vocab_size=SMALL_VOCAB), ('synth', 204, 50), 12),
+    'cfg3_cgcn_k1':         (dict(prune_k=1, rnn=True, vocab_size=SMALL_VOCAB), ('synth', 205, 50), 13),
+    'cfg4_semeval_k1':      (dict(prune_k=1, dataset='semeval', num_class=19, vocab_size=SMALL_VOCAB),
+                             ('synth', 206, 50), 14),
+    'avg_pool_conv_l2':     (dict(prune_k=1, pooling='avg', conv_l2=0.01, vocab_size=SMALL_VOCAB),
+                             ('synth', 207, 24), 15),
+    'sum_pool_3layer_mlp1': (dict(prune_k=2, pooling='sum', num_layers=3, mlp_layers=1, pooling_l2=0.0,
+                                  vocab_size=SMALL_VOCAB), ('synth', 208, 24), 16),
+    'no_adj_1layer':        (dict(prune_k=1, no_adj=True, num_layers=1, vocab_size=SMALL_VOCAB),
+                             ('synth', 209, 24), 17),
+    'hidden64_k0':          (dict(prune_k=0, hidden_dim=64, emb_dim=50, pos_dim=5, ner_dim=0,
+                                  vocab_size=SMALL_VOCAB), ('synth', 210, 16), 18),
+}
+# cases that additionally store train-mode (dropout drawn from torch.manual_seed(DROPOUT_SEED)) loss + gradients
+GRAD_CASES = ('cfg1_train_json_k1', 'cfg2_synth_k1', 'cfg3_cgcn_k1', 'cfg4_semeval_k1', 'avg_pool_conv_l2',
+              'sum_pool_3layer_mlp1')
+DROPOUT_SEED = 777
+
+# hand-written trees: (head, subj token ids, obj token ids, deprel) -- heads are 1-based, 0 = root
+EDGE_TREES = {
+    'chain5':              ([0, 1, 2, 3, 4], [4], [0], [11, 2, 3, 4, 5]),
+    'subj_is_ancestor':    ([0, 1, 2, 3, 4], [1], [4], [11, 2, 3, 4, 5]),
+    'same_token':          ([2, 0, 2, 3], [3], [3], [5, 11, 6, 7]),            # singleton tree -> all-zero adj
+    'star':                ([0, 1, 1, 1, 1, 1, 1], [2], [5], [11, 2, 3, 4, 5, 6, 7]),
+    'multi_token_spans':   ([2, 0, 2, 3, 3, 5, 5, 2], [3, 4], [6, 7], [7, 11, 10, 3, 4, 5, 6, 2]),
+    'two_roots_ent_in_2nd': ([0, 1, 0, 3, 4, 3], [4], [5], [11, 2, 11, 4, 5, 6]),
+    'two_roots_ent_in_1st': ([0, 1, 1, 0, 4], [1], [2], [11, 2, 3, 11, 5]),
+    'len1':                ([0], [0], [0], [11]),
+    'len2':                ([2, 0], [0], [1], [7, 11]),
+    'deep_left_comb':      ([2, 3, 4, 5, 6, 7, 8, 0], [0], [7], [2, 3, 4, 5, 6, 7, 8, 11]),
+    'obj_empty':           ([0, 1, 2, 2], [3], [], [11, 2, 3, 4]),             # reference runs with S only
+    'deprel_pad_id':       ([0, 1, 1, 2], [3], [2], [11, 0, 5, 0]),            # deprel 0: forward entry is 0
+    'wide_and_deep':       ([3, 3, 0, 3, 4, 4, 6, 6, 8, 8, 10, 10], [11], [6], [2, 3, 11, 4, 5, 6, 7, 8, 9, 10, 12, 13]),
+}
+
+
+def positions(span_tokens, length, fill=150, width=None):
+    """subj_pos / obj_pos row for a (possibly non-contiguous) token set: 0 inside, nonzero elsewhere."""
+    width = length if width is None else width
+    row = np.full(width, fill, dtype=np.int64)
+    row[:length] = np.arange(1, length + 1)
+    for t in span_tokens:
+        row[t] = 0
+    return row
+
+
+def bundled_vocab(raw_splits):
+    """Stub vocab over the bundled sample (entity tokens anonymised as loader.py:49-53 does)."""
+    words = set()
+    for data in raw_splits.values():
+        for d in data:
+            toks = list(d['token'])
+            toks[d['subj_start']:d['subj_end'] + 1] = ['SUBJ-' + d['subj_type']] * (d['subj_end'] - d['subj_start'] + 1)
+            toks[d['obj_start']:d['obj_end'] + 1] = ['OBJ-' + d['obj_type']] * (d['obj_end'] - d['obj_start'] + 1)
+            words.update(toks)
+    return ['<PAD>', '<UNK>'] + sorted(words)
+
+
+def batch_from_npz(z, prefix):
+    """Rebuild the loader 10-tuple stored by make_golden.py under ``prefix``."""
+    def g(name):
+        return torch.from_numpy(z['%s/%s' % (prefix, name)].astype(np.int64))
+    words = g('words')
+    return (words, words.eq(0), g('pos'), g('ner'), g('deprel'), g('head'), g('subj_pos'), g('obj_pos'),
+            g('rels'), [int(i) for i in z['%s/orig_idx' % prefix]])
