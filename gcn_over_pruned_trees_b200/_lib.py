@@ -1,0 +1,58 @@
+"""ctypes binding of libgptb200.so (C ABI declared in include/gpt_b200.h).
+
+The library is built in-tree by ``csrc/build.py`` (nvcc, sm_100a).  There is no fallback: if the shared object is
+missing, ``lib()`` raises, and every op in ``ops.py`` goes through ``lib()``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgptb200.so')
+
+_c_int = ctypes.c_int
+_c_f = ctypes.c_float
+_c_u32 = ctypes.c_uint32
+_p = ctypes.c_void_p
+
+# name -> argtypes; every function returns int except gpt_error_string
+SIGNATURES = {
+    'gpt_version': [],
+    'gpt_prune_csr': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p, _p, _p],
+    'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
+                              _c_int, _p],
+    'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
+    'gpt_pool3_fwd': [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p],
+    'gpt_pool3_bwd': [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_linear_fwd_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
+    'gpt_linear_dgrad_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
+    'gpt_linear_wgrad_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
+}
+
+_lib = None
+
+
+class GptError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly when the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GptError('%s not found: build it with `python %s` (nvcc, sm_100a). There is no CPU fallback.'
+                           % (LIB_PATH, os.path.join(_HERE, 'csrc', 'build.py')))
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _c_int
+        handle.gpt_error_string.argtypes = [_c_int]
+        handle.gpt_error_string.restype = ctypes.c_char_p
+        _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        raise GptError('%s failed with code %d: %s' % (what, code, lib().gpt_error_string(code).decode()))

@@ -1,0 +1,182 @@
+// K3 (fp32-exact mode) -- SIMT fp32 GEMMs for the W projection, its dgrad and its wgrad.
+//
+// The reference computes  W_l(Ax) + W_l(h)  with two nn.Linear calls per layer
+// (/root/reference/model/gcn.py:270-271); by linearity one projection  y = h W_l^T  per layer suffices, the bias
+// moves into the aggregation epilogue (aggregate.cu).  This file is the FFMA path: it accumulates in fp32 like
+// the reference's CPU/cuBLAS SGEMM and is what the 1e-5 logits/loss parity is stated for.  The tensor-core path
+// (tcgen05/TMEM, TF32x3 / BF16) lives in gemm_tcgen05.cu.
+//
+//   fwd   : Y[M,N]  = X[M,K]  . W[N,K]^T        (A k-contiguous, B k-contiguous)
+//   dgrad : dX[M,K] = dY[M,N] . W[N,K]          (A k-contiguous, B n-contiguous)
+//   wgrad : dW[N,K] = dY[M,N]^T . X[M,K]        (A m-contiguous, B n-contiguous; split over M, atomic reduce)
+//
+// 64x64 output tile, 16-deep k-slab, 256 threads x (4x4) micro-tile, operands staged k-major in shared memory.
+#include "gpt_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, kGemmThreads = 256;
+
+// C[m,n] (+)= sum_k A(m,k) * B(n,k)
+//   A_KC: A(m,k) = A[m*lda + k]   else A(m,k) = A[k*lda + m]
+//   B_KC: B(n,k) = B[n*ldb + k]   else B(n,k) = B[k*ldb + n]
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(kGemmThreads)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+             float* __restrict__ C, int ldc, int k_per_split, int atomic_out) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        // ---- stage A slab: 64 (m) x 16 (k) ---------------------------------------------------------------
+        if (A_KC) {
+            const int m = tid / 4, kk = (tid % 4) * 4;  // 4 consecutive k per thread
+            const int gm = m0 + m, gk = k0 + kk;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (gm < M) {
+                const float* src = A + (size_t)gm * lda + gk;
+                if (gk + 3 < k_end && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    const float4 f = *reinterpret_cast<const float4*>(src);
+                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gk + i < k_end) v[i] = src[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[kk + i][m] = v[i];
+        } else {
+            const int kk = tid / 16, m = (tid % 16) * 4;  // 4 consecutive m per thread
+            const int gk = k0 + kk, gm = m0 + m;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < k_end) {
+                const float* src = A + (size_t)gk * lda + gm;
+                if (gm + 3 < M && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    f = *reinterpret_cast<const float4*>(src);
+                } else {
+                    if (gm < M) f.x = src[0];
+                    if (gm + 1 < M) f.y = src[1];
+                    if (gm + 2 < M) f.z = src[2];
+                    if (gm + 3 < M) f.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(&As[kk][m]) = f;
+        }
+        // ---- stage B slab: 64 (n) x 16 (k) ---------------------------------------------------------------
+        if (B_KC) {
+            const int n = tid / 4, kk = (tid % 4) * 4;
+            const int gn = n0 + n, gk = k0 + kk;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (gn < N) {
+                const float* src = B + (size_t)gn * ldb + gk;
+                if (gk + 3 < k_end && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    const float4 f = *reinterpret_cast<const float4*>(src);
+                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gk + i < k_end) v[i] = src[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[kk + i][n] = v[i];
+        } else {
+            const int kk = tid / 16, n = (tid % 16) * 4;
+            const int gk = k0 + kk, gn = n0 + n;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < k_end) {
+                const float* src = B + (size_t)gk * ldb + gn;
+                if (gn + 3 < N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    f = *reinterpret_cast<const float4*>(src);
+                } else {
+                    if (gn < N) f.x = src[0];
+                    if (gn + 1 < N) f.y = src[1];
+                    if (gn + 2 < N) f.z = src[2];
+                    if (gn + 3 < N) f.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(&Bs[kk][n]) = f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float* dst = C + (size_t)gm * ldc + gn;
+            if (atomic_out) atomicAdd(dst, acc[i][j]);
+            else *dst = acc[i][j];
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+int run_sgemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int splits,
+              cudaStream_t st) {
+    if (M == 0 || N == 0) return GPT_OK;
+    splits = max(1, min(splits, (K + BK - 1) / BK));
+    int k_per_split = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (K + k_per_split - 1) / k_per_split;
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+    if (grid.y > 65535 || grid.z > 65535) return GPT_ERR_UNSUPPORTED;
+    sgemm_kernel<A_KC, B_KC><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, k_per_split,
+                                                           splits > 1 ? 1 : 0);
+    return gpt_launch_status();
+}
+
+__global__ void zero_rows_kernel(float* C, int rows, int cols, int ldc) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)rows * cols) C[(i / cols) * ldc + (i % cols)] = 0.f;
+}
+
+}  // namespace
+
+extern "C" int gpt_linear_fwd_f32(const float* x, const float* w, float* y, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(x && w && y && M >= 0 && N >= 1 && K >= 1);
+    return run_sgemm<true, true>(M, N, K, x, K, w, K, y, N, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_linear_dgrad_f32(const float* dy, const float* w, float* dx, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(dy && w && dx && M >= 0 && N >= 1 && K >= 1);
+    // dx[m,k] = sum_n dy[m,n] * w[n,k]: reduction index n; A = dy (n-contiguous), B(k, n) = w[n*K + k]
+    return run_sgemm<true, false>(M, K, N, dy, N, w, K, dx, K, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(dy && x && dw && M >= 0 && N >= 1 && K >= 1);
+    // dw[n,k] = sum_m dy[m,n] * x[m,k]: reduction index m; A(n, m) = dy[m*N + n], B(k, m) = x[m*K + k]
+    cudaStream_t st = (cudaStream_t)stream;
+    const long tiles = (long)((N + BN - 1) / BN) * ((K + BM - 1) / BM);
+    int splits = (int)max(1L, min((long)(M + 255) / 256, (4L * 148 + tiles - 1) / tiles));
+    if (splits > 1 || M == 0) {
+        const size_t n = (size_t)N * K;
+        zero_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dw, N, K, K);
+    }
+    if (M == 0) return gpt_launch_status();
+    return run_sgemm<false, false>(N, K, M, dy, N, x, K, dw, K, splits, st);
+}

@@ -1,0 +1,199 @@
+"""GCN relation classifier on the B200 kernels -- same classes, constructor arguments, forward signatures and
+``state_dict`` keys as /root/reference/model/gcn.py (GCNClassifier :15-36, GCNRelationModel :38-126, GCN :128-470,
+pool :473-483, rnn_zero_state :485-492), ``adj_type='regular'`` path.
+
+What changed underneath:
+  * the per-sentence numpy loop + dense [B,T,T] adjacency (gcn.py:96-110) is one kernel launch that leaves a CSR
+    on the device (ops.prune_csr -> csrc/prune_csr.cu); nothing is copied to the host inside forward()
+  * each layer is one projection GEMM + one fused gather/normalise/ReLU/dropout kernel (ops.gcn_layer) instead
+    of bmm + 2 Linear + div + relu + dropout (gcn.py:269-271, 390-393)
+  * the three pool() passes + cat (gcn.py:116-121) are one kernel (ops.pool3)
+There is no CPU implementation: inputs must live on a CUDA device.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+try:                                    # imported as gcn_over_pruned_trees_b200.model.gcn
+    from .. import constant, ops, torch_utils
+except ImportError:                     # imported as top-level `model.gcn` (package dir on PYTHONPATH, like the reference)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from gcn_over_pruned_trees_b200 import constant, ops, torch_utils
+
+
+class GCNClassifier(nn.Module):
+    """GCNRelationModel + linear classifier (reference gcn.py:15-36)."""
+
+    def __init__(self, opt, emb_matrix=None):
+        super().__init__()
+        self.gcn_model = GCNRelationModel(opt, emb_matrix=emb_matrix)
+        self.classifier = nn.Linear(opt['hidden_dim'], opt['num_class'])
+        self.opt = opt
+
+    def conv_l2(self):
+        return self.gcn_model.gcn.conv_l2()
+
+    def forward(self, inputs):
+        outputs, pooling_output = self.gcn_model(inputs)
+        return self.classifier(outputs), pooling_output
+
+    def get_deprel_emb(self):
+        return self.gcn_model.get_deprel_embedding()
+
+    def get_gcn_parameters(self):
+        return self.gcn_model.get_gcn_parameters()
+
+
+class GCNRelationModel(nn.Module):
+    def __init__(self, opt, emb_matrix=None):
+        super().__init__()
+        if opt.get('adj_type', 'regular') != 'regular':
+            raise NotImplementedError("adj_type=%r: only the 'regular' adjacency path is built (SURVEY.md 8f-2)"
+                                      % opt['adj_type'])
+        self.opt = opt
+        self.emb_matrix = emb_matrix
+        # tables are registered here AND on self.gcn, as in the reference (gcn.py:45-57,138): the checkpoint
+        # carries both key sets, pointing at shared storage
+        self.emb = nn.Embedding(opt['vocab_size'], opt['emb_dim'], padding_idx=constant.PAD_ID)
+        self.pos_emb = nn.Embedding(constant.NUM_POS, opt['pos_dim']) if opt['pos_dim'] > 0 else None
+        self.ner_emb = nn.Embedding(constant.NUM_NER, opt['ner_dim']) if opt['ner_dim'] > 0 else None
+        self.deprel_emb = nn.Embedding(constant.NUM_DEPREL, 1, padding_idx=0)   # unused by 'regular' (gcn.py:53-56)
+        self.init_embeddings()
+        self.gcn = GCN(opt, (self.emb, self.pos_emb, self.ner_emb, self.deprel_emb), opt['hidden_dim'],
+                       opt['num_layers'])
+        hidden = opt['hidden_dim']
+        layers = [nn.Linear(3 * hidden, hidden), nn.ReLU()]
+        for _ in range(opt['mlp_layers'] - 1):
+            layers += [nn.Linear(hidden, hidden), nn.ReLU()]
+        self.out_mlp = nn.Sequential(*layers)
+        self.last_csr = None
+
+    def get_deprel_embedding(self):
+        return self.deprel_emb.weight
+
+    def init_embeddings(self):
+        if self.emb_matrix is None:
+            self.emb.weight.data[1:, :].uniform_(-1.0, 1.0)
+        else:
+            self.emb_matrix = torch.from_numpy(self.emb_matrix)
+            self.emb.weight.data.copy_(self.emb_matrix)
+        topn = self.opt['topn']
+        if topn <= 0:
+            print("Do not finetune word embedding layer.")
+            self.emb.weight.requires_grad = False
+        elif topn < self.opt['vocab_size']:
+            print("Finetune top {} word embeddings.".format(topn))
+            self.emb.weight.register_hook(lambda g: torch_utils.keep_partial_grad(g, int(topn)))
+        else:
+            print("Finetune all embeddings.")
+
+    def forward(self, inputs):
+        if self.opt['dataset'] == 'tacred':
+            words, masks, pos, ner, deprel, head, subj_pos, obj_pos = inputs
+        else:
+            words, masks, pos, deprel, head, subj_pos, obj_pos = inputs
+        # K1: pruned trees -> CSR, on the device, no host round trip
+        csr = ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, self.opt['prune_k'])
+        self.last_csr = csr
+        h, _ = self.gcn(csr, inputs)
+        # K4: sentence / subject / object pools in one pass
+        pooled = ops.pool3(h, csr, self.opt['pooling'])
+        h_out = pooled[:, :self.opt['hidden_dim']]
+        return self.out_mlp(pooled), h_out
+
+    def get_gcn_parameters(self):
+        return self.gcn.get_gcn_parameters()
+
+
+class GCN(nn.Module):
+    """GCN / C-GCN over the pruned-tree CSR (reference gcn.py:128-395, regular branch)."""
+
+    def __init__(self, opt, embeddings, mem_dim, num_layers):
+        super().__init__()
+        self.opt = opt
+        self.layers = num_layers
+        self.use_cuda = opt['cuda']
+        self.mem_dim = mem_dim
+        self.in_dim = opt['emb_dim'] + opt['pos_dim'] + (opt['ner_dim'] if opt['dataset'] == 'tacred' else 0)
+        self.emb, self.pos_emb, self.ner_emb, self.deprel_emb = embeddings
+        if opt.get('rnn', False):      # C-GCN encoder stays on cuDNN (north_star)
+            self.rnn = nn.LSTM(self.in_dim, opt['rnn_hidden'], opt['rnn_layers'], batch_first=True,
+                               dropout=opt['rnn_dropout'], bidirectional=True)
+            self.in_dim = opt['rnn_hidden'] * 2
+            self.rnn_drop = nn.Dropout(opt['rnn_dropout'])
+        self.in_drop = nn.Dropout(opt['input_dropout'])
+        self.gcn_drop = nn.Dropout(opt['gcn_dropout'])   # kept for API parity; the fused kernel draws its own mask
+        if opt.get('emb_dropout', 0.0) > 0:
+            raise NotImplementedError('emb_dropout > 0 (EmbeddingDropout) is outside the built path (SURVEY.md 2-#8)')
+        self.W = nn.ModuleList(nn.Linear(self.in_dim if l == 0 else mem_dim, mem_dim) for l in range(num_layers))
+        self.gemm_mode = opt.get('gemm_mode', 'fp32')
+        # {seed, step} consumed by the in-kernel Philox dropout; int64 storage, read as uint64 by the kernel
+        self.register_buffer('rng_state', torch.tensor([torch.initial_seed() & 0x7fffffffffffffff, 0],
+                                                       dtype=torch.int64), persistent=False)
+        self.injected_masks = None      # tests only: {'in': m, 'rnn': m, 'gcn0': m, ...}, pre-scaled by 1/(1-p)
+
+    def conv_l2(self):
+        return sum(p.pow(2).sum() for lin in self.W for p in (lin.weight, lin.bias))
+
+    def get_gcn_parameters(self):
+        return self.W
+
+    def _host_dropout(self, x, module, name):
+        if self.injected_masks is not None and name in self.injected_masks:
+            return x * self.injected_masks[name]
+        return module(x)
+
+    def encode_with_rnn(self, rnn_inputs, masks, batch_size):
+        seq_lens = masks.eq(constant.PAD_ID).long().sum(1).cpu()      # reference gcn.py:186-197
+        h0, c0 = rnn_zero_state(batch_size, self.opt['rnn_hidden'], self.opt['rnn_layers'],
+                                use_cuda=rnn_inputs.is_cuda)
+        packed = nn.utils.rnn.pack_padded_sequence(rnn_inputs, seq_lens, batch_first=True, enforce_sorted=False)
+        out, _ = self.rnn(packed, (h0, c0))
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=rnn_inputs.size(1))
+        return out
+
+    def forward(self, adj, inputs):
+        if not isinstance(adj, ops.TreeCSR):
+            raise TypeError('GCN.forward takes the TreeCSR produced by ops.prune_csr, not a dense adjacency')
+        if self.opt['dataset'] == 'tacred':
+            words, masks, pos, ner, deprel, head, subj_pos, obj_pos = inputs
+        else:
+            words, masks, pos, deprel, head, subj_pos, obj_pos = inputs
+            ner = None
+        embs = [words if words.dim() > 2 else self.emb(words)]
+        if self.opt['pos_dim'] > 0:
+            embs.append(self.pos_emb(pos))
+        if self.opt['ner_dim'] > 0 and self.opt['dataset'] == 'tacred':
+            embs.append(self.ner_emb(ner))
+        x = self._host_dropout(torch.cat(embs, dim=2), self.in_drop, 'in')
+        if self.opt.get('rnn', False):
+            x = self._host_dropout(self.encode_with_rnn(x, masks, words.size(0)), self.rnn_drop, 'rnn')
+        use_adj = not self.opt.get('no_adj', False)
+        drop_p = self.opt['gcn_dropout'] if self.training else 0.0
+        if self.training and drop_p > 0 and self.injected_masks is None:
+            self.rng_state[1] += 1         # new dropout stream every training forward (graph-capture safe)
+        for l, lin in enumerate(self.W):
+            last = l == self.layers - 1
+            mask = None if self.injected_masks is None else self.injected_masks.get('gcn%d' % l)
+            p = 0.0 if (last or mask is not None) else drop_p
+            x = ops.gcn_layer(x, lin.weight, lin.bias, adj, use_adj=use_adj, drop_p=p, rng_state=self.rng_state,
+                              subseq=l, drop_mask=None if last else mask, gemm_mode=self.gemm_mode)
+        return x, adj.pool_mask()
+
+
+def pool(h, mask, type='max'):
+    """Single masked pool with the reference's semantics (gcn.py:473-483); the model itself uses ops.pool3."""
+    if type == 'max':
+        return h.masked_fill(mask, -constant.INFINITY_NUMBER).max(1)[0]
+    h = h.masked_fill(mask, 0)
+    if type == 'avg':
+        return h.sum(1) / (mask.size(1) - mask.float().sum(1))
+    return h.sum(1)
+
+
+def rnn_zero_state(batch_size, hidden_dim, num_layers, bidirectional=True, use_cuda=True):
+    shape = (num_layers * (2 if bidirectional else 1), batch_size, hidden_dim)
+    h0 = c0 = torch.zeros(*shape, device='cuda' if use_cuda else 'cpu')
+    return h0, c0

@@ -1,0 +1,105 @@
+"""Trainer API of the reference (/root/reference/model/trainer.py:14-127) on the B200 model.
+
+``GCNTrainer(opt, emb_matrix)``, ``.update(batch) -> loss tensor (caller runs backward/clip/step, train.py:220-227)``,
+``.predict(batch, unsort=True) -> (predictions, probs, loss)``, ``.save/.load`` with the same checkpoint dict
+``{'model': state_dict, 'config': opt}``, ``.update_lr``, ``.get_deprel_emb``; attributes ``model, criterion,
+parameters, optimizer, opt``.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .gcn import GCNClassifier
+try:
+    from .. import torch_utils
+except ImportError:
+    from gcn_over_pruned_trees_b200 import torch_utils
+
+
+class Trainer(object):
+    def __init__(self, opt, emb_matrix=None):
+        raise NotImplementedError
+
+    def update(self, batch):
+        raise NotImplementedError
+
+    def predict(self, batch):
+        raise NotImplementedError
+
+    def update_lr(self, new_lr):
+        torch_utils.change_lr(self.optimizer, new_lr)
+
+    def load(self, filename):
+        try:
+            checkpoint = torch.load(filename, map_location=None if torch.cuda.is_available() else 'cpu')
+        except BaseException:
+            print("Cannot load model from {}".format(filename))
+            exit()
+        self.model.load_state_dict(checkpoint['model'])
+        self.opt = checkpoint['config']
+
+    def save(self, filename, epoch):
+        params = {'model': self.model.state_dict(), 'config': self.opt}
+        try:
+            torch.save(params, filename)
+            print("model saved to {}".format(filename))
+        except BaseException:
+            print("[Warning: Saving failed... continuing anyway.]")
+
+
+def unpack_batch(batch, cuda):
+    """Loader tuple -> (inputs, labels, tokens, head, subj_pos, obj_pos, lens); TACRED 10-tuple or SemEval 9-tuple."""
+    if cuda:
+        inputs = [b.cuda(non_blocking=True) for b in batch[:-2]]
+        labels = batch[-2].cuda(non_blocking=True)
+    else:
+        inputs = list(batch[:-2])
+        labels = batch[-2]
+    tokens = batch[0]
+    off = 5 if len(batch) >= 10 else 4
+    head, subj_pos, obj_pos = batch[off], batch[off + 1], batch[off + 2]
+    lens = batch[1].eq(0).long().sum(1).squeeze()
+    return inputs, labels, tokens, head, subj_pos, obj_pos, lens
+
+
+class GCNTrainer(Trainer):
+    def __init__(self, opt, emb_matrix=None):
+        self.opt = opt
+        self.emb_matrix = emb_matrix
+        self.model = GCNClassifier(opt, emb_matrix=emb_matrix)
+        self.criterion = nn.CrossEntropyLoss()
+        self.parameters = [p for p in self.model.parameters() if p.requires_grad]
+        if opt['cuda']:
+            self.model.cuda()
+            self.criterion.cuda()
+        self.optimizer = torch_utils.get_optimizer(opt['optim'], self.parameters, opt['lr'])
+
+    def _loss(self, logits, pooling_output, labels):
+        loss = self.criterion(logits, labels)
+        if self.opt.get('conv_l2', 0) > 0:
+            loss = loss + self.model.conv_l2() * self.opt['conv_l2']
+        if self.opt.get('pooling_l2', 0) > 0:
+            loss = loss + self.opt['pooling_l2'] * (pooling_output ** 2).sum(1).mean()
+        return loss
+
+    def update(self, batch):
+        inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]
+        logits, pooling_output = self.model(inputs)
+        return self._loss(logits, pooling_output, labels)
+
+    def predict(self, batch, unsort=True):
+        inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]
+        orig_idx = batch[-1]
+        self.model.eval()
+        with torch.no_grad():
+            logits, _ = self.model(inputs)
+            loss = self.criterion(logits, labels)
+            probs = F.softmax(logits, 1).cpu().numpy().tolist()
+            predictions = np.argmax(logits.cpu().numpy(), axis=1).tolist()
+        if unsort:
+            _, predictions, probs = [list(t) for t in zip(*sorted(zip(orig_idx, predictions, probs)))]
+        return predictions, probs, loss.item()
+
+    def get_deprel_emb(self):
+        return self.model.get_deprel_emb()

@@ -1,0 +1,218 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (include/gpt_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream, and autograd orders the backward calls so that
+the caller-owned ``loss.backward()`` of the reference's train loop (/root/reference/train.py:220-221) keeps working.
+All arithmetic of the hot path happens in libgptb200.so.
+"""
+import torch
+
+from . import _lib
+
+POOL_TYPES = {'max': 0, 'avg': 1, 'sum': 2}
+GEMM_MODES = {'fp32': 0, 'tf32': 1, 'tf32x3': 2, 'bf16': 3}
+
+TREE_ERR_FATAL = 1 | 2 | 4 | 8 | 16 | 32
+TREE_ERR_NAMES = {1: 'head out of range', 2: 'no root', 4: 'cycle in head', 8: 'empty subject span',
+                  16: 'entities under different roots', 32: 'deprel id out of range',
+                  64: 'kept edge with deprel 0 (asymmetric adjacency)'}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dev(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.GptError('%s must be a CUDA tensor: the gpt_b200 path has no CPU fallback' % name)
+    if t.dtype != dtype:
+        raise _lib.GptError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class TreeCSR(object):
+    """Device-resident pruned-tree adjacency of one padded batch (output of K1)."""
+    __slots__ = ('B', 'T', 'rowptr', 'col', 'val', 'flags', 'denom', 'lens', 'err')
+
+    def __init__(self, B, T, device):
+        self.B, self.T = B, T
+        self.rowptr = torch.empty((B, T + 1), dtype=torch.int32, device=device)
+        self.col = torch.empty((B, 3 * T), dtype=torch.int32, device=device)
+        self.val = torch.empty((B, 3 * T), dtype=torch.uint8, device=device)
+        self.flags = torch.empty((B, T), dtype=torch.uint8, device=device)
+        self.denom = torch.empty((B, T), dtype=torch.float32, device=device)
+        self.lens = torch.empty((B,), dtype=torch.int32, device=device)
+        self.err = torch.empty((B,), dtype=torch.int32, device=device)
+
+    def to_dense(self):
+        """[B,T,T] float32 with the reference's relation-id values (tests / debugging; synchronises)."""
+        B, T = self.B, self.T
+        rowptr = self.rowptr.cpu().long()
+        col = self.col.cpu().long()
+        val = self.val.cpu().float()
+        adj = torch.zeros((B, T, T), dtype=torch.float32)
+        counts = rowptr[:, 1:] - rowptr[:, :-1]
+        for b in range(B):
+            nnz = int(rowptr[b, T])
+            if nnz == 0:
+                continue
+            rows = torch.repeat_interleave(torch.arange(T), counts[b])
+            adj[b, rows, col[b, :nnz]] = val[b, :nnz]
+        return adj
+
+    def pool_mask(self):
+        """bool [B,T,1], True where the token is not in the pruned tree (the reference's `mask`, gcn.py:262)."""
+        return (self.flags & 1).eq(0).unsqueeze(2)
+
+    def check(self):
+        """Raise on sentences the reference cannot process (synchronises; call outside the hot loop)."""
+        bad = (self.err & TREE_ERR_FATAL).nonzero().flatten().tolist()
+        if bad:
+            code = int(self.err[bad[0]])
+            why = ', '.join(n for bit, n in TREE_ERR_NAMES.items() if code & bit)
+            raise _lib.GptError('malformed dependency tree in batch row %d: %s' % (bad[0], why))
+
+
+def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k):
+    """K1: batched head_to_tree + tree_to_adj (model/tree.py:58-204, model/gcn.py:96-110) -> TreeCSR."""
+    head = _dev(head, torch.int64, 'head')
+    subj_pos = _dev(subj_pos, torch.int64, 'subj_pos')
+    obj_pos = _dev(obj_pos, torch.int64, 'obj_pos')
+    deprel = _dev(deprel, torch.int64, 'deprel')
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8) if masks.is_contiguous() else masks.contiguous().view(torch.uint8)
+    masks = _dev(masks, torch.uint8, 'masks')
+    B, T = head.shape
+    csr = TreeCSR(B, T, head.device)
+    rc = _lib.lib().gpt_prune_csr(_ptr(head), _ptr(subj_pos), _ptr(obj_pos), _ptr(deprel), _ptr(masks), B, T,
+                                  int(prune_k), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(csr.flags),
+                                  _ptr(csr.denom), _ptr(csr.lens), _ptr(csr.err), _stream())
+    _lib.check(rc, 'gpt_prune_csr')
+    return csr
+
+
+# ---- K3: projection ------------------------------------------------------------------------------------------
+
+def linear_fwd(x2d, weight, mode='fp32'):
+    M, K = x2d.shape
+    N = weight.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
+    if mode != 'fp32':
+        raise _lib.GptError('gemm mode %r not built' % mode)
+    _lib.check(_lib.lib().gpt_linear_fwd_f32(_ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream()),
+               'gpt_linear_fwd_f32')
+    return y
+
+
+def linear_dgrad(dy, weight, mode='fp32'):
+    M, N = dy.shape
+    K = weight.shape[1]
+    dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.lib().gpt_linear_dgrad_f32(_ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream()),
+               'gpt_linear_dgrad_f32')
+    return dx
+
+
+def linear_wgrad(dy, x2d, mode='fp32'):
+    M, N = dy.shape
+    K = x2d.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.lib().gpt_linear_wgrad_f32(_ptr(dy), _ptr(x2d), _ptr(dw), M, N, K, _stream()),
+               'gpt_linear_wgrad_f32')
+    return dw
+
+
+# ---- K2: aggregation -----------------------------------------------------------------------------------------
+
+def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq=0, drop_mask=None, force_vec=0):
+    B, T = csr.B, csr.T
+    H = y.shape[-1]
+    out = torch.empty((B, T, H), dtype=torch.float32, device=y.device)
+    rc = _lib.lib().gpt_gcn_aggregate_fwd(_ptr(y), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
+                                          _ptr(csr.flags), _ptr(bias), _ptr(out), B, T, H, int(bool(use_adj)),
+                                          float(drop_p), _ptr(rng_state), int(subseq), _ptr(drop_mask),
+                                          int(force_vec), _stream())
+    _lib.check(rc, 'gpt_gcn_aggregate_fwd')
+    return out
+
+
+def aggregate_bwd(gout, out, csr, use_adj=True, drop_p=0.0, drop_mask=None, want_dbias=True, force_vec=0):
+    B, T = csr.B, csr.T
+    H = out.shape[-1]
+    dy = torch.empty((B * T, H), dtype=torch.float32, device=out.device)
+    dbias = torch.zeros((H,), dtype=torch.float32, device=out.device) if want_dbias else None
+    rc = _lib.lib().gpt_gcn_aggregate_bwd(_ptr(gout), _ptr(out), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
+                                          _ptr(dy), _ptr(dbias), B, T, H, int(bool(use_adj)), float(drop_p),
+                                          _ptr(drop_mask), int(force_vec), _stream())
+    _lib.check(rc, 'gpt_gcn_aggregate_bwd')
+    return dy, dbias
+
+
+class _GcnLayer(torch.autograd.Function):
+    """One `regular` GCN layer (model/gcn.py:269-271, 390-393): projection GEMM + fused aggregation epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, csr, use_adj, drop_p, rng_state, subseq, drop_mask, gemm_mode):
+        x = _dev(x, torch.float32, 'x')
+        weight = _dev(weight, torch.float32, 'weight')
+        bias = _dev(bias, torch.float32, 'bias')
+        if drop_mask is not None:
+            drop_mask = _dev(drop_mask, torch.float32, 'drop_mask')
+        B, T, K = x.shape
+        y = linear_fwd(x.view(B * T, K), weight, gemm_mode)
+        out = aggregate_fwd(y, csr, bias, use_adj, drop_p if drop_mask is None else 0.0, rng_state, subseq, drop_mask)
+        ctx.csr, ctx.use_adj, ctx.gemm_mode = csr, use_adj, gemm_mode
+        ctx.drop_p = drop_p if drop_mask is None else 0.0
+        ctx.save_for_backward(x, weight, out, drop_mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight, out, drop_mask = ctx.saved_tensors
+        B, T, K = x.shape
+        gout = _dev(gout, torch.float32, 'grad_out')
+        dy, dbias = aggregate_bwd(gout, out, ctx.csr, ctx.use_adj, ctx.drop_p, drop_mask,
+                                  want_dbias=ctx.needs_input_grad[2])
+        dx = linear_dgrad(dy, weight, ctx.gemm_mode).view(B, T, K) if ctx.needs_input_grad[0] else None
+        dw = linear_wgrad(dy, x.view(B * T, K), ctx.gemm_mode) if ctx.needs_input_grad[1] else None
+        return dx, dw, dbias, None, None, None, None, None, None, None
+
+
+def gcn_layer(x, weight, bias, csr, use_adj=True, drop_p=0.0, rng_state=None, subseq=0, drop_mask=None,
+              gemm_mode='fp32'):
+    return _GcnLayer.apply(x, weight, bias, csr, use_adj, drop_p, rng_state, subseq, drop_mask, gemm_mode)
+
+
+# ---- K4: pooling -----------------------------------------------------------------------------------------------
+
+class _Pool3(torch.autograd.Function):
+    """cat[pool(h, not-in-tree), pool(h, not-subj), pool(h, not-obj)] (model/gcn.py:116-121, 473-483)."""
+
+    @staticmethod
+    def forward(ctx, h, csr, pool_type):
+        h = _dev(h, torch.float32, 'h')
+        B, T, H = h.shape
+        out = torch.empty((B, 3 * H), dtype=torch.float32, device=h.device)
+        argmax = torch.empty((B, 3 * H), dtype=torch.int32, device=h.device) if pool_type == 0 else None
+        _lib.check(_lib.lib().gpt_pool3_fwd(_ptr(h), _ptr(csr.flags), B, T, H, pool_type, _ptr(out), _ptr(argmax),
+                                            _stream()), 'gpt_pool3_fwd')
+        ctx.csr, ctx.pool_type, ctx.shape = csr, pool_type, (B, T, H)
+        ctx.save_for_backward(argmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (argmax,) = ctx.saved_tensors
+        B, T, H = ctx.shape
+        gout = _dev(gout, torch.float32, 'grad_out')
+        dh = torch.empty((B, T, H), dtype=torch.float32, device=gout.device)
+        _lib.check(_lib.lib().gpt_pool3_bwd(_ptr(gout), _ptr(argmax), _ptr(ctx.csr.flags), B, T, H, ctx.pool_type,
+                                            _ptr(dh), _stream()), 'gpt_pool3_bwd')
+        return dh, None, None
+
+
+def pool3(h, csr, pool_type='max'):
+    return _Pool3.apply(h, csr, POOL_TYPES[pool_type])

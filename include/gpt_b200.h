@@ -1,0 +1,105 @@
+/* gpt_b200 -- C ABI of the B200 (sm_100a) GCN-over-pruned-trees hot path.
+ *
+ * The reference (gstoica27/gcn-over-pruned-trees) has no FFI: its hot path is Python calling numpy and ATen.
+ * Each entry point below replaces a span of that Python; the span is cited as file:line into /root/reference.
+ * INTEGRATION.md shows the ctypes binding and where each call goes in the reference's model/gcn.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer valid on `stream` unless marked host; the caller owns all buffers
+ *   - stateless, no allocation, no synchronisation, safe under CUDA-graph capture
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return 0 on success, <0 for argument/support errors (GPT_ERR_*), >0 = cudaError_t of the launch
+ *   - batch layout: B sentences padded to T tokens; row r = b*T + t; activations are row-major [B*T, H] fp32
+ */
+#ifndef GPT_B200_H
+#define GPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPT_OK 0
+#define GPT_ERR_BAD_ARG (-1)
+#define GPT_ERR_UNSUPPORTED (-2)
+#define GPT_ERR_DRIVER (-3)
+
+/* flags[b,t] bits (gpt_prune_csr output) */
+#define GPT_FLAG_INTREE 1 /* token has >= 1 adjacency entry, i.e. is NOT pool-masked (model/gcn.py:262) */
+#define GPT_FLAG_SUBJ 2   /* subj_pos == 0 (model/gcn.py:116) */
+#define GPT_FLAG_OBJ 4    /* obj_pos == 0 */
+
+/* err[b] bits (gpt_prune_csr output).  Bits 1..32 are fatal for the sentence: it gets an empty adjacency, where
+ * the reference raises or never returns.  64 is a warning. */
+#define GPT_TREE_HEAD_RANGE 1
+#define GPT_TREE_NO_ROOT 2      /* model/tree.py:164 assert */
+#define GPT_TREE_CYCLE 4        /* model/tree.py:91-94 loops forever */
+#define GPT_TREE_EMPTY_SUBJ 8   /* model/tree.py:109 AttributeError */
+#define GPT_TREE_DISJOINT 16    /* model/tree.py:121-127 UnboundLocalError */
+#define GPT_TREE_DEPREL_RANGE 32
+#define GPT_TREE_DEPREL_PAD 64  /* kept edge with deprel 0: forward entry is 0, adjacency not symmetric */
+
+/* pooling type of gpt_pool3_* (model/gcn.py:473-483) */
+#define GPT_POOL_MAX 0
+#define GPT_POOL_AVG 1
+#define GPT_POOL_SUM 2
+
+/* GEMM arithmetic of gpt_linear_* */
+#define GPT_GEMM_FP32 0   /* SIMT FFMA, fp32 accumulate: the 1e-5 parity mode */
+#define GPT_GEMM_TF32 1   /* tcgen05 kind::tf32, one pass */
+#define GPT_GEMM_TF32X3 2 /* tcgen05 kind::tf32, hi/lo split, three passes: fp32-grade accuracy on tensor cores */
+#define GPT_GEMM_BF16 3   /* tcgen05 kind::f16 on bf16-rounded operands, fp32 accumulate */
+
+int gpt_version(void);
+/* host: static string for a return code of this library (cudaGetErrorString for positive codes) */
+const char* gpt_error_string(int code);
+
+/* K1. head_to_tree + tree_to_adj + the batch loop + adj!=0/denom/mask
+ *     (model/tree.py:58-165, model/tree.py:167-204, model/gcn.py:96-110, model/gcn.py:260-262).
+ * in : head, subj_pos, obj_pos, deprel  int64 [B,T] (loader layout, data/loader.py:110-121);
+ *      pad_mask uint8/bool [B,T], nonzero on padding (the `masks` tensor)
+ *      prune_k < 0: full tree, else path-centric pruning distance
+ * out: rowptr int32 [B,T+1]  offsets into the sentence's segment of col/val (segment b starts at b*3*T)
+ *      col    int32 [B,3*T]  column (token index inside the sentence), ascending inside a row
+ *      val    uint8 [B,3*T]  the reference's adjacency value: deprel (parent->child), deprel+42 (child->parent), 84
+ *      flags  uint8 [B,T]    GPT_FLAG_* ; denom float [B,T] = row nnz + 1 ; lens int32 [B] ; err int32 [B] */
+int gpt_prune_csr(const int64_t* head, const int64_t* subj_pos, const int64_t* obj_pos, const int64_t* deprel,
+                  const uint8_t* pad_mask, int B, int T, int prune_k, int32_t* rowptr, int32_t* col, uint8_t* val,
+                  uint8_t* flags, float* denom, int32_t* lens, int32_t* err, void* stream);
+
+/* K2 forward. One GCN layer after the projection y = h W^T (model/gcn.py:269-271, 390-393):
+ *     out_i = dropout(relu((sum_{j in row i} y_j + y_i + 2*bias) / denom_i)); rows with flags == 0 are written 0.
+ * use_adj = 0 is the --no_adj ablation (model/gcn.py:264-265).
+ * Dropout: drop_p > 0 draws Philox bits in-kernel from rng_state = {seed, step} (device uint64[2]) and `subseq`
+ * (layer id); or drop_mask (pre-scaled float [B*T,H], tests) multiplies the result; or neither.
+ * force_vec: 0 = auto, else 1/2/4 floats per lane (slice width 32*vec). */
+int gpt_gcn_aggregate_fwd(const float* y, const int32_t* rowptr, const int32_t* col, const float* denom,
+                          const uint8_t* flags, const float* bias, float* out, int B, int T, int H, int use_adj,
+                          float drop_p, const uint64_t* rng_state, uint32_t subseq, const float* drop_mask,
+                          int force_vec, void* stream);
+
+/* K2 backward (autograd of the lines above; the adjacency is symmetric so the same CSR is its transpose):
+ *     g_i = gout_i * dropscale * [out_i > 0] / denom_i ; dy_j = g_j + sum_{i in row j} g_i ; dbias += 2*sum_i g_i
+ * dbias (float [H]) is accumulated atomically and must be zeroed by the caller; may be NULL. */
+int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const int32_t* rowptr, const int32_t* col,
+                          const float* denom, float* dy, float* dbias, int B, int T, int H, int use_adj,
+                          float drop_p, const float* drop_mask, int force_vec, void* stream);
+
+/* K4. three masked pools + cat (model/gcn.py:116-121, 473-483): out float [B,3H] = [h_out, subj_out, obj_out];
+ * argmax int32 [B,3H] (token index or -1) is required for GPT_POOL_MAX. */
+int gpt_pool3_fwd(const float* h, const uint8_t* flags, int B, int T, int H, int pool_type, float* out,
+                  int32_t* argmax, void* stream);
+int gpt_pool3_bwd(const float* gout, const int32_t* argmax, const uint8_t* flags, int B, int T, int H,
+                  int pool_type, float* dh, void* stream);
+
+/* K3. the W projection without bias (model/gcn.py:270-271: W(Ax) + W(h) == (A+I) (h W^T) + 2b) and its autograd.
+ *     x [M,K], w [N,K] (nn.Linear layout), y/dy [M,N], dx [M,K], dw [N,K]; all row-major fp32. */
+int gpt_linear_fwd_f32(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
+int gpt_linear_dgrad_f32(const float* dy, const float* w, float* dx, int M, int N, int K, void* stream);
+int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPT_B200_H */

@@ -17,6 +17,9 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # fp32 parity: keep cuBLAS / cuDNN (the C-GCN LSTM) out of TF32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
         return
     skip = pytest.mark.skip(reason='no CUDA device')
     for item in items:

@@ -1,0 +1,366 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): every CUDA entry point, through the C ABI, against the
+oracle and against the committed reference outputs (tests/golden/*.npz).
+
+Tolerances (stated here once):
+  * adjacency: bit-exact (integer work)
+  * fp32 path: logits / loss <= 1e-5 relative (max|d| / max|ref|), gradients <= 1e-4 relative per tensor
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import weights
+from gcn_over_pruned_trees_b200 import ops, synth, _lib
+from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+from oracle import gcn_oracle, tree_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _csr_of(batch, k, dataset='tacred'):
+    off = 4 if dataset == 'tacred' else 3
+    deprel, head, subj_pos, obj_pos = [t.to(DEV) for t in batch[off:off + 4]]
+    return ops.prune_csr(head, subj_pos, obj_pos, deprel, batch[1].to(DEV), k)
+
+
+def _oracle_adj(batch, k):
+    lens = synth.batch_lengths(batch).numpy()
+    return tree_oracle.batch_adjacency(batch[5].numpy(), batch[6].numpy(), batch[7].numpy(), batch[4].numpy(), lens,
+                                       k, batch[0].shape[1])
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---------------------------------------------------------------- K1 ------------------------------------------
+
+@pytest.mark.parametrize('split', cases.SPLITS)
+def test_k1_bundled_sample_matches_reference(golden_adj, split):
+    batch = cases.batch_from_npz(golden_adj, split)
+    for k in cases.PRUNE_KS:
+        csr = _csr_of(batch, k)
+        assert int(csr.err.abs().sum()) == 0
+        got = csr.to_dense().numpy()
+        want = golden_adj['%s/adj_k%d' % (split, k)].astype(np.float32)
+        assert np.array_equal(got, want), (split, k)
+        # denom = rowsum(adj != 0) + 1 ; in-tree flag = (rowsum + colsum) != 0  (gcn.py:261-262)
+        nz = want != 0
+        assert np.array_equal(csr.denom.cpu().numpy(), nz.sum(2) + 1.0)
+        assert np.array_equal((csr.flags.cpu().numpy() & 1) != 0, (nz.sum(2) + nz.sum(1)) != 0)
+        assert np.array_equal(csr.lens.cpu().numpy(), synth.batch_lengths(batch).numpy())
+
+
+@pytest.mark.parametrize('seed', cases.SYNTH_ADJ_SEEDS + (1, 2, 3))
+def test_k1_synthetic_matches_oracle(seed):
+    batch = synth.make_batch(seed, batch_size=50)
+    for k in cases.PRUNE_KS + (7,):
+        csr = _csr_of(batch, k)
+        got = csr.to_dense().numpy()
+        assert np.array_equal(got, _oracle_adj(batch, k)), (seed, k)
+        # columns ascending inside every row (canonical CSR)
+        rp, col = csr.rowptr.cpu().numpy(), csr.col.cpu().numpy()
+        for b in range(0, 50, 7):
+            for t in range(batch[0].shape[1]):
+                seg = col[b, rp[b, t]:rp[b, t + 1]]
+                assert np.all(np.diff(seg) > 0)
+
+
+def test_k1_subj_obj_flags():
+    batch = synth.make_batch(4, batch_size=20)
+    csr = _csr_of(batch, 1)
+    f = csr.flags.cpu().numpy()
+    assert np.array_equal((f & 2) != 0, batch[6].numpy() == 0)
+    assert np.array_equal((f & 4) != 0, batch[7].numpy() == 0)
+
+
+@pytest.mark.parametrize('name', sorted(cases.EDGE_TREES))
+def test_k1_edge_trees(golden_adj, name):
+    head, subj, obj, deprel = cases.EDGE_TREES[name]
+    n, width = len(head), len(head) + 3           # padded on purpose
+    pad = lambda a, fill=0: torch.tensor([list(a) + [fill] * (width - n)], dtype=torch.int64, device=DEV)
+    masks = torch.tensor([[False] * n + [True] * (width - n)], device=DEV)
+    sp = torch.from_numpy(cases.positions(subj, n, width=width))[None].to(DEV)
+    op = torch.from_numpy(cases.positions(obj, n, width=width))[None].to(DEV)
+    for k in cases.PRUNE_KS:
+        csr = ops.prune_csr(pad(head), sp, op, pad(deprel), masks, k)
+        assert (int(csr.err[0]) & ops.TREE_ERR_FATAL) == 0, (name, k, int(csr.err[0]))
+        got = csr.to_dense().numpy()[0, :n, :n]
+        assert np.array_equal(got, golden_adj['edge/%s/k%d' % (name, k)].astype(np.float32)), (name, k)
+        assert csr.to_dense().numpy()[0, n:, :].sum() == 0
+
+
+def test_k1_512_token_sentences(golden_adj):
+    import hashlib
+    batch = synth.make_batch(900, batch_size=6, fixed_len=512)
+    for k in (-1, 1):
+        got = _csr_of(batch, k).to_dense().numpy()
+        sha = hashlib.sha256(got.astype(np.uint8).tobytes()).hexdigest()[:16]
+        assert sha == bytes(golden_adj['synth512/k%d/sha' % k]).decode()
+
+
+def test_k1_malformed_trees_are_flagged_not_hung():
+    def run(head, subj, obj, k, deprel=None):
+        n = len(head)
+        t = lambda a: torch.tensor([a], dtype=torch.int64, device=DEV)
+        deprel = deprel or [5] * n
+        csr = ops.prune_csr(t(head), torch.from_numpy(cases.positions(subj, n))[None].to(DEV),
+                            torch.from_numpy(cases.positions(obj, n))[None].to(DEV), t(deprel),
+                            torch.zeros((1, n), dtype=torch.bool, device=DEV), k)
+        return int(csr.err[0]), csr
+    e, csr = run([2, 3, 1], [0], [2], 1)
+    assert e & 4 and csr.to_dense().sum() == 0                       # cycle (reference: infinite loop)
+    assert run([2, 3, 1], [0], [2], -1)[0] & (2 | 4)                 # no root
+    assert run([0, 0], [0], [1], 0)[0] & 16                          # entities under different roots
+    assert run([0, 1], [], [1], 0)[0] & 8                            # empty subject span
+    assert run([0, 5], [0], [1], 0)[0] & 1                           # head out of range
+    assert run([0, 1], [0], [1], 0, deprel=[11, 250])[0] & 32        # deprel does not fit uint8 + 42
+    assert run([0, 1, 1, 2], [3], [2], 1, deprel=[11, 0, 5, 0])[0] == 64   # warning only
+    with pytest.raises(_lib.GptError):
+        csr.err.fill_(4)
+        csr.check()
+
+
+def test_no_cpu_fallback():
+    batch = synth.make_batch(0, batch_size=4)
+    with pytest.raises(_lib.GptError):
+        ops.prune_csr(batch[5], batch[6], batch[7], batch[4], batch[1], 1)
+
+
+# ---------------------------------------------------------------- K3 ------------------------------------------
+
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (50, 200, 360), (2750, 200, 360), (1000, 200, 200), (777, 64, 85),
+                                    (4096, 512, 360), (130, 37, 19)])
+def test_k3_fp32_gemms(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g)
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    x64, w64, dy64 = x.double(), w.double(), dy.double()
+    assert _rel(ops.linear_fwd(x, w).cpu(), (x64 @ w64.t()).cpu()) < 2e-6
+    assert _rel(ops.linear_dgrad(dy, w).cpu(), (dy64 @ w64).cpu()) < 2e-6
+    assert _rel(ops.linear_wgrad(dy, x).cpu(), (dy64.t() @ x64).cpu()) < 2e-6
+
+
+# ---------------------------------------------------------------- K2 ------------------------------------------
+
+def _dense_layer(x, w, b, adj, mask=None):
+    a = (adj != 0).double()
+    denom = a.sum(2, keepdim=True) + 1
+    z = ((a.bmm(x) @ w.t() + b) + (x @ w.t() + b)) / denom
+    out = torch.relu(z)
+    return out if mask is None else out * mask
+
+
+@pytest.mark.parametrize('k', (-1, 0, 1, 2))
+@pytest.mark.parametrize('H,K,vec', [(200, 360, 0), (200, 200, 1), (64, 40, 2), (200, 64, 4), (30, 17, 0)])
+def test_k2_layer_forward_backward_vs_dense(k, H, K, vec):
+    batch = synth.make_batch(20 + k, batch_size=24)
+    csr = _csr_of(batch, k)
+    B, T = batch[0].shape
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(B, T, K, device=DEV, generator=g, requires_grad=True)
+    w = (torch.randn(H, K, device=DEV, generator=g) / K ** 0.5).requires_grad_()
+    b = torch.randn(H, device=DEV, generator=g).requires_grad_()
+    mask = (torch.rand(B, T, H, device=DEV, generator=g) < 0.5).float() * 2.0
+    gout = torch.randn(B, T, H, device=DEV, generator=g)
+    observable = (csr.flags != 0).unsqueeze(2).double()          # rows that can reach the logits
+
+    out = ops.gcn_layer(x, w, b, csr, drop_mask=mask)
+    if vec:
+        y = ops.linear_fwd(x.detach().view(B * T, K), w.detach())
+        out_v = ops.aggregate_fwd(y, csr, b.detach(), drop_mask=mask, force_vec=vec)
+        assert torch.equal(out_v, out.detach())
+    (out * gout * observable.float()).sum().backward()
+
+    adj = csr.to_dense().to(DEV)
+    xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
+    ref = _dense_layer(xd, wd, bd, adj, mask.double())
+    (ref * gout.double() * observable).sum().backward()
+    assert _rel((out.detach().double() * observable).cpu(), (ref.detach() * observable).cpu()) < 1e-5
+    assert torch.all(out.detach()[csr.flags == 0] == 0)
+    assert _rel(x.grad.cpu(), xd.grad.cpu()) < 1e-5
+    assert _rel(w.grad.cpu(), wd.grad.cpu()) < 1e-5
+    assert _rel(b.grad.cpu(), bd.grad.cpu()) < 1e-5
+
+
+def test_k2_no_adj_ablation():
+    batch = synth.make_batch(31, batch_size=8)
+    csr = _csr_of(batch, 1)
+    B, T = batch[0].shape
+    x = torch.randn(B, T, 32, device=DEV)
+    w = torch.randn(48, 32, device=DEV)
+    b = torch.randn(48, device=DEV)
+    out = ops.gcn_layer(x, w, b, csr, use_adj=False)
+    ref = torch.relu((x @ w.t() + 2 * b) / csr.denom.unsqueeze(2)) * (csr.flags != 0).unsqueeze(2)
+    assert _rel(out.cpu(), ref.cpu()) < 1e-5
+
+
+def test_k2_philox_dropout_statistics_and_backward_consistency():
+    batch = synth.make_batch(33, batch_size=50)
+    csr = _csr_of(batch, -1)
+    B, T = batch[0].shape
+    H = 200
+    y = torch.rand(B * T, H, device=DEV) + 0.5                     # strictly positive pre-activations
+    bias = torch.zeros(H, device=DEV)
+    rng = torch.tensor([1234, 1], dtype=torch.int64, device=DEV)
+    base = ops.aggregate_fwd(y, csr, bias)
+    for p in (0.5, 0.1):
+        o1 = ops.aggregate_fwd(y, csr, bias, drop_p=p, rng_state=rng, subseq=0)
+        o1b = ops.aggregate_fwd(y, csr, bias, drop_p=p, rng_state=rng, subseq=0, force_vec=4)
+        assert torch.equal(o1, o1b)                                # pattern independent of the slicing
+        live = base > 0
+        keep = (o1 > 0)[live].float().mean().item()
+        assert abs(keep - (1 - p)) < 0.01
+        assert _rel(o1[o1 > 0].cpu(), (base[o1 > 0] / (1 - p)).cpu()) < 1e-5
+        o2 = ops.aggregate_fwd(y, csr, bias, drop_p=p, rng_state=rng, subseq=1)
+        rng2 = torch.tensor([1234, 2], dtype=torch.int64, device=DEV)
+        o3 = ops.aggregate_fwd(y, csr, bias, drop_p=p, rng_state=rng2, subseq=0)
+        assert not torch.equal(o1 > 0, o2 > 0) and not torch.equal(o1 > 0, o3 > 0)
+        # backward with the in-kernel mask == backward with the same mask given explicitly
+        gout = torch.randn(B, T, H, device=DEV)
+        dy1, db1 = ops.aggregate_bwd(gout, o1, csr, drop_p=p)
+        explicit = (o1 > 0).float() / (1 - p)
+        dy2, db2 = ops.aggregate_bwd(gout, o1, csr, drop_mask=explicit)
+        assert _rel(dy1.cpu(), dy2.cpu()) < 1e-6 and _rel(db1.cpu(), db2.cpu()) < 1e-5
+
+
+# ---------------------------------------------------------------- K4 ------------------------------------------
+
+@pytest.mark.parametrize('kind', ('max', 'avg', 'sum'))
+@pytest.mark.parametrize('H', (200, 37))
+def test_k4_pool3_vs_reference_pool(kind, H):
+    batch = synth.make_batch(41, batch_size=16)
+    csr = _csr_of(batch, 1)
+    B, T = batch[0].shape
+    h = (torch.rand(B, T, H, device=DEV) + 0.01).requires_grad_()      # no ties: argmax is unique
+    gout = torch.randn(B, 3 * H, device=DEV)
+    got = ops.pool3(h, csr, kind)
+    (got * gout).sum().backward()
+    hd = h.detach().clone().requires_grad_()
+    m = [csr.pool_mask(), batch[6].to(DEV).ne(0).unsqueeze(2), batch[7].to(DEV).ne(0).unsqueeze(2)]
+    ref = torch.cat([gcn_oracle.masked_pool(hd, mi, kind) for mi in m], dim=1)
+    (ref * gout).sum().backward()
+    assert _rel(got.detach().cpu(), ref.detach().cpu()) < 1e-6
+    assert _rel(h.grad.cpu(), hd.grad.cpu()) < 1e-6
+
+
+def test_k4_fully_masked_pool_is_minus_1e12():
+    # same-token subject/object -> singleton tree -> empty adjacency -> h_out = -1e12
+    head = torch.tensor([[2, 0, 2, 3]], device=DEV)
+    pos = torch.from_numpy(cases.positions([3], 4))[None].to(DEV)
+    csr = ops.prune_csr(head, pos, pos, torch.tensor([[5, 11, 6, 7]], device=DEV),
+                        torch.zeros((1, 4), dtype=torch.bool, device=DEV), 1)
+    h = torch.rand(1, 4, 8, device=DEV)
+    out = ops.pool3(h, csr, 'max')
+    assert torch.all(out[:, :8] == -1e12)
+    assert torch.equal(out[:, 8:16], h[:, 3]) and torch.equal(out[:, 16:], h[:, 3])
+
+
+# ---------------------------------------------------------------- whole model ---------------------------------
+
+def _setup(golden_adj, name):
+    over, source, wseed = cases.MODEL_CASES[name]
+    if source[0] == 'split':
+        batch = cases.batch_from_npz(golden_adj, source[1])
+        over = dict(over, vocab_size=int(golden_adj['vocab_size']))
+    else:
+        batch = synth.make_batch(source[1], batch_size=source[2], vocab_size=over['vocab_size'],
+                                 num_class=over.get('num_class', 42), dataset=over.get('dataset', 'tacred'))
+    opt = synth.tacred_opt(**over)
+    state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, wseed).items()}
+    trainer = GCNTrainer(dict(opt, cuda=True))
+    trainer.model.load_state_dict(state)
+    oracle = gcn_oracle.DenseClassifier(opt)
+    oracle.load_state_dict(state)
+    return opt, batch, trainer, oracle
+
+
+@pytest.mark.parametrize('name', sorted(cases.MODEL_CASES))
+def test_model_eval_matches_reference_outputs(golden_adj, golden_model, name):
+    opt, batch, trainer, _ = _setup(golden_adj, name)
+    trainer.model.eval()
+    with torch.no_grad():
+        inputs = [t.to(DEV) for t in batch[:-2]]
+        logits, h_out = trainer.model(inputs)
+        loss = trainer.update(batch)
+    assert _rel(logits.cpu(), golden_model['%s/logits' % name]) <= 1e-5
+    assert _rel(h_out.cpu(), golden_model['%s/h_out' % name]) <= 1e-5
+    assert abs(loss.item() - float(golden_model['%s/eval_loss' % name])) <= 1e-5 * abs(loss.item())
+    preds, probs, ploss = trainer.predict(batch)
+    assert preds == golden_model['%s/pred' % name].tolist()
+    assert _rel(np.asarray(probs), golden_model['%s/probs' % name]) <= 1e-5
+    assert abs(ploss - float(golden_model['%s/predict_loss' % name])) <= 1e-5 * abs(ploss)
+
+
+@pytest.mark.parametrize('name', cases.GRAD_CASES)
+def test_model_train_grads_match_oracle_with_injected_masks(golden_adj, name):
+    opt, batch, trainer, oracle = _setup(golden_adj, name)
+    B, T = batch[0].shape
+    g = torch.Generator().manual_seed(99)
+    in_dim = opt['emb_dim'] + opt['pos_dim'] + (opt['ner_dim'] if opt['dataset'] == 'tacred' else 0)
+
+    def drop(shape, p):
+        return (torch.rand(shape, generator=g) >= p).float() / (1 - p)
+    masks = {'in': drop((B, T, in_dim), opt['input_dropout'])}
+    if opt['rnn']:
+        masks['rnn'] = drop((B, T, 2 * opt['rnn_hidden']), opt['rnn_dropout'])
+    for l in range(opt['num_layers'] - 1):
+        masks['gcn%d' % l] = drop((B, T, opt['hidden_dim']), opt['gcn_dropout'])
+
+    oracle.train()
+    ref_loss, _ = oracle.loss(batch, masks)
+    ref_loss.backward()
+
+    trainer.model.train()
+    trainer.model.gcn_model.gcn.injected_masks = {k: v.to(DEV) for k, v in masks.items()}
+    loss = trainer.update(batch)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    ref_grads = {k: p.grad for k, p in oracle.named_parameters()}
+    checked = 0
+    for key, p in trainer.model.named_parameters():
+        rg = ref_grads[key]
+        if rg is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, key
+            continue
+        assert _rel(p.grad.cpu(), rg) <= 1e-4, key
+        checked += 1
+    assert checked >= 8
+
+
+def test_train_loop_step_runs_and_lowers_loss():
+    opt = synth.tacred_opt(vocab_size=500, cuda=True)
+    torch.manual_seed(0)
+    trainer = GCNTrainer(opt)
+    batch = synth.make_batch(7, batch_size=50, vocab_size=500)
+    trainer.model.train()
+    losses = []
+    for _ in range(12):                                   # train.py:213-227
+        trainer.optimizer.zero_grad()
+        loss = trainer.update(batch)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(trainer.model.parameters(), opt['max_grad_norm'])
+        trainer.optimizer.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+
+
+def test_checkpoint_round_trip(tmp_path):
+    opt = synth.tacred_opt(vocab_size=300, cuda=True)
+    a = GCNTrainer(opt)
+    f = str(tmp_path / 'ckpt.pt')
+    a.save(f, 1)
+    from gcn_over_pruned_trees_b200 import torch_utils
+    cfg = torch_utils.load_config(f)
+    b = GCNTrainer(cfg)
+    b.load(f)
+    batch = synth.make_batch(3, batch_size=10, vocab_size=300)
+    pa, _, la = a.predict(batch)
+    pb, _, lb = b.predict(batch)
+    assert pa == pb and la == lb
+    sd = b.model.state_dict()
+    assert sd['gcn_model.emb.weight'].data_ptr() == sd['gcn_model.gcn.emb.weight'].data_ptr()
