@@ -248,11 +248,10 @@ prune_csr_kernel(const long long* __restrict__ head, const long long* __restrict
         const int c_end = cptr[r + 1];
         for (int i = cptr[r]; i <= c_end; ++i) {
             const int c = (i < c_end) ? clist[i] : 0x7fffffff;
+            // pending {parent, self} entries smaller than the next child column, in ascending order
             if (!par_done && p < r && p < c) { cb[w] = p; vb[w] = pv; ++w; par_done = true; }
-            if (!self_done && r < c) {
-                cb[w] = r; vb[w] = 84; ++w; self_done = true;  // tree.py:190-192
-                if (!par_done && p < c) { cb[w] = p; vb[w] = pv; ++w; par_done = true; }
-            }
+            if (!self_done && r < c) { cb[w] = r; vb[w] = 84; ++w; self_done = true; }  // tree.py:190-192
+            if (!par_done && self_done && p < c) { cb[w] = p; vb[w] = pv; ++w; par_done = true; }
             if (i < c_end) { cb[w] = c; vb[w] = (unsigned char)(meta[c] & M_DEPREL); ++w; }  // tree.py:184
         }
     }

@@ -1,0 +1,97 @@
+"""Sentence-sharded data parallelism: one process per GPU, parameters replicated, one gradient all-reduce per step.
+
+The reference is single-device: every sentence's tree, CSR, aggregation and pooling live on one GPU,
+so the only exchange in a data-parallel step is the gradient all-reduce (NCCL over NVLink 5 / NVSwitch on the GPU
+box, gloo in the CPU tests).  Loss terms are batch means (trainer.py:94-100), so gradients are *averaged*.
+
+Small dense gradients travel in one flat bucket (a single collective: latency-bound), the word-embedding gradient
+-- the one large message, [V, emb_dim] -- is reduced in place without a staging copy.  Parameters whose gradient is
+None on every rank (deprel_emb in 'regular' mode; ner_emb on SemEval) are skipped consistently because the set is
+decided by the architecture, not by the data.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+LARGE_NUMEL = 1 << 20
+
+
+def init_from_env(backend=None):
+    """Join the process group torchrun describes (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*); no-op for 1 process."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def shard_batch(batch, rank, world):
+    """Rows rank::world of a loader batch (the unit of work is a sentence; no tree spans two ranks)."""
+    idx = torch.arange(rank, batch[0].shape[0], world)
+    fields = [t[idx] for t in batch[:-1]]
+    return tuple(fields) + ([batch[-1][i] for i in idx.tolist()],)
+
+
+class GradAllReducer(object):
+    """Average ``.grad`` of ``params`` over the process group after ``loss.backward()``, before clipping."""
+
+    def __init__(self, params, group=None):
+        seen, self.params = set(), []
+        for p in params:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                self.params.append(p)
+        self.group = group
+        self._flat = None
+
+    @property
+    def world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def reduce(self):
+        world = self.world
+        if world == 1:
+            return
+        small = [p for p in self.params if p.grad is not None and p.grad.numel() < LARGE_NUMEL]
+        large = [p for p in self.params if p.grad is not None and p.grad.numel() >= LARGE_NUMEL]
+        handles = []
+        for p in large:                      # in place, asynchronously, while the bucket is being packed
+            handles.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if small:
+            n = sum(p.grad.numel() for p in small)
+            if self._flat is None or self._flat.numel() != n or self._flat.device != small[0].grad.device:
+                self._flat = torch.empty(n, dtype=small[0].grad.dtype, device=small[0].grad.device)
+            views = []
+            off = 0
+            for p in small:
+                k = p.grad.numel()
+                views.append(self._flat[off:off + k].view_as(p.grad))
+                off += k
+            torch._foreach_copy_(views, [p.grad for p in small])
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._flat.div_(world)
+            torch._foreach_copy_([p.grad for p in small], views)
+        for h, p in zip(handles, large):
+            h.wait()
+            p.grad.div_(world)
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over all ranks (step time is the slowest rank's)."""
+    if not dist.is_initialized():
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
