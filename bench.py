@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- GCN training throughput on synthetic TACRED-shaped data (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload = "tacred_b50_k1", BASELINE.json configs[1] at prune_k=1): batches of 50 synthetic
+sentences per GPU (lengths clip(Poisson(36), 8, 96), uniform random recursive trees), 2-layer GCN, 360-d input,
+200-d hidden, V=50000 random-init 300-d embeddings, dropout on.  One step = what /root/reference/train.py:213-227 does
+per batch: zero_grad, GCNTrainer.update (forward + loss), backward, [gradient all-reduce when N > 1], global-norm
+clip at 5.0, SGD step.
+
+  value   sentences/s with the batches already resident in HBM (device-timed with CUDA events, max over ranks,
+          L2 flushed between steps)
+  e2e     same step driven through the reference-facing API from pinned HOST batches: H2D copy of the 9 batch
+          tensors + loss.item() D2H inside the timed region (wall clock around each step, L2 flushed between)
+  roofline      K2 aggregation forward at the large synthetic shape (BASELINE.json configs[4]: 512-token trees,
+                B=4096, H=512 -- the only shape where an HBM fraction means anything), timed live
+  cpu_baseline  the oracle's dense CPU restatement of the reference path, timed on this box's host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = 'gcn_train_sentences_per_sec'
+UNIT = 'sentences/s'
+BATCH = 50
+VOCAB = 50000
+N_BATCHES = 16          # distinct synthetic batches per rank, cycled
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--prune_k', type=int, default=1)
+    ap.add_argument('--gemm', default='fp32')
+    ap.add_argument('--no-roofline', action='store_true', help='skip the large-shape aggregation roofline run')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--roofline-batch', type=int, default=4096)
+    ap.add_argument('--cpu-steps', type=int, default=60)
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {'workload': 'tacred_b50_k%d' % args.prune_k, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world,
+            'len': 'clip(Poisson(36),8,96)', 'layers': 2, 'in_dim': 360, 'hidden': 200, 'vocab': VOCAB,
+            'prune_k': args.prune_k, 'gemm': args.gemm, 'parallelism': 'dp%d' % world,
+            'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd', 'l2': 'flushed between timed steps (256 MiB fill)'}
+
+
+# ------------------------------------------------------------------------------------------------ clocks -------
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference ----
+
+def cpu_reference_run(args, steps, warmup):
+    """The oracle's dense CPU restatement of the reference training step, all host threads."""
+    import torch
+    from gcn_over_pruned_trees_b200 import synth
+    from oracle import gcn_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    opt = synth.tacred_opt(vocab_size=VOCAB, prune_k=args.prune_k, cuda=False)
+    model = gcn_oracle.DenseClassifier(opt)
+    model.train()
+    optim = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=opt['lr'])
+    batches = [synth.make_batch(1000 + i, batch_size=BATCH, vocab_size=VOCAB) for i in range(min(N_BATCHES, 8))]
+    for i in range(warmup):
+        gcn_oracle.train_step(model, optim, batches[i % len(batches)], opt['max_grad_norm'])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        gcn_oracle.train_step(model, optim, batches[i % len(batches)], opt['max_grad_norm'])
+    dt = time.perf_counter() - t0
+    # the host-side tree + dense adjacency section alone (gcn.py:105-107), single Python thread
+    t1 = time.perf_counter()
+    n_adj = max(1, min(steps, 10))
+    for i in range(n_adj):
+        model.gcn_model.adjacency(list(batches[i % len(batches)][:-2]))
+    adj_ms = (time.perf_counter() - t1) / n_adj * 1e3
+    return {'value': BATCH * steps / dt, 'ms_per_step': dt / steps * 1e3, 'cores': cores, 'tree_adj_ms': adj_ms,
+            'sample': '%d steps x %d sentences after %d warm-up, V=%d, train mode' % (steps, BATCH, warmup, VOCAB)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, args.steps, max(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload_config(args, 1), parallelism='cpu'),
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                             'sample': r['sample'], 'tree_adj_ms_per_batch': r['tree_adj_ms']},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ b200 ---------
+
+def aggregation_roofline(args, peaks):
+    """K2 forward at the large synthetic shape, timed alone with CUDA events on the launching stream."""
+    import torch
+    from gcn_over_pruned_trees_b200 import ops, synth
+    B, T, H = args.roofline_batch, 512, 512
+    batch = synth.make_batch_torch(7, B, T, device='cuda')
+    csr = ops.prune_csr(batch[5], batch[6], batch[7], batch[4], batch[1], -1)
+    y = torch.randn(B * T, H, device='cuda')
+    bias = torch.zeros(H, device='cuda')
+    rng = torch.tensor([1, 1], dtype=torch.int64, device='cuda')
+    n_rows = int((csr.flags != 0).sum())
+    nnz = int(csr.rowptr[:, T].sum())
+    results = {}
+    for name, drop_p in (('fwd', 0.0), ('fwd_dropout', 0.5)):
+        for _ in range(3):
+            out = ops.aggregate_fwd(y, csr, bias, drop_p=drop_p, rng_state=rng)
+        reps = 10
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        torch.cuda.synchronize()
+        for a, b in ev:                      # y + out = 8.6 GB >> 126 MB of L2: every launch streams from HBM
+            a.record()
+            out = ops.aggregate_fwd(y, csr, bias, drop_p=drop_p, rng_state=rng)
+            b.record()
+        torch.cuda.synchronize()
+        results[name] = sum(a.elapsed_time(b) for a, b in ev) / reps
+    gout = torch.randn(B, T, H, device='cuda')
+    for _ in range(2):
+        ops.aggregate_bwd(gout, out, csr, drop_p=0.5)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record()
+        ops.aggregate_bwd(gout, out, csr, drop_p=0.5)
+        b.record()
+    torch.cuda.synchronize()
+    results['bwd'] = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    # algorithmic bytes: read each projected row once + write each output row once + CSR + denom
+    bytes_fwd = 2 * B * T * H * 4 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T + B * T
+    bytes_bwd = 3 * B * T * H * 4 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T
+    peak = peaks['hbm_gbs']
+    ach = bytes_fwd / (results['fwd_dropout'] * 1e-3) / 1e9
+    del y, out, gout
+    torch.cuda.empty_cache()
+    return {'bound': 'hbm', 'kernel': 'aggregate_fwd_kernel (K2, dropout on)', 'achieved': ach, 'peak': peak,
+            'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peaks['source'], 'traffic': None,
+            'workload': 'large512: B=%d x T=512 trees, H=512, prune_k=-1, rows=%d, nnz=%d' % (B, n_rows, nnz),
+            'bytes_per_launch': bytes_fwd, 'ms_per_launch': results['fwd_dropout'],
+            'frac_of_nominal_8000': ach / 8000.0,
+            'other': {'fwd_no_dropout_ms': results['fwd'],
+                      'fwd_no_dropout_gbs': bytes_fwd / (results['fwd'] * 1e-3) / 1e9,
+                      'bwd_ms': results['bwd'], 'bwd_gbs': bytes_bwd / (results['bwd'] * 1e-3) / 1e9,
+                      'bwd_bytes_per_launch': bytes_bwd}}
+
+
+def load_peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': float(p['hbm_gbs']), 'bf16_tflops': float(p['bf16_tflops']),
+                'bf16_tflops_sustained': float(p.get('bf16_tflops_sustained', p['bf16_tflops'])),
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0,
+            'source': 'fallback (B200_PROFILING.md)'}
+
+
+def run_b200(args):
+    import torch
+    from gcn_over_pruned_trees_b200 import _lib, ops, parallel, synth
+    from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+
+    rank, local_rank, world = parallel.init_from_env('nccl')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    torch.backends.cuda.matmul.allow_tf32 = False      # fp32 parity mode for the cuBLAS tail (MLP / classifier)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1234)                            # identical replicas on every rank
+    opt = synth.tacred_opt(vocab_size=VOCAB, prune_k=args.prune_k, cuda=True, gemm_mode=args.gemm)
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, 'w')
+    trainer = GCNTrainer(opt)
+    sys.stdout = _stdout
+    model = trainer.model
+    model.train()
+    reducer = parallel.GradAllReducer(model.parameters())
+    host = [synth.make_batch(1000 + rank * N_BATCHES + i, batch_size=BATCH, vocab_size=VOCAB) for i in range(N_BATCHES)]
+    host = [tuple(t.pin_memory() if torch.is_tensor(t) else t for t in b) for b in host]
+    resident = [tuple(t.to(dev) if torch.is_tensor(t) else t for t in b) for b in host]
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    params = list(model.parameters())
+
+    def step(batch):
+        trainer.optimizer.zero_grad(set_to_none=False)
+        loss = trainer.update(batch)
+        loss.backward()
+        reducer.reduce()
+        torch.nn.utils.clip_grad_norm_(params, opt['max_grad_norm'])
+        trainer.optimizer.step()
+        return loss
+
+    # first step allocates .grad tensors; zero_grad(set_to_none=False) keeps them afterwards
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % N_BATCHES])
+    torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps -------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _lib.lib().gpt_launch_count()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i, (a, b) in enumerate(events):
+        flush.fill_(0.0)
+        a.record()
+        step(resident[i % N_BATCHES])
+        b.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.lib().gpt_launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in events)
+    dev_ms = parallel.max_over_ranks(dev_ms, dev)
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = dev_ms / args.steps
+    value = BATCH * world * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: pinned host batches through GCNTrainer.update, loss.item() every step ---------------------------
+    h2d = sum(t.numel() * t.element_size() for t in host[0] if torch.is_tensor(t))
+    for i in range(3):
+        step(host[i % N_BATCHES]).item()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    e2e_s = 0.0
+    for i in range(args.steps):
+        flush.fill_(0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(host[i % N_BATCHES]).item()
+        e2e_s += time.perf_counter() - t0
+    parallel.barrier()
+    e2e_s = parallel.max_over_ranks(e2e_s, dev)
+    e2e = {'value': BATCH * world * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+           'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / args.steps * 1e3,
+           'api': 'GCNTrainer.update(pinned host batch) + backward + clip + SGD + loss.item()'}
+
+    if rank != 0:
+        return
+
+    # ---- per-entry-point device time inside the step (separate instrumented pass, not the headline) ------------
+    ops.TIMER = ops.KernelTimer()
+    n_prof = min(args.steps, 20)
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    pa.record()
+    for i in range(n_prof):
+        step(resident[i % N_BATCHES])
+    pb.record()
+    summary = ops.TIMER.summary()
+    ops.TIMER = None
+    prof_ms = pa.elapsed_time(pb)
+    kernels = {k: {'calls_per_step': c / n_prof, 'us_per_call': ms / c * 1e3, 'share_of_step': ms / prof_ms}
+               for k, (c, ms) in sorted(summary.items(), key=lambda kv: -kv[1][1])}
+
+    peaks = load_peaks()
+    roof = None
+    if not args.no_roofline and world == 1:
+        try:
+            roof = aggregation_roofline(args, peaks)
+        except Exception as exc:                # keep the headline line even if the 8.6 GB run cannot be placed
+            roof = {'error': repr(exc)}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(args, args.cpu_steps, 3)
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
+               'ms_per_step': r['ms_per_step'], 'tree_adj_ms_per_batch': r['tree_adj_ms']}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'gpu_launches_per_step': launches / args.steps, 'wall_ms_per_step_incl_flush': wall / args.steps * 1e3,
+            'roofline': roof, 'cpu_baseline': cpu, 'kernels': kernels}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -17,6 +17,7 @@ _p = ctypes.c_void_p
 # name -> argtypes; every function returns int except gpt_error_string
 SIGNATURES = {
     'gpt_version': [],
+    'gpt_launch_count': [],
     'gpt_prune_csr': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
                               _c_int, _p],
@@ -47,6 +48,7 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = _c_int
+        handle.gpt_launch_count.restype = ctypes.c_ulonglong
         handle.gpt_error_string.argtypes = [_c_int]
         handle.gpt_error_string.restype = ctypes.c_char_p
         _lib = handle

@@ -1,7 +1,11 @@
 // Library-level entry points of libgptb200.so (include/gpt_b200.h).
 #include "gpt_common.cuh"
 
+unsigned long long g_gpt_launches = 0;
+
 extern "C" int gpt_version(void) { return 100; }
+
+extern "C" unsigned long long gpt_launch_count(void) { return g_gpt_launches; }
 
 extern "C" const char* gpt_error_string(int code) {
     switch (code) {

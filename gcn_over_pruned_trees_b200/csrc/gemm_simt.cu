@@ -176,7 +176,8 @@ extern "C" int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, 
     if (splits > 1 || M == 0) {
         const size_t n = (size_t)N * K;
         zero_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dw, N, K, K);
+        const int rc = gpt_launch_status();
+        if (rc != GPT_OK || M == 0) return rc;
     }
-    if (M == 0) return gpt_launch_status();
     return run_sgemm<false, false>(N, K, M, dy, N, x, K, dw, K, splits, st);
 }

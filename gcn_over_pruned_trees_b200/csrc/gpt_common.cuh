@@ -17,7 +17,12 @@
         if (!(cond)) return GPT_ERR_BAD_ARG; \
     } while (0)
 
+// number of kernels this library has launched (host-side counter, read through gpt_launch_count())
+extern unsigned long long g_gpt_launches;
+
+// call once after every <<<>>> launch
 static inline int gpt_launch_status() {
+    ++g_gpt_launches;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GPT_OK : (int)e;
 }

@@ -21,6 +21,37 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer(object):
+    """Optional per-entry-point CUDA-event timing (bench.py's kernel table / roofline); off by default."""
+
+    def __init__(self):
+        self.events = {}
+
+    def add(self, name, start, stop):
+        self.events.setdefault(name, []).append((start, stop))
+
+    def summary(self):
+        """{name: (calls, total_ms)}; synchronises."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+TIMER = None   # set to a KernelTimer to time every C-ABI call on the launching stream
+
+
+def _call(name, *args):
+    fn = getattr(_lib.lib(), name)
+    if TIMER is None:
+        _lib.check(fn(*args), name)
+        return
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    rc = fn(*args)
+    stop.record()
+    TIMER.add(name, start, stop)
+    _lib.check(rc, name)
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -87,10 +118,9 @@ def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k):
     masks = _dev(masks, torch.uint8, 'masks')
     B, T = head.shape
     csr = TreeCSR(B, T, head.device)
-    rc = _lib.lib().gpt_prune_csr(_ptr(head), _ptr(subj_pos), _ptr(obj_pos), _ptr(deprel), _ptr(masks), B, T,
-                                  int(prune_k), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(csr.flags),
-                                  _ptr(csr.denom), _ptr(csr.lens), _ptr(csr.err), _stream())
-    _lib.check(rc, 'gpt_prune_csr')
+    _call('gpt_prune_csr', _ptr(head), _ptr(subj_pos), _ptr(obj_pos), _ptr(deprel), _ptr(masks), B, T,
+          int(prune_k), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(csr.flags),
+          _ptr(csr.denom), _ptr(csr.lens), _ptr(csr.err), _stream())
     return csr
 
 
@@ -102,8 +132,7 @@ def linear_fwd(x2d, weight, mode='fp32'):
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     if mode != 'fp32':
         raise _lib.GptError('gemm mode %r not built' % mode)
-    _lib.check(_lib.lib().gpt_linear_fwd_f32(_ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream()),
-               'gpt_linear_fwd_f32')
+    _call('gpt_linear_fwd_f32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
     return y
 
 
@@ -111,8 +140,7 @@ def linear_dgrad(dy, weight, mode='fp32'):
     M, N = dy.shape
     K = weight.shape[1]
     dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-    _lib.check(_lib.lib().gpt_linear_dgrad_f32(_ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream()),
-               'gpt_linear_dgrad_f32')
+    _call('gpt_linear_dgrad_f32', _ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream())
     return dx
 
 
@@ -120,8 +148,7 @@ def linear_wgrad(dy, x2d, mode='fp32'):
     M, N = dy.shape
     K = x2d.shape[1]
     dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
-    _lib.check(_lib.lib().gpt_linear_wgrad_f32(_ptr(dy), _ptr(x2d), _ptr(dw), M, N, K, _stream()),
-               'gpt_linear_wgrad_f32')
+    _call('gpt_linear_wgrad_f32', _ptr(dy), _ptr(x2d), _ptr(dw), M, N, K, _stream())
     return dw
 
 
@@ -131,11 +158,9 @@ def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq
     B, T = csr.B, csr.T
     H = y.shape[-1]
     out = torch.empty((B, T, H), dtype=torch.float32, device=y.device)
-    rc = _lib.lib().gpt_gcn_aggregate_fwd(_ptr(y), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
-                                          _ptr(csr.flags), _ptr(bias), _ptr(out), B, T, H, int(bool(use_adj)),
-                                          float(drop_p), _ptr(rng_state), int(subseq), _ptr(drop_mask),
-                                          int(force_vec), _stream())
-    _lib.check(rc, 'gpt_gcn_aggregate_fwd')
+    _call('gpt_gcn_aggregate_fwd', _ptr(y), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
+          _ptr(csr.flags), _ptr(bias), _ptr(out), B, T, H, int(bool(use_adj)),
+          float(drop_p), _ptr(rng_state), int(subseq), _ptr(drop_mask), int(force_vec), _stream())
     return out
 
 
@@ -144,10 +169,9 @@ def aggregate_bwd(gout, out, csr, use_adj=True, drop_p=0.0, drop_mask=None, want
     H = out.shape[-1]
     dy = torch.empty((B * T, H), dtype=torch.float32, device=out.device)
     dbias = torch.zeros((H,), dtype=torch.float32, device=out.device) if want_dbias else None
-    rc = _lib.lib().gpt_gcn_aggregate_bwd(_ptr(gout), _ptr(out), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
-                                          _ptr(dy), _ptr(dbias), B, T, H, int(bool(use_adj)), float(drop_p),
-                                          _ptr(drop_mask), int(force_vec), _stream())
-    _lib.check(rc, 'gpt_gcn_aggregate_bwd')
+    _call('gpt_gcn_aggregate_bwd', _ptr(gout), _ptr(out), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
+          _ptr(dy), _ptr(dbias), B, T, H, int(bool(use_adj)), float(drop_p), _ptr(drop_mask), int(force_vec),
+          _stream())
     return dy, dbias
 
 
@@ -197,8 +221,7 @@ class _Pool3(torch.autograd.Function):
         B, T, H = h.shape
         out = torch.empty((B, 3 * H), dtype=torch.float32, device=h.device)
         argmax = torch.empty((B, 3 * H), dtype=torch.int32, device=h.device) if pool_type == 0 else None
-        _lib.check(_lib.lib().gpt_pool3_fwd(_ptr(h), _ptr(csr.flags), B, T, H, pool_type, _ptr(out), _ptr(argmax),
-                                            _stream()), 'gpt_pool3_fwd')
+        _call('gpt_pool3_fwd', _ptr(h), _ptr(csr.flags), B, T, H, pool_type, _ptr(out), _ptr(argmax), _stream())
         ctx.csr, ctx.pool_type, ctx.shape = csr, pool_type, (B, T, H)
         ctx.save_for_backward(argmax)
         return out
@@ -209,8 +232,8 @@ class _Pool3(torch.autograd.Function):
         B, T, H = ctx.shape
         gout = _dev(gout, torch.float32, 'grad_out')
         dh = torch.empty((B, T, H), dtype=torch.float32, device=gout.device)
-        _lib.check(_lib.lib().gpt_pool3_bwd(_ptr(gout), _ptr(argmax), _ptr(ctx.csr.flags), B, T, H, ctx.pool_type,
-                                            _ptr(dh), _stream()), 'gpt_pool3_bwd')
+        _call('gpt_pool3_bwd', _ptr(gout), _ptr(argmax), _ptr(ctx.csr.flags), B, T, H, ctx.pool_type, _ptr(dh),
+              _stream())
         return dh, None, None
 
 

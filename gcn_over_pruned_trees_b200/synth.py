@@ -111,3 +111,40 @@ def tacred_opt(**overrides):
     )
     opt.update(overrides)
     return opt
+
+
+def make_batch_torch(seed, batch_size, length, vocab_size=50000, num_class=42, device='cuda'):
+    """Fixed-length batch (cfg5 shape: every sentence exactly ``length`` tokens) built with vectorised torch ops on
+    ``device`` -- same field layout and value ranges as make_batch, same uniform random recursive trees; the two
+    spans are drawn from different halves of the sentence (then randomly swapped) so they are disjoint."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    B, T = batch_size, length
+
+    def randint(lo, hi, shape):
+        return torch.randint(lo, hi, shape, device=device, generator=g)
+
+    perm = torch.rand((B, T), device=device, generator=g).argsort(1)
+    j = torch.arange(T, device=device)
+    r = (torch.rand((B, T), device=device, generator=g) * j).long().clamp_(max=T - 1)
+    r = torch.minimum(r, (j - 1).clamp_(min=0))
+    parent = perm.gather(1, r)
+    head = torch.zeros((B, T), dtype=torch.int64, device=device)
+    head.scatter_(1, perm[:, 1:], parent[:, 1:] + 1)
+    deprel = randint(2, constant.DEPREL_FORWARD_BOUND, (B, T))
+    deprel[head == 0] = constant.ROOT_DEPREL_ID
+    half = T // 2
+    a0 = randint(0, max(half - 3, 1), (B, 1))
+    b0 = randint(half, max(T - 3, half + 1), (B, 1))
+    a1 = a0 + randint(0, 3, (B, 1))
+    b1 = (b0 + randint(0, 3, (B, 1))).clamp_(max=T - 1)
+    swap = randint(0, 2, (B, 1)).bool()
+    ss, se = torch.where(swap, b0, a0), torch.where(swap, b1, a1)
+    os_, oe = torch.where(swap, a0, b0), torch.where(swap, a1, b1)
+    idx = j[None, :]
+
+    def positions(s, e):
+        return torch.where(idx < s, idx - s, torch.where(idx > e, idx - e, torch.zeros_like(idx)))
+
+    words = randint(2, vocab_size, (B, T))
+    return (words, words.eq(0), randint(2, constant.NUM_POS, (B, T)), randint(2, constant.NUM_NER, (B, T)), deprel,
+            head, positions(ss, se), positions(os_, oe), randint(0, num_class, (B,)), list(range(B)))

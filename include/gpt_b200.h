@@ -52,6 +52,8 @@ extern "C" {
 #define GPT_GEMM_BF16 3   /* tcgen05 kind::f16 on bf16-rounded operands, fp32 accumulate */
 
 int gpt_version(void);
+/* host: number of kernels launched by this library so far in this process (bench.py's gpu_launches) */
+unsigned long long gpt_launch_count(void);
 /* host: static string for a return code of this library (cudaGetErrorString for positive codes) */
 const char* gpt_error_string(int code);
 
