@@ -8,10 +8,11 @@
 // (row i of the CSR already contains the 84-valued diagonal, so the self term is counted twice and the bias
 // twice, exactly as the reference does).
 //
-// Mapping: one CTA per (sentence, 32*VEC-column slice).  The slice of all T projected rows of the sentence is
-// staged in shared memory with cp.async (each row is read from HBM exactly once), the sentence's CSR is staged
-// next to it, then one warp per node gathers its <= deg+1 rows out of shared memory with 32*VEC-wide loads and
-// applies the epilogue.  HBM traffic = read y once + write out once + CSR: the algorithmic minimum.
+// Mapping: one CTA per (sentence, HS-column slice), HS = 4*LPR in {32, 64, 128}.  The slice of all T projected
+// rows of the sentence is staged in shared memory with cp.async (each row is read from HBM exactly once), the
+// sentence's CSR / denom / flags are staged next to it (16-bit indices), then LPR lanes per node gather the
+// node's <= deg+1 rows out of shared memory with 128-bit loads (a warp works on 32/LPR nodes at a time, two
+// rows in flight per lane group) and apply the epilogue.  HBM traffic = read y once + write out once + CSR.
 //
 // Backward (adjacency is symmetric, so A^T = A and the same CSR is reused):
 //   g_i  = gout_i * dropscale * [out_i > 0] / denom_i          (staged into shared memory)
@@ -22,7 +23,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRowBlock = 8;  // rows that share one Philox call per column
+constexpr int kRowBlock = 8;  // consecutive rows that share one Philox call per column
 
 struct AggParams {
     const float* y;      // [B*T, H] projected rows (fwd) / gout (bwd)
@@ -51,154 +52,223 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-template <int VEC>
-struct Vec;
-template <>
-struct Vec<1> { using type = float; };
-template <>
-struct Vec<2> { using type = float2; };
-template <>
-struct Vec<4> { using type = float4; };
-
-template <int VEC>
-__device__ __forceinline__ void lds_add(float (&acc)[VEC], const float* p) {
-    typename Vec<VEC>::type v = *reinterpret_cast<const typename Vec<VEC>::type*>(p);
-    const float* f = reinterpret_cast<const float*>(&v);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] += f[i];
+__device__ __forceinline__ void add4(float4& a, const float4 b) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
 }
 
-template <int VEC, bool ALIGNED>
-__device__ __forceinline__ void store_row(float* dst, const float (&v)[VEC], int c, int H) {
-    if (ALIGNED) {
-        if (c < H) {  // H % 4 == 0 and c % VEC == 0: the vector is entirely inside or outside
-            typename Vec<VEC>::type pack;
-            float* f = reinterpret_cast<float*>(&pack);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) f[i] = v[i];
-            *reinterpret_cast<typename Vec<VEC>::type*>(dst) = pack;
+// Shared-memory accessors on 32-bit shared-window addresses: keeps all address arithmetic in 32 bits and stops
+// the compiler from re-deriving the carve-up inside the hot loops.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+
+// Shared-memory carve-up, identical for forward and backward.
+//   tile [T+1][HS]  staged rows; row T is all zeros (target of padded gather slots -> branch-free inner loop)
+//   meta [T]        .x = CSR row start | (row length << 16), .y = bits of 1/denom (0 for unobservable rows)
+//   col  [4T+2]     16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
+struct Smem {
+    float* tile;
+    uint2* meta;
+    unsigned short* col;
+};
+__host__ __device__ inline size_t tile_rows(int T, int lpr) {
+    const int groups = kWarps * (32 / lpr);
+    return (size_t)(T + 1 > groups ? T + 1 : groups);
+}
+__host__ __device__ inline size_t agg_smem_bytes(int T, int lpr) {
+    return tile_rows(T, lpr) * 4 * lpr * sizeof(float) + (size_t)T * sizeof(uint2) +
+           (size_t)(4 * T + 2) * sizeof(unsigned short);
+}
+__device__ __forceinline__ Smem carve(float* base, int T, int lpr) {
+    Smem s;
+    s.tile = base;
+    s.meta = reinterpret_cast<uint2*>(base + tile_rows(T, lpr) * 4 * lpr);
+    s.col = reinterpret_cast<unsigned short*>(s.meta + T);
+    return s;
+}
+
+// Stage the sentence's CSR (16-bit) and the per-row {start, length, 1/denom} words; zero the pad row.
+template <bool FWD>
+__device__ __forceinline__ void stage_meta(const AggParams& p, int b, const Smem& s, int HS) {
+    const int T = p.T;
+    const int* rp = p.rowptr + (size_t)b * (T + 1);
+    const int nnz = p.use_adj ? min(rp[T], p.cap) : 0;
+    const int* cb = p.col + (size_t)b * p.cap;
+    for (int e = threadIdx.x; e < nnz; e += kThreads) s.col[e] = (unsigned short)cb[e];
+    for (int t = threadIdx.x; t < T; t += kThreads) {
+        const int st = rp[t], len = p.use_adj ? rp[t + 1] - st : 0;
+        float inv = 0.f;
+        if (FWD) {
+            const bool on = p.flags[(size_t)b * T + t] != 0;  // observable row: in the tree, or an entity token
+            inv = on ? __frcp_rn(p.denom[(size_t)b * T + t]) : 0.f;
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i)
-            if (c + i < H) dst[i] = v[i];
+        s.meta[t] = make_uint2((unsigned)st | ((unsigned)len << 16), __float_as_uint(inv));
+    }
+    for (int c = threadIdx.x; c < HS; c += kThreads) s.tile[(size_t)T * HS + c] = 0.f;
+}
+
+// acc0/acc1 += the rows listed in two CSR rows.  The trip count is warp-uniform (max row length in the warp),
+// exhausted slots select the zero row, so the loop has no divergent control flow:
+//   per chain and trip: LDS.U16, ISETP+SEL, IMAD, LDS.128, 4 FADD.
+template <int HS>
+__device__ __forceinline__ void gather2(uint32_t tile_lane, uint32_t col_s, int T, unsigned m0, unsigned m1,
+                                        float4& acc0, float4& acc1) {
+    const int n0 = m0 >> 16, n1 = m1 >> 16;
+    uint32_t c0 = col_s + 2u * (m0 & 0xffffu), c1 = col_s + 2u * (m1 & 0xffffu);
+    const int trips = __reduce_max_sync(GPT_FULL_MASK, max(n0, n1));
+#pragma unroll 2
+    for (int k = 0; k < trips; ++k) {
+        const uint32_t r0 = lds_u16(c0), r1 = lds_u16(c1);
+        const uint32_t j0 = (k < n0) ? r0 : (uint32_t)T, j1 = (k < n1) ? r1 : (uint32_t)T;
+        const float4 x0 = lds128(tile_lane + j0 * (HS * 4)), x1 = lds128(tile_lane + j1 * (HS * 4));
+        add4(acc0, x0);
+        add4(acc1, x1);
+        c0 += 2;
+        c1 += 2;
     }
 }
 
-// Stage the sentence's CSR ([T+1] offsets + nnz columns) into shared memory.
-__device__ __forceinline__ void stage_csr(const AggParams& p, int b, int* s_rp, int* s_col) {
-    const int* rp = p.rowptr + (size_t)b * (p.T + 1);
-    for (int t = threadIdx.x; t <= p.T; t += kThreads) s_rp[t] = rp[t];
-    const int nnz = p.use_adj ? min(rp[p.T], p.cap) : 0;
-    const int* cb = p.col + (size_t)b * p.cap;
-    for (int e = threadIdx.x; e < nnz; e += kThreads) s_col[e] = cb[e];
+template <bool ALIGNED>
+__device__ __forceinline__ void store4(float* dst, const float4 v, int c, int H) {
+    if (ALIGNED) {
+        *reinterpret_cast<float4*>(dst) = v;  // caller checked c < H; H % 4 == 0 keeps the vector inside
+    } else {
+        if (c < H) dst[0] = v.x;
+        if (c + 1 < H) dst[1] = v.y;
+        if (c + 2 < H) dst[2] = v.z;
+        if (c + 3 < H) dst[3] = v.w;
+    }
 }
 
-template <int VEC, bool ALIGNED>
+enum { DROP_NONE = 0, DROP_PHILOX = 1, DROP_MASK = 2 };
+
+template <int LPR, bool ALIGNED, int DROP>
 __global__ void __launch_bounds__(kThreads) aggregate_fwd_kernel(const AggParams p) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int HS = 32 * VEC;
+    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = kWarps * RPW;
     const int T = p.T, H = p.H;
     const int b = blockIdx.y, col0 = blockIdx.x * HS;
-    float* tile = smem_f;
-    int* s_rp = reinterpret_cast<int*>(tile + (size_t)T * HS);
-    int* s_col = s_rp + (T + 1);
+    const Smem s = carve(smem_f, T, LPR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- stage y[b, :, col0 : col0+HS] -----------------------------------------------------------------------
     const float* yb = p.y + (size_t)b * T * H;
     if (ALIGNED) {
-        constexpr int CPR = HS / 4;  // 16-byte chunks per row
-        for (int q = tid; q < T * CPR; q += kThreads) {
-            const int row = q / CPR, cc = (q % CPR) * 4, c = col0 + cc;
-            float* dst = tile + row * HS + cc;
+        for (int q = tid; q < T * LPR; q += kThreads) {
+            const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
+            float* dst = s.tile + row * HS + cc;
             if (c < H) cp_async16(dst, yb + (size_t)row * H + c);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
         for (int q = tid; q < T * HS; q += kThreads) {
             const int row = q / HS, cc = q % HS, c = col0 + cc;
-            if (c < H) cp_async4(tile + q, yb + (size_t)row * H + c);
-            else tile[q] = 0.f;
+            if (c < H) cp_async4(s.tile + q, yb + (size_t)row * H + c);
+            else s.tile[q] = 0.f;
         }
     }
-    stage_csr(p, b, s_rp, s_col);
+    stage_meta<true>(p, b, s, HS);
     cp_async_wait_all();
     __syncthreads();
 
     // ---- per-thread constants ---------------------------------------------------------------------------------
-    const int c_lane = col0 + lane * VEC;
-    float bias2[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) bias2[v] = (c_lane + v < H) ? 2.0f * p.bias[c_lane + v] : 0.f;
-    const bool philox = (p.rng != nullptr) && (p.thresh16 > 0);
+    const int cl = (lane % LPR) * 4, c_lane = col0 + cl, sub = lane / LPR;
+    const bool col_ok = c_lane < H;  // lanes past H stay in the loops (warp-wide reduce inside) but never store
+    float4 bias2;
+    bias2.x = col_ok ? 2.0f * p.bias[c_lane] : 0.f;
+    bias2.y = (c_lane + 1 < H) ? 2.0f * p.bias[c_lane + 1] : 0.f;
+    bias2.z = (c_lane + 2 < H) ? 2.0f * p.bias[c_lane + 2] : 0.f;
+    bias2.w = (c_lane + 3 < H) ? 2.0f * p.bias[c_lane + 3] : 0.f;
     unsigned long long seed = 0, step = 0;
-    if (philox) { seed = p.rng[0]; step = p.rng[1]; }
+    if (DROP == DROP_PHILOX) { seed = p.rng[0]; step = p.rng[1]; }
+    const uint32_t tile_lane = smem_u32(s.tile) + (uint32_t)cl * 4u;
+    const uint32_t meta_s = smem_u32(s.meta), col_s = smem_u32(s.col);
+    const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
+    float* const out_lane = p.out + (size_t)b * T * H + c_lane;
+    const float* const mask_lane = (DROP == DROP_MASK) ? p.drop_mask + (size_t)b * T * H + c_lane : nullptr;
+    const unsigned thresh = p.thresh16;
+    const float dscale = p.drop_scale;
 
-    // ---- one warp per node, nodes taken in blocks of kRowBlock consecutive rows -------------------------------
-    for (int blk = warp; blk * kRowBlock < T; blk += kWarps) {
-        unsigned long long rlo[VEC], rhi[VEC];  // 8 x 16 random bits per column: one per row of the block
+    // ---- LPR lanes per node; every lane group walks its own blocks of kRowBlock consecutive rows.  The block loop
+    //      is warp-uniform (blk0); rows past T behave as empty rows and are not stored. ---------------------------
+    for (int blk0 = warp * RPW; blk0 * kRowBlock < T; blk0 += GROUPS) {
+        const int blk = blk0 + sub;
+        unsigned long long rlo[4] = {0, 0, 0, 0}, rhi[4] = {0, 0, 0, 0};  // 8 x 16 random bits per column
+        if (DROP == DROP_PHILOX) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { rlo[v] = 0; rhi[v] = 0; }
-        if (philox) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const Philox4 q = philox4x32_10((uint32_t)(c_lane + v) | (p.subseq << 20), (uint32_t)blk, (uint32_t)b,
-                                                (uint32_t)step, (uint32_t)seed,
-                                                (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+            for (int v = 0; v < 4; ++v) {
+                const Philox4 q = philox4x32(  // one call covers this column for the 8 rows of the block
+                    (uint32_t)(c_lane + v) | (p.subseq << 20), (uint32_t)blk, (uint32_t)b, (uint32_t)step,
+                    (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
                 rlo[v] = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
                 rhi[v] = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
             }
         }
-#pragma unroll 2
-        for (int r = 0; r < kRowBlock; ++r) {
-            const int i = blk * kRowBlock + r;
-            if (i >= T) continue;
-            const size_t grow = (size_t)b * T + i;
-            float res[VEC];
-            if (p.flags[grow] != 0) {  // warp-uniform: row is observable (in tree, or an entity token)
-                float acc[VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-                lds_add<VEC>(acc, tile + i * HS + lane * VEC);  // the separate W(h) self term
-                if (p.use_adj) {
-                    const int e1 = s_rp[i + 1];
-                    for (int e = s_rp[i]; e < e1; ++e) lds_add<VEC>(acc, tile + s_col[e] * HS + lane * VEC);
-                }
-                const float dn = p.denom[grow];
+        for (int r = 0; r < kRowBlock; r += 2) {
+            const int i0 = blk * kRowBlock + r, i1 = i0 + 1;
+            const bool v0 = i0 < T, v1 = i1 < T;
+            uint2 m0 = make_uint2(0u, 0u), m1 = make_uint2(0u, 0u);
+            if (v0) m0 = lds64(meta_s + (uint32_t)i0 * 8u);
+            if (v1) m1 = lds64(meta_s + (uint32_t)i1 * 8u);
+            // the separate W(h) self term (the CSR row holds the 84-diagonal a second time)
+            float4 acc0 = lds128(v0 ? tile_lane + (uint32_t)i0 * (HS * 4) : zero_row);
+            float4 acc1 = lds128(v1 ? tile_lane + (uint32_t)i1 * (HS * 4) : zero_row);
+            gather2<HS>(tile_lane, col_s, T, m0.x, m1.x, acc0, acc1);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    float z = (acc[v] + bias2[v]) / dn;
-                    z = fmaxf(z, 0.f);
-                    if (philox) {
-                        const uint32_t bits = (uint32_t)(((r < 4 ? rlo[v] : rhi[v]) >> ((r & 3) * 16)) & 0xffffull);
-                        z = (bits >= p.thresh16) ? z * p.drop_scale : 0.f;
+            for (int h = 0; h < 2; ++h) {
+                const float4 a = h ? acc1 : acc0;
+                const float inv = __uint_as_float(h ? m1.y : m0.y);  // 0 for unobservable rows -> output 0
+                float res[4] = {(a.x + bias2.x) * inv, (a.y + bias2.y) * inv, (a.z + bias2.z) * inv,
+                                (a.w + bias2.w) * inv};
+                const int rr = r + h;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    float t = fmaxf(res[v], 0.f);
+                    if (DROP == DROP_PHILOX) {
+                        const uint32_t bits = (uint32_t)(((rr < 4 ? rlo[v] : rhi[v]) >> ((rr & 3) * 16)) & 0xffffull);
+                        t = (bits >= thresh) ? t * dscale : 0.f;
                     }
-                    res[v] = z;
+                    res[v] = t;
                 }
-                if (p.drop_mask != nullptr) {
+                if ((h ? v1 : v0) && col_ok) {
+                    const uint32_t off = (uint32_t)(h ? i1 : i0) * (uint32_t)H;
+                    if (DROP == DROP_MASK) {
+                        const float* m = mask_lane + off;
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (c_lane + v < H) res[v] *= p.drop_mask[grow * H + c_lane + v];
+                        for (int v = 0; v < 4; ++v)
+                            if (c_lane + v < H) res[v] *= m[v];
+                    }
+                    store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
                 }
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) res[v] = 0.f;
             }
-            store_row<VEC, ALIGNED>(p.out + grow * H + c_lane, res, c_lane, H);
         }
     }
 }
 
-template <int VEC, bool ALIGNED>
+template <int LPR, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) aggregate_bwd_kernel(const AggParams p) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int HS = 32 * VEC;
+    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = kWarps * RPW;
     const int T = p.T, H = p.H;
     const int b = blockIdx.y, col0 = blockIdx.x * HS;
-    float* tile = smem_f;
-    int* s_rp = reinterpret_cast<int*>(tile + (size_t)T * HS);
-    int* s_col = s_rp + (T + 1);
+    const Smem s = carve(smem_f, T, LPR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- stage g = gout * dropscale * [out > 0] / denom --------------------------------------------------------
@@ -208,23 +278,25 @@ __global__ void __launch_bounds__(kThreads) aggregate_bwd_kernel(const AggParams
     const float* mb = p.drop_mask ? p.drop_mask + base : nullptr;
     const float* dnb = p.denom + (size_t)b * T;
     if (ALIGNED) {
-        constexpr int CPR = HS / 4;
-        for (int q = tid; q < T * CPR; q += kThreads) {
-            const int row = q / CPR, cc = (q % CPR) * 4, c = col0 + cc;
+        const uint32_t tile_s = smem_u32(s.tile);
+        const float ds = p.drop_scale;
+#pragma unroll 4
+        for (int q = tid; q < T * LPR; q += kThreads) {
+            const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < H) {
-                const size_t off = (size_t)row * H + c;
+                const uint32_t off = (uint32_t)row * (uint32_t)H + (uint32_t)c;
                 const float4 go = *reinterpret_cast<const float4*>(gb + off);
                 const float4 o = *reinterpret_cast<const float4*>(ob + off);
-                float4 m = make_float4(p.drop_scale, p.drop_scale, p.drop_scale, p.drop_scale);
+                float4 m = make_float4(ds, ds, ds, ds);
                 if (mb) m = *reinterpret_cast<const float4*>(mb + off);
-                const float dn = dnb[row];
-                g.x = o.x > 0.f ? go.x * m.x / dn : 0.f;
-                g.y = o.y > 0.f ? go.y * m.y / dn : 0.f;
-                g.z = o.z > 0.f ? go.z * m.z / dn : 0.f;
-                g.w = o.w > 0.f ? go.w * m.w / dn : 0.f;
+                const float inv = __frcp_rn(dnb[row]);
+                g.x = o.x > 0.f ? go.x * m.x * inv : 0.f;
+                g.y = o.y > 0.f ? go.y * m.y * inv : 0.f;
+                g.z = o.z > 0.f ? go.z * m.z * inv : 0.f;
+                g.w = o.w > 0.f ? go.w * m.w * inv : 0.f;
             }
-            *reinterpret_cast<float4*>(tile + row * HS + cc) = g;
+            sts128(tile_s + (uint32_t)(row * HS + cc) * 4u, g);
         }
     } else {
         for (int q = tid; q < T * HS; q += kThreads) {
@@ -233,65 +305,63 @@ __global__ void __launch_bounds__(kThreads) aggregate_bwd_kernel(const AggParams
             if (c < H) {
                 const size_t off = (size_t)row * H + c;
                 const float m = mb ? mb[off] : p.drop_scale;
-                g = ob[off] > 0.f ? gb[off] * m / dnb[row] : 0.f;
+                g = ob[off] > 0.f ? gb[off] * m * __frcp_rn(dnb[row]) : 0.f;
             }
-            tile[q] = g;
+            s.tile[q] = g;
         }
     }
-    stage_csr(p, b, s_rp, s_col);
+    stage_meta<false>(p, b, s, HS);
     __syncthreads();
 
     // ---- dy_j = g_j + sum_{i in row j} g_i ; column sums for dbias ---------------------------------------------
-    const int c_lane = col0 + lane * VEC;
-    float csum[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) csum[v] = 0.f;
-    for (int j = warp; j < T; j += kWarps) {
-        float acc[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        lds_add<VEC>(acc, tile + j * HS + lane * VEC);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) csum[v] += acc[v];
-        if (p.use_adj) {
-            const int e1 = s_rp[j + 1];
-            for (int e = s_rp[j]; e < e1; ++e) lds_add<VEC>(acc, tile + s_col[e] * HS + lane * VEC);
-        }
-        store_row<VEC, ALIGNED>(p.out + ((size_t)b * T + j) * H + c_lane, acc, c_lane, H);
+    const int cl = (lane % LPR) * 4, c_lane = col0 + cl, sub = lane / LPR;
+    const bool col_ok = c_lane < H;
+    const uint32_t tile_lane = smem_u32(s.tile) + (uint32_t)cl * 4u;
+    const uint32_t meta_s = smem_u32(s.meta), col_s = smem_u32(s.col);
+    const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
+    float* const out_lane = p.out + base + c_lane;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jb = warp * RPW * 2; jb < T; jb += GROUPS * 2) {   // warp-uniform
+        const int j0 = jb + sub * 2, j1 = j0 + 1;
+        const bool v0 = j0 < T, v1 = j1 < T;
+        unsigned m0 = 0u, m1 = 0u;
+        if (v0) m0 = lds64(meta_s + (uint32_t)j0 * 8u).x;
+        if (v1) m1 = lds64(meta_s + (uint32_t)j1 * 8u).x;
+        float4 acc0 = lds128(v0 ? tile_lane + (uint32_t)j0 * (HS * 4) : zero_row);
+        float4 acc1 = lds128(v1 ? tile_lane + (uint32_t)j1 * (HS * 4) : zero_row);
+        add4(csum, acc0);
+        add4(csum, acc1);
+        gather2<HS>(tile_lane, col_s, T, m0, m1, acc0, acc1);
+        const uint32_t off = (uint32_t)j0 * (uint32_t)H;
+        if (v0 && col_ok) store4<ALIGNED>(out_lane + off, acc0, c_lane, H);
+        if (v1 && col_ok) store4<ALIGNED>(out_lane + off + H, acc1, c_lane, H);
     }
     if (p.dbias != nullptr) {
-        __syncthreads();  // everyone is done reading the tile; reuse its head for the cross-warp reduction
-        float* red = tile;  // [kWarps][HS]
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) red[warp * HS + lane * VEC + v] = csum[v];
+        __syncthreads();  // everyone is done reading the tile; reuse its head for the cross-group reduction
+        float* red = s.tile;  // [GROUPS][HS]
+        *reinterpret_cast<float4*>(red + (warp * RPW + sub) * HS + cl) = csum;
         __syncthreads();
         for (int c = tid; c < HS; c += kThreads) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += red[w * HS + c];
-            if (col0 + c < H) atomicAdd(p.dbias + col0 + c, 2.0f * s);  // the bias enters the layer twice
+            float sum = 0.f;
+#pragma unroll 8
+            for (int g = 0; g < GROUPS; ++g) sum += red[g * HS + c];
+            if (col0 + c < H) atomicAdd(p.dbias + col0 + c, 2.0f * sum);  // the bias enters the layer twice
         }
     }
-}
-
-size_t agg_smem_bytes(int T, int vec) {
-    // tile [max(T, kWarps)][32*vec] floats + rowptr [T+1] + col [3T]
-    const size_t rows = (size_t)(T > kWarps ? T : kWarps);
-    return rows * 32 * vec * sizeof(float) + (size_t)(T + 1 + 3 * T) * sizeof(int);
 }
 
 // widest slice that still leaves >= 3 CTAs per SM and fills the machine at least ~2 waves
-int pick_vec(int B, int T, int H, int force) {
-    if (force == 1 || force == 2 || force == 4) return force;
-    int best = 1;
-    for (int vec = 4; vec >= 1; vec >>= 1) {
-        if (agg_smem_bytes(T, vec) > 75 * 1024) continue;  // 3 CTAs per SM
-        const long slices = (H + 32 * vec - 1) / (32 * vec);
-        if (vec > 1 && slices * B < 2 * 148) continue;
-        best = vec;
-        break;
+int pick_lpr(int B, int T, int H, int force_vec) {
+    if (force_vec == 1) return 8;
+    if (force_vec == 2) return 16;
+    if (force_vec == 4) return 32;
+    for (int lpr = 32; lpr >= 8; lpr >>= 1) {
+        if (agg_smem_bytes(T, lpr) > 74 * 1024) continue;  // 3 CTAs per SM
+        const long slices = (H + 4 * lpr - 1) / (4 * lpr);
+        if (lpr > 8 && slices * B < 2 * 148) continue;
+        return lpr;
     }
-    return best;
+    return 8;
 }
 
 template <typename K>
@@ -303,37 +373,46 @@ int ensure_smem(K kernel, size_t bytes) {
     return GPT_OK;
 }
 
-template <int VEC, bool ALIGNED>
+template <int LPR, bool ALIGNED>
 int launch(bool fwd, const AggParams& p, cudaStream_t st) {
-    const size_t smem = agg_smem_bytes(p.T, VEC);
+    const size_t smem = agg_smem_bytes(p.T, LPR);
     if (smem > 224 * 1024) return GPT_ERR_UNSUPPORTED;
-    dim3 grid((p.H + 32 * VEC - 1) / (32 * VEC), p.B);
+    dim3 grid((p.H + 4 * LPR - 1) / (4 * LPR), p.B);
     int rc;
     if (fwd) {
-        if ((rc = ensure_smem(aggregate_fwd_kernel<VEC, ALIGNED>, smem)) != GPT_OK) return rc;
-        aggregate_fwd_kernel<VEC, ALIGNED><<<grid, kThreads, smem, st>>>(p);
+        if (p.drop_mask != nullptr) {
+            if ((rc = ensure_smem(aggregate_fwd_kernel<LPR, ALIGNED, DROP_MASK>, smem)) != GPT_OK) return rc;
+            aggregate_fwd_kernel<LPR, ALIGNED, DROP_MASK><<<grid, kThreads, smem, st>>>(p);
+        } else if (p.rng != nullptr && p.thresh16 > 0) {
+            if ((rc = ensure_smem(aggregate_fwd_kernel<LPR, ALIGNED, DROP_PHILOX>, smem)) != GPT_OK) return rc;
+            aggregate_fwd_kernel<LPR, ALIGNED, DROP_PHILOX><<<grid, kThreads, smem, st>>>(p);
+        } else {
+            if ((rc = ensure_smem(aggregate_fwd_kernel<LPR, ALIGNED, DROP_NONE>, smem)) != GPT_OK) return rc;
+            aggregate_fwd_kernel<LPR, ALIGNED, DROP_NONE><<<grid, kThreads, smem, st>>>(p);
+        }
     } else {
-        if ((rc = ensure_smem(aggregate_bwd_kernel<VEC, ALIGNED>, smem)) != GPT_OK) return rc;
-        aggregate_bwd_kernel<VEC, ALIGNED><<<grid, kThreads, smem, st>>>(p);
+        if ((rc = ensure_smem(aggregate_bwd_kernel<LPR, ALIGNED>, smem)) != GPT_OK) return rc;
+        aggregate_bwd_kernel<LPR, ALIGNED><<<grid, kThreads, smem, st>>>(p);
     }
     return gpt_launch_status();
 }
 
 int dispatch(bool fwd, const AggParams& p, int force_vec, cudaStream_t st) {
+    if (4 * p.T + 2 > 65535) return GPT_ERR_UNSUPPORTED;  // 16-bit CSR indices / row lengths in shared memory
     const bool aligned = (p.H % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                          (p.aux == nullptr || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) &&
                          (p.drop_mask == nullptr || (reinterpret_cast<uintptr_t>(p.drop_mask) & 15) == 0);
-    int vec = pick_vec(p.B, p.T, p.H, force_vec);
-    while (vec > 1 && agg_smem_bytes(p.T, vec) > 224 * 1024) vec >>= 1;
+    int lpr = pick_lpr(p.B, p.T, p.H, force_vec);
+    while (lpr > 8 && agg_smem_bytes(p.T, lpr) > 224 * 1024) lpr >>= 1;
     if (aligned) {
-        if (vec == 4) return launch<4, true>(fwd, p, st);
-        if (vec == 2) return launch<2, true>(fwd, p, st);
-        return launch<1, true>(fwd, p, st);
+        if (lpr == 32) return launch<32, true>(fwd, p, st);
+        if (lpr == 16) return launch<16, true>(fwd, p, st);
+        return launch<8, true>(fwd, p, st);
     }
-    if (vec == 4) return launch<4, false>(fwd, p, st);
-    if (vec == 2) return launch<2, false>(fwd, p, st);
-    return launch<1, false>(fwd, p, st);
+    if (lpr == 32) return launch<32, false>(fwd, p, st);
+    if (lpr == 16) return launch<16, false>(fwd, p, st);
+    return launch<8, false>(fwd, p, st);
 }
 
 }  // namespace

@@ -60,11 +60,14 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
 struct Philox4 {
     uint32_t x, y, z, w;
 };
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                                 uint32_t k1) {
+// kPhiloxRounds = 7 is the smallest round count that is Crush-resistant in the paper (10 is its safety default);
+// dropout masks do not need the margin and the rounds are the kernel's largest ALU cost.
+constexpr int kPhiloxRounds = 7;
+__device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
         uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
