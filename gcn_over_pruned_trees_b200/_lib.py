@@ -19,9 +19,9 @@ SIGNATURES = {
     'gpt_version': [],
     'gpt_launch_count': [],
     'gpt_prune_csr': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p, _p, _p],
-    'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
+    'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
                               _c_int, _p],
-    'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
+    'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
     'gpt_pool3_fwd': [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p],
     'gpt_pool3_bwd': [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p],
     'gpt_linear_fwd_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],

@@ -8,26 +8,32 @@
 // (row i of the CSR already contains the 84-valued diagonal, so the self term is counted twice and the bias
 // twice, exactly as the reference does).
 //
-// Mapping: one CTA per (sentence, HS-column slice), HS = 4*LPR in {32, 64, 128}.  The slice of all T projected
-// rows of the sentence is staged in shared memory with cp.async (each row is read from HBM exactly once), the
-// sentence's CSR / denom / flags are staged next to it (16-bit indices), then LPR lanes per node gather the
-// node's <= deg+1 rows out of shared memory with 128-bit loads (a warp works on 32/LPR nodes at a time, two
-// rows in flight per lane group) and apply the epilogue.  HBM traffic = read y once + write out once + CSR.
+// Mapping.  A CTA owns one sentence and walks HS-column slices of its T projected rows (HS = 4*LPR floats).  A slice
+// [T x HS] is staged in shared memory with cp.async -- every row is read from HBM exactly once -- next to the
+// sentence's CSR (16-bit indices) and one packed {start, length, 1/denom} word per row.  LPR lanes then serve one
+// node: they gather its <= deg+1 rows out of shared memory with 128-bit loads (a warp works on 32/LPR nodes at a
+// time, two rows in flight per lane group, warp-uniform trip count, exhausted slots read a zero row: no divergent
+// control flow) and apply the epilogue.  When a sentence tile is large (few CTAs fit an SM) the CTA is persistent
+// over the sentence's slices and double-buffers them, so the next slice streams in while the current one is
+// gathered and written out; otherwise one slice per CTA and the SM overlaps many small CTAs.
+// HBM traffic = read y once + write out once + CSR (+ 1 bit per element of activation mask for the backward).
 //
 // Backward (adjacency is symmetric, so A^T = A and the same CSR is reused):
-//   g_i  = gout_i * dropscale * [out_i > 0] / denom_i          (staged into shared memory)
+//   g_i  = gout_i * dropscale * [out_i > 0] / denom_i          (formed in shared memory)
 //   dy_j = g_j + sum_{i in row j} g_i ,   dbias = 2 * sum_i g_i
+// [out_i > 0] comes from the forward's bit mask when given (reads 1/32 of the bytes) or from `out` itself.
 #include "gpt_common.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kRowBlock = 8;  // consecutive rows that share one Philox call per column
 
 struct AggParams {
     const float* y;      // [B*T, H] projected rows (fwd) / gout (bwd)
-    const float* aux;    // bwd: out of the forward pass
+    const float* aux;    // bwd: out of the forward pass (used when act_in == nullptr)
+    const uint32_t* act_in;   // bwd: activation bits written by the forward [B*T, ceil(H/32)]
+    uint32_t* act_out;        // fwd: optional activation bits
     const int* rowptr;   // [B, T+1]
     const int* col;      // [B, cap]
     const float* denom;  // [B*T]
@@ -37,23 +43,35 @@ struct AggParams {
     float* dbias;        // [H] (bwd, atomically accumulated)
     const float* drop_mask;              // optional explicit, pre-scaled mask [B*T, H]
     const unsigned long long* rng;       // optional {seed, step} on the device
-    int B, T, H, cap, use_adj;
+    int B, T, H, cap, use_adj, nbuf;
     unsigned subseq, thresh16;           // dropout: keep iff rand16 >= thresh16
     float drop_scale;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc));
 }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void add4(float4& a, const float4 b) {
-    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+
+// Four fp32 lanes held as two packed f32x2 registers: the gather adds with FADD2 (2 instructions per 16 bytes).
+struct Pack4 {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ void add_pk(Pack4& a, const Pack4 b) {
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.lo) : "l"(b.lo));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.hi) : "l"(b.hi));
+}
+__device__ __forceinline__ float4 unpack(const Pack4 a) {
+    float4 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(a.lo));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(a.hi));
+    return v;
 }
 
 // Shared-memory accessors on 32-bit shared-window addresses: keeps all address arithmetic in 32 bits and stops
@@ -62,6 +80,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ Pack4 lds_pk(uint32_t a) {
+    Pack4 v;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
@@ -75,72 +103,87 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 
-// Shared-memory carve-up, identical for forward and backward.
-//   tile [T+1][HS]  staged rows; row T is all zeros (target of padded gather slots -> branch-free inner loop)
-//   meta [T]        .x = CSR row start | (row length << 16), .y = bits of 1/denom (0 for unobservable rows)
-//   col  [4T+2]     16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
-struct Smem {
-    float* tile;
-    uint2* meta;
-    unsigned short* col;
-};
-__host__ __device__ inline size_t tile_rows(int T, int lpr) {
-    const int groups = kWarps * (32 / lpr);
-    return (size_t)(T + 1 > groups ? T + 1 : groups);
-}
-__host__ __device__ inline size_t agg_smem_bytes(int T, int lpr) {
-    return tile_rows(T, lpr) * 4 * lpr * sizeof(float) + (size_t)T * sizeof(uint2) +
-           (size_t)(4 * T + 2) * sizeof(unsigned short);
-}
-__device__ __forceinline__ Smem carve(float* base, int T, int lpr) {
-    Smem s;
-    s.tile = base;
-    s.meta = reinterpret_cast<uint2*>(base + tile_rows(T, lpr) * 4 * lpr);
-    s.col = reinterpret_cast<unsigned short*>(s.meta + T);
-    return s;
+// Shared-memory carve-up (host and device agree through these helpers):
+//   tile [nbuf][T+1][HS]  staged rows; row T is all zeros (target of padded gather slots)
+//   red  [GROUPS][HS]     backward only: per-lane-group column sums for dbias
+//   meta [T]              .x = CSR row start | (row length << 16), .y = bits of 1/denom (0: unobservable row)
+//   col  [4T+2]           16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
+//   actw [nbuf][32*ceil(T/32)]  backward with a bit mask only: the slice's activation words
+__host__ __device__ inline size_t tile_floats(int T, int lpr) { return (size_t)(T + 1) * 4 * lpr; }
+__host__ __device__ inline size_t act_words(int T) { return (size_t)((T + 31) / 32) * 32; }
+__host__ __device__ inline size_t agg_smem_bytes(int T, int lpr, int nbuf, int red_groups, bool act_stage,
+                                                 int bias_floats) {
+    return (size_t)nbuf * tile_floats(T, lpr) * sizeof(float) + (size_t)red_groups * 4 * lpr * sizeof(float) +
+           (act_stage ? (size_t)nbuf * act_words(T) * sizeof(uint32_t) : 0) + (size_t)T * sizeof(uint2) +
+           (size_t)(4 * T + 4) * sizeof(unsigned short) + (bias_floats ? (size_t)bias_floats * 4 + 16 : 0);
 }
 
-// Stage the sentence's CSR (16-bit) and the per-row {start, length, 1/denom} words; zero the pad row.
-template <bool FWD>
-__device__ __forceinline__ void stage_meta(const AggParams& p, int b, const Smem& s, int HS) {
+// Stage the sentence's CSR (16-bit) and the per-row {start, length, 1/denom} words; zero the pad rows.
+template <bool FWD, int NT>
+__device__ __forceinline__ void stage_meta(const AggParams& p, int b, float* tile0, size_t tile_stride, uint2* meta,
+                                           unsigned short* colv, int HS) {
     const int T = p.T;
     const int* rp = p.rowptr + (size_t)b * (T + 1);
     const int nnz = p.use_adj ? min(rp[T], p.cap) : 0;
     const int* cb = p.col + (size_t)b * p.cap;
-    for (int e = threadIdx.x; e < nnz; e += kThreads) s.col[e] = (unsigned short)cb[e];
-    for (int t = threadIdx.x; t < T; t += kThreads) {
+    for (int e = threadIdx.x; e < nnz; e += NT) colv[e] = (unsigned short)cb[e];
+    for (int t = threadIdx.x; t < T; t += NT) {
         const int st = rp[t], len = p.use_adj ? rp[t + 1] - st : 0;
-        float inv = 0.f;
-        if (FWD) {
-            const bool on = p.flags[(size_t)b * T + t] != 0;  // observable row: in the tree, or an entity token
-            inv = on ? __frcp_rn(p.denom[(size_t)b * T + t]) : 0.f;
-        }
-        s.meta[t] = make_uint2((unsigned)st | ((unsigned)len << 16), __float_as_uint(inv));
+        float inv = __frcp_rn(p.denom[(size_t)b * T + t]);
+        if (FWD && p.flags[(size_t)b * T + t] == 0) inv = 0.f;  // unobservable row (not in tree, not an entity)
+        meta[t] = make_uint2((unsigned)st | ((unsigned)len << 16), __float_as_uint(inv));
     }
-    for (int c = threadIdx.x; c < HS; c += kThreads) s.tile[(size_t)T * HS + c] = 0.f;
+    for (int c = threadIdx.x; c < HS * p.nbuf; c += NT)
+        tile0[(size_t)(c / HS) * tile_stride + (size_t)T * HS + (c % HS)] = 0.f;
 }
 
-// acc0/acc1 += the rows listed in two CSR rows.  The trip count is warp-uniform (max row length in the warp),
-// exhausted slots select the zero row, so the loop has no divergent control flow:
-//   per chain and trip: LDS.U16, ISETP+SEL, IMAD, LDS.128, 4 FADD.
+// Issue the asynchronous copy of slice `sl` of src[b] into a tile buffer (one commit group per call).
+template <int LPR, int NT, bool ALIGNED>
+__device__ __forceinline__ void issue_slice(const float* __restrict__ src_b, uint32_t tile_s, int T, int H, int sl) {
+    constexpr int HS = 4 * LPR;
+    const int col0 = sl * HS;
+    if (ALIGNED) {
+        for (int q = threadIdx.x; q < T * LPR; q += NT) {
+            const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
+            const uint32_t dst = tile_s + (uint32_t)(row * HS + cc) * 4u;
+            if (c < H) cp_async16(dst, src_b + (size_t)row * H + c);
+            else sts128(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    } else {
+        for (int q = threadIdx.x; q < T * HS; q += NT) {
+            const int row = q / HS, cc = q % HS, c = col0 + cc;
+            const uint32_t dst = tile_s + (uint32_t)q * 4u;
+            if (c < H) cp_async4(dst, src_b + (size_t)row * H + c);
+            else asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(0.f) : "memory");
+        }
+    }
+    cp_async_commit();
+}
+
+// acc[q] += the rows listed in CSR row q, four rows in flight per lane group.  The trip count is warp-uniform (max
+// row length in the warp), exhausted slots select the zero row, so the loop has no divergent control flow:
+//   per chain and trip: LDS.U16, ISETP+SEL, IMAD, LDS.128, 2 FADD2.
 template <int HS>
-__device__ __forceinline__ void gather2(uint32_t tile_lane, uint32_t col_s, int T, unsigned m0, unsigned m1,
-                                        float4& acc0, float4& acc1) {
-    const int n0 = m0 >> 16, n1 = m1 >> 16;
-    uint32_t c0 = col_s + 2u * (m0 & 0xffffu), c1 = col_s + 2u * (m1 & 0xffffu);
-    const int trips = __reduce_max_sync(GPT_FULL_MASK, max(n0, n1));
-#pragma unroll 2
+__device__ __forceinline__ void gather4(uint32_t tile_lane, uint32_t col_s, int T, const unsigned (&m)[4],
+                                        Pack4 (&acc)[4]) {
+    int n[4];
+    uint32_t c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { n[q] = m[q] >> 16; c[q] = col_s + 2u * (m[q] & 0xffffu); }
+    const int trips = __reduce_max_sync(GPT_FULL_MASK, max(max(n[0], n[1]), max(n[2], n[3])));
     for (int k = 0; k < trips; ++k) {
-        const uint32_t r0 = lds_u16(c0), r1 = lds_u16(c1);
-        const uint32_t j0 = (k < n0) ? r0 : (uint32_t)T, j1 = (k < n1) ? r1 : (uint32_t)T;
-        const float4 x0 = lds128(tile_lane + j0 * (HS * 4)), x1 = lds128(tile_lane + j1 * (HS * 4));
-        add4(acc0, x0);
-        add4(acc1, x1);
-        c0 += 2;
-        c1 += 2;
+        uint32_t j[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) j[q] = lds_u16(c[q] + 2u * (uint32_t)k);
+        Pack4 x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = lds_pk(tile_lane + ((k < n[q]) ? j[q] : (uint32_t)T) * (HS * 4));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) add_pk(acc[q], x[q]);
     }
 }
 
@@ -156,212 +199,314 @@ __device__ __forceinline__ void store4(float* dst, const float4 v, int c, int H)
     }
 }
 
+// Activation-bit layout (fwd writes, bwd reads; both use the LPR = 8 kernels, whose warp instruction covers 4 rows
+// x 32 columns): for sentence b, 32-row super block sb = row/32, 32-column slice sl = col/32,
+//   word  = (((b * ceil(T/32) + sb) * ceil(H/32) + sl) * 8 + row % 8) * 4 + col % 4
+//   bit   = ((row % 32) / 8) * 8 + (col % 32) / 4          (= the lane that owns the element in the forward)
+// so the four words of one (sb, sl, row % 8) are the four ballots of one forward step: one 16-byte store.
+__host__ __device__ inline size_t act_block(int b, int T, int H, int sb, int sl) {
+    return (((size_t)b * ((T + 31) / 32) + sb) * ((H + 31) / 32) + sl) * 32;
+}
+
 enum { DROP_NONE = 0, DROP_PHILOX = 1, DROP_MASK = 2 };
 
-template <int LPR, bool ALIGNED, int DROP>
-__global__ void __launch_bounds__(kThreads) aggregate_fwd_kernel(const AggParams p) {
+template <int LPR, int NT, bool ALIGNED, int DROP>
+__global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = kWarps * RPW;
+    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW;
     const int T = p.T, H = p.H;
-    const int b = blockIdx.y, col0 = blockIdx.x * HS;
-    const Smem s = carve(smem_f, T, LPR);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // ---- stage y[b, :, col0 : col0+HS] -----------------------------------------------------------------------
+    const int b = blockIdx.y;
+    const int nsl = (H + HS - 1) / HS;
+    const size_t tile_stride = tile_floats(T, LPR);
+    uint2* meta = reinterpret_cast<uint2*>(smem_f + (size_t)p.nbuf * tile_stride);
+    unsigned short* colv = reinterpret_cast<unsigned short*>(meta + T);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile_s0 = smem_u32(smem_f), tile_bytes = (uint32_t)tile_stride * 4u;
     const float* yb = p.y + (size_t)b * T * H;
-    if (ALIGNED) {
-        for (int q = tid; q < T * LPR; q += kThreads) {
-            const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
-            float* dst = s.tile + row * HS + cc;
-            if (c < H) cp_async16(dst, yb + (size_t)row * H + c);
-            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-        for (int q = tid; q < T * HS; q += kThreads) {
-            const int row = q / HS, cc = q % HS, c = col0 + cc;
-            if (c < H) cp_async4(s.tile + q, yb + (size_t)row * H + c);
-            else s.tile[q] = 0.f;
-        }
-    }
-    stage_meta<true>(p, b, s, HS);
-    cp_async_wait_all();
-    __syncthreads();
+
+    issue_slice<LPR, NT, ALIGNED>(yb, tile_s0, T, H, blockIdx.x);
+    stage_meta<true, NT>(p, b, smem_f, tile_stride, meta, colv, HS);
+    // 2*bias for every slice this CTA will visit (the bias enters the layer twice), zero past H
+    float* bias_sm = reinterpret_cast<float*>(colv + 4 * T + 2 + ((4 * T + 2) & 1));
+    bias_sm += (4 - ((reinterpret_cast<uintptr_t>(bias_sm) >> 2) & 3)) & 3;  // 16-byte aligned
+    for (int c = threadIdx.x; c < nsl * HS; c += NT) bias_sm[c] = (c < H) ? 2.0f * p.bias[c] : 0.f;
+    const uint32_t bias_s = smem_u32(bias_sm);
 
     // ---- per-thread constants ---------------------------------------------------------------------------------
-    const int cl = (lane % LPR) * 4, c_lane = col0 + cl, sub = lane / LPR;
-    const bool col_ok = c_lane < H;  // lanes past H stay in the loops (warp-wide reduce inside) but never store
-    float4 bias2;
-    bias2.x = col_ok ? 2.0f * p.bias[c_lane] : 0.f;
-    bias2.y = (c_lane + 1 < H) ? 2.0f * p.bias[c_lane + 1] : 0.f;
-    bias2.z = (c_lane + 2 < H) ? 2.0f * p.bias[c_lane + 2] : 0.f;
-    bias2.w = (c_lane + 3 < H) ? 2.0f * p.bias[c_lane + 3] : 0.f;
+    const int cl = (lane % LPR) * 4, sub = lane / LPR;
     unsigned long long seed = 0, step = 0;
     if (DROP == DROP_PHILOX) { seed = p.rng[0]; step = p.rng[1]; }
-    const uint32_t tile_lane = smem_u32(s.tile) + (uint32_t)cl * 4u;
-    const uint32_t meta_s = smem_u32(s.meta), col_s = smem_u32(s.col);
-    const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
-    float* const out_lane = p.out + (size_t)b * T * H + c_lane;
-    const float* const mask_lane = (DROP == DROP_MASK) ? p.drop_mask + (size_t)b * T * H + c_lane : nullptr;
+    const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv);
     const unsigned thresh = p.thresh16;
     const float dscale = p.drop_scale;
+    const bool write_act = (p.act_out != nullptr) && (LPR == 8);
 
-    // ---- LPR lanes per node; every lane group walks its own blocks of kRowBlock consecutive rows.  The block loop
-    //      is warp-uniform (blk0); rows past T behave as empty rows and are not stored. ---------------------------
-    for (int blk0 = warp * RPW; blk0 * kRowBlock < T; blk0 += GROUPS) {
-        const int blk = blk0 + sub;
-        unsigned long long rlo[4] = {0, 0, 0, 0}, rhi[4] = {0, 0, 0, 0};  // 8 x 16 random bits per column
-        if (DROP == DROP_PHILOX) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const Philox4 q = philox4x32(  // one call covers this column for the 8 rows of the block
-                    (uint32_t)(c_lane + v) | (p.subseq << 20), (uint32_t)blk, (uint32_t)b, (uint32_t)step,
-                    (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
-                rlo[v] = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
-                rhi[v] = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
-            }
+    int it = 0;
+    for (int sl = blockIdx.x; sl < nsl; sl += gridDim.x, ++it) {
+        const int nxt = sl + gridDim.x;
+        if (nxt < nsl) {  // stream the next slice into the other buffer while this one is processed
+            issue_slice<LPR, NT, ALIGNED>(yb, tile_s0 + (uint32_t)((it + 1) & 1) * tile_bytes, T, H, nxt);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-#pragma unroll
-        for (int r = 0; r < kRowBlock; r += 2) {
-            const int i0 = blk * kRowBlock + r, i1 = i0 + 1;
-            const bool v0 = i0 < T, v1 = i1 < T;
-            uint2 m0 = make_uint2(0u, 0u), m1 = make_uint2(0u, 0u);
-            if (v0) m0 = lds64(meta_s + (uint32_t)i0 * 8u);
-            if (v1) m1 = lds64(meta_s + (uint32_t)i1 * 8u);
-            // the separate W(h) self term (the CSR row holds the 84-diagonal a second time)
-            float4 acc0 = lds128(v0 ? tile_lane + (uint32_t)i0 * (HS * 4) : zero_row);
-            float4 acc1 = lds128(v1 ? tile_lane + (uint32_t)i1 * (HS * 4) : zero_row);
-            gather2<HS>(tile_lane, col_s, T, m0.x, m1.x, acc0, acc1);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4 a = h ? acc1 : acc0;
-                const float inv = __uint_as_float(h ? m1.y : m0.y);  // 0 for unobservable rows -> output 0
-                float res[4] = {(a.x + bias2.x) * inv, (a.y + bias2.y) * inv, (a.z + bias2.z) * inv,
-                                (a.w + bias2.w) * inv};
-                const int rr = r + h;
+        __syncthreads();
+
+        const int col0 = sl * HS, c_lane = col0 + cl;
+        const bool col_ok = c_lane < H;  // lanes past H stay in the loops (warp-wide ops inside) but never store
+        const float4 bias2 = lds128(bias_s + (uint32_t)c_lane * 4u);  // 2*bias, zero past H
+        const uint32_t tile_lane = tile_s0 + (uint32_t)(it & 1) * tile_bytes + (uint32_t)cl * 4u;
+        const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
+        float* const out_lane = p.out + (size_t)b * T * H + c_lane;
+        const float* const mask_lane = (DROP == DROP_MASK) ? p.drop_mask + (size_t)b * T * H + c_lane : nullptr;
+
+        // LPR lanes per node; every lane group walks its own blocks of kRowBlock consecutive rows, four rows in
+        // flight.  The block loop is warp-uniform (blk0); rows past T behave as empty rows and are not stored.
+        for (int blk0 = warp * RPW; blk0 * kRowBlock < T; blk0 += GROUPS) {
+            const int blk = blk0 + sub;
+            unsigned long long rlo[4] = {0, 0, 0, 0}, rhi[4] = {0, 0, 0, 0};  // 8 x 16 random bits per column
+            if (DROP == DROP_PHILOX) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    float t = fmaxf(res[v], 0.f);
-                    if (DROP == DROP_PHILOX) {
-                        const uint32_t bits = (uint32_t)(((rr < 4 ? rlo[v] : rhi[v]) >> ((rr & 3) * 16)) & 0xffffull);
-                        t = (bits >= thresh) ? t * dscale : 0.f;
-                    }
-                    res[v] = t;
+                    const Philox4 q = philox4x32(  // one call covers this column for the 8 rows of the block
+                        (uint32_t)(c_lane + v) | (p.subseq << 20), (uint32_t)blk, (uint32_t)b, (uint32_t)step,
+                        (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+                    rlo[v] = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+                    rhi[v] = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
                 }
-                if ((h ? v1 : v0) && col_ok) {
-                    const uint32_t off = (uint32_t)(h ? i1 : i0) * (uint32_t)H;
-                    if (DROP == DROP_MASK) {
-                        const float* m = mask_lane + off;
+            }
+            // activation words of this (super block, slice): [row % 8][4] words, see act_block()
+            uint32_t* const act_blk = write_act ? p.act_out + act_block(b, T, H, blk0 >> 2, sl) : nullptr;
 #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            if (c_lane + v < H) res[v] *= m[v];
+            for (int r = 0; r < kRowBlock; r += 4) {
+                const int i0 = blk * kRowBlock + r;
+                unsigned mx[4];
+                float inv[4];
+                Pack4 acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = i0 + q < T;
+                    uint2 m = make_uint2(0u, 0u);
+                    if (ok) m = lds64(meta_s + (uint32_t)(i0 + q) * 8u);
+                    mx[q] = m.x;
+                    inv[q] = __uint_as_float(m.y);  // 0 for unobservable rows -> output 0
+                    // the separate W(h) self term (the CSR row holds the 84-diagonal a second time)
+                    acc[q] = lds_pk(ok ? tile_lane + (uint32_t)(i0 + q) * (HS * 4) : zero_row);
+                }
+                gather4<HS>(tile_lane, col_s, T, mx, acc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 a = unpack(acc[q]);
+                    float res[4] = {(a.x + bias2.x) * inv[q], (a.y + bias2.y) * inv[q], (a.z + bias2.z) * inv[q],
+                                    (a.w + bias2.w) * inv[q]};
+                    const int rr = r + q;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        float t = fmaxf(res[v], 0.f);
+                        if (DROP == DROP_PHILOX) {
+                            const uint32_t bits =
+                                (uint32_t)(((rr < 4 ? rlo[v] : rhi[v]) >> ((rr & 3) * 16)) & 0xffffull);
+                            t = (bits >= thresh) ? t * dscale : 0.f;
+                        }
+                        res[v] = t;
                     }
-                    store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
+                    const bool live = (i0 + q < T) && col_ok;
+                    const uint32_t off = (uint32_t)(i0 + q) * (uint32_t)H;
+                    if (DROP == DROP_MASK) {
+                        if (live) {
+                            const float* m = mask_lane + off;
+#pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                if (c_lane + v < H) res[v] *= m[v];
+                        }
+                    }
+                    if (live) store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
+                    if (write_act) {  // CTA-uniform: the 4 ballots of this step are the 4 words of (sb, sl, rr)
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const uint32_t bal = __ballot_sync(GPT_FULL_MASK, live && res[v] > 0.f);
+                            if (lane == v) w = bal;
+                        }
+                        if (lane < 4) act_blk[rr * 4 + lane] = w;
+                    }
                 }
             }
         }
+        __syncthreads();  // everyone is done with this buffer before the next iteration refills it
     }
 }
 
-template <int LPR, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads) aggregate_bwd_kernel(const AggParams p) {
+template <int LPR, int NT, bool ALIGNED>
+__global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = kWarps * RPW;
+    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW;
     const int T = p.T, H = p.H;
-    const int b = blockIdx.y, col0 = blockIdx.x * HS;
-    const Smem s = carve(smem_f, T, LPR);
+    const int b = blockIdx.y;
+    const int nsl = (H + HS - 1) / HS;
+    const size_t tile_stride = tile_floats(T, LPR);
+    const bool use_act = (p.act_in != nullptr) && (LPR == 8);
+    const int nactw = (int)act_words(T);
+    float* red = smem_f + (size_t)p.nbuf * tile_stride;  // [GROUPS][HS]
+    uint32_t* actw = reinterpret_cast<uint32_t*>(red + GROUPS * HS);  // [nbuf][nactw] when use_act
+    uint2* meta = reinterpret_cast<uint2*>(actw + (use_act ? (size_t)p.nbuf * nactw : 0));
+    unsigned short* colv = reinterpret_cast<unsigned short*>(meta + T);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // ---- stage g = gout * dropscale * [out > 0] / denom --------------------------------------------------------
+    const uint32_t tile_s0 = smem_u32(smem_f), tile_bytes = (uint32_t)tile_stride * 4u;
+    const uint32_t actw_s0 = smem_u32(actw);
     const size_t base = (size_t)b * T * H;
     const float* gb = p.y + base;
-    const float* ob = p.aux + base;
-    const float* mb = p.drop_mask ? p.drop_mask + base : nullptr;
-    const float* dnb = p.denom + (size_t)b * T;
-    if (ALIGNED) {
-        const uint32_t tile_s = smem_u32(s.tile);
-        const float ds = p.drop_scale;
-#pragma unroll 4
-        for (int q = tid; q < T * LPR; q += kThreads) {
-            const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < H) {
-                const uint32_t off = (uint32_t)row * (uint32_t)H + (uint32_t)c;
-                const float4 go = *reinterpret_cast<const float4*>(gb + off);
-                const float4 o = *reinterpret_cast<const float4*>(ob + off);
-                float4 m = make_float4(ds, ds, ds, ds);
-                if (mb) m = *reinterpret_cast<const float4*>(mb + off);
-                const float inv = __frcp_rn(dnb[row]);
-                g.x = o.x > 0.f ? go.x * m.x * inv : 0.f;
-                g.y = o.y > 0.f ? go.y * m.y * inv : 0.f;
-                g.z = o.z > 0.f ? go.z * m.z * inv : 0.f;
-                g.w = o.w > 0.f ? go.w * m.w * inv : 0.f;
-            }
-            sts128(tile_s + (uint32_t)(row * HS + cc) * 4u, g);
-        }
-    } else {
-        for (int q = tid; q < T * HS; q += kThreads) {
-            const int row = q / HS, cc = q % HS, c = col0 + cc;
-            float g = 0.f;
-            if (c < H) {
-                const size_t off = (size_t)row * H + c;
-                const float m = mb ? mb[off] : p.drop_scale;
-                g = ob[off] > 0.f ? gb[off] * m * __frcp_rn(dnb[row]) : 0.f;
-            }
-            s.tile[q] = g;
-        }
-    }
-    stage_meta<false>(p, b, s, HS);
-    __syncthreads();
 
-    // ---- dy_j = g_j + sum_{i in row j} g_i ; column sums for dbias ---------------------------------------------
-    const int cl = (lane % LPR) * 4, c_lane = col0 + cl, sub = lane / LPR;
-    const bool col_ok = c_lane < H;
-    const uint32_t tile_lane = smem_u32(s.tile) + (uint32_t)cl * 4u;
-    const uint32_t meta_s = smem_u32(s.meta), col_s = smem_u32(s.col);
-    const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
-    float* const out_lane = p.out + base + c_lane;
-    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int jb = warp * RPW * 2; jb < T; jb += GROUPS * 2) {   // warp-uniform
-        const int j0 = jb + sub * 2, j1 = j0 + 1;
-        const bool v0 = j0 < T, v1 = j1 < T;
-        unsigned m0 = 0u, m1 = 0u;
-        if (v0) m0 = lds64(meta_s + (uint32_t)j0 * 8u).x;
-        if (v1) m1 = lds64(meta_s + (uint32_t)j1 * 8u).x;
-        float4 acc0 = lds128(v0 ? tile_lane + (uint32_t)j0 * (HS * 4) : zero_row);
-        float4 acc1 = lds128(v1 ? tile_lane + (uint32_t)j1 * (HS * 4) : zero_row);
-        add4(csum, acc0);
-        add4(csum, acc1);
-        gather2<HS>(tile_lane, col_s, T, m0, m1, acc0, acc1);
-        const uint32_t off = (uint32_t)j0 * (uint32_t)H;
-        if (v0 && col_ok) store4<ALIGNED>(out_lane + off, acc0, c_lane, H);
-        if (v1 && col_ok) store4<ALIGNED>(out_lane + off + H, acc1, c_lane, H);
-    }
-    if (p.dbias != nullptr) {
-        __syncthreads();  // everyone is done reading the tile; reuse its head for the cross-group reduction
-        float* red = s.tile;  // [GROUPS][HS]
-        *reinterpret_cast<float4*>(red + (warp * RPW + sub) * HS + cl) = csum;
+    // the slice's activation words travel in the same cp.async group as the slice itself
+    auto issue = [&](int buf, int sl) {
+        if (use_act) {
+            for (int q = tid; q < nactw / 4; q += NT) {  // 16-byte pieces; super block q/8, piece q%8
+                const uint32_t* src = p.act_in + act_block(b, T, H, q >> 3, sl) + (q & 7) * 4;
+                cp_async16(actw_s0 + (uint32_t)(buf * nactw + q * 4) * 4u, src);
+            }
+        }
+        issue_slice<LPR, NT, ALIGNED>(gb, tile_s0 + (uint32_t)buf * tile_bytes, T, H, sl);
+    };
+    issue(0, blockIdx.x);
+    stage_meta<false, NT>(p, b, smem_f, tile_stride, meta, colv, HS);
+
+    const int cl = (lane % LPR) * 4, sub = lane / LPR;
+    const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv);
+    const float ds = p.drop_scale;
+
+    int it = 0;
+    for (int sl = blockIdx.x; sl < nsl; sl += gridDim.x, ++it) {
+        const int nxt = sl + gridDim.x;
+        if (nxt < nsl) {
+            issue((it + 1) & 1, nxt);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        for (int c = tid; c < HS; c += kThreads) {
-            float sum = 0.f;
+
+        // ---- in place: g = gout * dropscale * [out > 0] / denom ------------------------------------------------
+        const int col0 = sl * HS;
+        const uint32_t tile_s = tile_s0 + (uint32_t)(it & 1) * tile_bytes;
+        const uint32_t actw_s = actw_s0 + (uint32_t)((it & 1) * nactw) * 4u;
+#pragma unroll 2
+        for (int q = tid; q < T * LPR; q += NT) {
+            const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
+            if (c >= H) continue;  // already zero-filled
+            const uint32_t a = tile_s + (uint32_t)(row * HS + cc) * 4u;
+            float4 g = lds128(a);
+            const float inv = __uint_as_float(lds64(meta_s + (uint32_t)row * 8u).y);
+            float f[4];
+            if (use_act) {
+                const uint4 w = lds128u(actw_s + (uint32_t)(((row >> 5) * 32 + (row & 7) * 4) * 4));
+                const int bit = ((row & 31) >> 3) * 8 + (cc >> 2);
+                f[0] = (float)((w.x >> bit) & 1u); f[1] = (float)((w.y >> bit) & 1u);
+                f[2] = (float)((w.z >> bit) & 1u); f[3] = (float)((w.w >> bit) & 1u);
+            } else {
+                const size_t off = base + (size_t)row * H + c;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) f[v] = (c + v < H && p.aux[off + v] > 0.f) ? 1.f : 0.f;
+            }
+            if (p.drop_mask != nullptr) {
+                const size_t off = base + (size_t)row * H + c;
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (c + v < H) f[v] *= p.drop_mask[off + v];
+            } else {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) f[v] *= ds;
+            }
+            g.x = g.x * f[0] * inv;  // same association order on every path: (gout * m) * inv
+            g.y = g.y * f[1] * inv;
+            g.z = g.z * f[2] * inv;
+            g.w = g.w * f[3] * inv;
+            sts128(a, g);
+        }
+        __syncthreads();
+
+        // ---- dy_j = g_j + sum_{i in row j} g_i ; column sums for dbias -------------------------------------------
+        const int c_lane = col0 + cl;
+        const bool col_ok = c_lane < H;
+        const uint32_t tile_lane = tile_s + (uint32_t)cl * 4u;
+        const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
+        float* const out_lane = p.out + base + c_lane;
+        Pack4 csum;
+        csum.lo = 0ull;
+        csum.hi = 0ull;
+        for (int jb = warp * RPW * 4; jb < T; jb += GROUPS * 4) {  // warp-uniform
+            const int j0 = jb + sub * 4;
+            unsigned mx[4];
+            Pack4 acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = j0 + q < T;
+                mx[q] = ok ? lds64(meta_s + (uint32_t)(j0 + q) * 8u).x : 0u;
+                acc[q] = lds_pk(ok ? tile_lane + (uint32_t)(j0 + q) * (HS * 4) : zero_row);
+                add_pk(csum, acc[q]);
+            }
+            gather4<HS>(tile_lane, col_s, T, mx, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j0 + q < T && col_ok)
+                    store4<ALIGNED>(out_lane + (uint32_t)(j0 + q) * (uint32_t)H, unpack(acc[q]), c_lane, H);
+        }
+        if (p.dbias != nullptr) *reinterpret_cast<float4*>(red + (warp * RPW + sub) * HS + cl) = unpack(csum);
+        __syncthreads();  // tile buffer free for the refill; red[] complete
+        if (p.dbias != nullptr) {
+            // red[] is rewritten only after the two barriers of the next iteration, so this read is safe
+            for (int c = tid; c < HS; c += NT) {
+                float sum = 0.f;
 #pragma unroll 8
-            for (int g = 0; g < GROUPS; ++g) sum += red[g * HS + c];
-            if (col0 + c < H) atomicAdd(p.dbias + col0 + c, 2.0f * sum);  // the bias enters the layer twice
+                for (int g = 0; g < GROUPS; ++g) sum += red[g * HS + c];
+                if (col0 + c < H) atomicAdd(p.dbias + col0 + c, 2.0f * sum);  // the bias enters the layer twice
+            }
         }
     }
 }
 
-// widest slice that still leaves >= 3 CTAs per SM and fills the machine at least ~2 waves
-int pick_lpr(int B, int T, int H, int force_vec) {
-    if (force_vec == 1) return 8;
-    if (force_vec == 2) return 16;
-    if (force_vec == 4) return 32;
-    for (int lpr = 32; lpr >= 8; lpr >>= 1) {
-        if (agg_smem_bytes(T, lpr) > 74 * 1024) continue;  // 3 CTAs per SM
-        const long slices = (H + 4 * lpr - 1) / (4 * lpr);
-        if (lpr > 8 && slices * B < 2 * 148) continue;
-        return lpr;
+// ---- host-side configuration ---------------------------------------------------------------------------------
+
+struct AggConfig {
+    int lpr, nt, nbuf, grid_x;
+    size_t smem;
+};
+
+// Small sentence tiles: one slice per CTA, many CTAs per SM overlap each other's load / gather / store phases.
+// Large tiles (< 4 CTAs would fit an SM): 512-thread persistent CTA, narrowest slice, double buffered.
+AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
+    const int T = p.T, H = p.H, B = p.B;
+    const bool act = fwd ? (p.act_out != nullptr) : (p.act_in != nullptr);  // bit layout is tied to LPR = 8
+    AggConfig c{};
+    auto slices = [&](int lpr) { return (H + 4 * lpr - 1) / (4 * lpr); };
+    auto bytes = [&](int lpr, int nt, int nbuf) {
+        return agg_smem_bytes(T, lpr, nbuf, fwd ? 0 : (nt / 32) * (32 / lpr), !fwd && act && lpr == 8,
+                              fwd ? slices(lpr) * 4 * lpr : 0);
+    };
+    if (force_vec == 1 || ((force_vec == 2 || force_vec == 4) && !act)) {
+        c.lpr = 8 * force_vec; c.nt = 256; c.nbuf = 1; c.grid_x = slices(c.lpr);
+        c.smem = bytes(c.lpr, 256, 1);
+        if (c.smem <= 224 * 1024) return c;
     }
-    return 8;
+    for (int lpr = act ? 8 : 32; lpr >= 8; lpr >>= 1) {
+        const size_t smem = bytes(lpr, 256, 1);
+        if (smem > 54 * 1024) continue;                       // want >= 4 CTAs per SM
+        if (lpr > 8 && (long)slices(lpr) * B < 2 * 148) continue;  // and enough CTAs to fill the machine
+        c.lpr = lpr; c.nt = 256; c.nbuf = 1; c.grid_x = slices(lpr); c.smem = smem;
+        return c;
+    }
+    c.lpr = 8; c.nt = 512;
+    const int nsl = slices(8);
+    int split = (2 * 148 + B - 1) / B;                         // CTAs per sentence needed to fill the machine
+    if (const char* e = getenv("GPT_AGG_SPLIT")) split = atoi(e);  // tuning knob (tools/agg_bench.py)
+    split = split < 1 ? 1 : (split > nsl ? nsl : split);
+    c.grid_x = split;
+    c.nbuf = (split < nsl) ? 2 : 1;
+    c.smem = bytes(8, 512, c.nbuf);
+    if (c.smem > 224 * 1024 && c.nbuf == 2) {                  // cannot double buffer: one slice per CTA
+        c.nbuf = 1; c.grid_x = nsl;
+        c.smem = bytes(8, 512, 1);
+    }
+    return c;
 }
 
 template <typename K>
@@ -373,54 +518,53 @@ int ensure_smem(K kernel, size_t bytes) {
     return GPT_OK;
 }
 
-template <int LPR, bool ALIGNED>
-int launch(bool fwd, const AggParams& p, cudaStream_t st) {
-    const size_t smem = agg_smem_bytes(p.T, LPR);
-    if (smem > 224 * 1024) return GPT_ERR_UNSUPPORTED;
-    dim3 grid((p.H + 4 * LPR - 1) / (4 * LPR), p.B);
-    int rc;
-    if (fwd) {
-        if (p.drop_mask != nullptr) {
-            if ((rc = ensure_smem(aggregate_fwd_kernel<LPR, ALIGNED, DROP_MASK>, smem)) != GPT_OK) return rc;
-            aggregate_fwd_kernel<LPR, ALIGNED, DROP_MASK><<<grid, kThreads, smem, st>>>(p);
-        } else if (p.rng != nullptr && p.thresh16 > 0) {
-            if ((rc = ensure_smem(aggregate_fwd_kernel<LPR, ALIGNED, DROP_PHILOX>, smem)) != GPT_OK) return rc;
-            aggregate_fwd_kernel<LPR, ALIGNED, DROP_PHILOX><<<grid, kThreads, smem, st>>>(p);
-        } else {
-            if ((rc = ensure_smem(aggregate_fwd_kernel<LPR, ALIGNED, DROP_NONE>, smem)) != GPT_OK) return rc;
-            aggregate_fwd_kernel<LPR, ALIGNED, DROP_NONE><<<grid, kThreads, smem, st>>>(p);
-        }
-    } else {
-        if ((rc = ensure_smem(aggregate_bwd_kernel<LPR, ALIGNED>, smem)) != GPT_OK) return rc;
-        aggregate_bwd_kernel<LPR, ALIGNED><<<grid, kThreads, smem, st>>>(p);
-    }
+template <typename K>
+int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, cudaStream_t st) {
+    int rc = ensure_smem(kernel, c.smem);
+    if (rc != GPT_OK) return rc;
+    kernel<<<dim3(c.grid_x, p.B), c.nt, c.smem, st>>>(p);
     return gpt_launch_status();
 }
 
-int dispatch(bool fwd, const AggParams& p, int force_vec, cudaStream_t st) {
+template <int LPR, int NT, bool ALIGNED>
+int launch(bool fwd, const AggConfig& c, const AggParams& p, cudaStream_t st) {
+    if (!fwd) return launch_kernel(aggregate_bwd_kernel<LPR, NT, ALIGNED>, c, p, st);
+    if (p.drop_mask != nullptr) return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_MASK>, c, p, st);
+    if (p.rng != nullptr && p.thresh16 > 0)
+        return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_PHILOX>, c, p, st);
+    return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_NONE>, c, p, st);
+}
+
+int dispatch(bool fwd, AggParams& p, int force_vec, cudaStream_t st) {
     if (4 * p.T + 2 > 65535) return GPT_ERR_UNSUPPORTED;  // 16-bit CSR indices / row lengths in shared memory
     const bool aligned = (p.H % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                         (p.aux == nullptr || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) &&
-                         (p.drop_mask == nullptr || (reinterpret_cast<uintptr_t>(p.drop_mask) & 15) == 0);
-    int lpr = pick_lpr(p.B, p.T, p.H, force_vec);
-    while (lpr > 8 && agg_smem_bytes(p.T, lpr) > 224 * 1024) lpr >>= 1;
+                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const AggConfig c = pick_config(p, fwd, force_vec);
+    if (c.smem > 224 * 1024) return GPT_ERR_UNSUPPORTED;
+    p.nbuf = c.nbuf;
+    if (c.nt == 512) return aligned ? launch<8, 512, true>(fwd, c, p, st) : launch<8, 512, false>(fwd, c, p, st);
     if (aligned) {
-        if (lpr == 32) return launch<32, true>(fwd, p, st);
-        if (lpr == 16) return launch<16, true>(fwd, p, st);
-        return launch<8, true>(fwd, p, st);
+        if (c.lpr == 32) return launch<32, 256, true>(fwd, c, p, st);
+        if (c.lpr == 16) return launch<16, 256, true>(fwd, c, p, st);
+        return launch<8, 256, true>(fwd, c, p, st);
     }
-    if (lpr == 32) return launch<32, false>(fwd, p, st);
-    if (lpr == 16) return launch<16, false>(fwd, p, st);
-    return launch<8, false>(fwd, p, st);
+    if (c.lpr == 32) return launch<32, 256, false>(fwd, c, p, st);
+    if (c.lpr == 16) return launch<16, 256, false>(fwd, c, p, st);
+    return launch<8, 256, false>(fwd, c, p, st);
+}
+
+void set_dropout(AggParams& p, float drop_p) {
+    unsigned th = (unsigned)(drop_p * 65536.0f + 0.5f);
+    p.thresh16 = th > 65535u ? 65535u : th;
+    p.drop_scale = (p.thresh16 > 0) ? 65536.0f / (65536.0f - (float)p.thresh16) : 1.0f;
 }
 
 }  // namespace
 
 extern "C" int gpt_gcn_aggregate_fwd(const float* y, const int32_t* rowptr, const int32_t* col, const float* denom,
-                                     const uint8_t* flags, const float* bias, float* out, int B, int T, int H,
-                                     int use_adj, float drop_p, const uint64_t* rng_state, uint32_t subseq,
-                                     const float* drop_mask, int force_vec, void* stream) {
+                                     const uint8_t* flags, const float* bias, float* out, uint32_t* act_mask, int B,
+                                     int T, int H, int use_adj, float drop_p, const uint64_t* rng_state,
+                                     uint32_t subseq, const float* drop_mask, int force_vec, void* stream) {
     GPT_CHECK_ARG(y && rowptr && col && denom && flags && bias && out);
     GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && H < (1 << 20) && drop_p >= 0.f && drop_p < 1.f);
     GPT_CHECK_ARG(!(drop_p > 0.f && rng_state == nullptr));  // dropout needs the device-side {seed, step}
@@ -428,30 +572,29 @@ extern "C" int gpt_gcn_aggregate_fwd(const float* y, const int32_t* rowptr, cons
     if (B > 65535) return GPT_ERR_UNSUPPORTED;
     AggParams p{};
     p.y = y; p.rowptr = rowptr; p.col = col; p.denom = denom; p.flags = flags; p.bias = bias; p.out = out;
+    p.act_out = act_mask;
     p.drop_mask = drop_mask;
     p.rng = (drop_p > 0.f) ? reinterpret_cast<const unsigned long long*>(rng_state) : nullptr;
     p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
     p.subseq = subseq & 0xfffu;
-    unsigned th = (unsigned)(drop_p * 65536.0f + 0.5f);
-    p.thresh16 = th > 65535u ? 65535u : th;
-    p.drop_scale = (p.thresh16 > 0) ? 65536.0f / (65536.0f - (float)p.thresh16) : 1.0f;
+    set_dropout(p, drop_p);
     return dispatch(true, p, force_vec, (cudaStream_t)stream);
 }
 
-extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const int32_t* rowptr, const int32_t* col,
-                                     const float* denom, float* dy, float* dbias, int B, int T, int H, int use_adj,
-                                     float drop_p, const float* drop_mask, int force_vec, void* stream) {
-    GPT_CHECK_ARG(gout && out && rowptr && col && denom && dy);
+extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* act_mask,
+                                     const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
+                                     float* dbias, int B, int T, int H, int use_adj, float drop_p,
+                                     const float* drop_mask, int force_vec, void* stream) {
+    GPT_CHECK_ARG(gout && (out || act_mask) && rowptr && col && denom && dy);
     GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && drop_p >= 0.f && drop_p < 1.f);
     if (B == 0) return GPT_OK;
     if (B > 65535) return GPT_ERR_UNSUPPORTED;
     AggParams p{};
-    p.y = gout; p.aux = out; p.rowptr = rowptr; p.col = col; p.denom = denom; p.out = dy; p.dbias = dbias;
+    p.y = gout; p.aux = out; p.act_in = act_mask; p.rowptr = rowptr; p.col = col; p.denom = denom; p.out = dy;
+    p.dbias = dbias;
     p.drop_mask = drop_mask;
     p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
-    unsigned th = (unsigned)(drop_p * 65536.0f + 0.5f);
-    th = th > 65535u ? 65535u : th;
-    // same scale the forward applied to kept elements (dropped ones have out == 0 and are masked by [out > 0])
-    p.drop_scale = (th > 0 && drop_mask == nullptr) ? 65536.0f / (65536.0f - (float)th) : 1.0f;
+    // same scale the forward applied to kept elements (dropped ones have out == 0 / a clear activation bit)
+    set_dropout(p, drop_mask == nullptr ? drop_p : 0.f);
     return dispatch(false, p, force_vec, (cudaStream_t)stream);
 }

@@ -154,24 +154,29 @@ def linear_wgrad(dy, x2d, mode='fp32'):
 
 # ---- K2: aggregation -----------------------------------------------------------------------------------------
 
-def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq=0, drop_mask=None, force_vec=0):
+def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq=0, drop_mask=None, force_vec=0,
+                  want_act=False):
+    """K2 forward; with want_act also returns the 1-bit-per-element activation mask the backward can read."""
     B, T = csr.B, csr.T
     H = y.shape[-1]
     out = torch.empty((B, T, H), dtype=torch.float32, device=y.device)
+    act = torch.empty((B * ((T + 31) // 32) * ((H + 31) // 32) * 32,), dtype=torch.int32,
+                      device=y.device) if want_act else None
     _call('gpt_gcn_aggregate_fwd', _ptr(y), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
-          _ptr(csr.flags), _ptr(bias), _ptr(out), B, T, H, int(bool(use_adj)),
+          _ptr(csr.flags), _ptr(bias), _ptr(out), _ptr(act), B, T, H, int(bool(use_adj)),
           float(drop_p), _ptr(rng_state), int(subseq), _ptr(drop_mask), int(force_vec), _stream())
-    return out
+    return (out, act) if want_act else out
 
 
-def aggregate_bwd(gout, out, csr, use_adj=True, drop_p=0.0, drop_mask=None, want_dbias=True, force_vec=0):
+def aggregate_bwd(gout, out, csr, use_adj=True, drop_p=0.0, drop_mask=None, want_dbias=True, force_vec=0, act=None):
+    """K2 backward; [out > 0] is taken from ``act`` (bit mask) when given, else from ``out``."""
     B, T = csr.B, csr.T
-    H = out.shape[-1]
-    dy = torch.empty((B * T, H), dtype=torch.float32, device=out.device)
-    dbias = torch.zeros((H,), dtype=torch.float32, device=out.device) if want_dbias else None
-    _call('gpt_gcn_aggregate_bwd', _ptr(gout), _ptr(out), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
-          _ptr(dy), _ptr(dbias), B, T, H, int(bool(use_adj)), float(drop_p), _ptr(drop_mask), int(force_vec),
-          _stream())
+    H = gout.shape[-1]
+    dy = torch.empty((B * T, H), dtype=torch.float32, device=gout.device)
+    dbias = torch.zeros((H,), dtype=torch.float32, device=gout.device) if want_dbias else None
+    _call('gpt_gcn_aggregate_bwd', _ptr(gout), _ptr(out), _ptr(act), _ptr(csr.rowptr), _ptr(csr.col),
+          _ptr(csr.denom), _ptr(dy), _ptr(dbias), B, T, H, int(bool(use_adj)), float(drop_p), _ptr(drop_mask),
+          int(force_vec), _stream())
     return dy, dbias
 
 
@@ -187,19 +192,20 @@ class _GcnLayer(torch.autograd.Function):
             drop_mask = _dev(drop_mask, torch.float32, 'drop_mask')
         B, T, K = x.shape
         y = linear_fwd(x.view(B * T, K), weight, gemm_mode)
-        out = aggregate_fwd(y, csr, bias, use_adj, drop_p if drop_mask is None else 0.0, rng_state, subseq, drop_mask)
+        out, act = aggregate_fwd(y, csr, bias, use_adj, drop_p if drop_mask is None else 0.0, rng_state, subseq,
+                                 drop_mask, want_act=True)
         ctx.csr, ctx.use_adj, ctx.gemm_mode = csr, use_adj, gemm_mode
         ctx.drop_p = drop_p if drop_mask is None else 0.0
-        ctx.save_for_backward(x, weight, out, drop_mask)
+        ctx.save_for_backward(x, weight, act, drop_mask)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, weight, out, drop_mask = ctx.saved_tensors
+        x, weight, act, drop_mask = ctx.saved_tensors
         B, T, K = x.shape
         gout = _dev(gout, torch.float32, 'grad_out')
-        dy, dbias = aggregate_bwd(gout, out, ctx.csr, ctx.use_adj, ctx.drop_p, drop_mask,
-                                  want_dbias=ctx.needs_input_grad[2])
+        dy, dbias = aggregate_bwd(gout, None, ctx.csr, ctx.use_adj, ctx.drop_p, drop_mask,
+                                  want_dbias=ctx.needs_input_grad[2], act=act)
         dx = linear_dgrad(dy, weight, ctx.gemm_mode).view(B, T, K) if ctx.needs_input_grad[0] else None
         dw = linear_wgrad(dy, x.view(B * T, K), ctx.gemm_mode) if ctx.needs_input_grad[1] else None
         return dx, dw, dbias, None, None, None, None, None, None, None

@@ -73,20 +73,24 @@ int gpt_prune_csr(const int64_t* head, const int64_t* subj_pos, const int64_t* o
 /* K2 forward. One GCN layer after the projection y = h W^T (model/gcn.py:269-271, 390-393):
  *     out_i = dropout(relu((sum_{j in row i} y_j + y_i + 2*bias) / denom_i)); rows with flags == 0 are written 0.
  * use_adj = 0 is the --no_adj ablation (model/gcn.py:264-265).
+ * act_mask (optional, uint32 [B * ceil(T/32) * ceil(H/32) * 32]): one bit per element, set where out > 0, for the
+ * backward.  Element (b, row, col) lives in word (((b*ceil(T/32) + row/32)*ceil(H/32) + col/32)*8 + row%8)*4 + col%4
+ * at bit ((row%32)/8)*8 + (col%32)/4.
  * Dropout: drop_p > 0 draws Philox bits in-kernel from rng_state = {seed, step} (device uint64[2]) and `subseq`
  * (layer id); or drop_mask (pre-scaled float [B*T,H], tests) multiplies the result; or neither.
- * force_vec: 0 = auto, else 1/2/4 floats per lane (slice width 32*vec). */
+ * force_vec: 0 = auto, else 1/2/4 -> slice width 32/64/128 columns, one slice per CTA. */
 int gpt_gcn_aggregate_fwd(const float* y, const int32_t* rowptr, const int32_t* col, const float* denom,
-                          const uint8_t* flags, const float* bias, float* out, int B, int T, int H, int use_adj,
-                          float drop_p, const uint64_t* rng_state, uint32_t subseq, const float* drop_mask,
-                          int force_vec, void* stream);
+                          const uint8_t* flags, const float* bias, float* out, uint32_t* act_mask, int B, int T,
+                          int H, int use_adj, float drop_p, const uint64_t* rng_state, uint32_t subseq,
+                          const float* drop_mask, int force_vec, void* stream);
 
 /* K2 backward (autograd of the lines above; the adjacency is symmetric so the same CSR is its transpose):
  *     g_i = gout_i * dropscale * [out_i > 0] / denom_i ; dy_j = g_j + sum_{i in row j} g_i ; dbias += 2*sum_i g_i
+ * [out_i > 0] is read from act_mask when it is not NULL, else from `out` (one of the two is required).
  * dbias (float [H]) is accumulated atomically and must be zeroed by the caller; may be NULL. */
-int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const int32_t* rowptr, const int32_t* col,
-                          const float* denom, float* dy, float* dbias, int B, int T, int H, int use_adj,
-                          float drop_p, const float* drop_mask, int force_vec, void* stream);
+int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* act_mask, const int32_t* rowptr,
+                          const int32_t* col, const float* denom, float* dy, float* dbias, int B, int T, int H,
+                          int use_adj, float drop_p, const float* drop_mask, int force_vec, void* stream);
 
 /* K4. three masked pools + cat (model/gcn.py:116-121, 473-483): out float [B,3H] = [h_out, subj_out, obj_out];
  * argmax int32 [B,3H] (token index or -1) is required for GPT_POOL_MAX. */

@@ -51,11 +51,17 @@ def main():
     for name, p in (('fwd', 0.0), ('fwd+dropout', 0.5)):
         t = timeit(lambda: ops.aggregate_fwd(y, csr, bias, drop_p=p, rng_state=rng, force_vec=a.vec))
         print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % (name, t, fwd_bytes / t / 1e6, 100 * fwd_bytes / t / 1e6 / peak))
-    out = ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng)
+    t = timeit(lambda: ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng, force_vec=a.vec, want_act=True))
+    fb = fwd_bytes + B * T * H // 8
+    print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % ('fwd+drop+act', t, fb / t / 1e6, 100 * fb / t / 1e6 / peak))
+    out, act = ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng, want_act=True)
     gout = torch.randn(B, T, H, device='cuda')
     bwd_bytes = 3 * B * T * H * 4 + 4 * B * (T + 1) + 4 * nnz + 4 * B * T
     t = timeit(lambda: ops.aggregate_bwd(gout, out, csr, drop_p=0.5, force_vec=a.vec), reps=6)
-    print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % ('bwd', t, bwd_bytes / t / 1e6, 100 * bwd_bytes / t / 1e6 / peak))
+    print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % ('bwd(out)', t, bwd_bytes / t / 1e6, 100 * bwd_bytes / t / 1e6 / peak))
+    bwd_bytes = 2 * B * T * H * 4 + B * T * H // 8 + 4 * B * (T + 1) + 4 * nnz + 4 * B * T
+    t = timeit(lambda: ops.aggregate_bwd(gout, None, csr, drop_p=0.5, force_vec=a.vec, act=act), reps=6)
+    print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % ('bwd(act)', t, bwd_bytes / t / 1e6, 100 * bwd_bytes / t / 1e6 / peak))
     h = out
     pool_bytes = B * T * H * 4 + B * 3 * H * 8 + B * T
     t = timeit(lambda: ops._Pool3.apply(h, csr, 0))
