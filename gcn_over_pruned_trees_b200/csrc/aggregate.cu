@@ -10,12 +10,14 @@
 //
 // Mapping.  A CTA owns one sentence and walks HS-column slices of its T projected rows (HS = 4*LPR floats).  A slice
 // [T x HS] is staged in shared memory with cp.async -- every row is read from HBM exactly once -- next to the
-// sentence's CSR (16-bit indices) and one packed {start, length, 1/denom} word per row.  LPR lanes then serve one
-// node: they gather its <= deg+1 rows out of shared memory with 128-bit loads (a warp works on 32/LPR nodes at a
-// time, two rows in flight per lane group, warp-uniform trip count, exhausted slots read a zero row: no divergent
-// control flow) and apply the epilogue.  When a sentence tile is large (few CTAs fit an SM) the CTA is persistent
-// over the sentence's slices and double-buffers them, so the next slice streams in while the current one is
-// gathered and written out; otherwise one slice per CTA and the SM overlaps many small CTAs.
+// sentence's CSR (16-bit indices), one packed {start, length, 1/denom} word per row and a permutation of the rows
+// sorted by row length.  LPR lanes serve one node: they gather its <= deg+1 rows out of shared memory with 128-bit
+// loads and packed FADD2 adds.  A warp works on 32/LPR lane groups x 4 rows in flight; the rows it takes together
+// are neighbours in the length-sorted order, so the warp-uniform trip count is close to every row's own length
+// (exhausted slots read a zero row: no divergent control flow, little padded work).  When a sentence tile is
+// large (few CTAs fit an SM) the CTA is persistent over the sentence's slices and double-buffers them, so the next
+// slice streams in while the current one is gathered and written out; otherwise one slice per CTA and the SM
+// overlaps many small CTAs.
 // HBM traffic = read y once + write out once + CSR (+ 1 bit per element of activation mask for the backward).
 //
 // Backward (adjacency is symmetric, so A^T = A and the same CSR is reused):
@@ -27,12 +29,12 @@
 
 namespace {
 
-constexpr int kRowBlock = 8;  // consecutive rows that share one Philox call per column
+constexpr int kLenBuckets = 16;  // rows are bucketed by min(length, 15) for the length-sorted order
 
 struct AggParams {
     const float* y;      // [B*T, H] projected rows (fwd) / gout (bwd)
     const float* aux;    // bwd: out of the forward pass (used when act_in == nullptr)
-    const uint32_t* act_in;   // bwd: activation bits written by the forward [B*T, ceil(H/32)]
+    const uint32_t* act_in;   // bwd: activation bits written by the forward, see act_index()
     uint32_t* act_out;        // fwd: optional activation bits
     const int* rowptr;   // [B, T+1]
     const int* col;      // [B, cap]
@@ -57,7 +59,6 @@ __device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 
 // Four fp32 lanes held as two packed f32x2 registers: the gather adds with FADD2 (2 instructions per 16 bytes).
 struct Pack4 {
@@ -87,14 +88,14 @@ __device__ __forceinline__ Pack4 lds_pk(uint32_t a) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint4 lds128u(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
@@ -107,41 +108,77 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
                  : "memory");
 }
 
-// Shared-memory carve-up (host and device agree through these helpers):
-//   tile [nbuf][T+1][HS]  staged rows; row T is all zeros (target of padded gather slots)
+// ---- shared-memory carve-up (host and device agree through Layout) -------------------------------------------
+//   tile [nbuf][T+1][HS]  staged rows; row T is all zeros (target of padded gather slots and of rows past T)
 //   red  [GROUPS][HS]     backward only: per-lane-group column sums for dbias
-//   meta [T]              .x = CSR row start | (row length << 16), .y = bits of 1/denom (0: unobservable row)
-//   col  [4T+2]           16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
-//   actw [nbuf][32*ceil(T/32)]  backward with a bit mask only: the slice's activation words
+//   bits [nbuf or 1][..]  backward: the slice's activation words (when a bit mask is given);
+//                         forward: the slice's dropout keep-words (in-kernel Philox dropout)
+//   bias [slices*HS]      forward: 2*bias for every column, zero past H
+//   meta [T+1]            .x = CSR row start | (row length << 16), .y = bits of 1/denom (0: unobservable row)
+//   perm [..]             row ids sorted by row length (longest first), padded with T
+//   col  [4T+4]           16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
+struct Layout {
+    size_t tile, red, bits, bias, meta, perm, col, total;  // byte offsets
+};
 __host__ __device__ inline size_t tile_floats(int T, int lpr) { return (size_t)(T + 1) * 4 * lpr; }
-__host__ __device__ inline size_t act_words(int T) { return (size_t)((T + 31) / 32) * 32; }
-__host__ __device__ inline size_t agg_smem_bytes(int T, int lpr, int nbuf, int red_groups, bool act_stage,
-                                                 int bias_floats) {
-    return (size_t)nbuf * tile_floats(T, lpr) * sizeof(float) + (size_t)red_groups * 4 * lpr * sizeof(float) +
-           (act_stage ? (size_t)nbuf * act_words(T) * sizeof(uint32_t) : 0) + (size_t)T * sizeof(uint2) +
-           (size_t)(4 * T + 4) * sizeof(unsigned short) + (bias_floats ? (size_t)bias_floats * 4 + 16 : 0);
+__host__ __device__ inline int perm_len(int T, int groups) {
+    return ((T + groups * 4 - 1) / (groups * 4)) * groups * 4;
+}
+__host__ __device__ inline int bits_stride(int T, int lpr) { return ((T * ((4 * lpr + 31) / 32) + 3) / 4) * 4; }
+__host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int nbuf, bool fwd, bool bits) {
+    const int groups = (nt / 32) * (32 / lpr), hs = 4 * lpr;
+    Layout L;
+    size_t o = 0;
+    L.tile = o; o += (size_t)nbuf * tile_floats(T, lpr) * 4;
+    L.red = o;  o += fwd ? 0 : (size_t)groups * hs * 4;
+    L.bits = o; o += bits ? (size_t)(fwd ? 1 : nbuf) * bits_stride(T, lpr) * 4 : 0;
+    L.bias = o; o += fwd ? (size_t)((H + hs - 1) / hs) * hs * 4 : 0;
+    L.meta = o; o += (size_t)((T + 2) / 2 * 2) * 8;
+    L.perm = o; o += (size_t)perm_len(T, groups) * 2;
+    o = (o + 3) / 4 * 4;
+    L.col = o;  o += (size_t)(4 * T + 4) * 2;
+    L.total = (o + 15) / 16 * 16;
+    return L;
 }
 
-// Stage the sentence's CSR (16-bit) and the per-row {start, length, 1/denom} words; zero the pad rows.
+// Stage the sentence's CSR (16-bit), the per-row {start, length, 1/denom} words and the length-sorted row order;
+// zero the pad rows.  Block-wide (contains barriers).
 template <bool FWD, int NT>
 __device__ __forceinline__ void stage_meta(const AggParams& p, int b, float* tile0, size_t tile_stride, uint2* meta,
-                                           unsigned short* colv, int HS) {
+                                           unsigned short* perm, int nperm, unsigned short* colv, int HS) {
+    __shared__ int hist[kLenBuckets];
     const int T = p.T;
     const int* rp = p.rowptr + (size_t)b * (T + 1);
     const int nnz = p.use_adj ? min(rp[T], p.cap) : 0;
     const int* cb = p.col + (size_t)b * p.cap;
+    if (threadIdx.x < kLenBuckets) hist[threadIdx.x] = 0;
     for (int e = threadIdx.x; e < nnz; e += NT) colv[e] = (unsigned short)cb[e];
+    for (int c = threadIdx.x; c < HS * p.nbuf; c += NT)
+        tile0[(size_t)(c / HS) * tile_stride + (size_t)T * HS + (c % HS)] = 0.f;
+    for (int t = T + threadIdx.x; t < nperm; t += NT) perm[t] = (unsigned short)T;
+    if (threadIdx.x == 0) meta[T] = make_uint2(0u, 0u);  // rows past T: empty, unobservable
+    __syncthreads();
     for (int t = threadIdx.x; t < T; t += NT) {
         const int st = rp[t], len = p.use_adj ? rp[t + 1] - st : 0;
         float inv = __frcp_rn(p.denom[(size_t)b * T + t]);
         if (FWD && p.flags[(size_t)b * T + t] == 0) inv = 0.f;  // unobservable row (not in tree, not an entity)
         meta[t] = make_uint2((unsigned)st | ((unsigned)len << 16), __float_as_uint(inv));
+        atomicAdd(&hist[kLenBuckets - 1 - min(len, kLenBuckets - 1)], 1);  // longest rows first
     }
-    for (int c = threadIdx.x; c < HS * p.nbuf; c += NT)
-        tile0[(size_t)(c / HS) * tile_stride + (size_t)T * HS + (c % HS)] = 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < kLenBuckets; ++k) { const int n = hist[k]; hist[k] = run; run += n; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += NT) {
+        const int len = (int)(meta[t].x >> 16);
+        perm[atomicAdd(&hist[kLenBuckets - 1 - min(len, kLenBuckets - 1)], 1)] = (unsigned short)t;
+    }
+    // (the caller's first barrier publishes perm / meta / col)
 }
 
-// Issue the asynchronous copy of slice `sl` of src[b] into a tile buffer (one commit group per call).
+// Issue the asynchronous copy of slice `sl` of src[b] into a tile buffer (caller commits the group).
 template <int LPR, int NT, bool ALIGNED>
 __device__ __forceinline__ void issue_slice(const float* __restrict__ src_b, uint32_t tile_s, int T, int H, int sl) {
     constexpr int HS = 4 * LPR;
@@ -161,11 +198,10 @@ __device__ __forceinline__ void issue_slice(const float* __restrict__ src_b, uin
             else asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(0.f) : "memory");
         }
     }
-    cp_async_commit();
 }
 
 // acc[q] += the rows listed in CSR row q, four rows in flight per lane group.  The trip count is warp-uniform (max
-// row length in the warp), exhausted slots select the zero row, so the loop has no divergent control flow:
+// row length in the warp; rows taken together have nearly equal lengths), exhausted slots select the zero row:
 //   per chain and trip: LDS.U16, ISETP+SEL, IMAD, LDS.128, 2 FADD2.
 template <int HS>
 __device__ __forceinline__ void gather4(uint32_t tile_lane, uint32_t col_s, int T, const unsigned (&m)[4],
@@ -199,179 +235,189 @@ __device__ __forceinline__ void store4(float* dst, const float4 v, int c, int H)
     }
 }
 
-// Activation-bit layout (fwd writes, bwd reads; both use the LPR = 8 kernels, whose warp instruction covers 4 rows
-// x 32 columns): for sentence b, 32-row super block sb = row/32, 32-column slice sl = col/32,
-//   word  = (((b * ceil(T/32) + sb) * ceil(H/32) + sl) * 8 + row % 8) * 4 + col % 4
-//   bit   = ((row % 32) / 8) * 8 + (col % 32) / 4          (= the lane that owns the element in the forward)
-// so the four words of one (sb, sl, row % 8) are the four ballots of one forward step: one 16-byte store.
-__host__ __device__ inline size_t act_block(int b, int T, int H, int sb, int sl) {
-    return (((size_t)b * ((T + 31) / 32) + sb) * ((H + 31) / 32) + sl) * 32;
+// Activation-bit layout (fwd writes, bwd reads; LPR = 8 kernels only): one 32-bit word per (sentence, 32-column
+// slice, row), bit k <-> column 32*slice + k:   word index = (b * ceil(H/32) + slice) * T + row.
+__host__ __device__ inline size_t act_index(int b, int T, int H, int sl) {
+    return ((size_t)b * ((H + 31) / 32) + sl) * T;
 }
 
 enum { DROP_NONE = 0, DROP_PHILOX = 1, DROP_MASK = 2 };
 
 template <int LPR, int NT, bool ALIGNED, int DROP>
 __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
-    extern __shared__ __align__(16) float smem_f[];
-    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW, WPR = (HS + 31) / 32;
     const int T = p.T, H = p.H;
     const int b = blockIdx.y;
     const int nsl = (H + HS - 1) / HS;
+    const bool write_act = (p.act_out != nullptr) && (LPR == 8);
+    const Layout L = make_layout(T, H, LPR, NT, p.nbuf, true, DROP == DROP_PHILOX);
+    float* tile0 = reinterpret_cast<float*>(smem_raw + L.tile);
+    uint32_t* keepw = reinterpret_cast<uint32_t*>(smem_raw + L.bits);
+    float* bias_sm = reinterpret_cast<float*>(smem_raw + L.bias);
+    uint2* meta = reinterpret_cast<uint2*>(smem_raw + L.meta);
+    unsigned short* perm = reinterpret_cast<unsigned short*>(smem_raw + L.perm);
+    unsigned short* colv = reinterpret_cast<unsigned short*>(smem_raw + L.col);
     const size_t tile_stride = tile_floats(T, LPR);
-    uint2* meta = reinterpret_cast<uint2*>(smem_f + (size_t)p.nbuf * tile_stride);
-    unsigned short* colv = reinterpret_cast<unsigned short*>(meta + T);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile_s0 = smem_u32(smem_f), tile_bytes = (uint32_t)tile_stride * 4u;
+    const uint32_t tile_s0 = smem_u32(tile0), tile_bytes = (uint32_t)tile_stride * 4u;
     const float* yb = p.y + (size_t)b * T * H;
 
     issue_slice<LPR, NT, ALIGNED>(yb, tile_s0, T, H, blockIdx.x);
-    stage_meta<true, NT>(p, b, smem_f, tile_stride, meta, colv, HS);
-    // 2*bias for every slice this CTA will visit (the bias enters the layer twice), zero past H
-    float* bias_sm = reinterpret_cast<float*>(colv + 4 * T + 2 + ((4 * T + 2) & 1));
-    bias_sm += (4 - ((reinterpret_cast<uintptr_t>(bias_sm) >> 2) & 3)) & 3;  // 16-byte aligned
+    cp_async_commit();
+    stage_meta<true, NT>(p, b, tile0, tile_stride, meta, perm, perm_len(T, GROUPS), colv, HS);
     for (int c = threadIdx.x; c < nsl * HS; c += NT) bias_sm[c] = (c < H) ? 2.0f * p.bias[c] : 0.f;
-    const uint32_t bias_s = smem_u32(bias_sm);
 
     // ---- per-thread constants ---------------------------------------------------------------------------------
     const int cl = (lane % LPR) * 4, sub = lane / LPR;
     unsigned long long seed = 0, step = 0;
     if (DROP == DROP_PHILOX) { seed = p.rng[0]; step = p.rng[1]; }
-    const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv);
+    const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv), perm_s = smem_u32(perm);
+    const uint32_t bias_s = smem_u32(bias_sm), keep_s = smem_u32(keepw);
     const unsigned thresh = p.thresh16;
     const float dscale = p.drop_scale;
-    const bool write_act = (p.act_out != nullptr) && (LPR == 8);
 
     int it = 0;
     for (int sl = blockIdx.x; sl < nsl; sl += gridDim.x, ++it) {
         const int nxt = sl + gridDim.x;
+        const int col0 = sl * HS;
         if (nxt < nsl) {  // stream the next slice into the other buffer while this one is processed
             issue_slice<LPR, NT, ALIGNED>(yb, tile_s0 + (uint32_t)((it + 1) & 1) * tile_bytes, T, H, nxt);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+            cp_async_commit();
         }
+        if (DROP == DROP_PHILOX) {
+            // Dropout keep-words of this slice (one bit per element), drawn while the slice is still in flight.
+            // One Philox call = 8 rows x 1 column x 16 bits; the stream depends only on
+            // (seed, step, layer, sentence, row, column), never on the tiling.
+            for (int blk = warp; blk * 8 < T; blk += NT / 32) {
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    const int c = col0 + w * 32 + lane;
+                    const Philox4 q = philox4x32((uint32_t)c | (p.subseq << 20), (uint32_t)blk, (uint32_t)b,
+                                                 (uint32_t)step, (uint32_t)seed,
+                                                 (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+                    const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+                    uint32_t mine = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const uint32_t bits = (r4[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+                        const uint32_t bal = __ballot_sync(GPT_FULL_MASK, bits >= thresh);
+                        if (lane == r) mine = bal;
+                    }
+                    if (lane < 8 && blk * 8 + lane < T) keepw[(blk * 8 + lane) * WPR + w] = mine;
+                }
+            }
+        }
+        if (nxt < nsl) cp_async_wait<1>();
+        else cp_async_wait<0>();
         __syncthreads();
 
-        const int col0 = sl * HS, c_lane = col0 + cl;
+        const int c_lane = col0 + cl;
         const bool col_ok = c_lane < H;  // lanes past H stay in the loops (warp-wide ops inside) but never store
         const float4 bias2 = lds128(bias_s + (uint32_t)c_lane * 4u);  // 2*bias, zero past H
         const uint32_t tile_lane = tile_s0 + (uint32_t)(it & 1) * tile_bytes + (uint32_t)cl * 4u;
-        const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
         float* const out_lane = p.out + (size_t)b * T * H + c_lane;
         const float* const mask_lane = (DROP == DROP_MASK) ? p.drop_mask + (size_t)b * T * H + c_lane : nullptr;
+        uint32_t* const act_sl = write_act ? p.act_out + act_index(b, T, H, sl) : nullptr;
 
-        // LPR lanes per node; every lane group walks its own blocks of kRowBlock consecutive rows, four rows in
-        // flight.  The block loop is warp-uniform (blk0); rows past T behave as empty rows and are not stored.
-        for (int blk0 = warp * RPW; blk0 * kRowBlock < T; blk0 += GROUPS) {
-            const int blk = blk0 + sub;
-            unsigned long long rlo[4] = {0, 0, 0, 0}, rhi[4] = {0, 0, 0, 0};  // 8 x 16 random bits per column
-            if (DROP == DROP_PHILOX) {
+        // LPR lanes per node, four nodes in flight per lane group, taken in length-sorted order.  The loop is
+        // warp-uniform; slots past T map to the zero row / empty meta entry and are never stored.
+        for (int base0 = warp * RPW * 4; base0 < T; base0 += GROUPS * 4) {
+            const uint2 pr = lds64(perm_s + (uint32_t)(base0 + sub * 4) * 2u);
+            const int rows[4] = {(int)(pr.x & 0xffffu), (int)(pr.x >> 16), (int)(pr.y & 0xffffu), (int)(pr.y >> 16)};
+            unsigned mx[4];
+            float inv[4];
+            Pack4 acc[4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const Philox4 q = philox4x32(  // one call covers this column for the 8 rows of the block
-                        (uint32_t)(c_lane + v) | (p.subseq << 20), (uint32_t)blk, (uint32_t)b, (uint32_t)step,
-                        (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
-                    rlo[v] = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
-                    rhi[v] = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
-                }
+            for (int q = 0; q < 4; ++q) {
+                const uint2 m = lds64(meta_s + (uint32_t)rows[q] * 8u);
+                mx[q] = m.x;
+                inv[q] = __uint_as_float(m.y);  // 0 for unobservable rows -> output 0
+                // the separate W(h) self term (the CSR row holds the 84-diagonal a second time)
+                acc[q] = lds_pk(tile_lane + (uint32_t)rows[q] * (HS * 4));
             }
-            // activation words of this (super block, slice): [row % 8][4] words, see act_block()
-            uint32_t* const act_blk = write_act ? p.act_out + act_block(b, T, H, blk0 >> 2, sl) : nullptr;
+            gather4<HS>(tile_lane, col_s, T, mx, acc);
 #pragma unroll
-            for (int r = 0; r < kRowBlock; r += 4) {
-                const int i0 = blk * kRowBlock + r;
-                unsigned mx[4];
-                float inv[4];
-                Pack4 acc[4];
+            for (int q = 0; q < 4; ++q) {
+                const int i = rows[q];
+                const float4 a = unpack(acc[q]);
+                float res[4] = {fmaxf((a.x + bias2.x) * inv[q], 0.f), fmaxf((a.y + bias2.y) * inv[q], 0.f),
+                                fmaxf((a.z + bias2.z) * inv[q], 0.f), fmaxf((a.w + bias2.w) * inv[q], 0.f)};
+                const bool live = (i < T) && col_ok;
+                if (DROP == DROP_PHILOX) {
+                    const uint32_t kw = lds32(keep_s + (uint32_t)((i < T ? i : 0) * WPR + (cl >> 5)) * 4u) >> (cl & 31);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool ok = i0 + q < T;
-                    uint2 m = make_uint2(0u, 0u);
-                    if (ok) m = lds64(meta_s + (uint32_t)(i0 + q) * 8u);
-                    mx[q] = m.x;
-                    inv[q] = __uint_as_float(m.y);  // 0 for unobservable rows -> output 0
-                    // the separate W(h) self term (the CSR row holds the 84-diagonal a second time)
-                    acc[q] = lds_pk(ok ? tile_lane + (uint32_t)(i0 + q) * (HS * 4) : zero_row);
+                    for (int v = 0; v < 4; ++v) res[v] = ((kw >> v) & 1u) ? res[v] * dscale : 0.f;
                 }
-                gather4<HS>(tile_lane, col_s, T, mx, acc);
+                const uint32_t off = (uint32_t)i * (uint32_t)H;
+                if (DROP == DROP_MASK) {
+                    if (live) {
+                        const float* m = mask_lane + off;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 a = unpack(acc[q]);
-                    float res[4] = {(a.x + bias2.x) * inv[q], (a.y + bias2.y) * inv[q], (a.z + bias2.z) * inv[q],
-                                    (a.w + bias2.w) * inv[q]};
-                    const int rr = r + q;
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        float t = fmaxf(res[v], 0.f);
-                        if (DROP == DROP_PHILOX) {
-                            const uint32_t bits =
-                                (uint32_t)(((rr < 4 ? rlo[v] : rhi[v]) >> ((rr & 3) * 16)) & 0xffffull);
-                            t = (bits >= thresh) ? t * dscale : 0.f;
-                        }
-                        res[v] = t;
+                        for (int v = 0; v < 4; ++v)
+                            if (c_lane + v < H) res[v] *= m[v];
                     }
-                    const bool live = (i0 + q < T) && col_ok;
-                    const uint32_t off = (uint32_t)(i0 + q) * (uint32_t)H;
-                    if (DROP == DROP_MASK) {
-                        if (live) {
-                            const float* m = mask_lane + off;
-#pragma unroll
-                            for (int v = 0; v < 4; ++v)
-                                if (c_lane + v < H) res[v] *= m[v];
-                        }
-                    }
-                    if (live) store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
-                    if (write_act) {  // CTA-uniform: the 4 ballots of this step are the 4 words of (sb, sl, rr)
-                        uint32_t w = 0;
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const uint32_t bal = __ballot_sync(GPT_FULL_MASK, live && res[v] > 0.f);
-                            if (lane == v) w = bal;
-                        }
-                        if (lane < 4) act_blk[rr * 4 + lane] = w;
-                    }
+                }
+                if (live) store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
+                if (write_act) {  // CTA-uniform; LPR == 8: the lane group's 8 nibbles make the row's 32-bit word
+                    uint32_t nib = (res[0] > 0.f ? 1u : 0u) | (res[1] > 0.f ? 2u : 0u) | (res[2] > 0.f ? 4u : 0u) |
+                                   (res[3] > 0.f ? 8u : 0u);
+                    uint32_t word = live ? nib << cl : 0u;
+                    word |= __shfl_xor_sync(GPT_FULL_MASK, word, 1);  // OR over the 8 lanes of the group
+                    word |= __shfl_xor_sync(GPT_FULL_MASK, word, 2);
+                    word |= __shfl_xor_sync(GPT_FULL_MASK, word, 4);
+                    if (live && cl == 0) act_sl[i] = word;
                 }
             }
         }
-        __syncthreads();  // everyone is done with this buffer before the next iteration refills it
+        __syncthreads();  // everyone is done with this buffer / keep-words before the next iteration refills them
     }
 }
 
 template <int LPR, int NT, bool ALIGNED>
 __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
-    extern __shared__ __align__(16) float smem_f[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW;
     const int T = p.T, H = p.H;
     const int b = blockIdx.y;
     const int nsl = (H + HS - 1) / HS;
-    const size_t tile_stride = tile_floats(T, LPR);
     const bool use_act = (p.act_in != nullptr) && (LPR == 8);
-    const int nactw = (int)act_words(T);
-    float* red = smem_f + (size_t)p.nbuf * tile_stride;  // [GROUPS][HS]
-    uint32_t* actw = reinterpret_cast<uint32_t*>(red + GROUPS * HS);  // [nbuf][nactw] when use_act
-    uint2* meta = reinterpret_cast<uint2*>(actw + (use_act ? (size_t)p.nbuf * nactw : 0));
-    unsigned short* colv = reinterpret_cast<unsigned short*>(meta + T);
+    const Layout L = make_layout(T, H, LPR, NT, p.nbuf, false, use_act);
+    float* tile0 = reinterpret_cast<float*>(smem_raw + L.tile);
+    float* red = reinterpret_cast<float*>(smem_raw + L.red);  // [GROUPS][HS]
+    uint32_t* actw = reinterpret_cast<uint32_t*>(smem_raw + L.bits);
+    uint2* meta = reinterpret_cast<uint2*>(smem_raw + L.meta);
+    unsigned short* perm = reinterpret_cast<unsigned short*>(smem_raw + L.perm);
+    unsigned short* colv = reinterpret_cast<unsigned short*>(smem_raw + L.col);
+    const size_t tile_stride = tile_floats(T, LPR);
+    const int actw_stride = bits_stride(T, LPR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tile_s0 = smem_u32(smem_f), tile_bytes = (uint32_t)tile_stride * 4u;
+    const uint32_t tile_s0 = smem_u32(tile0), tile_bytes = (uint32_t)tile_stride * 4u;
     const uint32_t actw_s0 = smem_u32(actw);
     const size_t base = (size_t)b * T * H;
     const float* gb = p.y + base;
+    // 16-byte async copies of the activation words need T % 4 == 0 and an aligned source
+    const bool act16 = use_act && (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.act_in) & 15) == 0);
 
     // the slice's activation words travel in the same cp.async group as the slice itself
     auto issue = [&](int buf, int sl) {
         if (use_act) {
-            for (int q = tid; q < nactw / 4; q += NT) {  // 16-byte pieces; super block q/8, piece q%8
-                const uint32_t* src = p.act_in + act_block(b, T, H, q >> 3, sl) + (q & 7) * 4;
-                cp_async16(actw_s0 + (uint32_t)(buf * nactw + q * 4) * 4u, src);
+            const uint32_t* src = p.act_in + act_index(b, T, H, sl);
+            const uint32_t dst = actw_s0 + (uint32_t)(buf * actw_stride) * 4u;
+            if (act16) {
+                for (int q = tid; q < T / 4; q += NT) cp_async16(dst + (uint32_t)q * 16u, src + q * 4);
+            } else {
+                for (int q = tid; q < T; q += NT) cp_async4(dst + (uint32_t)q * 4u, src + q);
             }
         }
         issue_slice<LPR, NT, ALIGNED>(gb, tile_s0 + (uint32_t)buf * tile_bytes, T, H, sl);
+        cp_async_commit();
     };
     issue(0, blockIdx.x);
-    stage_meta<false, NT>(p, b, smem_f, tile_stride, meta, colv, HS);
+    stage_meta<false, NT>(p, b, tile0, tile_stride, meta, perm, perm_len(T, GROUPS), colv, HS);
 
     const int cl = (lane % LPR) * 4, sub = lane / LPR;
-    const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv);
+    const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv), perm_s = smem_u32(perm);
     const float ds = p.drop_scale;
 
     int it = 0;
@@ -388,7 +434,7 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
         // ---- in place: g = gout * dropscale * [out > 0] / denom ------------------------------------------------
         const int col0 = sl * HS;
         const uint32_t tile_s = tile_s0 + (uint32_t)(it & 1) * tile_bytes;
-        const uint32_t actw_s = actw_s0 + (uint32_t)((it & 1) * nactw) * 4u;
+        const uint32_t actw_s = actw_s0 + (uint32_t)((it & 1) * actw_stride) * 4u;
 #pragma unroll 2
         for (int q = tid; q < T * LPR; q += NT) {
             const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
@@ -398,10 +444,9 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
             const float inv = __uint_as_float(lds64(meta_s + (uint32_t)row * 8u).y);
             float f[4];
             if (use_act) {
-                const uint4 w = lds128u(actw_s + (uint32_t)(((row >> 5) * 32 + (row & 7) * 4) * 4));
-                const int bit = ((row & 31) >> 3) * 8 + (cc >> 2);
-                f[0] = (float)((w.x >> bit) & 1u); f[1] = (float)((w.y >> bit) & 1u);
-                f[2] = (float)((w.z >> bit) & 1u); f[3] = (float)((w.w >> bit) & 1u);
+                const uint32_t w = lds32(actw_s + (uint32_t)row * 4u) >> cc;  // LPR == 8: cc < 32
+#pragma unroll
+                for (int v = 0; v < 4; ++v) f[v] = (float)((w >> v) & 1u);
             } else {
                 const size_t off = base + (size_t)row * H + c;
 #pragma unroll
@@ -428,27 +473,26 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
         const int c_lane = col0 + cl;
         const bool col_ok = c_lane < H;
         const uint32_t tile_lane = tile_s + (uint32_t)cl * 4u;
-        const uint32_t zero_row = tile_lane + (uint32_t)T * (HS * 4);
         float* const out_lane = p.out + base + c_lane;
         Pack4 csum;
         csum.lo = 0ull;
         csum.hi = 0ull;
-        for (int jb = warp * RPW * 4; jb < T; jb += GROUPS * 4) {  // warp-uniform
-            const int j0 = jb + sub * 4;
+        for (int base0 = warp * RPW * 4; base0 < T; base0 += GROUPS * 4) {  // warp-uniform
+            const uint2 pr = lds64(perm_s + (uint32_t)(base0 + sub * 4) * 2u);
+            const int rows[4] = {(int)(pr.x & 0xffffu), (int)(pr.x >> 16), (int)(pr.y & 0xffffu), (int)(pr.y >> 16)};
             unsigned mx[4];
             Pack4 acc[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const bool ok = j0 + q < T;
-                mx[q] = ok ? lds64(meta_s + (uint32_t)(j0 + q) * 8u).x : 0u;
-                acc[q] = lds_pk(ok ? tile_lane + (uint32_t)(j0 + q) * (HS * 4) : zero_row);
+                mx[q] = lds64(meta_s + (uint32_t)rows[q] * 8u).x;
+                acc[q] = lds_pk(tile_lane + (uint32_t)rows[q] * (HS * 4));  // slots past T read the zero row
                 add_pk(csum, acc[q]);
             }
             gather4<HS>(tile_lane, col_s, T, mx, acc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (j0 + q < T && col_ok)
-                    store4<ALIGNED>(out_lane + (uint32_t)(j0 + q) * (uint32_t)H, unpack(acc[q]), c_lane, H);
+                if (rows[q] < T && col_ok)
+                    store4<ALIGNED>(out_lane + (uint32_t)rows[q] * (uint32_t)H, unpack(acc[q]), c_lane, H);
         }
         if (p.dbias != nullptr) *reinterpret_cast<float4*>(red + (warp * RPW + sub) * HS + cl) = unpack(csum);
         __syncthreads();  // tile buffer free for the refill; red[] complete
@@ -476,11 +520,11 @@ struct AggConfig {
 AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
     const int T = p.T, H = p.H, B = p.B;
     const bool act = fwd ? (p.act_out != nullptr) : (p.act_in != nullptr);  // bit layout is tied to LPR = 8
+    const bool philox = fwd && p.rng != nullptr && p.thresh16 > 0 && p.drop_mask == nullptr;
     AggConfig c{};
     auto slices = [&](int lpr) { return (H + 4 * lpr - 1) / (4 * lpr); };
     auto bytes = [&](int lpr, int nt, int nbuf) {
-        return agg_smem_bytes(T, lpr, nbuf, fwd ? 0 : (nt / 32) * (32 / lpr), !fwd && act && lpr == 8,
-                              fwd ? slices(lpr) * 4 * lpr : 0);
+        return make_layout(T, H, lpr, nt, nbuf, fwd, fwd ? philox : (act && lpr == 8)).total;
     };
     if (force_vec == 1 || ((force_vec == 2 || force_vec == 4) && !act)) {
         c.lpr = 8 * force_vec; c.nt = 256; c.nbuf = 1; c.grid_x = slices(c.lpr);
@@ -510,18 +554,11 @@ AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
 }
 
 template <typename K>
-int ensure_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
-        cudaError_t a = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, cudaStream_t st) {
+    if (c.smem > 48 * 1024) {
+        cudaError_t a = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (a != cudaSuccess) return (int)a;
     }
-    return GPT_OK;
-}
-
-template <typename K>
-int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, cudaStream_t st) {
-    int rc = ensure_smem(kernel, c.smem);
-    if (rc != GPT_OK) return rc;
     kernel<<<dim3(c.grid_x, p.B), c.nt, c.smem, st>>>(p);
     return gpt_launch_status();
 }
@@ -536,7 +573,7 @@ int launch(bool fwd, const AggConfig& c, const AggParams& p, cudaStream_t st) {
 }
 
 int dispatch(bool fwd, AggParams& p, int force_vec, cudaStream_t st) {
-    if (4 * p.T + 2 > 65535) return GPT_ERR_UNSUPPORTED;  // 16-bit CSR indices / row lengths in shared memory
+    if (4 * p.T + 4 > 65535) return GPT_ERR_UNSUPPORTED;  // 16-bit CSR indices / row lengths in shared memory
     const bool aligned = (p.H % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const AggConfig c = pick_config(p, fwd, force_vec);

@@ -160,8 +160,7 @@ def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq
     B, T = csr.B, csr.T
     H = y.shape[-1]
     out = torch.empty((B, T, H), dtype=torch.float32, device=y.device)
-    act = torch.empty((B * ((T + 31) // 32) * ((H + 31) // 32) * 32,), dtype=torch.int32,
-                      device=y.device) if want_act else None
+    act = torch.empty((B * ((H + 31) // 32) * T,), dtype=torch.int32, device=y.device) if want_act else None
     _call('gpt_gcn_aggregate_fwd', _ptr(y), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom),
           _ptr(csr.flags), _ptr(bias), _ptr(out), _ptr(act), B, T, H, int(bool(use_adj)),
           float(drop_p), _ptr(rng_state), int(subseq), _ptr(drop_mask), int(force_vec), _stream())

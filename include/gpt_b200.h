@@ -73,9 +73,8 @@ int gpt_prune_csr(const int64_t* head, const int64_t* subj_pos, const int64_t* o
 /* K2 forward. One GCN layer after the projection y = h W^T (model/gcn.py:269-271, 390-393):
  *     out_i = dropout(relu((sum_{j in row i} y_j + y_i + 2*bias) / denom_i)); rows with flags == 0 are written 0.
  * use_adj = 0 is the --no_adj ablation (model/gcn.py:264-265).
- * act_mask (optional, uint32 [B * ceil(T/32) * ceil(H/32) * 32]): one bit per element, set where out > 0, for the
- * backward.  Element (b, row, col) lives in word (((b*ceil(T/32) + row/32)*ceil(H/32) + col/32)*8 + row%8)*4 + col%4
- * at bit ((row%32)/8)*8 + (col%32)/4.
+ * act_mask (optional, uint32 [B, ceil(H/32), T]): one bit per element, set where out > 0, for the backward.
+ * Element (b, row, col) is bit col%32 of word (b*ceil(H/32) + col/32)*T + row.
  * Dropout: drop_p > 0 draws Philox bits in-kernel from rng_state = {seed, step} (device uint64[2]) and `subseq`
  * (layer id); or drop_mask (pre-scaled float [B*T,H], tests) multiplies the result; or neither.
  * force_vec: 0 = auto, else 1/2/4 -> slice width 32/64/128 columns, one slice per CTA. */
