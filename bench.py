@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--prune_k', type=int, default=1)
     ap.add_argument('--gemm', default='fp32')
+    ap.add_argument('--eager', action='store_true', help='time the eager five-call step instead of the CUDA graph')
     ap.add_argument('--no-roofline', action='store_true', help='skip the large-shape aggregation roofline run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--roofline-batch', type=int, default=4096)
@@ -59,7 +60,8 @@ def workload_config(args, world):
     return {'workload': 'tacred_b50_k%d' % args.prune_k, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world,
             'len': 'clip(Poisson(36),8,96)', 'layers': 2, 'in_dim': 360, 'hidden': 200, 'vocab': VOCAB,
             'prune_k': args.prune_k, 'gemm': args.gemm, 'parallelism': 'dp%d' % world,
-            'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd', 'l2': 'flushed between timed steps (256 MiB fill)'}
+            'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd',
+            'engine': 'eager' if args.eager else 'cuda_graph_per_batch_shape', 'l2': 'flushed between timed steps (256 MiB fill)'}
 
 
 # ------------------------------------------------------------------------------------------------ clocks -------
@@ -248,7 +250,7 @@ def run_b200(args):
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     params = list(model.parameters())
 
-    def step(batch):
+    def eager_step(batch):       # the reference's five calls, train.py:213-227
         trainer.optimizer.zero_grad(set_to_none=False)
         loss = trainer.update(batch)
         loss.backward()
@@ -257,7 +259,14 @@ def run_b200(args):
         trainer.optimizer.step()
         return loss
 
-    # first step allocates .grad tensors; zero_grad(set_to_none=False) keeps them afterwards
+    from gcn_over_pruned_trees_b200.engine import GraphedTrainStep
+    graphed = GraphedTrainStep(trainer, reducer=reducer)
+    step = eager_step if args.eager else graphed
+
+    # warm-up: every batch shape runs eagerly 3x, is captured, and is replayed at least once
+    for _ in range(5):
+        for bt in resident:
+            step(bt)
     for i in range(max(args.warmup, 3)):
         step(resident[i % N_BATCHES])
     torch.cuda.synchronize()
@@ -266,6 +275,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = _lib.lib().gpt_launch_count()
+    launches = 0
     parallel.barrier()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
@@ -274,34 +284,45 @@ def run_b200(args):
         a.record()
         step(resident[i % N_BATCHES])
         b.record()
+        if not args.eager:
+            launches += graphed.launches_per_replay(resident[i % N_BATCHES])
     torch.cuda.synchronize()
     parallel.barrier()
     wall = time.perf_counter() - wall0
-    launches = _lib.lib().gpt_launch_count() - launches0
+    launches += _lib.lib().gpt_launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in events)
     dev_ms = parallel.max_over_ranks(dev_ms, dev)
     clocks = sampler.stop() if sampler else None
     ms_per_step = dev_ms / args.steps
     value = BATCH * world * args.steps / (dev_ms * 1e-3)
 
-    # ---- e2e: pinned host batches through GCNTrainer.update, loss.item() every step ---------------------------
+    # ---- e2e: pinned host batches through the public API, loss read back every step -----------------------------
     h2d = sum(t.numel() * t.element_size() for t in host[0] if torch.is_tensor(t))
-    for i in range(3):
-        step(host[i % N_BATCHES]).item()
-    parallel.barrier()
-    torch.cuda.synchronize()
-    e2e_s = 0.0
-    for i in range(args.steps):
-        flush.fill_(0.0)
+
+    def timed_host_loop(fn, n):
+        for i in range(3):
+            fn(host[i % N_BATCHES]).item()
+        parallel.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step(host[i % N_BATCHES]).item()
-        e2e_s += time.perf_counter() - t0
-    parallel.barrier()
-    e2e_s = parallel.max_over_ranks(e2e_s, dev)
+        total = 0.0
+        for i in range(n):
+            flush.fill_(0.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(host[i % N_BATCHES]).item()
+            total += time.perf_counter() - t0
+        parallel.barrier()
+        return parallel.max_over_ranks(total, dev)
+
+    e2e_s = timed_host_loop(step, args.steps)
     e2e = {'value': BATCH * world * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / args.steps * 1e3,
-           'api': 'GCNTrainer.update(pinned host batch) + backward + clip + SGD + loss.item()'}
+           'api': ('GCNTrainer.update(host batch) + backward + clip + SGD + loss.item()' if args.eager else
+                   'GCNTrainer.train_step(pinned host batch) [one CUDA-graph replay] + loss.item()')}
+    n_eager = min(args.steps, 30)
+    eager_s = timed_host_loop(eager_step, n_eager)
+    e2e['dropin_eager'] = {'value': BATCH * world * n_eager / eager_s, 'ms_per_step': eager_s / n_eager * 1e3,
+                           'api': 'reference call sequence train.py:213-227 on the new model package, eager'}
 
     if rank != 0:
         return
@@ -313,7 +334,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     pa.record()
     for i in range(n_prof):
-        step(resident[i % N_BATCHES])
+        eager_step(resident[i % N_BATCHES])
     pb.record()
     summary = ops.TIMER.summary()
     ops.TIMER = None

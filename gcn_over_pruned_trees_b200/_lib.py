@@ -27,6 +27,11 @@ SIGNATURES = {
     'gpt_linear_fwd_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_wgrad_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
+    'gpt_embed_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p],
+    'gpt_embed_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p,
+                      _c_u32, _p],
+    'gpt_embed_rows_sqnorm': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_embed_rows_sgd': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _p],
 }
 
 _lib = None

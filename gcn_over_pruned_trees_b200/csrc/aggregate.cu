@@ -26,6 +26,7 @@
 // [out_i > 0] comes from the forward's bit mask when given (reads 1/32 of the bytes) or from `out` itself.
 #include "gpt_common.cuh"
 #include <cstdlib>
+#include <unordered_map>
 
 namespace {
 
@@ -555,9 +556,12 @@ AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
 
 template <typename K>
 int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, cudaStream_t st) {
-    if (c.smem > 48 * 1024) {
+    static std::unordered_map<const void*, size_t> configured;  // opt in to large dynamic smem once per kernel
+    size_t& have = configured[reinterpret_cast<const void*>(kernel)];
+    if (c.smem > 48 * 1024 && c.smem > have) {
         cudaError_t a = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (a != cudaSuccess) return (int)a;
+        have = c.smem;
     }
     kernel<<<dim3(c.grid_x, p.B), c.nt, c.smem, st>>>(p);
     return gpt_launch_status();

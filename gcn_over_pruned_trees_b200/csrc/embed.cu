@@ -1,0 +1,217 @@
+// K5 -- input embedding stage of GCN.forward and its row-sparse gradient / optimiser path.
+//
+// Forward replaces  cat[emb(words), pos_emb(pos), ner_emb(ner)] -> in_drop   (/root/reference/model/gcn.py:235-247)
+// -- three gather kernels, a concat and a dropout in the reference -- with one kernel that writes the layer-0
+// input row [emb_dim + pos_dim + ner_dim] once, with the dropout mask drawn in-kernel (Philox, same {seed, step}
+// device state as the GCN layers).
+//
+// Backward: the reference's word-embedding gradient is a dense [V, emb_dim] tensor that is zero outside the <= B*T
+// rows the batch touches (60 MB at V = 50 000 for ~1 000 live rows); zeroing, clipping and updating it densely
+// dominates a TACRED-size step on a GPU.  Here dX rows are scattered into the tables with atomics (rows of tokens
+// that are not observable have exactly zero gradient and are skipped), and -- for the plain-SGD configuration the
+// reference ships (train_gcn.sh:4) -- three small kernels finish the step touching only the live rows:
+//   embed_bwd      : G[w] += dX[t] * mask ; owner[w] = min token index with that word (dedup for the passes below)
+//   rows_sqnorm    : sq += sum over owned rows of |G[w]|^2          (the embedding's share of the global grad norm)
+//   rows_sgd       : W[w] -= lr * clip * G[w] ; G[w] = 0 ; owner[w] = INT_MAX      (G stays all-zero between steps)
+// which is arithmetic-identical to clip_grad_norm_ + SGD over the dense tensor (train.py:224-227).
+#include "gpt_common.cuh"
+
+namespace {
+
+constexpr int kEmbThreads = 128;
+
+struct EmbParams {
+    const long long* words;
+    const long long* pos;
+    const long long* ner;      // may be null (SemEval / ner_dim == 0)
+    const float* emb_w;        // [V, E]
+    const float* pos_w;        // [P, Dp] or null
+    const float* ner_w;        // [N, Dn] or null
+    int n_rows, V, E, Dp, Dn;
+    unsigned thresh16, subseq;
+    float drop_scale;
+    const unsigned long long* rng;
+};
+
+// one CTA per token row; thread c handles column group c*8 .. c*8+7 (one Philox call per thread)
+__global__ void __launch_bounds__(kEmbThreads)
+embed_fwd_kernel(const EmbParams p, float* __restrict__ x) {
+    const int row = blockIdx.x;
+    const int D = p.E + p.Dp + p.Dn;
+    const long long w = p.words[row];
+    const long long ps = p.pos_w ? p.pos[row] : 0;
+    const long long nr = p.ner_w ? p.ner[row] : 0;
+    const bool drop = p.thresh16 > 0;
+    unsigned long long seed = 0, step = 0;
+    if (drop) { seed = p.rng[0]; step = p.rng[1]; }
+    float* xr = x + (size_t)row * D;
+    for (int g = threadIdx.x; g * 8 < D; g += kEmbThreads) {
+        Philox4 q{0, 0, 0, 0};
+        if (drop)
+            q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step, (uint32_t)seed,
+                           (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+        const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            if (c >= D) break;
+            float v;
+            if (c < p.E) v = p.emb_w[(size_t)w * p.E + c];
+            else if (c < p.E + p.Dp) v = p.pos_w[(size_t)ps * p.Dp + (c - p.E)];
+            else v = p.ner_w[(size_t)nr * p.Dn + (c - p.E - p.Dp)];
+            if (drop) {
+                const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                v = bits >= p.thresh16 ? v * p.drop_scale : 0.f;
+            }
+            xr[c] = v;
+        }
+    }
+}
+
+// scatter dX (after the same dropout mask) into the tables; word rows additionally record their first token
+__global__ void __launch_bounds__(kEmbThreads)
+embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned char* __restrict__ flags,
+                 float* __restrict__ g_emb, float* __restrict__ g_pos, float* __restrict__ g_ner,
+                 int* __restrict__ owner, int topn) {
+    const int row = blockIdx.x;
+    if (flags != nullptr && flags[row] == 0) return;  // unobservable token: its gradient row is exactly zero
+    const int D = p.E + p.Dp + p.Dn;
+    const long long w = p.words[row];
+    const long long ps = p.pos_w ? p.pos[row] : 0;
+    const long long nr = p.ner_w ? p.ner[row] : 0;
+    const bool word_live = g_emb != nullptr && w != 0 && w < topn;  // padding_idx = 0; rows >= topn are frozen
+    const bool drop = p.thresh16 > 0;
+    unsigned long long seed = 0, step = 0;
+    if (drop) { seed = p.rng[0]; step = p.rng[1]; }
+    if (threadIdx.x == 0 && word_live && owner != nullptr) atomicMin(owner + w, row);
+    const float* dr = dx + (size_t)row * D;
+    for (int g = threadIdx.x; g * 8 < D; g += kEmbThreads) {
+        Philox4 q{0, 0, 0, 0};
+        if (drop)
+            q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step, (uint32_t)seed,
+                           (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+        const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            if (c >= D) break;
+            float v = dr[c];
+            if (drop) {
+                const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                v = bits >= p.thresh16 ? v * p.drop_scale : 0.f;
+            }
+            if (v == 0.f) continue;
+            if (c < p.E) { if (word_live) atomicAdd(g_emb + (size_t)w * p.E + c, v); }
+            else if (c < p.E + p.Dp) { if (g_pos) atomicAdd(g_pos + (size_t)ps * p.Dp + (c - p.E), v); }
+            else if (g_ner) atomicAdd(g_ner + (size_t)nr * p.Dn + (c - p.E - p.Dp), v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kEmbThreads)
+rows_sqnorm_kernel(const long long* __restrict__ words, const int* __restrict__ owner, const float* __restrict__ g,
+                   int n_rows, int E, int topn, float* __restrict__ sq) {
+    const int row = blockIdx.x;
+    const long long w = words[row];
+    if (w == 0 || w >= topn || owner[w] != row) return;  // every live word row is counted once, by its first token
+    float s = 0.f;
+    for (int c = threadIdx.x; c < E; c += kEmbThreads) { const float v = g[(size_t)w * E + c]; s += v * v; }
+    s = warp_sum_f(s);
+    __shared__ float part[kEmbThreads / 32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < kEmbThreads / 32; ++i) t += part[i];
+        atomicAdd(sq, t);
+    }
+}
+
+// W[w] -= lr * min(1, max_norm / (sqrt(total_sq) + 1e-6)) * G[w]; G[w] = 0; owner[w] = INT_MAX
+__global__ void __launch_bounds__(kEmbThreads)
+rows_sgd_kernel(const long long* __restrict__ words, int* __restrict__ owner, float* __restrict__ g,
+                float* __restrict__ w_tab, int n_rows, int E, int topn, const float* __restrict__ total_sq,
+                float max_norm, float lr) {
+    const int row = blockIdx.x;
+    const long long w = words[row];
+    if (w == 0 || w >= topn || owner[w] != row) return;
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*total_sq) + 1e-6f));  // clip_grad_norm_ semantics
+    const float a = lr * coef;
+    for (int c = threadIdx.x; c < E; c += kEmbThreads) {
+        const size_t i = (size_t)w * E + c;
+        w_tab[i] -= a * g[i];
+        g[i] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) owner[w] = 0x7fffffff;
+}
+
+int fill_params(EmbParams& p, const int64_t* words, const int64_t* pos, const int64_t* ner, const float* emb_w,
+                const float* pos_w, const float* ner_w, int n_rows, int V, int E, int Dp, int Dn, float drop_p,
+                const uint64_t* rng, uint32_t subseq) {
+    if (!(words && emb_w) || n_rows < 0 || V < 1 || E < 1 || Dp < 0 || Dn < 0) return GPT_ERR_BAD_ARG;
+    if ((Dp > 0) != (pos_w != nullptr && pos != nullptr)) return GPT_ERR_BAD_ARG;
+    if ((Dn > 0) != (ner_w != nullptr && ner != nullptr)) return GPT_ERR_BAD_ARG;
+    if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && rng == nullptr)) return GPT_ERR_BAD_ARG;
+    p.words = reinterpret_cast<const long long*>(words);
+    p.pos = reinterpret_cast<const long long*>(pos);
+    p.ner = reinterpret_cast<const long long*>(ner);
+    p.emb_w = emb_w; p.pos_w = pos_w; p.ner_w = ner_w;
+    p.n_rows = n_rows; p.V = V; p.E = E; p.Dp = Dp; p.Dn = Dn;
+    unsigned th = (unsigned)(drop_p * 65536.0f + 0.5f);
+    p.thresh16 = th > 65535u ? 65535u : th;
+    p.drop_scale = p.thresh16 > 0 ? 65536.0f / (65536.0f - (float)p.thresh16) : 1.0f;
+    p.subseq = subseq & 0xfffu;
+    p.rng = reinterpret_cast<const unsigned long long*>(rng);
+    return GPT_OK;
+}
+
+}  // namespace
+
+extern "C" int gpt_embed_fwd(const int64_t* words, const int64_t* pos, const int64_t* ner, const float* emb_w,
+                             const float* pos_w, const float* ner_w, float* x, int n_rows, int V, int E, int Dp, int Dn,
+                             float drop_p, const uint64_t* rng_state, uint32_t subseq, void* stream) {
+    EmbParams p{};
+    int rc = fill_params(p, words, pos, ner, emb_w, pos_w, ner_w, n_rows, V, E, Dp, Dn, drop_p, rng_state, subseq);
+    if (rc != GPT_OK || x == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
+    if (n_rows == 0) return GPT_OK;
+    embed_fwd_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(p, x);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_embed_bwd(const float* dx, const uint8_t* flags, const int64_t* words, const int64_t* pos,
+                             const int64_t* ner, float* g_emb, float* g_pos, float* g_ner, int32_t* owner, int n_rows,
+                             int V, int E, int Dp, int Dn, int topn, float drop_p, const uint64_t* rng_state,
+                             uint32_t subseq, void* stream) {
+    EmbParams p{};
+    // the tables themselves are not read in the backward; reuse the checker with dummy non-null table pointers
+    int rc = fill_params(p, words, pos, ner, dx, Dp > 0 ? dx : nullptr, Dn > 0 ? dx : nullptr, n_rows, V, E, Dp, Dn,
+                         drop_p, rng_state, subseq);
+    if (rc != GPT_OK || dx == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
+    if (n_rows == 0) return GPT_OK;
+    embed_bwd_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(p, dx, flags, g_emb, g_pos, g_ner, owner,
+                                                                       topn < V ? topn : V);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner, const float* g_emb, int n_rows, int E,
+                                     int topn, float* sq, void* stream) {
+    GPT_CHECK_ARG(words && owner && g_emb && sq && n_rows >= 0 && E >= 1);
+    if (n_rows == 0) return GPT_OK;
+    rows_sqnorm_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(words),
+                                                                         owner, g_emb, n_rows, E, topn, sq);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_embed_rows_sgd(const int64_t* words, int32_t* owner, float* g_emb, float* emb_w, int n_rows, int E,
+                                  int topn, const float* total_sq, float max_norm, float lr, void* stream) {
+    GPT_CHECK_ARG(words && owner && g_emb && emb_w && n_rows >= 0 && E >= 1);
+    GPT_CHECK_ARG(max_norm <= 0.f || total_sq != nullptr);
+    if (n_rows == 0) return GPT_OK;
+    rows_sgd_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(words), owner,
+                                                                      g_emb, emb_w, n_rows, E, topn, total_sq, max_norm,
+                                                                      lr);
+    return gpt_launch_status();
+}

@@ -133,6 +133,7 @@ class GCN(nn.Module):
         self.register_buffer('rng_state', torch.tensor([torch.initial_seed() & 0x7fffffffffffffff, 0],
                                                        dtype=torch.int64), persistent=False)
         self.injected_masks = None      # tests only: {'in': m, 'rnn': m, 'gcn0': m, ...}, pre-scaled by 1/(1-p)
+        self.sparse_embedding = None    # ops.SparseEmbeddingState while engine.GraphedTrainStep drives the step
 
     def conv_l2(self):
         return sum(p.pow(2).sum() for lin in self.W for p in (lin.weight, lin.bias))
@@ -162,18 +163,29 @@ class GCN(nn.Module):
         else:
             words, masks, pos, deprel, head, subj_pos, obj_pos = inputs
             ner = None
-        embs = [words if words.dim() > 2 else self.emb(words)]
-        if self.opt['pos_dim'] > 0:
-            embs.append(self.pos_emb(pos))
-        if self.opt['ner_dim'] > 0 and self.opt['dataset'] == 'tacred':
-            embs.append(self.ner_emb(ner))
-        x = self._host_dropout(torch.cat(embs, dim=2), self.in_drop, 'in')
+        use_ner = self.opt['ner_dim'] > 0 and self.opt['dataset'] == 'tacred'
+        if self.training and self.injected_masks is None:
+            self.rng_state[1] += 1         # new dropout streams every training forward (graph-capture safe)
+        if words.dim() > 2 or self.injected_masks is not None:
+            # pre-computed token vectors (BERT path of the loader) or injected test masks: plain lookups
+            embs = [words if words.dim() > 2 else self.emb(words)]
+            if self.opt['pos_dim'] > 0:
+                embs.append(self.pos_emb(pos))
+            if use_ner:
+                embs.append(self.ner_emb(ner))
+            x = self._host_dropout(torch.cat(embs, dim=2), self.in_drop, 'in')
+        else:
+            # K5: gather + concat + input dropout in one kernel; its backward scatters straight into the tables
+            x = ops.embed_concat(words, pos, ner if use_ner else None, self.emb.weight,
+                                 self.pos_emb.weight if self.opt['pos_dim'] > 0 else None,
+                                 self.ner_emb.weight if use_ner else None,
+                                 drop_p=self.opt['input_dropout'] if self.training else 0.0, rng_state=self.rng_state,
+                                 subseq=0xE0, flags=None if self.opt.get('rnn', False) else adj.flags,
+                                 topn=self.opt['topn'], sparse=self.sparse_embedding)
         if self.opt.get('rnn', False):
             x = self._host_dropout(self.encode_with_rnn(x, masks, words.size(0)), self.rnn_drop, 'rnn')
         use_adj = not self.opt.get('no_adj', False)
         drop_p = self.opt['gcn_dropout'] if self.training else 0.0
-        if self.training and drop_p > 0 and self.injected_masks is None:
-            self.rng_state[1] += 1         # new dropout stream every training forward (graph-capture safe)
         for l, lin in enumerate(self.W):
             last = l == self.layers - 1
             mask = None if self.injected_masks is None else self.injected_masks.get('gcn%d' % l)

@@ -101,5 +101,17 @@ class GCNTrainer(Trainer):
             _, predictions, probs = [list(t) for t in zip(*sorted(zip(orig_idx, predictions, probs)))]
         return predictions, probs, loss.item()
 
+    def train_step(self, batch, reducer=None):
+        """One whole optimisation step (zero_grad, forward, loss, backward, clip, optimizer step -- the five calls of
+        train.py:213-227) as a single CUDA-graph replay; returns the loss as a device scalar.  Not part of the
+        reference API: the reference-compatible path is update() + caller-owned backward/clip/step."""
+        if getattr(self, '_graphed', None) is None:
+            try:
+                from ..engine import GraphedTrainStep
+            except ImportError:
+                from gcn_over_pruned_trees_b200.engine import GraphedTrainStep
+            self._graphed = GraphedTrainStep(self, reducer=reducer)
+        return self._graphed(batch)
+
     def get_deprel_emb(self):
         return self.model.get_deprel_emb()

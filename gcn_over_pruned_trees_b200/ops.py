@@ -244,3 +244,79 @@ class _Pool3(torch.autograd.Function):
 
 def pool3(h, csr, pool_type='max'):
     return _Pool3.apply(h, csr, POOL_TYPES[pool_type])
+
+
+# ---- K5: input embeddings ------------------------------------------------------------------------------------
+
+class SparseEmbeddingState(object):
+    """Workspace of the row-sparse word-embedding gradient path (engine.GraphedTrainStep): G is a dense [V, E]
+    buffer that is all-zero between steps, owner[w] the first token of the current batch that uses word w."""
+
+    def __init__(self, weight, topn):
+        V, E = weight.shape
+        self.G = torch.zeros_like(weight)
+        self.owner = torch.full((V,), 0x7fffffff, dtype=torch.int32, device=weight.device)
+        self.sq = torch.zeros((1,), dtype=torch.float32, device=weight.device)
+        self.topn = int(min(max(topn, 0), V))
+        self.words = None           # the batch's word ids (static buffer), set by the forward
+
+
+class _EmbedConcat(torch.autograd.Function):
+    """dropout(cat[emb(words), pos_emb(pos), ner_emb(ner)]) (model/gcn.py:235-247) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, words, pos, ner, emb_w, pos_w, ner_w, drop_p, rng_state, subseq, flags, topn, sparse):
+        words = _dev(words, torch.int64, 'words')
+        emb_w = _dev(emb_w, torch.float32, 'emb.weight')
+        n_rows = words.numel()
+        V, E = emb_w.shape
+        Dp = pos_w.shape[1] if pos_w is not None else 0
+        Dn = ner_w.shape[1] if ner_w is not None else 0
+        x = torch.empty(words.shape + (E + Dp + Dn,), dtype=torch.float32, device=words.device)
+        _call('gpt_embed_fwd', _ptr(words), _ptr(pos if Dp else None), _ptr(ner if Dn else None), _ptr(emb_w),
+              _ptr(pos_w), _ptr(ner_w), _ptr(x), n_rows, V, E, Dp, Dn, float(drop_p),
+              _ptr(rng_state if drop_p > 0 else None), int(subseq), _stream())
+        ctx.meta = (n_rows, V, E, Dp, Dn, float(drop_p), rng_state, int(subseq), int(topn), sparse)
+        ctx.shapes = (emb_w.shape, None if pos_w is None else pos_w.shape, None if ner_w is None else ner_w.shape)
+        ctx.save_for_backward(words, pos, ner, flags)
+        if sparse is not None:
+            sparse.words = words
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        words, pos, ner, flags = ctx.saved_tensors
+        n_rows, V, E, Dp, Dn, drop_p, rng_state, subseq, topn, sparse = ctx.meta
+        dx = _dev(dx, torch.float32, 'grad_out')
+        dev = dx.device
+        want_emb, want_pos, want_ner = ctx.needs_input_grad[3], ctx.needs_input_grad[4], ctx.needs_input_grad[5]
+        g_pos = torch.zeros(ctx.shapes[1], dtype=torch.float32, device=dev) if (want_pos and Dp) else None
+        g_ner = torch.zeros(ctx.shapes[2], dtype=torch.float32, device=dev) if (want_ner and Dn) else None
+        if sparse is not None:          # side effect into the engine's all-zero-between-steps buffer
+            g_emb, owner, ret_emb = (sparse.G if want_emb else None), sparse.owner, None
+        else:
+            g_emb = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev) if want_emb else None
+            owner, ret_emb = None, g_emb
+        _call('gpt_embed_bwd', _ptr(dx), _ptr(flags), _ptr(words), _ptr(pos if Dp else None),
+              _ptr(ner if Dn else None), _ptr(g_emb), _ptr(g_pos), _ptr(g_ner), _ptr(owner), n_rows, V, E, Dp, Dn,
+              topn, drop_p, _ptr(rng_state if drop_p > 0 else None), subseq, _stream())
+        return None, None, None, ret_emb, g_pos, g_ner, None, None, None, None, None, None
+
+
+def embed_concat(words, pos, ner, emb_w, pos_w, ner_w, drop_p=0.0, rng_state=None, subseq=0, flags=None, topn=None,
+                 sparse=None):
+    V = emb_w.shape[0]
+    topn = V if topn is None else int(min(max(topn, 0), V))      # train.py's default topn is 1e10
+    return _EmbedConcat.apply(words, pos, ner, emb_w, pos_w, ner_w, drop_p, rng_state, subseq, flags, topn, sparse)
+
+
+def embed_rows_sqnorm(state):
+    V, E = state.G.shape
+    _call('gpt_embed_rows_sqnorm', _ptr(state.words), _ptr(state.owner), _ptr(state.G), state.words.numel(), E,
+          state.topn, _ptr(state.sq), _stream())
+
+
+def embed_rows_sgd(state, weight, total_sq, max_norm, lr):
+    V, E = state.G.shape
+    _call('gpt_embed_rows_sgd', _ptr(state.words), _ptr(state.owner), _ptr(state.G), _ptr(weight),
+          state.words.numel(), E, state.topn, _ptr(total_sq), float(max_norm), float(lr), _stream())

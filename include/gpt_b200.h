@@ -104,6 +104,27 @@ int gpt_linear_fwd_f32(const float* x, const float* w, float* y, int M, int N, i
 int gpt_linear_dgrad_f32(const float* dy, const float* w, float* dx, int M, int N, int K, void* stream);
 int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
 
+/* K5. input stage of GCN.forward (model/gcn.py:235-247): x[r] = dropout(cat[emb_w[words[r]], pos_w[pos[r]],
+ *     ner_w[ner[r]]]) for the n_rows = B*T token slots; x is [n_rows, E+Dp+Dn].  pos/pos_w and ner/ner_w are NULL when
+ *     Dp / Dn is 0 (ner: SemEval).  Dropout as in K2 (Philox from rng_state = {seed, step}). */
+int gpt_embed_fwd(const int64_t* words, const int64_t* pos, const int64_t* ner, const float* emb_w, const float* pos_w,
+                  const float* ner_w, float* x, int n_rows, int V, int E, int Dp, int Dn, float drop_p,
+                  const uint64_t* rng_state, uint32_t subseq, void* stream);
+/* K5 backward: scatter-add dx (re-applying the same dropout mask) into the gradient tables (all accumulated with
+ *     atomics, caller zeroes them; any of g_emb/g_pos/g_ner may be NULL).  Rows with flags == 0 are skipped (their
+ *     gradient is exactly zero), word id 0 (padding_idx) and ids >= topn (model/gcn.py:83-86) get no gradient.
+ *     owner (optional int32 [V], preset to INT_MAX): first token index of every touched word row. */
+int gpt_embed_bwd(const float* dx, const uint8_t* flags, const int64_t* words, const int64_t* pos, const int64_t* ner,
+                  float* g_emb, float* g_pos, float* g_ner, int32_t* owner, int n_rows, int V, int E, int Dp, int Dn,
+                  int topn, float drop_p, const uint64_t* rng_state, uint32_t subseq, void* stream);
+/* Row-sparse tail of clip_grad_norm_ + SGD for the word embedding (train.py:224-227), touching only the rows the
+ *     batch used: sq += sum |G[w]|^2 over touched rows;  then  W[w] -= lr * min(1, max_norm/(sqrt(*total_sq)+1e-6)) *
+ *     G[w], G[w] = 0, owner[w] = INT_MAX.  total_sq must hold the squared global gradient norm of ALL parameters. */
+int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner, const float* g_emb, int n_rows, int E, int topn,
+                          float* sq, void* stream);
+int gpt_embed_rows_sgd(const int64_t* words, int32_t* owner, float* g_emb, float* emb_w, int n_rows, int E, int topn,
+                       const float* total_sq, float max_norm, float lr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -401,3 +401,97 @@ def test_checkpoint_round_trip(tmp_path):
     assert pa == pb and la == lb
     sd = b.model.state_dict()
     assert sd['gcn_model.emb.weight'].data_ptr() == sd['gcn_model.gcn.emb.weight'].data_ptr()
+
+
+# ---------------------------------------------------------------- engine --------------------------------------
+
+def test_graphed_train_step_matches_eager_steps():
+    # dropout off so that the two runs are comparable; same init, same batches
+    over = dict(vocab_size=700, cuda=True, input_dropout=0.0, gcn_dropout=0.0)
+    batches = [synth.make_batch(50 + i, batch_size=50, vocab_size=700, pad_to=64) for i in range(3)]
+
+    def run(graphed):
+        torch.manual_seed(5)
+        tr = GCNTrainer(synth.tacred_opt(**over))
+        tr.model.train()
+        losses = []
+        for step in range(9):
+            b = batches[step % 3]
+            if graphed:
+                losses.append(float(tr.train_step(b)))
+            else:
+                tr.optimizer.zero_grad()
+                loss = tr.update(b)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(tr.model.parameters(), tr.opt['max_grad_norm'])
+                tr.optimizer.step()
+                losses.append(loss.item())
+        return losses, {k: v.detach().cpu() for k, v in tr.model.state_dict().items()}, tr
+
+    l0, s0, _ = run(False)
+    l1, s1, tr = run(True)
+    assert tr._graphed.replays >= 5                       # steps 4.. of the single shape are graph replays
+    assert np.allclose(l0, l1, rtol=2e-5)
+    for k in s0:
+        assert _rel(s1[k], s0[k]) < 5e-5, k
+
+
+def test_graphed_train_step_with_dropout_trains():
+    torch.manual_seed(0)
+    tr = GCNTrainer(synth.tacred_opt(vocab_size=500, cuda=True))
+    tr.model.train()
+    batch = synth.make_batch(7, batch_size=50, vocab_size=500)
+    losses = [float(tr.train_step(batch)) for _ in range(30)]
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
+    assert len(set(losses[10:20])) > 1                    # dropout stream advances between replays
+
+
+# ---------------------------------------------------------------- K5 ------------------------------------------
+
+@pytest.mark.parametrize('dataset', ('tacred', 'semeval'))
+def test_k5_embed_concat_vs_torch(dataset):
+    V, E, Dp, Dn = 300, 300, 30, 30 if dataset == 'tacred' else 0
+    batch = synth.make_batch(61, batch_size=20, vocab_size=V, dataset=dataset)
+    words, pos = batch[0].to(DEV), batch[2].to(DEV)
+    ner = batch[3].to(DEV) if dataset == 'tacred' else None
+    g = torch.Generator(device=DEV).manual_seed(1)
+    tabs = [torch.randn(V, E, device=DEV, generator=g).requires_grad_(),
+            torch.randn(47, Dp, device=DEV, generator=g).requires_grad_(),
+            torch.randn(15, 30, device=DEV, generator=g).requires_grad_() if Dn else None]
+    x = ops.embed_concat(words, pos, ner, tabs[0], tabs[1], tabs[2])
+    r = torch.randn(x.shape, device=DEV, generator=g)
+    (x * r).sum().backward()
+    ref_t = [t.detach().clone().requires_grad_() if t is not None else None for t in tabs]
+    parts = [torch.nn.functional.embedding(words, ref_t[0], padding_idx=0), torch.nn.functional.embedding(pos, ref_t[1])]
+    if Dn:
+        parts.append(torch.nn.functional.embedding(ner, ref_t[2]))
+    xr = torch.cat(parts, 2)
+    (xr * r).sum().backward()
+    assert torch.equal(x, xr)
+    for a, b in zip(tabs, ref_t):
+        if a is not None:
+            assert _rel(a.grad.cpu(), b.grad.cpu()) < 1e-5
+
+
+def test_k5_dropout_mask_is_replayed_in_backward_and_topn_freezes_rows():
+    V, E = 200, 64
+    batch = synth.make_batch(62, batch_size=30, vocab_size=V)
+    words, pos, ner = batch[0].to(DEV), batch[2].to(DEV), batch[3].to(DEV)
+    emb = (torch.rand(V, E, device=DEV) + 0.5).requires_grad_()
+    pw = (torch.rand(47, 8, device=DEV) + 0.5).requires_grad_()
+    nw = (torch.rand(15, 8, device=DEV) + 0.5).requires_grad_()
+    rng = torch.tensor([99, 5], dtype=torch.int64, device=DEV)
+    x = ops.embed_concat(words, pos, ner, emb, pw, nw, drop_p=0.5, rng_state=rng, subseq=3, topn=150)
+    keep = (x != 0)
+    frac = keep[words != 0].float().mean().item()
+    assert abs(frac - 0.5) < 0.02
+    r = torch.randn(x.shape, device=DEV)
+    (x * r).sum().backward()
+    want = torch.zeros(V, E, device=DEV)
+    want.index_put_((words.flatten(),), (r * keep * 2.0)[..., :E].reshape(-1, E), accumulate=True)
+    want[0] = 0
+    want[150:] = 0                                          # frozen rows (topn)
+    assert _rel(emb.grad.cpu(), want.cpu()) < 1e-5
+    x2 = ops.embed_concat(words, pos, ner, emb, pw, nw, drop_p=0.5, rng_state=rng + torch.tensor([0, 1], device=DEV),
+                          subseq=3)
+    assert not torch.equal(x2 != 0, keep)
