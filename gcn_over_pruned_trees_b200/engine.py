@@ -106,6 +106,7 @@ class GraphedTrainStep(object):
             if self.reducer is None:
                 self._update()
         entry['g1'], entry['loss'] = g1, loss
+        entry['grads'] = [p.grad for p in self.reducer.params if p.grad is not None] if self.reducer else None
         if self.reducer is not None:
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, pool=g1.pool()):
@@ -137,7 +138,7 @@ class GraphedTrainStep(object):
             entry['labels'].copy_(labels, non_blocking=True)
         entry['g1'].replay()
         if self.reducer is not None:
-            self.reducer.reduce()
+            self.reducer.reduce(entry['grads'])     # the buffers this shape's graph writes
             entry['g2'].replay()
         self.replays += 1
         return entry['loss']

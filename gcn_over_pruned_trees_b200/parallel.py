@@ -33,9 +33,11 @@ def init_from_env(backend=None):
 
 
 def shard_batch(batch, rank, world):
-    """Rows rank::world of a loader batch (the unit of work is a sentence; no tree spans two ranks)."""
+    """Rows rank::world of a loader batch (the unit of work is a sentence; no tree spans two ranks), re-padded to the
+    shard's own longest sentence, as the loader would have padded it (data/loader.py:167-174)."""
     idx = torch.arange(rank, batch[0].shape[0], world)
-    fields = [t[idx] for t in batch[:-1]]
+    width = int((~batch[1][idx]).sum(1).max()) if idx.numel() else 0
+    fields = [t[idx][:, :width].contiguous() if t.dim() >= 2 else t[idx] for t in batch[:-1]]
     return tuple(fields) + ([batch[-1][i] for i in idx.tolist()],)
 
 
@@ -55,32 +57,39 @@ class GradAllReducer(object):
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
-    def reduce(self):
+    def grads(self):
+        """The gradient tensors reduce() would act on right now (None entries skipped)."""
+        return [p.grad for p in self.params if p.grad is not None]
+
+    def reduce(self, grads=None):
+        """Average gradients in place.  ``grads`` pins the tensors (a CUDA-graph engine passes the buffers its graph
+        writes, which need not be what ``p.grad`` currently points at); default: the parameters' current ``.grad``."""
         world = self.world
         if world == 1:
             return
-        small = [p for p in self.params if p.grad is not None and p.grad.numel() < LARGE_NUMEL]
-        large = [p for p in self.params if p.grad is not None and p.grad.numel() >= LARGE_NUMEL]
+        grads = self.grads() if grads is None else grads
+        small = [g for g in grads if g.numel() < LARGE_NUMEL]
+        large = [g for g in grads if g.numel() >= LARGE_NUMEL]
         handles = []
-        for p in large:                      # in place, asynchronously, while the bucket is being packed
-            handles.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for g in large:                      # in place, asynchronously, while the bucket is being packed
+            handles.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         if small:
-            n = sum(p.grad.numel() for p in small)
-            if self._flat is None or self._flat.numel() != n or self._flat.device != small[0].grad.device:
-                self._flat = torch.empty(n, dtype=small[0].grad.dtype, device=small[0].grad.device)
+            n = sum(g.numel() for g in small)
+            if self._flat is None or self._flat.numel() != n or self._flat.device != small[0].device:
+                self._flat = torch.empty(n, dtype=small[0].dtype, device=small[0].device)
             views = []
             off = 0
-            for p in small:
-                k = p.grad.numel()
-                views.append(self._flat[off:off + k].view_as(p.grad))
+            for g in small:
+                k = g.numel()
+                views.append(self._flat[off:off + k].view_as(g))
                 off += k
-            torch._foreach_copy_(views, [p.grad for p in small])
+            torch._foreach_copy_(views, small)
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
             self._flat.div_(world)
-            torch._foreach_copy_([p.grad for p in small], views)
-        for h, p in zip(handles, large):
+            torch._foreach_copy_(small, views)
+        for h, g in zip(handles, large):
             h.wait()
-            p.grad.div_(world)
+            g.div_(world)
 
 
 def barrier():
