@@ -1,0 +1,281 @@
+// K3 (tensor-core mode) -- the W projection of a GCN layer as a tcgen05 / TMEM GEMM fed by TMA (sm_100a).
+//
+//   Y[M,N] = X[M,K] . W[N,K]^T     fp32 in HBM, TF32 on the 5th-gen tensor cores, fp32 accumulation in TMEM
+//
+// (the one dense contraction on the path: /root/reference/model/gcn.py:270-271 computes W(Ax) + W(h); by linearity a
+// single projection per layer suffices, see aggregate.cu).  Both operands are K-major, so fp32 rows are loaded as
+// they lie in HBM: TMA brings [128 x 32] / [N_tile x 32] fp32 boxes (128-byte rows, SWIZZLE_128B) into a 4-stage
+// shared-memory ring, one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = N_tile <= 256, K = 8 per
+// instruction, 4 per stage) with the accumulator in tensor memory, tcgen05.commit releases ring slots and finally
+// signals the epilogue warps, which read the accumulator with tcgen05.ld (32 lanes x 32 columns per warp) and store
+// fp32 rows.  No operand conversion pass: kind::tf32 consumes the fp32 bit patterns (low 13 mantissa bits ignored).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (warp w may only touch TMEM lanes 32*(w % 4) .. +31, so the four epilogue warps cover all 128 rows).
+//
+// dgrad  dX[M,K] = dY[M,N] . W[N,K]  runs through the same kernel with a transposed copy of W (tiny) as operand B.
+// Accuracy: one TF32 pass (10-bit mantissa operands, fp32 accumulate): ~1e-3 relative; the fp32-parity mode of
+// the package is the FFMA path in gemm_simt.cu.
+#include "gpt_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;        // rows per CTA tile (UMMA M)
+constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle atom
+constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
+constexpr int STAGES = 2;       // 2 x 48 KB per CTA: two CTAs share an SM, one's epilogue overlaps the other's MMAs
+constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();  // a lost arrival must fail the launch, never hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset (unused for swizzled K-major, canonical value 1) in [16,30), stride byte offset =
+// 8 rows x 128 B = 1024 B (>> 4 = 64) in [32,46), descriptor version 1 (Blackwell) in [46,48), layout 2 = SWIZZLE_128B
+// in [61,64).  The tile base must be 1024-byte aligned; advancing K inside the atom adds (bytes >> 4) to the address.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 float* __restrict__ C, int M, int N, int K, int n_tile, int tmem_cols) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_holder;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * n_tile;
+    const int nkb = (K + BK - 1) / BK;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_tile * BK * 4;
+    const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte aligned tiles
+    const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[STAGES]), done = smem_addr(&bars[2 * STAGES]);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // one warp allocates the accumulator columns and owns the deallocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_addr(&tmem_base_holder)), "r"((uint32_t)tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(empty0 + 8 * s, ((kb / STAGES) - 1) & 1);
+                const uint32_t a_dst = tiles + (uint32_t)s * (a_bytes + b_bytes), b_dst = a_dst + a_bytes;
+                mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
+                tma_load_2d(a_dst, &tm_a, full0 + 8 * s, kb * BK, m0);   // OOB rows / columns arrive as zeros
+                tma_load_2d(b_dst, &tm_b, full0 + 8 * s, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9,
+            // 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_src = tiles + (uint32_t)s * (a_bytes + b_bytes), b_src = a_src + a_bytes;
+                const uint64_t a_desc = make_kmajor_desc(a_src), b_desc = make_kmajor_desc(b_src);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes inside the swizzle atom = +2 in the address field
+                    umma_tf32(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(empty0 + 8 * s);           // slot is free once these MMAs have read it
+            }
+            umma_commit(done);                          // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        float* crow = C + (size_t)row * N + n0;
+        const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        for (int c0 = 0; c0 < n_tile; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                  "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                  "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int c = n0 + c0 + j;
+                    if (vec_ok && c + 3 < N) {
+                        *reinterpret_cast<float4*>(crow + c0 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                        __uint_as_float(v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (c + i < N) crow[c0 + j + i] = __uint_as_float(v[j + i]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
+                     : "memory");
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float t[32][33];
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (x < cols && y0 + j < rows) t[j][threadIdx.x] = in[(size_t)(y0 + j) * cols + x];
+    __syncthreads();
+    const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (ox < rows && oy0 + j < cols) out[(size_t)(oy0 + j) * rows + ox] = t[threadIdx.x][j];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// row-major fp32 [rows, cols] -> boxes of [box_rows x 32] floats, 128-byte swizzle, zero fill out of bounds
+int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return GPT_ERR_DRIVER;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GPT_OK : GPT_ERR_DRIVER;
+}
+
+// C[M,N] = A[M,K] . B[N,K]^T
+int run_tf32_gemm(const float* A, const float* B, float* C, int M, int N, int K, cudaStream_t st) {
+    if (M == 0) return GPT_OK;
+    // TMA: 16-byte aligned bases and row pitches
+    if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return GPT_ERR_UNSUPPORTED;
+    const int n_tiles = (N + 255) / 256;
+    int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;   // UMMA N: multiple of 16 at M = 128, <= 256
+    if (n_tile < 16) n_tile = 16;
+    int tmem_cols = 32;
+    while (tmem_cols < n_tile) tmem_cols <<= 1;
+    alignas(64) CUtensorMap tm_a, tm_b;
+    int rc = make_map(&tm_a, A, M, K, BM);
+    if (rc != GPT_OK) return rc;
+    if ((rc = make_map(&tm_b, B, N, K, n_tile)) != GPT_OK) return rc;
+    const size_t smem = (size_t)STAGES * (BM * BK * 4 + (size_t)n_tile * BK * 4) + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t a = cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (a != cudaSuccess) return (int)a;
+        configured = smem;
+    }
+    dim3 grid((M + BM - 1) / BM, n_tiles);
+    tf32_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, C, M, N, K, n_tile, tmem_cols);
+    return gpt_launch_status();
+}
+
+}  // namespace
+
+extern "C" int gpt_linear_fwd_tf32(const float* x, const float* w, float* y, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(x && w && y && M >= 0 && N >= 1 && K >= 1);
+    return run_tf32_gemm(x, w, y, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_workspace, int M, int N,
+                                     int K, void* stream) {
+    GPT_CHECK_ARG(dy && w && dx && wt_workspace && M >= 0 && N >= 1 && K >= 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    // operand B must be K-major over the reduction index n: W^T [K, N]
+    transpose_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, st>>>(w, wt_workspace, N, K);
+    int rc = gpt_launch_status();
+    if (rc != GPT_OK) return rc;
+    return run_tf32_gemm(dy, wt_workspace, dx, M, K, N, st);
+}

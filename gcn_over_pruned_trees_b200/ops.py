@@ -126,13 +126,24 @@ def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k):
 
 # ---- K3: projection ------------------------------------------------------------------------------------------
 
+def _tf32_ok(*dims):
+    return all(d % 4 == 0 for d in dims)
+
+
 def linear_fwd(x2d, weight, mode='fp32'):
+    """y = x W^T.  mode 'fp32': FFMA (parity mode); 'tf32': tcgen05/TMEM GEMM fed by TMA (falls back to FFMA when the
+    shape cannot be described to TMA, i.e. a row pitch that is not a multiple of 16 bytes)."""
     M, K = x2d.shape
     N = weight.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
-    if mode != 'fp32':
+    if mode not in GEMM_MODES:
+        raise _lib.GptError('unknown gemm mode %r' % mode)
+    if mode == 'tf32' and _tf32_ok(K):
+        _call('gpt_linear_fwd_tf32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
+    elif mode in ('fp32', 'tf32'):
+        _call('gpt_linear_fwd_f32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
+    else:
         raise _lib.GptError('gemm mode %r not built' % mode)
-    _call('gpt_linear_fwd_f32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
     return y
 
 
@@ -140,7 +151,11 @@ def linear_dgrad(dy, weight, mode='fp32'):
     M, N = dy.shape
     K = weight.shape[1]
     dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-    _call('gpt_linear_dgrad_f32', _ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream())
+    if mode == 'tf32' and _tf32_ok(N, K):
+        wt = torch.empty((K, N), dtype=torch.float32, device=dy.device)
+        _call('gpt_linear_dgrad_tf32', _ptr(dy), _ptr(weight), _ptr(dx), _ptr(wt), M, N, K, _stream())
+    else:
+        _call('gpt_linear_dgrad_f32', _ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream())
     return dx
 
 

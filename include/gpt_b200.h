@@ -103,6 +103,12 @@ int gpt_pool3_bwd(const float* gout, const int32_t* argmax, const uint8_t* flags
 int gpt_linear_fwd_f32(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
 int gpt_linear_dgrad_f32(const float* dy, const float* w, float* dx, int M, int N, int K, void* stream);
 int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
+/* K3 on the tensor cores: tcgen05.mma kind::tf32, TMA-fed, accumulator in TMEM (GPT_GEMM_TF32, ~1e-3 relative).
+ *     Needs K % 4 == 0 (and N % 4 == 0 for dgrad) and 16-byte aligned operands, else GPT_ERR_UNSUPPORTED.
+ *     dgrad takes a float [K*N] workspace for the transposed weight. */
+int gpt_linear_fwd_tf32(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
+int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_workspace, int M, int N, int K,
+                          void* stream);
 
 /* K5. input stage of GCN.forward (model/gcn.py:235-247): x[r] = dropout(cat[emb_w[words[r]], pos_w[pos[r]],
  *     ner_w[ner[r]]]) for the n_rows = B*T token slots; x is [n_rows, E+Dp+Dn].  pos/pos_w and ner/ner_w are NULL when

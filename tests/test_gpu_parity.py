@@ -495,3 +495,37 @@ def test_k5_dropout_mask_is_replayed_in_backward_and_topn_freezes_rows():
     x2 = ops.embed_concat(words, pos, ner, emb, pw, nw, drop_p=0.5, rng_state=rng + torch.tensor([0, 1], device=DEV),
                           subseq=3)
     assert not torch.equal(x2 != 0, keep)
+
+
+# ---------------------------------------------------------------- K3 on tcgen05 -------------------------------
+
+@pytest.mark.parametrize('M,N,K', [(128, 16, 32), (50, 200, 360), (2750, 200, 360), (2750, 200, 200), (4096, 512, 360),
+                                    (9999, 512, 512), (300, 300, 100), (777, 64, 84)])
+def test_k3_tcgen05_tf32_gemm(M, N, K):
+    # tolerance of one TF32 pass (10-bit mantissa operands, fp32 accumulation in TMEM): 2e-3 of the output scale
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g)
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    y = ops.linear_fwd(x, w, 'tf32')
+    assert _rel(y.cpu(), (x.double() @ w.double().t()).cpu()) < 2e-3
+    dx = ops.linear_dgrad(dy, w, 'tf32')
+    assert _rel(dx.cpu(), (dy.double() @ w.double()).cpu()) < 2e-3
+    # operands that are exactly representable in TF32 must give the fp32 result up to accumulation order
+    xq = (x.view(torch.int32) & -8192).view(torch.float32)
+    wq = (w.view(torch.int32) & -8192).view(torch.float32)
+    assert _rel(ops.linear_fwd(xq, wq, 'tf32').cpu(), (xq.double() @ wq.double().t()).cpu()) < 1e-5
+
+
+def test_model_in_tf32_mode_tracks_fp32_mode():
+    # stated bf16/tf32-class tolerance for the tensor-core mode: logits within 1e-2 relative of the fp32 path
+    torch.manual_seed(3)
+    batch = synth.make_batch(9, batch_size=50, vocab_size=800)
+    a = GCNTrainer(synth.tacred_opt(vocab_size=800, cuda=True))
+    b = GCNTrainer(synth.tacred_opt(vocab_size=800, cuda=True, gemm_mode='tf32'))
+    b.model.load_state_dict(a.model.state_dict())
+    a.model.eval(); b.model.eval()
+    with torch.no_grad():
+        la, _ = a.model([t.to(DEV) for t in batch[:-2]])
+        lb, _ = b.model([t.to(DEV) for t in batch[:-2]])
+    assert _rel(lb.cpu(), la.cpu()) < 1e-2
