@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--prune_k', type=int, default=1)
-    ap.add_argument('--gemm', default='fp32')
+    ap.add_argument('--gemm', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--eager', action='store_true', help='time the eager five-call step instead of the CUDA graph')
     ap.add_argument('--no-roofline', action='store_true', help='skip the large-shape aggregation roofline run')
     ap.add_argument('--no-cpu-baseline', action='store_true')

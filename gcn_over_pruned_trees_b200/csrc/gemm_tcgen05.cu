@@ -14,8 +14,17 @@
 // (warp w may only touch TMEM lanes 32*(w % 4) .. +31, so the four epilogue warps cover all 128 rows).
 //
 // dgrad  dX[M,K] = dY[M,N] . W[N,K]  runs through the same kernel with a transposed copy of W (tiny) as operand B.
-// Accuracy: one TF32 pass (10-bit mantissa operands, fp32 accumulate): ~1e-3 relative; the fp32-parity mode of
-// the package is the FFMA path in gemm_simt.cu.
+//
+// Accuracy modes.  kind::tf32 truncates each fp32 operand to its upper 19 bits (measured on B200: the low 13 mantissa
+// bits are ignored, for A and for B), so with  a = a_hi + a_lo,  a_hi = trunc_tf32(a),  a_lo = a - a_hi (exact):
+//   PASSES = 1:  A.B ~ A_hi.B_hi                                   one TF32 pass, ~1e-3 relative
+//   PASSES = 3:  A.B ~ A_hi.B_hi + A_lo.B_hi + A_hi.B_lo           "3xTF32": fp32-grade (~1e-6), the parity mode
+// For PASSES = 3 hi is *rounded* to TF32 (|lo| <= 2^-12 |a|, zero-mean), which makes the truncation the tensor core
+// applies to lo and the dropped lo.lo term ~2^-23 each.  B_hi / B_lo (the weight) are precomputed by a tiny kernel
+// and arrive by TMA; A_hi / A_lo are produced in shared memory by the four epilogue warps, which are idle during the
+// main loop: they rewrite the freshly landed A tile in place as hi and store lo next to it (element-wise, so the
+// 128B swizzle is preserved), fence the generic->async proxy and arrive on a per-stage mbarrier the MMA thread
+// waits on.
 #include "gpt_common.cuh"
 #include <cuda.h>
 
@@ -54,6 +63,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float v) {  // round to nearest TF32 (ties away), low 13 bits zero
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -80,26 +95,34 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 2)
+template <int PASSES>
+__global__ void __launch_bounds__(kGemmThreads, PASSES == 1 ? 2 : 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 float* __restrict__ C, int M, int N, int K, int n_tile, int tmem_cols) {
+                 const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
+                 int tmem_cols) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
+    __shared__ __align__(8) unsigned long long bars[3 * STAGES + 1];
     __shared__ uint32_t tmem_base_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * n_tile;
     const int nkb = (K + BK - 1) / BK;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_tile * BK * 4;
+    // stage layout: [A | A_lo | B | B_lo] (the lo tiles only for PASSES == 3); every tile is 1024-byte aligned
+    const uint32_t stage_bytes = (PASSES == 3 ? 2u : 1u) * (a_bytes + b_bytes);
+    const uint32_t off_alo = a_bytes, off_b = (PASSES == 3 ? 2u : 1u) * a_bytes, off_blo = off_b + b_bytes;
     const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte aligned tiles
-    const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[STAGES]), done = smem_addr(&bars[2 * STAGES]);
+    const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[STAGES]), split0 = smem_addr(&bars[2 * STAGES]);
+    const uint32_t done = smem_addr(&bars[3 * STAGES]);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b)) : "memory");
+        if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b_lo)) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
+            mbar_init(split0 + 8 * s, 128);   // the four splitter warps
         }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -120,10 +143,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 if (kb >= STAGES) mbar_wait(empty0 + 8 * s, ((kb / STAGES) - 1) & 1);
-                const uint32_t a_dst = tiles + (uint32_t)s * (a_bytes + b_bytes), b_dst = a_dst + a_bytes;
-                mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
-                tma_load_2d(a_dst, &tm_a, full0 + 8 * s, kb * BK, m0);   // OOB rows / columns arrive as zeros
-                tma_load_2d(b_dst, &tm_b, full0 + 8 * s, kb * BK, n0);
+                const uint32_t st = tiles + (uint32_t)s * stage_bytes;
+                mbar_expect_tx(full0 + 8 * s, a_bytes + (PASSES == 3 ? 2u : 1u) * b_bytes);
+                tma_load_2d(st, &tm_a, full0 + 8 * s, kb * BK, m0);      // OOB rows / columns arrive as zeros
+                tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, kb * BK, n0);
+                if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, kb * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -135,18 +159,48 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                    ((uint32_t)(BM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
-                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                // PASSES == 3: the splitters arrive after the TMA bytes have landed and A_lo is written
+                mbar_wait((PASSES == 3 ? split0 : full0) + 8 * s, (kb / STAGES) & 1);
                 tc_fence_after();
-                const uint32_t a_src = tiles + (uint32_t)s * (a_bytes + b_bytes), b_src = a_src + a_bytes;
-                const uint64_t a_desc = make_kmajor_desc(a_src), b_desc = make_kmajor_desc(b_src);
+                const uint32_t st = tiles + (uint32_t)s * stage_bytes;
+                const uint64_t a_desc = make_kmajor_desc(st), b_desc = make_kmajor_desc(st + off_b);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes inside the swizzle atom = +2 in the address field
                     umma_tf32(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                if (PASSES == 3) {
+                    const uint64_t alo_desc = make_kmajor_desc(st + off_alo), blo_desc = make_kmajor_desc(st + off_blo);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(tmem_base, alo_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(tmem_base, a_desc + 2 * k, blo_desc + 2 * k, idesc, 1u);
+                }
                 umma_commit(empty0 + 8 * s);           // slot is free once these MMAs have read it
             }
             umma_commit(done);                          // accumulator complete
         }
     } else {
+        if (PASSES == 3) {
+            // ===== splitters: A -> A_hi (in place), A_lo = A - A_hi, element-wise in the swizzled tile =====
+            const uint32_t t = threadIdx.x - 64;       // 0..127
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                const uint32_t src = tiles + (uint32_t)s * stage_bytes + t * 16u, dst = src + off_alo;
+#pragma unroll
+                for (uint32_t i = 0; i < a_bytes / (128 * 16); ++i) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + i * 2048u));
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + i * 2048u), "f"(h.x), "f"(h.y),
+                                 "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * 2048u), "f"(v.x - h.x),
+                                 "f"(v.y - h.y), "f"(v.z - h.z), "f"(v.w - h.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
+                mbar_arrive(split0 + 8 * s);
+            }
+        }
         // ===== epilogue: TMEM -> registers -> global =====
         mbar_wait(done, 0);
         tc_fence_after();
@@ -173,6 +227,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int c = n0 + c0 + j;
+                    if (c0 + j >= n_tile) break;        // n_tile is a multiple of 16, not of 32: stay inside this tile
                     if (vec_ok && c + 3 < N) {
                         *reinterpret_cast<float4*>(crow + c0 + j) =
                             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -235,30 +290,60 @@ int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_ro
     return r == CUDA_SUCCESS ? GPT_OK : GPT_ERR_DRIVER;
 }
 
-// C[M,N] = A[M,K] . B[N,K]^T
-int run_tf32_gemm(const float* A, const float* B, float* C, int M, int N, int K, cudaStream_t st) {
+__global__ void tf32_split_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
+                                  size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = in[i], h = tf32_hi(v);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
+template <int PASSES>
+int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
+                int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st) {
+    const size_t smem = (size_t)STAGES * (PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * 4) + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t a = cudaFuncSetAttribute(tf32_gemm_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (a != cudaSuccess) return (int)a;
+        configured = smem;
+    }
+    dim3 grid((M + BM - 1) / BM, n_tiles);
+    tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, tmem_cols);
+    return gpt_launch_status();
+}
+
+// C[M,N] = A[M,K] . B[N,K]^T ; b_lo != nullptr selects the 3xTF32 mode (b_lo = B - trunc_tf32(B), same layout)
+int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, int M, int N, int K, cudaStream_t st) {
     if (M == 0) return GPT_OK;
     // TMA: 16-byte aligned bases and row pitches
-    if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+        (reinterpret_cast<uintptr_t>(b_lo) & 15))
         return GPT_ERR_UNSUPPORTED;
     const int n_tiles = (N + 255) / 256;
     int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;   // UMMA N: multiple of 16 at M = 128, <= 256
     if (n_tile < 16) n_tile = 16;
     int tmem_cols = 32;
     while (tmem_cols < n_tile) tmem_cols <<= 1;
-    alignas(64) CUtensorMap tm_a, tm_b;
+    alignas(64) CUtensorMap tm_a, tm_b, tm_b_lo;
     int rc = make_map(&tm_a, A, M, K, BM);
     if (rc != GPT_OK) return rc;
     if ((rc = make_map(&tm_b, B, N, K, n_tile)) != GPT_OK) return rc;
-    const size_t smem = (size_t)STAGES * (BM * BK * 4 + (size_t)n_tile * BK * 4) + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t a = cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (a != cudaSuccess) return (int)a;
-        configured = smem;
-    }
-    dim3 grid((M + BM - 1) / BM, n_tiles);
-    tf32_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, C, M, N, K, n_tile, tmem_cols);
+    if ((rc = make_map(&tm_b_lo, b_lo ? b_lo : B, N, K, n_tile)) != GPT_OK) return rc;
+    if (b_lo != nullptr) return launch_gemm<3>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st);
+    return launch_gemm<1>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st);
+}
+
+int split_hi_lo(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {  // hi may alias in
+    tf32_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, hi, lo, n);
+    return gpt_launch_status();
+}
+
+int transpose(const float* w, float* wt, int N, int K, cudaStream_t st) {
+    transpose_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, st>>>(w, wt, N, K);
     return gpt_launch_status();
 }
 
@@ -266,16 +351,37 @@ int run_tf32_gemm(const float* A, const float* B, float* C, int M, int N, int K,
 
 extern "C" int gpt_linear_fwd_tf32(const float* x, const float* w, float* y, int M, int N, int K, void* stream) {
     GPT_CHECK_ARG(x && w && y && M >= 0 && N >= 1 && K >= 1);
-    return run_tf32_gemm(x, w, y, M, N, K, (cudaStream_t)stream);
+    return run_tf32_gemm(x, w, nullptr, y, M, N, K, (cudaStream_t)stream);
 }
 
-extern "C" int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_workspace, int M, int N,
-                                     int K, void* stream) {
-    GPT_CHECK_ARG(dy && w && dx && wt_workspace && M >= 0 && N >= 1 && K >= 1);
+extern "C" int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* workspace, int M, int N, int K,
+                                     void* stream) {
+    GPT_CHECK_ARG(dy && w && dx && workspace && M >= 0 && N >= 1 && K >= 1);
     cudaStream_t st = (cudaStream_t)stream;
-    // operand B must be K-major over the reduction index n: W^T [K, N]
-    transpose_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, st>>>(w, wt_workspace, N, K);
-    int rc = gpt_launch_status();
+    int rc = transpose(w, workspace, N, K, st);  // operand B must be K-major over the reduction index n: W^T [K, N]
     if (rc != GPT_OK) return rc;
-    return run_tf32_gemm(dy, wt_workspace, dx, M, K, N, st);
+    return run_tf32_gemm(dy, workspace, nullptr, dx, M, K, N, st);
+}
+
+extern "C" int gpt_linear_fwd_tf32x3(const float* x, const float* w, float* y, float* workspace, int M, int N, int K,
+                                     void* stream) {
+    GPT_CHECK_ARG(x && w && y && workspace && M >= 0 && N >= 1 && K >= 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* w_hi = workspace;
+    float* w_lo = workspace + (size_t)N * K;
+    int rc = split_hi_lo(w, w_hi, w_lo, (size_t)N * K, st);
+    if (rc != GPT_OK) return rc;
+    return run_tf32_gemm(x, w_hi, w_lo, y, M, N, K, st);
+}
+
+extern "C" int gpt_linear_dgrad_tf32x3(const float* dy, const float* w, float* dx, float* workspace, int M, int N,
+                                       int K, void* stream) {
+    GPT_CHECK_ARG(dy && w && dx && workspace && M >= 0 && N >= 1 && K >= 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wt = workspace;
+    float* wt_lo = workspace + (size_t)N * K;
+    int rc = transpose(w, wt, N, K, st);
+    if (rc != GPT_OK) return rc;
+    if ((rc = split_hi_lo(wt, wt, wt_lo, (size_t)N * K, st)) != GPT_OK) return rc;
+    return run_tf32_gemm(dy, wt, wt_lo, dx, M, K, N, st);
 }

@@ -140,7 +140,10 @@ def linear_fwd(x2d, weight, mode='fp32'):
         raise _lib.GptError('unknown gemm mode %r' % mode)
     if mode == 'tf32' and _tf32_ok(K):
         _call('gpt_linear_fwd_tf32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
-    elif mode in ('fp32', 'tf32'):
+    elif mode == 'tf32x3' and _tf32_ok(K):
+        ws = torch.empty((2, N, K), dtype=torch.float32, device=x2d.device)
+        _call('gpt_linear_fwd_tf32x3', _ptr(x2d), _ptr(weight), _ptr(y), _ptr(ws), M, N, K, _stream())
+    elif mode in ('fp32', 'tf32', 'tf32x3'):
         _call('gpt_linear_fwd_f32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
     else:
         raise _lib.GptError('gemm mode %r not built' % mode)
@@ -154,6 +157,9 @@ def linear_dgrad(dy, weight, mode='fp32'):
     if mode == 'tf32' and _tf32_ok(N, K):
         wt = torch.empty((K, N), dtype=torch.float32, device=dy.device)
         _call('gpt_linear_dgrad_tf32', _ptr(dy), _ptr(weight), _ptr(dx), _ptr(wt), M, N, K, _stream())
+    elif mode == 'tf32x3' and _tf32_ok(N, K):
+        ws = torch.empty((2, K, N), dtype=torch.float32, device=dy.device)
+        _call('gpt_linear_dgrad_tf32x3', _ptr(dy), _ptr(weight), _ptr(dx), _ptr(ws), M, N, K, _stream())
     else:
         _call('gpt_linear_dgrad_f32', _ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream())
     return dx

@@ -109,6 +109,13 @@ int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int 
 int gpt_linear_fwd_tf32(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
 int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_workspace, int M, int N, int K,
                           void* stream);
+/* K3, 3xTF32 (GPT_GEMM_TF32X3): A.B ~ A_hi.B_hi + A_lo.B_hi + A_hi.B_lo with hi = round_tf32(x), lo = x - hi;
+ *     fp32-grade accuracy (~1e-6 relative) on the tensor cores.  workspace: float [2*N*K] (weight hi / lo parts,
+ *     transposed for dgrad). */
+int gpt_linear_fwd_tf32x3(const float* x, const float* w, float* y, float* workspace, int M, int N, int K,
+                          void* stream);
+int gpt_linear_dgrad_tf32x3(const float* dy, const float* w, float* dx, float* workspace, int M, int N, int K,
+                            void* stream);
 
 /* K5. input stage of GCN.forward (model/gcn.py:235-247): x[r] = dropout(cat[emb_w[words[r]], pos_w[pos[r]],
  *     ner_w[ner[r]]]) for the n_rows = B*T token slots; x is [n_rows, E+Dp+Dn].  pos/pos_w and ner/ner_w are NULL when

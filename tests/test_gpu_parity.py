@@ -299,8 +299,9 @@ def test_k4_fully_masked_pool_is_minus_1e12():
 
 # ---------------------------------------------------------------- whole model ---------------------------------
 
-def _setup(golden_adj, name):
+def _setup(golden_adj, name, gemm_mode='fp32'):
     over, source, wseed = cases.MODEL_CASES[name]
+    over = dict(over, gemm_mode=gemm_mode)
     if source[0] == 'split':
         batch = cases.batch_from_npz(golden_adj, source[1])
         over = dict(over, vocab_size=int(golden_adj['vocab_size']))
@@ -316,9 +317,10 @@ def _setup(golden_adj, name):
     return opt, batch, trainer, oracle
 
 
+@pytest.mark.parametrize('gemm_mode', ('fp32', 'tf32x3'))
 @pytest.mark.parametrize('name', sorted(cases.MODEL_CASES))
-def test_model_eval_matches_reference_outputs(golden_adj, golden_model, name):
-    opt, batch, trainer, _ = _setup(golden_adj, name)
+def test_model_eval_matches_reference_outputs(golden_adj, golden_model, name, gemm_mode):
+    opt, batch, trainer, _ = _setup(golden_adj, name, gemm_mode)
     trainer.model.eval()
     with torch.no_grad():
         inputs = [t.to(DEV) for t in batch[:-2]]
@@ -333,9 +335,10 @@ def test_model_eval_matches_reference_outputs(golden_adj, golden_model, name):
     assert abs(ploss - float(golden_model['%s/predict_loss' % name])) <= 1e-5 * abs(ploss)
 
 
+@pytest.mark.parametrize('gemm_mode', ('fp32', 'tf32x3'))
 @pytest.mark.parametrize('name', cases.GRAD_CASES)
-def test_model_train_grads_match_oracle_with_injected_masks(golden_adj, name):
-    opt, batch, trainer, oracle = _setup(golden_adj, name)
+def test_model_train_grads_match_oracle_with_injected_masks(golden_adj, name, gemm_mode):
+    opt, batch, trainer, oracle = _setup(golden_adj, name, gemm_mode)
     B, T = batch[0].shape
     g = torch.Generator().manual_seed(99)
     in_dim = opt['emb_dim'] + opt['pos_dim'] + (opt['ner_dim'] if opt['dataset'] == 'tacred' else 0)
@@ -500,7 +503,7 @@ def test_k5_dropout_mask_is_replayed_in_backward_and_topn_freezes_rows():
 # ---------------------------------------------------------------- K3 on tcgen05 -------------------------------
 
 @pytest.mark.parametrize('M,N,K', [(128, 16, 32), (50, 200, 360), (2750, 200, 360), (2750, 200, 200), (4096, 512, 360),
-                                    (9999, 512, 512), (300, 300, 100), (777, 64, 84)])
+                                    (9999, 512, 512), (300, 300, 100), (777, 64, 84), (2750, 200, 400), (640, 72, 600)])
 def test_k3_tcgen05_tf32_gemm(M, N, K):
     # tolerance of one TF32 pass (10-bit mantissa operands, fp32 accumulation in TMEM): 2e-3 of the output scale
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
@@ -529,3 +532,29 @@ def test_model_in_tf32_mode_tracks_fp32_mode():
         la, _ = a.model([t.to(DEV) for t in batch[:-2]])
         lb, _ = b.model([t.to(DEV) for t in batch[:-2]])
     assert _rel(lb.cpu(), la.cpu()) < 1e-2
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 16, 32), (50, 200, 360), (2750, 200, 360), (2750, 200, 200), (4096, 512, 360),
+                                    (9999, 512, 512), (300, 300, 100), (777, 64, 84), (2750, 200, 400), (640, 72, 600)])
+def test_k3_tcgen05_3xtf32_gemm_is_fp32_grade(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g)
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    # the tensor core accumulates with truncation, so the error grows ~linearly with the reduction length
+    # (measured 6e-7 at K=32, 3e-6 at K=360); 1e-5 of the output scale is the bound this mode is held to
+    assert _rel(ops.linear_fwd(x, w, 'tf32x3').cpu(), (x.double() @ w.double().t()).cpu()) < 1e-5
+    assert _rel(ops.linear_dgrad(dy, w, 'tf32x3').cpu(), (dy.double() @ w.double()).cpu()) < 1e-5
+
+
+def test_tf32_operands_are_truncated_not_rounded():
+    # the 3xTF32 split relies on it: the tensor core must see exactly trunc_tf32(a) when handed a raw fp32 a
+    x = torch.zeros(128, 32, device=DEV)
+    w = torch.zeros(16, 32, device=DEV)
+    vals = [1 + 2 ** -11 + 2 ** -12, 1 + 2 ** -10 + 2 ** -11, -(1 + 2 ** -11 + 2 ** -12), 1 + 2 ** -13]
+    for i, v in enumerate(vals):
+        x[i, 0] = v
+    w[0, 0] = 1.0
+    y = ops.linear_fwd(x, w, 'tf32')
+    want = (x[:4, 0].view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(y[:4, 0], want)
