@@ -33,7 +33,7 @@ namespace {
 constexpr int BM = 128;        // rows per CTA tile (UMMA M)
 constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
-constexpr int STAGES = 2;       // 2 x 48 KB per CTA: two CTAs share an SM, one's epilogue overlaps the other's MMAs
+constexpr int kMaxStages = 8;   // ring depth is chosen at launch: as many stages as fit in shared memory
 constexpr int kGemmThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,12 +96,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 template <int PASSES>
-__global__ void __launch_bounds__(kGemmThreads, PASSES == 1 ? 2 : 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
-                 int tmem_cols) {
+                 int tmem_cols, int STAGES) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[3 * STAGES + 1];
+    __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,8 +112,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t stage_bytes = (PASSES == 3 ? 2u : 1u) * (a_bytes + b_bytes);
     const uint32_t off_alo = a_bytes, off_b = (PASSES == 3 ? 2u : 1u) * a_bytes, off_blo = off_b + b_bytes;
     const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte aligned tiles
-    const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[STAGES]), split0 = smem_addr(&bars[2 * STAGES]);
-    const uint32_t done = smem_addr(&bars[3 * STAGES]);
+    const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[kMaxStages]);
+    const uint32_t split0 = smem_addr(&bars[2 * kMaxStages]), done = smem_addr(&bars[3 * kMaxStages]);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
@@ -303,7 +303,13 @@ __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restric
 template <int PASSES>
 int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
                 int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st) {
-    const size_t smem = (size_t)STAGES * (PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * 4) + 1024;
+    const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * 4);
+    int stages = (int)((200 * 1024) / stage);
+    const int nkb = (K + BK - 1) / BK;
+    stages = stages > kMaxStages ? kMaxStages : stages;
+    stages = stages > nkb ? nkb : stages;
+    stages = stages < 1 ? 1 : stages;
+    const size_t smem = (size_t)stages * stage + 1024;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t a = cudaFuncSetAttribute(tf32_gemm_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -312,18 +318,24 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
         configured = smem;
     }
     dim3 grid((M + BM - 1) / BM, n_tiles);
-    tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, tmem_cols);
+    tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, tmem_cols,
+                                                               stages);
     return gpt_launch_status();
 }
 
-// C[M,N] = A[M,K] . B[N,K]^T ; b_lo != nullptr selects the 3xTF32 mode (b_lo = B - trunc_tf32(B), same layout)
+// C[M,N] = A[M,K] . B[N,K]^T ; b_lo != nullptr selects the 3xTF32 mode (B = rounded hi part, b_lo = lo part)
 int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, int M, int N, int K, cudaStream_t st) {
     if (M == 0) return GPT_OK;
     // TMA: 16-byte aligned bases and row pitches
     if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
         (reinterpret_cast<uintptr_t>(b_lo) & 15))
         return GPT_ERR_UNSUPPORTED;
-    const int n_tiles = (N + 255) / 256;
+    // N tile: as wide as possible (A is re-read once per N tile) unless that leaves most SMs idle; a narrower tile
+    // also makes the stages smaller, i.e. the ring deeper, which is what hides TMA latency when M is small
+    const int m_tiles = (M + BM - 1) / BM;
+    int cap = 256;
+    while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
+    const int n_tiles = (N + cap - 1) / cap;
     int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;   // UMMA N: multiple of 16 at M = 128, <= 256
     if (n_tile < 16) n_tile = 16;
     int tmem_cols = 32;
@@ -335,6 +347,32 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
     if ((rc = make_map(&tm_b_lo, b_lo ? b_lo : B, N, K, n_tile)) != GPT_OK) return rc;
     if (b_lo != nullptr) return launch_gemm<3>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st);
     return launch_gemm<1>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st);
+}
+
+// w [N,K] -> ws = [w_hi | w_lo | wt_hi | wt_lo]  (wt = w^T [K,N]); hi = round_tf32, lo = w - hi
+__global__ void weight_prep_kernel(const float* __restrict__ w, float* __restrict__ ws, int N, int K) {
+    __shared__ float th[32][33], tl[32][33];
+    const size_t nk = (size_t)N * K;
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;   // x: k index, y: n index
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        if (x < K && y0 + j < N) {
+            const size_t i = (size_t)(y0 + j) * K + x;
+            const float v = w[i], h = tf32_hi(v);
+            ws[i] = h;
+            ws[nk + i] = v - h;
+            th[j][threadIdx.x] = h;
+            tl[j][threadIdx.x] = v - h;
+        }
+    }
+    __syncthreads();
+    const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;  // ox: n index, oy: k index
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        if (ox < N && oy0 + j < K) {
+            const size_t o = (size_t)(oy0 + j) * N + ox;
+            ws[2 * nk + o] = th[threadIdx.x][j];
+            ws[3 * nk + o] = tl[threadIdx.x][j];
+        }
+    }
 }
 
 int split_hi_lo(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {  // hi may alias in
@@ -363,25 +401,20 @@ extern "C" int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx,
     return run_tf32_gemm(dy, workspace, nullptr, dx, M, K, N, st);
 }
 
-extern "C" int gpt_linear_fwd_tf32x3(const float* x, const float* w, float* y, float* workspace, int M, int N, int K,
-                                     void* stream) {
-    GPT_CHECK_ARG(x && w && y && workspace && M >= 0 && N >= 1 && K >= 1);
-    cudaStream_t st = (cudaStream_t)stream;
-    float* w_hi = workspace;
-    float* w_lo = workspace + (size_t)N * K;
-    int rc = split_hi_lo(w, w_hi, w_lo, (size_t)N * K, st);
-    if (rc != GPT_OK) return rc;
-    return run_tf32_gemm(x, w_hi, w_lo, y, M, N, K, st);
+extern "C" int gpt_weight_prep_tf32x3(const float* w, float* ws, int N, int K, void* stream) {
+    GPT_CHECK_ARG(w && ws && N >= 1 && K >= 1);
+    weight_prep_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(w, ws, N, K);
+    return gpt_launch_status();
 }
 
-extern "C" int gpt_linear_dgrad_tf32x3(const float* dy, const float* w, float* dx, float* workspace, int M, int N,
-                                       int K, void* stream) {
-    GPT_CHECK_ARG(dy && w && dx && workspace && M >= 0 && N >= 1 && K >= 1);
-    cudaStream_t st = (cudaStream_t)stream;
-    float* wt = workspace;
-    float* wt_lo = workspace + (size_t)N * K;
-    int rc = transpose(w, wt, N, K, st);
-    if (rc != GPT_OK) return rc;
-    if ((rc = split_hi_lo(wt, wt, wt_lo, (size_t)N * K, st)) != GPT_OK) return rc;
-    return run_tf32_gemm(dy, wt, wt_lo, dx, M, K, N, st);
+extern "C" int gpt_linear_fwd_tf32x3(const float* x, const float* ws, float* y, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(x && ws && y && M >= 0 && N >= 1 && K >= 1);
+    return run_tf32_gemm(x, ws, ws + (size_t)N * K, y, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* dx, int M, int N, int K,
+                                       void* stream) {
+    GPT_CHECK_ARG(dy && ws && dx && M >= 0 && N >= 1 && K >= 1);
+    const size_t nk = (size_t)N * K;
+    return run_tf32_gemm(dy, ws + 2 * nk, ws + 3 * nk, dx, M, K, N, (cudaStream_t)stream);
 }

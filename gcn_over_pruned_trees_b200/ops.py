@@ -130,19 +130,30 @@ def _tf32_ok(*dims):
     return all(d % 4 == 0 for d in dims)
 
 
-def linear_fwd(x2d, weight, mode='fp32'):
-    """y = x W^T.  mode 'fp32': FFMA (parity mode); 'tf32': tcgen05/TMEM GEMM fed by TMA (falls back to FFMA when the
-    shape cannot be described to TMA, i.e. a row pitch that is not a multiple of 16 bytes)."""
+def weight_prep(weight, mode):
+    """Per-step operand preparation of the 3xTF32 projection: [w_hi | w_lo | w^T_hi | w^T_lo]; None otherwise."""
+    N, K = weight.shape
+    if mode != 'tf32x3' or not _tf32_ok(N, K):
+        return None
+    ws = torch.empty((4, N * K), dtype=torch.float32, device=weight.device)
+    _call('gpt_weight_prep_tf32x3', _ptr(weight), _ptr(ws), N, K, _stream())
+    return ws
+
+
+def linear_fwd(x2d, weight, mode='fp32', ws=None):
+    """y = x W^T.  'tf32x3': tcgen05/TMEM GEMM fed by TMA, 3xTF32 (fp32-grade); 'tf32': one TF32 pass; 'fp32': FFMA.
+    The tensor-core modes fall back to FFMA when the shape cannot be described to TMA (row pitch % 16 B != 0)."""
     M, K = x2d.shape
     N = weight.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     if mode not in GEMM_MODES:
         raise _lib.GptError('unknown gemm mode %r' % mode)
+    if mode == 'tf32x3' and ws is None:
+        ws = weight_prep(weight, mode)
     if mode == 'tf32' and _tf32_ok(K):
         _call('gpt_linear_fwd_tf32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
-    elif mode == 'tf32x3' and _tf32_ok(K):
-        ws = torch.empty((2, N, K), dtype=torch.float32, device=x2d.device)
-        _call('gpt_linear_fwd_tf32x3', _ptr(x2d), _ptr(weight), _ptr(y), _ptr(ws), M, N, K, _stream())
+    elif mode == 'tf32x3' and ws is not None:
+        _call('gpt_linear_fwd_tf32x3', _ptr(x2d), _ptr(ws), _ptr(y), M, N, K, _stream())
     elif mode in ('fp32', 'tf32', 'tf32x3'):
         _call('gpt_linear_fwd_f32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
     else:
@@ -150,16 +161,17 @@ def linear_fwd(x2d, weight, mode='fp32'):
     return y
 
 
-def linear_dgrad(dy, weight, mode='fp32'):
+def linear_dgrad(dy, weight, mode='fp32', ws=None):
     M, N = dy.shape
     K = weight.shape[1]
     dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    if mode == 'tf32x3' and ws is None:
+        ws = weight_prep(weight, mode)
     if mode == 'tf32' and _tf32_ok(N, K):
         wt = torch.empty((K, N), dtype=torch.float32, device=dy.device)
         _call('gpt_linear_dgrad_tf32', _ptr(dy), _ptr(weight), _ptr(dx), _ptr(wt), M, N, K, _stream())
-    elif mode == 'tf32x3' and _tf32_ok(N, K):
-        ws = torch.empty((2, K, N), dtype=torch.float32, device=dy.device)
-        _call('gpt_linear_dgrad_tf32x3', _ptr(dy), _ptr(weight), _ptr(dx), _ptr(ws), M, N, K, _stream())
+    elif mode == 'tf32x3' and ws is not None:
+        _call('gpt_linear_dgrad_tf32x3', _ptr(dy), _ptr(ws), _ptr(dx), M, N, K, _stream())
     else:
         _call('gpt_linear_dgrad_f32', _ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream())
     return dx
@@ -211,22 +223,23 @@ class _GcnLayer(torch.autograd.Function):
         if drop_mask is not None:
             drop_mask = _dev(drop_mask, torch.float32, 'drop_mask')
         B, T, K = x.shape
-        y = linear_fwd(x.view(B * T, K), weight, gemm_mode)
+        ws = weight_prep(weight, gemm_mode)          # split / transposed weight, shared by forward and dgrad
+        y = linear_fwd(x.view(B * T, K), weight, gemm_mode, ws)
         out, act = aggregate_fwd(y, csr, bias, use_adj, drop_p if drop_mask is None else 0.0, rng_state, subseq,
                                  drop_mask, want_act=True)
         ctx.csr, ctx.use_adj, ctx.gemm_mode = csr, use_adj, gemm_mode
         ctx.drop_p = drop_p if drop_mask is None else 0.0
-        ctx.save_for_backward(x, weight, act, drop_mask)
+        ctx.save_for_backward(x, weight, act, drop_mask, ws)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, weight, act, drop_mask = ctx.saved_tensors
+        x, weight, act, drop_mask, ws = ctx.saved_tensors
         B, T, K = x.shape
         gout = _dev(gout, torch.float32, 'grad_out')
         dy, dbias = aggregate_bwd(gout, None, ctx.csr, ctx.use_adj, ctx.drop_p, drop_mask,
                                   want_dbias=ctx.needs_input_grad[2], act=act)
-        dx = linear_dgrad(dy, weight, ctx.gemm_mode).view(B, T, K) if ctx.needs_input_grad[0] else None
+        dx = linear_dgrad(dy, weight, ctx.gemm_mode, ws).view(B, T, K) if ctx.needs_input_grad[0] else None
         dw = linear_wgrad(dy, x.view(B * T, K), ctx.gemm_mode) if ctx.needs_input_grad[1] else None
         return dx, dw, dbias, None, None, None, None, None, None, None
 

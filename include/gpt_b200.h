@@ -110,12 +110,12 @@ int gpt_linear_fwd_tf32(const float* x, const float* w, float* y, int M, int N, 
 int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_workspace, int M, int N, int K,
                           void* stream);
 /* K3, 3xTF32 (GPT_GEMM_TF32X3): A.B ~ A_hi.B_hi + A_lo.B_hi + A_hi.B_lo with hi = round_tf32(x), lo = x - hi;
- *     fp32-grade accuracy (~1e-6 relative) on the tensor cores.  workspace: float [2*N*K] (weight hi / lo parts,
- *     transposed for dgrad). */
-int gpt_linear_fwd_tf32x3(const float* x, const float* w, float* y, float* workspace, int M, int N, int K,
-                          void* stream);
-int gpt_linear_dgrad_tf32x3(const float* dy, const float* w, float* dx, float* workspace, int M, int N, int K,
-                            void* stream);
+ *     fp32-grade accuracy on the tensor cores (the default projection; passes the 1e-5 logits parity).
+ *     gpt_weight_prep_tf32x3 splits / transposes the weight once per step into ws = float [4*N*K]
+ *     ([w_hi | w_lo | w^T_hi | w^T_lo]); fwd and dgrad then take ws in place of w. */
+int gpt_weight_prep_tf32x3(const float* w, float* ws, int N, int K, void* stream);
+int gpt_linear_fwd_tf32x3(const float* x, const float* ws, float* y, int M, int N, int K, void* stream);
+int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* dx, int M, int N, int K, void* stream);
 
 /* K5. input stage of GCN.forward (model/gcn.py:235-247): x[r] = dropout(cat[emb_w[words[r]], pos_w[pos[r]],
  *     ner_w[ner[r]]]) for the n_rows = B*T token slots; x is [n_rows, E+Dp+Dn].  pos/pos_w and ner/ner_w are NULL when
