@@ -13,6 +13,7 @@ _c_int = ctypes.c_int
 _c_f = ctypes.c_float
 _c_u32 = ctypes.c_uint32
 _p = ctypes.c_void_p
+_c_ll = ctypes.c_longlong
 
 # name -> argtypes; every function returns int except gpt_error_string
 SIGNATURES = {
@@ -27,6 +28,7 @@ SIGNATURES = {
     'gpt_linear_fwd_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_wgrad_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
+    'gpt_linear_wgrad_f32_acc': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_fwd_tf32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_tf32': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_weight_prep_tf32x3': [_p, _p, _c_int, _c_int, _p],
@@ -37,6 +39,12 @@ SIGNATURES = {
                       _c_u32, _p],
     'gpt_embed_rows_sqnorm': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_embed_rows_sgd': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _p],
+    'gpt_head_fwd_bwd': [_p, _p, _p, _p, _c_int, _p, _p, _c_int, _c_int, _c_int, _c_f, _c_int, _p, _p, _p, _p, _p, _p,
+                         _p],
+    'gpt_head_wgrad': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p],
+    'gpt_update_partials': [_c_ll, _c_int],
+    'gpt_update_sqnorm': [_p, _c_ll, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_update_apply': [_p, _p, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _c_f, _p, _p, _p],
 }
 
 _lib = None

@@ -137,7 +137,7 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
 
 template <bool A_KC, bool B_KC>
 int run_sgemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int splits,
-              cudaStream_t st) {
+              cudaStream_t st, bool force_atomic = false) {
     if (M == 0 || N == 0) return GPT_OK;
     splits = max(1, min(splits, (K + BK - 1) / BK));
     int k_per_split = ((K + splits - 1) / splits + BK - 1) / BK * BK;
@@ -145,7 +145,7 @@ int run_sgemm(int M, int N, int K, const float* A, int lda, const float* B, int 
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
     if (grid.y > 65535 || grid.z > 65535) return GPT_ERR_UNSUPPORTED;
     sgemm_kernel<A_KC, B_KC><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, k_per_split,
-                                                           splits > 1 ? 1 : 0);
+                                                           (splits > 1 || force_atomic) ? 1 : 0);
     return gpt_launch_status();
 }
 
@@ -180,4 +180,12 @@ extern "C" int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, 
         if (rc != GPT_OK || M == 0) return rc;
     }
     return run_sgemm<false, false>(N, K, M, dy, N, x, K, dw, K, splits, st);
+}
+
+extern "C" int gpt_linear_wgrad_f32_acc(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(dy && x && dw && M >= 0 && N >= 1 && K >= 1);
+    if (M == 0) return GPT_OK;
+    const long tiles = (long)((N + BN - 1) / BN) * ((K + BM - 1) / BM);
+    int splits = (int)max(1L, min((long)(M + 255) / 256, (4L * 148 + tiles - 1) / tiles));
+    return run_sgemm<false, false>(N, K, M, dy, N, x, K, dw, K, splits, (cudaStream_t)stream, /*force_atomic=*/true);
 }

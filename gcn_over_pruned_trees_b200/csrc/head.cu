@@ -1,0 +1,398 @@
+// K6 -- classifier head: out_mlp + classifier + loss, forward and backward, in two launches.
+//
+// Replaces, for one batch of pooled sentence vectors [B, 3H] (the output of K4):
+//   out_mlp    Linear(3H,H)+ReLU, (mlp_layers-1) x Linear(H,H)+ReLU       /root/reference/model/gcn.py:64-68,122
+//   classifier Linear(H, num_class)                                        model/gcn.py:21,29
+//   loss       CrossEntropy(mean) + pooling_l2 * mean_b sum_h h_out^2      model/trainer.py:94-100
+// and the autograd of all of it (loss.backward(), train.py:221).  In the reference this is ~45 ATen launches per
+// step on [50, <=600] operands -- pure launch latency.  Here:
+//   head_fwd_bwd_kernel : one CTA per sentence (R sentences when B is large).  Every layer is a matrix-vector
+//       product against weights that all CTAs stream from L2 at the same time: warp-per-output-row dot products with
+//       128-bit loads for the forward, thread-per-column sums for the data gradient.  Activations never leave shared
+//       memory; the kernel emits logits, the per-sentence loss, d(loss)/d(pooled) and what the weight gradient needs.
+//   head_wgrad_kernel   : dW_l = dpre_l^T . in_l and db_l for every layer as 32x64 tiles of one flat grid, each tile
+//       summing over the whole batch (no atomics: deterministic), plus one CTA that adds the per-sentence losses in
+//       a fixed order.
+#include "gpt_common.cuh"
+
+namespace {
+
+constexpr int kHeadThreads = 512;
+constexpr int kMaxMlp = 4;
+constexpr int kDgradPartCols = 2048;  // floats of split-N partial sums per sentence (G * K <= 4 * kHeadThreads)
+
+struct HeadParams {
+    const float* pooled;        // [B, 3H]
+    const long long* labels;    // [B]
+    const float* w[kMaxMlp];    // w[0] [H, 3H], w[l>0] [H, H]   (nn.Linear layout)
+    const float* b[kMaxMlp];    // [H]
+    const float* wc;            // [C, H]
+    const float* bc;            // [C]
+    int B, H, C, n_mlp, train;
+    float pooling_l2, inv_B;
+    float* logits;              // [B, C]
+    float* loss_rows;           // [B]  CE_b / B + pooling_l2 * |h_out_b|^2 / B
+    float* acts;                // [B, n_mlp, H]  post-ReLU activations          (train)
+    float* dacts;               // [B, n_mlp, H]  d loss / d pre-activation      (train)
+    float* dlogits;             // [B, C]                                        (train)
+    float* dpooled;             // [B, 3H]                                       (train)
+};
+
+// s_out[r][n] = act(sum_k s_in[r][k] * W[n][k] + bias[n]);  K % 4 == 0; one warp per 4 output rows of W
+template <int R, bool RELU>
+__device__ __forceinline__ void dense_fwd(const float* __restrict__ W, const float* __restrict__ bias,
+                                          const float* s_in, int ld_in, float* s_out, int ld_out, int N, int K) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int K4 = K >> 2;
+    for (int n0 = warp * 4; n0 < N; n0 += nw * 4) {
+        float acc[4][R];
+        const float4* wr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            wr[j] = reinterpret_cast<const float4*>(W + (size_t)min(n0 + j, N - 1) * K);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
+        }
+        for (int k4 = lane; k4 < K4; k4 += 32) {
+            float4 wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = __ldg(wr[j] + k4);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 x = reinterpret_cast<const float4*>(s_in + r * ld_in)[k4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc[j][r] += wv[j].x * x.x + wv[j].y * x.y + wv[j].z * x.z + wv[j].w * x.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float v = warp_sum_f(acc[j][r]);
+                if (lane == j * R + r && n0 + j < N) {
+                    const float o = v + bias[n0 + j];
+                    s_out[r * ld_out + n0 + j] = RELU ? fmaxf(o, 0.f) : o;
+                }
+            }
+        }
+    }
+}
+
+// s_din[r][k] = sum_n s_dout[r][n] * W[n][k]; a thread owns 4 consecutive k (one 128-bit column of W) and a residue
+// class of n; the G classes are added through s_part.  Rows of W whose dout is zero for every sentence of the CTA
+// (ReLU-dead units: about half) are skipped.
+template <int R>
+__device__ __forceinline__ void dense_dgrad(const float* __restrict__ W, const float* s_dout, int ld_dout,
+                                            float* s_part, float* s_din, int ld_din, int N, int K) {
+    const int K4 = K >> 2;
+    const int G = K4 <= (int)blockDim.x ? min((int)blockDim.x / K4, kDgradPartCols / K) : 1;
+    const int Gc = G < 1 ? 1 : G;
+    for (int item = threadIdx.x; item < Gc * K4; item += blockDim.x) {
+        const int g = item / K4, k4 = item - g * K4;
+        float4 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* wc = reinterpret_cast<const float4*>(W) + k4;
+#pragma unroll 4
+        for (int n = g; n < N; n += Gc) {
+            float d[R];
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { d[r] = s_dout[r * ld_dout + n]; any |= d[r] != 0.f; }
+            if (!any) continue;
+            const float4 wv = __ldg(wc + (size_t)n * K4);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r].x += d[r] * wv.x; acc[r].y += d[r] * wv.y; acc[r].z += d[r] * wv.z; acc[r].w += d[r] * wv.w;
+            }
+        }
+        if (Gc == 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) reinterpret_cast<float4*>(s_din + r * ld_din)[k4] = acc[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) reinterpret_cast<float4*>(s_part + (size_t)(g * R + r) * K)[k4] = acc[r];
+        }
+    }
+    __syncthreads();
+    if (Gc > 1) {
+        for (int i = threadIdx.x; i < R * K; i += blockDim.x) {
+            const int r = i / K, k = i - r * K;
+            float s = 0.f;
+            for (int g = 0; g < Gc; ++g) s += s_part[(size_t)(g * R + r) * K + k];
+            s_din[r * ld_din + k] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_bwd_kernel(const HeadParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = p.H, C = p.C, K0 = 3 * p.H, L = p.n_mlp;
+    const int Cp = (C + 3) & ~3;
+    float* s_in = smem;                          // [R][K0]      pooled rows, later d(pooled)
+    float* s_h = s_in + R * K0;                  // [L][R][H]    post-ReLU activations
+    float* s_logit = s_h + L * R * H;            // [R][Cp]
+    float* s_dl = s_logit + R * Cp;              // [R][Cp]
+    float* s_d0 = s_dl + R * Cp;                 // [R][H]
+    float* s_d1 = s_d0 + R * H;                  // [R][H]
+    float* s_part = s_d1 + R * H;                // [R][max(kDgradPartCols, K0)]
+    const int b0 = blockIdx.x * R;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < R * (K0 >> 2); i += blockDim.x) {
+        const int r = i / (K0 >> 2), k4 = i - r * (K0 >> 2);
+        const int b = min(b0 + r, p.B - 1);
+        reinterpret_cast<float4*>(s_in + r * K0)[k4] = __ldg(reinterpret_cast<const float4*>(p.pooled + (size_t)b * K0) + k4);
+    }
+    __syncthreads();
+
+    // ---- forward -------------------------------------------------------------------------------------------------
+    for (int l = 0; l < L; ++l) {
+        const float* in = l == 0 ? s_in : s_h + (l - 1) * R * H;
+        dense_fwd<R, true>(p.w[l], p.b[l], in, l == 0 ? K0 : H, s_h + l * R * H, H, H, l == 0 ? K0 : H);
+        __syncthreads();
+    }
+    dense_fwd<R, false>(p.wc, p.bc, s_h + (L - 1) * R * H, H, s_logit, Cp, C, H);
+    __syncthreads();
+
+    // ---- loss + d logits: one warp per sentence --------------------------------------------------------------------
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < R && b0 + warp < p.B) {
+            const int r = warp, b = b0 + r;
+            const float* lg = s_logit + r * Cp;
+            float m = -INFINITY;
+            for (int c = lane; c < C; c += 32) m = fmaxf(m, lg[c]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(GPT_FULL_MASK, m, o));
+            float s = 0.f;
+            for (int c = lane; c < C; c += 32) s += expf(lg[c] - m);
+            s = warp_sum_f(s);
+            const float lse = m + logf(s);
+            const int label = (int)p.labels[b];
+            float l2 = 0.f;
+            if (p.pooling_l2 > 0.f) {
+                for (int k = lane; k < H; k += 32) { const float v = s_in[r * K0 + k]; l2 += v * v; }
+                l2 = warp_sum_f(l2);
+            }
+            for (int c = lane; c < C; c += 32) {
+                const float pr = expf(lg[c] - lse);
+                const float d = (pr - (c == label ? 1.f : 0.f)) * p.inv_B;
+                s_dl[r * Cp + c] = d;
+                p.logits[(size_t)b * C + c] = lg[c];
+                if (p.train) p.dlogits[(size_t)b * C + c] = d;
+            }
+            if (lane == 0) p.loss_rows[b] = (lse - lg[label]) * p.inv_B + p.pooling_l2 * l2 * p.inv_B;
+        } else if (warp < R) {
+            for (int c = lane; c < C; c += 32) s_dl[warp * Cp + c] = 0.f;   // padding sentence of the last CTA
+        }
+    }
+    if (!p.train) return;
+    __syncthreads();
+
+    // ---- backward: data gradients down to d(pooled) ----------------------------------------------------------------
+    for (int i = tid; i < R * L * H; i += blockDim.x) {          // activations for the weight-gradient kernel
+        const int l = i / (R * H), rem = i - l * R * H, r = rem / H, n = rem - r * H;
+        if (b0 + r < p.B) p.acts[((size_t)(b0 + r) * L + l) * H + n] = s_h[i];
+    }
+    dense_dgrad<R>(p.wc, s_dl, Cp, s_part, s_d0, H, C, H);        // d post-activation of the last mlp layer
+    float* d_cur = s_d0;
+    float* d_nxt = s_d1;
+    for (int l = L - 1; l >= 0; --l) {
+        for (int i = tid; i < R * H; i += blockDim.x) {           // through the ReLU; keep for dW_l
+            const int r = i / H, n = i - r * H;
+            const float d = s_h[(l * R + r) * H + n] > 0.f ? d_cur[i] : 0.f;
+            d_cur[i] = d;
+            if (b0 + r < p.B) p.dacts[((size_t)(b0 + r) * L + l) * H + n] = d;
+        }
+        __syncthreads();
+        if (l > 0) {
+            dense_dgrad<R>(p.w[l], d_cur, H, s_part, d_nxt, H, H, H);
+            float* t = d_cur; d_cur = d_nxt; d_nxt = t;
+        } else {
+            // d(pooled) = d_pre0 . W0 + 2 * pooling_l2 / B * [h_out, 0, 0]; s_in still holds the pooled rows
+            float* s_dp = s_h;                                    // activations are no longer needed: reuse as [R][K0]
+            const bool fits = L * H >= K0;                        // s_h holds L*R*H floats
+            float* dst = fits ? s_dp : s_part + (size_t)R * max(kDgradPartCols, K0);   // spill area past the partials
+            dense_dgrad<R>(p.w[0], d_cur, H, s_part, dst, K0, H, K0);
+            const float c2 = 2.f * p.pooling_l2 * p.inv_B;
+            for (int i = tid; i < R * K0; i += blockDim.x) {
+                const int r = i / K0, k = i - r * K0;
+                if (b0 + r >= p.B) continue;
+                float v = dst[i];
+                if (k < H) v += c2 * s_in[i];
+                p.dpooled[(size_t)(b0 + r) * K0 + k] = v;
+            }
+        }
+    }
+}
+
+size_t head_smem_bytes(int R, int H, int C, int L) {
+    const int K0 = 3 * H, Cp = (C + 3) & ~3;
+    size_t f = (size_t)R * K0 + (size_t)L * R * H + 2 * (size_t)R * Cp + 2 * (size_t)R * H +
+               (size_t)R * (K0 > kDgradPartCols ? K0 : kDgradPartCols);
+    if (L * H < K0) f += (size_t)R * K0;         // separate d(pooled) staging when it does not fit over s_h
+    return f * sizeof(float);
+}
+
+// ---- weight gradients ----------------------------------------------------------------------------------------------
+
+constexpr int kWgThreads = 256, kTN = 32, kTK = 64, kTB = 32;
+
+struct WgradParams {
+    const float* pooled;        // [B, 3H]
+    const float* acts;          // [B, L, H]
+    const float* dacts;         // [B, L, H]
+    const float* dlogits;       // [B, C]
+    const float* loss_rows;     // [B]
+    int B, H, C, n_mlp;
+    float* dw[kMaxMlp + 1];     // per layer, classifier last
+    float* db[kMaxMlp + 1];
+    float* loss;                // scalar
+    int tile_start[kMaxMlp + 2];
+};
+
+__global__ void __launch_bounds__(kWgThreads)
+head_wgrad_kernel(const WgradParams p) {
+    __shared__ float s_d[kTB][kTN + 1];
+    __shared__ __align__(16) float s_x[kTB][kTK];
+    __shared__ float s_red[kWgThreads / 32];
+    const int L = p.n_mlp, tid = threadIdx.x;
+    const int total = p.tile_start[L + 1];
+    if ((int)blockIdx.x == total) {            // the extra CTA: loss = sum_b loss_rows[b], fixed order
+        float s = 0.f;
+        for (int b = tid; b < p.B; b += kWgThreads) s += p.loss_rows[b];
+        s = warp_sum_f(s);
+        if ((tid & 31) == 0) s_red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < kWgThreads / 32; ++i) t += s_red[i];
+            *p.loss = t;
+        }
+        return;
+    }
+    int layer = 0;
+    while (layer < L && (int)blockIdx.x >= p.tile_start[layer + 1]) ++layer;
+    const int N = layer < L ? p.H : p.C;
+    const int K = layer == 0 ? 3 * p.H : p.H;
+    const float* dpre = layer < L ? p.dacts + (size_t)layer * p.H : p.dlogits;
+    const int ld_d = layer < L ? L * p.H : p.C;
+    const float* in = layer == 0 ? p.pooled : p.acts + (size_t)(layer - 1) * p.H;
+    const int ld_x = layer == 0 ? 3 * p.H : L * p.H;
+    const int tiles_k = (K + kTK - 1) / kTK;
+    const int t = blockIdx.x - p.tile_start[layer];
+    const int n_base = (t / tiles_k) * kTN, k_base = (t % tiles_k) * kTK;
+    const int tn = tid >> 4, tk = tid & 15;    // 16 x 16 threads: 2 n x 4 k each
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    float bs0 = 0.f, bs1 = 0.f;
+    for (int bb = 0; bb < p.B; bb += kTB) {
+        for (int i = tid; i < kTB * kTN; i += kWgThreads) {
+            const int r = i / kTN, c = i - r * kTN;
+            const int b = bb + r, n = n_base + c;
+            s_d[r][c] = (b < p.B && n < N) ? dpre[(size_t)b * ld_d + n] : 0.f;
+        }
+        for (int i = tid; i < kTB * kTK; i += kWgThreads) {
+            const int r = i / kTK, c = i - r * kTK;
+            const int b = bb + r, k = k_base + c;
+            s_x[r][c] = (b < p.B && k < K) ? in[(size_t)b * ld_x + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < kTB; ++r) {
+            const float d0 = s_d[r][tn * 2], d1 = s_d[r][tn * 2 + 1];
+            const float4 x = reinterpret_cast<const float4*>(&s_x[r][0])[tk];
+            acc0.x += d0 * x.x; acc0.y += d0 * x.y; acc0.z += d0 * x.z; acc0.w += d0 * x.w;
+            acc1.x += d1 * x.x; acc1.y += d1 * x.y; acc1.z += d1 * x.z; acc1.w += d1 * x.w;
+            bs0 += d0; bs1 += d1;
+        }
+        __syncthreads();
+    }
+    float* dw = p.dw[layer];
+    const float4 accs[2] = {acc0, acc1};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int n = n_base + tn * 2 + j;
+        if (n >= N) continue;
+        const float v[4] = {accs[j].x, accs[j].y, accs[j].z, accs[j].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k_base + tk * 4 + q;
+            if (k < K) dw[(size_t)n * K + k] = v[q];
+        }
+        if (k_base == 0 && tk == 0) p.db[layer][n] = j == 0 ? bs0 : bs1;
+    }
+}
+
+}  // namespace
+
+extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, const float* const* w,
+                                const float* const* b, int n_mlp, const float* wc, const float* bc, int B, int H, int C,
+                                float pooling_l2, int train, float* logits, float* loss_rows, float* acts, float* dacts,
+                                float* dlogits, float* dpooled, void* stream) {
+    GPT_CHECK_ARG(pooled && labels && w && b && wc && bc && logits && loss_rows);
+    GPT_CHECK_ARG(B >= 0 && H >= 1 && C >= 1 && n_mlp >= 1 && pooling_l2 >= 0.f);
+    GPT_CHECK_ARG(!train || (acts && dacts && dlogits && dpooled));
+    if (n_mlp > kMaxMlp || H % 4 != 0 || C > 1024) return GPT_ERR_UNSUPPORTED;
+    if (B == 0) return GPT_OK;
+    HeadParams p{};
+    p.pooled = pooled; p.labels = reinterpret_cast<const long long*>(labels);
+    for (int l = 0; l < n_mlp; ++l) {
+        GPT_CHECK_ARG(w[l] && b[l]);
+        p.w[l] = w[l]; p.b[l] = b[l];
+    }
+    p.wc = wc; p.bc = bc;
+    p.B = B; p.H = H; p.C = C; p.n_mlp = n_mlp; p.train = train;
+    p.pooling_l2 = pooling_l2; p.inv_B = 1.0f / (float)B;
+    p.logits = logits; p.loss_rows = loss_rows; p.acts = acts; p.dacts = dacts; p.dlogits = dlogits; p.dpooled = dpooled;
+    // sentences per CTA: 1 while a wave of CTAs fits the machine, then 2 / 4 so that weights are streamed less often
+    const int R = B <= 296 ? 1 : (B <= 1184 ? 2 : 4);
+    const size_t smem = head_smem_bytes(R, H, C, n_mlp);
+    if (smem > 200 * 1024) return GPT_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    static size_t configured[3] = {0, 0, 0};
+    const int slot = R == 1 ? 0 : (R == 2 ? 1 : 2);
+    if (smem > configured[slot]) {
+        if (R == 1) e = cudaFuncSetAttribute(head_fwd_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else if (R == 2) e = cudaFuncSetAttribute(head_fwd_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else e = cudaFuncSetAttribute(head_fwd_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured[slot] = smem;
+    }
+    const int grid = (B + R - 1) / R;
+    if (R == 1) head_fwd_bwd_kernel<1><<<grid, kHeadThreads, smem, st>>>(p);
+    else if (R == 2) head_fwd_bwd_kernel<2><<<grid, kHeadThreads, smem, st>>>(p);
+    else head_fwd_bwd_kernel<4><<<grid, kHeadThreads, smem, st>>>(p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_head_wgrad(const float* pooled, const float* acts, const float* dacts, const float* dlogits,
+                              const float* loss_rows, int B, int H, int C, int n_mlp, float* const* dw,
+                              float* const* db, float* dwc, float* dbc, float* loss, void* stream) {
+    GPT_CHECK_ARG(pooled && acts && dacts && dlogits && loss_rows && dw && db && dwc && dbc && loss);
+    GPT_CHECK_ARG(B >= 1 && H >= 1 && C >= 1 && n_mlp >= 1);
+    if (n_mlp > kMaxMlp) return GPT_ERR_UNSUPPORTED;
+    WgradParams p{};
+    p.pooled = pooled; p.acts = acts; p.dacts = dacts; p.dlogits = dlogits; p.loss_rows = loss_rows;
+    p.B = B; p.H = H; p.C = C; p.n_mlp = n_mlp; p.loss = loss;
+    int tiles = 0;
+    for (int l = 0; l <= n_mlp; ++l) {
+        const int N = l < n_mlp ? H : C, K = l == 0 ? 3 * H : H;
+        p.tile_start[l] = tiles;
+        tiles += ((N + kTN - 1) / kTN) * ((K + kTK - 1) / kTK);
+        if (l < n_mlp) {
+            GPT_CHECK_ARG(dw[l] && db[l]);
+            p.dw[l] = dw[l]; p.db[l] = db[l];
+        } else {
+            p.dw[l] = dwc; p.db[l] = dbc;
+        }
+    }
+    p.tile_start[n_mlp + 1] = tiles;
+    head_wgrad_kernel<<<tiles + 1, kWgThreads, 0, (cudaStream_t)stream>>>(p);
+    return gpt_launch_status();
+}

@@ -147,3 +147,225 @@ class GraphedTrainStep(object):
         """Number of this library's kernels inside one replay for the batch's shape (0 before capture)."""
         key = (tuple(batch[0].shape), len(batch) - 2)
         return self.kernels_per_replay.get(key, 0)
+
+
+class FlatParameters(object):
+    """Every dense trainable parameter re-homed as a view into ONE fp32 buffer, with a parallel gradient buffer.
+
+    ``state_dict`` keys, shapes and values are unchanged (the nn.Parameters stay what they are; only their storage
+    moves), so checkpoints and the reference-facing API keep working.  One flat buffer is what makes clip + SGD a
+    two-launch affair (csrc/update.cu) and the data-parallel exchange a single message.
+    """
+    ALIGN = 64      # floats: 256-byte aligned slices (TMA / float4 safe)
+
+    def __init__(self, named_params):
+        self.names, self.params, self.offsets = [], [], []
+        total = 0
+        for name, p in named_params:
+            self.names.append(name)
+            self.params.append(p)
+            self.offsets.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        dev = self.params[0].device
+        self.param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_views = {}
+        for name, p, off in zip(self.names, self.params, self.offsets):
+            view = self.param[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            self.grad_views[id(p)] = self.grad[off:off + p.numel()].view_as(p)
+
+    def g(self, p):
+        return self.grad_views[id(p)]
+
+
+class FusedTrainStep(object):
+    """The whole optimisation step as ~22 launches of this library, no ATen kernels, captured once per batch shape.
+
+    Same arithmetic as the reference's five-call sequence (train.py:213-227) on the `regular` GCN with plain SGD:
+    K1 prune -> K5 embed -> L x (K3 project, K2 aggregate) -> K4 pool -> K6 head (out_mlp, classifier, loss and their
+    backward) -> K4/K2/K3/K5 backward into one flat gradient buffer (+ the live word-embedding rows) -> K7 clip + SGD.
+    Autograd is not involved: the order of calls below IS the backward.  ``supported(trainer)`` says whether a
+    configuration can run here; everything else stays on GraphedTrainStep (autograd under capture).
+    """
+
+    def __init__(self, trainer, max_grad_norm=None, warmup=2):
+        from . import ops
+        why = self.unsupported_reason(trainer)
+        if why:
+            raise ValueError('FusedTrainStep: ' + why)
+        self.trainer, self.model, self.opt = trainer, trainer.model, trainer.opt
+        self.max_grad_norm = trainer.opt['max_grad_norm'] if max_grad_norm is None else max_grad_norm
+        self.warmup = warmup
+        gm = self.model.gcn_model
+        self.gcn = gm.gcn
+        self.tacred = self.opt['dataset'] == 'tacred'
+        self.use_pos = self.opt['pos_dim'] > 0
+        self.use_ner = self.opt['ner_dim'] > 0 and self.tacred
+        dense = []
+        for name, p in self.model.named_parameters():
+            if p is gm.emb.weight or p is gm.deprel_emb.weight or not p.requires_grad:
+                continue
+            if gm.ner_emb is not None and p is gm.ner_emb.weight and not self.use_ner:
+                continue            # never receives a gradient (model/gcn.py:244): torch's SGD skips it too
+            if gm.pos_emb is not None and p is gm.pos_emb.weight and not self.use_pos:
+                continue
+            dense.append((name, p))
+        self.flat = FlatParameters(dense)
+        emb = gm.emb.weight
+        self.emb_weight = emb
+        self.sparse = ops.SparseEmbeddingState(emb.data, self.opt['topn']) if emb.requires_grad else None
+        self.mlp = [m for m in gm.out_mlp if isinstance(m, torch.nn.Linear)]
+        self.cls = self.model.classifier
+        n_rows_max = 0
+        self.partials = torch.zeros(1024, dtype=torch.float32, device=emb.device)
+        self.total_norm = torch.zeros((), dtype=torch.float32, device=emb.device)
+        self.gcn.rng_state[1] += 1          # the autograd path advances the stream before its first forward
+        self._graphs, self._seen = {}, {}
+        self._lr = self.trainer.optimizer.param_groups[0]['lr']
+        self.kernels_per_replay = {}
+        self.replays = 0
+        self.exchange = None                # data-parallel hook: callable(flat_grad, sparse) between backward and K7
+
+    @staticmethod
+    def unsupported_reason(trainer):
+        opt = trainer.opt
+        o = trainer.optimizer
+        plain_sgd = isinstance(o, torch.optim.SGD) and len(o.param_groups) == 1 and all(
+            g.get('momentum', 0) == 0 and g.get('weight_decay', 0) == 0 and not g.get('nesterov', False) and
+            not g.get('maximize', False) for g in o.param_groups)
+        if not opt.get('cuda', False):
+            return 'needs a CUDA device'
+        if not plain_sgd:
+            return 'optimizer is not plain SGD'
+        if opt.get('rnn', False):
+            return 'C-GCN encoder (cuDNN LSTM) runs under autograd'
+        if opt.get('conv_l2', 0) > 0:
+            return 'conv_l2 > 0'
+        if opt['hidden_dim'] % 4 != 0 or opt['mlp_layers'] > 4:
+            return 'head shape outside K6'
+        if trainer.model.gcn_model.gcn.injected_masks is not None:
+            return 'injected dropout masks'
+        return None
+
+    # -- the step: the order of calls is the program -----------------------------------------------------------------
+    def _run(self, inputs, labels, update=True):
+        from . import ops
+        opt, gcn, fl = self.opt, self.gcn, self.flat
+        if self.tacred:
+            words, masks, pos, ner, deprel, head, subj_pos, obj_pos = inputs
+        else:
+            words, masks, pos, deprel, head, subj_pos, obj_pos = inputs
+            ner = None
+        gm = self.model.gcn_model
+        B, T = words.shape
+        H = opt['hidden_dim']
+        rng = gcn.rng_state
+        mode = gcn.gemm_mode
+        use_adj = not opt.get('no_adj', False)
+        ptype = ops.POOL_TYPES[opt['pooling']]
+        p_in, p_gcn = opt['input_dropout'], opt['gcn_dropout']
+        pos_w = gm.pos_emb.weight if self.use_pos else None
+        ner_w = gm.ner_emb.weight if self.use_ner else None
+        # forward
+        csr = ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'])
+        x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
+                          None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
+        xs, acts, wss = [], [], []
+        h = x
+        n_layers = len(gcn.W)
+        for l, lin in enumerate(gcn.W):
+            ws = ops.weight_prep(lin.weight.data, mode)
+            y = ops.linear_fwd(h.view(B * T, -1), lin.weight.data, mode, ws)
+            xs.append(h)
+            wss.append(ws)
+            h, act = ops.aggregate_fwd(y, csr, lin.bias.data, use_adj, 0.0 if l == n_layers - 1 else p_gcn, rng, l,
+                                       None, want_act=True)
+            acts.append(act)
+        pooled, argmax = ops.pool3_fwd(h, csr, ptype)
+        buf = ops.HeadBuffers(B, H, self.cls.weight.shape[0], len(self.mlp), words.device)
+        ops.head_fwd_bwd(pooled, labels, [m.weight.data for m in self.mlp], [m.bias.data for m in self.mlp],
+                         self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=True)
+        # backward
+        ops.head_wgrad(pooled, buf, [fl.g(m.weight) for m in self.mlp], [fl.g(m.bias) for m in self.mlp],
+                       fl.g(self.cls.weight), fl.g(self.cls.bias))
+        dh = ops.pool3_bwd(buf.dpooled, argmax, csr, ptype, H)
+        for l in range(n_layers - 1, -1, -1):
+            lin = gcn.W[l]
+            dy, _ = ops.aggregate_bwd(dh, None, csr, use_adj, 0.0 if l == n_layers - 1 else p_gcn, None,
+                                      act=acts[l], dbias_out=fl.g(lin.bias))
+            ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True)
+            dh = ops.linear_dgrad(dy, lin.weight.data, mode, wss[l]).view(B, T, -1)
+        sp = self.sparse
+        if sp is not None:
+            sp.words = words
+        ops.embed_bwd(dh, csr.flags, words, pos if self.use_pos else None, ner if self.use_ner else None,
+                      sp.G if sp is not None else None, fl.g(pos_w) if pos_w is not None else None,
+                      fl.g(ner_w) if ner_w is not None else None, sp.owner if sp is not None else None,
+                      self.emb_weight.shape[0], self.emb_weight.shape[1], sp.topn if sp is not None else 0, p_in, rng,
+                      0xE0)
+        self.last_csr = csr
+        scale = 1.0
+        if self.exchange is not None:
+            scale = self.exchange(fl.grad, sp)
+        if update:
+            ops.update_sqnorm(fl.grad, sp, self.partials)
+            ops.update_apply(fl.param, fl.grad, sp, self.emb_weight.data, self.partials, self.max_grad_norm,
+                             self.trainer.optimizer.param_groups[0]['lr'], scale, self.total_norm, rng[1:])
+        return buf.loss, buf.logits
+
+    def _capture(self, key, inputs, labels):
+        from . import _lib
+        entry = {'inputs': [t.clone() for t in inputs], 'labels': labels.clone()}
+        torch.cuda.synchronize()
+        n0 = _lib.lib().gpt_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            entry['loss'], entry['logits'] = self._run(entry['inputs'], entry['labels'])
+        entry['graph'] = g
+        self.kernels_per_replay[key] = int(_lib.lib().gpt_launch_count() - n0)
+        self._graphs[key] = entry
+        return entry
+
+    @torch.no_grad()
+    def __call__(self, batch):
+        lr = self.trainer.optimizer.param_groups[0]['lr']
+        if lr != self._lr:              # the learning rate is baked into the captured update: re-capture
+            self._graphs.clear()
+            self._lr = lr
+        fields, labels = batch[:-2], batch[-2]
+        key = (tuple(fields[0].shape), len(fields))
+        entry = self._graphs.get(key)
+        if entry is None:
+            inputs, labels = unpack_batch(batch, True)[:2]
+            seen = self._seen.get(key, 0)
+            self._seen[key] = seen + 1
+            if seen < self.warmup:      # first steps of a new shape run eagerly (lazy module loading, smem attributes)
+                return self._run(inputs, labels)[0]
+            entry = self._capture(key, inputs, labels)
+        else:
+            for s, t in zip(entry['inputs'], fields):
+                s.copy_(t, non_blocking=True)
+            entry['labels'].copy_(labels, non_blocking=True)
+        entry['graph'].replay()
+        self.replays += 1
+        return entry['loss']
+
+    @torch.no_grad()
+    def gradients(self, batch):
+        """Run forward + backward only (eager, no update) and return {parameter name: gradient clone}, the word-embedding
+        gradient as a dense tensor; the gradient buffers are left zeroed.  For tests."""
+        inputs, labels = unpack_batch(batch, True)[:2]
+        loss, logits = self._run(inputs, labels, update=False)
+        out = {n: self.flat.g(p).clone() for n, p in zip(self.flat.names, self.flat.params)}
+        if self.sparse is not None:
+            out['gcn_model.emb.weight'] = self.sparse.G.clone()
+            self.sparse.G.zero_()
+            self.sparse.owner.fill_(0x7fffffff)
+        self.flat.grad.zero_()
+        return loss.clone(), logits.clone(), out
+
+    def launches_per_replay(self, batch):
+        key = (tuple(batch[0].shape), len(batch) - 2)
+        return self.kernels_per_replay.get(key, 0)

@@ -107,10 +107,14 @@ class GCNTrainer(Trainer):
         reference API: the reference-compatible path is update() + caller-owned backward/clip/step."""
         if getattr(self, '_graphed', None) is None:
             try:
-                from ..engine import GraphedTrainStep
+                from ..engine import FusedTrainStep, GraphedTrainStep
             except ImportError:
-                from gcn_over_pruned_trees_b200.engine import GraphedTrainStep
-            self._graphed = GraphedTrainStep(self, reducer=reducer)
+                from gcn_over_pruned_trees_b200.engine import FusedTrainStep, GraphedTrainStep
+            single = reducer is None or reducer.world == 1
+            if single and FusedTrainStep.unsupported_reason(self) is None:
+                self._graphed = FusedTrainStep(self)         # library kernels only, no autograd
+            else:
+                self._graphed = GraphedTrainStep(self, reducer=reducer)
         return self._graphed(batch)
 
     def get_deprel_emb(self):

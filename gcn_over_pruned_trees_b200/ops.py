@@ -177,11 +177,13 @@ def linear_dgrad(dy, weight, mode='fp32', ws=None):
     return dx
 
 
-def linear_wgrad(dy, x2d, mode='fp32'):
+def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False):
+    """dw = dy^T x.  accumulate: add into ``out`` (which the caller keeps zeroed between steps) instead of overwriting."""
     M, N = dy.shape
     K = x2d.shape[1]
-    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
-    _call('gpt_linear_wgrad_f32', _ptr(dy), _ptr(x2d), _ptr(dw), M, N, K, _stream())
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
+    _call('gpt_linear_wgrad_f32_acc' if accumulate else 'gpt_linear_wgrad_f32', _ptr(dy), _ptr(x2d), _ptr(dw), M, N,
+          K, _stream())
     return dw
 
 
@@ -200,12 +202,17 @@ def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq
     return (out, act) if want_act else out
 
 
-def aggregate_bwd(gout, out, csr, use_adj=True, drop_p=0.0, drop_mask=None, want_dbias=True, force_vec=0, act=None):
-    """K2 backward; [out > 0] is taken from ``act`` (bit mask) when given, else from ``out``."""
+def aggregate_bwd(gout, out, csr, use_adj=True, drop_p=0.0, drop_mask=None, want_dbias=True, force_vec=0, act=None,
+                  dbias_out=None):
+    """K2 backward; [out > 0] is taken from ``act`` (bit mask) when given, else from ``out``.  ``dbias_out``: add
+    the bias gradient into this (caller-zeroed) buffer instead of a fresh one."""
     B, T = csr.B, csr.T
     H = gout.shape[-1]
     dy = torch.empty((B * T, H), dtype=torch.float32, device=gout.device)
-    dbias = torch.zeros((H,), dtype=torch.float32, device=gout.device) if want_dbias else None
+    if dbias_out is not None:
+        dbias = dbias_out
+    else:
+        dbias = torch.zeros((H,), dtype=torch.float32, device=gout.device) if want_dbias else None
     _call('gpt_gcn_aggregate_bwd', _ptr(gout), _ptr(out), _ptr(act), _ptr(csr.rowptr), _ptr(csr.col),
           _ptr(csr.denom), _ptr(dy), _ptr(dbias), B, T, H, int(bool(use_adj)), float(drop_p), _ptr(drop_mask),
           int(force_vec), _stream())
@@ -278,6 +285,22 @@ class _Pool3(torch.autograd.Function):
 
 def pool3(h, csr, pool_type='max'):
     return _Pool3.apply(h, csr, POOL_TYPES[pool_type])
+
+
+def pool3_fwd(h, csr, pool_type):
+    """K4 without autograd (engine.FusedTrainStep): -> (pooled [B,3H], argmax or None)."""
+    B, T, H = h.shape
+    out = torch.empty((B, 3 * H), dtype=torch.float32, device=h.device)
+    argmax = torch.empty((B, 3 * H), dtype=torch.int32, device=h.device) if pool_type == 0 else None
+    _call('gpt_pool3_fwd', _ptr(h), _ptr(csr.flags), B, T, H, pool_type, _ptr(out), _ptr(argmax), _stream())
+    return out, argmax
+
+
+def pool3_bwd(gout, argmax, csr, pool_type, H):
+    B, T = csr.B, csr.T
+    dh = torch.empty((B, T, H), dtype=torch.float32, device=gout.device)
+    _call('gpt_pool3_bwd', _ptr(gout), _ptr(argmax), _ptr(csr.flags), B, T, H, pool_type, _ptr(dh), _stream())
+    return dh
 
 
 # ---- K5: input embeddings ------------------------------------------------------------------------------------
@@ -354,3 +377,88 @@ def embed_rows_sgd(state, weight, total_sq, max_norm, lr):
     V, E = state.G.shape
     _call('gpt_embed_rows_sgd', _ptr(state.words), _ptr(state.owner), _ptr(state.G), _ptr(weight),
           state.words.numel(), E, state.topn, _ptr(total_sq), float(max_norm), float(lr), _stream())
+
+
+def embed_fwd(words, pos, ner, emb_w, pos_w, ner_w, drop_p, rng_state, subseq):
+    """K5 forward without autograd (engine.FusedTrainStep)."""
+    V, E = emb_w.shape
+    Dp = pos_w.shape[1] if pos_w is not None else 0
+    Dn = ner_w.shape[1] if ner_w is not None else 0
+    x = torch.empty(words.shape + (E + Dp + Dn,), dtype=torch.float32, device=words.device)
+    _call('gpt_embed_fwd', _ptr(words), _ptr(pos if Dp else None), _ptr(ner if Dn else None), _ptr(emb_w),
+          _ptr(pos_w), _ptr(ner_w), _ptr(x), words.numel(), V, E, Dp, Dn, float(drop_p),
+          _ptr(rng_state if drop_p > 0 else None), int(subseq), _stream())
+    return x
+
+
+def embed_bwd(dx, flags, words, pos, ner, g_emb, g_pos, g_ner, owner, V, E, topn, drop_p, rng_state, subseq):
+    """K5 backward: scatter-add into caller-zeroed tables (any of g_emb / g_pos / g_ner may be None)."""
+    Dp = g_pos.shape[1] if g_pos is not None else 0
+    Dn = g_ner.shape[1] if g_ner is not None else 0
+    _call('gpt_embed_bwd', _ptr(dx), _ptr(flags), _ptr(words), _ptr(pos if Dp else None), _ptr(ner if Dn else None),
+          _ptr(g_emb), _ptr(g_pos), _ptr(g_ner), _ptr(owner), words.numel(), V, E, Dp, Dn, int(topn), float(drop_p),
+          _ptr(rng_state if drop_p > 0 else None), int(subseq), _stream())
+
+
+# ---- K6: classifier head -------------------------------------------------------------------------------------------
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class HeadBuffers(object):
+    """Outputs / workspace of K6 for a batch of B sentences."""
+
+    def __init__(self, B, H, C, n_mlp, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.logits = torch.empty((B, C), **f)
+        self.loss_rows = torch.empty((B,), **f)
+        self.acts = torch.empty((B, n_mlp, H), **f)
+        self.dacts = torch.empty((B, n_mlp, H), **f)
+        self.dlogits = torch.empty((B, C), **f)
+        self.dpooled = torch.empty((B, 3 * H), **f)
+        self.loss = torch.empty((), **f)
+
+
+def head_fwd_bwd(pooled, labels, weights, biases, wc, bc, pooling_l2, buf, train=True):
+    """K6: out_mlp + classifier + CE / pooling_l2 loss (+ data gradients when train) into ``buf`` (HeadBuffers)."""
+    B, K0 = pooled.shape
+    H, C = K0 // 3, wc.shape[0]
+    _call('gpt_head_fwd_bwd', _ptr(pooled), _ptr(labels), _ptr_array(weights), _ptr_array(biases), len(weights),
+          _ptr(wc), _ptr(bc), B, H, C, float(pooling_l2), int(bool(train)), _ptr(buf.logits), _ptr(buf.loss_rows),
+          _ptr(buf.acts), _ptr(buf.dacts), _ptr(buf.dlogits), _ptr(buf.dpooled), _stream())
+    return buf
+
+
+def head_wgrad(pooled, buf, dws, dbs, dwc, dbc):
+    """K6 weight gradients (overwrites dws / dbs / dwc / dbc) and the scalar loss -> buf.loss."""
+    B, K0 = pooled.shape
+    H, C = K0 // 3, dwc.shape[0]
+    _call('gpt_head_wgrad', _ptr(pooled), _ptr(buf.acts), _ptr(buf.dacts), _ptr(buf.dlogits), _ptr(buf.loss_rows),
+          B, H, C, len(dws), _ptr_array(dws), _ptr_array(dbs), _ptr(dwc), _ptr(dbc), _ptr(buf.loss), _stream())
+    return buf.loss
+
+
+# ---- K7: clip + SGD ---------------------------------------------------------------------------------------------------
+
+def update_partials(n, n_rows):
+    return int(_lib.lib().gpt_update_partials(int(n), int(n_rows)))
+
+
+def update_sqnorm(flat_grad, sparse, partials):
+    """Partial sums of g^2 over the flat dense gradient and (sparse: SparseEmbeddingState or None) the live word rows."""
+    n_rows = sparse.words.numel() if sparse is not None else 0
+    _call('gpt_update_sqnorm', _ptr(flat_grad), flat_grad.numel(), _ptr(sparse.words if sparse else None),
+          _ptr(sparse.owner if sparse else None), _ptr(sparse.G if sparse else None), n_rows,
+          sparse.G.shape[1] if sparse else 1, sparse.topn if sparse else 0, _ptr(partials), _stream())
+
+
+def update_apply(flat_param, flat_grad, sparse, emb_weight, partials, max_norm, lr, grad_scale=1.0, total_norm=None,
+                 step_counter=None):
+    n_rows = sparse.words.numel() if sparse is not None else 0
+    _call('gpt_update_apply', _ptr(flat_param), _ptr(flat_grad), flat_grad.numel(),
+          _ptr(sparse.words if sparse else None), _ptr(sparse.owner if sparse else None),
+          _ptr(sparse.G if sparse else None), _ptr(emb_weight if sparse else None), n_rows,
+          sparse.G.shape[1] if sparse else 1, sparse.topn if sparse else 0, _ptr(partials), float(max_norm), float(lr),
+          float(grad_scale), _ptr(total_norm), _ptr(step_counter), _stream())

@@ -103,6 +103,8 @@ int gpt_pool3_bwd(const float* gout, const int32_t* argmax, const uint8_t* flags
 int gpt_linear_fwd_f32(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
 int gpt_linear_dgrad_f32(const float* dy, const float* w, float* dx, int M, int N, int K, void* stream);
 int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
+/* dw += dy^T x (no zero-fill launch: for gradient buffers the caller keeps zeroed between steps, see K7) */
+int gpt_linear_wgrad_f32_acc(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
 /* K3 on the tensor cores: tcgen05.mma kind::tf32, TMA-fed, accumulator in TMEM (GPT_GEMM_TF32, ~1e-3 relative).
  *     Needs K % 4 == 0 (and N % 4 == 0 for dgrad) and 16-byte aligned operands, else GPT_ERR_UNSUPPORTED.
  *     dgrad takes a float [K*N] workspace for the transposed weight. */
@@ -137,6 +139,39 @@ int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner, const floa
                           float* sq, void* stream);
 int gpt_embed_rows_sgd(const int64_t* words, int32_t* owner, float* g_emb, float* emb_w, int n_rows, int E, int topn,
                        const float* total_sq, float max_norm, float lr, void* stream);
+
+/* K6. classifier head for one batch of pooled vectors [B,3H] (K4 output): out_mlp (model/gcn.py:64-68,122: n_mlp x
+ *     Linear+ReLU, w[0] [H,3H], w[l>0] [H,H]), classifier (model/gcn.py:21,29: wc [C,H]), and the loss of
+ *     model/trainer.py:94-100 without the conv_l2 term: CrossEntropy(mean) + pooling_l2 * mean_b sum_h pooled[b,h<H]^2.
+ *     w / b are HOST arrays of n_mlp device pointers.  Needs H % 4 == 0, n_mlp <= 4.
+ *     out: logits [B,C]; loss_rows [B] (the loss is their sum).  With train != 0 also the backward of loss.backward()
+ *     (train.py:221) down to dpooled [B,3H], plus acts / dacts [B,n_mlp,H] (post-ReLU activations and
+ *     d loss / d pre-activations) and dlogits [B,C] for gpt_head_wgrad. */
+int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, const float* const* w, const float* const* b,
+                     int n_mlp, const float* wc, const float* bc, int B, int H, int C, float pooling_l2, int train,
+                     float* logits, float* loss_rows, float* acts, float* dacts, float* dlogits, float* dpooled,
+                     void* stream);
+/* K6 weight gradients: dw[l] = dacts[:,l,:]^T . in_l, db[l] = column sums (in_0 = pooled, in_l = acts[:,l-1,:]);
+ *     dwc / dbc from dlogits and the last activation; *loss = sum_b loss_rows[b].  Overwrites (no accumulation, no
+ *     atomics: deterministic).  dw / db are HOST arrays of n_mlp device pointers. */
+int gpt_head_wgrad(const float* pooled, const float* acts, const float* dacts, const float* dlogits,
+                   const float* loss_rows, int B, int H, int C, int n_mlp, float* const* dw, float* const* db,
+                   float* dwc, float* dbc, float* loss, void* stream);
+
+/* K7. clip_grad_norm_(max_norm) + plain SGD + zero_grad (train.py:224-227, --optim sgd) over ONE flat fp32 parameter /
+ *     gradient buffer of n elements (16-byte aligned) plus the word-embedding rows the batch touched (words int64
+ *     [n_rows], owner / g_emb as written by gpt_embed_bwd; n_rows may be 0).
+ *     gpt_update_partials (host) = number of floats `partials` must hold.  gpt_update_sqnorm writes per-CTA partial
+ *     sums of g^2; gpt_update_apply re-adds them in a fixed order, norm = grad_scale * sqrt(sum),
+ *     coef = min(1, max_norm / (norm + 1e-6)) (max_norm <= 0: no clipping), then p -= lr * coef * grad_scale * g and
+ *     g = 0 for the flat buffer and the live rows (owner reset to INT_MAX).  total_norm (optional) receives norm;
+ *     *step_counter (optional; word 1 of the {seed, step} dropout state) is incremented. */
+int gpt_update_partials(long long n, int n_rows);
+int gpt_update_sqnorm(const float* grad, long long n, const int64_t* words, const int32_t* owner, const float* g_emb,
+                      int n_rows, int E, int topn, float* partials, void* stream);
+int gpt_update_apply(float* param, float* grad, long long n, const int64_t* words, int32_t* owner, float* g_emb,
+                     float* emb_w, int n_rows, int E, int topn, const float* partials, float max_norm, float lr,
+                     float grad_scale, float* total_norm, uint64_t* step_counter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,254 @@
+"""GPU tests of the fused step: K6 (classifier head), K7 (clip + SGD) and engine.FusedTrainStep, against plain PyTorch
+fp32 restatements of the reference lines they replace (model/gcn.py:64-68,122, model/trainer.py:94-100,
+train.py:224-227) and against the autograd path of this package.
+
+Tolerances: logits / loss <= 1e-5 relative, gradients <= 1e-4 relative per tensor, parameters after N steps <= 5e-5.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gcn_over_pruned_trees_b200 import ops, synth
+from gcn_over_pruned_trees_b200.engine import FusedTrainStep, GraphedTrainStep
+from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _rel(a, b):
+    a = a.detach().double().cpu().numpy()
+    b = b.detach().double().cpu().numpy()
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---------------------------------------------------------------- K6 ------------------------------------------------
+
+@pytest.mark.parametrize('B,H,C,L,l2', [(50, 200, 42, 2, 0.003), (7, 64, 10, 1, 0.0), (300, 200, 19, 3, 0.003),
+                                        (1300, 32, 42, 2, 0.01), (1, 200, 42, 2, 0.003), (64, 512, 42, 2, 0.003),
+                                        (33, 36, 5, 4, 0.5)])
+def test_k6_head_matches_torch(B, H, C, L, l2):
+    g = torch.Generator().manual_seed(B * 7 + H)
+    pooled = (torch.randn(B, 3 * H, generator=g) * 1.5).to(DEV).requires_grad_()
+    labels = torch.randint(0, C, (B,), generator=g).to(DEV)
+    ws = [(torch.randn(H, 3 * H if l == 0 else H, generator=g) / np.sqrt(3 * H if l == 0 else H)).to(DEV).requires_grad_()
+          for l in range(L)]
+    bs = [(torch.randn(H, generator=g) * 0.1).to(DEV).requires_grad_() for _ in range(L)]
+    wc = (torch.randn(C, H, generator=g) / np.sqrt(H)).to(DEV).requires_grad_()
+    bc = (torch.randn(C, generator=g) * 0.1).to(DEV).requires_grad_()
+    # reference: out_mlp -> classifier -> CE + pooling_l2 * mean_b sum_h h_out^2
+    h = pooled
+    for w, b in zip(ws, bs):
+        h = F.relu(F.linear(h, w, b))
+    logits = F.linear(h, wc, bc)
+    loss = F.cross_entropy(logits, labels) + l2 * (pooled[:, :H] ** 2).sum(1).mean()
+    loss.backward()
+
+    buf = ops.HeadBuffers(B, H, C, L, DEV)
+    with torch.no_grad():
+        ops.head_fwd_bwd(pooled.detach(), labels, [w.detach() for w in ws], [b.detach() for b in bs], wc.detach(),
+                         bc.detach(), l2, buf, train=True)
+        dws = [torch.full_like(w, 7.0) for w in ws]          # overwritten, not accumulated
+        dbs = [torch.full_like(b, 7.0) for b in bs]
+        dwc, dbc = torch.full_like(wc, 7.0), torch.full_like(bc, 7.0)
+        got_loss = ops.head_wgrad(pooled.detach(), buf, dws, dbs, dwc, dbc)
+    assert _rel(buf.logits, logits) <= 1e-5
+    assert abs(float(got_loss) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert _rel(buf.dpooled, pooled.grad) <= 1e-4
+    for l in range(L):
+        assert _rel(dws[l], ws[l].grad) <= 1e-4, l
+        assert _rel(dbs[l], bs[l].grad) <= 1e-4, l
+    assert _rel(dwc, wc.grad) <= 1e-4
+    assert _rel(dbc, bc.grad) <= 1e-4
+
+
+def test_k6_eval_mode_writes_logits_and_loss_only():
+    B, H, C = 20, 200, 42
+    pooled = torch.randn(B, 3 * H, device=DEV)
+    labels = torch.randint(0, C, (B,), device=DEV)
+    w = [torch.randn(H, 3 * H, device=DEV) * 0.05, torch.randn(H, H, device=DEV) * 0.05]
+    b = [torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)]
+    wc, bc = torch.randn(C, H, device=DEV) * 0.1, torch.zeros(C, device=DEV)
+    buf = ops.HeadBuffers(B, H, C, 2, DEV)
+    buf.dpooled.fill_(123.0)
+    ops.head_fwd_bwd(pooled, labels, w, b, wc, bc, 0.0, buf, train=False)
+    h = F.relu(F.linear(F.relu(F.linear(pooled, w[0], b[0])), w[1], b[1]))
+    ref = F.linear(h, wc, bc)
+    assert _rel(buf.logits, ref) <= 1e-5
+    assert abs(float(buf.loss_rows.sum()) - float(F.cross_entropy(ref, labels))) <= 1e-5
+    assert float(buf.dpooled.min()) == 123.0
+
+
+def test_k6_unsupported_shapes_are_refused():
+    from gcn_over_pruned_trees_b200 import _lib
+    B, H, C = 4, 30, 5          # H % 4 != 0
+    buf = ops.HeadBuffers(B, H, C, 1, DEV)
+    with pytest.raises(_lib.GptError):
+        ops.head_fwd_bwd(torch.randn(B, 3 * H, device=DEV), torch.zeros(B, dtype=torch.int64, device=DEV),
+                         [torch.randn(H, 3 * H, device=DEV)], [torch.zeros(H, device=DEV)],
+                         torch.randn(C, H, device=DEV), torch.zeros(C, device=DEV), 0.0, buf)
+
+
+# ---------------------------------------------------------------- K7 ------------------------------------------------
+
+@pytest.mark.parametrize('n,scale_grads', [(281_000, 1.0), (281_003, 40.0), (5, 40.0), (3_000_000, 0.01)])
+def test_k7_clip_sgd_matches_torch(n, scale_grads):
+    torch.manual_seed(n)
+    V, E, rows = 3000, 300, 700
+    p = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV) * scale_grads / np.sqrt(n)
+    emb = torch.randn(V, E, device=DEV)
+    words = torch.randint(0, V, (rows,), device=DEV)
+    words[::13] = 0                                           # padding_idx rows never move
+    topn = 2500                                               # rows >= topn are frozen (model/gcn.py:83-86)
+    st = ops.SparseEmbeddingState(emb, topn)
+    st.words = words
+    live = torch.unique(words[(words != 0) & (words < topn)])
+    st.G[live] = torch.randn(live.numel(), E, device=DEV) * scale_grads / 50
+    for r in range(rows - 1, -1, -1):                         # owner = first token of every live word
+        w = int(words[r])
+        if w != 0 and w < topn:
+            st.owner[w] = r
+    # reference: clip_grad_norm_ + SGD over (flat, dense embedding gradient)
+    p_ref, e_ref = p.clone().requires_grad_(), emb.clone().requires_grad_()
+    p_ref.grad, e_ref.grad = g.clone(), st.G.clone()
+    norm_ref = torch.nn.utils.clip_grad_norm_([p_ref, e_ref], 5.0)
+    torch.optim.SGD([p_ref, e_ref], lr=0.3).step()
+
+    partials = torch.zeros(1024, device=DEV)
+    norm = torch.zeros((), device=DEV)
+    counter = torch.tensor([11, 5], dtype=torch.int64, device=DEV)
+    ops.update_sqnorm(g, st, partials)
+    ops.update_apply(p, g, st, emb, partials, 5.0, 0.3, 1.0, norm, counter[1:])
+    assert abs(float(norm) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+    assert _rel(p, p_ref) <= 1e-6
+    assert _rel(emb, e_ref) <= 1e-6
+    assert float(g.abs().max()) == 0.0 and float(st.G.abs().max()) == 0.0       # zero_grad is part of the kernel
+    assert int(st.owner.min()) == 0x7fffffff
+    assert counter.tolist() == [11, 6]
+
+
+def test_k7_grad_scale_is_the_data_parallel_mean():
+    n = 10_000
+    p = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV)
+    p_ref = p.clone().requires_grad_()
+    p_ref.grad = g / 4
+    torch.nn.utils.clip_grad_norm_([p_ref], 5.0)
+    torch.optim.SGD([p_ref], lr=0.3).step()
+    partials = torch.zeros(1024, device=DEV)
+    ops.update_sqnorm(g, None, partials)
+    ops.update_apply(p, g, None, None, partials, 5.0, 0.3, 0.25)
+    assert _rel(p, p_ref) <= 1e-6
+
+
+# ---------------------------------------------------------------- engine ----------------------------------------------
+
+def _autograd_grads(tr, batch):
+    tr.optimizer.zero_grad()
+    loss = tr.update(batch)
+    loss.backward()
+    return loss.detach(), {n: p.grad.detach().clone() for n, p in tr.model.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize('over', [dict(), dict(dataset='semeval', num_class=19, ner_dim=0),
+                                  dict(dataset='semeval', num_class=10), dict(pooling='avg'),
+                                  dict(mlp_layers=1, num_layers=3), dict(prune_k=-1, hidden_dim=64),
+                                  dict(topn=300), dict(no_adj=True)])
+def test_fused_step_gradients_match_autograd_path(over):
+    """Same weights, dropout off: FusedTrainStep's hand-ordered backward == autograd over the per-op Functions."""
+    cfg = dict(vocab_size=900, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32')
+    cfg.update(over)
+    opt = synth.tacred_opt(**cfg)
+    torch.manual_seed(3)
+    a = GCNTrainer(dict(opt))
+    b = GCNTrainer(dict(opt))
+    b.model.load_state_dict(a.model.state_dict())
+    a.model.train()
+    b.model.train()
+    batch = synth.make_batch(21, batch_size=50, vocab_size=900, num_class=opt['num_class'], dataset=opt['dataset'])
+    loss_ref, ref = _autograd_grads(a, batch)
+    fused = FusedTrainStep(b)
+    loss, logits, got = fused.gradients(batch)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    for name, g in ref.items():
+        assert name in got, name
+        assert _rel(got[name], g) <= 1e-4, name
+    assert set(got) == set(ref)
+
+
+def test_fused_step_with_dropout_uses_the_same_streams_as_the_autograd_path():
+    opt = synth.tacred_opt(vocab_size=900, cuda=True, gemm_mode='fp32')
+    torch.manual_seed(4)
+    a = GCNTrainer(dict(opt))
+    b = GCNTrainer(dict(opt))
+    b.model.load_state_dict(a.model.state_dict())
+    b.model.gcn_model.gcn.rng_state.copy_(a.model.gcn_model.gcn.rng_state)
+    a.model.train()
+    b.model.train()
+    batch = synth.make_batch(22, batch_size=50, vocab_size=900)
+    fused = FusedTrainStep(b)               # advances the step word once, like the first autograd forward will
+    loss_ref, ref = _autograd_grads(a, batch)
+    loss, _, got = fused.gradients(batch)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    for name, g in ref.items():
+        assert _rel(got[name], g) <= 1e-4, name
+
+
+def test_fused_steps_match_reference_call_sequence():
+    """N fused (graph-replayed) steps == N x [zero_grad, update, backward, clip_grad_norm_, SGD.step] (train.py:213-227)."""
+    over = dict(vocab_size=700, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32')
+    batches = [synth.make_batch(50 + i, batch_size=50, vocab_size=700, pad_to=64) for i in range(3)]
+
+    def run(fused):
+        torch.manual_seed(5)
+        tr = GCNTrainer(synth.tacred_opt(**over))
+        tr.model.train()
+        losses = []
+        for step in range(9):
+            bt = batches[step % 3]
+            if fused:
+                losses.append(float(tr.train_step(bt)))
+            else:
+                tr.optimizer.zero_grad()
+                loss = tr.update(bt)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(tr.model.parameters(), tr.opt['max_grad_norm'])
+                tr.optimizer.step()
+                losses.append(loss.item())
+        return losses, {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}, tr
+
+    l0, s0, _ = run(False)
+    l1, s1, tr = run(True)
+    assert isinstance(tr._graphed, FusedTrainStep)
+    assert tr._graphed.replays >= 5
+    assert np.allclose(l0, l1, rtol=2e-5)
+    for k in s0:
+        assert _rel(s1[k], s0[k]) < 5e-5, k
+    # the trainer API still works on the re-homed parameters: predict, save/load layout
+    preds, probs, loss = tr.predict(batches[0])
+    assert len(preds) == 50 and np.isfinite(loss)
+    sd = tr.model.state_dict()
+    assert sd['gcn_model.gcn.W.0.weight'].shape == (200, 360)
+
+
+def test_autograd_graph_engine_is_still_selected_when_fused_cannot_run():
+    tr = GCNTrainer(synth.tacred_opt(vocab_size=500, cuda=True, conv_l2=1e-4))
+    assert FusedTrainStep.unsupported_reason(tr) is not None
+    tr.model.train()
+    batch = synth.make_batch(7, batch_size=50, vocab_size=500)
+    losses = [float(tr.train_step(batch)) for _ in range(6)]
+    assert isinstance(tr._graphed, GraphedTrainStep) and np.isfinite(losses).all()
+
+
+def test_fused_step_lr_change_recaptures():
+    tr = GCNTrainer(synth.tacred_opt(vocab_size=500, cuda=True, input_dropout=0.0, gcn_dropout=0.0))
+    tr.model.train()
+    batch = synth.make_batch(8, batch_size=50, vocab_size=500)
+    for _ in range(4):
+        tr.train_step(batch)
+    w0 = tr.model.classifier.weight.detach().clone()
+    tr.update_lr(0.0)
+    tr.train_step(batch)
+    assert torch.equal(tr.model.classifier.weight, w0)         # lr 0: nothing moves
