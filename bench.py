@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument('--prune_k', type=int, default=1)
     ap.add_argument('--gemm', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--eager', action='store_true', help='time the eager five-call step instead of the CUDA graph')
+    ap.add_argument('--autograd-engine', action='store_true',
+                    help='use GraphedTrainStep (autograd under capture) instead of FusedTrainStep')
     ap.add_argument('--no-roofline', action='store_true', help='skip the large-shape aggregation roofline run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--roofline-batch', type=int, default=4096)
@@ -61,7 +63,8 @@ def workload_config(args, world):
             'len': 'clip(Poisson(36),8,96)', 'layers': 2, 'in_dim': 360, 'hidden': 200, 'vocab': VOCAB,
             'prune_k': args.prune_k, 'gemm': args.gemm, 'parallelism': 'dp%d' % world,
             'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd',
-            'engine': 'eager' if args.eager else 'cuda_graph_per_batch_shape', 'l2': 'flushed between timed steps (256 MiB fill)'}
+            'engine': 'eager' if args.eager else ('cuda_graph_autograd' if args.autograd_engine or world > 1 else
+                                                  'cuda_graph_fused_step'), 'l2': 'flushed between timed steps (256 MiB fill)'}
 
 
 # ------------------------------------------------------------------------------------------------ clocks -------
@@ -259,8 +262,9 @@ def run_b200(args):
         trainer.optimizer.step()
         return loss
 
-    from gcn_over_pruned_trees_b200.engine import GraphedTrainStep
-    graphed = GraphedTrainStep(trainer, reducer=reducer)
+    from gcn_over_pruned_trees_b200.engine import FusedTrainStep, GraphedTrainStep
+    fused = world == 1 and not args.autograd_engine and FusedTrainStep.unsupported_reason(trainer) is None
+    graphed = FusedTrainStep(trainer) if fused else GraphedTrainStep(trainer, reducer=reducer)
     step = eager_step if args.eager else graphed
 
     # warm-up: every batch shape runs eagerly 3x, is captured, and is replayed at least once
@@ -334,7 +338,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     pa.record()
     for i in range(n_prof):
-        eager_step(resident[i % N_BATCHES])
+        if fused and not args.eager:        # the same call sequence the graph replays, launched eagerly
+            with torch.no_grad():
+                graphed._run(list(resident[i % N_BATCHES][:-2]), resident[i % N_BATCHES][-2])
+        else:
+            eager_step(resident[i % N_BATCHES])
     pb.record()
     summary = ops.TIMER.summary()
     ops.TIMER = None

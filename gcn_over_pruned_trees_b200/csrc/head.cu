@@ -53,16 +53,24 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ W, const flo
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
         }
-        for (int k4 = lane; k4 < K4; k4 += 32) {
-            float4 wv[4];
+        for (int k4 = lane; k4 < K4; k4 += 64) {               // 8 independent 128-bit loads in flight per lane
+            const bool two = k4 + 32 < K4;
+            float4 wv[4], wu[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) wv[j] = __ldg(wr[j] + k4);
+            for (int j = 0; j < 4; ++j) {
+                wv[j] = __ldg(wr[j] + k4);
+                wu[j] = two ? __ldg(wr[j] + k4 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float4 x = reinterpret_cast<const float4*>(s_in + r * ld_in)[k4];
+                const float4 z = two ? reinterpret_cast<const float4*>(s_in + r * ld_in)[k4 + 32]
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 4; ++j) {
                     acc[j][r] += wv[j].x * x.x + wv[j].y * x.y + wv[j].z * x.z + wv[j].w * x.w;
+                    acc[j][r] += wu[j].x * z.x + wu[j].y * z.y + wu[j].z * z.z + wu[j].w * z.w;
+                }
             }
         }
 #pragma unroll
@@ -94,18 +102,28 @@ __device__ __forceinline__ void dense_dgrad(const float* __restrict__ W, const f
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* wc = reinterpret_cast<const float4*>(W) + k4;
-#pragma unroll 4
-        for (int n = g; n < N; n += Gc) {
-            float d[R];
-            bool any = false;
+        constexpr int U = 8;                                    // rows of W in flight per thread
+        for (int n = g; n < N; n += Gc * U) {
+            float4 wv[U];
+            float d[U][R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) { d[r] = s_dout[r * ld_dout + n]; any |= d[r] != 0.f; }
-            if (!any) continue;
-            const float4 wv = __ldg(wc + (size_t)n * K4);
+            for (int u = 0; u < U; ++u) {
+                const int nn = n + u * Gc;
+                bool any = false;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r].x += d[r] * wv.x; acc[r].y += d[r] * wv.y; acc[r].z += d[r] * wv.z; acc[r].w += d[r] * wv.w;
+                for (int r = 0; r < R; ++r) {
+                    d[u][r] = nn < N ? s_dout[r * ld_dout + nn] : 0.f;
+                    any |= d[u][r] != 0.f;
+                }
+                wv[u] = any ? __ldg(wc + (size_t)nn * K4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[r].x += d[u][r] * wv[u].x; acc[r].y += d[u][r] * wv[u].y;
+                    acc[r].z += d[u][r] * wv[u].z; acc[r].w += d[u][r] * wv[u].w;
+                }
         }
         if (Gc == 1) {
 #pragma unroll
@@ -142,6 +160,18 @@ head_fwd_bwd_kernel(const HeadParams p) {
     float* s_part = s_d1 + R * H;                // [R][max(kDgradPartCols, K0)]
     const int b0 = blockIdx.x * R;
     const int tid = threadIdx.x;
+
+    // warm L2: together the CTAs touch every weight line once, so the DRAM latency is paid once and in parallel
+    // instead of once per pass of every layer
+    {
+        const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gsize = (size_t)gridDim.x * blockDim.x;
+        for (int l = 0; l <= L; ++l) {
+            const float* base = l < L ? p.w[l] : p.wc;
+            const size_t lines = ((size_t)(l < L ? H : C) * (l == 0 ? K0 : H) * sizeof(float) + 127) / 128;
+            for (size_t i = gtid; i < lines; i += gsize)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 32));
+        }
+    }
 
     for (int i = tid; i < R * (K0 >> 2); i += blockDim.x) {
         const int r = i / (K0 >> 2), k4 = i - r * (K0 >> 2);

@@ -19,6 +19,7 @@ namespace {
 constexpr int kUpdThreads = 256;
 constexpr int kUpdWarps = kUpdThreads / 32;
 constexpr int kMaxPartials = 1024;
+constexpr int kRowVec = 3;           // float4 per lane held in registers: rows up to 384 floats in one round trip
 
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
     v = warp_sum_f(v);
@@ -33,8 +34,6 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 }
 
 // CTAs [0, dense_blocks): flat gradient; CTAs [dense_blocks, dense_blocks + row_blocks): embedding rows.
-// A warp of a row CTA takes 32 consecutive token slots, finds the ones that own a live word row with one ballot and
-// then sums those rows with all lanes.
 __global__ void __launch_bounds__(kUpdThreads)
 update_sqnorm_kernel(const float* __restrict__ grad, long long n, const long long* __restrict__ words,
                      const int* __restrict__ owner, const float* __restrict__ g_emb, int n_rows, int E, int topn,
@@ -51,24 +50,28 @@ update_sqnorm_kernel(const float* __restrict__ grad, long long n, const long lon
         }
         if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = grad[(n4 << 2) + threadIdx.x]; s += v * v; }
     } else {
+        // one warp per token slot (grid-stride): thousands of independent {word -> owner -> row} chains in flight
         const int row_blocks = gridDim.x - dense_blocks;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int base = (((int)blockIdx.x - dense_blocks) * kUpdWarps + warp) * 32; base < n_rows;
-             base += row_blocks * kUpdWarps * 32) {
-            const int row = base + lane;
-            long long w = 0;
-            bool live = false;
-            if (row < n_rows) {
-                w = words[row];
-                live = w != 0 && w < topn && owner[w] == row;
-            }
-            unsigned m = __ballot_sync(GPT_FULL_MASK, live);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const long long ww = __shfl_sync(GPT_FULL_MASK, w, src);
-                const float* gr = g_emb + (size_t)ww * E;
-                for (int c = lane; c < E; c += 32) { const float v = gr[c]; s += v * v; }
+        for (int row = ((int)blockIdx.x - dense_blocks) * kUpdWarps + warp; row < n_rows;
+             row += row_blocks * kUpdWarps) {
+            const long long w = words[row];
+            if (w == 0 || w >= topn || owner[w] != row) continue;     // warp-uniform
+            const float* gr = g_emb + (size_t)w * E;
+            if ((E & 3) == 0) {
+                const float4* g4 = reinterpret_cast<const float4*>(gr);
+                float4 v[kRowVec];
+#pragma unroll
+                for (int i = 0; i < kRowVec; ++i)
+                    v[i] = lane + 32 * i < (E >> 2) ? g4[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < kRowVec; ++i) s += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+                for (int c = lane + 32 * kRowVec; c < (E >> 2); c += 32) {
+                    const float4 u = g4[c];
+                    s += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+                }
+            } else {
+                for (int c = lane; c < E; c += 32) { const float u = gr[c]; s += u * u; }
             }
         }
     }
@@ -117,29 +120,45 @@ update_apply_kernel(float* __restrict__ param, float* __restrict__ grad, long lo
     } else {
         const int row_blocks = gridDim.x - dense_blocks;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int base = (((int)blockIdx.x - dense_blocks) * kUpdWarps + warp) * 32; base < n_rows;
-             base += row_blocks * kUpdWarps * 32) {
-            const int row = base + lane;
-            long long w = 0;
-            bool live = false;
-            if (row < n_rows) {
-                w = words[row];
-                live = w != 0 && w < topn && owner[w] == row;
-            }
-            unsigned m = __ballot_sync(GPT_FULL_MASK, live);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const long long ww = __shfl_sync(GPT_FULL_MASK, w, src);
-                float* gr = g_emb + (size_t)ww * E;
-                float* wr = emb_w + (size_t)ww * E;
+        for (int row = ((int)blockIdx.x - dense_blocks) * kUpdWarps + warp; row < n_rows;
+             row += row_blocks * kUpdWarps) {
+            const long long w = words[row];
+            if (w == 0 || w >= topn || owner[w] != row) continue;     // warp-uniform
+            float* gr = g_emb + (size_t)w * E;
+            float* wr = emb_w + (size_t)w * E;
+            if ((E & 3) == 0) {
+                float4* g4 = reinterpret_cast<float4*>(gr);
+                float4* w4 = reinterpret_cast<float4*>(wr);
+                float4 gv[kRowVec], wv[kRowVec];
+#pragma unroll
+                for (int i = 0; i < kRowVec; ++i) {      // all loads of the row first: one round trip to HBM
+                    const bool in = lane + 32 * i < (E >> 2);
+                    gv[i] = in ? g4[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    wv[i] = in ? w4[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < kRowVec; ++i) {
+                    if (lane + 32 * i < (E >> 2)) {
+                        wv[i].x -= a * gv[i].x; wv[i].y -= a * gv[i].y; wv[i].z -= a * gv[i].z; wv[i].w -= a * gv[i].w;
+                        w4[lane + 32 * i] = wv[i];
+                        g4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                for (int c = lane + 32 * kRowVec; c < (E >> 2); c += 32) {
+                    const float4 g = g4[c];
+                    float4 q = w4[c];
+                    q.x -= a * g.x; q.y -= a * g.y; q.z -= a * g.z; q.w -= a * g.w;
+                    w4[c] = q;
+                    g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
                 for (int c = lane; c < E; c += 32) {
                     wr[c] -= a * gr[c];
                     gr[c] = 0.f;
                 }
             }
             __syncwarp();
-            if (live) owner[w] = 0x7fffffff;     // only the owning token resets it; nobody else reads it any more
+            if (lane == 0) owner[w] = 0x7fffffff;   // readers of other tokens of this word see "not mine" either way
         }
     }
 }
@@ -148,8 +167,8 @@ int plan(long long n, int n_rows, int* dense_blocks, int* row_blocks) {
     long long db = (n / 4 + kUpdThreads * 4 - 1) / (kUpdThreads * 4);     // ~4 float4 per thread
     if (db < 1) db = 1;
     if (db > 296) db = 296;
-    int rb = n_rows > 0 ? (n_rows + kUpdWarps * 32 - 1) / (kUpdWarps * 32) : 0;
-    if (rb > 296) rb = 296;
+    int rb = n_rows > 0 ? (n_rows + kUpdWarps - 1) / kUpdWarps : 0;     // one warp per token slot ...
+    if (rb > kMaxPartials - 296) rb = kMaxPartials - 296;               // ... grid-stride beyond that
     *dense_blocks = n > 0 ? (int)db : 0;
     *row_blocks = rb;
     return *dense_blocks + rb;

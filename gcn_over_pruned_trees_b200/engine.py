@@ -226,6 +226,7 @@ class FusedTrainStep(object):
         self._lr = self.trainer.optimizer.param_groups[0]['lr']
         self.kernels_per_replay = {}
         self.replays = 0
+        self.side = (torch.cuda.Stream(), torch.cuda.Stream())
         self.exchange = None                # data-parallel hook: callable(flat_grad, sparse) between backward and K7
 
     @staticmethod
@@ -268,18 +269,46 @@ class FusedTrainStep(object):
         p_in, p_gcn = opt['input_dropout'], opt['gcn_dropout']
         pos_w = gm.pos_emb.weight if self.use_pos else None
         ner_w = gm.ner_emb.weight if self.use_ner else None
+        # Independent work runs on two side streams (forked / joined with events, so the same code is what the CUDA
+        # graph captures as parallel branches): K1 and the weight preparation beside the embedding stage, every weight
+        # gradient beside the data-gradient chain.  Buffers touched by a side stream are allocated here, on the main
+        # stream, and kept alive in `keep` until the final join.
+        main = torch.cuda.current_stream()
+        sa, sb = self.side
+        keep = []
+
+        def fork(stream):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            stream.wait_event(ev)
+
+        def join(stream):
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            main.wait_event(ev)
+
+        n_layers = len(gcn.W)
+        csr = ops.TreeCSR(B, T, words.device)
+        wss = [ops.weight_prep_buffer(lin.weight.data, mode) for lin in gcn.W]
+        keep += [csr, wss]
         # forward
-        csr = ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'])
+        fork(sa)
+        fork(sb)
+        with torch.cuda.stream(sa):
+            ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'], out=csr)
+        with torch.cuda.stream(sb):
+            for lin, ws in zip(gcn.W, wss):
+                ops.weight_prep(lin.weight.data, mode, out=ws)
         x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
                           None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
-        xs, acts, wss = [], [], []
+        join(sb)
+        xs, acts = [], []
         h = x
-        n_layers = len(gcn.W)
         for l, lin in enumerate(gcn.W):
-            ws = ops.weight_prep(lin.weight.data, mode)
-            y = ops.linear_fwd(h.view(B * T, -1), lin.weight.data, mode, ws)
+            y = ops.linear_fwd(h.view(B * T, -1), lin.weight.data, mode, wss[l])
+            if l == 0:
+                join(sa)
             xs.append(h)
-            wss.append(ws)
             h, act = ops.aggregate_fwd(y, csr, lin.bias.data, use_adj, 0.0 if l == n_layers - 1 else p_gcn, rng, l,
                                        None, want_act=True)
             acts.append(act)
@@ -288,14 +317,21 @@ class FusedTrainStep(object):
         ops.head_fwd_bwd(pooled, labels, [m.weight.data for m in self.mlp], [m.bias.data for m in self.mlp],
                          self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=True)
         # backward
-        ops.head_wgrad(pooled, buf, [fl.g(m.weight) for m in self.mlp], [fl.g(m.bias) for m in self.mlp],
-                       fl.g(self.cls.weight), fl.g(self.cls.bias))
+        keep += [pooled, buf, xs]
+        fork(sa)
+        with torch.cuda.stream(sa):
+            ops.head_wgrad(pooled, buf, [fl.g(m.weight) for m in self.mlp], [fl.g(m.bias) for m in self.mlp],
+                           fl.g(self.cls.weight), fl.g(self.cls.bias))
         dh = ops.pool3_bwd(buf.dpooled, argmax, csr, ptype, H)
         for l in range(n_layers - 1, -1, -1):
             lin = gcn.W[l]
             dy, _ = ops.aggregate_bwd(dh, None, csr, use_adj, 0.0 if l == n_layers - 1 else p_gcn, None,
                                       act=acts[l], dbias_out=fl.g(lin.bias))
-            ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True)
+            keep.append(dy)
+            side = sb if (n_layers - 1 - l) % 2 == 0 else sa
+            fork(side)
+            with torch.cuda.stream(side):
+                ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True)
             dh = ops.linear_dgrad(dy, lin.weight.data, mode, wss[l]).view(B, T, -1)
         sp = self.sparse
         if sp is not None:
@@ -305,6 +341,9 @@ class FusedTrainStep(object):
                       fl.g(ner_w) if ner_w is not None else None, sp.owner if sp is not None else None,
                       self.emb_weight.shape[0], self.emb_weight.shape[1], sp.topn if sp is not None else 0, p_in, rng,
                       0xE0)
+        join(sa)
+        join(sb)
+        del keep
         self.last_csr = csr
         scale = 1.0
         if self.exchange is not None:

@@ -107,7 +107,7 @@ class TreeCSR(object):
             raise _lib.GptError('malformed dependency tree in batch row %d: %s' % (bad[0], why))
 
 
-def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k):
+def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k, out=None):
     """K1: batched head_to_tree + tree_to_adj (model/tree.py:58-204, model/gcn.py:96-110) -> TreeCSR."""
     head = _dev(head, torch.int64, 'head')
     subj_pos = _dev(subj_pos, torch.int64, 'subj_pos')
@@ -117,7 +117,7 @@ def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k):
         masks = masks.view(torch.uint8) if masks.is_contiguous() else masks.contiguous().view(torch.uint8)
     masks = _dev(masks, torch.uint8, 'masks')
     B, T = head.shape
-    csr = TreeCSR(B, T, head.device)
+    csr = TreeCSR(B, T, head.device) if out is None else out
     _call('gpt_prune_csr', _ptr(head), _ptr(subj_pos), _ptr(obj_pos), _ptr(deprel), _ptr(masks), B, T,
           int(prune_k), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(csr.flags),
           _ptr(csr.denom), _ptr(csr.lens), _ptr(csr.err), _stream())
@@ -130,12 +130,19 @@ def _tf32_ok(*dims):
     return all(d % 4 == 0 for d in dims)
 
 
-def weight_prep(weight, mode):
-    """Per-step operand preparation of the 3xTF32 projection: [w_hi | w_lo | w^T_hi | w^T_lo]; None otherwise."""
+def weight_prep_buffer(weight, mode):
     N, K = weight.shape
     if mode != 'tf32x3' or not _tf32_ok(N, K):
         return None
-    ws = torch.empty((4, N * K), dtype=torch.float32, device=weight.device)
+    return torch.empty((4, N * K), dtype=torch.float32, device=weight.device)
+
+
+def weight_prep(weight, mode, out=None):
+    """Per-step operand preparation of the 3xTF32 projection: [w_hi | w_lo | w^T_hi | w^T_lo]; None otherwise."""
+    N, K = weight.shape
+    ws = weight_prep_buffer(weight, mode) if out is None else out
+    if ws is None:
+        return None
     _call('gpt_weight_prep_tf32x3', _ptr(weight), _ptr(ws), N, K, _stream())
     return ws
 
