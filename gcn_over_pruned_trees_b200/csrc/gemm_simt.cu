@@ -154,6 +154,101 @@ __global__ void zero_rows_kernel(float* C, int rows, int cols, int ldc) {
     if (i < (size_t)rows * cols) C[(i / cols) * ldc + (i % cols)] = 0.f;
 }
 
+// wgrad over the rows that carry a gradient: dW[n,k] += sum_{m : flags[m] != 0} dY[m,n] * X[m,k].
+// Rows of tokens outside the pruned tree (and padding) have dY == 0 exactly; at prune_k = 1 that is ~3/4 of a
+// TACRED-shaped batch.  Each CTA owns a 64x64 tile of dW and a contiguous range of rows; it compacts the live rows
+// of a window into a shared index list (ballot + warp-count prefix) and reduces over that list in slabs of 16.
+constexpr int kRowWin = 2048;
+
+__global__ void __launch_bounds__(kGemmThreads)
+wgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, const unsigned char* __restrict__ flags,
+                  float* __restrict__ dw, int M, int N, int K, int rows_per_cta) {
+    __shared__ __align__(16) float As[BK][BM + 4];   // [slab row][n]
+    __shared__ __align__(16) float Bs[BK][BN + 4];   // [slab row][k]
+    __shared__ int s_rows[kRowWin];
+    __shared__ int s_wcnt[kGemmThreads / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * BM, k0 = blockIdx.y * BN;
+    const int r_begin = blockIdx.z * rows_per_cta, r_end = min(M, r_begin + rows_per_cta);
+    const int ty = tid / 16, tx = tid % 16;
+    const bool vec_a = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    const bool vec_b = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int w0 = r_begin; w0 < r_end; w0 += kRowWin) {
+        const int w1 = min(r_end, w0 + kRowWin);
+        int n_act = 0;
+        for (int base = w0; base < w1; base += kGemmThreads) {
+            const int r = base + tid;
+            const bool live = r < w1 && (flags == nullptr || flags[r] != 0);
+            const unsigned m = __ballot_sync(GPT_FULL_MASK, live);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            int before = 0, round = 0;
+#pragma unroll
+            for (int w = 0; w < kGemmThreads / 32; ++w) {
+                const int c = s_wcnt[w];
+                before += w < warp ? c : 0;
+                round += c;
+            }
+            if (live) s_rows[n_act + before + __popc(m & ((1u << lane) - 1u))] = r;
+            n_act += round;
+            __syncthreads();
+        }
+        for (int s0 = 0; s0 < n_act; s0 += BK) {
+            const int rr = tid / 16, c4 = (tid % 16) * 4;
+            const int row = s0 + rr < n_act ? s_rows[s0 + rr] : -1;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (row >= 0) {
+                const float* pa = dy + (size_t)row * N + n0 + c4;
+                const float* pb = x + (size_t)row * K + k0 + c4;
+                if (vec_a && n0 + c4 + 3 < N) a = __ldg(reinterpret_cast<const float4*>(pa));
+                else {
+                    if (n0 + c4 < N) a.x = pa[0];
+                    if (n0 + c4 + 1 < N) a.y = pa[1];
+                    if (n0 + c4 + 2 < N) a.z = pa[2];
+                    if (n0 + c4 + 3 < N) a.w = pa[3];
+                }
+                if (vec_b && k0 + c4 + 3 < K) b = __ldg(reinterpret_cast<const float4*>(pb));
+                else {
+                    if (k0 + c4 < K) b.x = pb[0];
+                    if (k0 + c4 + 1 < K) b.y = pb[1];
+                    if (k0 + c4 + 2 < K) b.z = pb[2];
+                    if (k0 + c4 + 3 < K) b.w = pb[3];
+                }
+            }
+            *reinterpret_cast<float4*>(&As[rr][c4]) = a;
+            *reinterpret_cast<float4*>(&Bs[rr][c4]) = b;
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                const float4 av4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                const float av[4] = {av4.x, av4.y, av4.z, av4.w}, bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < K && acc[i][j] != 0.f) atomicAdd(dw + (size_t)n * K + k, acc[i][j]);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int gpt_linear_fwd_f32(const float* x, const float* w, float* y, int M, int N, int K, void* stream) {
@@ -188,4 +283,18 @@ extern "C" int gpt_linear_wgrad_f32_acc(const float* dy, const float* x, float* 
     const long tiles = (long)((N + BN - 1) / BN) * ((K + BM - 1) / BM);
     int splits = (int)max(1L, min((long)(M + 255) / 256, (4L * 148 + tiles - 1) / tiles));
     return run_sgemm<false, false>(N, K, M, dy, N, x, K, dw, K, splits, (cudaStream_t)stream, /*force_atomic=*/true);
+}
+
+extern "C" int gpt_linear_wgrad_rows_f32(const float* dy, const float* x, const uint8_t* flags, float* dw, int M,
+                                         int N, int K, void* stream) {
+    GPT_CHECK_ARG(dy && x && dw && M >= 0 && N >= 1 && K >= 1);
+    if (M == 0) return GPT_OK;
+    const long tiles = (long)((N + BM - 1) / BM) * ((K + BN - 1) / BN);
+    int splits = (int)max(1L, min((long)(M + 255) / 256, (4L * 148 + tiles - 1) / tiles));
+    int rows_per_cta = ((M + splits - 1) / splits + 31) / 32 * 32;
+    splits = (M + rows_per_cta - 1) / rows_per_cta;
+    dim3 grid((N + BM - 1) / BM, (K + BN - 1) / BN, splits);
+    if (grid.y > 65535 || grid.z > 65535) return GPT_ERR_UNSUPPORTED;
+    wgrad_rows_kernel<<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(dy, x, flags, dw, M, N, K, rows_per_cta);
+    return gpt_launch_status();
 }

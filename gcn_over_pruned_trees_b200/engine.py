@@ -331,7 +331,8 @@ class FusedTrainStep(object):
             side = sb if (n_layers - 1 - l) % 2 == 0 else sa
             fork(side)
             with torch.cuda.stream(side):
-                ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True)
+                ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True,
+                                 flags=csr.flags)
             dh = ops.linear_dgrad(dy, lin.weight.data, mode, wss[l]).view(B, T, -1)
         sp = self.sparse
         if sp is not None:

@@ -184,11 +184,15 @@ def linear_dgrad(dy, weight, mode='fp32', ws=None):
     return dx
 
 
-def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False):
-    """dw = dy^T x.  accumulate: add into ``out`` (which the caller keeps zeroed between steps) instead of overwriting."""
+def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False, flags=None):
+    """dw = dy^T x.  accumulate: add into ``out`` (which the caller keeps zeroed between steps) instead of overwriting;
+    with ``flags`` (K1's per-row flags) only rows that carry a gradient are read."""
     M, N = dy.shape
     K = x2d.shape[1]
     dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
+    if accumulate and flags is not None:
+        _call('gpt_linear_wgrad_rows_f32', _ptr(dy), _ptr(x2d), _ptr(flags), _ptr(dw), M, N, K, _stream())
+        return dw
     _call('gpt_linear_wgrad_f32_acc' if accumulate else 'gpt_linear_wgrad_f32', _ptr(dy), _ptr(x2d), _ptr(dw), M, N,
           K, _stream())
     return dw

@@ -105,6 +105,10 @@ int gpt_linear_dgrad_f32(const float* dy, const float* w, float* dx, int M, int 
 int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
 /* dw += dy^T x (no zero-fill launch: for gradient buffers the caller keeps zeroed between steps, see K7) */
 int gpt_linear_wgrad_f32_acc(const float* dy, const float* x, float* dw, int M, int N, int K, void* stream);
+/* dw += dy^T x over the rows with flags[m] != 0 only (flags = gpt_prune_csr's [B*T] output, NULL = all rows): the
+ * other rows of dy are exactly zero (K2 backward), so they are never read */
+int gpt_linear_wgrad_rows_f32(const float* dy, const float* x, const uint8_t* flags, float* dw, int M, int N, int K,
+                              void* stream);
 /* K3 on the tensor cores: tcgen05.mma kind::tf32, TMA-fed, accumulator in TMEM (GPT_GEMM_TF32, ~1e-3 relative).
  *     Needs K % 4 == 0 (and N % 4 == 0 for dgrad) and 16-byte aligned operands, else GPT_ERR_UNSUPPORTED.
  *     dgrad takes a float [K*N] workspace for the transposed weight. */

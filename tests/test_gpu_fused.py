@@ -252,3 +252,22 @@ def test_fused_step_lr_change_recaptures():
     tr.update_lr(0.0)
     tr.train_step(batch)
     assert torch.equal(tr.model.classifier.weight, w0)         # lr 0: nothing moves
+
+
+# ---------------------------------------------------------------- K3 wgrad over live rows -----------------------------
+
+@pytest.mark.parametrize('M,N,K,frac', [(2750, 200, 360, 0.25), (2750, 200, 200, 0.4), (50, 64, 85, 1.0),
+                                        (5000, 30, 17, 0.02), (9000, 512, 360, 0.7), (300, 200, 360, 0.0)])
+def test_k3_wgrad_over_live_rows(M, N, K, frac):
+    g = torch.Generator().manual_seed(M + N)
+    flags = (torch.rand(M, generator=g) < frac).to(torch.uint8).to(DEV) * 5
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    live = flags != 0
+    ref = (dy * live[:, None]).double().t() @ x.double()
+    dw = torch.full((N, K), 2.0, device=DEV)                  # accumulates into what is there
+    ops.linear_wgrad(dy, x, out=dw, accumulate=True, flags=flags)     # rows with flags == 0 are never read
+    assert _rel(dw - 2.0, ref) <= 1e-5 if frac > 0 else float((dw - 2.0).abs().max()) == 0.0
+    dw2 = torch.zeros((N, K), device=DEV)
+    ops.linear_wgrad(dy, x, out=dw2, accumulate=True, flags=None)     # no flags: every row
+    assert _rel(dw2, dy.double().t() @ x.double()) <= 1e-5
