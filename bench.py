@@ -63,8 +63,10 @@ def workload_config(args, world):
             'len': 'clip(Poisson(36),8,96)', 'layers': 2, 'in_dim': 360, 'hidden': 200, 'vocab': VOCAB,
             'prune_k': args.prune_k, 'gemm': args.gemm, 'parallelism': 'dp%d' % world,
             'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd',
-            'engine': 'eager' if args.eager else ('cuda_graph_autograd' if args.autograd_engine or world > 1 else
-                                                  'cuda_graph_fused_step'), 'l2': 'flushed between timed steps (256 MiB fill)'}
+            'engine': 'eager' if args.eager else ('cuda_graph_autograd' if args.autograd_engine else
+                                                  'cuda_graph_fused_step'),
+            'exchange': 'none' if world == 1 else ('nccl_allreduce' if args.autograd_engine or args.eager else
+                                                   'nvlink_peer_memory_push_reduce (K8)'), 'l2': 'flushed between timed steps (256 MiB fill)'}
 
 
 # ------------------------------------------------------------------------------------------------ clocks -------
@@ -263,8 +265,11 @@ def run_b200(args):
         return loss
 
     from gcn_over_pruned_trees_b200.engine import FusedTrainStep, GraphedTrainStep
-    fused = world == 1 and not args.autograd_engine and FusedTrainStep.unsupported_reason(trainer) is None
-    graphed = FusedTrainStep(trainer) if fused else GraphedTrainStep(trainer, reducer=reducer)
+    fused = not args.autograd_engine and FusedTrainStep.unsupported_reason(trainer) is None
+    if fused:       # N > 1: gradients meet through NVLink peer memory inside the step's own kernels (K8), no NCCL
+        graphed = FusedTrainStep(trainer, data_parallel=world > 1, max_rows=BATCH * 128)
+    else:
+        graphed = GraphedTrainStep(trainer, reducer=reducer)
     step = eager_step if args.eager else graphed
 
     # warm-up: every batch shape runs eagerly 3x, is captured, and is replayed at least once
@@ -323,17 +328,21 @@ def run_b200(args):
            'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / args.steps * 1e3,
            'api': ('GCNTrainer.update(host batch) + backward + clip + SGD + loss.item()' if args.eager else
                    'GCNTrainer.train_step(pinned host batch) [one CUDA-graph replay] + loss.item()')}
-    n_eager = min(args.steps, 30)
-    eager_s = timed_host_loop(eager_step, n_eager)
-    e2e['dropin_eager'] = {'value': BATCH * world * n_eager / eager_s, 'ms_per_step': eager_s / n_eager * 1e3,
-                           'api': 'reference call sequence train.py:213-227 on the new model package, eager'}
-
+    if world == 1:
+        n_eager = min(args.steps, 30)
+        eager_s = timed_host_loop(eager_step, n_eager)
+        e2e['dropin_eager'] = {'value': BATCH * world * n_eager / eager_s, 'ms_per_step': eager_s / n_eager * 1e3,
+                               'api': 'reference call sequence train.py:213-227 on the new model package, eager'}
+    if world > 1:
+        parallel.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
 
     # ---- per-entry-point device time inside the step (separate instrumented pass, not the headline) ------------
-    ops.TIMER = ops.KernelTimer()
-    n_prof = min(args.steps, 20)
+    kernels = None
+    ops.TIMER = ops.KernelTimer() if world == 1 else None
+    n_prof = min(args.steps, 20) if world == 1 else 0
     pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     pa.record()
@@ -344,11 +353,15 @@ def run_b200(args):
         else:
             eager_step(resident[i % N_BATCHES])
     pb.record()
-    summary = ops.TIMER.summary()
-    ops.TIMER = None
-    prof_ms = pa.elapsed_time(pb)
-    kernels = {k: {'calls_per_step': c / n_prof, 'us_per_call': ms / c * 1e3, 'share_of_step': ms / prof_ms}
-               for k, (c, ms) in sorted(summary.items(), key=lambda kv: -kv[1][1])}
+    if ops.TIMER is not None:
+        summary = ops.TIMER.summary()
+        ops.TIMER = None
+        prof_ms = pa.elapsed_time(pb)
+        # eager launches: each interval also contains the host-side gap before the launch; the ncu launch list under
+        # profiles/ holds the kernel-only durations
+        kernels = {k: {'calls_per_step': c / n_prof, 'us_per_call_incl_launch_gap': ms / c * 1e3,
+                       'share_of_step': ms / prof_ms}
+                   for k, (c, ms) in sorted(summary.items(), key=lambda kv: -kv[1][1])}
 
     peaks = load_peaks()
     roof = None

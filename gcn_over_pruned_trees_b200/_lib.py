@@ -43,6 +43,16 @@ SIGNATURES = {
     'gpt_head_fwd_bwd': [_p, _p, _p, _p, _c_int, _p, _p, _c_int, _c_int, _c_int, _c_f, _c_int, _p, _p, _p, _p, _p, _p,
                          _p],
     'gpt_head_wgrad': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p],
+    'gpt_dp_region_bytes': [_c_int, _c_int, _c_int, _c_int, _c_ll],
+    'gpt_dp_partials': [_c_int, _c_int, _c_int, _c_int, _c_ll],
+    'gpt_dp_alloc': [_c_ll, _p, _p],
+    'gpt_dp_open': [_p, _p],
+    'gpt_dp_close': [_p],
+    'gpt_dp_free': [_p],
+    'gpt_dp_region_init': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p],
+    'gpt_dp_push': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _p],
+    'gpt_dp_reduce': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p],
+    'gpt_dp_apply': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_f, _c_f, _p, _p, _p],
     'gpt_update_partials': [_c_ll, _c_int],
     'gpt_update_sqnorm': [_p, _c_ll, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_update_apply': [_p, _p, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _c_f, _p, _p, _p],
@@ -68,6 +78,7 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = _c_int
         handle.gpt_launch_count.restype = ctypes.c_ulonglong
+        handle.gpt_dp_region_bytes.restype = ctypes.c_longlong
         handle.gpt_error_string.argtypes = [_c_int]
         handle.gpt_error_string.restype = ctypes.c_char_p
         _lib = handle

@@ -190,7 +190,7 @@ class FusedTrainStep(object):
     configuration can run here; everything else stays on GraphedTrainStep (autograd under capture).
     """
 
-    def __init__(self, trainer, max_grad_norm=None, warmup=2):
+    def __init__(self, trainer, max_grad_norm=None, warmup=2, data_parallel=False, max_rows=8192):
         from . import ops
         why = self.unsupported_reason(trainer)
         if why:
@@ -218,7 +218,6 @@ class FusedTrainStep(object):
         self.sparse = ops.SparseEmbeddingState(emb.data, self.opt['topn']) if emb.requires_grad else None
         self.mlp = [m for m in gm.out_mlp if isinstance(m, torch.nn.Linear)]
         self.cls = self.model.classifier
-        n_rows_max = 0
         self.partials = torch.zeros(1024, dtype=torch.float32, device=emb.device)
         self.total_norm = torch.zeros((), dtype=torch.float32, device=emb.device)
         self.gcn.rng_state[1] += 1          # the autograd path advances the stream before its first forward
@@ -227,7 +226,12 @@ class FusedTrainStep(object):
         self.kernels_per_replay = {}
         self.replays = 0
         self.side = (torch.cuda.Stream(), torch.cuda.Stream())
-        self.exchange = None                # data-parallel hook: callable(flat_grad, sparse) between backward and K7
+        self.exchange = None
+        self.max_rows = max_rows
+        if data_parallel:                   # collective: every rank constructs its engine at the same point
+            from .parallel import PeerExchange
+            self.exchange = PeerExchange(max_rows, emb.shape[1], emb.shape[0], self.flat.grad.numel())
+            self.partials = torch.zeros(max(1024, self.exchange.n_partials), dtype=torch.float32, device=emb.device)
 
     @staticmethod
     def unsupported_reason(trainer):
@@ -346,13 +350,19 @@ class FusedTrainStep(object):
         join(sb)
         del keep
         self.last_csr = csr
-        scale = 1.0
-        if self.exchange is not None:
-            scale = self.exchange(fl.grad, sp)
-        if update:
+        lr = self.trainer.optimizer.param_groups[0]['lr']
+        if not update:
+            pass
+        elif self.exchange is None:                           # K7
             ops.update_sqnorm(fl.grad, sp, self.partials)
-            ops.update_apply(fl.param, fl.grad, sp, self.emb_weight.data, self.partials, self.max_grad_norm,
-                             self.trainer.optimizer.param_groups[0]['lr'], scale, self.total_norm, rng[1:])
+            ops.update_apply(fl.param, fl.grad, sp, self.emb_weight.data, self.partials, self.max_grad_norm, lr, 1.0,
+                             self.total_norm, rng[1:])
+        else:                                                 # K8: exchange over peer memory + K7 on the mean
+            ex = self.exchange
+            ops.dp_push(ex.ptrs, ex.rank, ex.shape, fl.grad, sp)
+            ops.dp_reduce(ex.ptrs[ex.rank], ex.shape, fl.grad, self.partials)
+            ops.dp_apply(ex.ptrs[ex.rank], ex.shape, fl.param, fl.grad, self.emb_weight.data, self.partials,
+                         self.max_grad_norm, lr, self.total_norm, rng[1:])
         return buf.loss, buf.logits
 
     def _capture(self, key, inputs, labels):

@@ -473,3 +473,55 @@ def update_apply(flat_param, flat_grad, sparse, emb_weight, partials, max_norm, 
           _ptr(sparse.G if sparse else None), _ptr(emb_weight if sparse else None), n_rows,
           sparse.G.shape[1] if sparse else 1, sparse.topn if sparse else 0, _ptr(partials), float(max_norm), float(lr),
           float(grad_scale), _ptr(total_norm), _ptr(step_counter), _stream())
+
+
+# ---- K8: data-parallel exchange over peer memory -----------------------------------------------------------------
+
+class ExchangeRegion(object):
+    """One rank's exchange region (csrc/dp.cu): cudaMalloc'ed by the library, shareable through its cudaIpc handle."""
+
+    def __init__(self, world, cap_rows, E, V, n_flat):
+        import ctypes
+        self.shape = (int(world), int(cap_rows), int(E), int(V), int(n_flat))
+        nbytes = _lib.lib().gpt_dp_region_bytes(*self.shape)
+        if nbytes <= 0:
+            raise _lib.GptError('bad exchange layout %r' % (self.shape,))
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().gpt_dp_alloc(nbytes, ctypes.byref(ptr), handle), 'gpt_dp_alloc')
+        self.ptr, self.handle, self.nbytes = ptr.value, handle.raw, nbytes
+        self.n_partials = int(_lib.lib().gpt_dp_partials(*self.shape))
+        _call('gpt_dp_region_init', self.ptr, *self.shape, _stream())
+        torch.cuda.current_stream().synchronize()
+
+    def free(self):
+        if self.ptr:
+            _lib.lib().gpt_dp_free(self.ptr)
+            self.ptr = None
+
+
+def open_peer_region(handle):
+    """Map a peer rank's region (its 64-byte cudaIpc handle) into this process -> device pointer."""
+    import ctypes
+    ptr = ctypes.c_void_p()
+    _lib.check(_lib.lib().gpt_dp_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)), 'gpt_dp_open')
+    return ptr.value
+
+
+def dp_push(region_ptrs, rank, shape, flat_grad, sparse):
+    import ctypes
+    arr = (ctypes.c_void_p * len(region_ptrs))(*region_ptrs)
+    n_rows = sparse.words.numel() if sparse is not None else 0
+    _call('gpt_dp_push', arr, rank, *shape, _ptr(flat_grad), _ptr(sparse.G if sparse else None),
+          _ptr(sparse.owner if sparse else None), _ptr(sparse.words if sparse else None), n_rows,
+          sparse.topn if sparse else 0, _stream())
+
+
+def dp_reduce(region_ptr, shape, flat_grad, partials):
+    _call('gpt_dp_reduce', region_ptr, *shape, _ptr(flat_grad), _ptr(partials), _stream())
+
+
+def dp_apply(region_ptr, shape, flat_param, flat_grad, emb_weight, partials, max_norm, lr, total_norm=None,
+             step_counter=None):
+    _call('gpt_dp_apply', region_ptr, *shape, _ptr(flat_param), _ptr(flat_grad), _ptr(emb_weight), _ptr(partials),
+          float(max_norm), float(lr), _ptr(total_norm), _ptr(step_counter), _stream())

@@ -104,3 +104,30 @@ def max_over_ranks(value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class PeerExchange(object):
+    """The exchange regions of all ranks of one node, mapped into this process (csrc/dp.cu, K8).
+
+    Construction is collective: every rank allocates its region, the 64-byte cudaIpc handles travel through the
+    process group once (all_gather_object), peers are opened, and a barrier guarantees that every region is
+    initialised before the first push.  After that the step path never calls NCCL: ranks meet through flags in
+    peer memory, inside the kernels.
+    """
+
+    def __init__(self, cap_rows, emb_dim, vocab, n_flat, group=None):
+        from . import ops
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise ValueError('PeerExchange is a single-node (<= 8 GPU) exchange')
+        self.region = ops.ExchangeRegion(self.world, cap_rows, emb_dim, vocab, n_flat)
+        self.shape = self.region.shape
+        self.n_partials = self.region.n_partials
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, self.region.handle, group=group)
+        self.ptrs = [self.region.ptr if r == self.rank else ops.open_peer_region(handles[r])
+                     for r in range(self.world)]
+        if self.world > 1:
+            dist.barrier(group=group)

@@ -177,6 +177,34 @@ int gpt_update_apply(float* param, float* grad, long long n, const int64_t* word
                      float* emb_w, int n_rows, int E, int topn, const float* partials, float max_norm, float lr,
                      float grad_scale, float* total_norm, uint64_t* step_counter, void* stream);
 
+/* K8. data-parallel gradient exchange over NVLink peer memory, fused with K7 (csrc/dp.cu; the reference is
+ *     single-device, so this replaces nothing: it is the one collective sentence sharding adds).
+ *     Every rank owns a region of gpt_dp_region_bytes(); regions[q] is rank q's region as mapped in this process
+ *     (own: gpt_dp_alloc, peers: gpt_dp_open on the 64-byte cudaIpc handle).  W <= 8; cap_rows >= n_rows of any step.
+ *     Per step, in stream order on every rank:
+ *       gpt_dp_push    stores this rank's flat gradient, live word ids / rows and word->slot map into every region,
+ *                      raises flags[rank] = step everywhere; clears g_emb rows and owner marks
+ *       gpt_dp_reduce  waits for all W flags, sums in rank order (bit-identical on every rank) into flat_g and the
+ *                      first-owner row slots, writes gpt_dp_partials() partial sums of g^2
+ *       gpt_dp_apply   K7 with the mean gradient (sum / W): clip, SGD, resets; advances the region's step and
+ *                      *step_counter
+ *     A rank that waits more than ~10 s for a peer traps (the launch fails) instead of spinning for ever. */
+long long gpt_dp_region_bytes(int W, int cap_rows, int E, int V, long long n_flat);
+int gpt_dp_partials(int W, int cap_rows, int E, int V, long long n_flat);
+int gpt_dp_alloc(long long bytes, void** ptr, void* ipc_handle_out /* 64 bytes, host */);
+int gpt_dp_open(const void* ipc_handle, void** ptr);
+int gpt_dp_close(void* ptr);
+int gpt_dp_free(void* ptr);
+int gpt_dp_region_init(void* region, int W, int cap_rows, int E, int V, long long n_flat, void* stream);
+int gpt_dp_push(void* const* regions /* host array of W device pointers */, int rank, int W, int cap_rows, int E, int V,
+                long long n_flat, const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words, int n_rows,
+                int topn, void* stream);
+int gpt_dp_reduce(void* region, int W, int cap_rows, int E, int V, long long n_flat, float* flat_g, float* partials,
+                  void* stream);
+int gpt_dp_apply(void* region, int W, int cap_rows, int E, int V, long long n_flat, float* param, float* flat_g,
+                 float* emb_w, const float* partials, float max_norm, float lr, float* total_norm,
+                 uint64_t* step_counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

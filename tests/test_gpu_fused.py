@@ -271,3 +271,92 @@ def test_k3_wgrad_over_live_rows(M, N, K, frac):
     dw2 = torch.zeros((N, K), device=DEV)
     ops.linear_wgrad(dy, x, out=dw2, accumulate=True, flags=None)     # no flags: every row
     assert _rel(dw2, dy.double().t() @ x.double()) <= 1e-5
+
+
+# ---------------------------------------------------------------- K8 (virtual ranks on one GPU) ------------------------
+
+def _sparse_state(emb, words, topn, scale, gen):
+    V, E = emb.shape
+    st = ops.SparseEmbeddingState(emb, topn)
+    st.words = words
+    live = torch.unique(words[(words != 0) & (words < topn)])
+    st.G[live] = (torch.randn(live.numel(), E, generator=gen) * scale).to(DEV)
+    first = {}
+    for r, w in enumerate(words.tolist()):
+        if w != 0 and w < topn and w not in first:
+            first[w] = r
+    for w, r in first.items():
+        st.owner[w] = r
+    return st
+
+
+@pytest.mark.parametrize('W', (1, 2, 3, 8))
+def test_k8_exchange_of_virtual_ranks_is_the_mean_gradient_and_bit_identical(W):
+    """W exchange regions in ONE process stand in for W GPUs (peer pointers are ordinary device pointers here): after
+    push x W, reduce + apply on every 'rank' must equal clip_grad_norm_ + SGD on the mean gradient, and the replicas
+    must stay bit-identical.  Three steps, so both parities and all resets are exercised."""
+    gen = torch.Generator().manual_seed(100 + W)
+    n, V, E, cap, topn = 70_016, 900, 300, 512, 850
+    regions = [ops.ExchangeRegion(W, cap, E, V, n) for _ in range(W)]
+    ptrs = [r.ptr for r in regions]
+    shape = regions[0].shape
+    p0 = torch.randn(n, generator=gen).to(DEV)
+    e0 = torch.randn(V, E, generator=gen).to(DEV)
+    params = [p0.clone() for _ in range(W)]
+    embs = [e0.clone() for _ in range(W)]
+    p_ref, e_ref = p0.clone().requires_grad_(), e0.clone().requires_grad_()
+    sgd = torch.optim.SGD([p_ref, e_ref], lr=0.3)
+    partials = torch.zeros(max(1024, regions[0].n_partials), device=DEV)
+    counter = torch.tensor([1, 0], dtype=torch.int64, device=DEV)
+    states = [None] * W
+    for step in range(3):
+        grads, dense_G = [], []
+        for r in range(W):
+            n_rows = int(torch.randint(100, cap, (1,), generator=gen))
+            words = torch.randint(0, V, (n_rows,), generator=gen).to(DEV)    # overlapping vocabularies
+            g = (torch.randn(n, generator=gen) * (30.0 if step == 1 else 0.01)).to(DEV)   # step 1 clips
+            if states[r] is None:
+                states[r] = _sparse_state(embs[r], words, topn, 0.05, gen)
+            else:                       # G / owner were cleaned by the previous push: refill
+                st = _sparse_state(embs[r], words, topn, 0.05, gen)
+                assert float(states[r].G.abs().max()) == 0.0 and int(states[r].owner.min()) == 0x7fffffff
+                states[r] = st
+            grads.append(g.clone())
+            dense_G.append(states[r].G.clone())
+            ops.dp_push(ptrs, r, shape, g, states[r])
+        for r in range(W):
+            g_buf = torch.empty(n, device=DEV)
+            ops.dp_reduce(ptrs[r], shape, g_buf, partials)
+            ops.dp_apply(ptrs[r], shape, params[r], g_buf, embs[r], partials, 5.0, 0.3, None, counter[1:])
+            assert float(g_buf.abs().max()) == 0.0
+        p_ref.grad = torch.stack(grads).sum(0) / W
+        e_ref.grad = torch.stack(dense_G).sum(0) / W
+        torch.nn.utils.clip_grad_norm_([p_ref, e_ref], 5.0)
+        sgd.step()
+        for r in range(W):
+            assert torch.equal(params[r], params[0]) and torch.equal(embs[r], embs[0]), (step, r)
+        assert _rel(params[0], p_ref) <= 2e-6, step
+        assert _rel(embs[0], e_ref) <= 2e-6, step
+    assert int(counter[1]) == 3 * W
+    for r in regions:
+        r.free()
+
+
+def test_fused_step_through_the_exchange_path_world_1():
+    """data_parallel=True with a single rank: K8 (push to self, reduce, apply) must train like K7."""
+    over = dict(vocab_size=700, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32')
+    batches = [synth.make_batch(60 + i, batch_size=50, vocab_size=700, pad_to=64) for i in range(2)]
+
+    def run(dp):
+        torch.manual_seed(6)
+        tr = GCNTrainer(synth.tacred_opt(**over))
+        tr.model.train()
+        eng = FusedTrainStep(tr, data_parallel=dp, max_rows=4096)
+        losses = [float(eng(batches[i % 2])) for i in range(7)]
+        return losses, {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+
+    l0, s0 = run(False)
+    l1, s1 = run(True)
+    assert np.allclose(l0, l1, rtol=1e-5)
+    for k in s0:
+        assert _rel(s1[k], s0[k]) < 1e-5, k
