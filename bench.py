@@ -191,25 +191,31 @@ def aggregation_roofline(args, peaks):
         torch.cuda.synchronize()
         results[name] = sum(a.elapsed_time(b) for a, b in ev) / reps
     gout = torch.randn(B, T, H, device='cuda')
-    for _ in range(2):
-        ops.aggregate_bwd(gout, out, csr, drop_p=0.5)
+    out, act = ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng, want_act=True)
+    for _ in range(2):                       # as the model runs it: [out > 0] from the 1-bit activation mask
+        ops.aggregate_bwd(gout, None, csr, drop_p=0.5, act=act)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
     torch.cuda.synchronize()
     for a, b in ev:
         a.record()
-        ops.aggregate_bwd(gout, out, csr, drop_p=0.5)
+        ops.aggregate_bwd(gout, None, csr, drop_p=0.5, act=act)
         b.record()
     torch.cuda.synchronize()
     results['bwd'] = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
     # algorithmic bytes: read each projected row once + write each output row once + CSR + denom
     bytes_fwd = 2 * B * T * H * 4 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T + B * T
-    bytes_bwd = 3 * B * T * H * 4 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T
+    bytes_bwd = 2 * B * T * H * 4 + B * T * H // 8 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T
     peak = peaks['hbm_gbs']
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+    tpath = os.path.join(REPO, 'profiles', 'r01_k2_fwd_traffic.json')
+    if os.path.exists(tpath) and B == 4096:
+        t = json.load(open(tpath))
+        traffic = t['dram_bytes_read'] + t['dram_bytes_write']
     ach = bytes_fwd / (results['fwd_dropout'] * 1e-3) / 1e9
-    del y, out, gout
+    del y, out, gout, act
     torch.cuda.empty_cache()
     return {'bound': 'hbm', 'kernel': 'aggregate_fwd_kernel (K2, dropout on)', 'achieved': ach, 'peak': peak,
-            'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peaks['source'], 'traffic': None,
+            'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peaks['source'], 'traffic': traffic,
             'workload': 'large512: B=%d x T=512 trees, H=512, prune_k=-1, rows=%d, nnz=%d' % (B, n_rows, nnz),
             'bytes_per_launch': bytes_fwd, 'ms_per_launch': results['fwd_dropout'],
             'frac_of_nominal_8000': ach / 8000.0,
@@ -271,6 +277,11 @@ def run_b200(args):
     else:
         graphed = GraphedTrainStep(trainer, reducer=reducer)
     step = eager_step if args.eager else graphed
+    host_tuples, resident_tuples = host, resident
+    if fused and not args.eager:    # loader batches packed into one contiguous buffer each: one copy per step
+        from gcn_over_pruned_trees_b200.engine import PackedBatch
+        host = [PackedBatch(b, pin=True) for b in host_tuples]
+        resident = [b.to(dev) for b in host]
 
     # warm-up: every batch shape runs eagerly 3x, is captured, and is replayed at least once
     for _ in range(5):
@@ -306,7 +317,7 @@ def run_b200(args):
     value = BATCH * world * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: pinned host batches through the public API, loss read back every step -----------------------------
-    h2d = sum(t.numel() * t.element_size() for t in host[0] if torch.is_tensor(t))
+    h2d = sum(t.numel() * t.element_size() for t in host_tuples[0] if torch.is_tensor(t))
 
     def timed_host_loop(fn, n):
         for i in range(3):
@@ -327,7 +338,13 @@ def run_b200(args):
     e2e = {'value': BATCH * world * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / args.steps * 1e3,
            'api': ('GCNTrainer.update(host batch) + backward + clip + SGD + loss.item()' if args.eager else
-                   'GCNTrainer.train_step(pinned host batch) [one CUDA-graph replay] + loss.item()')}
+                   'train_step(pinned host batch, packed: 1 H2D copy) [one CUDA-graph replay] + loss.item()')}
+    if fused and not args.eager:
+        host = host_tuples
+        t_s = timed_host_loop(step, min(args.steps, 50))
+        e2e['loader_tuple'] = {'value': BATCH * world * min(args.steps, 50) / t_s,
+                               'ms_per_step': t_s / min(args.steps, 50) * 1e3,
+                               'api': 'train_step(pinned 10-tuple as the reference loader emits it: 9 H2D copies)'}
     if world == 1:
         n_eager = min(args.steps, 30)
         eager_s = timed_host_loop(eager_step, n_eager)
@@ -349,9 +366,9 @@ def run_b200(args):
     for i in range(n_prof):
         if fused and not args.eager:        # the same call sequence the graph replays, launched eagerly
             with torch.no_grad():
-                graphed._run(list(resident[i % N_BATCHES][:-2]), resident[i % N_BATCHES][-2])
+                graphed._run(list(resident_tuples[i % N_BATCHES][:-2]), resident_tuples[i % N_BATCHES][-2])
         else:
-            eager_step(resident[i % N_BATCHES])
+            eager_step(resident_tuples[i % N_BATCHES])
     pb.record()
     if ops.TIMER is not None:
         summary = ops.TIMER.summary()

@@ -149,6 +149,53 @@ class GraphedTrainStep(object):
         return self.kernels_per_replay.get(key, 0)
 
 
+class PackedBatch(object):
+    """A loader batch (data/loader.py:140-141 10-tuple, semeval_loader.py:119 9-tuple) laid out in ONE contiguous
+    buffer -- int64 fields, labels, then the bool pad mask -- so that a step needs a single copy (H2D from pinned
+    memory, or D2D) instead of nine.  ``fields`` / ``labels`` are views with the loader's shapes and dtypes."""
+
+    def __init__(self, batch=None, device='cpu', pin=False, like=None):
+        if like is not None:
+            B, T, n_fields = like.key
+            dtypes = like.dtypes
+        else:
+            fields = list(batch[:-2])
+            B, T = fields[0].shape
+            n_fields = len(fields)
+            dtypes = [f.dtype for f in fields]
+        self.key = (B, T, n_fields)
+        self.dtypes = dtypes
+        sizes = [B * T * torch.empty((), dtype=d).element_size() for d in dtypes]
+        order = sorted(range(n_fields), key=lambda i: -torch.empty((), dtype=dtypes[i]).element_size())
+        offs, o = {}, 0
+        for i in order:                         # widest element types first: every view stays naturally aligned
+            offs[i] = o
+            o += (sizes[i] + 15) // 16 * 16
+        off_lab = o
+        o += (B * 8 + 15) // 16 * 16
+        if device == 'cpu':
+            self.buf = torch.empty(o, dtype=torch.uint8, pin_memory=pin)
+        else:
+            self.buf = torch.empty(o, dtype=torch.uint8, device=device)
+        self.fields = [self.buf[offs[i]:offs[i] + sizes[i]].view(dtypes[i]).view(B, T) for i in range(n_fields)]
+        self.labels = self.buf[off_lab:off_lab + B * 8].view(torch.int64)
+        self.orig_idx = None
+        if batch is not None:
+            for v, f in zip(self.fields, batch[:-2]):
+                v.copy_(f)
+            self.labels.copy_(batch[-2])
+            self.orig_idx = batch[-1]
+
+    def to(self, device):
+        out = PackedBatch(like=self, device=device)
+        out.buf.copy_(self.buf)
+        out.orig_idx = self.orig_idx
+        return out
+
+    def as_tuple(self):
+        return tuple(self.fields) + (self.labels, self.orig_idx)
+
+
 class FlatParameters(object):
     """Every dense trainable parameter re-homed as a view into ONE fp32 buffer, with a parallel gradient buffer.
 
@@ -367,7 +414,8 @@ class FusedTrainStep(object):
 
     def _capture(self, key, inputs, labels):
         from . import _lib
-        entry = {'inputs': [t.clone() for t in inputs], 'labels': labels.clone()}
+        static = PackedBatch(batch=tuple(inputs) + (labels, None), device=inputs[0].device)
+        entry = {'packed': static, 'inputs': static.fields, 'labels': static.labels}
         torch.cuda.synchronize()
         n0 = _lib.lib().gpt_launch_count()
         g = torch.cuda.CUDAGraph()
@@ -384,6 +432,9 @@ class FusedTrainStep(object):
         if lr != self._lr:              # the learning rate is baked into the captured update: re-capture
             self._graphs.clear()
             self._lr = lr
+        packed = batch if isinstance(batch, PackedBatch) else None
+        if packed is not None:
+            batch = packed.as_tuple()
         fields, labels = batch[:-2], batch[-2]
         key = (tuple(fields[0].shape), len(fields))
         entry = self._graphs.get(key)
@@ -394,6 +445,8 @@ class FusedTrainStep(object):
             if seen < self.warmup:      # first steps of a new shape run eagerly (lazy module loading, smem attributes)
                 return self._run(inputs, labels)[0]
             entry = self._capture(key, inputs, labels)
+        elif packed is not None:        # one copy: pinned host -> device, or device -> device
+            entry['packed'].buf.copy_(packed.buf, non_blocking=True)
         else:
             for s, t in zip(entry['inputs'], fields):
                 s.copy_(t, non_blocking=True)
@@ -417,5 +470,7 @@ class FusedTrainStep(object):
         return loss.clone(), logits.clone(), out
 
     def launches_per_replay(self, batch):
+        if isinstance(batch, PackedBatch):
+            batch = batch.as_tuple()
         key = (tuple(batch[0].shape), len(batch) - 2)
         return self.kernels_per_replay.get(key, 0)
