@@ -23,6 +23,9 @@ SIGNATURES = {
     'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
                               _c_int, _p],
     'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
+    'gpt_gcn_aggregate_bwd_pre': [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _p],
+    'gpt_pool3_bwd_masked': [_p, _p, _p, _p, _p, _c_f, _c_int, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_linear_dgrad_tf32x3_masked': [_p, _p, _p, _p, _p, _c_f, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_pool3_fwd': [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p],
     'gpt_pool3_bwd': [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p],
     'gpt_linear_fwd_f32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],

@@ -47,7 +47,9 @@ struct AggParams {
     const float* drop_mask;              // optional explicit, pre-scaled mask [B*T, H]
     const unsigned long long* rng;       // optional {seed, step} on the device
     int B, T, H, cap, use_adj, nbuf;
+    int pre_scaled;      // bwd: the input already is g = gout * dropscale * [out > 0] / denom (fused into its producer)
     unsigned subseq, thresh16;           // dropout: keep iff rand16 >= thresh16
+    int drop_bits;                       // random bits spent per element: 16, or 1 when p == 0.5 exactly
     float drop_scale;
 };
 
@@ -290,6 +292,20 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
             // Dropout keep-words of this slice (one bit per element), drawn while the slice is still in flight.
             // One Philox call = 8 rows x 1 column x 16 bits; the stream depends only on
             // (seed, step, layer, sentence, row, column), never on the tiling.
+            if (p.drop_bits == 1) {
+                // p = 0.5 (the reference's gcn_dropout default): one random BIT per element.  One Philox call per
+                // thread = the keep-words of 4 rows x one 32-column block -- no ballots, 1/64 of the calls.
+                for (int idx = threadIdx.x; idx < ((T + 3) >> 2) * WPR; idx += NT) {
+                    const int rq = idx / WPR, w = idx - rq * WPR;
+                    const Philox4 q = philox4x32((uint32_t)(col0 / 32 + w) | (p.subseq << 20), (uint32_t)rq,
+                                                 (uint32_t)b ^ 0x31415926u, (uint32_t)step, (uint32_t)seed,
+                                                 (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+                    const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (rq * 4 + r < T) keepw[(rq * 4 + r) * WPR + w] = r4[r];
+                }
+            } else {
             for (int blk = warp; blk * 8 < T; blk += NT / 32) {
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) {
@@ -307,6 +323,7 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
                     }
                     if (lane < 8 && blk * 8 + lane < T) keepw[(blk * 8 + lane) * WPR + w] = mine;
                 }
+            }
             }
         }
         if (nxt < nsl) cp_async_wait<1>();
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
     const int T = p.T, H = p.H;
     const int b = blockIdx.y;
     const int nsl = (H + HS - 1) / HS;
-    const bool use_act = (p.act_in != nullptr) && (LPR == 8);
+    const bool use_act = (p.act_in != nullptr) && (LPR == 8) && !p.pre_scaled;
     const Layout L = make_layout(T, H, LPR, NT, p.nbuf, false, use_act);
     float* tile0 = reinterpret_cast<float*>(smem_raw + L.tile);
     float* red = reinterpret_cast<float*>(smem_raw + L.red);  // [GROUPS][HS]
@@ -436,6 +453,7 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
         const int col0 = sl * HS;
         const uint32_t tile_s = tile_s0 + (uint32_t)(it & 1) * tile_bytes;
         const uint32_t actw_s = actw_s0 + (uint32_t)((it & 1) * actw_stride) * 4u;
+        if (!p.pre_scaled) {
 #pragma unroll 2
         for (int q = tid; q < T * LPR; q += NT) {
             const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
@@ -469,6 +487,7 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
             sts128(a, g);
         }
         __syncthreads();
+        }
 
         // ---- dy_j = g_j + sum_{i in row j} g_i ; column sums for dbias -------------------------------------------
         const int c_lane = col0 + cl;
@@ -520,7 +539,7 @@ struct AggConfig {
 // Large tiles (< 4 CTAs would fit an SM): 512-thread persistent CTA, narrowest slice, double buffered.
 AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
     const int T = p.T, H = p.H, B = p.B;
-    const bool act = fwd ? (p.act_out != nullptr) : (p.act_in != nullptr);  // bit layout is tied to LPR = 8
+    const bool act = fwd ? (p.act_out != nullptr) : (p.act_in != nullptr && !p.pre_scaled);  // bit layout: LPR = 8
     const bool philox = fwd && p.rng != nullptr && p.thresh16 > 0 && p.drop_mask == nullptr;
     AggConfig c{};
     auto slices = [&](int lpr) { return (H + 4 * lpr - 1) / (4 * lpr); };
@@ -598,6 +617,7 @@ void set_dropout(AggParams& p, float drop_p) {
     unsigned th = (unsigned)(drop_p * 65536.0f + 0.5f);
     p.thresh16 = th > 65535u ? 65535u : th;
     p.drop_scale = (p.thresh16 > 0) ? 65536.0f / (65536.0f - (float)p.thresh16) : 1.0f;
+    p.drop_bits = (p.thresh16 == 32768u) ? 1 : 16;
 }
 
 }  // namespace
@@ -637,5 +657,20 @@ extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const 
     p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
     // same scale the forward applied to kept elements (dropped ones have out == 0 / a clear activation bit)
     set_dropout(p, drop_mask == nullptr ? drop_p : 0.f);
+    return dispatch(false, p, force_vec, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_gcn_aggregate_bwd_pre(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom,
+                                         float* dy, float* dbias, int B, int T, int H, int use_adj, int force_vec,
+                                         void* stream) {
+    GPT_CHECK_ARG(g && rowptr && col && denom && dy);
+    GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1);
+    if (B == 0) return GPT_OK;
+    if (B > 65535) return GPT_ERR_UNSUPPORTED;
+    AggParams p{};
+    p.y = g; p.rowptr = rowptr; p.col = col; p.denom = denom; p.out = dy; p.dbias = dbias;
+    p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
+    p.pre_scaled = 1;
+    set_dropout(p, 0.f);
     return dispatch(false, p, force_vec, (cudaStream_t)stream);
 }

@@ -36,6 +36,16 @@ constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
 constexpr int kMaxStages = 8;   // ring depth is chosen at launch: as many stages as fit in shared memory
 constexpr int kGemmThreads = 192;
 
+// Optional epilogue of the data-gradient GEMM: the consumer of dX is K2's backward of the previous layer, whose first
+// step is g = dX * dropscale * [out > 0] / denom.  Doing it here, where every thread already holds 32 consecutive
+// columns of one row, removes a whole shared-memory pass (and a barrier per slice) from the HBM-bound K2 backward.
+struct MaskEpilogue {
+    const uint32_t* act;     // activation bits of the previous layer's forward, [B, ceil(N/32), T] (K2 layout); or null
+    const float* denom;      // [B*T]
+    float scale;             // dropout scale of the previous layer's forward
+    int T;
+};
+
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -99,7 +109,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
-                 int tmem_cols, int STAGES) {
+                 int tmem_cols, int STAGES, const MaskEpilogue ep) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_holder;
@@ -208,6 +218,13 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int row = m0 + q * 32 + lane;
         float* crow = C + (size_t)row * N + n0;
         const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        float ep_inv = 0.f;
+        const uint32_t* ep_words = nullptr;                 // act word of (sentence, 32-column block 0, token)
+        if (ep.act != nullptr && row < M) {
+            const int bb = row / ep.T, tt = row - bb * ep.T;
+            ep_inv = __frcp_rn(ep.denom[row]);
+            ep_words = ep.act + ((size_t)bb * ((N + 31) / 32)) * ep.T + tt;
+        }
         for (int c0 = 0; c0 < n_tile; c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -223,6 +240,17 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ep_words != nullptr) {                      // g = (dx * (bit * scale)) * (1 / denom), as K2 forms it
+                const int cg = n0 + c0, wi = cg >> 5, sh = cg & 31, nw = (N + 31) / 32;
+                unsigned long long bits = wi < nw ? (unsigned long long)ep_words[(size_t)wi * ep.T] : 0ull;
+                if (sh != 0 && wi + 1 < nw) bits |= (unsigned long long)ep_words[(size_t)(wi + 1) * ep.T] << 32;
+                const uint32_t m = (uint32_t)(bits >> sh);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float f = (float)((m >> j) & 1u) * ep.scale;
+                    v[j] = __float_as_uint(__uint_as_float(v[j]) * f * ep_inv);
+                }
+            }
             if (row < M) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -302,7 +330,7 @@ __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restric
 
 template <int PASSES>
 int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
-                int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st) {
+                int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st, const MaskEpilogue& ep) {
     const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * 4);
     int stages = (int)((200 * 1024) / stage);
     const int nkb = (K + BK - 1) / BK;
@@ -319,12 +347,13 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
     }
     dim3 grid((M + BM - 1) / BM, n_tiles);
     tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, tmem_cols,
-                                                               stages);
+                                                               stages, ep);
     return gpt_launch_status();
 }
 
 // C[M,N] = A[M,K] . B[N,K]^T ; b_lo != nullptr selects the 3xTF32 mode (B = rounded hi part, b_lo = lo part)
-int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, int M, int N, int K, cudaStream_t st) {
+int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, int M, int N, int K, cudaStream_t st,
+                  const MaskEpilogue ep = MaskEpilogue{nullptr, nullptr, 1.f, 1}) {
     if (M == 0) return GPT_OK;
     // TMA: 16-byte aligned bases and row pitches
     if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
@@ -345,8 +374,8 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
     if (rc != GPT_OK) return rc;
     if ((rc = make_map(&tm_b, B, N, K, n_tile)) != GPT_OK) return rc;
     if ((rc = make_map(&tm_b_lo, b_lo ? b_lo : B, N, K, n_tile)) != GPT_OK) return rc;
-    if (b_lo != nullptr) return launch_gemm<3>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st);
-    return launch_gemm<1>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st);
+    if (b_lo != nullptr) return launch_gemm<3>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep);
+    return launch_gemm<1>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep);
 }
 
 // w [N,K] -> ws = [w_hi | w_lo | wt_hi | wt_lo]  (wt = w^T [K,N]); hi = round_tf32, lo = w - hi
@@ -417,4 +446,13 @@ extern "C" int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* 
     GPT_CHECK_ARG(dy && ws && dx && M >= 0 && N >= 1 && K >= 1);
     const size_t nk = (size_t)N * K;
     return run_tf32_gemm(dy, ws + 2 * nk, ws + 3 * nk, dx, M, K, N, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, const uint32_t* act_prev,
+                                              const float* denom, float drop_scale_prev, int T, int M, int N, int K,
+                                              void* stream) {
+    GPT_CHECK_ARG(dy && ws && g && act_prev && denom && T >= 1 && M >= 0 && M % T == 0 && N >= 1 && K >= 1);
+    const size_t nk = (size_t)N * K;
+    return run_tf32_gemm(dy, ws + 2 * nk, ws + 3 * nk, g, M, K, N, (cudaStream_t)stream,
+                         MaskEpilogue{act_prev, denom, drop_scale_prev, T});
 }

@@ -120,7 +120,8 @@ size_t pool_fwd_smem(int T, int H, int V) {
 
 __global__ void __launch_bounds__(kPoolThreads)
 pool3_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
-                 const unsigned char* __restrict__ flags, int T, int H, int type, float* __restrict__ dh) {
+                 const unsigned char* __restrict__ flags, int T, int H, int type, float* __restrict__ dh,
+                 const uint32_t* __restrict__ act, const float* __restrict__ denom, float scale) {
     extern __shared__ unsigned char s_flags[];
     const int b = blockIdx.y;
     int cnt[3] = {0, 0, 0};
@@ -158,6 +159,10 @@ pool3_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
             for (int k = 0; k < 3; ++k)
                 if (f & (1u << k)) v += g[k];
         }
+        if (act != nullptr) {   // fused first step of K2's backward: g = dh * dropscale * [out > 0] / denom
+            const uint32_t w = act[((size_t)b * ((H + 31) / 32) + (c >> 5)) * T + t];
+            v = v * ((float)((w >> (c & 31)) & 1u) * scale) * __frcp_rn(denom[(size_t)b * T + t]);
+        }
         db[(size_t)t * H] = v;
     }
 }
@@ -194,6 +199,21 @@ extern "C" int gpt_pool3_bwd(const float* gout, const int32_t* argmax, const uin
     if (B == 0) return GPT_OK;
     if (B > 65535 || T > 48 * 1024) return GPT_ERR_UNSUPPORTED;
     dim3 grid((H + kPoolThreads - 1) / kPoolThreads, B);
-    pool3_bwd_kernel<<<grid, kPoolThreads, T, (cudaStream_t)stream>>>(gout, argmax, flags, T, H, pool_type, dh);
+    pool3_bwd_kernel<<<grid, kPoolThreads, T, (cudaStream_t)stream>>>(gout, argmax, flags, T, H, pool_type, dh, nullptr,
+                                                                      nullptr, 1.f);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_pool3_bwd_masked(const float* gout, const int32_t* argmax, const uint8_t* flags,
+                                    const uint32_t* act, const float* denom, float drop_scale, int B, int T, int H,
+                                    int pool_type, float* g, void* stream) {
+    GPT_CHECK_ARG(gout && flags && g && act && denom);
+    GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && pool_type >= 0 && pool_type <= 2);
+    GPT_CHECK_ARG(pool_type != POOL_MAX || argmax != nullptr);
+    if (B == 0) return GPT_OK;
+    if (B > 65535 || T > 48 * 1024) return GPT_ERR_UNSUPPORTED;
+    dim3 grid((H + kPoolThreads - 1) / kPoolThreads, B);
+    pool3_bwd_kernel<<<grid, kPoolThreads, T, (cudaStream_t)stream>>>(gout, argmax, flags, T, H, pool_type, g, act,
+                                                                      denom, drop_scale);
     return gpt_launch_status();
 }

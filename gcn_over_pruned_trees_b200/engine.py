@@ -373,18 +373,31 @@ class FusedTrainStep(object):
         with torch.cuda.stream(sa):
             ops.head_wgrad(pooled, buf, [fl.g(m.weight) for m in self.mlp], [fl.g(m.bias) for m in self.mlp],
                            fl.g(self.cls.weight), fl.g(self.cls.bias))
-        dh = ops.pool3_bwd(buf.dpooled, argmax, csr, ptype, H)
+        # K2's backward prologue (g = d * dropscale * [out > 0] / denom) is fused into whatever produces d: K4's backward
+        # for the last layer, the dgrad GEMM's epilogue below it; ('dh', .) marks a gradient that still needs it
+        cur = ('g', ops.pool3_bwd_masked(buf.dpooled, argmax, csr, ptype, H, acts[-1], 0.0))
         for l in range(n_layers - 1, -1, -1):
             lin = gcn.W[l]
-            dy, _ = ops.aggregate_bwd(dh, None, csr, use_adj, 0.0 if l == n_layers - 1 else p_gcn, None,
-                                      act=acts[l], dbias_out=fl.g(lin.bias))
+            if cur[0] == 'g':
+                dy = ops.aggregate_bwd_pre(cur[1], csr, use_adj, dbias_out=fl.g(lin.bias))
+            else:
+                dy, _ = ops.aggregate_bwd(cur[1], None, csr, use_adj, 0.0 if l == n_layers - 1 else p_gcn, None,
+                                          act=acts[l], dbias_out=fl.g(lin.bias))
             keep.append(dy)
             side = sb if (n_layers - 1 - l) % 2 == 0 else sa
             fork(side)
             with torch.cuda.stream(side):
                 ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True,
                                  flags=csr.flags)
-            dh = ops.linear_dgrad(dy, lin.weight.data, mode, wss[l]).view(B, T, -1)
+            g = None
+            if l > 0 and mode == 'tf32x3':
+                g = ops.linear_dgrad_masked(dy, lin.weight.data, wss[l], acts[l - 1], csr, p_gcn)
+            if g is not None:
+                cur = ('g', g.view(B, T, -1))
+            else:
+                dh = ops.linear_dgrad(dy, lin.weight.data, mode, wss[l]).view(B, T, -1)
+                cur = ('dh', dh)
+        dh = cur[1]
         sp = self.sparse
         if sp is not None:
             sp.words = words

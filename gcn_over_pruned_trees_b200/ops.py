@@ -525,3 +525,41 @@ def dp_apply(region_ptr, shape, flat_param, flat_grad, emb_weight, partials, max
              step_counter=None):
     _call('gpt_dp_apply', region_ptr, *shape, _ptr(flat_param), _ptr(flat_grad), _ptr(emb_weight), _ptr(partials),
           float(max_norm), float(lr), _ptr(total_norm), _ptr(step_counter), _stream())
+
+
+# ---- backward chain with K2's prologue fused into its producers -------------------------------------------------
+
+def drop_scale(p):
+    """The scale K2 applies to kept elements: keep-probability is quantised to 16 bits."""
+    th = min(int(p * 65536.0 + 0.5), 65535)
+    return 65536.0 / (65536.0 - th) if th > 0 else 1.0
+
+
+def pool3_bwd_masked(gout, argmax, csr, pool_type, H, act, p_drop):
+    """K4 backward writing g = dh * dropscale * [out > 0] / denom (input of aggregate_bwd_pre)."""
+    B, T = csr.B, csr.T
+    g = torch.empty((B, T, H), dtype=torch.float32, device=gout.device)
+    _call('gpt_pool3_bwd_masked', _ptr(gout), _ptr(argmax), _ptr(csr.flags), _ptr(act), _ptr(csr.denom),
+          float(drop_scale(p_drop)), B, T, H, pool_type, _ptr(g), _stream())
+    return g
+
+
+def linear_dgrad_masked(dy, weight, ws, act_prev, csr, p_drop_prev):
+    """K3 dgrad (3xTF32) writing g of the previous layer instead of dx; None when the shape is not TMA-describable."""
+    M, N = dy.shape
+    K = weight.shape[1]
+    if ws is None or not _tf32_ok(N, K):
+        return None
+    g = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    _call('gpt_linear_dgrad_tf32x3_masked', _ptr(dy), _ptr(ws), _ptr(g), _ptr(act_prev), _ptr(csr.denom),
+          float(drop_scale(p_drop_prev)), csr.T, M, N, K, _stream())
+    return g
+
+
+def aggregate_bwd_pre(g, csr, use_adj=True, dbias_out=None, force_vec=0):
+    B, T = csr.B, csr.T
+    H = g.shape[-1]
+    dy = torch.empty((B * T, H), dtype=torch.float32, device=g.device)
+    _call('gpt_gcn_aggregate_bwd_pre', _ptr(g), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom), _ptr(dy),
+          _ptr(dbias_out), B, T, H, int(bool(use_adj)), int(force_vec), _stream())
+    return dy

@@ -91,12 +91,24 @@ int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* a
                           const int32_t* col, const float* denom, float* dy, float* dbias, int B, int T, int H,
                           int use_adj, float drop_p, const float* drop_mask, int force_vec, void* stream);
 
+/* K2 backward when the first step (g = gout * dropscale * [out > 0] / denom) was fused into the kernel that produced
+ * the gradient (gpt_linear_dgrad_tf32x3_masked, gpt_pool3_bwd_masked): dy_j = g_j + sum_{i in row j} g_i,
+ * dbias += 2 * sum_i g_i.  One shared-memory pass and one barrier per slice less than gpt_gcn_aggregate_bwd. */
+int gpt_gcn_aggregate_bwd_pre(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
+                              float* dbias, int B, int T, int H, int use_adj, int force_vec, void* stream);
+
 /* K4. three masked pools + cat (model/gcn.py:116-121, 473-483): out float [B,3H] = [h_out, subj_out, obj_out];
  * argmax int32 [B,3H] (token index or -1) is required for GPT_POOL_MAX. */
 int gpt_pool3_fwd(const float* h, const uint8_t* flags, int B, int T, int H, int pool_type, float* out,
                   int32_t* argmax, void* stream);
 int gpt_pool3_bwd(const float* gout, const int32_t* argmax, const uint8_t* flags, int B, int T, int H,
                   int pool_type, float* dh, void* stream);
+
+/* K4 backward fused with the first step of the last layer's K2 backward (act / denom / drop_scale as in
+ * gpt_gcn_aggregate_bwd): writes g instead of dh */
+int gpt_pool3_bwd_masked(const float* gout, const int32_t* argmax, const uint8_t* flags, const uint32_t* act,
+                         const float* denom, float drop_scale, int B, int T, int H, int pool_type, float* g,
+                         void* stream);
 
 /* K3. the W projection without bias (model/gcn.py:270-271: W(Ax) + W(h) == (A+I) (h W^T) + 2b) and its autograd.
  *     x [M,K], w [N,K] (nn.Linear layout), y/dy [M,N], dx [M,K], dw [N,K]; all row-major fp32. */
@@ -122,6 +134,10 @@ int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_
 int gpt_weight_prep_tf32x3(const float* w, float* ws, int N, int K, void* stream);
 int gpt_linear_fwd_tf32x3(const float* x, const float* ws, float* y, int M, int N, int K, void* stream);
 int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* dx, int M, int N, int K, void* stream);
+/* dgrad with the previous layer's K2-backward prologue in the epilogue: g = (dy . w) * drop_scale_prev *
+ * [out_prev > 0] / denom, act_prev in K2's bit layout over the K columns of dx, rows = B*T sentences of T tokens */
+int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, const uint32_t* act_prev,
+                                   const float* denom, float drop_scale_prev, int T, int M, int N, int K, void* stream);
 
 /* K5. input stage of GCN.forward (model/gcn.py:235-247): x[r] = dropout(cat[emb_w[words[r]], pos_w[pos[r]],
  *     ner_w[ner[r]]]) for the n_rows = B*T token slots; x is [n_rows, E+Dp+Dn].  pos/pos_w and ner/ner_w are NULL when

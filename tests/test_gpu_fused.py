@@ -360,3 +360,42 @@ def test_fused_step_through_the_exchange_path_world_1():
     assert np.allclose(l0, l1, rtol=1e-5)
     for k in s0:
         assert _rel(s1[k], s0[k]) < 1e-5, k
+
+
+# ---------------------------------------------------------------- fused K2-backward prologue --------------------------
+
+@pytest.mark.parametrize('T,H,k', [(64, 200, 1), (96, 64, -1), (512, 512, -1), (40, 100, 2)])
+def test_k2_backward_prologue_fused_into_its_producers(T, H, k):
+    """pool3_bwd_masked / linear_dgrad_masked + aggregate_bwd_pre == pool3_bwd / linear_dgrad + aggregate_bwd."""
+    B = 6 if T == 512 else 40
+    batch = synth.make_batch(91, batch_size=B, vocab_size=500, pad_to=T, max_len=T, mean_len=T // 2)
+    dev = [t.to(DEV) if torch.is_tensor(t) else t for t in batch]
+    csr = ops.prune_csr(dev[5], dev[6], dev[7], dev[4], dev[1], k)
+    y = torch.randn(B * T, H, device=DEV)
+    bias = torch.randn(H, device=DEV) * 0.1
+    rng = torch.tensor([77, 3], dtype=torch.int64, device=DEV)
+    for p in (0.0, 0.5, 0.3):
+        out, act = ops.aggregate_fwd(y, csr, bias, drop_p=p, rng_state=rng, subseq=1, want_act=True)
+        # producer 1: K4 backward
+        pooled, argmax = ops.pool3_fwd(out, csr, 0)
+        gp = torch.randn(B, 3 * H, device=DEV)
+        dh = ops.pool3_bwd(gp, argmax, csr, 0, H)
+        dy_ref, db_ref = ops.aggregate_bwd(dh, None, csr, drop_p=p, act=act)
+        g = ops.pool3_bwd_masked(gp, argmax, csr, 0, H, act, p)
+        db = torch.zeros(H, device=DEV)
+        dy = ops.aggregate_bwd_pre(g, csr, dbias_out=db)
+        assert torch.equal(dy, dy_ref)
+        assert _rel(db, db_ref) <= 1e-5
+        # producer 2: the dgrad GEMM epilogue (3xTF32), N_next -> H
+        N2 = 200 if H != 512 else 512
+        w = torch.randn(N2, H, device=DEV) / np.sqrt(H)
+        ws = ops.weight_prep(w, 'tf32x3')
+        dnext = torch.randn(B * T, N2, device=DEV)
+        dx = ops.linear_dgrad(dnext, w, 'tf32x3', ws).view(B, T, H)
+        dy_ref, db_ref = ops.aggregate_bwd(dx, None, csr, drop_p=p, act=act)
+        g = ops.linear_dgrad_masked(dnext, w, ws, act, csr, p)
+        assert g is not None
+        db = torch.zeros(H, device=DEV)
+        dy = ops.aggregate_bwd_pre(g.view(B, T, H), csr, dbias_out=db)
+        assert torch.equal(dy, dy_ref)
+        assert _rel(db, db_ref) <= 1e-5
