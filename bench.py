@@ -202,6 +202,18 @@ def aggregation_roofline(args, peaks):
         b.record()
     torch.cuda.synchronize()
     results['bwd'] = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    db = torch.zeros(H, device='cuda')      # as FusedTrainStep runs it: prologue fused into the producer of gout
+    for _ in range(2):
+        ops.aggregate_bwd_pre(gout, csr, dbias_out=db)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record()
+        ops.aggregate_bwd_pre(gout, csr, dbias_out=db)
+        b.record()
+    torch.cuda.synchronize()
+    results['bwd_pre'] = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    bytes_bwd_pre = 2 * B * T * H * 4 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T
     # algorithmic bytes: read each projected row once + write each output row once + CSR + denom
     bytes_fwd = 2 * B * T * H * 4 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T + B * T
     bytes_bwd = 2 * B * T * H * 4 + B * T * H // 8 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T
@@ -222,7 +234,10 @@ def aggregation_roofline(args, peaks):
             'other': {'fwd_no_dropout_ms': results['fwd'],
                       'fwd_no_dropout_gbs': bytes_fwd / (results['fwd'] * 1e-3) / 1e9,
                       'bwd_ms': results['bwd'], 'bwd_gbs': bytes_bwd / (results['bwd'] * 1e-3) / 1e9,
-                      'bwd_bytes_per_launch': bytes_bwd}}
+                      'bwd_bytes_per_launch': bytes_bwd,
+                      'bwd_pre_scaled_ms': results['bwd_pre'],
+                      'bwd_pre_scaled_gbs': bytes_bwd_pre / (results['bwd_pre'] * 1e-3) / 1e9,
+                      'bwd_pre_scaled_frac': bytes_bwd_pre / (results['bwd_pre'] * 1e-3) / 1e9 / peak}}
 
 
 def load_peaks():

@@ -19,6 +19,7 @@ _c_ll = ctypes.c_longlong
 SIGNATURES = {
     'gpt_version': [],
     'gpt_launch_count': [],
+    'gpt_l2_prefetch': [_p, _c_ll, _p],
     'gpt_prune_csr': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
                               _c_int, _p],

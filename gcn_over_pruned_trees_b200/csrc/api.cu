@@ -18,3 +18,21 @@ extern "C" const char* gpt_error_string(int code) {
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "gpt_b200: unknown error";
 }
+
+// Pull a buffer into L2 ahead of its first use (one prefetch per 128-byte line, no data returned to the SM).
+// engine.FusedTrainStep issues this for the flat parameter buffer on a side stream at the start of a step, so the
+// classifier head and the projections do not pay DRAM latency on their first touch of the weights.
+__global__ void l2_prefetch_kernel(const unsigned char* __restrict__ p, size_t lines) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+}
+
+extern "C" int gpt_l2_prefetch(const void* ptr, long long bytes, void* stream) {
+    GPT_CHECK_ARG(ptr != nullptr && bytes >= 0);
+    if (bytes == 0) return GPT_OK;
+    const size_t lines = ((size_t)bytes + 127) / 128;
+    size_t blocks = (lines + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    l2_prefetch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(ptr), lines);
+    return gpt_launch_status();
+}

@@ -14,6 +14,10 @@
 //       summing over the whole batch (no atomics: deterministic), plus one CTA that adds the per-sentence losses in
 //       a fixed order.
 #include "gpt_common.cuh"
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -28,7 +32,7 @@ struct HeadParams {
     const float* b[kMaxMlp];    // [H]
     const float* wc;            // [C, H]
     const float* bc;            // [C]
-    int B, H, C, n_mlp, train;
+    int B, H, C, n_mlp, train, prefetch;
     float pooling_l2, inv_B;
     float* logits;              // [B, C]
     float* loss_rows;           // [B]  CE_b / B + pooling_l2 * |h_out_b|^2 / B
@@ -38,13 +42,25 @@ struct HeadParams {
     float* dpooled;             // [B, 3H]                                       (train)
 };
 
-// s_out[r][n] = act(sum_k s_in[r][k] * W[n][k] + bias[n]);  K % 4 == 0; one warp per 4 output rows of W
+// volatile: ptxas keeps these in program order, i.e. all loads of a batch are issued before the first consumer
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// s_out[r][n] = act(sum_k s_in[r][k] * W[n][k] + bias[n]);  K % 4 == 0; one warp per 4 output rows of W.
+// The CTAs of a cluster share one sentence group: they take the 4-row groups round-robin (each streams 1/CS of W) and
+// store every result into the shared memory of ALL ranks (DSMEM), so after the cluster barrier each holds the layer.
 template <int R, bool RELU>
-__device__ __forceinline__ void dense_fwd(const float* __restrict__ W, const float* __restrict__ bias,
-                                          const float* s_in, int ld_in, float* s_out, int ld_out, int N, int K) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+__device__ __forceinline__ void dense_fwd(cg::cluster_group& cluster, const float* __restrict__ W,
+                                          const float* __restrict__ bias, const float* s_in, int ld_in, float* s_out,
+                                          int ld_out, int N, int K) {
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int gwarp = (int)(threadIdx.x >> 5) * cs + crank;          // interleave ranks: balanced for any N
     const int K4 = K >> 2;
-    for (int n0 = warp * 4; n0 < N; n0 += nw * 4) {
+    for (int n0 = gwarp * 4; n0 < N; n0 += nw * cs * 4) {
         float acc[4][R];
         const float4* wr[4];
 #pragma unroll
@@ -53,23 +69,28 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ W, const flo
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
         }
-        for (int k4 = lane; k4 < K4; k4 += 64) {               // 8 independent 128-bit loads in flight per lane
-            const bool two = k4 + 32 < K4;
-            float4 wv[4], wu[4];
+        // U x 4 independent 128-bit loads are issued before the first use (addresses clamped, tails zeroed through
+        // the activation operand): the loop is bound by round trips to L2, so loads in flight are what matters
+        constexpr int U = 3;
+        for (int k4 = lane; k4 < K4; k4 += 32 * U) {
+            float4 wv[U][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                wv[j] = __ldg(wr[j] + k4);
-                wu[j] = two ? __ldg(wr[j] + k4 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < U; ++u) {
+                const int kk = min(k4 + 32 * u, K4 - 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wv[u][j] = ld_nc_f4(wr[j] + kk);
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 x = reinterpret_cast<const float4*>(s_in + r * ld_in)[k4];
-                const float4 z = two ? reinterpret_cast<const float4*>(s_in + r * ld_in)[k4 + 32]
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < U; ++u) {
+                const bool in = k4 + 32 * u < K4;
+                const int kk = min(k4 + 32 * u, K4 - 1);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    acc[j][r] += wv[j].x * x.x + wv[j].y * x.y + wv[j].z * x.z + wv[j].w * x.w;
-                    acc[j][r] += wu[j].x * z.x + wu[j].y * z.y + wu[j].z * z.z + wu[j].w * z.w;
+                for (int r = 0; r < R; ++r) {
+                    float4 x = reinterpret_cast<const float4*>(s_in + r * ld_in)[kk];
+                    if (!in) x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        acc[j][r] += wv[u][j].x * x.x + wv[u][j].y * x.y + wv[u][j].z * x.z + wv[u][j].w * x.w;
                 }
             }
         }
@@ -79,8 +100,9 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ W, const flo
             for (int r = 0; r < R; ++r) {
                 const float v = warp_sum_f(acc[j][r]);
                 if (lane == j * R + r && n0 + j < N) {
-                    const float o = v + bias[n0 + j];
-                    s_out[r * ld_out + n0 + j] = RELU ? fmaxf(o, 0.f) : o;
+                    float o = v + bias[n0 + j];
+                    o = RELU ? fmaxf(o, 0.f) : o;
+                    for (int q = 0; q < cs; ++q) cluster.map_shared_rank(s_out, q)[r * ld_out + n0 + j] = o;
                 }
             }
         }
@@ -90,14 +112,22 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ W, const flo
 // s_din[r][k] = sum_n s_dout[r][n] * W[n][k]; a thread owns 4 consecutive k (one 128-bit column of W) and a residue
 // class of n; the G classes are added through s_part.  Rows of W whose dout is zero for every sentence of the CTA
 // (ReLU-dead units: about half) are skipped.
+// In a cluster every rank owns a contiguous range of the 128-bit columns (1/CS of W) and, unless `broadcast` is off
+// (last layer: the result goes straight to global memory), stores its part of s_din into every rank.
 template <int R>
-__device__ __forceinline__ void dense_dgrad(const float* __restrict__ W, const float* s_dout, int ld_dout,
-                                            float* s_part, float* s_din, int ld_din, int N, int K) {
+__device__ __forceinline__ void dense_dgrad(cg::cluster_group& cluster, const float* __restrict__ W,
+                                            const float* s_dout, int ld_dout, float* s_part, float* s_din,
+                                            int ld_din, int N, int K, bool broadcast, int* k_lo_out, int* k_hi_out) {
     const int K4 = K >> 2;
-    const int G = K4 <= (int)blockDim.x ? min((int)blockDim.x / K4, kDgradPartCols / K) : 1;
+    const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int k4_lo = (int)(((long long)K4 * crank) / cs), k4_hi = (int)(((long long)K4 * (crank + 1)) / cs);
+    const int K4c = k4_hi - k4_lo;                          // this rank's columns
+    *k_lo_out = k4_lo * 4;
+    *k_hi_out = k4_hi * 4;
+    const int G = (K4c > 0 && K4c <= (int)blockDim.x) ? min((int)blockDim.x / K4c, kDgradPartCols / (4 * K4c)) : 1;
     const int Gc = G < 1 ? 1 : G;
-    for (int item = threadIdx.x; item < Gc * K4; item += blockDim.x) {
-        const int g = item / K4, k4 = item - g * K4;
+    for (int item = threadIdx.x; item < Gc * K4c; item += blockDim.x) {
+        const int g = item / K4c, k4 = k4_lo + (item - g * K4c);
         float4 acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -109,13 +139,9 @@ __device__ __forceinline__ void dense_dgrad(const float* __restrict__ W, const f
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int nn = n + u * Gc;
-                bool any = false;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    d[u][r] = nn < N ? s_dout[r * ld_dout + nn] : 0.f;
-                    any |= d[u][r] != 0.f;
-                }
-                wv[u] = any ? __ldg(wc + (size_t)nn * K4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < R; ++r) d[u][r] = nn < N ? s_dout[r * ld_dout + nn] : 0.f;
+                wv[u] = ld_nc_f4(wc + (size_t)min(nn, N - 1) * K4);     // unconditional: keeps the batch in flight
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -127,26 +153,40 @@ __device__ __forceinline__ void dense_dgrad(const float* __restrict__ W, const f
         }
         if (Gc == 1) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) reinterpret_cast<float4*>(s_din + r * ld_din)[k4] = acc[r];
+            for (int r = 0; r < R; ++r) {
+                if (broadcast) {
+                    for (int q = 0; q < cs; ++q)
+                        reinterpret_cast<float4*>(cluster.map_shared_rank(s_din, q) + r * ld_din)[k4] = acc[r];
+                } else {
+                    reinterpret_cast<float4*>(s_din + r * ld_din)[k4] = acc[r];
+                }
+            }
         } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) reinterpret_cast<float4*>(s_part + (size_t)(g * R + r) * K)[k4] = acc[r];
+            for (int r = 0; r < R; ++r)
+                reinterpret_cast<float4*>(s_part + (size_t)(g * R + r) * (4 * K4c))[k4 - k4_lo] = acc[r];
         }
     }
     __syncthreads();
     if (Gc > 1) {
-        for (int i = threadIdx.x; i < R * K; i += blockDim.x) {
-            const int r = i / K, k = i - r * K;
+        const int Kc = 4 * K4c;
+        for (int i = threadIdx.x; i < R * Kc; i += blockDim.x) {
+            const int r = i / Kc, kk = i - r * Kc;
             float s = 0.f;
-            for (int g = 0; g < Gc; ++g) s += s_part[(size_t)(g * R + r) * K + k];
-            s_din[r * ld_din + k] = s;
+            for (int g = 0; g < Gc; ++g) s += s_part[(size_t)(g * R + r) * Kc + kk];
+            const int k = k4_lo * 4 + kk;
+            if (broadcast) {
+                for (int q = 0; q < cs; ++q) cluster.map_shared_rank(s_din, q)[r * ld_din + k] = s;
+            } else {
+                s_din[r * ld_din + k] = s;
+            }
         }
-        __syncthreads();
     }
+    cluster.sync();
 }
 
 template <int R>
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kHeadThreads, 1)
 head_fwd_bwd_kernel(const HeadParams p) {
     extern __shared__ __align__(16) float smem[];
     const int H = p.H, C = p.C, K0 = 3 * p.H, L = p.n_mlp;
@@ -158,12 +198,14 @@ head_fwd_bwd_kernel(const HeadParams p) {
     float* s_d0 = s_dl + R * Cp;                 // [R][H]
     float* s_d1 = s_d0 + R * H;                  // [R][H]
     float* s_part = s_d1 + R * H;                // [R][max(kDgradPartCols, K0)]
-    const int b0 = blockIdx.x * R;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int b0 = (int)(blockIdx.x / cs) * R;
     const int tid = threadIdx.x;
 
     // warm L2: together the CTAs touch every weight line once, so the DRAM latency is paid once and in parallel
     // instead of once per pass of every layer
-    {
+    if (p.prefetch) {
         const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gsize = (size_t)gridDim.x * blockDim.x;
         for (int l = 0; l <= L; ++l) {
             const float* base = l < L ? p.w[l] : p.wc;
@@ -178,16 +220,16 @@ head_fwd_bwd_kernel(const HeadParams p) {
         const int b = min(b0 + r, p.B - 1);
         reinterpret_cast<float4*>(s_in + r * K0)[k4] = __ldg(reinterpret_cast<const float4*>(p.pooled + (size_t)b * K0) + k4);
     }
-    __syncthreads();
+    cluster.sync();     // also: every CTA of the cluster is resident before anybody stores into its shared memory
 
     // ---- forward -------------------------------------------------------------------------------------------------
     for (int l = 0; l < L; ++l) {
         const float* in = l == 0 ? s_in : s_h + (l - 1) * R * H;
-        dense_fwd<R, true>(p.w[l], p.b[l], in, l == 0 ? K0 : H, s_h + l * R * H, H, H, l == 0 ? K0 : H);
-        __syncthreads();
+        dense_fwd<R, true>(cluster, p.w[l], p.b[l], in, l == 0 ? K0 : H, s_h + l * R * H, H, H, l == 0 ? K0 : H);
+        cluster.sync();
     }
-    dense_fwd<R, false>(p.wc, p.bc, s_h + (L - 1) * R * H, H, s_logit, Cp, C, H);
-    __syncthreads();
+    dense_fwd<R, false>(cluster, p.wc, p.bc, s_h + (L - 1) * R * H, H, s_logit, Cp, C, H);
+    cluster.sync();
 
     // ---- loss + d logits: one warp per sentence --------------------------------------------------------------------
     {
@@ -213,10 +255,13 @@ head_fwd_bwd_kernel(const HeadParams p) {
                 const float pr = expf(lg[c] - lse);
                 const float d = (pr - (c == label ? 1.f : 0.f)) * p.inv_B;
                 s_dl[r * Cp + c] = d;
-                p.logits[(size_t)b * C + c] = lg[c];
-                if (p.train) p.dlogits[(size_t)b * C + c] = d;
+                if (crank == 0) {
+                    p.logits[(size_t)b * C + c] = lg[c];
+                    if (p.train) p.dlogits[(size_t)b * C + c] = d;
+                }
             }
-            if (lane == 0) p.loss_rows[b] = (lse - lg[label]) * p.inv_B + p.pooling_l2 * l2 * p.inv_B;
+            if (lane == 0 && crank == 0)
+                p.loss_rows[b] = (lse - lg[label]) * p.inv_B + p.pooling_l2 * l2 * p.inv_B;
         } else if (warp < R) {
             for (int c = lane; c < C; c += 32) s_dl[warp * Cp + c] = 0.f;   // padding sentence of the last CTA
         }
@@ -225,11 +270,12 @@ head_fwd_bwd_kernel(const HeadParams p) {
     __syncthreads();
 
     // ---- backward: data gradients down to d(pooled) ----------------------------------------------------------------
-    for (int i = tid; i < R * L * H; i += blockDim.x) {          // activations for the weight-gradient kernel
+    int k_lo, k_hi;
+    for (int i = tid + crank * (int)blockDim.x; i < R * L * H; i += (int)blockDim.x * cs) {   // for the wgrad kernel
         const int l = i / (R * H), rem = i - l * R * H, r = rem / H, n = rem - r * H;
         if (b0 + r < p.B) p.acts[((size_t)(b0 + r) * L + l) * H + n] = s_h[i];
     }
-    dense_dgrad<R>(p.wc, s_dl, Cp, s_part, s_d0, H, C, H);        // d post-activation of the last mlp layer
+    dense_dgrad<R>(cluster, p.wc, s_dl, Cp, s_part, s_d0, H, C, H, true, &k_lo, &k_hi);   // d post-act of last layer
     float* d_cur = s_d0;
     float* d_nxt = s_d1;
     for (int l = L - 1; l >= 0; --l) {
@@ -237,24 +283,25 @@ head_fwd_bwd_kernel(const HeadParams p) {
             const int r = i / H, n = i - r * H;
             const float d = s_h[(l * R + r) * H + n] > 0.f ? d_cur[i] : 0.f;
             d_cur[i] = d;
-            if (b0 + r < p.B) p.dacts[((size_t)(b0 + r) * L + l) * H + n] = d;
+            if (crank == 0 && b0 + r < p.B) p.dacts[((size_t)(b0 + r) * L + l) * H + n] = d;
         }
         __syncthreads();
         if (l > 0) {
-            dense_dgrad<R>(p.w[l], d_cur, H, s_part, d_nxt, H, H, H);
+            dense_dgrad<R>(cluster, p.w[l], d_cur, H, s_part, d_nxt, H, H, H, true, &k_lo, &k_hi);
             float* t = d_cur; d_cur = d_nxt; d_nxt = t;
         } else {
             // d(pooled) = d_pre0 . W0 + 2 * pooling_l2 / B * [h_out, 0, 0]; s_in still holds the pooled rows
             float* s_dp = s_h;                                    // activations are no longer needed: reuse as [R][K0]
             const bool fits = L * H >= K0;                        // s_h holds L*R*H floats
             float* dst = fits ? s_dp : s_part + (size_t)R * max(kDgradPartCols, K0);   // spill area past the partials
-            dense_dgrad<R>(p.w[0], d_cur, H, s_part, dst, K0, H, K0);
+            dense_dgrad<R>(cluster, p.w[0], d_cur, H, s_part, dst, K0, H, K0, false, &k_lo, &k_hi);
             const float c2 = 2.f * p.pooling_l2 * p.inv_B;
-            for (int i = tid; i < R * K0; i += blockDim.x) {
-                const int r = i / K0, k = i - r * K0;
+            const int Kc = k_hi - k_lo;                           // this rank's columns of d(pooled)
+            for (int i = tid; i < R * Kc; i += blockDim.x) {
+                const int r = i / Kc, k = k_lo + (i - r * Kc);
                 if (b0 + r >= p.B) continue;
-                float v = dst[i];
-                if (k < H) v += c2 * s_in[i];
+                float v = dst[r * K0 + k];
+                if (k < H) v += c2 * s_in[r * K0 + k];
                 p.dpooled[(size_t)(b0 + r) * K0 + k] = v;
             }
         }
@@ -378,6 +425,7 @@ extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, cons
     p.wc = wc; p.bc = bc;
     p.B = B; p.H = H; p.C = C; p.n_mlp = n_mlp; p.train = train;
     p.pooling_l2 = pooling_l2; p.inv_B = 1.0f / (float)B;
+    p.prefetch = getenv("GPT_HEAD_NOPF") == nullptr;
     p.logits = logits; p.loss_rows = loss_rows; p.acts = acts; p.dacts = dacts; p.dlogits = dlogits; p.dpooled = dpooled;
     // sentences per CTA: 1 while a wave of CTAs fits the machine, then 2 / 4 so that weights are streamed less often
     const int R = B <= 296 ? 1 : (B <= 1184 ? 2 : 4);
@@ -394,11 +442,31 @@ extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, cons
         if (e != cudaSuccess) return (int)e;
         configured[slot] = smem;
     }
-    const int grid = (B + R - 1) / R;
-    if (R == 1) head_fwd_bwd_kernel<1><<<grid, kHeadThreads, smem, st>>>(p);
-    else if (R == 2) head_fwd_bwd_kernel<2><<<grid, kHeadThreads, smem, st>>>(p);
-    else head_fwd_bwd_kernel<4><<<grid, kHeadThreads, smem, st>>>(p);
-    return gpt_launch_status();
+    const int groups = (B + R - 1) / R;
+    // CTAs per sentence group: a pair of CTAs halves the number of dependent round trips to L2 per layer as long as
+    // every CTA has an SM to itself (123 registers x 512 threads = one CTA per SM); wider clusters lose more to the
+    // cluster barriers than they gain (tools/head_bench.py: B=50: cs 1 / 2 / 4 -> 33 / 24 / 37 us)
+    int cs = (R == 1 && groups * 2 <= 148) ? 2 : 1;
+    if (const char* e2 = getenv("GPT_HEAD_CS")) cs = atoi(e2) > 0 ? atoi(e2) : cs;   // tuning knob (tools/head_bench.py)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(groups * cs));
+    cfg.blockDim = dim3(kHeadThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (R == 1) e = cudaLaunchKernelEx(&cfg, head_fwd_bwd_kernel<1>, p);
+    else if (R == 2) e = cudaLaunchKernelEx(&cfg, head_fwd_bwd_kernel<2>, p);
+    else e = cudaLaunchKernelEx(&cfg, head_fwd_bwd_kernel<4>, p);
+    ++g_gpt_launches;
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? GPT_OK : (int)e;
 }
 
 extern "C" int gpt_head_wgrad(const float* pooled, const float* acts, const float* dacts, const float* dlogits,

@@ -348,6 +348,7 @@ class FusedTrainStep(object):
         with torch.cuda.stream(sa):
             ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'], out=csr)
         with torch.cuda.stream(sb):
+            ops.l2_prefetch(fl.param)            # every dense weight: first touches later in the step hit L2
             for lin, ws in zip(gcn.W, wss):
                 ops.weight_prep(lin.weight.data, mode, out=ws)
         x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,

@@ -124,6 +124,11 @@ def prune_csr(head, subj_pos, obj_pos, deprel, masks, prune_k, out=None):
     return csr
 
 
+def l2_prefetch(t):
+    """Warm L2 with a tensor's bytes ahead of its first use."""
+    _call('gpt_l2_prefetch', _ptr(t), t.numel() * t.element_size(), _stream())
+
+
 # ---- K3: projection ------------------------------------------------------------------------------------------
 
 def _tf32_ok(*dims):

@@ -57,6 +57,9 @@ unsigned long long gpt_launch_count(void);
 /* host: static string for a return code of this library (cudaGetErrorString for positive codes) */
 const char* gpt_error_string(int code);
 
+/* prefetch [ptr, ptr + bytes) into L2 (no data is returned); used to warm the weights ahead of their first use */
+int gpt_l2_prefetch(const void* ptr, long long bytes, void* stream);
+
 /* K1. head_to_tree + tree_to_adj + the batch loop + adj!=0/denom/mask
  *     (model/tree.py:58-165, model/tree.py:167-204, model/gcn.py:96-110, model/gcn.py:260-262).
  * in : head, subj_pos, obj_pos, deprel  int64 [B,T] (loader layout, data/loader.py:110-121);

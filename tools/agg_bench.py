@@ -62,6 +62,12 @@ def main():
     bwd_bytes = 2 * B * T * H * 4 + B * T * H // 8 + 4 * B * (T + 1) + 4 * nnz + 4 * B * T
     t = timeit(lambda: ops.aggregate_bwd(gout, None, csr, drop_p=0.5, force_vec=a.vec, act=act), reps=6)
     print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % ('bwd(act)', t, bwd_bytes / t / 1e6, 100 * bwd_bytes / t / 1e6 / peak))
+    g = torch.randn(B, T, H, device='cuda')
+    bwd_bytes = 2 * B * T * H * 4 + 4 * B * (T + 1) + 4 * nnz + 4 * B * T
+    db = torch.zeros(H, device='cuda')
+    t = timeit(lambda: ops.aggregate_bwd_pre(g, csr, dbias_out=db), reps=6)
+    print('K2 %-12s %.3f ms  %.0f GB/s (%.1f%%)' % ('bwd(pre)', t, bwd_bytes / t / 1e6, 100 * bwd_bytes / t / 1e6 / peak))
+    del g
     h = out
     pool_bytes = B * T * H * 4 + B * 3 * H * 8 + B * T
     t = timeit(lambda: ops._Pool3.apply(h, csr, 0))
