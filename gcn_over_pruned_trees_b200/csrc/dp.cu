@@ -29,6 +29,7 @@ constexpr int kDpWarps = kDpThreads / 32;
 constexpr int kDpMaxWorld = 8;
 constexpr int kDpRowVec = 3;
 constexpr int kDpMaxBlocks = 1024;
+constexpr int kDpChunk = 8;           // token-slot entries a warp fetches together (reduce / apply)
 
 struct DpLayout {
     int W, cap_rows, E, V;
@@ -75,6 +76,13 @@ __device__ __forceinline__ float* dp_rows(const DpLayout& L, unsigned char* base
 }
 __device__ __forceinline__ int* dp_slot(const DpLayout& L, unsigned char* base, int par, int r) {
     return reinterpret_cast<int*>(base + L.off_slot) + (size_t)(par * L.W + r) * L.V;
+}
+
+// reduce: a warp serves dp_chunk(W) entries at a time, lane = (entry, rank) with dp_pow2(W) lanes per entry
+__host__ __device__ __forceinline__ int dp_pow2(int W) { return W <= 1 ? 1 : W <= 2 ? 2 : W <= 4 ? 4 : 8; }
+__host__ __device__ __forceinline__ int dp_chunk(int W) {
+    const int c = 32 / dp_pow2(W);
+    return c < kDpChunk ? c : kDpChunk;
 }
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -162,18 +170,22 @@ dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restr
     }
     if (blockIdx.x == 0 && tid == 0)
         for (int q = 0; q < W; ++q) dp_nrows(L, P.base[q], par)[rank] = n_rows;
-    // publish: every thread makes its stores visible system-wide, the last CTA to finish raises the flags
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned* done = reinterpret_cast<unsigned*>(self + L.off_done);
-        const unsigned prev = atomicAdd(done, 1u);
-        if (prev == gridDim.x - 1) {
-            *done = 0u;
-            __threadfence_system();
-            for (int q = 0; q < W; ++q) st_release_sys(dp_flags(L, P.base[q]) + rank, step);
-        }
+    // no fence here: the flags are raised by the NEXT kernel in stream order (dp_signal_kernel, or CTA 0 of
+    // dp_reduce_kernel), i.e. after this grid has completed and its stores have drained
+}
+
+// flags[rank] = step in every region.  Runs in a kernel that FOLLOWS dp_push_kernel in stream order: a grid starts only
+// after the previous one has completed and its stores (peer stores included) have been performed, so whoever
+// acquires the flag sees the pushed data.
+__device__ __forceinline__ void dp_raise_flags(const DpLayout& L, const DpPeers& P, int rank, unsigned long long step) {
+    if ((int)threadIdx.x < L.W) {
+        __threadfence_system();
+        st_release_sys(dp_flags(L, P.base[threadIdx.x]) + rank, step);
     }
+}
+
+__global__ void dp_signal_kernel(const DpLayout L, const DpPeers P, int rank) {
+    dp_raise_flags(L, P, rank, *reinterpret_cast<const unsigned long long*>(P.base[rank] + L.off_step));
 }
 
 __device__ __forceinline__ float dp_block_sum(float v, float* s_red) {
@@ -197,68 +209,121 @@ __device__ __forceinline__ void dp_entry(const int* s_off, int W, int e, int* r,
 }
 
 // ---- reduce (local memory only, after the flags) -------------------------------------------------------------------
-__global__ void __launch_bounds__(kDpThreads)
-dp_reduce_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __restrict__ flat_g, int dense_blocks,
-                 float* __restrict__ partials) {
+__global__ void __launch_bounds__(kDpThreads, 4)
+dp_reduce_kernel(const DpLayout L, const DpPeers P, int rank, int signal, float* __restrict__ flat_g,
+                 int dense_blocks, float* __restrict__ partials) {
     __shared__ float s_red[kDpWarps];
-    __shared__ int s_off[kDpMaxWorld + 1];
+    __shared__ int s_off[kDpMaxWorld + 1], s_n[kDpMaxWorld];
+    unsigned char* self = P.base[rank];
     const unsigned long long step = *reinterpret_cast<const unsigned long long*>(self + L.off_step);
     const int par = (int)(step & 1ull);
     const int W = L.W, tid = threadIdx.x;
+    if (signal && blockIdx.x == 0) dp_raise_flags(L, P, rank, step);
     if (tid < W) {      // a peer that died must not leave this GPU spinning for ever: trap after ~10 s
         const unsigned long long* f = dp_flags(L, self) + tid;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < step) {
-            __nanosleep(200);
+            __nanosleep(100);
             if (clock64() - t0 > 20000000000ll) __trap();
         }
+        s_n[tid] = min(dp_nrows(L, self, par)[tid], L.cap_rows);
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid <= W) {
         int o = 0;
-        for (int r = 0; r < W; ++r) { s_off[r] = o; o += min(dp_nrows(L, self, par)[r], L.cap_rows); }
-        s_off[W] = o;
+        for (int r = 0; r < tid; ++r) o += s_n[r];
+        s_off[tid] = o;
     }
     __syncthreads();
     float s = 0.f;
     if ((int)blockIdx.x < dense_blocks) {
         const long long n4 = L.n_flat >> 2;
         for (long long i = (long long)blockIdx.x * kDpThreads + tid; i < n4; i += (long long)dense_blocks * kDpThreads) {
-            float4 a = reinterpret_cast<const float4*>(dp_dense(L, self, par, 0))[i];
-            for (int r = 1; r < W; ++r) {
-                const float4 b = reinterpret_cast<const float4*>(dp_dense(L, self, par, r))[i];
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
+            float4 t[kDpMaxWorld];                               // every rank's slice in flight before the first add
+#pragma unroll
+            for (int r = 0; r < kDpMaxWorld; ++r)
+                if (r < W) t[r] = reinterpret_cast<const float4*>(dp_dense(L, self, par, r))[i];
+            float4 a = t[0];
+#pragma unroll
+            for (int r = 1; r < kDpMaxWorld; ++r)
+                if (r < W) { a.x += t[r].x; a.y += t[r].y; a.z += t[r].z; a.w += t[r].w; }
             reinterpret_cast<float4*>(flat_g)[i] = a;
             s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
         }
     } else {
+        // Token-slot entries of all ranks, kDpChunk per warp: the lanes fetch the ids together, then the live ones are
+        // served one after the other with every load of a row (and of its contributions) issued before the first store.
         const int row_blocks = gridDim.x - dense_blocks;
         const int warp = tid >> 5, lane = tid & 31;
-        const int E = L.E;
+        const int E = L.E, E4 = E >> 2;
+        const bool vec = (E & 3) == 0 && E4 <= 32 * kDpRowVec;
         const int total = s_off[W];
-        for (int e = ((int)blockIdx.x - dense_blocks) * kDpWarps + warp; e < total; e += row_blocks * kDpWarps) {
-            int r, i;
-            dp_entry(s_off, W, e, &r, &i);
-            int* ids = dp_ids(L, self, par, r);
-            const int w = ids[i];
-            if (w < 0) continue;
-            bool first = true;
-            for (int r2 = 0; r2 < r; ++r2) first &= dp_slot(L, self, par, r2)[w] < 0;
-            if (!first) {                      // a lower rank owns this word: it will pick this row up
-                __syncwarp();
-                if (lane == 0) ids[i] = -1;
-                continue;
+        const unsigned wmask = (1u << W) - 1u;
+        // lane = (entry j of the chunk, rank q): one instruction fetches, for every entry, the slot every rank holds
+        // for its word
+        const int Wp = dp_pow2(W), chunk = dp_chunk(W);
+        const int jl = lane / Wp, ql = lane - jl * Wp;
+        const int stride = row_blocks * kDpWarps * chunk;
+        for (int base = (((int)blockIdx.x - dense_blocks) * kDpWarps + warp) * chunk; base < total; base += stride) {
+            const int e = base + jl;
+            int r = 0, i = 0, w = -1;
+            if (jl < chunk && e < total) {
+                dp_entry(s_off, W, e, &r, &i);
+                w = dp_ids(L, self, par, r)[i];
             }
-            float* mine = dp_rows(L, self, par, r) + (size_t)i * E;
-            for (int c = lane; c < E; c += 32) {
-                float a = mine[c];
-                for (int r2 = r + 1; r2 < W; ++r2) {
-                    const int s2 = dp_slot(L, self, par, r2)[w];
-                    if (s2 >= 0) a += dp_rows(L, self, par, r2)[(size_t)s2 * E + c];
+            int sl = -1;
+            if (w >= 0 && ql < W) sl = dp_slot(L, self, par, ql)[w];
+            const unsigned hasm = __ballot_sync(GPT_FULL_MASK, sl >= 0);
+            unsigned livem = __ballot_sync(GPT_FULL_MASK, w >= 0 && ql == 0);
+            while (livem) {
+                const int j = __ffs(livem) - 1;                       // lane (entry, rank 0)
+                livem &= livem - 1u;
+                const int rj = __shfl_sync(GPT_FULL_MASK, r, j), ij = __shfl_sync(GPT_FULL_MASK, i, j);
+                const unsigned has = (hasm >> j) & wmask;
+                if (has & ((1u << rj) - 1u)) {     // a lower rank owns this word: it will pick this row up
+                    if (lane == 0) dp_ids(L, self, par, rj)[ij] = -1;
+                    continue;
                 }
-                mine[c] = a;
-                s += a * a;
+                float* mine = dp_rows(L, self, par, rj) + (size_t)ij * E;
+                if (vec) {
+                    float4 acc[kDpRowVec];
+#pragma unroll
+                    for (int k = 0; k < kDpRowVec; ++k)
+                        acc[k] = lane + 32 * k < E4 ? reinterpret_cast<const float4*>(mine)[lane + 32 * k]
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned oth = has & ~((2u << rj) - 1u);        // higher ranks holding the word, in rank order
+                    while (oth) {
+                        const int r2 = __ffs(oth) - 1;
+                        oth &= oth - 1u;
+                        const int s2 = __shfl_sync(GPT_FULL_MASK, sl, (j + r2) & 31);
+                        const float4* src = reinterpret_cast<const float4*>(dp_rows(L, self, par, r2) + (size_t)s2 * E);
+                        float4 t[kDpRowVec];
+#pragma unroll
+                        for (int k = 0; k < kDpRowVec; ++k)
+                            t[k] = lane + 32 * k < E4 ? src[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < kDpRowVec; ++k) {
+                            acc[k].x += t[k].x; acc[k].y += t[k].y; acc[k].z += t[k].z; acc[k].w += t[k].w;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kDpRowVec; ++k)
+                        if (lane + 32 * k < E4) {
+                            reinterpret_cast<float4*>(mine)[lane + 32 * k] = acc[k];
+                            s += acc[k].x * acc[k].x + acc[k].y * acc[k].y + acc[k].z * acc[k].z + acc[k].w * acc[k].w;
+                        }
+                } else {
+                    int slots[kDpMaxWorld];
+#pragma unroll
+                    for (int r2 = 0; r2 < kDpMaxWorld; ++r2) slots[r2] = __shfl_sync(GPT_FULL_MASK, sl, (j + r2) & 31);
+                    for (int c = lane; c < E; c += 32) {
+                        float a = mine[c];
+                        for (int r2 = rj + 1; r2 < W; ++r2)
+                            if ((has >> r2) & 1u) a += dp_rows(L, self, par, r2)[(size_t)slots[r2] * E + c];
+                        mine[c] = a;
+                        s += a * a;
+                    }
+                }
             }
         }
     }
@@ -267,7 +332,7 @@ dp_reduce_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __re
 }
 
 // ---- apply ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kDpThreads)
+__global__ void __launch_bounds__(kDpThreads, 6)
 dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __restrict__ param,
                 float* __restrict__ flat_g, float* __restrict__ emb_w, int dense_blocks,
                 const float* __restrict__ partials, int n_partials, float max_norm, float lr,
@@ -279,10 +344,10 @@ dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __res
     const int par = (int)(step & 1ull);
     const int W = L.W, tid = threadIdx.x;
     const float inv_w = 1.0f / (float)W;
-    if (tid == 0) {
+    if (tid >= 32 && tid <= 32 + W) {          // (warp 1: off the path of the norm below)
         int o = 0;
-        for (int r = 0; r < W; ++r) { s_off[r] = o; o += min(dp_nrows(L, self, par)[r], L.cap_rows); }
-        s_off[W] = o;
+        for (int r = 0; r < tid - 32; ++r) o += min(dp_nrows(L, self, par)[r], L.cap_rows);
+        s_off[tid - 32] = o;
     }
     {
         float s = 0.f;
@@ -310,17 +375,44 @@ dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __res
     } else {
         const int row_blocks = gridDim.x - dense_blocks;
         const int warp = tid >> 5, lane = tid & 31;
-        const int E = L.E;
+        const int E = L.E, E4 = E >> 2;
+        const bool vec = (E & 3) == 0 && E4 <= 32 * kDpRowVec;
         const int total = s_off[W];
-        for (int e = ((int)blockIdx.x - dense_blocks) * kDpWarps + warp; e < total; e += row_blocks * kDpWarps) {
-            int r, i;
-            dp_entry(s_off, W, e, &r, &i);
-            const int w = dp_ids(L, self, par, r)[i];
-            if (w < 0) continue;                               // not live, or folded into a lower rank's entry
-            const float* row = dp_rows(L, self, par, r) + (size_t)i * E;
-            float* wr = emb_w + (size_t)w * E;
-            for (int c = lane; c < E; c += 32) wr[c] -= a * row[c];
-            if (lane < W && lane >= r) dp_slot(L, self, par, lane)[w] = -1;
+        const int stride = row_blocks * kDpWarps * kDpChunk;
+        for (int base = (((int)blockIdx.x - dense_blocks) * kDpWarps + warp) * kDpChunk; base < total; base += stride) {
+            const int e = base + lane;
+            int r = 0, i = 0, w = -1;                            // w < 0: not live, or folded into a lower rank's entry
+            if (lane < kDpChunk && e < total) {
+                dp_entry(s_off, W, e, &r, &i);
+                w = dp_ids(L, self, par, r)[i];
+            }
+            unsigned livem = __ballot_sync(GPT_FULL_MASK, w >= 0);
+            while (livem) {
+                const int j = __ffs(livem) - 1;
+                livem &= livem - 1u;
+                const int wj = __shfl_sync(GPT_FULL_MASK, w, j), rj = __shfl_sync(GPT_FULL_MASK, r, j),
+                          ij = __shfl_sync(GPT_FULL_MASK, i, j);
+                const float* row = dp_rows(L, self, par, rj) + (size_t)ij * E;
+                float* wr = emb_w + (size_t)wj * E;
+                if (vec) {
+                    float4 g[kDpRowVec], p[kDpRowVec];
+#pragma unroll
+                    for (int k = 0; k < kDpRowVec; ++k)
+                        if (lane + 32 * k < E4) {
+                            g[k] = reinterpret_cast<const float4*>(row)[lane + 32 * k];
+                            p[k] = reinterpret_cast<const float4*>(wr)[lane + 32 * k];
+                        }
+#pragma unroll
+                    for (int k = 0; k < kDpRowVec; ++k)
+                        if (lane + 32 * k < E4) {
+                            p[k].x -= a * g[k].x; p[k].y -= a * g[k].y; p[k].z -= a * g[k].z; p[k].w -= a * g[k].w;
+                            reinterpret_cast<float4*>(wr)[lane + 32 * k] = p[k];
+                        }
+                } else {
+                    for (int c = lane; c < E; c += 32) wr[c] -= a * row[c];
+                }
+                if (lane < W && lane >= rj) dp_slot(L, self, par, lane)[wj] = -1;
+            }
         }
     }
     // the last CTA to finish opens the next step
@@ -338,10 +430,11 @@ dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __res
 }
 
 void plan(const DpLayout& L, int* dense_blocks, int* row_blocks) {
-    long long db = (L.n_flat / 4 + kDpThreads * 4 - 1) / (kDpThreads * 4);
+    long long db = (L.n_flat / 4 + kDpThreads - 1) / kDpThreads;       // one float4 per thread while that fits
     if (db < 1) db = 1;
     if (db > 296) db = 296;
-    long long rb = ((long long)L.W * L.cap_rows + kDpWarps - 1) / kDpWarps;
+    const int per_block = kDpWarps * dp_chunk(L.W);
+    long long rb = ((long long)L.W * L.cap_rows + per_block - 1) / per_block;
     if (rb > kDpMaxBlocks - 296) rb = kDpMaxBlocks - 296;
     *dense_blocks = (int)db;
     *row_blocks = (int)rb;
@@ -425,22 +518,49 @@ extern "C" int gpt_dp_push(void* const* regions, int rank, int W, int cap_rows, 
     int d, r;
     plan(L, &d, &r);
     int rb = (n_rows + kDpWarps - 1) / kDpWarps;
-    if (rb > r) rb = r;
+    if (rb > kDpMaxBlocks - 296) rb = kDpMaxBlocks - 296;      // one warp per token slot
+    (void)r;
     dp_push_kernel<<<d + rb, kDpThreads, 0, (cudaStream_t)stream>>>(
         L, P, rank, flat_g, g_emb, owner, reinterpret_cast<const long long*>(words), n_rows, topn, d);
     return gpt_launch_status();
 }
 
-extern "C" int gpt_dp_reduce(void* region, int W, int cap_rows, int E, int V, long long n_flat, float* flat_g,
-                             float* partials, void* stream) {
-    GPT_CHECK_ARG(region && flat_g && partials && (reinterpret_cast<uintptr_t>(flat_g) & 15) == 0);
+static int dp_peers(void* const* regions, int W, DpPeers* P) {
+    for (int q = 0; q < W; ++q) {
+        GPT_CHECK_ARG(regions[q]);
+        P->base[q] = reinterpret_cast<unsigned char*>(regions[q]);
+    }
+    return GPT_OK;
+}
+
+extern "C" int gpt_dp_signal(void* const* regions, int rank, int W, int cap_rows, int E, int V, long long n_flat,
+                             void* stream) {
+    GPT_CHECK_ARG(regions && rank >= 0 && rank < W);
+    int rc = check_layout(W, cap_rows, E, V, n_flat);
+    if (rc != GPT_OK) return rc;
+    DpPeers P{};
+    if ((rc = dp_peers(regions, W, &P)) != GPT_OK) return rc;
+    dp_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(make_layout(W, cap_rows, E, V, n_flat), P, rank);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_dp_reduce(void* const* regions, int rank, int signal, int W, int cap_rows, int E, int V,
+                             long long n_flat, float* flat_g, float* partials, void* stream) {
+    GPT_CHECK_ARG(regions && rank >= 0 && rank < W && flat_g && partials);
+    GPT_CHECK_ARG((reinterpret_cast<uintptr_t>(flat_g) & 15) == 0);
     int rc = check_layout(W, cap_rows, E, V, n_flat);
     if (rc != GPT_OK) return rc;
     const DpLayout L = make_layout(W, cap_rows, E, V, n_flat);
+    DpPeers P{};
+    if (signal) {
+        if ((rc = dp_peers(regions, W, &P)) != GPT_OK) return rc;
+    } else {
+        GPT_CHECK_ARG(regions[rank]);
+        P.base[rank] = reinterpret_cast<unsigned char*>(regions[rank]);
+    }
     int d, r;
     plan(L, &d, &r);
-    dp_reduce_kernel<<<d + r, kDpThreads, 0, (cudaStream_t)stream>>>(L, reinterpret_cast<unsigned char*>(region),
-                                                                      flat_g, d, partials);
+    dp_reduce_kernel<<<d + r, kDpThreads, 0, (cudaStream_t)stream>>>(L, P, rank, signal, flat_g, d, partials);
     return gpt_launch_status();
 }
 

@@ -522,8 +522,17 @@ def dp_push(region_ptrs, rank, shape, flat_grad, sparse):
           sparse.topn if sparse else 0, _stream())
 
 
-def dp_reduce(region_ptr, shape, flat_grad, partials):
-    _call('gpt_dp_reduce', region_ptr, *shape, _ptr(flat_grad), _ptr(partials), _stream())
+def dp_signal(region_ptrs, rank, shape):
+    """Raise this rank's flags in every region (only needed when dp_reduce is called with signal=False)."""
+    import ctypes
+    arr = (ctypes.c_void_p * len(region_ptrs))(*region_ptrs)
+    _call('gpt_dp_signal', arr, rank, *shape, _stream())
+
+
+def dp_reduce(region_ptrs, rank, shape, flat_grad, partials, signal=True):
+    import ctypes
+    arr = (ctypes.c_void_p * len(region_ptrs))(*region_ptrs)
+    _call('gpt_dp_reduce', arr, rank, 1 if signal else 0, *shape, _ptr(flat_grad), _ptr(partials), _stream())
 
 
 def dp_apply(region_ptr, shape, flat_param, flat_grad, emb_weight, partials, max_norm, lr, total_norm=None,

@@ -201,10 +201,13 @@ int gpt_update_apply(float* param, float* grad, long long n, const int64_t* word
  *     Every rank owns a region of gpt_dp_region_bytes(); regions[q] is rank q's region as mapped in this process
  *     (own: gpt_dp_alloc, peers: gpt_dp_open on the 64-byte cudaIpc handle).  W <= 8; cap_rows >= n_rows of any step.
  *     Per step, in stream order on every rank:
- *       gpt_dp_push    stores this rank's flat gradient, live word ids / rows and word->slot map into every region,
- *                      raises flags[rank] = step everywhere; clears g_emb rows and owner marks
- *       gpt_dp_reduce  waits for all W flags, sums in rank order (bit-identical on every rank) into flat_g and the
- *                      first-owner row slots, writes gpt_dp_partials() partial sums of g^2
+ *       gpt_dp_push    stores this rank's flat gradient, live word ids / rows and word->slot map into every region;
+ *                      clears g_emb rows and owner marks.  No fence inside: the flags are raised by the next launch
+ *       gpt_dp_reduce  signal != 0: first raises flags[rank] = step in every region (the push grid has completed by
+ *                      then, so its peer stores have been performed); waits for all W flags, sums in rank order
+ *                      (bit-identical on every rank) into flat_g and the first-owner row slots, writes
+ *                      gpt_dp_partials() partial sums of g^2.  signal == 0: only regions[rank] is read and the caller
+ *                      raises the flags itself with gpt_dp_signal (several ranks driven from one stream: tests)
  *       gpt_dp_apply   K7 with the mean gradient (sum / W): clip, SGD, resets; advances the region's step and
  *                      *step_counter
  *     A rank that waits more than ~10 s for a peer traps (the launch fails) instead of spinning for ever. */
@@ -218,8 +221,9 @@ int gpt_dp_region_init(void* region, int W, int cap_rows, int E, int V, long lon
 int gpt_dp_push(void* const* regions /* host array of W device pointers */, int rank, int W, int cap_rows, int E, int V,
                 long long n_flat, const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words, int n_rows,
                 int topn, void* stream);
-int gpt_dp_reduce(void* region, int W, int cap_rows, int E, int V, long long n_flat, float* flat_g, float* partials,
-                  void* stream);
+int gpt_dp_signal(void* const* regions, int rank, int W, int cap_rows, int E, int V, long long n_flat, void* stream);
+int gpt_dp_reduce(void* const* regions, int rank, int signal, int W, int cap_rows, int E, int V, long long n_flat,
+                  float* flat_g, float* partials, void* stream);
 int gpt_dp_apply(void* region, int W, int cap_rows, int E, int V, long long n_flat, float* param, float* flat_g,
                  float* emb_w, const float* partials, float max_norm, float lr, float* total_norm,
                  uint64_t* step_counter, void* stream);

@@ -54,7 +54,12 @@ def main():
         loss_err = max(abs(a - b) / abs(b) for a, b in zip(mean_loss.tolist(), ref_losses))
         ok = ok and worst < 5e-5 and loss_err < 2e-5
         msg += '; vs full-batch single process: params rel %.2e, loss rel %.2e' % (worst, loss_err)
-        print('DP_CHECK %s world=%d %s' % ('OK' if ok else 'FAIL', world, msg), flush=True)
+        line = 'DP_CHECK %s world=%d %s' % ('OK' if ok else 'FAIL', world, msg)
+        print(line, flush=True)
+        out_dir = os.path.join(REPO, 'gpurun_out')
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, 'dp_check_w%d.txt' % world), 'w') as f:
+                f.write(line + '\n')
     flag = torch.tensor([1 if ok else 0], device='cuda')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()

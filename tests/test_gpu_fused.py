@@ -324,9 +324,10 @@ def test_k8_exchange_of_virtual_ranks_is_the_mean_gradient_and_bit_identical(W):
             grads.append(g.clone())
             dense_G.append(states[r].G.clone())
             ops.dp_push(ptrs, r, shape, g, states[r])
+            ops.dp_signal(ptrs, r, shape)
         for r in range(W):
             g_buf = torch.empty(n, device=DEV)
-            ops.dp_reduce(ptrs[r], shape, g_buf, partials)
+            ops.dp_reduce(ptrs, r, shape, g_buf, partials, signal=False)
             ops.dp_apply(ptrs[r], shape, params[r], g_buf, embs[r], partials, 5.0, 0.3, None, counter[1:])
             assert float(g_buf.abs().max()) == 0.0
         p_ref.grad = torch.stack(grads).sum(0) / W
