@@ -178,18 +178,20 @@ def aggregation_roofline(args, peaks):
     n_rows = int((csr.flags != 0).sum())
     nnz = int(csr.rowptr[:, T].sum())
     results = {}
-    for name, drop_p in (('fwd', 0.0), ('fwd_dropout', 0.5)):
+    # 'fwd_train' is the variant the training step launches for every layer but the last: dropout + activation bit mask
+    for name, drop_p, want_act in (('fwd', 0.0, False), ('fwd_dropout', 0.5, False), ('fwd_train', 0.5, True)):
         for _ in range(3):
-            out = ops.aggregate_fwd(y, csr, bias, drop_p=drop_p, rng_state=rng)
+            out = ops.aggregate_fwd(y, csr, bias, drop_p=drop_p, rng_state=rng, want_act=want_act)
         reps = 10
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         torch.cuda.synchronize()
         for a, b in ev:                      # y + out = 8.6 GB >> 126 MB of L2: every launch streams from HBM
             a.record()
-            out = ops.aggregate_fwd(y, csr, bias, drop_p=drop_p, rng_state=rng)
+            out = ops.aggregate_fwd(y, csr, bias, drop_p=drop_p, rng_state=rng, want_act=want_act)
             b.record()
         torch.cuda.synchronize()
         results[name] = sum(a.elapsed_time(b) for a, b in ev) / reps
+        del out
     gout = torch.randn(B, T, H, device='cuda')
     out, act = ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng, want_act=True)
     for _ in range(2):                       # as the model runs it: [out > 0] from the 1-bit activation mask
@@ -223,21 +225,27 @@ def aggregation_roofline(args, peaks):
     if os.path.exists(tpath) and B == 4096:
         t = json.load(open(tpath))
         traffic = t['dram_bytes_read'] + t['dram_bytes_write']
-    ach = bytes_fwd / (results['fwd_dropout'] * 1e-3) / 1e9
+    bytes_train = bytes_fwd + B * T * H // 8             # + the 1-bit activation mask the backward reads
+    ach = bytes_train / (results['fwd_train'] * 1e-3) / 1e9
     del y, out, gout, act
     torch.cuda.empty_cache()
-    return {'bound': 'hbm', 'kernel': 'aggregate_fwd_kernel (K2, dropout on)', 'achieved': ach, 'peak': peak,
-            'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peaks['source'], 'traffic': traffic,
+    gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9  # noqa: E731
+    return {'bound': 'hbm', 'kernel': 'aggregate_fwd_kernel<8,512,1,1> (K2 forward as the training step runs it: '
+                                      'dropout 0.5 + activation bit mask)',
+            'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peaks['source'],
+            'traffic': traffic,
             'workload': 'large512: B=%d x T=512 trees, H=512, prune_k=-1, rows=%d, nnz=%d' % (B, n_rows, nnz),
-            'bytes_per_launch': bytes_fwd, 'ms_per_launch': results['fwd_dropout'],
+            'bytes_per_launch': bytes_train, 'ms_per_launch': results['fwd_train'],
             'frac_of_nominal_8000': ach / 8000.0,
-            'other': {'fwd_no_dropout_ms': results['fwd'],
-                      'fwd_no_dropout_gbs': bytes_fwd / (results['fwd'] * 1e-3) / 1e9,
-                      'bwd_ms': results['bwd'], 'bwd_gbs': bytes_bwd / (results['bwd'] * 1e-3) / 1e9,
+            'other': {'fwd_no_dropout_ms': results['fwd'], 'fwd_no_dropout_gbs': gbs(bytes_fwd, results['fwd']),
+                      'fwd_dropout_no_mask_ms': results['fwd_dropout'],
+                      'fwd_dropout_no_mask_gbs': gbs(bytes_fwd, results['fwd_dropout']),
+                      'fwd_dropout_no_mask_frac': gbs(bytes_fwd, results['fwd_dropout']) / peak,
+                      'bwd_ms': results['bwd'], 'bwd_gbs': gbs(bytes_bwd, results['bwd']),
                       'bwd_bytes_per_launch': bytes_bwd,
                       'bwd_pre_scaled_ms': results['bwd_pre'],
-                      'bwd_pre_scaled_gbs': bytes_bwd_pre / (results['bwd_pre'] * 1e-3) / 1e9,
-                      'bwd_pre_scaled_frac': bytes_bwd_pre / (results['bwd_pre'] * 1e-3) / 1e9 / peak}}
+                      'bwd_pre_scaled_gbs': gbs(bytes_bwd_pre, results['bwd_pre']),
+                      'bwd_pre_scaled_frac': gbs(bytes_bwd_pre, results['bwd_pre']) / peak}}
 
 
 def load_peaks():

@@ -106,6 +106,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
@@ -120,15 +123,18 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
 //   meta [T+1]            .x = CSR row start | (row length << 16), .y = bits of 1/denom (0: unobservable row)
 //   perm [..]             row ids sorted by row length (longest first), padded with T
 //   col  [4T+4]           16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
+//   actb [T][8]           forward, when the activation mask is written: one byte per (row, lane of the row's group)
+//                         holding that lane's 4 activation bits; packed into the row's 32-bit word after the slice
 struct Layout {
-    size_t tile, red, bits, bias, meta, perm, col, total;  // byte offsets
+    size_t tile, red, bits, bias, meta, perm, col, actb, total;  // byte offsets
 };
 __host__ __device__ inline size_t tile_floats(int T, int lpr) { return (size_t)(T + 1) * 4 * lpr; }
 __host__ __device__ inline int perm_len(int T, int groups) {
     return ((T + groups * 4 - 1) / (groups * 4)) * groups * 4;
 }
 __host__ __device__ inline int bits_stride(int T, int lpr) { return ((T * ((4 * lpr + 31) / 32) + 3) / 4) * 4; }
-__host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int nbuf, bool fwd, bool bits) {
+__host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int nbuf, bool fwd, bool bits,
+                                              bool actb = false) {
     const int groups = (nt / 32) * (32 / lpr), hs = 4 * lpr;
     Layout L;
     size_t o = 0;
@@ -140,6 +146,8 @@ __host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int
     L.perm = o; o += (size_t)perm_len(T, groups) * 2;
     o = (o + 3) / 4 * 4;
     L.col = o;  o += (size_t)(4 * T + 4) * 2;
+    o = (o + 7) / 8 * 8;
+    L.actb = o; o += actb ? (size_t)T * 8 : 0;
     L.total = (o + 15) / 16 * 16;
     return L;
 }
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
     const int b = blockIdx.y;
     const int nsl = (H + HS - 1) / HS;
     const bool write_act = (p.act_out != nullptr) && (LPR == 8);
-    const Layout L = make_layout(T, H, LPR, NT, p.nbuf, true, DROP == DROP_PHILOX);
+    const Layout L = make_layout(T, H, LPR, NT, p.nbuf, true, DROP == DROP_PHILOX, write_act);
     float* tile0 = reinterpret_cast<float*>(smem_raw + L.tile);
     uint32_t* keepw = reinterpret_cast<uint32_t*>(smem_raw + L.bits);
     float* bias_sm = reinterpret_cast<float*>(smem_raw + L.bias);
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
     unsigned long long seed = 0, step = 0;
     if (DROP == DROP_PHILOX) { seed = p.rng[0]; step = p.rng[1]; }
     const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv), perm_s = smem_u32(perm);
-    const uint32_t bias_s = smem_u32(bias_sm), keep_s = smem_u32(keepw);
+    const uint32_t bias_s = smem_u32(bias_sm), keep_s = smem_u32(keepw), actb_s = smem_u32(smem_raw + L.actb);
     const unsigned thresh = p.thresh16;
     const float dscale = p.drop_scale;
 
@@ -377,18 +385,23 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
                     }
                 }
                 if (live) store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
-                if (write_act) {  // CTA-uniform; LPR == 8: the lane group's 8 nibbles make the row's 32-bit word
-                    uint32_t nib = (res[0] > 0.f ? 1u : 0u) | (res[1] > 0.f ? 2u : 0u) | (res[2] > 0.f ? 4u : 0u) |
-                                   (res[3] > 0.f ? 8u : 0u);
-                    uint32_t word = live ? nib << cl : 0u;
-                    word |= __shfl_xor_sync(GPT_FULL_MASK, word, 1);  // OR over the 8 lanes of the group
-                    word |= __shfl_xor_sync(GPT_FULL_MASK, word, 2);
-                    word |= __shfl_xor_sync(GPT_FULL_MASK, word, 4);
-                    if (live && cl == 0) act_sl[i] = word;
+                if (write_act && i < T) {  // CTA-uniform; LPR == 8: this lane's 4 activation bits, packed after the slice
+                    const uint32_t nib = (res[0] > 0.f ? 1u : 0u) | (res[1] > 0.f ? 2u : 0u) | (res[2] > 0.f ? 4u : 0u) |
+                                         (res[3] > 0.f ? 8u : 0u);
+                    sts_u8(actb_s + (uint32_t)i * 8u + (uint32_t)(lane % LPR), col_ok ? nib : 0u);
                 }
             }
         }
         __syncthreads();  // everyone is done with this buffer / keep-words before the next iteration refills them
+        if (write_act) {
+            // the row's 8 nibbles -> its 32-bit activation word, stored in row order (coalesced); the barrier after the
+            // next slice has landed orders these reads before the next writes of actb
+            for (int t = threadIdx.x; t < T; t += NT) {
+                const uint2 v = lds64(actb_s + (uint32_t)t * 8u);
+                const uint32_t lo = v.x | (v.x >> 4), hi = v.y | (v.y >> 4);
+                act_sl[t] = ((lo & 0xffu) | ((lo >> 8) & 0xff00u)) | (((hi & 0xffu) | ((hi >> 8) & 0xff00u)) << 16);
+            }
+        }
     }
 }
 
@@ -544,7 +557,7 @@ AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
     AggConfig c{};
     auto slices = [&](int lpr) { return (H + 4 * lpr - 1) / (4 * lpr); };
     auto bytes = [&](int lpr, int nt, int nbuf) {
-        return make_layout(T, H, lpr, nt, nbuf, fwd, fwd ? philox : (act && lpr == 8)).total;
+        return make_layout(T, H, lpr, nt, nbuf, fwd, fwd ? philox : (act && lpr == 8), fwd && act && lpr == 8).total;
     };
     if (force_vec == 1 || ((force_vec == 2 || force_vec == 4) && !act)) {
         c.lpr = 8 * force_vec; c.nt = 256; c.nbuf = 1; c.grid_x = slices(c.lpr);

@@ -178,10 +178,7 @@ dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restr
 // after the previous one has completed and its stores (peer stores included) have been performed, so whoever
 // acquires the flag sees the pushed data.
 __device__ __forceinline__ void dp_raise_flags(const DpLayout& L, const DpPeers& P, int rank, unsigned long long step) {
-    if ((int)threadIdx.x < L.W) {
-        __threadfence_system();
-        st_release_sys(dp_flags(L, P.base[threadIdx.x]) + rank, step);
-    }
+    if ((int)threadIdx.x < L.W) st_release_sys(dp_flags(L, P.base[threadIdx.x]) + rank, step);
 }
 
 __global__ void dp_signal_kernel(const DpLayout L, const DpPeers P, int rank) {

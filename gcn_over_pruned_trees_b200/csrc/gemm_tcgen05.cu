@@ -109,13 +109,15 @@ template <int PASSES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
-                 int tmem_cols, int STAGES, const MaskEpilogue ep) {
+                 int n_tiles, int tmem_cols, int STAGES, const MaskEpilogue ep) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * n_tile;
+    // N tiles of one M tile are neighbours in launch order: they run at the same time and the second read of the A tile
+    // is served by L2 instead of HBM
+    const int m0 = (int)(blockIdx.x / n_tiles) * BM, n0 = (int)(blockIdx.x % n_tiles) * n_tile;
     const int nkb = (K + BK - 1) / BK;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_tile * BK * 4;
     // stage layout: [A | A_lo | B | B_lo] (the lo tiles only for PASSES == 3); every tile is 1024-byte aligned
@@ -345,9 +347,9 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
         if (a != cudaSuccess) return (int)a;
         configured = smem;
     }
-    dim3 grid((M + BM - 1) / BM, n_tiles);
-    tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, tmem_cols,
-                                                               stages, ep);
+    dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles));
+    tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
+                                                               tmem_cols, stages, ep);
     return gpt_launch_status();
 }
 
