@@ -189,12 +189,24 @@ def linear_dgrad(dy, weight, mode='fp32', ws=None):
     return dx
 
 
+WGRAD_TC_MIN_ROWS = 32768     # below this the FFMA kernel over the live rows wins (TACRED-shaped batches: ~2 750 rows)
+
+
+def wgrad_tc_ok(M, N, K):
+    """Shapes csrc/wgrad_tcgen05.cu takes: TMA-describable, accumulator fits tensor memory, reduction long enough."""
+    return M >= WGRAD_TC_MIN_ROWS and K % 4 == 0 and N % 4 == 0 and K <= 512
+
+
 def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False, flags=None):
     """dw = dy^T x.  accumulate: add into ``out`` (which the caller keeps zeroed between steps) instead of overwriting;
     with ``flags`` (K1's per-row flags) only rows that carry a gradient are read."""
     M, N = dy.shape
     K = x2d.shape[1]
     dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
+    if accumulate and mode == 'tf32x3' and wgrad_tc_ok(M, N, K):
+        # long reductions: tensor cores (3xTF32), the row range split over the SMs
+        _call('gpt_linear_wgrad_tf32x3', _ptr(dy), _ptr(x2d), _ptr(flags), _ptr(dw), M, N, K, _stream())
+        return dw
     if accumulate and flags is not None:
         _call('gpt_linear_wgrad_rows_f32', _ptr(dy), _ptr(x2d), _ptr(flags), _ptr(dw), M, N, K, _stream())
         return dw

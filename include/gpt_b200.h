@@ -124,6 +124,13 @@ int gpt_linear_wgrad_f32_acc(const float* dy, const float* x, float* dw, int M, 
  * other rows of dy are exactly zero (K2 backward), so they are never read */
 int gpt_linear_wgrad_rows_f32(const float* dy, const float* x, const uint8_t* flags, float* dw, int M, int N, int K,
                               void* stream);
+/*     the same on the tensor cores (csrc/wgrad_tcgen05.cu): both operands are taken MN-major exactly as they lie in
+ *     HBM (TMA boxes of [32 fp32 x 16 rows] = canonical swizzle atoms, no transposed copy), 3xTF32 (fp32-grade) with the
+ *     fp32 accumulator in tensor memory, the row range split over one CTA per SM, partial sums added into dw with
+ *     vector reductions.  flags may be NULL (every row).  GPT_ERR_UNSUPPORTED when K > 512 or K, N are not multiples of
+ *     4: use gpt_linear_wgrad_rows_f32. */
+int gpt_linear_wgrad_tf32x3(const float* dy, const float* x, const uint8_t* flags, float* dw, long long M, int N, int K,
+                            void* stream);
 /* K3 on the tensor cores: tcgen05.mma kind::tf32, TMA-fed, accumulator in TMEM (GPT_GEMM_TF32, ~1e-3 relative).
  *     Needs K % 4 == 0 (and N % 4 == 0 for dgrad) and 16-byte aligned operands, else GPT_ERR_UNSUPPORTED.
  *     dgrad takes a float [K*N] workspace for the transposed weight. */

@@ -273,6 +273,32 @@ def test_k3_wgrad_over_live_rows(M, N, K, frac):
     assert _rel(dw2, dy.double().t() @ x.double()) <= 1e-5
 
 
+@pytest.mark.parametrize('M,N,K,frac', [(40000, 512, 360, 1.0), (33000, 200, 360, 0.4), (65536 + 5, 512, 512, 0.7),
+                                        (32768, 64, 100, 1.0), (50000, 200, 200, 0.0)])
+def test_k3_wgrad_on_tensor_cores_is_fp32_grade(M, N, K, frac):
+    """csrc/wgrad_tcgen05.cu (MN-major operands straight from HBM, 3xTF32): dw += dy^T x over the live rows, against
+    fp64 at the fp32 parity tolerance (1e-5 relative); rows with flags == 0 may hold anything."""
+    assert ops.wgrad_tc_ok(M, N, K)
+    g = torch.Generator().manual_seed(M + N + K)
+    flags = None
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    if frac < 1.0:
+        flags = (torch.rand(M, generator=g) < frac).to(torch.uint8).to(DEV) * 3
+        dead = flags == 0
+        dy[dead] = float('nan')                       # never accumulated
+        x[dead] = float('inf')
+    live = torch.ones(M, dtype=torch.bool, device=DEV) if flags is None else flags != 0
+    ref = torch.where(live[:, None], dy, torch.zeros_like(dy)).double().t() @ \
+        torch.where(live[:, None], x, torch.zeros_like(x)).double()
+    dw = torch.full((N, K), 0.5, device=DEV)          # accumulates into what is there
+    ops.linear_wgrad(dy, x, 'tf32x3', out=dw, accumulate=True, flags=flags)
+    if frac > 0:
+        assert _rel(dw - 0.5, ref) <= 1e-5
+    else:
+        assert float((dw - 0.5).abs().max()) == 0.0
+
+
 # ---------------------------------------------------------------- K8 (virtual ranks on one GPU) ------------------------
 
 def _sparse_state(emb, words, topn, scale, gen):

@@ -33,13 +33,17 @@ def main():
         w = torch.randn(N, K, device='cuda')
         dy = torch.randn(M, N, device='cuda')
         fl = 2.0 * M * N * K
-        for mode in ('fp32', 'tf32'):
+        for mode in ('fp32', 'tf32', 'tf32x3'):
             t = timeit(lambda: ops.linear_fwd(x, w, mode))
             print('%-22s fwd   %-5s %9.3f ms %8.1f TFLOP/s' % (shp, mode, t, fl / t / 1e9))
             t = timeit(lambda: ops.linear_dgrad(dy, w, mode))
             print('%-22s dgrad %-5s %9.3f ms %8.1f TFLOP/s' % (shp, mode, t, fl / t / 1e9))
-        t = timeit(lambda: ops.linear_wgrad(dy, x))
+        t = timeit(lambda: ops.linear_wgrad(dy, x), reps=3, warm=1)
         print('%-22s wgrad %-5s %9.3f ms %8.1f TFLOP/s' % (shp, 'fp32', t, fl / t / 1e9))
+        if ops.wgrad_tc_ok(M, N, K):
+            dw = torch.zeros(N, K, device='cuda')
+            t = timeit(lambda: ops.linear_wgrad(dy, x, 'tf32x3', out=dw, accumulate=True))
+            print('%-22s wgrad %-5s %9.3f ms %8.1f TFLOP/s' % (shp, 'tf32x3', t, fl / t / 1e9))
         torch.backends.cuda.matmul.allow_tf32 = True
         t = timeit(lambda: torch.matmul(x, w.t()))
         print('%-22s fwd   %-5s %9.3f ms %8.1f TFLOP/s' % (shp, 'cublas-tf32', t, fl / t / 1e9))
