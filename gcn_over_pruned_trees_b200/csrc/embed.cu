@@ -84,6 +84,7 @@ embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned
     unsigned long long seed = 0, step = 0;
     if (drop) { seed = p.rng[0]; step = p.rng[1]; }
     if (threadIdx.x == 0 && word_live && owner != nullptr) atomicMin(owner + w, row);
+    const bool vec_rows = (p.E & 3) == 0 && (reinterpret_cast<uintptr_t>(g_emb) & 15) == 0;   // 16-byte aligned quads
     const float* dr = dx + (size_t)row * D;
     for (int g = threadIdx.x; g * 8 < D; g += kEmbThreads) {
         Philox4 q{0, 0, 0, 0};
@@ -91,19 +92,35 @@ embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned
             q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step, (uint32_t)seed,
                            (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
         const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+        float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int c = g * 8 + k;
-            if (c >= D) break;
-            float v = dr[c];
+            v[k] = c < D ? dr[c] : 0.f;
             if (drop) {
                 const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                v = bits >= p.thresh16 ? v * p.drop_scale : 0.f;
+                v[k] = bits >= p.thresh16 ? v[k] * p.drop_scale : 0.f;
             }
-            if (v == 0.f) continue;
-            if (c < p.E) { if (word_live) atomicAdd(g_emb + (size_t)w * p.E + c, v); }
-            else if (c < p.E + p.Dp) { if (g_pos) atomicAdd(g_pos + (size_t)ps * p.Dp + (c - p.E), v); }
-            else if (g_ner) atomicAdd(g_ner + (size_t)nr * p.Dn + (c - p.E - p.Dp), v);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                   // two quads of columns
+            const int c = g * 8 + 4 * h;
+            if (c >= D) break;
+            if (vec_rows && c + 3 < p.E) {              // whole quad in the word row: one 16-byte reduction
+                if (word_live && (v[4 * h] != 0.f || v[4 * h + 1] != 0.f || v[4 * h + 2] != 0.f || v[4 * h + 3] != 0.f))
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g_emb + (size_t)w * p.E + c),
+                                 "f"(v[4 * h]), "f"(v[4 * h + 1]), "f"(v[4 * h + 2]), "f"(v[4 * h + 3]) : "memory");
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cc = c + k;
+                const float u = v[4 * h + k];
+                if (cc >= D || u == 0.f) continue;
+                if (cc < p.E) { if (word_live) atomicAdd(g_emb + (size_t)w * p.E + cc, u); }
+                else if (cc < p.E + p.Dp) { if (g_pos) atomicAdd(g_pos + (size_t)ps * p.Dp + (cc - p.E), u); }
+                else if (g_ner) atomicAdd(g_ner + (size_t)nr * p.Dn + (cc - p.E - p.Dp), u);
+            }
         }
     }
 }

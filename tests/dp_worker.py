@@ -1,8 +1,16 @@
 """Worker of tests/test_gpu_multi.py: run under torchrun with one process per GPU.
 
 Every rank trains on its shard (rows rank::world) of the same global batches through FusedTrainStep(data_parallel=True)
-(K8: exchange over NVLink peer memory); rank 0 also trains a single-process replica on the full batches.  Checks:
-replicas bit-identical across ranks; parameters equal to the full-batch run within 5e-5 (dropout off)."""
+(K8: exchange over NVLink peer memory); rank 0 also trains a single-process replica on the full batches.  Checks, every
+step: replicas bit-identical across ranks; parameters after the step equal to the full-batch step within 5e-6.
+
+The two runs are compared in LOCKSTEP -- before every step all ranks load the single-process replica's parameters --
+because free-running trajectories are not comparable at this tolerance: a pre-activation of the output MLP that is
+zero to within rounding falls on either side of the ReLU under a 1e-7 perturbation, and that sentence's whole
+contribution to the unit's gradient row flips with it (measured: 2e-7 relative noise on the parameters moves them by
+up to 6e-3 after 8 steps at these sizes, scratch/knife.py).  From identical parameters the
+forward is bit-identical per sentence, so only the summation order of the gradient differs.  The exchange state
+(step parity, slot tables, owner marks, gradient buffers) still carries over from step to step."""
 import os
 import sys
 
@@ -27,34 +35,41 @@ def main():
     tr = GCNTrainer(synth.tacred_opt(**over))
     tr.model.train()
     eng = FusedTrainStep(tr, data_parallel=True, max_rows=8192)
-    losses = []
-    for s in range(steps):
-        shard = parallel.shard_batch(batches[s % 3], rank, world)
-        losses.append(float(eng(shard)))
-    torch.cuda.synchronize()
-    flat = torch.cat([p.detach().reshape(-1) for p in tr.model.parameters()])
-    gathered = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(gathered, flat)
-    identical = all(torch.equal(g, gathered[0]) for g in gathered)
-    mean_loss = torch.tensor(losses, device='cuda')
-    dist.all_reduce(mean_loss)
-    mean_loss /= world
-    ok = identical
-    msg = 'replicas bit-identical: %s' % identical
+    params = list(tr.model.parameters())
+    sizes = [p.numel() for p in params]
+    ref = ref_eng = None
     if rank == 0:
         torch.manual_seed(11)
         ref = GCNTrainer(synth.tacred_opt(**over))
         ref.model.train()
         ref_eng = FusedTrainStep(ref)
-        ref_losses = [float(ref_eng(batches[s % 3])) for s in range(steps)]
-        worst = 0.0
-        for (k, a), (_, b) in zip(tr.model.state_dict().items(), ref.model.state_dict().items()):
-            d = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
-            worst = max(worst, d)
-        loss_err = max(abs(a - b) / abs(b) for a, b in zip(mean_loss.tolist(), ref_losses))
-        ok = ok and worst < 5e-5 and loss_err < 2e-5
-        msg += '; vs full-batch single process: params rel %.2e, loss rel %.2e' % (worst, loss_err)
-        line = 'DP_CHECK %s world=%d %s' % ('OK' if ok else 'FAIL', world, msg)
+    ok, worst, loss_err, identical = True, 0.0, 0.0, True
+    for s in range(steps):
+        vec = torch.empty(sum(sizes), device='cuda')
+        if rank == 0:
+            vec.copy_(torch.cat([p.detach().reshape(-1) for p in ref.model.parameters()]))
+        dist.broadcast(vec, 0)
+        for p, chunk in zip(params, vec.split(sizes)):
+            p.data.copy_(chunk.view_as(p))                    # in place: the step graphs keep their addresses
+        shard = parallel.shard_batch(batches[s % 3], rank, world)
+        loss = eng(shard).clone()
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        identical = identical and all(torch.equal(g, gathered[0]) for g in gathered)
+        dist.all_reduce(loss)
+        loss /= world
+        if rank == 0:
+            ref_loss = float(ref_eng(batches[s % 3]))
+            for a, b in zip(params, ref.model.parameters()):
+                worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+            loss_err = max(loss_err, abs(float(loss) - ref_loss) / abs(ref_loss))
+    ok = identical
+    if rank == 0:
+        ok = ok and worst < 5e-6 and loss_err < 2e-5
+        line = ('DP_CHECK %s world=%d steps=%d (lockstep) replicas bit-identical: %s; vs full-batch single process: '
+                'params rel %.2e, loss rel %.2e' % ('OK' if ok else 'FAIL', world, steps, identical, worst, loss_err))
         print(line, flush=True)
         out_dir = os.path.join(REPO, 'gpurun_out')
         if os.path.isdir(out_dir):
