@@ -373,6 +373,55 @@ def run_b200(args):
         eager_s = timed_host_loop(eager_step, n_eager)
         e2e['dropin_eager'] = {'value': BATCH * world * n_eager / eager_s, 'ms_per_step': eager_s / n_eager * 1e3,
                                'api': 'reference call sequence train.py:213-227 on the new model package, eager'}
+    # ---- K9: batches assembled on the device from a resident token arena ----------------------
+    loader_info = None
+    if fused and not args.eager:
+        from gcn_over_pruned_trees_b200.data.loader import DataLoader as DeviceLoader
+        examples = []
+        for bt in host_tuples:
+            lens = (~bt[1]).sum(1).tolist()
+            for r, n in enumerate(lens):
+                examples.append(tuple(bt[f][r, :n].tolist() for f in (0, 2, 3, 4, 5, 6, 7)) + (int(bt[8][r]),))
+        _stdout = sys.stdout
+        sys.stdout = open(os.devnull, 'w')
+        dl = DeviceLoader.from_processed(examples, BATCH, {'word_dropout': 0.04, 'lower': False, 'dataset': 'tacred'},
+                                         evaluation=False, device=dev, seed=1234 + rank)
+        sys.stdout = _stdout
+        n_dl = len(dl)
+        for i in range(4 * n_dl):                           # every batch shape captured before timing
+            step.step_from(dl, i % n_dl)
+        torch.cuda.synchronize()
+        parallel.barrier()
+        total = 0.0
+        for i in range(args.steps):
+            flush.fill_(0.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step.step_from(dl, i % n_dl).item()
+            total += time.perf_counter() - t0
+        parallel.barrier()
+        total = parallel.max_over_ranks(total, dev)
+        e2e['device_loader'] = {'value': BATCH * world * args.steps / total, 'ms_per_step': total / args.steps * 1e3,
+                                'h2d_bytes_per_step': 0,
+                                'api': 'loss = engine.step_from(loader, i): K9 writes the batch from the resident token arena '
+                                       '(word dropout on) into the static input buffer, then one CUDA-graph replay + '
+                                       'loss.item()'}
+        if rank == 0:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(dl.RING * n_dl):                 # fill every shape's buffer ring first
+                dl.packed(i % n_dl)
+            torch.cuda.synchronize()
+            ea.record()
+            for i in range(200):
+                dl.packed(i % n_dl)
+            eb.record()
+            torch.cuda.synchronize()
+            tokens = sum(len(e[0]) for e in examples) / n_dl
+            width = sum(b[2] for b in dl.batches) / n_dl
+            loader_info = {'kernel': 'build_batch_kernel (K9)', 'us_per_batch_incl_launch_gap': ea.elapsed_time(eb) / 200 * 1e3,
+                           'algorithmic_bytes_per_batch': int(tokens * 28 + 57 * BATCH * width + 12 * BATCH),
+                           'bound': 'launch latency (0.2 MB per batch)'}
+
     if world > 1:
         parallel.barrier()
         torch.distributed.destroy_process_group()
@@ -416,12 +465,22 @@ def run_b200(args):
         cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
                'ms_per_step': r['ms_per_step'], 'tree_adj_ms_per_batch': r['tree_adj_ms']}
 
+    if loader_info is not None and not args.no_cpu_baseline and world == 1:
+        from oracle import loader_oracle            # the reference loader's per-batch Python work, restated
+        t0 = time.perf_counter()
+        n_cpu = 0
+        while time.perf_counter() - t0 < 2.0:
+            k = n_cpu % (len(examples) // BATCH)
+            loader_oracle.get_batch(examples[k * BATCH:(k + 1) * BATCH], False, 0.04)
+            n_cpu += 1
+        loader_info['cpu_port_us_per_batch'] = (time.perf_counter() - t0) / n_cpu * 1e6
+        loader_info['cpu_port'] = 'oracle/loader_oracle.get_batch (data/loader.py:81-141 restated), 1 thread, host tensors only'
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'gpu_launches_per_step': launches / args.steps, 'wall_ms_per_step_incl_flush': wall / args.steps * 1e3,
-            'roofline': roof, 'cpu_baseline': cpu, 'kernels': kernels}
+            'roofline': roof, 'cpu_baseline': cpu, 'loader': loader_info, 'kernels': kernels}
     print(json.dumps(line))
 
 

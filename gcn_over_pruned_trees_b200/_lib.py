@@ -59,6 +59,7 @@ SIGNATURES = {
     'gpt_dp_signal': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p],
     'gpt_dp_reduce': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p],
     'gpt_dp_apply': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_f, _c_f, _p, _p, _p],
+    'gpt_build_batch': [_p, _p, _p, _p, _c_int, _c_int, _c_f, ctypes.c_uint64, ctypes.c_uint64, _p, _p, _p, _p],
     'gpt_update_partials': [_c_ll, _c_int],
     'gpt_update_sqnorm': [_p, _c_ll, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_update_apply': [_p, _p, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _c_f, _p, _p, _p],

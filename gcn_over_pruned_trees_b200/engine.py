@@ -470,6 +470,20 @@ class FusedTrainStep(object):
         return entry['loss']
 
     @torch.no_grad()
+    def step_from(self, loader, key):
+        """One training step on batch ``key`` of a device-resident loader (data/loader.py): K9 writes the batch
+        straight into the captured step's static input buffer -- no copy at all -- and the graph is replayed."""
+        _, n, T, _, _ = loader.batches[key]
+        entry = self._graphs.get(((n, T), 8 if loader.tacred else 7))
+        lr = self.trainer.optimizer.param_groups[0]['lr']
+        if entry is None or lr != self._lr:
+            return self(loader.packed(key))
+        loader.packed(key, out=entry['packed'])
+        entry['graph'].replay()
+        self.replays += 1
+        return entry['loss']
+
+    @torch.no_grad()
     def gradients(self, batch):
         """Run forward + backward only (eager, no update) and return {parameter name: gradient clone}, the word-embedding
         gradient as a dense tensor; the gradient buffers are left zeroed.  For tests."""

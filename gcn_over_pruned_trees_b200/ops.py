@@ -589,3 +589,25 @@ def aggregate_bwd_pre(g, csr, use_adj=True, dbias_out=None, force_vec=0):
     _call('gpt_gcn_aggregate_bwd_pre', _ptr(g), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom), _ptr(dy),
           _ptr(dbias_out), B, T, H, int(bool(use_adj)), int(force_vec), _stream())
     return dy
+
+
+# ---- K9: device-resident batch builder ------------------------------------------------------------------------------
+
+def build_batch(arena, offsets, labels, sel, B, T, word_dropout, seed, stream_id, out, masks, rels):
+    """One loader batch from the token arena (csrc/batch.cu).  arena / out: 7 entries (int32 / int64 device tensors,
+    None for an absent NER field) in the order words, pos, ner, deprel, head, subj_pos, obj_pos."""
+    import ctypes
+    for t in [a for a in arena if a is not None] + [offsets, labels, sel, masks, rels] + [o for o in out if o is not None]:
+        if not t.is_cuda:
+            raise _lib.GptError('build_batch needs CUDA tensors: the gpt_b200 path has no CPU fallback')
+    a = (ctypes.c_void_p * 7)(*[_ptr(t) for t in arena])
+    o = (ctypes.c_void_p * 7)(*[_ptr(t) for t in out])
+    _call('gpt_build_batch', a, _ptr(offsets), _ptr(labels), _ptr(sel), int(B), int(T), float(word_dropout),
+          int(seed) & 0xffffffffffffffff, int(stream_id) & 0xffffffffffffffff, o, _ptr(masks), _ptr(rels), _stream())
+
+
+def build_batch_raw(arena_arr, offsets_ptr, labels_ptr, sel_ptr, B, T, word_dropout, seed, stream_id, out_arr,
+                    masks_ptr, rels_ptr):
+    """build_batch with every pointer already resolved (the loader caches them: this runs once per training step)."""
+    _call('gpt_build_batch', arena_arr, offsets_ptr, labels_ptr, sel_ptr, int(B), int(T), float(word_dropout),
+          int(seed) & 0xffffffffffffffff, int(stream_id) & 0xffffffffffffffff, out_arr, masks_ptr, rels_ptr, _stream())

@@ -235,6 +235,17 @@ int gpt_dp_apply(void* region, int W, int cap_rows, int E, int V, long long n_fl
                  float* emb_w, const float* partials, float max_norm, float lr, float* total_norm,
                  uint64_t* step_counter, void* stream);
 
+/* K9. device-resident batch builder (csrc/batch.cu): DataLoader.__getitem__ of the reference (data/loader.py:81-141,
+ *     semeval_loader.py:75-119) from a token arena in HBM.  arena[7] = host array of device pointers to int32 arrays
+ *     indexed by token {words, pos, ner, deprel, head, subj_pos, obj_pos} (ner NULL for 9-tuple batches), offsets int64
+ *     [n_sentences+1], labels int32 [n_sentences], sel int32 [B] = the batch's sentence ids in output row order
+ *     (the caller sorts by length, loader.py:176-180).  Writes out[7] int64 [B,T] (pad 0; 150 for the two position
+ *     fields), masks uint8 [B,T] = (t >= len), rels int64 [B].  word_dropout > 0: a token != <UNK> becomes <UNK>
+ *     with that probability (loader.py:181-188), Philox stream keyed by (seed, stream_id, sentence, token). */
+int gpt_build_batch(const int32_t* const* arena, const int64_t* offsets, const int32_t* labels, const int32_t* sel,
+                    int B, int T, float word_dropout, uint64_t seed, uint64_t stream_id, int64_t* const* out,
+                    uint8_t* masks, int64_t* rels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
