@@ -49,7 +49,7 @@ class GraphedTrainStep(object):
         plain_sgd = isinstance(opt, torch.optim.SGD) and all(
             g.get('momentum', 0) == 0 and g.get('weight_decay', 0) == 0 and not g.get('nesterov', False) and
             not g.get('maximize', False) for g in opt.param_groups)
-        if not (plain_sgd and emb.requires_grad and emb.is_cuda and self.reducer is None) or self.opt.get('rnn', False):
+        if not (plain_sgd and emb.requires_grad and emb.is_cuda and self.reducer is None):
             return None
         state = ops.SparseEmbeddingState(emb.data, self.opt['topn'])
         gcn.sparse_embedding = state

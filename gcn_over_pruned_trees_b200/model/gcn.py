@@ -15,6 +15,7 @@ import sys
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 try:                                    # imported as gcn_over_pruned_trees_b200.model.gcn
     from .. import constant, ops, torch_utils
@@ -149,7 +150,37 @@ class GCN(nn.Module):
         return module(x)
 
     def encode_with_rnn(self, rnn_inputs, masks, batch_size):
-        seq_lens = masks.eq(constant.PAD_ID).long().sum(1).cpu()      # reference gcn.py:186-197
+        """BiLSTM over the padded batch (reference gcn.py:186-197: pack_padded_sequence -> nn.LSTM -> pad_packed_sequence),
+        same arithmetic WITHOUT leaving the device: the reference needs the lengths on the host to pack, which costs a
+        synchronisation and makes cuDNN's descriptors data dependent (no CUDA-graph capture).  An LSTM is causal, so a
+        forward pass over the padded rows is exact on the real tokens; the backward direction runs as a forward LSTM
+        (with the ``_reverse`` weights) over each sentence reversed inside its own length -- a gather with an index
+        built on the device -- and is un-reversed by the same gather.  Padded positions are zeroed, as
+        pad_packed_sequence does.  Still cuDNN (torch._VF.lstm), two unidirectional calls per layer."""
+        B, T, _ = rnn_inputs.shape
+        H, L = self.opt['rnn_hidden'], self.opt['rnn_layers']
+        lens = masks.eq(constant.PAD_ID).sum(1, keepdim=True)                        # [B,1], stays on the device
+        t = torch.arange(T, device=rnn_inputs.device).unsqueeze(0)                   # [1,T]
+        valid = t < lens                                                             # [B,T]
+        rev = torch.where(valid, lens - 1 - t, t)                                    # an involution on every row
+        h0 = rnn_inputs.new_zeros((1, B, H))                                         # rnn_zero_state, gcn.py:485-492
+        x = rnn_inputs
+        for l in range(L):
+            names = ['weight_ih_l%d', 'weight_hh_l%d', 'bias_ih_l%d', 'bias_hh_l%d']
+            w_f = [getattr(self.rnn, n % l) for n in names]
+            w_b = [getattr(self.rnn, (n % l) + '_reverse') for n in names]
+            idx = rev.unsqueeze(2).expand(-1, -1, x.size(2))
+            out_f = torch._VF.lstm(x, (h0, h0), w_f, True, 1, 0.0, self.training, False, True)[0]
+            out_b = torch._VF.lstm(x.gather(1, idx), (h0, h0), w_b, True, 1, 0.0, self.training, False, True)[0]
+            out_b = out_b.gather(1, rev.unsqueeze(2).expand(-1, -1, H))
+            x = torch.cat([out_f, out_b], dim=2) * valid.unsqueeze(2).to(out_f.dtype)
+            if l < L - 1 and self.training and self.opt['rnn_dropout'] > 0:          # nn.LSTM's inter-layer dropout
+                x = F.dropout(x, self.opt['rnn_dropout'], True)
+        return x
+
+    def encode_with_rnn_packed(self, rnn_inputs, masks, batch_size):
+        """The reference's own sequence of calls (gcn.py:186-197); kept for the parity test of encode_with_rnn."""
+        seq_lens = masks.eq(constant.PAD_ID).long().sum(1).cpu()
         h0, c0 = rnn_zero_state(batch_size, self.opt['rnn_hidden'], self.opt['rnn_layers'],
                                 use_cuda=rnn_inputs.is_cuda)
         packed = nn.utils.rnn.pack_padded_sequence(rnn_inputs, seq_lens, batch_first=True, enforce_sorted=False)

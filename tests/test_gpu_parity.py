@@ -558,3 +558,40 @@ def test_tf32_operands_are_truncated_not_rounded():
     y = ops.linear_fwd(x, w, 'tf32')
     want = (x[:4, 0].view(torch.int32) & -8192).view(torch.float32)
     assert torch.equal(y[:4, 0], want)
+
+
+# ---------------------------------------------------------------- C-GCN encoder without leaving the device -----------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('layers', (1, 2))
+def test_device_resident_bilstm_equals_the_packed_sequence_path(layers, monkeypatch):
+    """GCN.encode_with_rnn (two unidirectional cuDNN LSTMs over the padded batch, the backward direction on sentences
+    reversed inside their own length) == the reference's pack_padded_sequence -> nn.LSTM -> pad_packed_sequence
+    (gcn.py:186-197): outputs and every gradient, ragged lengths including length 1 and full width."""
+    torch.manual_seed(layers)
+    monkeypatch.setattr(torch.backends.cudnn, 'allow_tf32', False)     # cuDNN's LSTM GEMMs in fp32 on both paths
+    opt = synth.tacred_opt(vocab_size=300, cuda=True, rnn=True, rnn_hidden=48, rnn_layers=layers, rnn_dropout=0.0)
+    model = GCNTrainer(opt).model.gcn_model.gcn
+    B, T, D = 9, 23, model.rnn.input_size
+    lens = torch.tensor([23, 17, 17, 9, 5, 2, 1, 1, 12])
+    masks = (torch.arange(T)[None, :] >= lens[:, None]).cuda()
+    x1 = torch.randn(B, T, D, device='cuda', requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_()
+    g = torch.randn(B, T, 96, device='cuda')
+    for training in (False, True):
+        model.train(training)
+        a = model.encode_with_rnn(x1, masks, B)
+        b = model.encode_with_rnn_packed(x2, masks, B)
+        assert a.shape == b.shape == (B, T, 96)
+        # cuDNN runs different algorithms for packed and padded inputs (observed 8e-6 at |out| <= 1, with or without
+        # TF32); the end-to-end bound is the 1e-5 logits parity of cfg3 against the reference (test_model_*)
+        assert float((a - b).abs().max()) <= 2e-5
+        assert float(a[masks].abs().max()) == 0.0                      # padded positions are zero
+    model.zero_grad()
+    (a * g).sum().backward()
+    ga = {n: p.grad.clone() for n, p in model.rnn.named_parameters()}
+    model.zero_grad()
+    (b * g).sum().backward()
+    for n, p in model.rnn.named_parameters():
+        assert float((ga[n] - p.grad).abs().max()) <= 1e-4 * max(1.0, float(p.grad.abs().max())), n
+    assert float((x1.grad - x2.grad).abs().max()) <= 1e-4
