@@ -23,6 +23,8 @@ SIGNATURES = {
     'gpt_prune_csr': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     'gpt_gcn_aggregate_fwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p,
                               _c_int, _p],
+    'gpt_gcn_aggregate_fwd_pool': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p],
+    'gpt_gcn_aggregate_fwd_pool_supported': [_c_int, _c_int, _c_int],
     'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
     'gpt_gcn_aggregate_bwd_pre': [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_pool3_bwd_masked': [_p, _p, _p, _p, _p, _c_f, _c_int, _c_int, _c_int, _c_int, _p, _p],
@@ -38,6 +40,7 @@ SIGNATURES = {
     'gpt_linear_fwd_tf32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_tf32': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_weight_prep_tf32x3': [_p, _p, _c_int, _c_int, _p],
+    'gpt_weight_prep_tf32x3_batch': [_p, _p, _p, _p, _c_int, _p],
     'gpt_linear_fwd_tf32x3': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_tf32x3': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_embed_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p],

@@ -44,6 +44,8 @@ struct AggParams {
     const float* bias;   // [H] (fwd)
     float* out;          // [B*T, H]
     float* dbias;        // [H] (bwd, atomically accumulated)
+    float* pool_out;     // fwd, optional: [B, 3H] masked max pools of the layer output (K4 fused, see POOL)
+    int* pool_arg;       // fwd, optional: [B, 3H] their argmax rows (-1: empty pool)
     const float* drop_mask;              // optional explicit, pre-scaled mask [B*T, H]
     const unsigned long long* rng;       // optional {seed, step} on the device
     int B, T, H, cap, use_adj, nbuf;
@@ -123,10 +125,11 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
 //   meta [T+1]            .x = CSR row start | (row length << 16), .y = bits of 1/denom (0: unobservable row)
 //   perm [..]             row ids sorted by row length (longest first), padded with T
 //   col  [4T+4]           16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
+//   pool [NT/32][3][HS]x2 forward with fused pooling: per-warp partial (max, argmax) of the three pools
 //   actb [T][8]           forward, when the activation mask is written: one byte per (row, lane of the row's group)
 //                         holding that lane's 4 activation bits; packed into the row's 32-bit word after the slice
 struct Layout {
-    size_t tile, red, bits, bias, meta, perm, col, actb, total;  // byte offsets
+    size_t tile, red, bits, bias, meta, perm, col, actb, pool, total;  // byte offsets
 };
 __host__ __device__ inline size_t tile_floats(int T, int lpr) { return (size_t)(T + 1) * 4 * lpr; }
 __host__ __device__ inline int perm_len(int T, int groups) {
@@ -134,7 +137,7 @@ __host__ __device__ inline int perm_len(int T, int groups) {
 }
 __host__ __device__ inline int bits_stride(int T, int lpr) { return ((T * ((4 * lpr + 31) / 32) + 3) / 4) * 4; }
 __host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int nbuf, bool fwd, bool bits,
-                                              bool actb = false) {
+                                              bool actb = false, bool pool = false) {
     const int groups = (nt / 32) * (32 / lpr), hs = 4 * lpr;
     Layout L;
     size_t o = 0;
@@ -148,6 +151,7 @@ __host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int
     L.col = o;  o += (size_t)(4 * T + 4) * 2;
     o = (o + 7) / 8 * 8;
     L.actb = o; o += actb ? (size_t)T * 8 : 0;
+    L.pool = o; o += pool ? (size_t)(nt / 32) * 3 * hs * 8 : 0;   // per-warp (value, argmax) partials of the fused pools
     L.total = (o + 15) / 16 * 16;
     return L;
 }
@@ -254,15 +258,20 @@ __host__ __device__ inline size_t act_index(int b, int T, int H, int sl) {
 
 enum { DROP_NONE = 0, DROP_PHILOX = 1, DROP_MASK = 2 };
 
-template <int LPR, int NT, bool ALIGNED, int DROP>
+// POOL: the CTA holds every row of its column slice, so the three masked max pools of the layer output
+// (/root/reference/model/gcn.py:116-121, K4) fall out of the same pass: each thread keeps (max, argmax) of its 4 columns
+// over the rows it serves, lane groups meet by shuffles, warps in shared memory.  Ties keep the smallest row, an empty
+// pool yields -1e12 / -1, exactly as pool3_fwd_kernel.  p.out may then be null: the layer output itself is not stored.
+template <int LPR, int NT, bool ALIGNED, int DROP, bool POOL = false>
 __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
+    GPT_PDL_TRIGGER();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW, WPR = (HS + 31) / 32;
     const int T = p.T, H = p.H;
     const int b = blockIdx.y;
     const int nsl = (H + HS - 1) / HS;
     const bool write_act = (p.act_out != nullptr) && (LPR == 8);
-    const Layout L = make_layout(T, H, LPR, NT, p.nbuf, true, DROP == DROP_PHILOX, write_act);
+    const Layout L = make_layout(T, H, LPR, NT, p.nbuf, true, DROP == DROP_PHILOX, write_act, POOL);
     float* tile0 = reinterpret_cast<float*>(smem_raw + L.tile);
     uint32_t* keepw = reinterpret_cast<uint32_t*>(smem_raw + L.bits);
     float* bias_sm = reinterpret_cast<float*>(smem_raw + L.bias);
@@ -274,10 +283,23 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
     const uint32_t tile_s0 = smem_u32(tile0), tile_bytes = (uint32_t)tile_stride * 4u;
     const float* yb = p.y + (size_t)b * T * H;
 
-    issue_slice<LPR, NT, ALIGNED>(yb, tile_s0, T, H, blockIdx.x);
-    cp_async_commit();
+    // the CSR (K1, joined long before this launch) and the bias are not products of the preceding grid: staged while
+    // it drains; y is, so its first slice is requested after the wait
+    // Small tiles (NT == 256, a launch-latency-bound step): staged before the wait, so that it overlaps the tail of the
+    // preceding grid.  Large tiles (NT == 512, bandwidth-bound): the first slice is requested first and the staging
+    // overlaps its flight instead.
+    if (NT == 512) {
+        GPT_PDL_WAIT();
+        issue_slice<LPR, NT, ALIGNED>(yb, tile_s0, T, H, blockIdx.x);
+        cp_async_commit();
+    }
     stage_meta<true, NT>(p, b, tile0, tile_stride, meta, perm, perm_len(T, GROUPS), colv, HS);
     for (int c = threadIdx.x; c < nsl * HS; c += NT) bias_sm[c] = (c < H) ? 2.0f * p.bias[c] : 0.f;
+    if (NT != 512) {
+        GPT_PDL_WAIT();
+        issue_slice<LPR, NT, ALIGNED>(yb, tile_s0, T, H, blockIdx.x);
+        cp_async_commit();
+    }
 
     // ---- per-thread constants ---------------------------------------------------------------------------------
     const int cl = (lane % LPR) * 4, sub = lane / LPR;
@@ -287,6 +309,15 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
     const uint32_t bias_s = smem_u32(bias_sm), keep_s = smem_u32(keepw), actb_s = smem_u32(smem_raw + L.actb);
     const unsigned thresh = p.thresh16;
     const float dscale = p.drop_scale;
+
+    float pool_v[POOL ? 3 : 1][4];
+    int pool_a[POOL ? 3 : 1][4];
+    if (POOL) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { pool_v[POOL ? k : 0][v] = -1e12f; pool_a[POOL ? k : 0][v] = -1; }
+    }
 
     int it = 0;
     for (int sl = blockIdx.x; sl < nsl; sl += gridDim.x, ++it) {
@@ -384,7 +415,24 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
                             if (c_lane + v < H) res[v] *= m[v];
                     }
                 }
-                if (live) store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
+                if (live && p.out != nullptr)
+                    store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
+                if (POOL && live) {
+                    const unsigned f = p.flags[(size_t)b * T + i];       // bit0 in tree, bit1 subject, bit2 object
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (f & (1u << k)) {
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const int kk = POOL ? k : 0;
+                                if (res[v] > pool_v[kk][v] || (res[v] == pool_v[kk][v] && i < pool_a[kk][v])) {
+                                    pool_v[kk][v] = res[v];
+                                    pool_a[kk][v] = i;
+                                }
+                            }
+                        }
+                    }
+                }
                 if (write_act && i < T) {  // CTA-uniform; LPR == 8: this lane's 4 activation bits, packed after the slice
                     const uint32_t nib = (res[0] > 0.f ? 1u : 0u) | (res[1] > 0.f ? 2u : 0u) | (res[2] > 0.f ? 4u : 0u) |
                                          (res[3] > 0.f ? 8u : 0u);
@@ -393,6 +441,42 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
             }
         }
         __syncthreads();  // everyone is done with this buffer / keep-words before the next iteration refills them
+        if (POOL) {      // (one slice per CTA in this mode, see dispatch)
+            float* s_pv = reinterpret_cast<float*>(smem_raw + L.pool);
+            int* s_pa = reinterpret_cast<int*>(s_pv + (NT / 32) * 3 * HS);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    float val = pool_v[POOL ? k : 0][v];
+                    int arg = pool_a[POOL ? k : 0][v];
+#pragma unroll
+                    for (int o = LPR; o < 32; o <<= 1) {                 // the lane groups of the warp share the columns
+                        const float ov = __shfl_xor_sync(GPT_FULL_MASK, val, o);
+                        const int oa = __shfl_xor_sync(GPT_FULL_MASK, arg, o);
+                        if (ov > val || (ov == val && oa >= 0 && (arg < 0 || oa < arg))) { val = ov; arg = oa; }
+                    }
+                    if (sub == 0) {
+                        s_pv[(warp * 3 + k) * HS + cl + v] = val;
+                        s_pa[(warp * 3 + k) * HS + cl + v] = arg;
+                    }
+                }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < 3 * HS; idx += NT) {
+                const int k = idx / HS, c = idx - k * HS;
+                float val = s_pv[k * HS + c];
+                int arg = s_pa[k * HS + c];
+                for (int w = 1; w < NT / 32; ++w) {
+                    const float ov = s_pv[(w * 3 + k) * HS + c];
+                    const int oa = s_pa[(w * 3 + k) * HS + c];
+                    if (ov > val || (ov == val && oa >= 0 && (arg < 0 || oa < arg))) { val = ov; arg = oa; }
+                }
+                if (col0 + c < H) {
+                    p.pool_out[(size_t)b * 3 * H + (size_t)k * H + col0 + c] = val;
+                    p.pool_arg[(size_t)b * 3 * H + (size_t)k * H + col0 + c] = arg;
+                }
+            }
+        }
         if (write_act) {
             // the row's 8 nibbles -> its 32-bit activation word, stored in row order (coalesced); the barrier after the
             // next slice has landed orders these reads before the next writes of actb
@@ -407,6 +491,7 @@ __global__ void __launch_bounds__(NT) aggregate_fwd_kernel(const AggParams p) {
 
 template <int LPR, int NT, bool ALIGNED>
 __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
+    GPT_PDL_TRIGGER();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW;
     const int T = p.T, H = p.H;
@@ -444,8 +529,15 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
         issue_slice<LPR, NT, ALIGNED>(gb, tile_s0 + (uint32_t)buf * tile_bytes, T, H, sl);
         cp_async_commit();
     };
-    issue(0, blockIdx.x);
+    if (NT == 512) {    // large tiles: first slice in flight while the CSR is staged (see the forward)
+        GPT_PDL_WAIT();
+        issue(0, blockIdx.x);
+    }
     stage_meta<false, NT>(p, b, tile0, tile_stride, meta, perm, perm_len(T, GROUPS), colv, HS);
+    if (NT != 512) {
+        GPT_PDL_WAIT();     // (CSR staged while the preceding grid drains; its product, the incoming gradient, after)
+        issue(0, blockIdx.x);
+    }
 
     const int cl = (lane % LPR) * 4, sub = lane / LPR;
     const uint32_t meta_s = smem_u32(meta), col_s = smem_u32(colv), perm_s = smem_u32(perm);
@@ -557,7 +649,8 @@ AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
     AggConfig c{};
     auto slices = [&](int lpr) { return (H + 4 * lpr - 1) / (4 * lpr); };
     auto bytes = [&](int lpr, int nt, int nbuf) {
-        return make_layout(T, H, lpr, nt, nbuf, fwd, fwd ? philox : (act && lpr == 8), fwd && act && lpr == 8).total;
+        return make_layout(T, H, lpr, nt, nbuf, fwd, fwd ? philox : (act && lpr == 8), fwd && act && lpr == 8,
+                           fwd && p.pool_out != nullptr).total;
     };
     if (force_vec == 1 || ((force_vec == 2 || force_vec == 4) && !act)) {
         c.lpr = 8 * force_vec; c.nt = 256; c.nbuf = 1; c.grid_x = slices(c.lpr);
@@ -595,7 +688,7 @@ int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, cudaStream_t
         if (a != cudaSuccess) return (int)a;
         have = c.smem;
     }
-    kernel<<<dim3(c.grid_x, p.B), c.nt, c.smem, st>>>(p);
+    gpt_launch(kernel, dim3(c.grid_x, p.B), dim3(c.nt), c.smem, st, p);
     return gpt_launch_status();
 }
 
@@ -605,6 +698,10 @@ int launch(bool fwd, const AggConfig& c, const AggParams& p, cudaStream_t st) {
     if (p.drop_mask != nullptr) return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_MASK>, c, p, st);
     if (p.rng != nullptr && p.thresh16 > 0)
         return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_PHILOX>, c, p, st);
+    if (p.pool_out != nullptr) {
+        if (LPR == 8 && NT == 256) return launch_kernel(aggregate_fwd_kernel<8, 256, ALIGNED, DROP_NONE, true>, c, p, st);
+        return GPT_ERR_UNSUPPORTED;
+    }
     return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_NONE>, c, p, st);
 }
 
@@ -653,6 +750,35 @@ extern "C" int gpt_gcn_aggregate_fwd(const float* y, const int32_t* rowptr, cons
     p.subseq = subseq & 0xfffu;
     set_dropout(p, drop_p);
     return dispatch(true, p, force_vec, (cudaStream_t)stream);
+}
+
+// K2 forward of the LAST layer fused with K4 (max pooling): writes pooled [B,3H] / argmax [B,3H] (+ the activation
+// mask); `out` may be NULL when the layer output itself is not needed.  GPT_ERR_UNSUPPORTED when the sentence tile is
+// too large for the one-slice-per-CTA configuration (callers then run gpt_gcn_aggregate_fwd + gpt_pool3_fwd).
+extern "C" int gpt_gcn_aggregate_fwd_pool(const float* y, const int32_t* rowptr, const int32_t* col,
+                                          const float* denom, const uint8_t* flags, const float* bias, float* out,
+                                          uint32_t* act_mask, float* pooled, int32_t* argmax, int B, int T, int H,
+                                          int use_adj, void* stream) {
+    GPT_CHECK_ARG(y && rowptr && col && denom && flags && bias && act_mask && pooled && argmax);
+    GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && H < (1 << 20));
+    if (B == 0) return GPT_OK;
+    if (B > 65535) return GPT_ERR_UNSUPPORTED;
+    AggParams p{};
+    p.y = y; p.rowptr = rowptr; p.col = col; p.denom = denom; p.flags = flags; p.bias = bias; p.out = out;
+    p.act_out = act_mask; p.pool_out = pooled; p.pool_arg = argmax;
+    p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
+    set_dropout(p, 0.f);
+    return dispatch(true, p, 0, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_gcn_aggregate_fwd_pool_supported(int B, int T, int H) {
+    if (B < 1 || B > 65535 || T < 1 || H < 1 || 4 * T + 4 > 65535) return 0;
+    AggParams p{};
+    p.B = B; p.T = T; p.H = H;
+    p.act_out = reinterpret_cast<uint32_t*>(1);      // only null-ness is looked at by pick_config
+    p.pool_out = reinterpret_cast<float*>(1);
+    const AggConfig c = pick_config(p, true, 0);
+    return (c.nt == 256 && c.lpr == 8) ? 1 : 0;
 }
 
 extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* act_mask,

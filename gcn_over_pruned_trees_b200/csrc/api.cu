@@ -3,6 +3,12 @@
 
 unsigned long long g_gpt_launches = 0;
 
+#include <cstdlib>
+int g_gpt_pdl = [] {
+    const char* e = getenv("GPT_PDL");
+    return (e == nullptr || atoi(e) != 0) ? 1 : 0;
+}();
+
 extern "C" int gpt_version(void) { return 100; }
 
 extern "C" unsigned long long gpt_launch_count(void) { return g_gpt_launches; }

@@ -36,6 +36,7 @@ struct EmbParams {
 // one CTA per token row; thread c handles column group c*8 .. c*8+7 (one Philox call per thread)
 __global__ void __launch_bounds__(kEmbThreads)
 embed_fwd_kernel(const EmbParams p, float* __restrict__ x) {
+    GPT_PDL_ENTER();
     const int row = blockIdx.x;
     const int D = p.E + p.Dp + p.Dn;
     const long long w = p.words[row];
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(kEmbThreads)
 embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned char* __restrict__ flags,
                  float* __restrict__ g_emb, float* __restrict__ g_pos, float* __restrict__ g_ner,
                  int* __restrict__ owner, int topn) {
+    GPT_PDL_ENTER();
     const int row = blockIdx.x;
     if (flags != nullptr && flags[row] == 0) return;  // unobservable token: its gradient row is exactly zero
     const int D = p.E + p.Dp + p.Dn;
@@ -194,7 +196,7 @@ extern "C" int gpt_embed_fwd(const int64_t* words, const int64_t* pos, const int
     int rc = fill_params(p, words, pos, ner, emb_w, pos_w, ner_w, n_rows, V, E, Dp, Dn, drop_p, rng_state, subseq);
     if (rc != GPT_OK || x == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
     if (n_rows == 0) return GPT_OK;
-    embed_fwd_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(p, x);
+    gpt_launch(embed_fwd_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream, p, x);
     return gpt_launch_status();
 }
 
@@ -208,7 +210,7 @@ extern "C" int gpt_embed_bwd(const float* dx, const uint8_t* flags, const int64_
                          drop_p, rng_state, subseq);
     if (rc != GPT_OK || dx == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
     if (n_rows == 0) return GPT_OK;
-    embed_bwd_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(p, dx, flags, g_emb, g_pos, g_ner, owner,
+    gpt_launch(embed_bwd_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream, p, dx, flags, g_emb, g_pos, g_ner, owner,
                                                                        topn < V ? topn : V);
     return gpt_launch_status();
 }

@@ -237,10 +237,17 @@ wgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
             __syncthreads();
         }
     }
+    const bool vec_out = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && (k0 + tx * 4 + 3 < K);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int n = n0 + ty * 4 + i;
         if (n >= N) continue;
+        if (vec_out) {           // one 16-byte reduction instead of four atomics (the partial sums of all splits meet in L2)
+            if (acc[i][0] != 0.f || acc[i][1] != 0.f || acc[i][2] != 0.f || acc[i][3] != 0.f)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + (size_t)n * K + k0 + tx * 4),
+                             "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = k0 + tx * 4 + j;

@@ -34,7 +34,8 @@ constexpr int BM = 128;        // rows per CTA tile (UMMA M)
 constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
 constexpr int kMaxStages = 8;   // ring depth is chosen at launch: as many stages as fit in shared memory
-constexpr int kGemmThreads = 192;
+constexpr int kSplitWarps = 8;          // warps 2..9: operand split (3xTF32) during the main loop, then the epilogue
+constexpr int kGemmThreads = 64 + 32 * kSplitWarps;
 
 // Optional epilogue of the data-gradient GEMM: the consumer of dX is K2's backward of the previous layer, whose first
 // step is g = dX * dropscale * [out > 0] / denom.  Doing it here, where every thread already holds 32 consecutive
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
                  int n_tiles, int tmem_cols, int STAGES, const MaskEpilogue ep) {
+    GPT_PDL_TRIGGER();
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_holder;
@@ -134,7 +136,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
-            mbar_init(split0 + 8 * s, 128);   // the four splitter warps
+            mbar_init(split0 + 8 * s, 32 * kSplitWarps);   // every splitter thread arrives
         }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,6 +150,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_holder;
+    GPT_PDL_WAIT();     // barriers, tensor memory and descriptors are ready; only now are the operands (and C) touched
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -193,21 +196,25 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     } else {
         if (PASSES == 3) {
             // ===== splitters: A -> A_hi (in place), A_lo = A - A_hi, element-wise in the swizzled tile =====
-            const uint32_t t = threadIdx.x - 64;       // 0..127
+            const uint32_t t = threadIdx.x - 64;       // 0..255: 16-byte chunk t, t + 256, ... of the A tile
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
                 const uint32_t src = tiles + (uint32_t)s * stage_bytes + t * 16u, dst = src + off_alo;
+                constexpr uint32_t kIters = (BM * BK * 4) / (32 * kSplitWarps * 16);
+                float4 v[kIters];
 #pragma unroll
-                for (uint32_t i = 0; i < a_bytes / (128 * 16); ++i) {
-                    float4 v;
+                for (uint32_t i = 0; i < kIters; ++i)       // all loads of the thread in flight together
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + i * 2048u));
-                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + i * 2048u), "f"(h.x), "f"(h.y),
-                                 "f"(h.z), "f"(h.w) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * 2048u), "f"(v.x - h.x),
-                                 "f"(v.y - h.y), "f"(v.z - h.z), "f"(v.w - h.w) : "memory");
+                                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                                 : "r"(src + i * (32u * kSplitWarps * 16u)));
+#pragma unroll
+                for (uint32_t i = 0; i < kIters; ++i) {
+                    const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + i * (32u * kSplitWarps * 16u)),
+                                 "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * (32u * kSplitWarps * 16u)),
+                                 "f"(v[i].x - h.x), "f"(v[i].y - h.y), "f"(v[i].z - h.z), "f"(v[i].w - h.w) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core
                 mbar_arrive(split0 + 8 * s);
@@ -227,7 +234,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             ep_inv = __frcp_rn(ep.denom[row]);
             ep_words = ep.act + ((size_t)bb * ((N + 31) / 32)) * ep.T + tt;
         }
-        for (int c0 = 0; c0 < n_tile; c0 += 32) {
+        // warps 2..5 take the first half of the tile's 32-column blocks, warps 6..9 the second half
+        const int nblk = (n_tile + 31) / 32, half_blk = (nblk + 1) / 2;
+        const int c_begin = (warp - 2) < 4 ? 0 : half_blk * 32, c_end = (warp - 2) < 4 ? min(n_tile, half_blk * 32) : n_tile;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             asm volatile(
@@ -348,7 +358,7 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
         configured = smem;
     }
     dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles));
-    tf32_gemm_kernel<PASSES><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
+    gpt_launch(tf32_gemm_kernel<PASSES>, grid, dim3(kGemmThreads), smem, st, tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
                                                                tmem_cols, stages, ep);
     return gpt_launch_status();
 }
@@ -406,6 +416,43 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restric
     }
 }
 
+// every layer's weight in one launch (blockIdx.z = layer): the side stream that prepares the operands then needs one
+// launch latency instead of one per layer before the first projection may start
+struct PrepBatch {
+    const float* w[8];
+    float* ws[8];
+    int N[8], K[8];
+};
+__global__ void weight_prep_batch_kernel(const PrepBatch b) {
+    __shared__ float th[32][33], tl[32][33];
+    const int l = blockIdx.z;
+    const float* __restrict__ w = b.w[l];
+    float* __restrict__ ws = b.ws[l];
+    const int N = b.N[l], K = b.K[l];
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    if (blockIdx.x * 32 >= K || y0 >= N) return;              // (CTA-uniform) this layer's matrix is smaller than the grid
+    const size_t nk = (size_t)N * K;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        if (x < K && y0 + j < N) {
+            const size_t i = (size_t)(y0 + j) * K + x;
+            const float v = w[i], h = tf32_hi(v);
+            ws[i] = h;
+            ws[nk + i] = v - h;
+            th[j][threadIdx.x] = h;
+            tl[j][threadIdx.x] = v - h;
+        }
+    }
+    __syncthreads();
+    const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        if (ox < N && oy0 + j < K) {
+            const size_t o = (size_t)(oy0 + j) * N + ox;
+            ws[2 * nk + o] = th[threadIdx.x][j];
+            ws[3 * nk + o] = tl[threadIdx.x][j];
+        }
+    }
+}
+
 int split_hi_lo(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {  // hi may alias in
     tf32_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, hi, lo, n);
     return gpt_launch_status();
@@ -435,6 +482,22 @@ extern "C" int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx,
 extern "C" int gpt_weight_prep_tf32x3(const float* w, float* ws, int N, int K, void* stream) {
     GPT_CHECK_ARG(w && ws && N >= 1 && K >= 1);
     weight_prep_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(w, ws, N, K);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_weight_prep_tf32x3_batch(const float* const* w, float* const* ws, const int* N, const int* K,
+                                            int n_layers, void* stream) {
+    GPT_CHECK_ARG(w && ws && N && K && n_layers >= 1 && n_layers <= 8);
+    PrepBatch b{};
+    int max_n = 0, max_k = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        GPT_CHECK_ARG(w[l] && ws[l] && N[l] >= 1 && K[l] >= 1);
+        b.w[l] = w[l]; b.ws[l] = ws[l]; b.N[l] = N[l]; b.K[l] = K[l];
+        max_n = N[l] > max_n ? N[l] : max_n;
+        max_k = K[l] > max_k ? K[l] : max_k;
+    }
+    weight_prep_batch_kernel<<<dim3((max_k + 31) / 32, (max_n + 31) / 32, n_layers), dim3(32, 8), 0,
+                               (cudaStream_t)stream>>>(b);
     return gpt_launch_status();
 }
 

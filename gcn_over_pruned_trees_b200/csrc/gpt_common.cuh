@@ -20,6 +20,44 @@
 // number of kernels this library has launched (host-side counter, read through gpt_launch_count())
 extern unsigned long long g_gpt_launches;
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// A training step is a chain of ~15 short dependent kernels; between two of them the GPU otherwise idles for the
+// launch latency of the next grid.  Kernels launched through gpt_launch() carry
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next grid may be set up and its CTAs made resident while the
+// previous one is still running.  Every such kernel starts with GPT_PDL_ENTER(): `griddepcontrol.wait` blocks until
+// the preceding grid has COMPLETED and its memory is visible (so nothing about data dependencies changes, reads and
+// writes alike), `griddepcontrol.launch_dependents` lets the grid after this one start its own launch.  Captured
+// into a CUDA graph these become programmatic edges.  GPT_PDL=0 in the environment launches without the attribute.
+#define GPT_PDL_ENTER()                                                   \
+    do {                                                                  \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
+    } while (0)
+
+// Kernels whose prologue touches nothing the preceding grid produces (shared-memory / tensor-memory set-up, reads of
+// data that older grids wrote) trigger first, run the prologue, and only then wait -- the prologue overlaps the tail of
+// the preceding grid.  Global WRITES always come after the wait (the preceding grid may still read a recycled buffer).
+#define GPT_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define GPT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+extern int g_gpt_pdl;
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gpt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_gpt_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // call once after every <<<>>> launch
 static inline int gpt_launch_status() {
     ++g_gpt_launches;

@@ -188,6 +188,7 @@ __device__ __forceinline__ void dense_dgrad(cg::cluster_group& cluster, const fl
 template <int R>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 head_fwd_bwd_kernel(const HeadParams p) {
+    GPT_PDL_ENTER();
     extern __shared__ __align__(16) float smem[];
     const int H = p.H, C = p.C, K0 = 3 * p.H, L = p.n_mlp;
     const int Cp = (C + 3) & ~3;
@@ -453,13 +454,15 @@ extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, cons
     cfg.blockDim = dim3(kHeadThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_gpt_pdl ? 2 : 1;
     if (R == 1) e = cudaLaunchKernelEx(&cfg, head_fwd_bwd_kernel<1>, p);
     else if (R == 2) e = cudaLaunchKernelEx(&cfg, head_fwd_bwd_kernel<2>, p);
     else e = cudaLaunchKernelEx(&cfg, head_fwd_bwd_kernel<4>, p);

@@ -25,6 +25,7 @@ template <int V>   // V = 4: H % 4 == 0, float4 columns; V = 1: any H
 __global__ void __launch_bounds__(kPoolFwdThreads)
 pool3_fwd_kernel(const float* __restrict__ h, const unsigned char* __restrict__ flags, int T, int H, int type,
                  float* __restrict__ out, int* __restrict__ argmax) {
+    GPT_PDL_ENTER();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_n, s_cnt[3];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kPoolThreads)
 pool3_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
                  const unsigned char* __restrict__ flags, int T, int H, int type, float* __restrict__ dh,
                  const uint32_t* __restrict__ act, const float* __restrict__ denom, float scale) {
+    GPT_PDL_ENTER();
     extern __shared__ unsigned char s_flags[];
     const int b = blockIdx.y;
     int cnt[3] = {0, 0, 0};
@@ -186,8 +188,8 @@ extern "C" int gpt_pool3_fwd(const float* h, const uint8_t* flags, int B, int T,
         if (e != cudaSuccess) return (int)e;
         configured[vec] = smem;
     }
-    if (vec) pool3_fwd_kernel<4><<<B, kPoolFwdThreads, smem, (cudaStream_t)stream>>>(h, flags, T, H, pool_type, out, argmax);
-    else pool3_fwd_kernel<1><<<B, kPoolFwdThreads, smem, (cudaStream_t)stream>>>(h, flags, T, H, pool_type, out, argmax);
+    if (vec) gpt_launch(pool3_fwd_kernel<4>, dim3(B), dim3(kPoolFwdThreads), smem, (cudaStream_t)stream, h, flags, T, H, pool_type, out, argmax);
+    else gpt_launch(pool3_fwd_kernel<1>, dim3(B), dim3(kPoolFwdThreads), smem, (cudaStream_t)stream, h, flags, T, H, pool_type, out, argmax);
     return gpt_launch_status();
 }
 
@@ -199,7 +201,7 @@ extern "C" int gpt_pool3_bwd(const float* gout, const int32_t* argmax, const uin
     if (B == 0) return GPT_OK;
     if (B > 65535 || T > 48 * 1024) return GPT_ERR_UNSUPPORTED;
     dim3 grid((H + kPoolThreads - 1) / kPoolThreads, B);
-    pool3_bwd_kernel<<<grid, kPoolThreads, T, (cudaStream_t)stream>>>(gout, argmax, flags, T, H, pool_type, dh, nullptr,
+    gpt_launch(pool3_bwd_kernel, grid, dim3(kPoolThreads), (size_t)T, (cudaStream_t)stream, gout, argmax, flags, T, H, pool_type, dh, nullptr,
                                                                       nullptr, 1.f);
     return gpt_launch_status();
 }
@@ -213,7 +215,7 @@ extern "C" int gpt_pool3_bwd_masked(const float* gout, const int32_t* argmax, co
     if (B == 0) return GPT_OK;
     if (B > 65535 || T > 48 * 1024) return GPT_ERR_UNSUPPORTED;
     dim3 grid((H + kPoolThreads - 1) / kPoolThreads, B);
-    pool3_bwd_kernel<<<grid, kPoolThreads, T, (cudaStream_t)stream>>>(gout, argmax, flags, T, H, pool_type, g, act,
+    gpt_launch(pool3_bwd_kernel, grid, dim3(kPoolThreads), (size_t)T, (cudaStream_t)stream, gout, argmax, flags, T, H, pool_type, g, act,
                                                                       denom, drop_scale);
     return gpt_launch_status();
 }

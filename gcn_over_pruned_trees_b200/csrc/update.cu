@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kUpdThreads)
 update_sqnorm_kernel(const float* __restrict__ grad, long long n, const long long* __restrict__ words,
                      const int* __restrict__ owner, const float* __restrict__ g_emb, int n_rows, int E, int topn,
                      int dense_blocks, float* __restrict__ partials) {
+    GPT_PDL_ENTER();
     __shared__ float s_red[kUpdWarps];
     float s = 0.f;
     if ((int)blockIdx.x < dense_blocks) {
@@ -85,6 +86,7 @@ update_apply_kernel(float* __restrict__ param, float* __restrict__ grad, long lo
                     float* __restrict__ emb_w, int n_rows, int E, int topn, int dense_blocks,
                     const float* __restrict__ partials, int n_partials, float max_norm, float lr, float grad_scale,
                     float* __restrict__ total_norm, unsigned long long* __restrict__ step_counter) {
+    GPT_PDL_ENTER();
     __shared__ float s_red[kUpdWarps];
     __shared__ float s_coef;
     if (blockIdx.x == 0 && threadIdx.x == 0 && step_counter != nullptr) *step_counter += 1ull;
@@ -190,7 +192,7 @@ extern "C" int gpt_update_sqnorm(const float* grad, long long n, const int64_t* 
     const int blocks = plan(n, n_rows, &d, &r);
     if (blocks == 0) return GPT_OK;
     if (blocks > kMaxPartials) return GPT_ERR_UNSUPPORTED;
-    update_sqnorm_kernel<<<blocks, kUpdThreads, 0, (cudaStream_t)stream>>>(
+    gpt_launch(update_sqnorm_kernel, dim3(blocks), dim3(kUpdThreads), 0, (cudaStream_t)stream, 
         grad, n, reinterpret_cast<const long long*>(words), owner, g_emb, n_rows, E, topn, d, partials);
     return gpt_launch_status();
 }
@@ -206,7 +208,7 @@ extern "C" int gpt_update_apply(float* param, float* grad, long long n, const in
     int d, r;
     const int blocks = plan(n, n_rows, &d, &r);
     if (blocks == 0) return GPT_OK;
-    update_apply_kernel<<<blocks, kUpdThreads, 0, (cudaStream_t)stream>>>(
+    gpt_launch(update_apply_kernel, dim3(blocks), dim3(kUpdThreads), 0, (cudaStream_t)stream, 
         param, grad, n, reinterpret_cast<const long long*>(words), owner, g_emb, emb_w, n_rows, E, topn, d, partials,
         blocks, max_norm, lr, grad_scale, total_norm, reinterpret_cast<unsigned long long*>(step_counter));
     return gpt_launch_status();

@@ -339,6 +339,7 @@ class FusedTrainStep(object):
             main.wait_event(ev)
 
         n_layers = len(gcn.W)
+        fuse_pool = ptype == ops.POOL_TYPES['max'] and ops.aggregate_pool_ok(B, T, H)
         csr = ops.TreeCSR(B, T, words.device)
         wss = [ops.weight_prep_buffer(lin.weight.data, mode) for lin in gcn.W]
         keep += [csr, wss]
@@ -348,12 +349,13 @@ class FusedTrainStep(object):
         with torch.cuda.stream(sa):
             ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'], out=csr)
         with torch.cuda.stream(sb):
+            ops.weight_prep_all([lin.weight.data for lin in gcn.W], mode, wss)    # one launch: the first GEMM waits for it
+            ev_prep = torch.cuda.Event()
+            ev_prep.record(sb)
             ops.l2_prefetch(fl.param)            # every dense weight: first touches later in the step hit L2
-            for lin, ws in zip(gcn.W, wss):
-                ops.weight_prep(lin.weight.data, mode, out=ws)
         x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
                           None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
-        join(sb)
+        main.wait_event(ev_prep)                 # (the prefetch behind it is joined at the end of the step)
         xs, acts = [], []
         h = x
         for l, lin in enumerate(gcn.W):
@@ -361,10 +363,15 @@ class FusedTrainStep(object):
             if l == 0:
                 join(sa)
             xs.append(h)
+            if l == n_layers - 1 and fuse_pool:     # last layer: K2 + K4 in one launch, h itself is never stored
+                pooled, argmax, act, _ = ops.aggregate_fwd_pool(y, csr, lin.bias.data, use_adj)
+                acts.append(act)
+                break
             h, act = ops.aggregate_fwd(y, csr, lin.bias.data, use_adj, 0.0 if l == n_layers - 1 else p_gcn, rng, l,
                                        None, want_act=True)
             acts.append(act)
-        pooled, argmax = ops.pool3_fwd(h, csr, ptype)
+        if not fuse_pool:
+            pooled, argmax = ops.pool3_fwd(h, csr, ptype)
         buf = ops.HeadBuffers(B, H, self.cls.weight.shape[0], len(self.mlp), words.device)
         ops.head_fwd_bwd(pooled, labels, [m.weight.data for m in self.mlp], [m.bias.data for m in self.mlp],
                          self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=True)

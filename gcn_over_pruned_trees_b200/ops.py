@@ -152,6 +152,22 @@ def weight_prep(weight, mode, out=None):
     return ws
 
 
+def weight_prep_all(weights, mode, outs):
+    """weight_prep for every layer in one launch; layers whose shape has no tensor-core path (out is None) are skipped."""
+    import ctypes
+    todo = [(w, o) for w, o in zip(weights, outs) if o is not None]
+    if mode != 'tf32x3' or not todo:
+        return
+    n = len(todo)
+    if n > 8:
+        for w, o in todo:
+            weight_prep(w, mode, out=o)
+        return
+    _call('gpt_weight_prep_tf32x3_batch', (ctypes.c_void_p * n)(*[_ptr(w) for w, _ in todo]),
+          (ctypes.c_void_p * n)(*[_ptr(o) for _, o in todo]), (ctypes.c_int * n)(*[w.shape[0] for w, _ in todo]),
+          (ctypes.c_int * n)(*[w.shape[1] for w, _ in todo]), n, _stream())
+
+
 def linear_fwd(x2d, weight, mode='fp32', ws=None):
     """y = x W^T.  'tf32x3': tcgen05/TMEM GEMM fed by TMA, 3xTF32 (fp32-grade); 'tf32': one TF32 pass; 'fp32': FFMA.
     The tensor-core modes fall back to FFMA when the shape cannot be described to TMA (row pitch % 16 B != 0)."""
@@ -189,7 +205,8 @@ def linear_dgrad(dy, weight, mode='fp32', ws=None):
     return dx
 
 
-WGRAD_TC_MIN_ROWS = 32768     # below this the FFMA kernel over the live rows wins (TACRED-shaped batches: ~2 750 rows)
+import os as _os
+WGRAD_TC_MIN_ROWS = int(_os.environ.get('GPT_WGRAD_TC_MIN_ROWS', 32768))   # below: FFMA kernel over the live rows
 
 
 def wgrad_tc_ok(M, N, K):
@@ -216,6 +233,24 @@ def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False, flags=None):
 
 
 # ---- K2: aggregation -----------------------------------------------------------------------------------------
+
+def aggregate_pool_ok(B, T, H):
+    """True when K2's last-layer forward can also produce the three max pools (csrc/aggregate.cu, POOL mode)."""
+    return bool(_lib.lib().gpt_gcn_aggregate_fwd_pool_supported(int(B), int(T), int(H)))
+
+
+def aggregate_fwd_pool(y, csr, bias, use_adj=True, want_out=False):
+    """K2 forward of the last layer fused with K4 (max): -> (pooled [B,3H], argmax [B,3H], act mask, out or None)."""
+    B, T = csr.B, csr.T
+    H = y.shape[-1]
+    out = torch.empty((B, T, H), dtype=torch.float32, device=y.device) if want_out else None
+    act = torch.empty((B * ((H + 31) // 32) * T,), dtype=torch.int32, device=y.device)
+    pooled = torch.empty((B, 3 * H), dtype=torch.float32, device=y.device)
+    argmax = torch.empty((B, 3 * H), dtype=torch.int32, device=y.device)
+    _call('gpt_gcn_aggregate_fwd_pool', _ptr(y), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom), _ptr(csr.flags),
+          _ptr(bias), _ptr(out), _ptr(act), _ptr(pooled), _ptr(argmax), B, T, H, int(bool(use_adj)), _stream())
+    return pooled, argmax, act, out
+
 
 def aggregate_fwd(y, csr, bias, use_adj=True, drop_p=0.0, rng_state=None, subseq=0, drop_mask=None, force_vec=0,
                   want_act=False):

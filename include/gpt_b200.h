@@ -90,6 +90,15 @@ int gpt_gcn_aggregate_fwd(const float* y, const int32_t* rowptr, const int32_t* 
  *     g_i = gout_i * dropscale * [out_i > 0] / denom_i ; dy_j = g_j + sum_{i in row j} g_i ; dbias += 2*sum_i g_i
  * [out_i > 0] is read from act_mask when it is not NULL, else from `out` (one of the two is required).
  * dbias (float [H]) is accumulated atomically and must be zeroed by the caller; may be NULL. */
+/*     Last layer fused with K4 (max pooling): same arithmetic, plus pooled [B,3H] = [h_out | subj_out | obj_out] and
+ *     argmax int32 [B,3H] exactly as gpt_pool3_fwd(type max) would produce them from the layer output (ties: smallest
+ *     row; empty pool: -1e12 / -1).  out may be NULL (the layer output is then never stored).  No dropout (the last
+ *     layer has none, gcn.py:393).  gpt_gcn_aggregate_fwd_pool_supported(B,T,H) = 1 when the sentence tile fits the
+ *     one-slice-per-CTA configuration this mode needs; otherwise the call returns GPT_ERR_UNSUPPORTED. */
+int gpt_gcn_aggregate_fwd_pool(const float* y, const int32_t* rowptr, const int32_t* col, const float* denom,
+                               const uint8_t* flags, const float* bias, float* out, uint32_t* act_mask, float* pooled,
+                               int32_t* argmax, int B, int T, int H, int use_adj, void* stream);
+int gpt_gcn_aggregate_fwd_pool_supported(int B, int T, int H);
 int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* act_mask, const int32_t* rowptr,
                           const int32_t* col, const float* denom, float* dy, float* dbias, int B, int T, int H,
                           int use_adj, float drop_p, const float* drop_mask, int force_vec, void* stream);
@@ -142,6 +151,9 @@ int gpt_linear_dgrad_tf32(const float* dy, const float* w, float* dx, float* wt_
  *     gpt_weight_prep_tf32x3 splits / transposes the weight once per step into ws = float [4*N*K]
  *     ([w_hi | w_lo | w^T_hi | w^T_lo]); fwd and dgrad then take ws in place of w. */
 int gpt_weight_prep_tf32x3(const float* w, float* ws, int N, int K, void* stream);
+/*     the same for n_layers <= 8 weights in one launch (host arrays of device pointers / sizes) */
+int gpt_weight_prep_tf32x3_batch(const float* const* w, float* const* ws, const int* N, const int* K, int n_layers,
+                                 void* stream);
 int gpt_linear_fwd_tf32x3(const float* x, const float* ws, float* y, int M, int N, int K, void* stream);
 int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* dx, int M, int N, int K, void* stream);
 /* dgrad with the previous layer's K2-backward prologue in the epilogue: g = (dy . w) * drop_scale_prev *

@@ -299,6 +299,35 @@ def test_k3_wgrad_on_tensor_cores_is_fp32_grade(M, N, K, frac):
         assert float((dw - 0.5).abs().max()) == 0.0
 
 
+# ---------------------------------------------------------------- K2 (last layer) + K4 in one launch ------------------
+
+@pytest.mark.parametrize('B,T,H,k,seed', [(50, 64, 200, 1, 0), (50, 96, 200, -1, 1), (7, 33, 64, 0, 2), (20, 40, 100, 2, 3),
+                                          (16, 24, 36, 1, 4)])
+def test_k2_last_layer_with_fused_max_pooling_equals_k2_then_k4(B, T, H, k, seed):
+    """gpt_gcn_aggregate_fwd_pool == gpt_gcn_aggregate_fwd followed by gpt_pool3_fwd(max): layer output, activation
+    mask, pooled values and argmax rows bit for bit (ties, empty pools and entity tokens outside the tree included)."""
+    assert ops.aggregate_pool_ok(B, T, H)
+    batch = synth.make_batch(900 + seed, batch_size=B, vocab_size=500, pad_to=T, max_len=T, mean_len=min(36, T // 2))
+    dev = [t.to(DEV) for t in batch[:8]]
+    csr = ops.prune_csr(dev[5], dev[6], dev[7], dev[4], dev[1], k)
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(B * T, H, generator=g).to(DEV)
+    y[torch.rand(B * T, generator=g).to(DEV) < 0.1] = 0.0          # whole rows of zeros: ties at the ReLU floor
+    bias = (torch.randn(H, generator=g) * 0.1).to(DEV)
+    out_ref, act_ref = ops.aggregate_fwd(y, csr, bias, want_act=True)
+    pooled_ref, arg_ref = ops.pool3_fwd(out_ref, csr, ops.POOL_TYPES['max'])
+    pooled, argmax, act, out = ops.aggregate_fwd_pool(y, csr, bias, want_out=True)
+    assert torch.equal(out, out_ref) and torch.equal(act, act_ref)
+    assert torch.equal(pooled, pooled_ref)
+    assert torch.equal(argmax, arg_ref)
+    pooled2, argmax2, act2, none = ops.aggregate_fwd_pool(y, csr, bias)       # without storing the layer output
+    assert none is None and torch.equal(pooled2, pooled_ref) and torch.equal(argmax2, arg_ref) and torch.equal(act2, act_ref)
+
+
+def test_fused_pooling_is_declined_for_large_sentence_tiles():
+    assert not ops.aggregate_pool_ok(64, 512, 512)
+
+
 # ---------------------------------------------------------------- K8 (virtual ranks on one GPU) ------------------------
 
 def _sparse_state(emb, words, topn, scale, gen):
