@@ -25,6 +25,7 @@ SIGNATURES = {
                               _c_int, _p],
     'gpt_gcn_aggregate_fwd_pool': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_gcn_aggregate_fwd_pool_supported': [_c_int, _c_int, _c_int],
+    'gpt_gcn_aggregate_bwd_pool': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
     'gpt_gcn_aggregate_bwd_pre': [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_pool3_bwd_masked': [_p, _p, _p, _p, _p, _c_f, _c_int, _c_int, _c_int, _c_int, _p, _p],

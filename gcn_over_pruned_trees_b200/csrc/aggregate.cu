@@ -46,6 +46,8 @@ struct AggParams {
     float* dbias;        // [H] (bwd, atomically accumulated)
     float* pool_out;     // fwd, optional: [B, 3H] masked max pools of the layer output (K4 fused, see POOL)
     int* pool_arg;       // fwd, optional: [B, 3H] their argmax rows (-1: empty pool)
+    const float* pool_g;       // bwd, optional: d loss / d pooled [B, 3H]: the incoming gradient is built from it,
+    const int* pool_arg_in;    //      the argmax rows and the activation bits in shared memory (K4's backward fused)
     const float* drop_mask;              // optional explicit, pre-scaled mask [B*T, H]
     const unsigned long long* rng;       // optional {seed, step} on the device
     int B, T, H, cap, use_adj, nbuf;
@@ -515,6 +517,7 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
     // 16-byte async copies of the activation words need T % 4 == 0 and an aligned source
     const bool act16 = use_act && (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.act_in) & 15) == 0);
 
+    const bool from_pool = p.pool_g != nullptr;     // the gradient arrives as d(pooled), not as a [B,T,H] tensor
     // the slice's activation words travel in the same cp.async group as the slice itself
     auto issue = [&](int buf, int sl) {
         if (use_act) {
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
                 for (int q = tid; q < T; q += NT) cp_async4(dst + (uint32_t)q * 4u, src + q);
             }
         }
-        issue_slice<LPR, NT, ALIGNED>(gb, tile_s0 + (uint32_t)buf * tile_bytes, T, H, sl);
+        if (!from_pool) issue_slice<LPR, NT, ALIGNED>(gb, tile_s0 + (uint32_t)buf * tile_bytes, T, H, sl);
         cp_async_commit();
     };
     if (NT == 512) {    // large tiles: first slice in flight while the CSR is staged (see the forward)
@@ -558,7 +561,33 @@ __global__ void __launch_bounds__(NT) aggregate_bwd_kernel(const AggParams p) {
         const int col0 = sl * HS;
         const uint32_t tile_s = tile_s0 + (uint32_t)(it & 1) * tile_bytes;
         const uint32_t actw_s = actw_s0 + (uint32_t)((it & 1) * actw_stride) * 4u;
-        if (!p.pre_scaled) {
+        if (from_pool) {
+            // g = dh * [out > 0] / denom with dh = scatter of d(pooled) to the argmax rows (pool3_bwd_kernel's
+            // arithmetic, same order of operations): at most three non-zero entries per column
+            for (int q = tid; q < T * LPR; q += NT) sts128(tile_s + (uint32_t)q * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
+            __syncthreads();
+            if (tid < HS && col0 + tid < H) {
+                const size_t o = (size_t)b * 3 * H + col0 + tid;
+                float v[3];
+                int r[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { v[k] = p.pool_g[o + (size_t)k * H]; r[k] = p.pool_arg_in[o + (size_t)k * H]; }
+                if (r[1] == r[0] && r[1] >= 0) { v[0] += v[1]; r[1] = -1; }
+                if (r[2] >= 0) {
+                    if (r[2] == r[0]) { v[0] += v[2]; r[2] = -1; }
+                    else if (r[2] == r[1]) { v[1] += v[2]; r[2] = -1; }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (r[k] < 0 || r[k] >= T) continue;
+                    const uint32_t w = lds32(actw_s + (uint32_t)r[k] * 4u) >> tid;       // LPR == 8: HS == 32
+                    const float inv = __uint_as_float(lds64(meta_s + (uint32_t)r[k] * 8u).y);
+                    const float g = v[k] * ((float)(w & 1u) * ds) * inv;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile_s + (uint32_t)(r[k] * HS + tid) * 4u), "f"(g) : "memory");
+                }
+            }
+            __syncthreads();
+        } else if (!p.pre_scaled) {
 #pragma unroll 2
         for (int q = tid; q < T * LPR; q += NT) {
             const int row = q / LPR, cc = (q % LPR) * 4, c = col0 + cc;
@@ -797,6 +826,23 @@ extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const 
     // same scale the forward applied to kept elements (dropped ones have out == 0 / a clear activation bit)
     set_dropout(p, drop_mask == nullptr ? drop_p : 0.f);
     return dispatch(false, p, force_vec, (cudaStream_t)stream);
+}
+
+// K2 backward of the LAST layer fused with K4's backward (max pooling): the incoming gradient is d(pooled) [B,3H] +
+// argmax [B,3H]; g = scatter(d pooled) * [out > 0] / denom is formed in shared memory, never in HBM.
+extern "C" int gpt_gcn_aggregate_bwd_pool(const float* dpooled, const int32_t* argmax, const uint32_t* act_mask,
+                                          const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
+                                          float* dbias, int B, int T, int H, int use_adj, void* stream) {
+    GPT_CHECK_ARG(dpooled && argmax && act_mask && rowptr && col && denom && dy);
+    GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1);
+    if (B == 0) return GPT_OK;
+    if (B > 65535) return GPT_ERR_UNSUPPORTED;
+    AggParams p{};
+    p.y = dpooled; p.act_in = act_mask; p.rowptr = rowptr; p.col = col; p.denom = denom; p.out = dy; p.dbias = dbias;
+    p.pool_g = dpooled; p.pool_arg_in = argmax;
+    p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
+    set_dropout(p, 0.f);
+    return dispatch(false, p, 0, (cudaStream_t)stream);
 }
 
 extern "C" int gpt_gcn_aggregate_bwd_pre(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom,

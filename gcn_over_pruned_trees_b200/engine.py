@@ -383,10 +383,12 @@ class FusedTrainStep(object):
                            fl.g(self.cls.weight), fl.g(self.cls.bias))
         # K2's backward prologue (g = d * dropscale * [out > 0] / denom) is fused into whatever produces d: K4's backward
         # for the last layer, the dgrad GEMM's epilogue below it; ('dh', .) marks a gradient that still needs it
-        cur = ('g', ops.pool3_bwd_masked(buf.dpooled, argmax, csr, ptype, H, acts[-1], 0.0))
+        cur = ('pool', None) if fuse_pool else ('g', ops.pool3_bwd_masked(buf.dpooled, argmax, csr, ptype, H, acts[-1], 0.0))
         for l in range(n_layers - 1, -1, -1):
             lin = gcn.W[l]
-            if cur[0] == 'g':
+            if cur[0] == 'pool':                # K4's backward inside K2's: the [B,T,H] gradient never exists
+                dy = ops.aggregate_bwd_pool(buf.dpooled, argmax, acts[-1], csr, H, use_adj, dbias_out=fl.g(lin.bias))
+            elif cur[0] == 'g':
                 dy = ops.aggregate_bwd_pre(cur[1], csr, use_adj, dbias_out=fl.g(lin.bias))
             else:
                 dy, _ = ops.aggregate_bwd(cur[1], None, csr, use_adj, 0.0 if l == n_layers - 1 else p_gcn, None,

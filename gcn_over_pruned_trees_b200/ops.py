@@ -239,6 +239,15 @@ def aggregate_pool_ok(B, T, H):
     return bool(_lib.lib().gpt_gcn_aggregate_fwd_pool_supported(int(B), int(T), int(H)))
 
 
+def aggregate_bwd_pool(dpooled, argmax, act, csr, H, use_adj=True, dbias_out=None):
+    """K4 backward (max) + K2 backward of the last layer in one launch: d(pooled) [B,3H] -> dy [B*T, H]."""
+    B, T = csr.B, csr.T
+    dy = torch.empty((B * T, H), dtype=torch.float32, device=dpooled.device)
+    _call('gpt_gcn_aggregate_bwd_pool', _ptr(dpooled), _ptr(argmax), _ptr(act), _ptr(csr.rowptr), _ptr(csr.col),
+          _ptr(csr.denom), _ptr(dy), _ptr(dbias_out), B, T, H, int(bool(use_adj)), _stream())
+    return dy
+
+
 def aggregate_fwd_pool(y, csr, bias, use_adj=True, want_out=False):
     """K2 forward of the last layer fused with K4 (max): -> (pooled [B,3H], argmax [B,3H], act mask, out or None)."""
     B, T = csr.B, csr.T

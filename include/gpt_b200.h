@@ -99,6 +99,11 @@ int gpt_gcn_aggregate_fwd_pool(const float* y, const int32_t* rowptr, const int3
                                const uint8_t* flags, const float* bias, float* out, uint32_t* act_mask, float* pooled,
                                int32_t* argmax, int B, int T, int H, int use_adj, void* stream);
 int gpt_gcn_aggregate_fwd_pool_supported(int B, int T, int H);
+/*     Last layer's backward fused with K4's backward (max pooling): takes d(pooled) [B,3H] and argmax [B,3H] instead of
+ *     a [B,T,H] gradient; equals gpt_pool3_bwd_masked followed by gpt_gcn_aggregate_bwd_pre bit for bit. */
+int gpt_gcn_aggregate_bwd_pool(const float* dpooled, const int32_t* argmax, const uint32_t* act_mask,
+                               const int32_t* rowptr, const int32_t* col, const float* denom, float* dy, float* dbias,
+                               int B, int T, int H, int use_adj, void* stream);
 int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* act_mask, const int32_t* rowptr,
                           const int32_t* col, const float* denom, float* dy, float* dbias, int B, int T, int H,
                           int use_adj, float drop_p, const float* drop_mask, int force_vec, void* stream);

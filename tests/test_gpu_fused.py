@@ -324,6 +324,31 @@ def test_k2_last_layer_with_fused_max_pooling_equals_k2_then_k4(B, T, H, k, seed
     assert none is None and torch.equal(pooled2, pooled_ref) and torch.equal(argmax2, arg_ref) and torch.equal(act2, act_ref)
 
 
+@pytest.mark.parametrize('B,T,H,k,seed', [(50, 64, 200, 1, 0), (50, 96, 200, -1, 1), (7, 33, 64, 0, 2), (20, 40, 100, 2, 3),
+                                          (6, 512, 96, -1, 5)])
+def test_k2_last_layer_backward_with_fused_pool_backward_equals_k4_then_k2(B, T, H, k, seed):
+    """gpt_gcn_aggregate_bwd_pool == gpt_pool3_bwd_masked + gpt_gcn_aggregate_bwd_pre, bit for bit (dy and dbias),
+    including pools that share an argmax row, empty pools (argmax -1) and the large-tile configuration."""
+    batch = synth.make_batch(950 + seed, batch_size=B, vocab_size=500, pad_to=T, max_len=T, mean_len=min(36, T // 2))
+    dev = [t.to(DEV) for t in batch[:8]]
+    csr = ops.prune_csr(dev[5], dev[6], dev[7], dev[4], dev[1], k)
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(B * T, H, generator=g).to(DEV)
+    bias = (torch.randn(H, generator=g) * 0.1).to(DEV)
+    out, act = ops.aggregate_fwd(y, csr, bias, want_act=True)
+    pooled, argmax = ops.pool3_fwd(out, csr, ops.POOL_TYPES['max'])
+    argmax[0, :5] = -1                                              # an empty pool
+    argmax[1 % B, H:H + 7] = argmax[1 % B, 0:7]                     # two pools meeting in one row
+    dpooled = torch.randn(B, 3 * H, generator=g).to(DEV)
+    db_ref = torch.zeros(H, device=DEV)
+    gg = ops.pool3_bwd_masked(dpooled, argmax, csr, ops.POOL_TYPES['max'], H, act, 0.0)
+    dy_ref = ops.aggregate_bwd_pre(gg, csr, dbias_out=db_ref)
+    db = torch.zeros(H, device=DEV)
+    dy = ops.aggregate_bwd_pool(dpooled, argmax, act, csr, H, dbias_out=db)
+    assert torch.equal(dy.view(-1), dy_ref.view(-1))
+    assert float((db - db_ref).abs().max()) <= 1e-5 * max(1.0, float(db_ref.abs().max()))   # atomics: order only
+
+
 def test_fused_pooling_is_declined_for_large_sentence_tiles():
     assert not ops.aggregate_pool_ok(64, 512, 512)
 
