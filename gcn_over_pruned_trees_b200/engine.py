@@ -12,6 +12,8 @@ the SGD update -- is captured once per batch shape into a CUDA graph and replaye
 the trainer API keep working), same loss value.  Data-parallel runs split the step into two graphs around the
 gradient all-reduce (backward | all-reduce | clip + update).
 """
+import os
+
 import torch
 
 from .model.trainer import unpack_batch
@@ -273,6 +275,9 @@ class FusedTrainStep(object):
         self.kernels_per_replay = {}
         self.replays = 0
         self.side = (torch.cuda.Stream(), torch.cuda.Stream())
+        # the step is captured on a high-priority stream: when a side branch (weight gradients, K1) and the chain of
+        # data-dependent kernels compete for SMs, the chain goes first
+        self.capture_stream = torch.cuda.Stream(priority=-1) if os.environ.get('GPT_PRIO', '1') != '0' else None
         self.exchange = None
         self.max_rows = max_rows
         if data_parallel:                   # collective: every rank constructs its engine at the same point
@@ -442,7 +447,7 @@ class FusedTrainStep(object):
         torch.cuda.synchronize()
         n0 = _lib.lib().gpt_launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self.capture_stream):
             entry['loss'], entry['logits'] = self._run(entry['inputs'], entry['labels'])
         entry['graph'] = g
         self.kernels_per_replay[key] = int(_lib.lib().gpt_launch_count() - n0)
