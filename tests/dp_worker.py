@@ -8,7 +8,7 @@ The two runs are compared in LOCKSTEP -- before every step all ranks load the si
 because free-running trajectories are not comparable at this tolerance: a pre-activation of the output MLP that is
 zero to within rounding falls on either side of the ReLU under a 1e-7 perturbation, and that sentence's whole
 contribution to the unit's gradient row flips with it (measured: 2e-7 relative noise on the parameters moves them by
-up to 6e-3 after 8 steps at these sizes, scratch/knife.py).  From identical parameters the
+up to 6e-3 after 8 steps at these sizes, tools/relu_knife_edge.py).  From identical parameters the
 forward is bit-identical per sentence, so only the summation order of the gradient differs.  The exchange state
 (step parity, slot tables, owner marks, gradient buffers) still carries over from step to step."""
 import os

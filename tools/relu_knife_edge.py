@@ -1,5 +1,14 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""How far do two correct fp32 training runs drift apart?  Trains the same model twice from parameters that differ by
+2e-7 relative noise and reports the largest relative parameter deviation after 8 steps.  At TACRED batch sizes a
+pre-activation of the output MLP within rounding of zero falls on either side of the ReLU, and that sentence's whole
+contribution to the unit's gradient row flips with it: deviations of 1e-4..6e-3 are common, which
+is why tests/dp_worker.py compares data-parallel and single-process runs in lockstep."""
+import os
+import sys
+
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gcn_over_pruned_trees_b200 import synth
 from gcn_over_pruned_trees_b200.engine import FusedTrainStep
 from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
