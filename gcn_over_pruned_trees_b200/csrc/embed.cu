@@ -69,61 +69,91 @@ embed_fwd_kernel(const EmbParams p, float* __restrict__ x) {
     }
 }
 
-// scatter dX (after the same dropout mask) into the tables; word rows additionally record their first token
+// scatter dX (after the same dropout mask) into the tables; word rows additionally record their first token.
+// MULTI = false: one CTA per token row (TACRED-sized batches: thousands of short CTAs).  MULTI = true (>= 64 K rows):
+// a CTA walks many rows and first collects the gradients of the small tables -- 47 POS and 15 NER rows, i.e. millions of
+// atomics onto ~60 cache lines at the large shape -- in shared memory (ids < kSmallIds; larger ids go to memory
+// directly) and flushes each touched entry once.
+constexpr int kSmallIds = 64;
+
+template <bool MULTI>
 __global__ void __launch_bounds__(kEmbThreads)
 embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned char* __restrict__ flags,
                  float* __restrict__ g_emb, float* __restrict__ g_pos, float* __restrict__ g_ner,
                  int* __restrict__ owner, int topn) {
     GPT_PDL_ENTER();
-    const int row = blockIdx.x;
-    if (flags != nullptr && flags[row] == 0) return;  // unobservable token: its gradient row is exactly zero
+    extern __shared__ float s_small[];                   // MULTI: [kSmallIds][Dp] then [kSmallIds][Dn]
+    float* s_pos = s_small;
+    float* s_ner = s_small + kSmallIds * p.Dp;
+    if (MULTI) {
+        for (int i = threadIdx.x; i < kSmallIds * (p.Dp + p.Dn); i += kEmbThreads) s_small[i] = 0.f;
+        __syncthreads();
+    }
     const int D = p.E + p.Dp + p.Dn;
-    const long long w = p.words[row];
-    const long long ps = p.pos_w ? p.pos[row] : 0;
-    const long long nr = p.ner_w ? p.ner[row] : 0;
-    const bool word_live = g_emb != nullptr && w != 0 && w < topn;  // padding_idx = 0; rows >= topn are frozen
     const bool drop = p.thresh16 > 0;
     unsigned long long seed = 0, step = 0;
     if (drop) { seed = p.rng[0]; step = p.rng[1]; }
-    if (threadIdx.x == 0 && word_live && owner != nullptr) atomicMin(owner + w, row);
     const bool vec_rows = (p.E & 3) == 0 && (reinterpret_cast<uintptr_t>(g_emb) & 15) == 0;   // 16-byte aligned quads
-    const float* dr = dx + (size_t)row * D;
-    for (int g = threadIdx.x; g * 8 < D; g += kEmbThreads) {
-        Philox4 q{0, 0, 0, 0};
-        if (drop)
-            q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step, (uint32_t)seed,
-                           (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
-        const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
-        float v[8];
+    for (int row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        if (flags != nullptr && flags[row] == 0) continue;  // unobservable token: its gradient row is exactly zero
+        const long long w = p.words[row];
+        const long long ps = p.pos_w ? p.pos[row] : 0;
+        const long long nr = p.ner_w ? p.ner[row] : 0;
+        const bool word_live = g_emb != nullptr && w != 0 && w < topn;  // padding_idx = 0; rows >= topn are frozen
+        if (threadIdx.x == 0 && word_live && owner != nullptr) atomicMin(owner + w, row);
+        const float* dr = dx + (size_t)row * D;
+        for (int g = threadIdx.x; g * 8 < D; g += kEmbThreads) {
+            Philox4 q{0, 0, 0, 0};
+            if (drop)
+                q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step,
+                               (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+            const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+            float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = g * 8 + k;
-            v[k] = c < D ? dr[c] : 0.f;
-            if (drop) {
-                const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                v[k] = bits >= p.thresh16 ? v[k] * p.drop_scale : 0.f;
+            for (int k = 0; k < 8; ++k) {
+                const int c = g * 8 + k;
+                v[k] = c < D ? dr[c] : 0.f;
+                if (drop) {
+                    const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                    v[k] = bits >= p.thresh16 ? v[k] * p.drop_scale : 0.f;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                   // two quads of columns
+                const int c = g * 8 + 4 * h;
+                if (c >= D) break;
+                if (vec_rows && c + 3 < p.E) {              // whole quad in the word row: one 16-byte reduction
+                    if (word_live && (v[4 * h] != 0.f || v[4 * h + 1] != 0.f || v[4 * h + 2] != 0.f || v[4 * h + 3] != 0.f))
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g_emb + (size_t)w * p.E + c),
+                                     "f"(v[4 * h]), "f"(v[4 * h + 1]), "f"(v[4 * h + 2]), "f"(v[4 * h + 3]) : "memory");
+                    continue;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cc = c + k;
+                    const float u = v[4 * h + k];
+                    if (cc >= D || u == 0.f) continue;
+                    if (cc < p.E) {
+                        if (word_live) atomicAdd(g_emb + (size_t)w * p.E + cc, u);
+                    } else if (cc < p.E + p.Dp) {
+                        if (g_pos) {
+                            if (MULTI && ps < kSmallIds) atomicAdd(s_pos + (int)ps * p.Dp + (cc - p.E), u);
+                            else atomicAdd(g_pos + (size_t)ps * p.Dp + (cc - p.E), u);
+                        }
+                    } else if (g_ner) {
+                        if (MULTI && nr < kSmallIds) atomicAdd(s_ner + (int)nr * p.Dn + (cc - p.E - p.Dp), u);
+                        else atomicAdd(g_ner + (size_t)nr * p.Dn + (cc - p.E - p.Dp), u);
+                    }
+                }
             }
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                   // two quads of columns
-            const int c = g * 8 + 4 * h;
-            if (c >= D) break;
-            if (vec_rows && c + 3 < p.E) {              // whole quad in the word row: one 16-byte reduction
-                if (word_live && (v[4 * h] != 0.f || v[4 * h + 1] != 0.f || v[4 * h + 2] != 0.f || v[4 * h + 3] != 0.f))
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g_emb + (size_t)w * p.E + c),
-                                 "f"(v[4 * h]), "f"(v[4 * h + 1]), "f"(v[4 * h + 2]), "f"(v[4 * h + 3]) : "memory");
-                continue;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int cc = c + k;
-                const float u = v[4 * h + k];
-                if (cc >= D || u == 0.f) continue;
-                if (cc < p.E) { if (word_live) atomicAdd(g_emb + (size_t)w * p.E + cc, u); }
-                else if (cc < p.E + p.Dp) { if (g_pos) atomicAdd(g_pos + (size_t)ps * p.Dp + (cc - p.E), u); }
-                else if (g_ner) atomicAdd(g_ner + (size_t)nr * p.Dn + (cc - p.E - p.Dp), u);
-            }
-        }
+    }
+    if (MULTI) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSmallIds * p.Dp; i += kEmbThreads)
+            if (g_pos && s_pos[i] != 0.f) atomicAdd(g_pos + i, s_pos[i]);        // same [id][column] layout as the table
+        for (int i = threadIdx.x; i < kSmallIds * p.Dn; i += kEmbThreads)
+            if (g_ner && s_ner[i] != 0.f) atomicAdd(g_ner + i, s_ner[i]);
     }
 }
 
@@ -210,8 +240,18 @@ extern "C" int gpt_embed_bwd(const float* dx, const uint8_t* flags, const int64_
                          drop_p, rng_state, subseq);
     if (rc != GPT_OK || dx == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
     if (n_rows == 0) return GPT_OK;
-    gpt_launch(embed_bwd_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream, p, dx, flags, g_emb, g_pos, g_ner, owner,
-                                                                       topn < V ? topn : V);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const int tn = topn < V ? topn : V;
+    if (n_rows >= 65536) {      // many rows: a few resident CTAs walk them, small-table gradients meet in shared memory
+        const size_t smem = (size_t)kSmallIds * (Dp + Dn) * sizeof(float);
+        if (smem <= 48 * 1024) {
+            gpt_launch(embed_bwd_kernel<true>, dim3(148 * 8), dim3(kEmbThreads), smem, st, p, dx, flags, g_emb, g_pos,
+                       g_ner, owner, tn);
+            return gpt_launch_status();
+        }
+    }
+    gpt_launch(embed_bwd_kernel<false>, dim3(n_rows), dim3(kEmbThreads), 0, st, p, dx, flags, g_emb, g_pos, g_ner, owner,
+               tn);
     return gpt_launch_status();
 }
 

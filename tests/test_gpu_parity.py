@@ -476,6 +476,29 @@ def test_k5_embed_concat_vs_torch(dataset):
             assert _rel(a.grad.cpu(), b.grad.cpu()) < 1e-5
 
 
+def test_k5_backward_over_many_rows_collects_the_small_tables_in_shared_memory():
+    """>= 64 K token rows: the multi-row backward kernel (POS / NER gradients summed in shared memory, flushed once per
+    CTA) against torch, including POS ids beyond the 64 rows the shared table holds."""
+    V, E, Dp, Dn, n = 500, 300, 30, 30, 70_001
+    g = torch.Generator(device=DEV).manual_seed(5)
+    words = torch.randint(0, V, (1, n), device=DEV, generator=g)
+    pos = torch.randint(0, 80, (1, n), device=DEV, generator=g)           # ids 64..79 take the direct path
+    ner = torch.randint(0, 15, (1, n), device=DEV, generator=g)
+    tabs = [torch.randn(V, E, device=DEV, generator=g).requires_grad_(),
+            torch.randn(80, Dp, device=DEV, generator=g).requires_grad_(),
+            torch.randn(15, Dn, device=DEV, generator=g).requires_grad_()]
+    x = ops.embed_concat(words, pos, ner, tabs[0], tabs[1], tabs[2])
+    r = torch.randn(x.shape, device=DEV, generator=g)
+    (x * r).sum().backward()
+    ref_t = [t.detach().clone().requires_grad_() for t in tabs]
+    xr = torch.cat([torch.nn.functional.embedding(words, ref_t[0], padding_idx=0),
+                    torch.nn.functional.embedding(pos, ref_t[1]), torch.nn.functional.embedding(ner, ref_t[2])], 2)
+    (xr * r).sum().backward()
+    assert torch.equal(x, xr)
+    for a, b in zip(tabs, ref_t):
+        assert _rel(a.grad.double().cpu(), b.grad.double().cpu()) < 2e-5      # thousands of fp32 additions per entry
+
+
 def test_k5_dropout_mask_is_replayed_in_backward_and_topn_freezes_rows():
     V, E = 200, 64
     batch = synth.make_batch(62, batch_size=30, vocab_size=V)
