@@ -8,18 +8,25 @@
 //   dp_push_kernel    each rank stores, with plain coalesced stores over NVLink, into the region of EVERY rank
 //                     (itself included, slot = its rank): its flat dense gradient (1.1 MB), the word id of every
 //                     token slot that owns a live embedding row (-1 otherwise), those rows themselves, and
-//                     slot_of_word[rank][w] = token slot.  Then a system-scope release of flags[rank] = step on every
-//                     peer.  It also clears the rank's own G rows / owner marks, so the next backward starts clean.
-//   dp_reduce_kernel  waits (acquire) until the flags of all ranks carry this step, then works on LOCAL memory only:
-//                     flat gradient = sum over ranks in rank order; for every word, the lowest (rank, slot) that has
-//                     it adds the rows of the higher ranks found through slot_of_word, in rank order.  Every rank
-//                     performs bit-identical additions, so replicas never drift.  Emits the g^2 partial sums.
+//                     slot_of_word[rank][w] = token slot.  It also clears the rank's own G rows / owner marks, so the
+//                     next backward starts clean.  No fence and no flag: an in-kernel system-scope fence per CTA cost
+//                     ~5 us and was the largest item of this kernel.
+//   dp_reduce_kernel  CTA 0 first raises flags[rank] = step on every peer (st.release.sys) -- this grid starts only
+//                     after the push grid has completed, so the pushed data has been performed by then -- and every
+//                     CTA waits (acquire) until the flags of all ranks carry this step, then works on LOCAL memory
+//                     only: flat gradient = sum over ranks in rank order (all ranks' slices in flight before the first
+//                     add); rows: a warp takes 32 / W' token-slot entries at a time with lane = (entry, rank), so one
+//                     load fetches the slot every rank holds for each word; the lowest (rank, slot) that has a word
+//                     adds the rows of the higher ranks in rank order, every load of a row issued before its first
+//                     store.  Every rank performs bit-identical additions, so replicas never drift.  Emits the g^2
+//                     partial sums.
 //   dp_apply_kernel   K7 on the reduced values (mean = sum / W): clip coefficient, p -= lr * coef * g, resets.
 //
 // Buffers are double-buffered by step parity: a rank can be at most one step ahead of the slowest one (it cannot pass
 // the next reduce), so what it pushes for step s+1 never overwrites what a peer still reads for step s.
 // One-shot (every rank receives everything) is the right shape for <= 2.3 MB per rank on NVSwitch: (W-1) x 2.3 MB per
-// GPU at 900 GB/s is < 20 us at W = 8, with a single synchronisation.
+// GPU at 900 GB/s is < 20 us at W = 8, with a single synchronisation.  tools/dp_bench.py times the three kernels with
+// W virtual ranks on one GPU (W = 8: 136 us -> 55 us with the structure above).
 #include "gpt_common.cuh"
 
 namespace {
