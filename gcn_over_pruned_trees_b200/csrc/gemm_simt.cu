@@ -199,42 +199,56 @@ wgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
             n_act += round;
             __syncthreads();
         }
-        for (int s0 = 0; s0 < n_act; s0 += BK) {
-            const int rr = tid / 16, c4 = (tid % 16) * 4;
-            const int row = s0 + rr < n_act ? s_rows[s0 + rr] : -1;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (row >= 0) {
-                const float* pa = dy + (size_t)row * N + n0 + c4;
-                const float* pb = x + (size_t)row * K + k0 + c4;
-                if (vec_a && n0 + c4 + 3 < N) a = __ldg(reinterpret_cast<const float4*>(pa));
-                else {
-                    if (n0 + c4 < N) a.x = pa[0];
-                    if (n0 + c4 + 1 < N) a.y = pa[1];
-                    if (n0 + c4 + 2 < N) a.z = pa[2];
-                    if (n0 + c4 + 3 < N) a.w = pa[3];
+        // slabs of BK live rows; the global loads of kSlabBatch slabs are issued together, so that a CTA pays the memory
+        // latency once per batch instead of once per slab (a slab's 16 x 64 x 64 FMAs are far shorter than a load)
+        constexpr int kSlabBatch = 3;
+        const int rr = tid / 16, c4 = (tid % 16) * 4;
+        for (int s0 = 0; s0 < n_act; s0 += BK * kSlabBatch) {
+            float4 av[kSlabBatch], bv[kSlabBatch];
+#pragma unroll
+            for (int u = 0; u < kSlabBatch; ++u) {
+                const int idx = s0 + u * BK + rr;
+                const int row = idx < n_act ? s_rows[idx] : -1;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (row >= 0) {
+                    const float* pa = dy + (size_t)row * N + n0 + c4;
+                    const float* pb = x + (size_t)row * K + k0 + c4;
+                    if (vec_a && n0 + c4 + 3 < N) a = __ldg(reinterpret_cast<const float4*>(pa));
+                    else {
+                        if (n0 + c4 < N) a.x = pa[0];
+                        if (n0 + c4 + 1 < N) a.y = pa[1];
+                        if (n0 + c4 + 2 < N) a.z = pa[2];
+                        if (n0 + c4 + 3 < N) a.w = pa[3];
+                    }
+                    if (vec_b && k0 + c4 + 3 < K) b = __ldg(reinterpret_cast<const float4*>(pb));
+                    else {
+                        if (k0 + c4 < K) b.x = pb[0];
+                        if (k0 + c4 + 1 < K) b.y = pb[1];
+                        if (k0 + c4 + 2 < K) b.z = pb[2];
+                        if (k0 + c4 + 3 < K) b.w = pb[3];
+                    }
                 }
-                if (vec_b && k0 + c4 + 3 < K) b = __ldg(reinterpret_cast<const float4*>(pb));
-                else {
-                    if (k0 + c4 < K) b.x = pb[0];
-                    if (k0 + c4 + 1 < K) b.y = pb[1];
-                    if (k0 + c4 + 2 < K) b.z = pb[2];
-                    if (k0 + c4 + 3 < K) b.w = pb[3];
+                av[u] = a;
+                bv[u] = b;
+            }
+#pragma unroll
+            for (int u = 0; u < kSlabBatch; ++u) {
+                if (s0 + u * BK >= n_act) break;                       // CTA-uniform
+                *reinterpret_cast<float4*>(&As[rr][c4]) = av[u];
+                *reinterpret_cast<float4*>(&Bs[rr][c4]) = bv[u];
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < BK; ++kk) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                    const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                    const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
                 }
+                __syncthreads();
             }
-            *reinterpret_cast<float4*>(&As[rr][c4]) = a;
-            *reinterpret_cast<float4*>(&Bs[rr][c4]) = b;
-            __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < BK; ++kk) {
-                const float4 av4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-                const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-                const float av[4] = {av4.x, av4.y, av4.z, av4.w}, bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-            }
-            __syncthreads();
         }
     }
     const bool vec_out = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && (k0 + tx * 4 + 3 < K);
