@@ -53,6 +53,7 @@ def parse_args():
                     help='use GraphedTrainStep (autograd under capture) instead of FusedTrainStep')
     ap.add_argument('--no-roofline', action='store_true', help='skip the large-shape aggregation roofline run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-loader', action='store_true', help='skip the K9 device-loader leg (short profiler passes)')
     ap.add_argument('--roofline-batch', type=int, default=4096)
     ap.add_argument('--cpu-steps', type=int, default=60)
     return ap.parse_args()
@@ -375,7 +376,7 @@ def run_b200(args):
                                'api': 'reference call sequence train.py:213-227 on the new model package, eager'}
     # ---- K9: batches assembled on the device from a resident token arena ----------------------
     loader_info = None
-    if fused and not args.eager:
+    if fused and not args.eager and not args.no_loader:
         from gcn_over_pruned_trees_b200.data.loader import DataLoader as DeviceLoader
         examples = []
         for bt in host_tuples:

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list into a per-kernel table for ONE training step
-(steps are delimited by the prune_csr kernel)."""
+(steps are delimited by the prune_csr kernel; without a step index the last of the shortest steps, i.e. a fused
+one, is taken)."""
 import collections
 import csv
 import sys
@@ -14,7 +15,12 @@ def main():
     i_name, i_val, i_id = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('ID')
     recs = [(r[i_name], float(r[i_val].replace(',', ''))) for r in rows[1:] if r[i_id].isdigit()]
     marks = [i for i, (n, v) in enumerate(recs) if 'prune_csr' in n]
-    s, e = marks[which - 1], marks[which]
+    segs = [(marks[i], marks[i + 1]) for i in range(len(marks) - 1)]
+    if len(sys.argv) > 2:
+        s, e = segs[which]
+    else:       # the fused step: the shortest segments (eager / autograd steps of the same run launch several times more)
+        fewest = min(e - s for s, e in segs)
+        s, e = [se for se in segs if se[1] - se[0] == fewest][-1]
     step = recs[s:e]
     tot = sum(v for _, v in step)
     agg = collections.OrderedDict()
