@@ -96,3 +96,33 @@ def test_state_dict_layout_matches_reference_checkpoints(name):
 def test_unsupported_paths_fail_loudly():
     with pytest.raises(NotImplementedError):
         trainer_mod.GCNTrainer(synth.tacred_opt(vocab_size=50, adj_type='full_deprel'))
+
+
+def test_packed_batch_is_one_buffer_with_the_loader_views():
+    """PackedBatch (engine.py): a loader tuple in ONE contiguous buffer -- same shapes, dtypes and values, every view
+    naturally aligned, and `like=` reproduces the layout for the static device copy."""
+    from gcn_over_pruned_trees_b200.engine import PackedBatch
+    for dataset in ('tacred', 'semeval'):
+        batch = synth.make_batch(5, batch_size=7, vocab_size=300, dataset=dataset)
+        pb = PackedBatch(batch)
+        fields = batch[:-2]
+        assert len(pb.fields) == len(fields) and pb.key == (7, fields[0].shape[1], len(fields))
+        for v, f in zip(pb.fields, fields):
+            assert v.dtype == f.dtype and v.shape == f.shape and torch.equal(v, f)
+            assert v.data_ptr() % v.element_size() == 0
+            lo, hi = pb.buf.data_ptr(), pb.buf.data_ptr() + pb.buf.numel()
+            assert lo <= v.data_ptr() and v.data_ptr() + v.numel() * v.element_size() <= hi
+        assert torch.equal(pb.labels, batch[-2]) and pb.orig_idx == batch[-1]
+        twin = PackedBatch(like=pb)
+        twin.buf.copy_(pb.buf)
+        assert all(torch.equal(a, b) for a, b in zip(twin.as_tuple()[:-1], pb.as_tuple()[:-1]))
+
+
+def test_loader_row_order_and_widths_are_planned_on_the_host():
+    """data/loader.py: the length sort (reference tie-break) and the batch widths need only the sentence lengths."""
+    from gcn_over_pruned_trees_b200.data import loader as dloader
+    lens = [3, 7, 7, 2, 9, 7]
+    rows = dloader.sorted_rows(lens)
+    assert rows == [4, 5, 2, 1, 0, 3]                      # descending length, ties by descending position
+    assert [lens[r] for r in rows] == sorted(lens, reverse=True)
+    assert dloader.get_positions(0, 0, 4) == [0, 1, 2, 3] and dloader.get_positions(3, 3, 4) == [-3, -2, -1, 0]
