@@ -9,8 +9,14 @@ sentence on the host, ``adj.bmm(h)``, two ``Linear`` calls per layer, three ``ma
 so that timing it measures the reference's CPU algorithm, and so that the CUDA path (CSR gather, one GEMM per
 layer) is checked against an independent formulation.
 
+Also restated: the fork's relation-aware layers ``adj_type='full_deprel'`` and
+``'diagonal_deprel'`` with edge dropout, relation forgetting, ``deprel_max_depth``, ``deprel_directed`` and
+``deprel_self_loop``.
+
 Reference lines restated:
   module/parameter layout      /root/reference/model/gcn.py:15-22, 38-68, 128-176
+  relation-aware layers        /root/reference/model/gcn.py:272-294 (diagonal), 296-386 + 400-434 (full),
+                               436-449 (edge dropout), 451-470 (relation forgetting)
   embedding concat + in_drop   /root/reference/model/gcn.py:235-247
   BiLSTM encoder (C-GCN)       /root/reference/model/gcn.py:186-197, 250-253, 485-492
   adjacency binarise/denom     /root/reference/model/gcn.py:260-265
@@ -44,7 +50,65 @@ class _DenseGCN(nn.Module):
                                dropout=opt['rnn_dropout'], bidirectional=True)
             width = 2 * opt['rnn_hidden']
         hidden = opt['hidden_dim']
-        self.W = nn.ModuleList(nn.Linear(width if l == 0 else hidden, hidden) for l in range(opt['num_layers']))
+        self.adj_type = opt.get('adj_type', 'regular')
+        if self.adj_type == 'diagonal_deprel':        # gcn.py:153-155: no per-layer weights at all
+            self.preprocessor = nn.Linear(width, hidden)
+        elif self.adj_type == 'full_deprel':          # gcn.py:164-167: ONE Linear(in, D*H) shared by every layer
+            self.W = nn.Linear(width, opt['deprel_emb_dim'] * hidden)
+        else:
+            self.W = nn.ModuleList(nn.Linear(width if l == 0 else hidden, hidden)
+                                   for l in range(opt['num_layers']))
+
+    # ---- relation-aware layers ------------------------------------------------------------------------------
+    def _edge_keep(self, a, name, masks):
+        """gcn.py:436-449: Bernoulli(edge_keep_prob) over the DENSE matrix, drawn per direction and per layer."""
+        if masks is not None and name in masks:
+            return a * masks[name]
+        p = self.opt.get('edge_keep_prob', 1.0)
+        if self.training and p < 1.0:
+            return torch.empty_like(a).bernoulli_(p) * a
+        return a
+
+    def _forget(self, e, name, masks):
+        """gcn.py:451-470: with probability 1 - deprel_keep_prop a token's relation vector becomes all ones."""
+        if masks is not None and name in masks:
+            keep = masks[name]
+        else:
+            p = self.opt.get('deprel_keep_prop', 1.0)
+            if not (self.training and p < 1.0):
+                return e
+            keep = torch.empty((e.size(0), e.size(1), 1)).bernoulli_(p)
+        return torch.where(keep.expand_as(e) == 1, e, torch.ones_like(e))
+
+    def _relation_layer(self, adj, x, deprel, l, masks):
+        """One layer's pre-normalisation sum for the two relation-aware modes.  ``adj`` holds the relation ids:
+        (0,42) parent->child, (42,84) child->parent, 84 self loop (tree.py:184-192)."""
+        fwd = ((adj > 0) & (adj < 42)).float()
+        rev = ((adj > 42) & (adj < 84)).float()
+        e_f = self.deprel_emb(deprel)                  # keyed by the token's OWN incoming relation ...
+        e_r = self.deprel_emb(deprel + 42)             # ... in both directions (gcn.py:315, 349)
+        e_s = self.deprel_emb.weight[84]
+        if self.adj_type == 'diagonal_deprel':         # gcn.py:272-294: no dropout of edges, no forgetting
+            return fwd.bmm(e_f * x) + rev.bmm(e_r * x) + x * e_s
+        D, H = self.opt['deprel_emb_dim'], self.opt['hidden_dim']
+        w = self.W.weight.reshape(D, -1, H)            # a reshape of [D*H, in], NOT a permute (gcn.py:301)
+        b = self.W.bias.reshape(D, H)
+        deep = l >= self.opt['deprel_max_depth']       # gcn.py:324-325, 355-356, 376-379
+
+        def traverse(e):                               # gcn.py:400-415
+            return torch.einsum('bnd,bnk,dkh->bnh', e, x, w) + e @ b
+
+        fwd = self._edge_keep(fwd, 'edge_f%d' % l, masks)
+        e_f = self._forget(e_f, 'forget_f%d' % l, masks)
+        total = fwd.bmm(traverse(torch.ones_like(e_f) if deep else e_f))
+        if not self.opt['deprel_directed']:
+            rev = self._edge_keep(rev, 'edge_r%d' % l, masks)
+            e_r = self._forget(e_r, 'forget_r%d' % l, masks)
+            total = total + rev.bmm(traverse(torch.ones_like(e_r) if deep else e_r))
+        if self.opt['deprel_self_loop']:               # gcn.py:369-386, 417-434: every token, kept or not
+            e = torch.ones_like(e_s) if deep else e_s
+            total = total + x @ torch.einsum('d,dkh->kh', e, w) + e @ b
+        return total
 
     def conv_l2(self):
         return sum(p.pow(2).sum() for lin in self.W for p in (lin.weight, lin.bias))
@@ -73,14 +137,20 @@ class _DenseGCN(nn.Module):
             y, _ = self.rnn(packed, (zeros, zeros))
             y, _ = nn.utils.rnn.pad_packed_sequence(y, batch_first=True)
             x = self._drop(y, self.opt['rnn_dropout'], 'rnn', masks)
+        if self.adj_type == 'diagonal_deprel':
+            x = self.preprocessor(x)                   # gcn.py:255-257
         a = (adj != 0).float()
         denom = a.sum(2, keepdim=True) + 1
         not_in_tree = (a.sum(2) + a.sum(1)).eq(0).unsqueeze(2)
         if self.opt.get('no_adj', False):
             a = torch.zeros_like(a)
-        last = len(self.W) - 1
-        for l, lin in enumerate(self.W):
-            z = (lin(a.bmm(x)) + lin(x)) / denom      # bias enters twice, self term twice
+        last = self.opt['num_layers'] - 1
+        for l in range(self.opt['num_layers']):
+            if self.adj_type == 'regular':
+                lin = self.W[l]
+                z = (lin(a.bmm(x)) + lin(x)) / denom  # bias enters twice, self term twice
+            else:
+                z = self._relation_layer(adj, x, deprel, l, masks) / denom
             x = F.relu(z)
             if l < last:
                 x = self._drop(x, self.opt['gcn_dropout'], 'gcn%d' % l, masks)
@@ -103,7 +173,9 @@ class _DenseRelationModel(nn.Module):
         self.emb = nn.Embedding(opt['vocab_size'], opt['emb_dim'], padding_idx=0)
         self.pos_emb = nn.Embedding(N_POS, opt['pos_dim']) if opt['pos_dim'] > 0 else None
         self.ner_emb = nn.Embedding(N_NER, opt['ner_dim']) if opt['ner_dim'] > 0 else None
-        self.deprel_emb = nn.Embedding(N_DEPREL, 1, padding_idx=0)   # dummy in regular mode, gcn.py:53-56
+        adj_type = opt.get('adj_type', 'regular')    # gcn.py:48-57: width H (diagonal), D (full), dummy 1 (regular)
+        side = {'regular': 1, 'diagonal_deprel': opt['hidden_dim']}.get(adj_type, opt.get('deprel_emb_dim', 1))
+        self.deprel_emb = nn.Embedding(N_DEPREL, side, padding_idx=0)
         self.emb.weight.data[1:].uniform_(-1.0, 1.0)
         self.gcn = _DenseGCN(opt, (self.emb, self.pos_emb, self.ner_emb, self.deprel_emb))
         hidden = opt['hidden_dim']

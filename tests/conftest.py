@@ -37,3 +37,9 @@ def golden_adj():
 def golden_model():
     import numpy as np
     return np.load(os.path.join(GOLDEN, 'model.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_deprel():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'deprel.npz'))

@@ -27,6 +27,39 @@ MODEL_CASES = {
     'hidden64_k0':          (dict(prune_k=0, hidden_dim=64, emb_dim=50, pos_dim=5, ner_dim=0,
                                   vocab_size=SMALL_VOCAB), ('synth', 210, 16), 18),
 }
+# relation-aware adjacency modes.  full_deprel shares ONE Linear(in, D*H) between the
+# layers, so the reference only runs when the GCN input width equals hidden_dim.
+_IN64 = dict(emb_dim=40, pos_dim=12, ner_dim=12, hidden_dim=64, vocab_size=SMALL_VOCAB)
+DEPREL_CASES = {
+    'full_k1_d8':          (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1), ('synth', 301, 24), 21),
+    'full_kfull_d16':      (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=16, prune_k=-1), ('synth', 302, 16), 22),
+    'full_directed':       (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=2, deprel_directed=True),
+                            ('synth', 303, 16), 23),
+    'full_no_self_loop':   (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1, deprel_self_loop=False),
+                            ('synth', 304, 16), 24),
+    'full_depth1_3layer':  (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1, num_layers=3,
+                                 deprel_max_depth=1), ('synth', 305, 16), 25),
+    'full_cgcn_h64':       (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1, rnn=True, rnn_hidden=32),
+                            ('synth', 306, 16), 26),
+    'full_semeval':        (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1, dataset='semeval',
+                                 emb_dim=52, num_class=19), ('synth', 307, 16), 27),
+    'full_split_train':    (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=12, prune_k=1), ('split', 'train'), 28),
+    'diag_k1':             (dict(adj_type='diagonal_deprel', prune_k=1, hidden_dim=64, vocab_size=SMALL_VOCAB),
+                            ('synth', 311, 24), 31),
+    'diag_kfull_3layer':   (dict(adj_type='diagonal_deprel', prune_k=-1, hidden_dim=48, num_layers=3,
+                                 vocab_size=SMALL_VOCAB), ('synth', 312, 16), 32),
+    'diag_cgcn':           (dict(adj_type='diagonal_deprel', prune_k=1, hidden_dim=64, rnn=True, rnn_hidden=40,
+                                 vocab_size=SMALL_VOCAB), ('synth', 313, 16), 33),
+}
+DEPREL_GRAD_CASES = ('full_k1_d8', 'full_directed', 'full_depth1_3layer', 'full_cgcn_h64', 'diag_k1')
+# train-mode cases of the reference with edge dropout / relation forgetting drawn from torch.manual_seed(DROPOUT_SEED)
+DEPREL_RANDOM_CASES = {
+    'full_edge_drop':      (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1, edge_keep_prob=0.7),
+                            ('synth', 321, 16), 41),
+    'full_forget':         (dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=1, deprel_keep_prop=0.6),
+                            ('synth', 322, 16), 42),
+}
+
 # cases that additionally store train-mode (dropout drawn from torch.manual_seed(DROPOUT_SEED)) loss + gradients
 GRAD_CASES = ('cfg1_train_json_k1', 'cfg2_synth_k1', 'cfg3_cgcn_k1', 'cfg4_semeval_k1', 'avg_pool_conv_l2',
               'sum_pool_3layer_mlp1')

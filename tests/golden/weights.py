@@ -12,7 +12,8 @@ N_POS, N_NER, N_DEPREL = 47, 15, 85
 
 
 def state_shapes(opt):
-    """{key: shape} of GCNClassifier.state_dict() for adj_type='regular' (incl. the duplicated embedding keys)."""
+    """{key: shape} of GCNClassifier.state_dict() (incl. the duplicated embedding keys); adj_type 'regular',
+    'full_deprel' (one shared Linear, gcn.py:164-167) or 'diagonal_deprel' (a preprocessor, no W, gcn.py:153-155)."""
     tacred = opt['dataset'] == 'tacred'
     hidden = opt['hidden_dim']
     shapes = {'gcn_model.emb.weight': (opt['vocab_size'], opt['emb_dim'])}
@@ -20,7 +21,9 @@ def state_shapes(opt):
         shapes['gcn_model.pos_emb.weight'] = (N_POS, opt['pos_dim'])
     if opt['ner_dim'] > 0:
         shapes['gcn_model.ner_emb.weight'] = (N_NER, opt['ner_dim'])
-    shapes['gcn_model.deprel_emb.weight'] = (N_DEPREL, 1)
+    adj_type = opt.get('adj_type', 'regular')
+    side = {'regular': 1, 'diagonal_deprel': hidden}.get(adj_type, opt.get('deprel_emb_dim', 1))
+    shapes['gcn_model.deprel_emb.weight'] = (N_DEPREL, side)
     width = opt['emb_dim'] + opt['pos_dim'] + (opt['ner_dim'] if tacred else 0)
     if opt.get('rnn', False):
         rh = opt['rnn_hidden']
@@ -32,9 +35,16 @@ def state_shapes(opt):
                 shapes['gcn_model.gcn.rnn.bias_ih_l%d%s' % (layer, suffix)] = (4 * rh,)
                 shapes['gcn_model.gcn.rnn.bias_hh_l%d%s' % (layer, suffix)] = (4 * rh,)
         width = 2 * rh
-    for layer in range(opt['num_layers']):
-        shapes['gcn_model.gcn.W.%d.weight' % layer] = (hidden, width if layer == 0 else hidden)
-        shapes['gcn_model.gcn.W.%d.bias' % layer] = (hidden,)
+    if adj_type == 'diagonal_deprel':
+        shapes['gcn_model.gcn.preprocessor.weight'] = (hidden, width)
+        shapes['gcn_model.gcn.preprocessor.bias'] = (hidden,)
+    elif adj_type == 'full_deprel':
+        shapes['gcn_model.gcn.W.weight'] = (side * hidden, width)
+        shapes['gcn_model.gcn.W.bias'] = (side * hidden,)
+    else:
+        for layer in range(opt['num_layers']):
+            shapes['gcn_model.gcn.W.%d.weight' % layer] = (hidden, width if layer == 0 else hidden)
+            shapes['gcn_model.gcn.W.%d.bias' % layer] = (hidden,)
     shapes['gcn_model.out_mlp.0.weight'] = (hidden, 3 * hidden)
     shapes['gcn_model.out_mlp.0.bias'] = (hidden,)
     for i in range(1, opt['mlp_layers']):
@@ -50,7 +60,9 @@ def make_state(opt, seed):
     state = {}
     for key, shape in state_shapes(opt).items():
         rng = np.random.default_rng([seed, zlib.crc32(key.encode())])
-        if 'emb.weight' in key:
+        if 'deprel_emb.weight' in key and opt.get('adj_type', 'regular') == 'full_deprel':
+            bound = 1.5 / np.sqrt(shape[1])               # relation vectors: keeps the sum over D terms O(1)
+        elif 'emb.weight' in key:
             bound = 1.0
         elif len(shape) == 2:
             bound = 1.0 / np.sqrt(shape[1])

@@ -94,8 +94,8 @@ def test_malformed_inputs_raise():
                                      np.array([11, 2]), 2, 0, 2)
 
 
-def _case_setup(golden_adj, name):
-    over, source, wseed = cases.MODEL_CASES[name]
+def _case_setup(golden_adj, name, table=None):
+    over, source, wseed = (cases.MODEL_CASES if table is None else table)[name]
     if source[0] == 'split':
         batch = cases.batch_from_npz(golden_adj, source[1])
         over = dict(over, vocab_size=int(golden_adj['vocab_size']))
@@ -140,3 +140,47 @@ def test_dense_model_matches_reference_train_grads(golden_adj, golden_model, nam
         assert abs(norm - float(golden_model['%s/grad/%s/norm' % (name, key)])) <= 1e-5 * max(norm, 1e-12), key
         checked += 1
     assert checked >= 8
+
+
+# ---- relation-aware adjacency modes: oracle vs tests/golden/deprel.npz (the real reference) ----
+
+_DEPREL_ALL = dict(cases.DEPREL_CASES, **cases.DEPREL_RANDOM_CASES)
+
+
+@pytest.mark.parametrize('name', sorted(_DEPREL_ALL))
+def test_relation_modes_match_reference_eval(golden_adj, golden_deprel, name):
+    opt, batch, model = _case_setup(golden_adj, name, _DEPREL_ALL)
+    model.eval()
+    with torch.no_grad():
+        loss, logits = model.loss(batch)
+        _, h_out = model(list(batch[:-2]))
+    want = golden_deprel['%s/logits' % name]
+    assert np.abs(logits.numpy() - want).max() <= 1e-6 * np.abs(want).max()
+    want = golden_deprel['%s/h_out' % name]
+    assert np.abs(h_out.numpy() - want).max() <= 2e-6 * np.abs(want).max()
+    assert abs(loss.item() - float(golden_deprel['%s/eval_loss' % name])) <= 1e-6 * abs(loss.item())
+
+
+@pytest.mark.parametrize('name', cases.DEPREL_GRAD_CASES + tuple(sorted(cases.DEPREL_RANDOM_CASES)))
+def test_relation_modes_match_reference_train_grads(golden_adj, golden_deprel, name):
+    """Train mode; every random draw (dropouts, edge dropout, relation forgetting) is taken in the reference's order
+    from the same seed, so losses and gradients are comparable."""
+    opt, batch, model = _case_setup(golden_adj, name, _DEPREL_ALL)
+    model.train()
+    torch.manual_seed(cases.DROPOUT_SEED)
+    loss, _ = model.loss(batch)
+    loss.backward()
+    assert abs(loss.item() - float(golden_deprel['%s/train_loss' % name])) <= 1e-6 * abs(loss.item())
+    seen, checked = set(), 0
+    for key, p in model.named_parameters():
+        if p.grad is None or id(p) in seen:
+            continue
+        seen.add(id(p))
+        sample, norm, total = weights.grad_digest(p.grad.numpy())
+        want = golden_deprel['%s/grad/%s/sample' % (name, key)]
+        scale = max(float(np.abs(want).max()), 1e-12)
+        assert np.abs(sample - want).max() <= 2e-5 * scale, key
+        assert abs(norm - float(golden_deprel['%s/grad/%s/norm' % (name, key)])) <= 1e-5 * max(norm, 1e-12), key
+        checked += 1
+    assert checked >= 8
+    assert any('deprel_emb' in k for k, p in model.named_parameters() if p.grad is not None)
