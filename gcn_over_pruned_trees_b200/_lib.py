@@ -64,6 +64,17 @@ SIGNATURES = {
     'gpt_dp_reduce': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p],
     'gpt_dp_apply': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_f, _c_f, _p, _p, _p],
     'gpt_build_batch': [_p, _p, _p, _p, _c_int, _c_int, _c_f, ctypes.c_uint64, ctypes.c_uint64, _p, _p, _p, _p],
+    'gpt_relmix_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p],
+    'gpt_relmix_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p],
+    'gpt_diagmix_fwd': [_p, _p, _p, _p, _c_int, _c_int, _p, _p, _p, _p],
+    'gpt_diagmix_bwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _p, _p, _p],
+    'gpt_agg3_fwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_f, _p, _c_u32, _c_int, _c_int, _c_f, _p, _c_int, _c_int,
+                     _c_int, _p, _p],
+    'gpt_agg3_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_f, _p, _c_u32, _c_int, _c_int, _c_f, _p, _c_int, _c_int,
+                     _c_int, _p, _p, _p, _p],
+    'gpt_edge_keep_dense': [_p, _c_int, _c_int, _c_u32, _c_int, _c_f, _p, _p],
+    'gpt_relation_keep_tokens': [_p, _c_int, _c_u32, _c_f, _p, _p, _p],
+    'gpt_colsum_acc': [_p, _c_ll, _c_int, _p, _p],
     'gpt_update_partials': [_c_ll, _c_int],
     'gpt_update_sqnorm': [_p, _c_ll, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_update_apply': [_p, _p, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _c_f, _p, _p, _p],

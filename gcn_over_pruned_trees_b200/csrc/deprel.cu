@@ -1,0 +1,525 @@
+// K10 -- relation-aware GCN layers over the pruned-tree CSR: adj_type 'full_deprel' and 'diagonal_deprel'.
+//
+// Replaces, per layer, the reference's dense path (all of it on [B,T,T] float matrices and [B,T,D,K] outer products)
+//   full_deprel      /root/reference/model/gcn.py:296-386, traverse_deprel :400-415, traverse_self_loop :417-434,
+//                    maybe_drop_edges :436-449, maybe_forget_deprels :451-470
+//   diagonal_deprel  /root/reference/model/gcn.py:272-294
+//   AxW / denom ; relu ; gcn_drop   /root/reference/model/gcn.py:390-393
+//
+// Restated.  With Z[n,d,:] = x_n . weight_l[d] (ONE projection GEMM per layer, K3, shared by the
+// three directions -- the reference runs the [B,T,D,K] x [D,K,H] contraction three times) and e(.) the relation
+// vectors,
+//   F_n = sum_d e(deprel_n)[d]      (Z[n,d,:] + bias_l[d])     "forward":  what a PARENT collects from child n
+//   R_n = sum_d e(deprel_n + 42)[d] (Z[n,d,:] + bias_l[d])     "reverse":  what a CHILD collects from its parent n --
+//                                                               keyed by the parent's own relation (gcn.py:349)
+//   S_n = sum_d e(84)[d]            (Z[n,d,:] + bias_l[d])     self loop
+//   out_i = dropout(relu((sum_{c child of i} keep(i,c) F_c + keep(i,p) R_{p = parent of i} + S_i) / denom_i))
+// (diagonal_deprel: F_n = e(deprel_n) * x_n etc., elementwise, no edge dropout.)  The CSR entry's value (K1's `val`)
+// tells the direction: 0 < val < 42 parent->child, 42 < val < 84 child->parent (tree.py:184-192).  For layers
+// l >= deprel_max_depth, and for tokens whose relation is "forgotten", the relation vector is all ones.
+// Tokens outside the pruned tree are written as zeros: they are not neighbours of kept tokens and are masked out
+// of all three pools, so they never reach the logits (same convention as K2).
+//
+// Mapping: one CTA per token row (grid-stride), threads over the H output columns, every global access coalesced
+// along H.  HBM-bound integer/fp32 work: relmix streams Z once ([N, D*H], the dominant traffic), agg3 reads each
+// F/R/S row once per incident edge out of L2.
+//
+// Backward (symmetric CSR: a row lists the parent and the children of its token, which is all a gather needs):
+//   g_i  = gout_i * d(out_i)/d(z_i) / denom_i
+//   dS_j = g_j ,  dF_j = keep(p,j) g_p (p = parent of j) ,  dR_j = sum_{c child of j} keep(c,j) g_c
+//   dZ[n,d,:] = e_f[d] dF_n + e_r[d] dR_n + e_s[d] dS_n ,  de(.)[d] += <d{F,R,S}_n, Z[n,d,:] + bias_l[d]>
+#include "gpt_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kFwdBound = 42;   // /root/reference/utils/constant.py:14
+constexpr int kRevBound = 84;   // constant.py:16; also the self-loop relation id (constant.py:17)
+
+__device__ __forceinline__ int rel_id(long long r) { return (r < 0 || r > kFwdBound) ? 0 : (int)r; }
+
+// Bernoulli(keep_prob) of entry [b, i, j] of the dense matrix of direction `dir` (0: parent->child matrix, 1: child->parent)
+// at layer `layer`: explicit dense masks when given (tests), else Philox keyed by {seed, step}.
+__device__ __forceinline__ bool edge_kept(const unsigned char* __restrict__ dense, const unsigned long long* __restrict__ rng,
+                                          float keep_prob, unsigned layer, unsigned dir, int b, int i, int j, int T) {
+    if (dense != nullptr) return dense[((size_t)b * T + i) * T + j] != 0;
+    if (keep_prob >= 1.f || rng == nullptr) return true;
+    const unsigned long long seed = rng[0], step = rng[1];
+    const Philox4 r = philox4x32((uint32_t)(b * T + i), (uint32_t)j, 0xED6E0000u | (layer << 1) | dir, (uint32_t)step,
+                                 (uint32_t)seed, (uint32_t)(seed >> 32));
+    return u01(r.x) < keep_prob;
+}
+
+// ---- relation mix: Z -> F, R, S ------------------------------------------------------------------------------------
+struct MixParams {
+    const float* Z;               // [N, D*H] projected rows (no bias)
+    const float* bias;            // [D*H]
+    const float* E;               // [85, D] relation vectors
+    const long long* deprel;      // [N]
+    const unsigned char* flags;   // [N]
+    const unsigned char* keep_f;  // optional [N]: 0 = this token's forward relation vector is forgotten (all ones)
+    const unsigned char* keep_r;  // optional [N]: same for the reverse direction
+    float* F;                     // fwd: outputs [N,H]; bwd: dF, dR, dS
+    float* R;
+    float* S;
+    float* dZ;                    // bwd: [N, D*H]
+    float* dE;                    // bwd: [85, D], caller-zeroed, atomically accumulated
+    int N, D, H, deep;
+};
+
+__device__ __forceinline__ void load_relation_vectors(const MixParams& p, int n, int rf, float* ef, float* er, float* es) {
+    const bool forget_f = p.deep || (p.keep_f != nullptr && p.keep_f[n] == 0);
+    const bool forget_r = p.deep || (p.keep_r != nullptr && p.keep_r[n] == 0);
+    for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+        ef[d] = forget_f ? 1.f : p.E[(size_t)rf * p.D + d];
+        er[d] = forget_r ? 1.f : p.E[(size_t)(rf + kFwdBound) * p.D + d];
+        es[d] = p.deep ? 1.f : p.E[(size_t)kRevBound * p.D + d];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) relmix_fwd_kernel(const MixParams p) {
+    extern __shared__ float sm[];
+    float* ef = sm;
+    float* er = sm + p.D;
+    float* es = sm + 2 * p.D;
+    GPT_PDL_ENTER();
+    const size_t DH = (size_t)p.D * p.H;
+    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+        if (!(p.flags[n] & GPT_FLAG_INTREE)) {                 // CTA-uniform
+            for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+                p.F[(size_t)n * p.H + h] = 0.f;
+                p.R[(size_t)n * p.H + h] = 0.f;
+                p.S[(size_t)n * p.H + h] = 0.f;
+            }
+            continue;
+        }
+        load_relation_vectors(p, n, rel_id(p.deprel[n]), ef, er, es);
+        __syncthreads();
+        for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+            const float* __restrict__ z = p.Z + (size_t)n * DH + h;
+            const float* __restrict__ b = p.bias + h;
+            float f = 0.f, r = 0.f, s = 0.f;
+            for (int d = 0; d < p.D; ++d) {
+                const float v = z[(size_t)d * p.H] + b[(size_t)d * p.H];
+                f = fmaf(ef[d], v, f);
+                r = fmaf(er[d], v, r);
+                s = fmaf(es[d], v, s);
+            }
+            p.F[(size_t)n * p.H + h] = f;
+            p.R[(size_t)n * p.H + h] = r;
+            p.S[(size_t)n * p.H + h] = s;
+        }
+        __syncthreads();                                       // ef/er/es are rewritten for the next row
+    }
+}
+
+// smem: ef, er, es [D] | dF, dR, dS [H] | acc84 [D]
+__global__ void __launch_bounds__(kThreads) relmix_bwd_kernel(const MixParams p) {
+    extern __shared__ float sm[];
+    float* ef = sm;
+    float* er = sm + p.D;
+    float* es = sm + 2 * p.D;
+    float* gf = sm + 3 * p.D;
+    float* gr = gf + p.H;
+    float* gs = gr + p.H;
+    float* acc84 = gs + p.H;      // this CTA's share of the self-loop vector's gradient, flushed once at the end
+    GPT_PDL_ENTER();
+    const size_t DH = (size_t)p.D * p.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int d = threadIdx.x; d < p.D; d += blockDim.x) acc84[d] = 0.f;
+    __syncthreads();
+    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+        float* __restrict__ dz = p.dZ + (size_t)n * DH;
+        if (!(p.flags[n] & GPT_FLAG_INTREE)) {                 // CTA-uniform; the projection's gradients read every row
+            for (size_t i = threadIdx.x; i < DH; i += blockDim.x) dz[i] = 0.f;
+            continue;
+        }
+        const int rf = rel_id(p.deprel[n]);
+        const bool forget_f = p.deep || (p.keep_f != nullptr && p.keep_f[n] == 0);
+        const bool forget_r = p.deep || (p.keep_r != nullptr && p.keep_r[n] == 0);
+        load_relation_vectors(p, n, rf, ef, er, es);
+        for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+            gf[h] = p.F[(size_t)n * p.H + h];
+            gr[h] = p.R[(size_t)n * p.H + h];
+            gs[h] = p.S[(size_t)n * p.H + h];
+        }
+        __syncthreads();
+        const float* __restrict__ z = p.Z + (size_t)n * DH;
+        for (int d = warp; d < p.D; d += nwarps) {             // a relation slot d always belongs to the same warp
+            const float a = ef[d], b = er[d], c = es[d];
+            float sf = 0.f, sr = 0.f, ss = 0.f;
+            for (int h = lane; h < p.H; h += 32) {
+                const float v = z[(size_t)d * p.H + h] + p.bias[(size_t)d * p.H + h];
+                const float x = gf[h], y = gr[h], w = gs[h];
+                sf = fmaf(x, v, sf);
+                sr = fmaf(y, v, sr);
+                ss = fmaf(w, v, ss);
+                dz[(size_t)d * p.H + h] = fmaf(a, x, fmaf(b, y, c * w));
+            }
+            sf = warp_sum_f(sf);
+            sr = warp_sum_f(sr);
+            ss = warp_sum_f(ss);
+            if (lane == 0 && !p.deep) {
+                if (!forget_f && rf != 0) atomicAdd(p.dE + (size_t)rf * p.D + d, sf);      // row 0 is padding_idx
+                if (!forget_r) atomicAdd(p.dE + (size_t)(rf + kFwdBound) * p.D + d, sr);
+                acc84[d] += ss;
+            }
+        }
+        __syncthreads();
+    }
+    if (!p.deep)
+        for (int d = warp; d < p.D; d += nwarps)
+            if (lane == 0 && acc84[d] != 0.f) atomicAdd(p.dE + (size_t)kRevBound * p.D + d, acc84[d]);
+}
+
+// ---- diagonal mode: elementwise relation gates -----------------------------------------------------------------------
+struct DiagParams {
+    const float* x;               // [N,H]
+    const float* E;               // [85,H]
+    const long long* deprel;
+    const unsigned char* flags;
+    float* F;                     // fwd: outputs; bwd: dF, dR, dS
+    float* R;
+    float* S;
+    float* dx;                    // bwd [N,H]
+    float* dE;                    // bwd [85,H], caller-zeroed
+    int N, H;
+};
+
+__global__ void __launch_bounds__(kThreads) diagmix_fwd_kernel(const DiagParams p) {
+    GPT_PDL_ENTER();
+    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+        const bool in = (p.flags[n] & GPT_FLAG_INTREE) != 0;
+        const int rf = rel_id(p.deprel[n]);
+        for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+            const size_t o = (size_t)n * p.H + h;
+            const float v = in ? p.x[o] : 0.f;
+            p.F[o] = v * p.E[(size_t)rf * p.H + h];
+            p.R[o] = v * p.E[(size_t)(rf + kFwdBound) * p.H + h];
+            p.S[o] = v * p.E[(size_t)kRevBound * p.H + h];
+        }
+    }
+}
+
+// smem: acc84 [H]
+__global__ void __launch_bounds__(kThreads) diagmix_bwd_kernel(const DiagParams p) {
+    extern __shared__ float sm[];
+    GPT_PDL_ENTER();
+    for (int h = threadIdx.x; h < p.H; h += blockDim.x) sm[h] = 0.f;   // each thread only ever touches its own h
+    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+        const bool in = (p.flags[n] & GPT_FLAG_INTREE) != 0;
+        const int rf = rel_id(p.deprel[n]);
+        for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+            const size_t o = (size_t)n * p.H + h;
+            if (!in) {
+                p.dx[o] = 0.f;
+                continue;
+            }
+            const float a = p.F[o], b = p.R[o], c = p.S[o], v = p.x[o];
+            p.dx[o] = fmaf(a, p.E[(size_t)rf * p.H + h],
+                           fmaf(b, p.E[(size_t)(rf + kFwdBound) * p.H + h], c * p.E[(size_t)kRevBound * p.H + h]));
+            if (rf != 0) atomicAdd(p.dE + (size_t)rf * p.H + h, a * v);
+            atomicAdd(p.dE + (size_t)(rf + kFwdBound) * p.H + h, b * v);
+            sm[h] += c * v;
+        }
+    }
+    for (int h = threadIdx.x; h < p.H; h += blockDim.x)
+        if (sm[h] != 0.f) atomicAdd(p.dE + (size_t)kRevBound * p.H + h, sm[h]);
+}
+
+// ---- aggregation over the CSR with the layer epilogue -----------------------------------------------------------------
+struct Agg3Params {
+    const float* F;               // fwd: [N,H] inputs; bwd: unused
+    const float* R;
+    const float* S;
+    const float* gout;            // bwd: d loss / d out [N,H]
+    const float* outp;            // bwd: the forward's output (after dropout)
+    float* out;                   // fwd: [N,H]
+    float* dF;                    // bwd outputs [N,H]
+    float* dR;
+    float* dS;
+    const int* rowptr;            // [B, T+1]
+    const int* col;               // [B, cap]
+    const unsigned char* val;     // [B, cap]
+    const float* denom;           // [N]
+    const unsigned char* flags;   // [N]
+    const unsigned char* keep_f;  // optional dense [B,T,T] edge masks (tests), one per direction
+    const unsigned char* keep_r;
+    const unsigned long long* rng;   // {seed, step} on the device: in-kernel edge dropout / dropout
+    const float* drop_mask;       // optional explicit, pre-scaled dropout mask [N,H] (tests)
+    int B, T, H, cap, directed, self_loop;
+    unsigned layer;
+    float edge_keep, drop_p;
+};
+
+__device__ __forceinline__ bool is_fwd(int v) { return v > 0 && v < kFwdBound; }
+__device__ __forceinline__ bool is_rev(int v) { return v > kFwdBound && v < kRevBound; }
+
+__global__ void __launch_bounds__(kThreads) agg3_fwd_kernel(const Agg3Params p) {
+    GPT_PDL_ENTER();
+    const int N = p.B * p.T;
+    const bool philox_drop = p.drop_mask == nullptr && p.drop_p > 0.f && p.rng != nullptr;
+    const float scale = philox_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int b = n / p.T, i = n - b * p.T;
+        if (!(p.flags[n] & GPT_FLAG_INTREE)) {
+            for (int h = threadIdx.x; h < p.H; h += blockDim.x) p.out[(size_t)n * p.H + h] = 0.f;
+            continue;
+        }
+        const int e0 = p.rowptr[(size_t)b * (p.T + 1) + i], e1 = p.rowptr[(size_t)b * (p.T + 1) + i + 1];
+        const int* __restrict__ col = p.col + (size_t)b * p.cap;
+        const unsigned char* __restrict__ val = p.val + (size_t)b * p.cap;
+        const float dn = p.denom[n];
+        for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+            float acc = p.self_loop ? p.S[(size_t)n * p.H + h] : 0.f;
+            for (int e = e0; e < e1; ++e) {
+                const int j = col[e], v = val[e];
+                if (is_fwd(v)) {
+                    if (edge_kept(p.keep_f, p.rng, p.edge_keep, p.layer, 0u, b, i, j, p.T))
+                        acc += p.F[((size_t)b * p.T + j) * p.H + h];
+                } else if (is_rev(v) && !p.directed) {
+                    if (edge_kept(p.keep_r, p.rng, p.edge_keep, p.layer, 1u, b, i, j, p.T))
+                        acc += p.R[((size_t)b * p.T + j) * p.H + h];
+                }
+            }
+            float o = fmaxf(acc / dn, 0.f);
+            const size_t idx = (size_t)n * p.H + h;
+            if (p.drop_mask != nullptr) {
+                o *= p.drop_mask[idx];
+            } else if (philox_drop) {
+                const unsigned long long seed = p.rng[0], step = p.rng[1];
+                const Philox4 r = philox4x32((uint32_t)idx, (uint32_t)(idx >> 32), 0xD7090000u | p.layer, (uint32_t)step,
+                                             (uint32_t)seed, (uint32_t)(seed >> 32));
+                o = (u01(r.x) >= p.drop_p) ? o * scale : 0.f;
+            }
+            p.out[idx] = o;
+        }
+    }
+}
+
+// d(out)/d(z) recovered from the forward's output: out != 0 <=> the element was kept AND z > 0
+__device__ __forceinline__ float upstream(const Agg3Params& p, size_t idx, float scale, float inv_dn) {
+    const float o = p.outp[idx];
+    if (o == 0.f) return 0.f;
+    const float m = p.drop_mask != nullptr ? p.drop_mask[idx] : scale;
+    return p.gout[idx] * m * inv_dn;
+}
+
+__global__ void __launch_bounds__(kThreads) agg3_bwd_kernel(const Agg3Params p) {
+    GPT_PDL_ENTER();
+    const int N = p.B * p.T;
+    const bool philox_drop = p.drop_mask == nullptr && p.drop_p > 0.f && p.rng != nullptr;
+    const float scale = philox_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int b = n / p.T, j = n - b * p.T;
+        if (!(p.flags[n] & GPT_FLAG_INTREE)) {
+            for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+                const size_t idx = (size_t)n * p.H + h;
+                p.dF[idx] = 0.f;
+                p.dR[idx] = 0.f;
+                p.dS[idx] = 0.f;
+            }
+            continue;
+        }
+        const int e0 = p.rowptr[(size_t)b * (p.T + 1) + j], e1 = p.rowptr[(size_t)b * (p.T + 1) + j + 1];
+        const int* __restrict__ col = p.col + (size_t)b * p.cap;
+        const unsigned char* __restrict__ val = p.val + (size_t)b * p.cap;
+        const float inv_self = 1.f / p.denom[n];
+        for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
+            const size_t idx = (size_t)n * p.H + h;
+            float df = 0.f, dr = 0.f;
+            for (int e = e0; e < e1; ++e) {
+                const int i = col[e], v = val[e];
+                const size_t nb = ((size_t)b * p.T + i) * p.H + h;
+                if (is_rev(v)) {
+                    // i is j's parent: its row gathered F_j through entry [i, j] of the parent->child matrix
+                    if (edge_kept(p.keep_f, p.rng, p.edge_keep, p.layer, 0u, b, i, j, p.T))
+                        df += upstream(p, nb, scale, 1.f / p.denom[(size_t)b * p.T + i]);
+                } else if (is_fwd(v) && !p.directed) {
+                    // i is a child of j: its row gathered R_j through entry [i, j] of the child->parent matrix
+                    if (edge_kept(p.keep_r, p.rng, p.edge_keep, p.layer, 1u, b, i, j, p.T))
+                        dr += upstream(p, nb, scale, 1.f / p.denom[(size_t)b * p.T + i]);
+                }
+            }
+            p.dF[idx] = df;
+            p.dR[idx] = dr;
+            p.dS[idx] = p.self_loop ? upstream(p, idx, scale, inv_self) : 0.f;
+        }
+    }
+}
+
+// dense [B,T,T] copy of the Philox edge-keep decisions of one layer and direction (tests feed it to the oracle)
+__global__ void edge_keep_dense_kernel(const unsigned long long* __restrict__ rng, int B, int T, unsigned layer, unsigned dir,
+                                       float keep_prob, unsigned char* __restrict__ out) {
+    GPT_PDL_ENTER();
+    const size_t total = (size_t)B * T * T;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(k % T);
+        const size_t bi = k / T;
+        const int i = (int)(bi % T), b = (int)(bi / T);
+        out[k] = edge_kept(nullptr, rng, keep_prob, layer, dir, b, i, j, T) ? 1 : 0;
+    }
+}
+
+// per-token Bernoulli(keep_prop) for relation forgetting, one draw per direction (gcn.py:451-470)
+__global__ void token_keep_kernel(const unsigned long long* __restrict__ rng, int N, unsigned layer, float keep_prop,
+                                  unsigned char* __restrict__ keep_f, unsigned char* __restrict__ keep_r) {
+    GPT_PDL_ENTER();
+    const unsigned long long seed = rng[0], step = rng[1];
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const Philox4 r = philox4x32((uint32_t)n, 0u, 0xF0460000u | layer, (uint32_t)step, (uint32_t)seed,
+                                     (uint32_t)(seed >> 32));
+        keep_f[n] = u01(r.x) < keep_prop ? 1 : 0;
+        keep_r[n] = u01(r.y) < keep_prop ? 1 : 0;
+    }
+}
+
+// out[c] += sum_r a[r, c]   (bias gradient of the shared projection: column sums of dZ)
+__global__ void __launch_bounds__(256) colsum_acc_kernel(const float* __restrict__ a, long long rows, int cols, int chunk,
+                                                         float* __restrict__ out) {
+    GPT_PDL_ENTER();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long long r0 = (long long)blockIdx.y * chunk;
+    const long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += a[(size_t)r * cols + c];
+    atomicAdd(out + c, s);
+}
+
+inline unsigned row_grid(long long rows) {
+    const long long cap = 148LL * 16;      // resident CTAs of 128 threads per SM x SM count: one wave, grid-stride beyond
+    return (unsigned)(rows < 1 ? 1 : (rows < cap ? rows : cap));
+}
+
+}  // namespace
+
+extern "C" int gpt_relmix_fwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                              const uint8_t* keep_f, const uint8_t* keep_r, int N, int D, int H, int deep, float* F,
+                              float* R, float* S, void* stream) {
+    GPT_CHECK_ARG(Z && bias && E && deprel && flags && F && R && S && N >= 0 && D >= 1 && H >= 1);
+    if (N == 0) return GPT_OK;
+    if ((size_t)3 * D * sizeof(float) > 48 * 1024) return GPT_ERR_UNSUPPORTED;
+    MixParams p{};
+    p.Z = Z; p.bias = bias; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags;
+    p.keep_f = keep_f; p.keep_r = keep_r; p.F = F; p.R = R; p.S = S; p.N = N; p.D = D; p.H = H; p.deep = deep;
+    gpt_launch(relmix_fwd_kernel, dim3(row_grid(N)), dim3(kThreads), (size_t)3 * D * sizeof(float), (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_relmix_bwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                              const uint8_t* keep_f, const uint8_t* keep_r, const float* dF, const float* dR,
+                              const float* dS, int N, int D, int H, int deep, float* dZ, float* dE, void* stream) {
+    GPT_CHECK_ARG(Z && bias && E && deprel && flags && dF && dR && dS && dZ && dE && N >= 0 && D >= 1 && H >= 1);
+    if (N == 0) return GPT_OK;
+    const size_t smem = ((size_t)4 * D + 3 * H) * sizeof(float);
+    if (smem > 48 * 1024) return GPT_ERR_UNSUPPORTED;
+    MixParams p{};
+    p.Z = Z; p.bias = bias; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags;
+    p.keep_f = keep_f; p.keep_r = keep_r; p.F = const_cast<float*>(dF); p.R = const_cast<float*>(dR);
+    p.S = const_cast<float*>(dS); p.dZ = dZ; p.dE = dE; p.N = N; p.D = D; p.H = H; p.deep = deep;
+    gpt_launch(relmix_bwd_kernel, dim3(row_grid(N)), dim3(kThreads), smem, (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_diagmix_fwd(const float* x, const float* E, const int64_t* deprel, const uint8_t* flags, int N, int H,
+                               float* F, float* R, float* S, void* stream) {
+    GPT_CHECK_ARG(x && E && deprel && flags && F && R && S && N >= 0 && H >= 1);
+    if (N == 0) return GPT_OK;
+    DiagParams p{};
+    p.x = x; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags; p.F = F; p.R = R; p.S = S;
+    p.N = N; p.H = H;
+    gpt_launch(diagmix_fwd_kernel, dim3(row_grid(N)), dim3(kThreads), 0, (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_diagmix_bwd(const float* x, const float* E, const int64_t* deprel, const uint8_t* flags, const float* dF,
+                               const float* dR, const float* dS, int N, int H, float* dx, float* dE, void* stream) {
+    GPT_CHECK_ARG(x && E && deprel && flags && dF && dR && dS && dx && dE && N >= 0 && H >= 1);
+    if (N == 0) return GPT_OK;
+    if ((size_t)H * sizeof(float) > 48 * 1024) return GPT_ERR_UNSUPPORTED;
+    DiagParams p{};
+    p.x = x; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags;
+    p.F = const_cast<float*>(dF); p.R = const_cast<float*>(dR); p.S = const_cast<float*>(dS); p.dx = dx; p.dE = dE;
+    p.N = N; p.H = H;
+    gpt_launch(diagmix_bwd_kernel, dim3(row_grid(N)), dim3(kThreads), (size_t)H * sizeof(float), (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+static int fill_agg3(Agg3Params& p, const int32_t* rowptr, const int32_t* col, const uint8_t* val, const float* denom,
+                     const uint8_t* flags, const uint8_t* keep_f, const uint8_t* keep_r, float edge_keep, const void* rng,
+                     unsigned layer, int directed, int self_loop, float drop_p, const float* drop_mask, int B, int T, int H) {
+    GPT_CHECK_ARG(rowptr && col && val && denom && flags && B >= 0 && T >= 1 && H >= 1);
+    GPT_CHECK_ARG(edge_keep >= 0.f && drop_p >= 0.f && drop_p < 1.f && layer < 0x8000u);
+    GPT_CHECK_ARG(!(edge_keep < 1.f && !(keep_f && keep_r) && rng == nullptr));
+    p.rowptr = rowptr; p.col = col; p.val = val; p.denom = denom; p.flags = flags; p.keep_f = keep_f; p.keep_r = keep_r;
+    p.rng = static_cast<const unsigned long long*>(rng); p.drop_mask = drop_mask; p.B = B; p.T = T; p.H = H; p.cap = 3 * T;
+    p.directed = directed; p.self_loop = self_loop; p.layer = layer; p.edge_keep = edge_keep; p.drop_p = drop_p;
+    return GPT_OK;
+}
+
+extern "C" int gpt_agg3_fwd(const float* F, const float* R, const float* S, const int32_t* rowptr, const int32_t* col,
+                            const uint8_t* val, const float* denom, const uint8_t* flags, const uint8_t* keep_f,
+                            const uint8_t* keep_r, float edge_keep, const void* rng_state, unsigned layer, int directed,
+                            int self_loop, float drop_p, const float* drop_mask, int B, int T, int H, float* out,
+                            void* stream) {
+    GPT_CHECK_ARG(F && R && S && out);
+    Agg3Params p{};
+    int rc = fill_agg3(p, rowptr, col, val, denom, flags, keep_f, keep_r, edge_keep, rng_state, layer, directed, self_loop,
+                       drop_p, drop_mask, B, T, H);
+    if (rc != GPT_OK) return rc;
+    if (B == 0) return GPT_OK;
+    p.F = F; p.R = R; p.S = S; p.out = out;
+    gpt_launch(agg3_fwd_kernel, dim3(row_grid((long long)B * T)), dim3(kThreads), 0, (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_agg3_bwd(const float* gout, const float* out, const int32_t* rowptr, const int32_t* col,
+                            const uint8_t* val, const float* denom, const uint8_t* flags, const uint8_t* keep_f,
+                            const uint8_t* keep_r, float edge_keep, const void* rng_state, unsigned layer, int directed,
+                            int self_loop, float drop_p, const float* drop_mask, int B, int T, int H, float* dF, float* dR,
+                            float* dS, void* stream) {
+    GPT_CHECK_ARG(gout && out && dF && dR && dS);
+    Agg3Params p{};
+    int rc = fill_agg3(p, rowptr, col, val, denom, flags, keep_f, keep_r, edge_keep, rng_state, layer, directed, self_loop,
+                       drop_p, drop_mask, B, T, H);
+    if (rc != GPT_OK) return rc;
+    if (B == 0) return GPT_OK;
+    p.gout = gout; p.outp = out; p.dF = dF; p.dR = dR; p.dS = dS;
+    gpt_launch(agg3_bwd_kernel, dim3(row_grid((long long)B * T)), dim3(kThreads), 0, (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_edge_keep_dense(const void* rng_state, int B, int T, unsigned layer, int dir, float keep_prob,
+                                   uint8_t* out, void* stream) {
+    GPT_CHECK_ARG(rng_state && out && B >= 0 && T >= 1 && (dir == 0 || dir == 1) && layer < 0x8000u);
+    if (B == 0) return GPT_OK;
+    const size_t total = (size_t)B * T * T;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gpt_launch(edge_keep_dense_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+               static_cast<const unsigned long long*>(rng_state), B, T, layer, (unsigned)dir, keep_prob, out);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_relation_keep_tokens(const void* rng_state, int N, unsigned layer, float keep_prop, uint8_t* keep_f,
+                                        uint8_t* keep_r, void* stream) {
+    GPT_CHECK_ARG(rng_state && keep_f && keep_r && N >= 0 && layer < 0x8000u);
+    if (N == 0) return GPT_OK;
+    int blocks = (N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gpt_launch(token_keep_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+               static_cast<const unsigned long long*>(rng_state), N, layer, keep_prop, keep_f, keep_r);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* stream) {
+    GPT_CHECK_ARG(a && out && rows >= 0 && cols >= 1);
+    if (rows == 0) return GPT_OK;
+    const int chunk = 64;
+    const long long row_blocks = (rows + chunk - 1) / chunk;
+    GPT_CHECK_ARG(row_blocks <= 65535);
+    gpt_launch(colsum_acc_kernel, dim3((unsigned)((cols + 255) / 256), (unsigned)row_blocks), dim3(256), 0,
+               (cudaStream_t)stream, a, rows, cols, chunk, out);
+    return gpt_launch_status();
+}

@@ -28,17 +28,26 @@ extern unsigned long long g_gpt_launches;
 // the preceding grid has COMPLETED and its memory is visible (so nothing about data dependencies changes, reads and
 // writes alike), `griddepcontrol.launch_dependents` lets the grid after this one start its own launch.  Captured
 // into a CUDA graph these become programmatic edges.  GPT_PDL=0 in the environment launches without the attribute.
+#ifdef GPT_HOST_EMULATION   // tests/emu: the kernels' source compiled for the host (no GPU in the build container)
+#define GPT_PDL_ENTER() do { } while (0)
+#else
 #define GPT_PDL_ENTER()                                                   \
     do {                                                                  \
         asm volatile("griddepcontrol.wait;" ::: "memory");                \
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
     } while (0)
+#endif
 
 // Kernels whose prologue touches nothing the preceding grid produces (shared-memory / tensor-memory set-up, reads of
 // data that older grids wrote) trigger first, run the prologue, and only then wait -- the prologue overlaps the tail of
 // the preceding grid.  Global WRITES always come after the wait (the preceding grid may still read a recycled buffer).
+#ifdef GPT_HOST_EMULATION
+#define GPT_PDL_TRIGGER() do { } while (0)
+#define GPT_PDL_WAIT() do { } while (0)
+#else
 #define GPT_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define GPT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 
 extern int g_gpt_pdl;
 

@@ -298,6 +298,8 @@ class FusedTrainStep(object):
             return 'optimizer is not plain SGD'
         if opt.get('rnn', False):
             return 'C-GCN encoder (cuDNN LSTM) runs under autograd'
+        if opt.get('adj_type', 'regular') != 'regular':
+            return 'relation-aware layers (csrc/deprel.cu) run under autograd'
         if opt.get('conv_l2', 0) > 0:
             return 'conv_l2 > 0'
         if opt['hidden_dim'] % 4 != 0 or opt['mlp_layers'] > 4:

@@ -1,6 +1,7 @@
 """GCN relation classifier on the B200 kernels -- same classes, constructor arguments, forward signatures and
 ``state_dict`` keys as /root/reference/model/gcn.py (GCNClassifier :15-36, GCNRelationModel :38-126, GCN :128-470,
-pool :473-483, rnn_zero_state :485-492), ``adj_type='regular'`` path.
+pool :473-483, rnn_zero_state :485-492): ``adj_type='regular'`` and the fork's relation-aware ``'full_deprel'`` /
+``'diagonal_deprel'`` layers (gcn.py:272-386, 400-470).
 
 What changed underneath:
   * the per-sentence numpy loop + dense [B,T,T] adjacency (gcn.py:96-110) is one kernel launch that leaves a CSR
@@ -8,6 +9,9 @@ What changed underneath:
   * each layer is one projection GEMM + one fused gather/normalise/ReLU/dropout kernel (ops.gcn_layer) instead
     of bmm + 2 Linear + div + relu + dropout (gcn.py:269-271, 390-393)
   * the three pool() passes + cat (gcn.py:116-121) are one kernel (ops.pool3)
+  * relation-aware layers: one projection GEMM shared by the forward / reverse / self-loop traversals + a relation
+    mix kernel + a direction-aware CSR gather (ops.relation_layer_full / relation_layer_diag -> csrc/deprel.cu)
+    instead of three [B,T,D,K] outer products, three [D,K,H] contractions and two dense bmm per layer
 There is no CPU implementation: inputs must live on a CUDA device.
 """
 import os
@@ -50,9 +54,10 @@ class GCNClassifier(nn.Module):
 class GCNRelationModel(nn.Module):
     def __init__(self, opt, emb_matrix=None):
         super().__init__()
-        if opt.get('adj_type', 'regular') != 'regular':
-            raise NotImplementedError("adj_type=%r: only the 'regular' adjacency path is built (SURVEY.md 8f-2)"
-                                      % opt['adj_type'])
+        adj_type = opt.get('adj_type', 'regular')
+        if adj_type not in ('regular', 'full_deprel', 'diagonal_deprel'):
+            # 'concat_deprel' builds weights in the reference but its forward raises ValueError (gcn.py:388)
+            raise NotImplementedError("adj_type=%r is not a working mode of the reference (SURVEY.md 10-3)" % adj_type)
         self.opt = opt
         self.emb_matrix = emb_matrix
         # tables are registered here AND on self.gcn, as in the reference (gcn.py:45-57,138): the checkpoint
@@ -60,7 +65,10 @@ class GCNRelationModel(nn.Module):
         self.emb = nn.Embedding(opt['vocab_size'], opt['emb_dim'], padding_idx=constant.PAD_ID)
         self.pos_emb = nn.Embedding(constant.NUM_POS, opt['pos_dim']) if opt['pos_dim'] > 0 else None
         self.ner_emb = nn.Embedding(constant.NUM_NER, opt['ner_dim']) if opt['ner_dim'] > 0 else None
-        self.deprel_emb = nn.Embedding(constant.NUM_DEPREL, 1, padding_idx=0)   # unused by 'regular' (gcn.py:53-56)
+        # relation vectors (gcn.py:48-57): width hidden_dim ('diagonal_deprel'), deprel_emb_dim ('full_deprel'), or a
+        # dummy column that 'regular' never reads
+        side = {'regular': 1, 'diagonal_deprel': opt['hidden_dim']}.get(adj_type, opt.get('deprel_emb_dim', 1))
+        self.deprel_emb = nn.Embedding(constant.NUM_DEPREL, side, padding_idx=0)
         self.init_embeddings()
         self.gcn = GCN(opt, (self.emb, self.pos_emb, self.ner_emb, self.deprel_emb), opt['hidden_dim'],
                        opt['num_layers'])
@@ -109,7 +117,7 @@ class GCNRelationModel(nn.Module):
 
 
 class GCN(nn.Module):
-    """GCN / C-GCN over the pruned-tree CSR (reference gcn.py:128-395, regular branch)."""
+    """GCN / C-GCN over the pruned-tree CSR (reference gcn.py:128-470)."""
 
     def __init__(self, opt, embeddings, mem_dim, num_layers):
         super().__init__()
@@ -128,7 +136,20 @@ class GCN(nn.Module):
         self.gcn_drop = nn.Dropout(opt['gcn_dropout'])   # kept for API parity; the fused kernel draws its own mask
         if opt.get('emb_dropout', 0.0) > 0:
             raise NotImplementedError('emb_dropout > 0 (EmbeddingDropout) is outside the built path (SURVEY.md 2-#8)')
-        self.W = nn.ModuleList(nn.Linear(self.in_dim if l == 0 else mem_dim, mem_dim) for l in range(num_layers))
+        self.adj_type = opt.get('adj_type', 'regular')
+        if self.adj_type == 'diagonal_deprel':       # gcn.py:153-155: a preprocessor, no per-layer weights at all
+            self.preprocessor = nn.Linear(self.in_dim, mem_dim)
+            self.in_dim = mem_dim
+        elif self.adj_type == 'full_deprel':         # gcn.py:164-167: ONE Linear(in, D*H) shared by every layer
+            if num_layers > 1 and self.in_dim != mem_dim:
+                raise ValueError('full_deprel shares one Linear(in_dim, D*H) between the layers (gcn.py:164-167,301): the '
+                                 'GCN input width %d must equal hidden_dim %d (the reference fails inside einsum)'
+                                 % (self.in_dim, mem_dim))
+            self.W = nn.Linear(self.in_dim, opt['deprel_emb_dim'] * mem_dim, bias=True)
+        else:
+            self.W = nn.ModuleList(nn.Linear(self.in_dim if l == 0 else mem_dim, mem_dim) for l in range(num_layers))
+        if self.adj_type != 'regular' and (opt.get('edge_keep_prob', 1.0) <= 0 or opt.get('deprel_keep_prop', 1.0) < 0):
+            raise ValueError('edge_keep_prob must be in (0, 1], deprel_keep_prop in [0, 1]')
         # projection arithmetic: 'tf32x3' = tcgen05 3xTF32 (fp32-grade, passes the 1e-5 parity tests; FFMA fallback for
         # shapes TMA cannot describe), 'fp32' = FFMA everywhere, 'tf32' = one TF32 pass (~1e-3)
         self.gemm_mode = opt.get('gemm_mode', 'tf32x3')
@@ -139,7 +160,11 @@ class GCN(nn.Module):
         self.sparse_embedding = None    # ops.SparseEmbeddingState while engine.GraphedTrainStep drives the step
 
     def conv_l2(self):
-        return sum(p.pow(2).sum() for lin in self.W for p in (lin.weight, lin.bias))
+        if self.adj_type == 'full_deprel':
+            # the reference iterates `for w in self.W` over a single nn.Linear and raises TypeError (gcn.py:182,
+            # SURVEY.md 10-3); the penalty it evidently meant is the one over that shared layer
+            return self.W.weight.pow(2).sum() + self.W.bias.pow(2).sum()
+        return sum(p.pow(2).sum() for lin in self.W for p in (lin.weight, lin.bias))   # 'diagonal_deprel' has no W
 
     def get_gcn_parameters(self):
         return self.W
@@ -217,8 +242,10 @@ class GCN(nn.Module):
                                  topn=self.opt['topn'], sparse=self.sparse_embedding)
         if self.opt.get('rnn', False):
             x = self._host_dropout(self.encode_with_rnn(x, masks, words.size(0)), self.rnn_drop, 'rnn')
-        use_adj = not self.opt.get('no_adj', False)
         drop_p = self.opt['gcn_dropout'] if self.training else 0.0
+        if self.adj_type != 'regular':
+            return self._relation_layers(x, adj, deprel, drop_p), adj.pool_mask()
+        use_adj = not self.opt.get('no_adj', False)
         for l, lin in enumerate(self.W):
             last = l == self.layers - 1
             mask = None if self.injected_masks is None else self.injected_masks.get('gcn%d' % l)
@@ -226,6 +253,50 @@ class GCN(nn.Module):
             x = ops.gcn_layer(x, lin.weight, lin.bias, adj, use_adj=use_adj, drop_p=p, rng_state=self.rng_state,
                               subseq=l, drop_mask=None if last else mask, gemm_mode=self.gemm_mode)
         return x, adj.pool_mask()
+
+
+def _relation_layers(self, x, csr, deprel, drop_p):
+    """The layer loop of the relation-aware modes (gcn.py:272-386 + 390-393).  `no_adj` has no effect here, as in the
+    reference (these branches re-derive their masks from `adj`, gcn.py:276,308)."""
+    opt = self.opt
+    emb = self.deprel_emb.weight
+    injected = self.injected_masks
+    full = self.adj_type == 'full_deprel'
+    if full:
+        D, H = opt['deprel_emb_dim'], self.mem_dim
+        # weight_l = W.weight.reshape(D, in, H) is a reshape of the [D*H, in] matrix, not a permute (gcn.py:301);
+        # the projection GEMM wants the [D*H, in] matrix whose row d*H+h is weight_l[d, :, h]
+        wmat = self.W.weight.reshape(D, -1, H).permute(0, 2, 1).reshape(D * H, -1).contiguous()
+        ws = ops.weight_prep(wmat.detach(), self.gemm_mode)
+    else:
+        x = ops.linear(x, self.preprocessor.weight, self.preprocessor.bias, self.gemm_mode)    # gcn.py:255-257
+    B, T = csr.B, csr.T
+    for l in range(self.layers):
+        last = l == self.layers - 1
+        mask = None if injected is None else injected.get('gcn%d' % l)
+        cfg = ops.RelationLayerConfig(l, drop_p=0.0 if (last or mask is not None) else drop_p,
+                                      drop_mask=None if last else mask, rng_state=self.rng_state,
+                                      gemm_mode=self.gemm_mode)
+        if not full:
+            x = ops.relation_layer_diag(x, emb, csr, deprel, cfg)
+            continue
+        cfg.deep = l >= opt['deprel_max_depth']
+        cfg.directed, cfg.self_loop = bool(opt['deprel_directed']), bool(opt['deprel_self_loop'])
+        if injected is not None and ('edge_f%d' % l) in injected:
+            # tests: dense 0/1 [B,T,T] masks per direction, as maybe_drop_edges draws them (gcn.py:436-449)
+            cfg.keep_edges = tuple(injected['edge_%s%d' % (d, l)].to(torch.uint8).contiguous() for d in 'fr')
+        elif self.training and opt.get('edge_keep_prob', 1.0) < 1.0:
+            cfg.edge_keep = opt['edge_keep_prob']
+        if injected is not None and ('forget_f%d' % l) in injected:
+            cfg.keep_tokens = tuple(injected['forget_%s%d' % (d, l)].reshape(-1).to(torch.uint8).contiguous()
+                                    for d in 'fr')
+        elif self.training and opt.get('deprel_keep_prop', 1.0) < 1.0:
+            cfg.keep_tokens = ops.relation_keep_tokens(self.rng_state, B * T, l, opt['deprel_keep_prop'])
+        x = ops.relation_layer_full(x, wmat, self.W.bias, emb, csr, deprel, cfg, ws)
+    return x
+
+
+GCN._relation_layers = _relation_layers
 
 
 def pool(h, mask, type='max'):

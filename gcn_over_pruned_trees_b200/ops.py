@@ -328,6 +328,189 @@ def gcn_layer(x, weight, bias, csr, use_adj=True, drop_p=0.0, rng_state=None, su
     return _GcnLayer.apply(x, weight, bias, csr, use_adj, drop_p, rng_state, subseq, drop_mask, gemm_mode)
 
 
+# ---- K10: relation-aware layers (adj_type full_deprel / diagonal_deprel) ---------------------------------------------
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b on the K3 GEMMs (the diagonal mode's preprocessor, model/gcn.py:153-155, 255-257)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gemm_mode):
+        x = _dev(x, torch.float32, 'x')
+        weight = _dev(weight, torch.float32, 'weight')
+        ws = weight_prep(weight, gemm_mode)
+        y = linear_fwd(x.view(-1, x.shape[-1]), weight, gemm_mode, ws)
+        if bias is not None:
+            y += bias
+        ctx.gemm_mode = gemm_mode
+        ctx.save_for_backward(x, weight, ws)
+        return y.view(x.shape[:-1] + (weight.shape[0],))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, ws = ctx.saved_tensors
+        gy2 = _dev(gy, torch.float32, 'grad_out').view(-1, weight.shape[0])
+        dx = linear_dgrad(gy2, weight, ctx.gemm_mode, ws).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = linear_wgrad(gy2, x.view(-1, x.shape[-1]), ctx.gemm_mode) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.needs_input_grad[2]:
+            db = torch.zeros((weight.shape[0],), dtype=torch.float32, device=gy2.device)
+            _call('gpt_colsum_acc', _ptr(gy2), gy2.shape[0], gy2.shape[1], _ptr(db), _stream())
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, gemm_mode='fp32'):
+    return _Linear.apply(x, weight, bias, gemm_mode)
+
+
+class RelationLayerConfig(object):
+    """Per-layer switches of the relation-aware modes (all host scalars except the optional test masks)."""
+    __slots__ = ('layer', 'deep', 'directed', 'self_loop', 'edge_keep', 'keep_edges', 'keep_tokens', 'drop_p',
+                 'drop_mask', 'rng_state', 'gemm_mode')
+
+    def __init__(self, layer, deep=False, directed=False, self_loop=True, edge_keep=1.0, keep_edges=None,
+                 keep_tokens=None, drop_p=0.0, drop_mask=None, rng_state=None, gemm_mode='fp32'):
+        self.layer, self.deep, self.directed, self.self_loop = int(layer), bool(deep), bool(directed), bool(self_loop)
+        self.edge_keep = float(edge_keep)
+        self.keep_edges = keep_edges        # None or (uint8 [B,T,T] parent->child matrix, uint8 [B,T,T] child->parent)
+        self.keep_tokens = keep_tokens      # None or (uint8 [B*T] forward, uint8 [B*T] reverse): 0 = relation forgotten
+        self.drop_p, self.drop_mask, self.rng_state, self.gemm_mode = float(drop_p), drop_mask, rng_state, gemm_mode
+
+
+def edge_keep_dense(rng_state, B, T, layer, direction, keep_prob):
+    """The in-kernel edge-dropout decisions of (layer, direction) as a dense uint8 [B,T,T] (tests)."""
+    out = torch.empty((B, T, T), dtype=torch.uint8, device=rng_state.device)
+    _call('gpt_edge_keep_dense', _ptr(rng_state), B, T, int(layer), int(direction), float(keep_prob), _ptr(out),
+          _stream())
+    return out
+
+
+def relation_keep_tokens(rng_state, n_rows, layer, keep_prop):
+    """Relation forgetting draws (model/gcn.py:451-470): (keep_forward, keep_reverse) uint8 [n_rows]."""
+    kf = torch.empty((n_rows,), dtype=torch.uint8, device=rng_state.device)
+    kr = torch.empty((n_rows,), dtype=torch.uint8, device=rng_state.device)
+    _call('gpt_relation_keep_tokens', _ptr(rng_state), int(n_rows), int(layer), float(keep_prop), _ptr(kf), _ptr(kr),
+          _stream())
+    return kf, kr
+
+
+def _agg3_fwd(F, R, S, csr, cfg):
+    B, T = csr.B, csr.T
+    H = F.shape[-1]
+    out = torch.empty((B, T, H), dtype=torch.float32, device=F.device)
+    kf, kr = cfg.keep_edges if cfg.keep_edges is not None else (None, None)
+    _call('gpt_agg3_fwd', _ptr(F), _ptr(R), _ptr(S), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(csr.denom),
+          _ptr(csr.flags), _ptr(kf), _ptr(kr), cfg.edge_keep, _ptr(cfg.rng_state), cfg.layer, int(cfg.directed),
+          int(cfg.self_loop), cfg.drop_p if cfg.drop_mask is None else 0.0, _ptr(cfg.drop_mask), B, T, H, _ptr(out),
+          _stream())
+    return out
+
+
+def _agg3_bwd(gout, out, csr, cfg):
+    B, T = csr.B, csr.T
+    H = gout.shape[-1]
+    dF, dR, dS = (torch.empty((B * T, H), dtype=torch.float32, device=gout.device) for _ in range(3))
+    kf, kr = cfg.keep_edges if cfg.keep_edges is not None else (None, None)
+    _call('gpt_agg3_bwd', _ptr(gout), _ptr(out), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.val), _ptr(csr.denom),
+          _ptr(csr.flags), _ptr(kf), _ptr(kr), cfg.edge_keep, _ptr(cfg.rng_state), cfg.layer, int(cfg.directed),
+          int(cfg.self_loop), cfg.drop_p if cfg.drop_mask is None else 0.0, _ptr(cfg.drop_mask), B, T, H, _ptr(dF),
+          _ptr(dR), _ptr(dS), _stream())
+    return dF, dR, dS
+
+
+class _RelationLayerFull(torch.autograd.Function):
+    """One full_deprel layer (model/gcn.py:296-386 + 390-393): ONE projection GEMM Z = x Wmat^T shared by the three
+    directions, relation mix, CSR aggregation with the layer epilogue (csrc/deprel.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, wmat, bias, emb, csr, deprel, cfg, ws):
+        x = _dev(x, torch.float32, 'x')
+        wmat = _dev(wmat, torch.float32, 'wmat')
+        bias = _dev(bias, torch.float32, 'bias')
+        emb = _dev(emb, torch.float32, 'deprel_emb.weight')
+        deprel = _dev(deprel, torch.int64, 'deprel')
+        B, T, K = x.shape
+        D = emb.shape[1]
+        H = wmat.shape[0] // D
+        N = B * T
+        if emb.shape[0] != 85 or wmat.shape != (D * H, K) or bias.numel() != D * H:
+            raise _lib.GptError('full_deprel layer: inconsistent shapes')
+        Z = linear_fwd(x.view(N, K), wmat, cfg.gemm_mode, ws)
+        F, R, S = (torch.empty((N, H), dtype=torch.float32, device=x.device) for _ in range(3))
+        kf, kr = cfg.keep_tokens if cfg.keep_tokens is not None else (None, None)
+        _call('gpt_relmix_fwd', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr), N, D,
+              H, int(cfg.deep), _ptr(F), _ptr(R), _ptr(S), _stream())
+        out = _agg3_fwd(F, R, S, csr, cfg)
+        ctx.csr, ctx.cfg, ctx.dims = csr, cfg, (B, T, K, D, H)
+        ctx.save_for_backward(x, wmat, bias, emb, deprel, Z, out, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, wmat, bias, emb, deprel, Z, out, ws = ctx.saved_tensors
+        csr, cfg = ctx.csr, ctx.cfg
+        B, T, K, D, H = ctx.dims
+        N = B * T
+        gout = _dev(gout, torch.float32, 'grad_out')
+        dF, dR, dS = _agg3_bwd(gout, out, csr, cfg)
+        dZ = torch.empty((N, D * H), dtype=torch.float32, device=gout.device)
+        dE = torch.zeros_like(emb)
+        kf, kr = cfg.keep_tokens if cfg.keep_tokens is not None else (None, None)
+        _call('gpt_relmix_bwd', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
+              _ptr(dF), _ptr(dR), _ptr(dS), N, D, H, int(cfg.deep), _ptr(dZ), _ptr(dE), _stream())
+        dbias = None
+        if ctx.needs_input_grad[2]:
+            dbias = torch.zeros((D * H,), dtype=torch.float32, device=gout.device)
+            _call('gpt_colsum_acc', _ptr(dZ), N, D * H, _ptr(dbias), _stream())
+        dx = linear_dgrad(dZ, wmat, cfg.gemm_mode, ws).view(B, T, K) if ctx.needs_input_grad[0] else None
+        dw = linear_wgrad(dZ, x.view(N, K), cfg.gemm_mode) if ctx.needs_input_grad[1] else None
+        return dx, dw, dbias, (dE if ctx.needs_input_grad[3] else None), None, None, None, None
+
+
+def relation_layer_full(x, wmat, bias, emb, csr, deprel, cfg, ws=None):
+    """x [B,T,K]; wmat [D*H, K] with wmat[d*H+h, k] = W.weight.reshape(D,K,H)[d,k,h] (model/gcn.py:301); bias [D*H]."""
+    if ws is None:
+        ws = weight_prep(wmat, cfg.gemm_mode)
+    return _RelationLayerFull.apply(x, wmat, bias, emb, csr, deprel, cfg, ws)
+
+
+class _RelationLayerDiag(torch.autograd.Function):
+    """One diagonal_deprel layer (model/gcn.py:272-294 + 390-393): elementwise relation gates + CSR aggregation."""
+
+    @staticmethod
+    def forward(ctx, x, emb, csr, deprel, cfg):
+        x = _dev(x, torch.float32, 'x')
+        emb = _dev(emb, torch.float32, 'deprel_emb.weight')
+        deprel = _dev(deprel, torch.int64, 'deprel')
+        B, T, H = x.shape
+        N = B * T
+        if emb.shape != (85, H):
+            raise _lib.GptError('diagonal_deprel layer: deprel_emb must be [85, hidden_dim]')
+        F, R, S = (torch.empty((N, H), dtype=torch.float32, device=x.device) for _ in range(3))
+        _call('gpt_diagmix_fwd', _ptr(x), _ptr(emb), _ptr(deprel), _ptr(csr.flags), N, H, _ptr(F), _ptr(R), _ptr(S),
+              _stream())
+        out = _agg3_fwd(F, R, S, csr, cfg)
+        ctx.csr, ctx.cfg = csr, cfg
+        ctx.save_for_backward(x, emb, deprel, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, emb, deprel, out = ctx.saved_tensors
+        B, T, H = x.shape
+        N = B * T
+        gout = _dev(gout, torch.float32, 'grad_out')
+        dF, dR, dS = _agg3_bwd(gout, out, ctx.csr, ctx.cfg)
+        dx = torch.empty((B, T, H), dtype=torch.float32, device=gout.device)
+        dE = torch.zeros_like(emb)
+        _call('gpt_diagmix_bwd', _ptr(x), _ptr(emb), _ptr(deprel), _ptr(ctx.csr.flags), _ptr(dF), _ptr(dR), _ptr(dS), N,
+              H, _ptr(dx), _ptr(dE), _stream())
+        return dx, dE, None, None, None
+
+
+def relation_layer_diag(x, emb, csr, deprel, cfg):
+    return _RelationLayerDiag.apply(x, emb, csr, deprel, cfg)
+
+
 # ---- K4: pooling -----------------------------------------------------------------------------------------------
 
 class _Pool3(torch.autograd.Function):

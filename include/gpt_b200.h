@@ -263,6 +263,56 @@ int gpt_build_batch(const int32_t* const* arena, const int64_t* offsets, const i
                     int B, int T, float word_dropout, uint64_t seed, uint64_t stream_id, int64_t* const* out,
                     uint8_t* masks, int64_t* rels, void* stream);
 
+/* K10. relation-aware GCN layers (csrc/deprel.cu): adj_type 'full_deprel' (model/gcn.py:296-386, 400-434) and
+ *      'diagonal_deprel' (model/gcn.py:272-294), with edge dropout (:436-449), relation forgetting (:451-470),
+ *      deprel_max_depth, deprel_directed, deprel_self_loop, and the common /denom, ReLU, gcn_drop (:390-393).
+ *      The layer is: Z = x . Wmat^T with gpt_linear_fwd_* (Wmat[d*H+h, k] = W.weight.reshape(D,K,H)[d,k,h], :301),
+ *      gpt_relmix_fwd, gpt_agg3_fwd; backward: gpt_agg3_bwd, gpt_relmix_bwd, gpt_colsum_acc, gpt_linear_dgrad/wgrad_*.
+ *
+ * gpt_relmix_fwd: F/R/S[n,:] = sum_d e[d] (Z[n,d,:] + bias[d,:]) with e = E[deprel[n]] / E[deprel[n]+42] / E[84]
+ *     (traverse_deprel :400-415, traverse_self_loop :417-434).  E float [85,D]; Z float [N, D*H]; bias float [D*H];
+ *     keep_f / keep_r (optional uint8 [N]): 0 = the token's relation vector of that direction is replaced by ones
+ *     (maybe_forget_deprels); deep != 0 = every vector is ones (layer >= deprel_max_depth, :324-325,355-356,376-379).
+ *     Rows without GPT_FLAG_INTREE are written 0.
+ * gpt_relmix_bwd: dZ [N, D*H] (zeros on rows outside the tree) and dE [85,D] += (caller-zeroed, atomics; row 0 =
+ *     padding_idx and forgotten / deep vectors get nothing) from dF, dR, dS [N,H]. */
+int gpt_relmix_fwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                   const uint8_t* keep_f, const uint8_t* keep_r, int N, int D, int H, int deep, float* F, float* R,
+                   float* S, void* stream);
+int gpt_relmix_bwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                   const uint8_t* keep_f, const uint8_t* keep_r, const float* dF, const float* dR, const float* dS, int N,
+                   int D, int H, int deep, float* dZ, float* dE, void* stream);
+/* diagonal_deprel (model/gcn.py:272-294): F = E[deprel] * x, R = E[deprel+42] * x, S = E[84] * x, E float [85,H];
+ * backward: dx [N,H], dE [85,H] += (caller-zeroed). */
+int gpt_diagmix_fwd(const float* x, const float* E, const int64_t* deprel, const uint8_t* flags, int N, int H, float* F,
+                    float* R, float* S, void* stream);
+int gpt_diagmix_bwd(const float* x, const float* E, const int64_t* deprel, const uint8_t* flags, const float* dF,
+                    const float* dR, const float* dS, int N, int H, float* dx, float* dE, void* stream);
+/* gpt_agg3_fwd: out_i = dropout(relu((sum_{c: 0<val<42} keep_f[i,c] F_c + sum_{p: 42<val<84} keep_r[i,p] R_p + S_i) /
+ *     denom_i)) over gpt_prune_csr's rows (forward_adj_matrix.bmm + reverse_adj_matrix.bmm + self loop, :308-386, and
+ *     :390-393).  directed != 0 drops the R term (:339), self_loop == 0 the S term (:369).
+ *     Edge dropout (maybe_drop_edges): keep_f / keep_r = optional dense uint8 [B,T,T] masks, one per direction; else
+ *     edge_keep < 1 draws Bernoulli(edge_keep) per matrix entry in-kernel (Philox keyed by rng_state = {seed, step},
+ *     layer, direction, entry) -- gpt_edge_keep_dense materialises exactly those decisions.  No rescaling (:445).
+ *     Dropout: drop_mask (pre-scaled float [N,H]) or drop_p > 0 (in-kernel Philox) or neither.
+ * gpt_agg3_bwd: dF, dR, dS [N,H] from gout and the forward's out (d out/d z is recovered from out != 0). */
+int gpt_agg3_fwd(const float* F, const float* R, const float* S, const int32_t* rowptr, const int32_t* col,
+                 const uint8_t* val, const float* denom, const uint8_t* flags, const uint8_t* keep_f,
+                 const uint8_t* keep_r, float edge_keep, const void* rng_state, unsigned layer, int directed,
+                 int self_loop, float drop_p, const float* drop_mask, int B, int T, int H, float* out, void* stream);
+int gpt_agg3_bwd(const float* gout, const float* out, const int32_t* rowptr, const int32_t* col, const uint8_t* val,
+                 const float* denom, const uint8_t* flags, const uint8_t* keep_f, const uint8_t* keep_r, float edge_keep,
+                 const void* rng_state, unsigned layer, int directed, int self_loop, float drop_p,
+                 const float* drop_mask, int B, int T, int H, float* dF, float* dR, float* dS, void* stream);
+/* the in-kernel edge-dropout decisions of (layer, dir) as a dense uint8 [B,T,T]; dir 0 = parent->child matrix */
+int gpt_edge_keep_dense(const void* rng_state, int B, int T, unsigned layer, int dir, float keep_prob, uint8_t* out,
+                        void* stream);
+/* relation forgetting: keep_f / keep_r uint8 [N] ~ Bernoulli(keep_prop), independent per direction (:451-470) */
+int gpt_relation_keep_tokens(const void* rng_state, int N, unsigned layer, float keep_prop, uint8_t* keep_f,
+                             uint8_t* keep_r, void* stream);
+/* out[c] += sum_r a[r,c] (bias gradient of the shared projection); out is caller-zeroed */
+int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

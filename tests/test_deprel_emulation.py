@@ -1,0 +1,260 @@
+"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers) executed on host threads (tests/emu: one std::thread per
+CUDA thread, barriers for __syncthreads / shuffles) underneath the product's own Python layers -- model/gcn.py ->
+ops.py autograd Functions -> C ABI -- and checked against the real reference's outputs (tests/golden/deprel.npz) and
+against the oracle with identical injected masks.
+
+The build container has no GPU, so the pieces of the path that only exist as GPU code are replaced here, and only
+here, by stand-ins: K1's CSR is built from the oracle's dense adjacency, the K3 GEMMs are torch.matmul, K4 is the
+reference's pool(), K5 is nn.Embedding.  What this file pins is therefore K10's arithmetic, its direction / edge /
+forgetting conventions, the weight_l re-layout and every backward formula; the `-m gpu` tests in test_gpu_relation_modes.py
+run the same cases on the device with nothing replaced.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import weights
+from gcn_over_pruned_trees_b200 import _lib, ops, synth
+from gcn_over_pruned_trees_b200.model import gcn as gcn_mod
+from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+from oracle import gcn_oracle, tree_oracle
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+
+K10 = ('gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
+       'gpt_edge_keep_dense', 'gpt_relation_keep_tokens', 'gpt_colsum_acc')
+_ALL = dict(cases.DEPREL_CASES, **cases.DEPREL_RANDOM_CASES)
+
+
+def _cpu_csr(head, subj_pos, obj_pos, deprel, masks, prune_k, out=None):
+    """Stand-in for K1 with its output layout (include/gpt_b200.h, gpt_prune_csr): rows ascending by column."""
+    B, T = head.shape
+    lens = (masks.numpy() == 0).sum(1)
+    adj = tree_oracle.batch_adjacency(head.numpy(), subj_pos.numpy(), obj_pos.numpy(), deprel.numpy(), lens,
+                                      prune_k, T)
+    csr = ops.TreeCSR(B, T, head.device)
+    csr.col.zero_()
+    csr.val.zero_()
+    for b in range(B):
+        pos = 0
+        for i in range(T):
+            csr.rowptr[b, i] = pos
+            for j in np.nonzero(adj[b, i])[0]:
+                csr.col[b, pos] = int(j)
+                csr.val[b, pos] = int(adj[b, i, j])
+                pos += 1
+        csr.rowptr[b, T] = pos
+    nnz = torch.from_numpy((adj != 0).sum(2).astype(np.float32))
+    in_tree = torch.from_numpy(((adj != 0).sum(2) + (adj != 0).sum(1)) > 0)
+    csr.denom.copy_(nnz + 1)
+    csr.flags.copy_((in_tree.to(torch.uint8) | (subj_pos.eq(0).to(torch.uint8) << 1) |
+                     (obj_pos.eq(0).to(torch.uint8) << 2)))
+    csr.lens.copy_(torch.from_numpy(lens.astype(np.int32)))
+    csr.err.zero_()
+    return csr
+
+
+def _cpu_pool3(h, csr, pool_type='max'):
+    f = csr.flags
+    masks = [(f & bit).eq(0).unsqueeze(2) for bit in (1, 2, 4)]
+    return torch.cat([gcn_mod.pool(h, m, pool_type) for m in masks], dim=1)
+
+
+@pytest.fixture(scope='module')
+def emulated(request):
+    import emu_build
+    handle = ctypes.CDLL(emu_build.build())
+    for name in K10:
+        fn = getattr(handle, name)
+        fn.argtypes = _lib.SIGNATURES[name]
+        fn.restype = ctypes.c_int
+    mp = pytest.MonkeyPatch()
+    mp.setattr(_lib, '_lib', handle)
+    mp.setattr(ops, '_dev', lambda t, dtype, name: t.contiguous() if t.dtype == dtype else (_ for _ in ()).throw(
+        TypeError('%s must be %s' % (name, dtype))))
+    mp.setattr(ops, '_stream', lambda: None)
+    mp.setattr(ops, 'weight_prep', lambda weight, mode, out=None: None)
+    mp.setattr(ops, 'linear_fwd', lambda x2d, weight, mode='fp32', ws=None: x2d @ weight.t())
+    mp.setattr(ops, 'linear_dgrad', lambda dy, weight, mode='fp32', ws=None: dy @ weight)
+    mp.setattr(ops, 'linear_wgrad', lambda dy, x2d, mode='fp32', **kw: dy.t() @ x2d)
+    mp.setattr(ops, 'prune_csr', _cpu_csr)
+    mp.setattr(ops, 'pool3', _cpu_pool3)
+    yield handle
+    mp.undo()
+
+
+def _setup(golden_adj, name, batch_size=None):
+    over, source, wseed = _ALL[name]
+    if source[0] == 'split':
+        batch = cases.batch_from_npz(golden_adj, source[1])
+        over = dict(over, vocab_size=int(golden_adj['vocab_size']))
+    else:
+        batch = synth.make_batch(source[1], batch_size=batch_size or source[2], vocab_size=over['vocab_size'],
+                                 num_class=over.get('num_class', 42), dataset=over.get('dataset', 'tacred'))
+    opt = synth.tacred_opt(**over)
+    state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, wseed).items()}
+    trainer = GCNTrainer(dict(opt))
+    trainer.model.load_state_dict(state)
+    trainer.model.gcn_model.gcn.injected_masks = {}          # plain embedding lookups instead of K5
+    oracle = gcn_oracle.DenseClassifier(opt)
+    oracle.load_state_dict(state)
+    return opt, batch, trainer, oracle
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('name', sorted(cases.DEPREL_CASES))
+def test_emulated_kernels_match_reference_eval(emulated, golden_adj, golden_deprel, name):
+    opt, batch, trainer, _ = _setup(golden_adj, name)
+    trainer.model.eval()
+    with torch.no_grad():
+        logits, h_out = trainer.model(list(batch[:-2]))
+        loss = trainer.update(batch)
+    assert _rel(logits, torch.from_numpy(golden_deprel['%s/logits' % name])) <= 1e-5
+    assert _rel(h_out, torch.from_numpy(golden_deprel['%s/h_out' % name])) <= 1e-5
+    assert abs(loss.item() - float(golden_deprel['%s/eval_loss' % name])) <= 1e-5 * abs(loss.item())
+
+
+def _injected_masks(opt, batch, seed, edges=False, forget=False):
+    g = torch.Generator().manual_seed(seed)
+    B, T = batch[0].shape
+    tacred = opt['dataset'] == 'tacred'
+    width = opt['emb_dim'] + opt['pos_dim'] + (opt['ner_dim'] if tacred else 0)
+
+    def bern(shape, p):
+        return (torch.rand(shape, generator=g) < p).float()
+
+    masks = {'in': bern((B, T, width), 0.5) * 2.0}
+    if opt.get('rnn', False):
+        masks['rnn'] = bern((B, T, 2 * opt['rnn_hidden']), 0.5) * 2.0
+    for l in range(opt['num_layers'] - 1):
+        masks['gcn%d' % l] = bern((B, T, opt['hidden_dim']), 0.5) * 2.0
+    for l in range(opt['num_layers']):
+        if edges:
+            masks['edge_f%d' % l] = bern((B, T, T), 0.6)
+            masks['edge_r%d' % l] = bern((B, T, T), 0.6)
+        if forget:
+            masks['forget_f%d' % l] = bern((B, T, 1), 0.5)
+            masks['forget_r%d' % l] = bern((B, T, 1), 0.5)
+    return masks
+
+
+def _compare_grads(trainer, oracle, tol=2e-5):
+    got = dict(trainer.model.named_parameters())
+    checked = 0
+    for key, p in oracle.named_parameters():
+        if p.grad is None:
+            assert got[key].grad is None or float(got[key].grad.abs().max()) == 0.0, key
+            continue
+        assert got[key].grad is not None, key
+        assert _rel(got[key].grad, p.grad) <= tol, (key, _rel(got[key].grad, p.grad))
+        checked += 1
+    return checked
+
+
+@pytest.mark.parametrize('name,edges,forget', [
+    ('full_k1_d8', False, False), ('full_k1_d8', True, True), ('full_directed', True, False),
+    ('full_no_self_loop', False, True), ('full_depth1_3layer', True, True), ('full_cgcn_h64', False, False),
+    ('full_semeval', True, True), ('diag_k1', False, False), ('diag_kfull_3layer', False, False)])
+def test_emulated_kernels_train_grads_match_oracle(emulated, golden_adj, name, edges, forget):
+    """Train mode, every random draw injected into both sides: loss and all parameter gradients."""
+    opt, batch, trainer, oracle = _setup(golden_adj, name, batch_size=8)
+    masks = _injected_masks(opt, batch, seed=len(name), edges=edges, forget=forget)
+    trainer.model.train()
+    oracle.train()
+    trainer.model.gcn_model.gcn.injected_masks = masks
+    loss = trainer.update(batch)
+    loss.backward()
+    ref_loss, _ = oracle.loss(batch, masks)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert _compare_grads(trainer, oracle) >= 8
+    g = trainer.model.gcn_model.deprel_emb.weight.grad
+    assert float(g[0].abs().max()) == 0.0                    # padding_idx row
+
+
+def test_emulated_rows_beyond_one_wave_of_ctas(emulated, golden_adj):
+    """More token rows than the grid has CTAs (148 x 16): every CTA walks several rows."""
+    _ALL['_big'] = (dict(cases.DEPREL_CASES['full_k1_d8'][0], prune_k=-1), ('synth', 341, 72), 51)
+    try:
+        opt, batch, trainer, oracle = _setup(golden_adj, '_big')
+    finally:
+        del _ALL['_big']
+    assert batch[0].numel() > 148 * 16
+    masks = _injected_masks(opt, batch, seed=3, edges=True, forget=True)
+    trainer.model.train()
+    oracle.train()
+    trainer.model.gcn_model.gcn.injected_masks = masks
+    loss = trainer.update(batch)
+    loss.backward()
+    ref_loss, _ = oracle.loss(batch, masks)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert _compare_grads(trainer, oracle) >= 8
+
+
+def test_in_kernel_edge_dropout_and_forgetting_equal_their_materialised_masks(emulated, golden_adj):
+    """The Philox decisions taken inside agg3 / drawn by gpt_relation_keep_tokens, fed to the oracle as dense masks."""
+    name = 'full_edge_drop'
+    over = dict(_ALL[name][0], deprel_keep_prop=0.5)
+    _ALL['_philox'] = (over, ('synth', 331, 8), 43)
+    try:
+        opt, batch, trainer, oracle = _setup(golden_adj, '_philox')
+    finally:
+        del _ALL['_philox']
+    gcn = trainer.model.gcn_model.gcn
+    masks = _injected_masks(opt, batch, seed=5)              # dropouts injected; edges / forgetting left to Philox
+    gcn.injected_masks = dict(masks)
+    gcn.rng_state[0], gcn.rng_state[1] = 1234567, 3
+    B, T = batch[0].shape
+    for l in range(opt['num_layers']):
+        masks['edge_f%d' % l] = ops.edge_keep_dense(gcn.rng_state, B, T, l, 0, opt['edge_keep_prob']).float()
+        masks['edge_r%d' % l] = ops.edge_keep_dense(gcn.rng_state, B, T, l, 1, opt['edge_keep_prob']).float()
+        kf, kr = ops.relation_keep_tokens(gcn.rng_state, B * T, l, opt['deprel_keep_prop'])
+        masks['forget_f%d' % l], masks['forget_r%d' % l] = kf.view(B, T, 1).float(), kr.view(B, T, 1).float()
+        for m, p in ((masks['edge_f%d' % l], 0.7), (masks['edge_r%d' % l], 0.7), (masks['forget_f%d' % l], 0.5)):
+            assert abs(float(m.mean()) - p) < 0.06
+        assert not torch.equal(masks['edge_f%d' % l], masks['edge_r%d' % l])
+    assert not torch.equal(masks['edge_f0'], masks['edge_f1'])
+    trainer.model.train()
+    oracle.train()
+    loss = trainer.update(batch)
+    loss.backward()
+    ref_loss, _ = oracle.loss(batch, masks)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert _compare_grads(trainer, oracle) >= 8
+
+
+def test_in_kernel_dropout_rate_and_backward_consistency(emulated, golden_adj):
+    """gcn_drop drawn inside agg3: keep rate ~ 1-p, kept elements scaled by 1/(1-p), and the backward (which recovers
+    d out / d z from out != 0) equals autograd through the same realised mask."""
+    opt, batch, trainer, oracle = _setup(golden_adj, 'full_k1_d8', batch_size=8)
+    gcn = trainer.model.gcn_model.gcn
+    B, T = batch[0].shape
+    H = opt['hidden_dim']
+    inputs = list(batch[:-2])
+    csr = _cpu_csr(inputs[5], inputs[6], inputs[7], inputs[4], inputs[1], opt['prune_k'])
+    g = torch.Generator().manual_seed(0)
+    F, R, S = (torch.randn(B * T, H, generator=g) for _ in range(3))
+    cfg0 = ops.RelationLayerConfig(0, rng_state=gcn.rng_state)
+    cfg = ops.RelationLayerConfig(0, drop_p=0.5, rng_state=gcn.rng_state)
+    base = ops._agg3_fwd(F, R, S, csr, cfg0)
+    out = ops._agg3_fwd(F, R, S, csr, cfg)
+    live = base > 0
+    kept = (out != 0) & live
+    assert abs(float(kept.sum()) / float(live.sum()) - 0.5) < 0.03
+    assert torch.allclose(out[kept], base[kept] * 2.0)
+    gout = torch.randn(B, T, H, generator=g)
+    dF, dR, dS = ops._agg3_bwd(gout, out, csr, cfg)
+    cfg_m = ops.RelationLayerConfig(0, drop_mask=kept.float().view(B * T, H) * 2.0, rng_state=gcn.rng_state)
+    dF2, dR2, dS2 = ops._agg3_bwd(gout, ops._agg3_fwd(F, R, S, csr, cfg_m), csr, cfg_m)
+    for a, b in ((dF, dF2), (dR, dR2), (dS, dS2)):
+        assert torch.equal(a, b)

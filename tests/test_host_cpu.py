@@ -77,9 +77,12 @@ def test_unpack_batch_tacred_and_semeval():
         assert torch.equal(lens, synth.batch_lengths(b))
 
 
-@pytest.mark.parametrize('name', ['cfg1_train_json_k1', 'cfg3_cgcn_k1', 'cfg4_semeval_k1', 'sum_pool_3layer_mlp1'])
+@pytest.mark.parametrize('name', ['cfg1_train_json_k1', 'cfg3_cgcn_k1', 'cfg4_semeval_k1', 'sum_pool_3layer_mlp1',
+                                  'full_k1_d8', 'full_cgcn_h64', 'full_semeval', 'diag_k1', 'diag_cgcn'])
 def test_state_dict_layout_matches_reference_checkpoints(name):
-    over, _, wseed = cases.MODEL_CASES[name]
+    # the shape tables in weights.py are themselves pinned: make_golden.py / make_deprel_golden.py load states built
+    # from them into the REAL reference model with strict=True
+    over, _, wseed = dict(cases.MODEL_CASES, **cases.DEPREL_CASES)[name]
     opt = synth.tacred_opt(**dict(over, vocab_size=over.get('vocab_size', 963)))
     model = trainer_mod.GCNTrainer(opt).model
     want = weights.state_shapes(opt)
@@ -94,8 +97,21 @@ def test_state_dict_layout_matches_reference_checkpoints(name):
 
 
 def test_unsupported_paths_fail_loudly():
+    with pytest.raises(NotImplementedError):        # builds weights in the reference, but its forward raises (gcn.py:388)
+        trainer_mod.GCNTrainer(synth.tacred_opt(vocab_size=50, adj_type='concat_deprel'))
+    with pytest.raises(ValueError):                 # the reference dies inside einsum at layer 2
+        trainer_mod.GCNTrainer(synth.tacred_opt(vocab_size=50, adj_type='full_deprel', deprel_emb_dim=8))
     with pytest.raises(NotImplementedError):
-        trainer_mod.GCNTrainer(synth.tacred_opt(vocab_size=50, adj_type='full_deprel'))
+        trainer_mod.GCNTrainer(synth.tacred_opt(vocab_size=50, emb_dropout=0.1))
+
+
+def test_relation_modes_have_no_cpu_path():
+    from gcn_over_pruned_trees_b200._lib import GptError
+    over, source, _ = cases.DEPREL_CASES['full_k1_d8']
+    trainer = trainer_mod.GCNTrainer(synth.tacred_opt(**over))
+    batch = synth.make_batch(source[1], batch_size=4, vocab_size=over['vocab_size'])
+    with pytest.raises(GptError):
+        trainer.update(batch)
 
 
 def test_packed_batch_is_one_buffer_with_the_loader_views():
