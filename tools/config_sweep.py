@@ -57,7 +57,15 @@ def run(name, over, batch_kw, steps, n_batches=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--relation', action='store_true',
+                    help='only the relation-aware adjacency modes (K10): full_deprel with 50 relation slots '
+                         '(train_cgcn.sh:5) on a 200-wide input (the mode needs in_dim == hidden_dim), diagonal_deprel')
     a = ap.parse_args()
+    if a.relation:
+        run('gcn_full_deprel_d50_k1', dict(prune_k=1, adj_type='full_deprel', deprel_emb_dim=50, emb_dim=140), {},
+            a.steps)
+        run('gcn_diagonal_deprel_k1', dict(prune_k=1, adj_type='diagonal_deprel'), {}, a.steps)
+        return
     for k in (-1, 0, 1, 2):
         run('gcn_tacred_k%d' % k, dict(prune_k=k), {}, a.steps)
     run('cgcn_tacred_k1', dict(prune_k=1, rnn=True, rnn_hidden=200, rnn_layers=1), {}, a.steps)
