@@ -17,8 +17,11 @@
 // (diagonal_deprel: F_n = e(deprel_n) * x_n etc., elementwise, no edge dropout.)  The CSR entry's value (K1's `val`)
 // tells the direction: 0 < val < 42 parent->child, 42 < val < 84 child->parent (tree.py:184-192).  For layers
 // l >= deprel_max_depth, and for tokens whose relation is "forgotten", the relation vector is all ones.
-// Tokens outside the pruned tree are written as zeros: they are not neighbours of kept tokens and are masked out
-// of all three pools, so they never reach the logits (same convention as K2).
+// Rows with flags == 0 (outside the pruned tree and not an entity token) are written as zeros: they are not neighbours
+// of kept tokens and are masked out of all three pools, so they never reach the logits (same convention as K2).  An
+// entity token outside the tree (singleton tree; entity outside the last root's component for prune_k < 0) has an
+// empty CSR row and is computed as the reference computes it -- relu(S_i / 1) -- because the subject / object pools
+// read it.
 //
 // Mapping: one CTA per token row (grid-stride), threads over the H output columns, every global access coalesced
 // along H.  HBM-bound integer/fp32 work: relmix streams Z once ([N, D*H], the dominant traffic), agg3 reads each
@@ -29,6 +32,7 @@
 //   dS_j = g_j ,  dF_j = keep(p,j) g_p (p = parent of j) ,  dR_j = sum_{c child of j} keep(c,j) g_c
 //   dZ[n,d,:] = e_f[d] dF_n + e_r[d] dR_n + e_s[d] dS_n ,  de(.)[d] += <d{F,R,S}_n, Z[n,d,:] + bias_l[d]>
 #include "gpt_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -37,6 +41,8 @@ constexpr int kFwdBound = 42;   // /root/reference/utils/constant.py:14
 constexpr int kRevBound = 84;   // constant.py:16; also the self-loop relation id (constant.py:17)
 
 __device__ __forceinline__ int rel_id(long long r) { return (r < 0 || r > kFwdBound) ? 0 : (int)r; }
+// a row some pool can see: in the tree, or a subject / object token (flags of gpt_prune_csr)
+__device__ __forceinline__ bool observable(unsigned char f) { return f != 0; }
 
 // Bernoulli(keep_prob) of entry [b, i, j] of the dense matrix of direction `dir` (0: parent->child matrix, 1: child->parent)
 // at layer `layer`: explicit dense masks when given (tests), else Philox keyed by {seed, step}.
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) relmix_fwd_kernel(const MixParams p)
     GPT_PDL_ENTER();
     const size_t DH = (size_t)p.D * p.H;
     for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
-        if (!(p.flags[n] & GPT_FLAG_INTREE)) {                 // CTA-uniform
+        if (!observable(p.flags[n])) {                 // CTA-uniform
             for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
                 p.F[(size_t)n * p.H + h] = 0.f;
                 p.R[(size_t)n * p.H + h] = 0.f;
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) relmix_bwd_kernel(const MixParams p)
     __syncthreads();
     for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
         float* __restrict__ dz = p.dZ + (size_t)n * DH;
-        if (!(p.flags[n] & GPT_FLAG_INTREE)) {                 // CTA-uniform; the projection's gradients read every row
+        if (!observable(p.flags[n])) {                 // CTA-uniform; the projection's gradients read every row
             for (size_t i = threadIdx.x; i < DH; i += blockDim.x) dz[i] = 0.f;
             continue;
         }
@@ -189,7 +195,7 @@ struct DiagParams {
 __global__ void __launch_bounds__(kThreads) diagmix_fwd_kernel(const DiagParams p) {
     GPT_PDL_ENTER();
     for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
-        const bool in = (p.flags[n] & GPT_FLAG_INTREE) != 0;
+        const bool in = observable(p.flags[n]);
         const int rf = rel_id(p.deprel[n]);
         for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
             const size_t o = (size_t)n * p.H + h;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) diagmix_bwd_kernel(const DiagParams 
     GPT_PDL_ENTER();
     for (int h = threadIdx.x; h < p.H; h += blockDim.x) sm[h] = 0.f;   // each thread only ever touches its own h
     for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
-        const bool in = (p.flags[n] & GPT_FLAG_INTREE) != 0;
+        const bool in = observable(p.flags[n]);
         const int rf = rel_id(p.deprel[n]);
         for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
             const size_t o = (size_t)n * p.H + h;
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) agg3_fwd_kernel(const Agg3Params p) 
     const float scale = philox_drop ? 1.f / (1.f - p.drop_p) : 1.f;
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         const int b = n / p.T, i = n - b * p.T;
-        if (!(p.flags[n] & GPT_FLAG_INTREE)) {
+        if (!observable(p.flags[n])) {
             for (int h = threadIdx.x; h < p.H; h += blockDim.x) p.out[(size_t)n * p.H + h] = 0.f;
             continue;
         }
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(kThreads) agg3_bwd_kernel(const Agg3Params p) 
     const float scale = philox_drop ? 1.f / (1.f - p.drop_p) : 1.f;
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         const int b = n / p.T, j = n - b * p.T;
-        if (!(p.flags[n] & GPT_FLAG_INTREE)) {
+        if (!observable(p.flags[n])) {
             for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
                 const size_t idx = (size_t)n * p.H + h;
                 p.dF[idx] = 0.f;
@@ -388,7 +394,11 @@ __global__ void __launch_bounds__(256) colsum_acc_kernel(const float* __restrict
 }
 
 inline unsigned row_grid(long long rows) {
-    const long long cap = 148LL * 16;      // resident CTAs of 128 threads per SM x SM count: one wave, grid-stride beyond
+    long long cap = 148LL * 16;            // resident CTAs of 128 threads per SM x SM count: one wave, grid-stride beyond
+    if (const char* e = getenv("GPT_K10_MAX_CTAS")) {      // tuning / test knob: CTAs per launch
+        const long long v = atoll(e);
+        if (v > 0) cap = v;
+    }
     return (unsigned)(rows < 1 ? 1 : (rows < cap ? rows : cap));
 }
 

@@ -273,8 +273,8 @@ int gpt_build_batch(const int32_t* const* arena, const int64_t* offsets, const i
  *     (traverse_deprel :400-415, traverse_self_loop :417-434).  E float [85,D]; Z float [N, D*H]; bias float [D*H];
  *     keep_f / keep_r (optional uint8 [N]): 0 = the token's relation vector of that direction is replaced by ones
  *     (maybe_forget_deprels); deep != 0 = every vector is ones (layer >= deprel_max_depth, :324-325,355-356,376-379).
- *     Rows without GPT_FLAG_INTREE are written 0.
- * gpt_relmix_bwd: dZ [N, D*H] (zeros on rows outside the tree) and dE [85,D] += (caller-zeroed, atomics; row 0 =
+ *     Rows with flags == 0 are written 0 (as in K2); entity tokens outside the tree are computed.
+ * gpt_relmix_bwd: dZ [N, D*H] (zeros on rows with flags == 0) and dE [85,D] += (caller-zeroed, atomics; row 0 =
  *     padding_idx and forgotten / deep vectors get nothing) from dF, dR, dS [N,H]. */
 int gpt_relmix_fwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
                    const uint8_t* keep_f, const uint8_t* keep_r, int N, int D, int H, int deep, float* F, float* R,

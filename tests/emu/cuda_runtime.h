@@ -1,17 +1,19 @@
 // TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu (and the
-// helpers of csrc/gpt_common.cuh it uses) with g++ and run its kernels on CPU threads: one std::thread per CUDA thread of
-// a block, blocks executed one after the other, __syncthreads() / warp shuffles as barriers, atomics under a mutex.
+// helpers of csrc/gpt_common.cuh it uses) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
+// fiber (ucontext) on the calling OS thread, scheduled round-robin; __syncthreads() and the warp shuffles are barriers
+// at which a fiber yields; blocks run one after the other; exited threads stop counting towards barriers, as on the
+// device.  Single-threaded and deterministic (atomics are plain adds).
 // The build container has no GPU; this lets `-m "not gpu"` tests execute the kernels' actual source against the oracle.
 // Nothing under gcn_over_pruned_trees_b200/ includes or links this.
 #pragma once
-#include <barrier>
+#include <ucontext.h>
+
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
-#include <memory>
-#include <mutex>
-#include <thread>
+#include <functional>
 #include <utility>
 #include <vector>
 
@@ -51,51 +53,115 @@ struct cudaLaunchConfig_t {
     unsigned numAttrs;
 };
 
+inline emu_uint3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
 namespace emu {
+constexpr size_t kStackBytes = 128 * 1024;
+
+struct Barrier {
+    int arrived = 0, live = 0;
+    unsigned generation = 0;
+};
+struct Fiber {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    bool done = false;
+};
 struct Block {
-    std::barrier<> sync_bar, block_bar;
-    std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+    int n = 0, current = 0;
+    std::vector<Fiber> fibers;
+    ucontext_t scheduler;
+    Barrier sync;
+    std::vector<Barrier> warp;
     std::vector<uint32_t> warp_buf;
-    explicit Block(int n) : sync_bar(n), block_bar(n), warp_buf((size_t)((n + 31) / 32) * 32) {
-        for (int w = 0; w < (n + 31) / 32; ++w) {
-            const int lanes = (w + 1) * 32 <= n ? 32 : n - w * 32;
-            warp_bar.emplace_back(new std::barrier<>(lanes));
+    std::function<void()> body;
+};
+inline Block* block = nullptr;
+
+inline void yield() { swapcontext(&block->fibers[block->current].ctx, &block->scheduler); }
+
+inline void arrive_and_wait(Barrier& b) {
+    const unsigned g = b.generation;
+    if (++b.arrived >= b.live) {
+        b.arrived = 0;
+        ++b.generation;
+        return;
+    }
+    while (b.generation == g) yield();
+}
+// a thread that has exited no longer takes part in barriers
+inline void leave(Barrier& b) {
+    --b.live;
+    if (b.live > 0 && b.arrived >= b.live) {
+        b.arrived = 0;
+        ++b.generation;
+    }
+}
+inline void trampoline() {
+    Block* blk = block;
+    blk->body();
+    blk->fibers[blk->current].done = true;
+    leave(blk->sync);
+    leave(blk->warp[blk->current >> 5]);
+}
+
+inline void run_block(Block& blk) {
+    const int n = blk.n;
+    blk.sync = Barrier{0, n, 0};
+    for (int w = 0; w < (int)blk.warp.size(); ++w) blk.warp[w] = Barrier{0, (w + 1) * 32 <= n ? 32 : n - w * 32, 0};
+    for (int t = 0; t < n; ++t) {
+        Fiber& f = blk.fibers[t];
+        f.done = false;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = kStackBytes;
+        f.ctx.uc_link = &blk.scheduler;
+        makecontext(&f.ctx, trampoline, 0);
+    }
+    for (int remaining = n; remaining > 0;) {
+        remaining = 0;
+        for (int t = 0; t < n; ++t) {
+            Fiber& f = blk.fibers[t];
+            if (f.done) continue;
+            blk.current = t;
+            threadIdx = emu_uint3{(unsigned)t, 0, 0};
+            swapcontext(&blk.scheduler, &f.ctx);
+            if (!f.done) ++remaining;
         }
     }
-};
-inline thread_local Block* block = nullptr;
-inline std::mutex atomic_mutex;
+}
 }  // namespace emu
 
-inline thread_local emu_uint3 threadIdx, blockIdx;
-inline thread_local dim3 blockDim, gridDim;
-
-inline void __syncthreads() { emu::block->sync_bar.arrive_and_wait(); }
+inline void __syncthreads() {
+    emu::arrive_and_wait(emu::block->sync);
+    threadIdx = emu_uint3{(unsigned)emu::block->current, 0, 0};
+}
 
 template <typename T>
 inline T emu_shfl(T v, int src_lane) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int me = emu::block->current, warp = me >> 5, lane = me & 31;
     uint32_t bits;
     std::memcpy(&bits, &v, 4);
     emu::block->warp_buf[(size_t)warp * 32 + lane] = bits;
-    emu::block->warp_bar[warp]->arrive_and_wait();
+    emu::arrive_and_wait(emu::block->warp[warp]);
     const uint32_t got = emu::block->warp_buf[(size_t)warp * 32 + (src_lane & 31)];
-    emu::block->warp_bar[warp]->arrive_and_wait();
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    threadIdx = emu_uint3{(unsigned)me, 0, 0};
     T r;
     std::memcpy(&r, &got, 4);
     return r;
 }
 template <typename T>
-inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_shfl(v, (int)(threadIdx.x & 31) ^ o); }
+inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_shfl(v, (emu::block->current & 31) ^ o); }
 template <typename T>
 inline T __shfl_up_sync(unsigned, T v, int o) {
-    const int lane = threadIdx.x & 31;
+    const int lane = emu::block->current & 31;
     return emu_shfl(v, lane >= o ? lane - o : lane);
 }
 
 inline float atomicAdd(float* p, float v) {
-    std::lock_guard<std::mutex> g(emu::atomic_mutex);
     const float old = *p;
     *p = old + v;
     return old;
@@ -108,23 +174,22 @@ template <typename... K, typename... A>
 inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(K...), A... args) {
     const int n = (int)cfg->blockDim.x;
     if (cfg->blockDim.y != 1 || cfg->blockDim.z != 1 || cfg->gridDim.z != 1 || n < 1) return 1;
-    emu::Block blk(n);
-    const dim3 grid = cfg->gridDim, bdim = cfg->blockDim;
-    std::vector<std::thread> threads;
-    for (int t = 0; t < n; ++t) {
-        threads.emplace_back([&, t]() {
-            emu::block = &blk;
-            threadIdx = emu_uint3{(unsigned)t, 0, 0};
-            blockDim = bdim;
-            gridDim = grid;
-            for (unsigned by = 0; by < grid.y; ++by)
-                for (unsigned bx = 0; bx < grid.x; ++bx) {
-                    blockIdx = emu_uint3{bx, by, 0};
-                    kernel(args...);
-                    blk.block_bar.arrive_and_wait();     // shared memory belongs to one block at a time
-                }
-        });
-    }
-    for (auto& th : threads) th.join();
+    emu::Block blk;
+    blk.n = n;
+    blk.fibers.resize(n);
+    blk.warp.resize((n + 31) / 32);
+    blk.warp_buf.resize((size_t)((n + 31) / 32) * 32);
+    for (auto& f : blk.fibers) f.stack = static_cast<char*>(std::malloc(emu::kStackBytes));
+    blk.body = [&]() { kernel(args...); };
+    emu::block = &blk;
+    blockDim = cfg->blockDim;
+    gridDim = cfg->gridDim;
+    for (unsigned by = 0; by < cfg->gridDim.y; ++by)
+        for (unsigned bx = 0; bx < cfg->gridDim.x; ++bx) {
+            blockIdx = emu_uint3{bx, by, 0};
+            emu::run_block(blk);          // shared memory belongs to one block at a time
+        }
+    for (auto& f : blk.fibers) std::free(f.stack);
+    emu::block = nullptr;
     return cudaSuccess;
 }

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE -- build tests/emu/_build/libdeprel_emu.so: csrc/deprel.cu compiled by g++ against the host
-stand-in for the CUDA runtime in this directory (thread-per-CUDA-thread emulation; see cuda_runtime.h)."""
+stand-in for the CUDA runtime in this directory (one fiber per CUDA thread; see cuda_runtime.h)."""
 import os
 import subprocess
 
@@ -15,7 +15,7 @@ def build():
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    subprocess.check_call(['g++', '-std=c++20', '-O1', '-g', '-fPIC', '-shared', '-pthread', '-x', 'c++', '-I', HERE,
+    subprocess.check_call(['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-x', 'c++', '-I', HERE,
                            SRC, '-o', OUT])
     return OUT
 

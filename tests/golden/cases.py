@@ -51,6 +51,13 @@ DEPREL_CASES = {
     'diag_cgcn':           (dict(adj_type='diagonal_deprel', prune_k=1, hidden_dim=64, rnn=True, rnn_hidden=40,
                                  vocab_size=SMALL_VOCAB), ('synth', 313, 16), 33),
 }
+# batches whose sentence 0 gets a second root AFTER the first one, over an entity-free subtree: for prune_k < 0 the
+# reference keeps only the LAST root's component (tree.py:76-77), so the entity tokens are outside the tree (empty
+# adjacency rows) while the subject / object pools still read them -- in these modes they carry relu(self loop)
+DEPREL_CASES['full_entities_outside_tree'] = (
+    dict(_IN64, adj_type='full_deprel', deprel_emb_dim=8, prune_k=-1), ('synth_second_root', 308, 12), 29)
+DEPREL_CASES['diag_entities_outside_tree'] = (
+    dict(adj_type='diagonal_deprel', prune_k=-1, hidden_dim=64, vocab_size=SMALL_VOCAB), ('synth_second_root', 314, 12), 34)
 DEPREL_GRAD_CASES = ('full_k1_d8', 'full_directed', 'full_depth1_3layer', 'full_cgcn_h64', 'diag_k1')
 # train-mode cases of the reference with edge dropout / relation forgetting drawn from torch.manual_seed(DROPOUT_SEED)
 DEPREL_RANDOM_CASES = {
@@ -81,6 +88,48 @@ EDGE_TREES = {
     'deprel_pad_id':       ([0, 1, 1, 2], [3], [2], [11, 0, 5, 0]),            # deprel 0: forward entry is 0
     'wide_and_deep':       ([3, 3, 0, 3, 4, 4, 6, 6, 8, 8, 10, 10], [11], [6], [2, 3, 11, 4, 5, 6, 7, 8, 9, 10, 12, 13]),
 }
+
+
+def add_second_root(batch, row=0):
+    """Loader batch with sentence ``row`` given a second root: the token with the largest index that lies after the
+    root, has at least one child and no entity token in its subtree gets head 0."""
+    tacred = len(batch) >= 10
+    off = 5 if tacred else 4
+    head = batch[off].clone()
+    subj_pos, obj_pos = batch[off + 1], batch[off + 2]
+    n = int((~batch[1][row]).sum())
+    h = head[row, :n].tolist()
+    entity = [subj_pos[row, t].item() == 0 or obj_pos[row, t].item() == 0 for t in range(n)]
+    children = [[] for _ in range(n)]
+    for t, p in enumerate(h):
+        if p > 0:
+            children[p - 1].append(t)
+    root = h.index(0)
+
+    def subtree(v):
+        out, stack = [], [v]
+        while stack:
+            u = stack.pop()
+            out.append(u)
+            stack.extend(children[u])
+        return out
+
+    for v in range(n - 1, root, -1):
+        sub = subtree(v)
+        if len(sub) >= 2 and not any(entity[u] for u in sub):
+            head[row, v] = 0
+            return batch[:off] + (head,) + batch[off + 1:]
+    raise ValueError('sentence %d has no entity-free subtree after its root' % row)
+
+
+def make_case_batch(source, over, golden_adj=None):
+    """The batch a (DEPREL_)MODEL_CASES source describes."""
+    from gcn_over_pruned_trees_b200 import synth
+    if source[0] == 'split':
+        return batch_from_npz(golden_adj, source[1])
+    batch = synth.make_batch(source[1], batch_size=source[2], vocab_size=over['vocab_size'],
+                             num_class=over.get('num_class', 42), dataset=over.get('dataset', 'tacred'))
+    return add_second_root(batch) if source[0] == 'synth_second_root' else batch
 
 
 def positions(span_tokens, length, fill=150, width=None):

@@ -30,8 +30,7 @@ def main():
             batch = cases.batch_from_npz(golden_adj, source[1])
             over = dict(over, vocab_size=int(golden_adj['vocab_size']))
         else:
-            batch = synth.make_batch(source[1], batch_size=source[2], vocab_size=over['vocab_size'],
-                                     num_class=over.get('num_class', 42), dataset=over.get('dataset', 'tacred'))
+            batch = cases.make_case_batch(source, over)
         opt = synth.tacred_opt(**over)
         with contextlib.redirect_stdout(io.StringIO()):
             trainer = GCNTrainer(dict(opt))

@@ -1,5 +1,5 @@
-"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers) executed on host threads (tests/emu: one std::thread per
-CUDA thread, barriers for __syncthreads / shuffles) underneath the product's own Python layers -- model/gcn.py ->
+"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers) executed on the host (tests/emu: one fiber per CUDA
+thread, barriers for __syncthreads / shuffles) underneath the product's own Python layers -- model/gcn.py ->
 ops.py autograd Functions -> C ABI -- and checked against the real reference's outputs (tests/golden/deprel.npz) and
 against the oracle with identical injected masks.
 
@@ -38,17 +38,17 @@ def _cpu_csr(head, subj_pos, obj_pos, deprel, masks, prune_k, out=None):
     adj = tree_oracle.batch_adjacency(head.numpy(), subj_pos.numpy(), obj_pos.numpy(), deprel.numpy(), lens,
                                       prune_k, T)
     csr = ops.TreeCSR(B, T, head.device)
-    csr.col.zero_()
-    csr.val.zero_()
+    rowptr = np.zeros((B, T + 1), dtype=np.int32)
+    col = np.zeros((B, 3 * T), dtype=np.int32)
+    val = np.zeros((B, 3 * T), dtype=np.uint8)
     for b in range(B):
-        pos = 0
-        for i in range(T):
-            csr.rowptr[b, i] = pos
-            for j in np.nonzero(adj[b, i])[0]:
-                csr.col[b, pos] = int(j)
-                csr.val[b, pos] = int(adj[b, i, j])
-                pos += 1
-        csr.rowptr[b, T] = pos
+        rows, cols = np.nonzero(adj[b])                      # row-major: columns ascending inside a row
+        rowptr[b, 1:] = np.cumsum(np.bincount(rows, minlength=T))
+        col[b, :len(cols)] = cols
+        val[b, :len(cols)] = adj[b, rows, cols].astype(np.uint8)
+    csr.rowptr.copy_(torch.from_numpy(rowptr))
+    csr.col.copy_(torch.from_numpy(col))
+    csr.val.copy_(torch.from_numpy(val))
     nnz = torch.from_numpy((adj != 0).sum(2).astype(np.float32))
     in_tree = torch.from_numpy(((adj != 0).sum(2) + (adj != 0).sum(1)) > 0)
     csr.denom.copy_(nnz + 1)
@@ -94,8 +94,7 @@ def _setup(golden_adj, name, batch_size=None):
         batch = cases.batch_from_npz(golden_adj, source[1])
         over = dict(over, vocab_size=int(golden_adj['vocab_size']))
     else:
-        batch = synth.make_batch(source[1], batch_size=batch_size or source[2], vocab_size=over['vocab_size'],
-                                 num_class=over.get('num_class', 42), dataset=over.get('dataset', 'tacred'))
+        batch = cases.make_case_batch((source[0], source[1], batch_size or source[2]), over)
     opt = synth.tacred_opt(**over)
     state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, wseed).items()}
     trainer = GCNTrainer(dict(opt))
@@ -162,10 +161,11 @@ def _compare_grads(trainer, oracle, tol=2e-5):
 @pytest.mark.parametrize('name,edges,forget', [
     ('full_k1_d8', False, False), ('full_k1_d8', True, True), ('full_directed', True, False),
     ('full_no_self_loop', False, True), ('full_depth1_3layer', True, True), ('full_cgcn_h64', False, False),
-    ('full_semeval', True, True), ('diag_k1', False, False), ('diag_kfull_3layer', False, False)])
+    ('full_semeval', True, True), ('diag_k1', False, False), ('diag_kfull_3layer', False, False),
+    ('full_entities_outside_tree', True, False), ('diag_entities_outside_tree', False, False)])
 def test_emulated_kernels_train_grads_match_oracle(emulated, golden_adj, name, edges, forget):
     """Train mode, every random draw injected into both sides: loss and all parameter gradients."""
-    opt, batch, trainer, oracle = _setup(golden_adj, name, batch_size=8)
+    opt, batch, trainer, oracle = _setup(golden_adj, name, batch_size=None if 'outside_tree' in name else 8)
     masks = _injected_masks(opt, batch, seed=len(name), edges=edges, forget=forget)
     trainer.model.train()
     oracle.train()
@@ -180,14 +180,12 @@ def test_emulated_kernels_train_grads_match_oracle(emulated, golden_adj, name, e
     assert float(g[0].abs().max()) == 0.0                    # padding_idx row
 
 
-def test_emulated_rows_beyond_one_wave_of_ctas(emulated, golden_adj):
-    """More token rows than the grid has CTAs (148 x 16): every CTA walks several rows."""
-    _ALL['_big'] = (dict(cases.DEPREL_CASES['full_k1_d8'][0], prune_k=-1), ('synth', 341, 72), 51)
-    try:
-        opt, batch, trainer, oracle = _setup(golden_adj, '_big')
-    finally:
-        del _ALL['_big']
-    assert batch[0].numel() > 148 * 16
+def test_emulated_rows_beyond_one_wave_of_ctas(emulated, golden_adj, monkeypatch):
+    """Fewer CTAs than token rows (GPT_K10_MAX_CTAS; on the device the cap is 148 x 16): every CTA walks several rows --
+    shared-memory reuse across rows, per-CTA partial sums of the self-loop vector's gradient."""
+    monkeypatch.setenv('GPT_K10_MAX_CTAS', '24')
+    opt, batch, trainer, oracle = _setup(golden_adj, 'full_kfull_d16', batch_size=8)
+    assert batch[0].numel() > 24 * 8
     masks = _injected_masks(opt, batch, seed=3, edges=True, forget=True)
     trainer.model.train()
     oracle.train()

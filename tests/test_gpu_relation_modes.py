@@ -32,8 +32,7 @@ def _setup(golden_adj, name, gemm_mode='fp32', batch_size=None, table=None):
         batch = cases.batch_from_npz(golden_adj, source[1])
         over = dict(over, vocab_size=int(golden_adj['vocab_size']))
     else:
-        batch = synth.make_batch(source[1], batch_size=batch_size or source[2], vocab_size=over['vocab_size'],
-                                 num_class=over.get('num_class', 42), dataset=over.get('dataset', 'tacred'))
+        batch = cases.make_case_batch((source[0], source[1], batch_size or source[2]), over)
     opt = synth.tacred_opt(**over)
     state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, wseed).items()}
     trainer = GCNTrainer(dict(opt, cuda=True))
@@ -101,7 +100,8 @@ def _compare_grads(trainer, oracle, tol=1e-4):
     ('full_k1_d8', False, False), ('full_k1_d8', True, True), ('full_kfull_d16', True, False),
     ('full_directed', True, False), ('full_no_self_loop', False, True), ('full_depth1_3layer', True, True),
     ('full_cgcn_h64', False, False), ('full_semeval', True, True), ('full_split_train', False, False),
-    ('diag_k1', False, False), ('diag_kfull_3layer', False, False), ('diag_cgcn', False, False)])
+    ('diag_k1', False, False), ('diag_kfull_3layer', False, False), ('diag_cgcn', False, False),
+    ('full_entities_outside_tree', True, False), ('diag_entities_outside_tree', False, False)])
 def test_relation_modes_train_grads_match_oracle(golden_adj, name, edges, forget, gemm_mode):
     """Train mode, every random draw (dropouts, edge dropout, relation forgetting) injected into both sides."""
     opt, batch, trainer, oracle = _setup(golden_adj, name, gemm_mode)
