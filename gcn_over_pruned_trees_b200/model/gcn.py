@@ -213,6 +213,46 @@ class GCN(nn.Module):
         out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=rnn_inputs.size(1))
         return out
 
+    def _relation_layers(self, x, csr, deprel, drop_p):
+        """The layer loop of the relation-aware modes (gcn.py:272-386 + 390-393).  `no_adj` has no effect here, as in the
+        reference (these branches re-derive their masks from `adj`, gcn.py:276,308)."""
+        opt = self.opt
+        emb = self.deprel_emb.weight
+        injected = self.injected_masks
+        full = self.adj_type == 'full_deprel'
+        if full:
+            D, H = opt['deprel_emb_dim'], self.mem_dim
+            # weight_l = W.weight.reshape(D, in, H) is a reshape of the [D*H, in] matrix, not a permute (gcn.py:301);
+            # the projection GEMM wants the [D*H, in] matrix whose row d*H+h is weight_l[d, :, h]
+            wmat = self.W.weight.reshape(D, -1, H).permute(0, 2, 1).reshape(D * H, -1).contiguous()
+            ws = ops.weight_prep(wmat.detach(), self.gemm_mode)
+        else:
+            x = ops.linear(x, self.preprocessor.weight, self.preprocessor.bias, self.gemm_mode)    # gcn.py:255-257
+        B, T = csr.B, csr.T
+        for l in range(self.layers):
+            last = l == self.layers - 1
+            mask = None if injected is None else injected.get('gcn%d' % l)
+            cfg = ops.RelationLayerConfig(l, drop_p=0.0 if (last or mask is not None) else drop_p,
+                                          drop_mask=None if last else mask, rng_state=self.rng_state,
+                                          gemm_mode=self.gemm_mode)
+            if not full:
+                x = ops.relation_layer_diag(x, emb, csr, deprel, cfg)
+                continue
+            cfg.deep = l >= opt['deprel_max_depth']
+            cfg.directed, cfg.self_loop = bool(opt['deprel_directed']), bool(opt['deprel_self_loop'])
+            if injected is not None and ('edge_f%d' % l) in injected:
+                # tests: dense 0/1 [B,T,T] masks per direction, as maybe_drop_edges draws them (gcn.py:436-449)
+                cfg.keep_edges = tuple(injected['edge_%s%d' % (d, l)].to(torch.uint8).contiguous() for d in 'fr')
+            elif self.training and opt.get('edge_keep_prob', 1.0) < 1.0:
+                cfg.edge_keep = opt['edge_keep_prob']
+            if injected is not None and ('forget_f%d' % l) in injected:
+                cfg.keep_tokens = tuple(injected['forget_%s%d' % (d, l)].reshape(-1).to(torch.uint8).contiguous()
+                                        for d in 'fr')
+            elif self.training and opt.get('deprel_keep_prop', 1.0) < 1.0:
+                cfg.keep_tokens = ops.relation_keep_tokens(self.rng_state, B * T, l, opt['deprel_keep_prop'])
+            x = ops.relation_layer_full(x, wmat, self.W.bias, emb, csr, deprel, cfg, ws)
+        return x
+
     def forward(self, adj, inputs):
         if not isinstance(adj, ops.TreeCSR):
             raise TypeError('GCN.forward takes the TreeCSR produced by ops.prune_csr, not a dense adjacency')
@@ -253,50 +293,6 @@ class GCN(nn.Module):
             x = ops.gcn_layer(x, lin.weight, lin.bias, adj, use_adj=use_adj, drop_p=p, rng_state=self.rng_state,
                               subseq=l, drop_mask=None if last else mask, gemm_mode=self.gemm_mode)
         return x, adj.pool_mask()
-
-
-def _relation_layers(self, x, csr, deprel, drop_p):
-    """The layer loop of the relation-aware modes (gcn.py:272-386 + 390-393).  `no_adj` has no effect here, as in the
-    reference (these branches re-derive their masks from `adj`, gcn.py:276,308)."""
-    opt = self.opt
-    emb = self.deprel_emb.weight
-    injected = self.injected_masks
-    full = self.adj_type == 'full_deprel'
-    if full:
-        D, H = opt['deprel_emb_dim'], self.mem_dim
-        # weight_l = W.weight.reshape(D, in, H) is a reshape of the [D*H, in] matrix, not a permute (gcn.py:301);
-        # the projection GEMM wants the [D*H, in] matrix whose row d*H+h is weight_l[d, :, h]
-        wmat = self.W.weight.reshape(D, -1, H).permute(0, 2, 1).reshape(D * H, -1).contiguous()
-        ws = ops.weight_prep(wmat.detach(), self.gemm_mode)
-    else:
-        x = ops.linear(x, self.preprocessor.weight, self.preprocessor.bias, self.gemm_mode)    # gcn.py:255-257
-    B, T = csr.B, csr.T
-    for l in range(self.layers):
-        last = l == self.layers - 1
-        mask = None if injected is None else injected.get('gcn%d' % l)
-        cfg = ops.RelationLayerConfig(l, drop_p=0.0 if (last or mask is not None) else drop_p,
-                                      drop_mask=None if last else mask, rng_state=self.rng_state,
-                                      gemm_mode=self.gemm_mode)
-        if not full:
-            x = ops.relation_layer_diag(x, emb, csr, deprel, cfg)
-            continue
-        cfg.deep = l >= opt['deprel_max_depth']
-        cfg.directed, cfg.self_loop = bool(opt['deprel_directed']), bool(opt['deprel_self_loop'])
-        if injected is not None and ('edge_f%d' % l) in injected:
-            # tests: dense 0/1 [B,T,T] masks per direction, as maybe_drop_edges draws them (gcn.py:436-449)
-            cfg.keep_edges = tuple(injected['edge_%s%d' % (d, l)].to(torch.uint8).contiguous() for d in 'fr')
-        elif self.training and opt.get('edge_keep_prob', 1.0) < 1.0:
-            cfg.edge_keep = opt['edge_keep_prob']
-        if injected is not None and ('forget_f%d' % l) in injected:
-            cfg.keep_tokens = tuple(injected['forget_%s%d' % (d, l)].reshape(-1).to(torch.uint8).contiguous()
-                                    for d in 'fr')
-        elif self.training and opt.get('deprel_keep_prop', 1.0) < 1.0:
-            cfg.keep_tokens = ops.relation_keep_tokens(self.rng_state, B * T, l, opt['deprel_keep_prop'])
-        x = ops.relation_layer_full(x, wmat, self.W.bias, emb, csr, deprel, cfg, ws)
-    return x
-
-
-GCN._relation_layers = _relation_layers
 
 
 def pool(h, mask, type='max'):
