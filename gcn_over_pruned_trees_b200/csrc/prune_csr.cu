@@ -276,7 +276,11 @@ extern "C" int gpt_prune_csr(const int64_t* head, const int64_t* subj_pos, const
         configured = smem;
     }
     const int grid = (B + kWarpsPerCta - 1) / kWarpsPerCta;
+#ifdef GPT_HOST_EMULATION   // tests/emu: g++ has no <<<>>>
+    gpt_launch(prune_csr_kernel, dim3(grid), dim3(kWarpsPerCta * 32), smem, (cudaStream_t)stream,
+#else
     prune_csr_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(
+#endif
         reinterpret_cast<const long long*>(head), reinterpret_cast<const long long*>(subj_pos),
         reinterpret_cast<const long long*>(obj_pos), reinterpret_cast<const long long*>(deprel), pad_mask, B, T,
         prune_k, 3 * T, rowptr, col, val, flags, denom, lens, err);

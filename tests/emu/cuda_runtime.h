@@ -1,5 +1,5 @@
-// TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu (and the
-// helpers of csrc/gpt_common.cuh it uses) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
+// TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu and
+// csrc/prune_csr.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
 // fiber (ucontext) on the calling OS thread, scheduled round-robin; __syncthreads() and the warp shuffles are barriers
 // at which a fiber yields; blocks run one after the other; exited threads stop counting towards barriers, as on the
 // device.  Single-threaded and deterministic (atomics are plain adds).
@@ -160,6 +160,49 @@ inline T __shfl_up_sync(unsigned, T v, int o) {
     const int lane = emu::block->current & 31;
     return emu_shfl(v, lane >= o ? lane - o : lane);
 }
+
+inline void __syncwarp(unsigned = 0xffffffffu) {
+    const int me = emu::block->current;
+    emu::arrive_and_wait(emu::block->warp[me >> 5]);
+    threadIdx = emu_uint3{(unsigned)me, 0, 0};
+}
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) { return emu_shfl(v, src_lane); }
+// lanes of the warp that have not exited (K1's warps leave together, so this is 32 or the tail of a short block)
+inline int emu_warp_lanes() {
+    const int warp = emu::block->current >> 5;
+    return (warp + 1) * 32 <= emu::block->n ? 32 : emu::block->n - warp * 32;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    const int me = emu::block->current, warp = me >> 5, lane = me & 31;
+    emu::block->warp_buf[(size_t)warp * 32 + lane] = pred ? 1u : 0u;
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    unsigned m = 0;
+    for (int l = 0; l < emu_warp_lanes(); ++l) m |= emu::block->warp_buf[(size_t)warp * 32 + l] << l;
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    threadIdx = emu_uint3{(unsigned)me, 0, 0};
+    return m;
+}
+inline unsigned __match_any_sync(unsigned, int v) {
+    const int me = emu::block->current, warp = me >> 5, lane = me & 31;
+    emu::block->warp_buf[(size_t)warp * 32 + lane] = (uint32_t)v;
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    unsigned m = 0;
+    for (int l = 0; l < emu_warp_lanes(); ++l) m |= (emu::block->warp_buf[(size_t)warp * 32 + l] == (uint32_t)v ? 1u : 0u) << l;
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    threadIdx = emu_uint3{(unsigned)me, 0, 0};
+    return m;
+}
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int atomicAdd(int* p, int v) {
+    const int old = *p;
+    *p = old + v;
+    return old;
+}
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 inline float atomicAdd(float* p, float v) {
     const float old = *p;

@@ -1,22 +1,22 @@
-"""TEST INFRASTRUCTURE -- build tests/emu/_build/libdeprel_emu.so: csrc/deprel.cu compiled by g++ against the host
+"""TEST INFRASTRUCTURE -- build tests/emu/_build/libdeprel_emu.so: csrc/deprel.cu and csrc/prune_csr.cu compiled by g++ against the host
 stand-in for the CUDA runtime in this directory (one fiber per CUDA thread; see cuda_runtime.h)."""
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, '_build', 'libdeprel_emu.so')
-SRC = os.path.join(HERE, 'deprel_host.cpp')
-DEPS = [SRC, os.path.join(HERE, 'cuda_runtime.h'),
-        os.path.join(HERE, '..', '..', 'gcn_over_pruned_trees_b200', 'csrc', 'deprel.cu'),
-        os.path.join(HERE, '..', '..', 'gcn_over_pruned_trees_b200', 'csrc', 'gpt_common.cuh')]
+CSRC = os.path.join(HERE, '..', '..', 'gcn_over_pruned_trees_b200', 'csrc')
+SRCS = [os.path.join(HERE, 'deprel_host.cpp'), os.path.join(HERE, 'prune_host.cpp')]
+DEPS = SRCS + [os.path.join(HERE, 'cuda_runtime.h')] + [os.path.join(CSRC, f) for f in
+                                                         ('deprel.cu', 'prune_csr.cu', 'gpt_common.cuh')]
 
 
 def build():
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    subprocess.check_call(['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-x', 'c++', '-I', HERE,
-                           SRC, '-o', OUT])
+    subprocess.check_call(['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-x', 'c++', '-I', HERE] +
+                          SRCS + ['-o', OUT])
     return OUT
 
 

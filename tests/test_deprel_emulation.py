@@ -1,11 +1,11 @@
-"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers) executed on the host (tests/emu: one fiber per CUDA
+"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers) and csrc/prune_csr.cu (K1) executed on the host (tests/emu: one fiber per CUDA
 thread, barriers for __syncthreads / shuffles) underneath the product's own Python layers -- model/gcn.py ->
 ops.py autograd Functions -> C ABI -- and checked against the real reference's outputs (tests/golden/deprel.npz) and
 against the oracle with identical injected masks.
 
 The build container has no GPU, so the pieces of the path that only exist as GPU code are replaced here, and only
-here, by stand-ins: K1's CSR is built from the oracle's dense adjacency, the K3 GEMMs are torch.matmul, K4 is the
-reference's pool(), K5 is nn.Embedding.  What this file pins is therefore K10's arithmetic, its direction / edge /
+here, by stand-ins: the K3 GEMMs are torch.matmul, K4 is the reference's pool(), K5 is nn.Embedding.  What this file
+pins is therefore K1's CSR as K10 consumes it, K10's arithmetic, its direction / edge /
 forgetting conventions, the weight_l re-layout and every backward formula; the `-m gpu` tests in test_gpu_relation_modes.py
 run the same cases on the device with nothing replaced.
 """
@@ -22,41 +22,13 @@ import weights
 from gcn_over_pruned_trees_b200 import _lib, ops, synth
 from gcn_over_pruned_trees_b200.model import gcn as gcn_mod
 from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
-from oracle import gcn_oracle, tree_oracle
+from oracle import gcn_oracle
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
 
-K10 = ('gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
+K10 = ('gpt_prune_csr', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
        'gpt_edge_keep_dense', 'gpt_relation_keep_tokens', 'gpt_colsum_acc')
 _ALL = dict(cases.DEPREL_CASES, **cases.DEPREL_RANDOM_CASES)
-
-
-def _cpu_csr(head, subj_pos, obj_pos, deprel, masks, prune_k, out=None):
-    """Stand-in for K1 with its output layout (include/gpt_b200.h, gpt_prune_csr): rows ascending by column."""
-    B, T = head.shape
-    lens = (masks.numpy() == 0).sum(1)
-    adj = tree_oracle.batch_adjacency(head.numpy(), subj_pos.numpy(), obj_pos.numpy(), deprel.numpy(), lens,
-                                      prune_k, T)
-    csr = ops.TreeCSR(B, T, head.device)
-    rowptr = np.zeros((B, T + 1), dtype=np.int32)
-    col = np.zeros((B, 3 * T), dtype=np.int32)
-    val = np.zeros((B, 3 * T), dtype=np.uint8)
-    for b in range(B):
-        rows, cols = np.nonzero(adj[b])                      # row-major: columns ascending inside a row
-        rowptr[b, 1:] = np.cumsum(np.bincount(rows, minlength=T))
-        col[b, :len(cols)] = cols
-        val[b, :len(cols)] = adj[b, rows, cols].astype(np.uint8)
-    csr.rowptr.copy_(torch.from_numpy(rowptr))
-    csr.col.copy_(torch.from_numpy(col))
-    csr.val.copy_(torch.from_numpy(val))
-    nnz = torch.from_numpy((adj != 0).sum(2).astype(np.float32))
-    in_tree = torch.from_numpy(((adj != 0).sum(2) + (adj != 0).sum(1)) > 0)
-    csr.denom.copy_(nnz + 1)
-    csr.flags.copy_((in_tree.to(torch.uint8) | (subj_pos.eq(0).to(torch.uint8) << 1) |
-                     (obj_pos.eq(0).to(torch.uint8) << 2)))
-    csr.lens.copy_(torch.from_numpy(lens.astype(np.int32)))
-    csr.err.zero_()
-    return csr
 
 
 def _cpu_pool3(h, csr, pool_type='max'):
@@ -82,7 +54,6 @@ def emulated(request):
     mp.setattr(ops, 'linear_fwd', lambda x2d, weight, mode='fp32', ws=None: x2d @ weight.t())
     mp.setattr(ops, 'linear_dgrad', lambda dy, weight, mode='fp32', ws=None: dy @ weight)
     mp.setattr(ops, 'linear_wgrad', lambda dy, x2d, mode='fp32', **kw: dy.t() @ x2d)
-    mp.setattr(ops, 'prune_csr', _cpu_csr)
     mp.setattr(ops, 'pool3', _cpu_pool3)
     yield handle
     mp.undo()
@@ -239,7 +210,7 @@ def test_in_kernel_dropout_rate_and_backward_consistency(emulated, golden_adj):
     B, T = batch[0].shape
     H = opt['hidden_dim']
     inputs = list(batch[:-2])
-    csr = _cpu_csr(inputs[5], inputs[6], inputs[7], inputs[4], inputs[1], opt['prune_k'])
+    csr = ops.prune_csr(inputs[5], inputs[6], inputs[7], inputs[4], inputs[1], opt['prune_k'])
     g = torch.Generator().manual_seed(0)
     F, R, S = (torch.randn(B * T, H, generator=g) for _ in range(3))
     cfg0 = ops.RelationLayerConfig(0, rng_state=gcn.rng_state)
