@@ -1,5 +1,5 @@
-"""ORACLE (test infrastructure, not product code) -- CPU/PyTorch-fp32 restatement of the reference's
-``adj_type='regular'`` GCN classifier and of the loss ``GCNTrainer.update`` builds.
+"""ORACLE (test infrastructure, not product code) -- CPU/PyTorch-fp32 restatement of the reference's GCN classifier
+(``adj_type`` 'regular', 'full_deprel', 'diagonal_deprel') and of the loss ``GCNTrainer.update`` builds.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
 import this module.
@@ -24,8 +24,9 @@ Reference lines restated:
   pooling                      /root/reference/model/gcn.py:116-122, 473-483
   loss                         /root/reference/model/trainer.py:93-100
 
-Pinning: ``tests/golden/make_golden.py`` runs the real reference (imported from /root/reference) on seeded
-inputs and stores logits / loss / gradients; ``tests/test_oracle_golden.py`` checks this module against them.
+Pinning: ``tests/golden/make_golden.py`` and ``make_deprel_golden.py`` run the real reference (imported from
+/root/reference) on seeded inputs and store logits / loss / gradients; ``tests/test_oracle_golden.py`` checks this
+module against them.
 """
 import numpy as np
 import torch
