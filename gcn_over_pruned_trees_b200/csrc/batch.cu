@@ -77,6 +77,11 @@ extern "C" int gpt_build_batch(const int32_t* const* arena, const int64_t* offse
     p.B = B; p.T = T;
     p.thresh24 = (unsigned)(word_dropout * 16777216.0f);
     p.seed = seed; p.stream = stream_id;
+#ifdef GPT_HOST_EMULATION   // tests/emu: g++ has no <<<>>>
+    gpt_launch(build_batch_kernel, dim3((T + kBatchThreads - 1) / kBatchThreads, B), dim3(kBatchThreads), 0,
+               (cudaStream_t)stream, p);
+#else
     build_batch_kernel<<<dim3((T + kBatchThreads - 1) / kBatchThreads, B), kBatchThreads, 0, (cudaStream_t)stream>>>(p);
+#endif
     return gpt_launch_status();
 }
