@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu,
-// csrc/prune_csr.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
+// csrc/prune_csr.cu, csrc/pool3.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
 // fiber (ucontext) on the calling OS thread, scheduled round-robin; __syncthreads() and the warp shuffles are barriers
 // at which a fiber yields; blocks run one after the other; exited threads stop counting towards barriers, as on the
 // device.  Single-threaded and deterministic (atomics are plain adds).
@@ -22,7 +22,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__
+#define __shared__ thread_local   // one OS thread runs every fiber: function-scope and extern shared arrays alike
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
     unsigned x, y, z;
@@ -31,6 +32,13 @@ struct dim3 {
 struct emu_uint3 {
     unsigned x, y, z;
 };
+struct __attribute__((aligned(16))) float4 {
+    float x, y, z, w;
+};
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+inline float __frcp_rn(float x) { return 1.0f / x; }
 
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;

@@ -4,7 +4,7 @@
 #include "cuda_runtime.h"
 
 namespace {
-int smem[200 * 1024 / 4];   // the kernel's `extern __shared__ int smem[]`: one block runs at a time
+thread_local int smem[200 * 1024 / 4];   // the kernel's `extern __shared__ int smem[]`: one block runs at a time
 }
 
 #include "../../gcn_over_pruned_trees_b200/csrc/prune_csr.cu"

@@ -1,13 +1,13 @@
-"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers) and csrc/prune_csr.cu (K1) executed on the host (tests/emu: one fiber per CUDA
-thread, barriers for __syncthreads / shuffles) underneath the product's own Python layers -- model/gcn.py ->
-ops.py autograd Functions -> C ABI -- and checked against the real reference's outputs (tests/golden/deprel.npz) and
-against the oracle with identical injected masks.
+"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers), csrc/prune_csr.cu (K1) and csrc/pool3.cu (K4)
+executed on the host (tests/emu: one fiber per CUDA thread, barriers for __syncthreads / shuffles) underneath the
+product's own Python layers -- model/gcn.py -> ops.py autograd Functions -> C ABI -- and checked against the real
+reference's outputs (tests/golden/deprel.npz) and against the oracle with identical injected masks.
 
 The build container has no GPU, so the pieces of the path that only exist as GPU code are replaced here, and only
-here, by stand-ins: the K3 GEMMs are torch.matmul, K4 is the reference's pool(), K5 is nn.Embedding.  What this file
-pins is therefore K1's CSR as K10 consumes it, K10's arithmetic, its direction / edge /
-forgetting conventions, the weight_l re-layout and every backward formula; the `-m gpu` tests in test_gpu_relation_modes.py
-run the same cases on the device with nothing replaced.
+here, by stand-ins: the K3 GEMMs are torch.matmul, K5 is nn.Embedding.  What this file pins is therefore K1's CSR as
+K10 and K4 consume it, K10's arithmetic, its direction / edge / forgetting conventions, the weight_l re-layout and
+every backward formula; the `-m gpu` tests in test_gpu_relation_modes.py run the same cases on the device with nothing
+replaced.
 """
 import ctypes
 import os
@@ -20,21 +20,14 @@ import torch
 import cases
 import weights
 from gcn_over_pruned_trees_b200 import _lib, ops, synth
-from gcn_over_pruned_trees_b200.model import gcn as gcn_mod
 from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
 from oracle import gcn_oracle
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
 
-K10 = ('gpt_prune_csr', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
+K10 = ('gpt_prune_csr', 'gpt_pool3_fwd', 'gpt_pool3_bwd', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
        'gpt_edge_keep_dense', 'gpt_relation_keep_tokens', 'gpt_colsum_acc')
 _ALL = dict(cases.DEPREL_CASES, **cases.DEPREL_RANDOM_CASES)
-
-
-def _cpu_pool3(h, csr, pool_type='max'):
-    f = csr.flags
-    masks = [(f & bit).eq(0).unsqueeze(2) for bit in (1, 2, 4)]
-    return torch.cat([gcn_mod.pool(h, m, pool_type) for m in masks], dim=1)
 
 
 @pytest.fixture(scope='module')
@@ -54,7 +47,6 @@ def emulated(request):
     mp.setattr(ops, 'linear_fwd', lambda x2d, weight, mode='fp32', ws=None: x2d @ weight.t())
     mp.setattr(ops, 'linear_dgrad', lambda dy, weight, mode='fp32', ws=None: dy @ weight)
     mp.setattr(ops, 'linear_wgrad', lambda dy, x2d, mode='fp32', **kw: dy.t() @ x2d)
-    mp.setattr(ops, 'pool3', _cpu_pool3)
     yield handle
     mp.undo()
 
