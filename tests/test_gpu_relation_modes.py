@@ -207,8 +207,9 @@ def test_relation_modes_train_loop_lowers_the_loss(golden_adj, name):
 @pytest.mark.parametrize('name', ('full_k1_d8', 'diag_k1', 'full_edge_drop', 'full_forget'))
 def test_relation_modes_graphed_step_lowers_the_loss(golden_adj, name):
     """trainer.train_step: the same step captured into a CUDA graph (autograd under capture, GraphedTrainStep).  A
-    fresh trainer: an autograd graph kept alive from eager steps on the default stream pins its AccumulateGrad nodes
-    to that stream, which a capture on another stream may not depend on."""
+    fresh trainer: a capture that followed eager update()/backward() steps whose last loss tensor was still referenced
+    failed once with cudaErrorStreamCaptureImplicit (suspected: AccumulateGrad nodes kept alive
+    by the old graph carry the default stream)."""
     opt, batch, trainer, _ = _setup(golden_adj, name, 'tf32x3')
     trainer.model.train()
     graphed = [float(trainer.train_step(batch)) for _ in range(10)]
