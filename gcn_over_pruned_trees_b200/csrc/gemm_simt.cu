@@ -144,8 +144,13 @@ int run_sgemm(int M, int N, int K, const float* A, int lda, const float* B, int 
     splits = (K + k_per_split - 1) / k_per_split;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
     if (grid.y > 65535 || grid.z > 65535) return GPT_ERR_UNSUPPORTED;
+#ifdef GPT_HOST_EMULATION   // tests/emu: g++ has no <<<>>>
+    gpt_launch(sgemm_kernel<A_KC, B_KC>, grid, dim3(kGemmThreads), 0, st, M, N, K, A, lda, B, ldb, C, ldc, k_per_split,
+               (splits > 1 || force_atomic) ? 1 : 0);
+#else
     sgemm_kernel<A_KC, B_KC><<<grid, kGemmThreads, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, k_per_split,
                                                            (splits > 1 || force_atomic) ? 1 : 0);
+#endif
     return gpt_launch_status();
 }
 
@@ -258,8 +263,12 @@ wgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
         if (n >= N) continue;
         if (vec_out) {           // one 16-byte reduction instead of four atomics (the partial sums of all splits meet in L2)
             if (acc[i][0] != 0.f || acc[i][1] != 0.f || acc[i][2] != 0.f || acc[i][3] != 0.f)
+#ifdef GPT_HOST_EMULATION
+                for (int j = 0; j < 4; ++j) atomicAdd(dw + (size_t)n * K + k0 + tx * 4 + j, acc[i][j]);
+#else
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + (size_t)n * K + k0 + tx * 4),
                              "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
+#endif
             continue;
         }
 #pragma unroll
@@ -291,7 +300,11 @@ extern "C" int gpt_linear_wgrad_f32(const float* dy, const float* x, float* dw, 
     int splits = (int)max(1L, min((long)(M + 255) / 256, (4L * 148 + tiles - 1) / tiles));
     if (splits > 1 || M == 0) {
         const size_t n = (size_t)N * K;
+#ifdef GPT_HOST_EMULATION
+        gpt_launch(zero_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, dw, N, K, K);
+#else
         zero_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dw, N, K, K);
+#endif
         const int rc = gpt_launch_status();
         if (rc != GPT_OK || M == 0) return rc;
     }
@@ -316,6 +329,11 @@ extern "C" int gpt_linear_wgrad_rows_f32(const float* dy, const float* x, const 
     splits = (M + rows_per_cta - 1) / rows_per_cta;
     dim3 grid((N + BM - 1) / BM, (K + BN - 1) / BN, splits);
     if (grid.y > 65535 || grid.z > 65535) return GPT_ERR_UNSUPPORTED;
+#ifdef GPT_HOST_EMULATION
+    gpt_launch(wgrad_rows_kernel, grid, dim3(kGemmThreads), 0, (cudaStream_t)stream, dy, x, flags, dw, M, N, K,
+               rows_per_cta);
+#else
     wgrad_rows_kernel<<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(dy, x, flags, dw, M, N, K, rows_per_cta);
+#endif
     return gpt_launch_status();
 }

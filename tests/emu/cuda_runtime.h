@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu,
-// csrc/prune_csr.cu, csrc/pool3.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
+// csrc/prune_csr.cu, csrc/pool3.cu, csrc/gemm_simt.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
 // fiber (ucontext) on the calling OS thread, scheduled round-robin; __syncthreads() and the warp shuffles are barriers
 // at which a fiber yields; blocks run one after the other; exited threads stop counting towards barriers, as on the
 // device.  Single-threaded and deterministic (atomics are plain adds).
@@ -220,11 +220,13 @@ inline float atomicAdd(float* p, float v) {
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
+inline long max(long a, long b) { return a > b ? a : b; }
+inline long min(long a, long b) { return a < b ? a : b; }
 
 template <typename... K, typename... A>
 inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(K...), A... args) {
     const int n = (int)cfg->blockDim.x;
-    if (cfg->blockDim.y != 1 || cfg->blockDim.z != 1 || cfg->gridDim.z != 1 || n < 1) return 1;
+    if (cfg->blockDim.y != 1 || cfg->blockDim.z != 1 || n < 1) return 1;
     emu::Block blk;
     blk.n = n;
     blk.fibers.resize(n);
@@ -235,11 +237,12 @@ inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern
     emu::block = &blk;
     blockDim = cfg->blockDim;
     gridDim = cfg->gridDim;
-    for (unsigned by = 0; by < cfg->gridDim.y; ++by)
-        for (unsigned bx = 0; bx < cfg->gridDim.x; ++bx) {
-            blockIdx = emu_uint3{bx, by, 0};
-            emu::run_block(blk);          // shared memory belongs to one block at a time
-        }
+    for (unsigned bz = 0; bz < cfg->gridDim.z; ++bz)
+        for (unsigned by = 0; by < cfg->gridDim.y; ++by)
+            for (unsigned bx = 0; bx < cfg->gridDim.x; ++bx) {
+                blockIdx = emu_uint3{bx, by, bz};
+                emu::run_block(blk);      // shared memory belongs to one block at a time
+            }
     for (auto& f : blk.fibers) std::free(f.stack);
     emu::block = nullptr;
     return cudaSuccess;

@@ -1,11 +1,11 @@
-"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers), csrc/prune_csr.cu (K1) and csrc/pool3.cu (K4)
-executed on the host (tests/emu: one fiber per CUDA thread, barriers for __syncthreads / shuffles) underneath the
+"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers), csrc/prune_csr.cu (K1), csrc/pool3.cu (K4) and
+csrc/gemm_simt.cu (K3, fp32 mode) executed on the host (tests/emu: one fiber per CUDA thread, barriers for __syncthreads / shuffles) underneath the
 product's own Python layers -- model/gcn.py -> ops.py autograd Functions -> C ABI -- and checked against the real
 reference's outputs (tests/golden/deprel.npz) and against the oracle with identical injected masks.
 
 The build container has no GPU, so the pieces of the path that only exist as GPU code are replaced here, and only
-here, by stand-ins: the K3 GEMMs are torch.matmul, K5 is nn.Embedding.  What this file pins is therefore K1's CSR as
-K10 and K4 consume it, K10's arithmetic, its direction / edge / forgetting conventions, the weight_l re-layout and
+here, by a stand-in: K5 is nn.Embedding (and cuDNN's LSTM runs as torch's CPU LSTM).  What this file pins is
+therefore K1's CSR as K10 and K4 consume it, the projections and their gradients, K10's arithmetic, its direction / edge / forgetting conventions, the weight_l re-layout and
 every backward formula; the `-m gpu` tests in test_gpu_relation_modes.py run the same cases on the device with nothing
 replaced.
 """
@@ -25,7 +25,8 @@ from oracle import gcn_oracle
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
 
-K10 = ('gpt_prune_csr', 'gpt_pool3_fwd', 'gpt_pool3_bwd', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
+K10 = ('gpt_prune_csr', 'gpt_pool3_fwd', 'gpt_pool3_bwd', 'gpt_linear_fwd_f32', 'gpt_linear_dgrad_f32',
+       'gpt_linear_wgrad_f32', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
        'gpt_edge_keep_dense', 'gpt_relation_keep_tokens', 'gpt_colsum_acc')
 _ALL = dict(cases.DEPREL_CASES, **cases.DEPREL_RANDOM_CASES)
 
@@ -43,10 +44,6 @@ def emulated(request):
     mp.setattr(ops, '_dev', lambda t, dtype, name: t.contiguous() if t.dtype == dtype else (_ for _ in ()).throw(
         TypeError('%s must be %s' % (name, dtype))))
     mp.setattr(ops, '_stream', lambda: None)
-    mp.setattr(ops, 'weight_prep', lambda weight, mode, out=None: None)
-    mp.setattr(ops, 'linear_fwd', lambda x2d, weight, mode='fp32', ws=None: x2d @ weight.t())
-    mp.setattr(ops, 'linear_dgrad', lambda dy, weight, mode='fp32', ws=None: dy @ weight)
-    mp.setattr(ops, 'linear_wgrad', lambda dy, x2d, mode='fp32', **kw: dy.t() @ x2d)
     yield handle
     mp.undo()
 
@@ -58,7 +55,7 @@ def _setup(golden_adj, name, batch_size=None):
         over = dict(over, vocab_size=int(golden_adj['vocab_size']))
     else:
         batch = cases.make_case_batch((source[0], source[1], batch_size or source[2]), over)
-    opt = synth.tacred_opt(**over)
+    opt = synth.tacred_opt(**dict(over, gemm_mode='fp32'))       # K3's FFMA kernels; tcgen05 cannot be emulated
     state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, wseed).items()}
     trainer = GCNTrainer(dict(opt))
     trainer.model.load_state_dict(state)
