@@ -124,8 +124,12 @@ embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned
                 if (c >= D) break;
                 if (vec_rows && c + 3 < p.E) {              // whole quad in the word row: one 16-byte reduction
                     if (word_live && (v[4 * h] != 0.f || v[4 * h + 1] != 0.f || v[4 * h + 2] != 0.f || v[4 * h + 3] != 0.f))
+#ifdef GPT_HOST_EMULATION   // tests/emu
+                        for (int k = 0; k < 4; ++k) atomicAdd(g_emb + (size_t)w * p.E + c + k, v[4 * h + k]);
+#else
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g_emb + (size_t)w * p.E + c),
                                      "f"(v[4 * h]), "f"(v[4 * h + 1]), "f"(v[4 * h + 2]), "f"(v[4 * h + 3]) : "memory");
+#endif
                     continue;
                 }
 #pragma unroll
@@ -259,8 +263,13 @@ extern "C" int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner,
                                      int topn, float* sq, void* stream) {
     GPT_CHECK_ARG(words && owner && g_emb && sq && n_rows >= 0 && E >= 1);
     if (n_rows == 0) return GPT_OK;
+#ifdef GPT_HOST_EMULATION   // tests/emu: g++ has no <<<>>>
+    gpt_launch(rows_sqnorm_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream,
+               reinterpret_cast<const long long*>(words), owner, g_emb, n_rows, E, topn, sq);
+#else
     rows_sqnorm_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(words),
                                                                          owner, g_emb, n_rows, E, topn, sq);
+#endif
     return gpt_launch_status();
 }
 
@@ -269,8 +278,13 @@ extern "C" int gpt_embed_rows_sgd(const int64_t* words, int32_t* owner, float* g
     GPT_CHECK_ARG(words && owner && g_emb && emb_w && n_rows >= 0 && E >= 1);
     GPT_CHECK_ARG(max_norm <= 0.f || total_sq != nullptr);
     if (n_rows == 0) return GPT_OK;
+#ifdef GPT_HOST_EMULATION
+    gpt_launch(rows_sgd_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream,
+               reinterpret_cast<const long long*>(words), owner, g_emb, emb_w, n_rows, E, topn, total_sq, max_norm, lr);
+#else
     rows_sgd_kernel<<<n_rows, kEmbThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(words), owner,
                                                                       g_emb, emb_w, n_rows, E, topn, total_sq, max_norm,
                                                                       lr);
+#endif
     return gpt_launch_status();
 }

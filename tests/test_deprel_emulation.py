@@ -1,11 +1,12 @@
-"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers), csrc/prune_csr.cu (K1), csrc/pool3.cu (K4) and
-csrc/gemm_simt.cu (K3, fp32 mode) executed on the host (tests/emu: one fiber per CUDA thread, barriers for __syncthreads / shuffles) underneath the
+"""CPU: the SOURCE of csrc/deprel.cu (K10, relation-aware layers), csrc/prune_csr.cu (K1), csrc/embed.cu (K5),
+csrc/gemm_simt.cu (K3, fp32 mode) and csrc/pool3.cu (K4) executed on the host (tests/emu: one fiber per CUDA thread, barriers for __syncthreads / shuffles) underneath the
 product's own Python layers -- model/gcn.py -> ops.py autograd Functions -> C ABI -- and checked against the real
 reference's outputs (tests/golden/deprel.npz) and against the oracle with identical injected masks.
 
 The build container has no GPU, so the pieces of the path that only exist as GPU code are replaced here, and only
-here, by a stand-in: K5 is nn.Embedding (and cuDNN's LSTM runs as torch's CPU LSTM).  What this file pins is
-therefore K1's CSR as K10 and K4 consume it, the projections and their gradients, K10's arithmetic, its direction / edge / forgetting conventions, the weight_l re-layout and
+here: cuDNN's LSTM runs as torch's CPU LSTM, and where dropout masks are injected the embedding stage is torch's
+lookup (K5 draws its own Philox mask; the eval-mode cases run K5 itself).  What this file pins is therefore K1's CSR as
+K10 and K4 consume it, the embedding stage, the projections and their gradients, K10's arithmetic, its direction / edge / forgetting conventions, the weight_l re-layout and
 every backward formula; the `-m gpu` tests in test_gpu_relation_modes.py run the same cases on the device with nothing
 replaced.
 """
@@ -26,7 +27,7 @@ from oracle import gcn_oracle
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
 
 K10 = ('gpt_prune_csr', 'gpt_pool3_fwd', 'gpt_pool3_bwd', 'gpt_linear_fwd_f32', 'gpt_linear_dgrad_f32',
-       'gpt_linear_wgrad_f32', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
+       'gpt_linear_wgrad_f32', 'gpt_embed_fwd', 'gpt_embed_bwd', 'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
        'gpt_edge_keep_dense', 'gpt_relation_keep_tokens', 'gpt_colsum_acc')
 _ALL = dict(cases.DEPREL_CASES, **cases.DEPREL_RANDOM_CASES)
 
@@ -59,7 +60,6 @@ def _setup(golden_adj, name, batch_size=None):
     state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, wseed).items()}
     trainer = GCNTrainer(dict(opt))
     trainer.model.load_state_dict(state)
-    trainer.model.gcn_model.gcn.injected_masks = {}          # plain embedding lookups instead of K5
     oracle = gcn_oracle.DenseClassifier(opt)
     oracle.load_state_dict(state)
     return opt, batch, trainer, oracle
@@ -138,6 +138,27 @@ def test_emulated_kernels_train_grads_match_oracle(emulated, golden_adj, name, e
     assert _compare_grads(trainer, oracle) >= 8
     g = trainer.model.gcn_model.deprel_emb.weight.grad
     assert float(g[0].abs().max()) == 0.0                    # padding_idx row
+
+
+@pytest.mark.parametrize('name', ('full_k1_d8', 'diag_k1'))
+def test_emulated_whole_model_train_step_without_dropout(emulated, golden_adj, name):
+    """Nothing injected, nothing replaced (dropout probabilities 0): K1, K5 (forward + scatter backward), K3, K10 and K4
+    from source under the product's autograd path; loss and every gradient against the oracle."""
+    over, source, wseed = _ALL[name]
+    _ALL['_nodrop'] = (dict(over, input_dropout=0.0, gcn_dropout=0.0), (source[0], source[1], 8), wseed)
+    try:
+        opt, batch, trainer, oracle = _setup(golden_adj, '_nodrop')
+    finally:
+        del _ALL['_nodrop']
+    assert trainer.model.gcn_model.gcn.injected_masks is None
+    trainer.model.train()
+    oracle.train()
+    loss = trainer.update(batch)
+    loss.backward()
+    ref_loss, _ = oracle.loss(batch)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert _compare_grads(trainer, oracle) >= 8
 
 
 def test_emulated_rows_beyond_one_wave_of_ctas(emulated, golden_adj, monkeypatch):
