@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu,
-// csrc/prune_csr.cu, csrc/pool3.cu, csrc/gemm_simt.cu, csrc/embed.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
+// csrc/prune_csr.cu, csrc/pool3.cu, csrc/gemm_simt.cu, csrc/embed.cu, csrc/update.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
 // fiber (ucontext) on the calling OS thread, scheduled round-robin; __syncthreads() and the warp shuffles are barriers
 // at which a fiber yields; blocks run one after the other; exited threads stop counting towards barriers, as on the
 // device.  Single-threaded and deterministic (atomics are plain adds).

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE -- build tests/emu/_build/libdeprel_emu.so: csrc/{deprel,prune_csr,pool3,gemm_simt,embed,batch}.cu compiled by g++ against the host
+"""TEST INFRASTRUCTURE -- build tests/emu/_build/libdeprel_emu.so: csrc/{deprel,prune_csr,pool3,gemm_simt,embed,update,batch}.cu compiled by g++ against the host
 stand-in for the CUDA runtime in this directory (one fiber per CUDA thread; see cuda_runtime.h)."""
 import os
 import subprocess
@@ -6,9 +6,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, '_build', 'libdeprel_emu.so')
 CSRC = os.path.join(HERE, '..', '..', 'gcn_over_pruned_trees_b200', 'csrc')
-SRCS = [os.path.join(HERE, f) for f in ('deprel_host.cpp', 'prune_host.cpp', 'batch_host.cpp', 'pool_host.cpp', 'gemm_host.cpp', 'embed_host.cpp')]
+SRCS = [os.path.join(HERE, f) for f in ('deprel_host.cpp', 'prune_host.cpp', 'batch_host.cpp', 'pool_host.cpp', 'gemm_host.cpp', 'embed_host.cpp', 'update_host.cpp')]
 DEPS = SRCS + [os.path.join(HERE, 'cuda_runtime.h')] + [os.path.join(CSRC, f) for f in
-                                                         ('deprel.cu', 'prune_csr.cu', 'batch.cu', 'pool3.cu', 'gemm_simt.cu', 'embed.cu', 'gpt_common.cuh')]
+                                                         ('deprel.cu', 'prune_csr.cu', 'batch.cu', 'pool3.cu', 'gemm_simt.cu', 'embed.cu', 'update.cu', 'gpt_common.cuh')]
 
 
 def build():
