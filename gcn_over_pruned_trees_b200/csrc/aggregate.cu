@@ -61,6 +61,9 @@ struct AggParams {
     int tma_rows;
 };
 
+#ifdef GPT_HOST_EMULATION   // tests/emu: the same accessors on a host array instead of PTX
+#include "emu_smem_ops.h"
+#else
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc));
 }
@@ -121,6 +124,11 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
 
 // ---- shared-memory carve-up (host and device agree through Layout) -------------------------------------------
 //   tile [nbuf][T+1][HS]  staged rows; row T is all zeros (target of padded gather slots and of rows past T)
@@ -212,7 +220,7 @@ __device__ __forceinline__ void tma_bars_init(unsigned long long* bars) {
     if (threadIdx.x == 0) {
         tc::mbar_init(tc::smem_addr(&bars[0]), 1);
         tc::mbar_init(tc::smem_addr(&bars[1]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
 }
 
@@ -233,7 +241,7 @@ __device__ __forceinline__ void issue_slice(const float* __restrict__ src_b, uin
             const int row = q / HS, cc = q % HS, c = col0 + cc;
             const uint32_t dst = tile_s + (uint32_t)q * 4u;
             if (c < H) cp_async4(dst, src_b + (size_t)row * H + c);
-            else asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(0.f) : "memory");
+            else sts_f32(dst, 0.f);
         }
     }
 }
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 3) aggregate_bwd_kernel(co
                     const uint32_t w = lds32(actw_s + (uint32_t)r[k] * 4u) >> tid;       // LPR == 8: HS == 32
                     const float inv = __uint_as_float(lds64(meta_s + (uint32_t)r[k] * 8u).y);
                     const float g = v[k] * ((float)(w & 1u) * ds) * inv;
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile_s + (uint32_t)(r[k] * HS + tid) * 4u), "f"(g) : "memory");
+                    sts_f32(tile_s + (uint32_t)(r[k] * HS + tid) * 4u, g);
                 }
             }
             __syncthreads();

@@ -5,6 +5,9 @@
 
 namespace tc {
 
+#ifdef GPT_HOST_EMULATION   // tests/emu: K2's cp.async path runs on the host; the TMA / mbarrier entry points only have to compile
+#include "emu_tc_ops.h"
+#else
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -38,12 +41,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+#endif
 __device__ __forceinline__ float tf32_hi(float v) {  // round to nearest TF32 (ties away), low 13 bits zero
     return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+#ifndef GPT_HOST_EMULATION
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), Blackwell version bits: start address >> 4 in [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type in [61,64).

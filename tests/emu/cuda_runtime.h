@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE -- a host stand-in for <cuda_runtime.h>, just large enough to compile csrc/deprel.cu,
-// csrc/prune_csr.cu, csrc/pool3.cu, csrc/gemm_simt.cu, csrc/embed.cu, csrc/update.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
+// csrc/prune_csr.cu, csrc/pool3.cu, csrc/gemm_simt.cu, csrc/embed.cu, csrc/aggregate.cu, csrc/update.cu and csrc/batch.cu (and the helpers of csrc/gpt_common.cuh they use) with g++ and run its kernels on the CPU: every CUDA thread of a block is a
 // fiber (ucontext) on the calling OS thread, scheduled round-robin; __syncthreads() and the warp shuffles are barriers
 // at which a fiber yields; blocks run one after the other; exited threads stop counting towards barriers, as on the
 // device.  Single-threaded and deterministic (atomics are plain adds).
@@ -17,7 +17,13 @@
 #include <utility>
 #include <vector>
 
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline long max(long a, long b) { return a > b ? a : b; }
+inline long min(long a, long b) { return a < b ? a : b; }
+
 #define __global__
+#define __grid_constant__
 #define __device__
 #define __host__
 #define __forceinline__ inline
@@ -36,6 +42,29 @@ struct __attribute__((aligned(16))) float4 {
     float x, y, z, w;
 };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct __attribute__((aligned(8))) uint2 {
+    unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline unsigned __float_as_uint(float v) {
+    unsigned u;
+    std::memcpy(&u, &v, 4);
+    return u;
+}
+inline float __uint_as_float(unsigned u) {
+    float v;
+    std::memcpy(&v, &u, 4);
+    return v;
+}
+inline void __trap() { std::abort(); }
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+constexpr unsigned long long cudaEnableDefault = 0;
+inline int cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+    *fn = nullptr;
+    *q = cudaDriverEntryPointSymbolNotFound;     // no driver on the host: no tensor maps, K2 takes its cp.async path
+    return 1;
+}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline float __frcp_rn(float x) { return 1.0f / x; }
@@ -71,8 +100,13 @@ struct Barrier {
     int arrived = 0, live = 0;
     unsigned generation = 0;
 };
+#if defined(__x86_64__)
+#define EMU_FAST_SWITCH 1      // hand-written stack switch (emu_switch.cpp): swapcontext() costs two system calls
+extern "C" void emu_switch(void** save_sp, void* const* load_sp);
+#endif
 struct Fiber {
     ucontext_t ctx;
+    void* sp = nullptr;
     char* stack = nullptr;
     bool done = false;
 };
@@ -80,6 +114,7 @@ struct Block {
     int n = 0, current = 0;
     std::vector<Fiber> fibers;
     ucontext_t scheduler;
+    void* scheduler_sp = nullptr;
     Barrier sync;
     std::vector<Barrier> warp;
     std::vector<uint32_t> warp_buf;
@@ -87,7 +122,13 @@ struct Block {
 };
 inline Block* block = nullptr;
 
-inline void yield() { swapcontext(&block->fibers[block->current].ctx, &block->scheduler); }
+inline void yield() {
+#ifdef EMU_FAST_SWITCH
+    emu_switch(&block->fibers[block->current].sp, &block->scheduler_sp);
+#else
+    swapcontext(&block->fibers[block->current].ctx, &block->scheduler);
+#endif
+}
 
 inline void arrive_and_wait(Barrier& b) {
     const unsigned g = b.generation;
@@ -112,6 +153,10 @@ inline void trampoline() {
     blk->fibers[blk->current].done = true;
     leave(blk->sync);
     leave(blk->warp[blk->current >> 5]);
+#ifdef EMU_FAST_SWITCH
+    emu_switch(&blk->fibers[blk->current].sp, &blk->scheduler_sp);     // never resumed
+    std::abort();
+#endif
 }
 
 inline void run_block(Block& blk) {
@@ -121,11 +166,20 @@ inline void run_block(Block& blk) {
     for (int t = 0; t < n; ++t) {
         Fiber& f = blk.fibers[t];
         f.done = false;
+#ifdef EMU_FAST_SWITCH
+        // frame emu_switch() pops: six callee-saved registers, then `ret` into trampoline with the stack as after a call
+        void** top = reinterpret_cast<void**>((reinterpret_cast<uintptr_t>(f.stack) + kStackBytes) & ~(uintptr_t)15);
+        top[-1] = nullptr;
+        top[-2] = reinterpret_cast<void*>(&trampoline);
+        for (int i = 3; i <= 8; ++i) top[-i] = nullptr;
+        f.sp = top - 8;
+#else
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = f.stack;
         f.ctx.uc_stack.ss_size = kStackBytes;
         f.ctx.uc_link = &blk.scheduler;
         makecontext(&f.ctx, trampoline, 0);
+#endif
     }
     for (int remaining = n; remaining > 0;) {
         remaining = 0;
@@ -134,7 +188,11 @@ inline void run_block(Block& blk) {
             if (f.done) continue;
             blk.current = t;
             threadIdx = emu_uint3{(unsigned)t, 0, 0};
+#ifdef EMU_FAST_SWITCH
+            emu_switch(&blk.scheduler_sp, &f.sp);
+#else
             swapcontext(&blk.scheduler, &f.ctx);
+#endif
             if (!f.done) ++remaining;
         }
     }
@@ -201,6 +259,16 @@ inline unsigned __match_any_sync(unsigned, int v) {
     threadIdx = emu_uint3{(unsigned)me, 0, 0};
     return m;
 }
+inline int __reduce_max_sync(unsigned, int v) {
+    const int me = emu::block->current, warp = me >> 5, lane = me & 31;
+    emu::block->warp_buf[(size_t)warp * 32 + lane] = (uint32_t)v;
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    int m = v;
+    for (int l = 0; l < emu_warp_lanes(); ++l) m = max(m, (int)emu::block->warp_buf[(size_t)warp * 32 + l]);
+    emu::arrive_and_wait(emu::block->warp[warp]);
+    threadIdx = emu_uint3{(unsigned)me, 0, 0};
+    return m;
+}
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int atomicMin(int* p, int v) {
@@ -223,10 +291,6 @@ inline float atomicAdd(float* p, float v) {
     return old;
 }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-inline int max(int a, int b) { return a > b ? a : b; }
-inline int min(int a, int b) { return a < b ? a : b; }
-inline long max(long a, long b) { return a > b ? a : b; }
-inline long min(long a, long b) { return a < b ? a : b; }
 
 template <typename... K, typename... A>
 inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(K...), A... args) {
