@@ -15,7 +15,7 @@ def build():
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    subprocess.check_call(['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-fno-extern-tls-init', '-x', 'c++', '-I', HERE] +
+    subprocess.check_call(['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-fno-extern-tls-init', '-Wno-psabi', '-x', 'c++', '-I', HERE] +
                           SRCS + ['-o', OUT])
     return OUT
 

@@ -140,3 +140,36 @@ def test_k2_source_last_layer_fused_with_the_three_max_pools_both_directions():
     dh = ops.pool3_bwd(dpooled, argmax_ref, csr, 0, H)
     dy_ref, _ = ops.aggregate_bwd(dh, None, csr, act=act_ref)
     assert torch.equal(dy, dy_ref)
+
+
+@pytest.mark.parametrize('k', (-1, 1))
+def test_k2_source_persistent_double_buffered_path_512_tokens(k, monkeypatch):
+    """Large sentence tiles (the shape the roofline number is quoted on): the 512-thread CTA walks the sentence's column
+    slices with two buffers, the next slice in flight while the current one is gathered.  GPT_AGG_SPLIT=1 gives one
+    CTA per sentence, as a full machine would (B >= 296)."""
+    monkeypatch.setenv('GPT_AGG_SPLIT', '1')
+    B, T, H = 2, 512, 96
+    batch = synth.make_batch(900 + k, batch_size=B, fixed_len=T)
+    csr = _csr_of(batch, k)
+    assert int((csr.err & ops.TREE_ERR_FATAL).sum()) == 0
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(B * T, H, generator=g)
+    bias = torch.randn(H, generator=g)
+    gout = torch.randn(B, T, H, generator=g)
+    rng = torch.tensor([77, 2], dtype=torch.int64)
+    out, act = ops.aggregate_fwd(y, csr, bias, want_act=True)
+    assert torch.equal(out, ops.aggregate_fwd(y, csr, bias, force_vec=1))          # one slice per CTA, no pipelining
+    adj = (csr.to_dense() != 0).double()
+    ys = y.view(B, T, H).double()
+    ref = torch.relu((adj.bmm(ys) + ys + 2 * bias.double()) / csr.denom.double().unsqueeze(2)) * \
+        (csr.flags != 0).unsqueeze(2)
+    assert _rel(out, ref) < 1e-5
+    dy, db = ops.aggregate_bwd(gout, None, csr, act=act)
+    dy_small, db_small = ops.aggregate_bwd(gout, out, csr, force_vec=1)
+    assert torch.equal(dy, dy_small) and _rel(db, db_small) < 1e-5
+    # what the training step launches at this shape: in-kernel dropout 0.5 (1 random bit per element) + activation mask
+    o1, act1 = ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng, subseq=0, want_act=True)
+    assert torch.equal(o1, ops.aggregate_fwd(y, csr, bias, drop_p=0.5, rng_state=rng, subseq=0, force_vec=1))
+    live = out > 0
+    assert abs((o1 > 0)[live].float().mean().item() - 0.5) < 0.02
+    assert torch.equal(o1[o1 > 0], out[o1 > 0] * 2.0)
