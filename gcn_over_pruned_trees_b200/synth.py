@@ -37,6 +37,8 @@ def random_tree(rng, length):
 
 def random_spans(rng, length):
     """Two disjoint spans of 1-3 tokens: (subj_start, subj_end, obj_start, obj_end), ends inclusive."""
+    if length < 5:          # both starts are drawn from [0, length - 3): below 5 tokens the spans can never be disjoint
+        raise ValueError('random_spans needs sentences of at least 5 tokens, got %d' % length)
     while True:
         ss = int(rng.integers(0, max(length - 3, 1)))
         se = min(ss + int(rng.integers(1, 4)) - 1, length - 1)
