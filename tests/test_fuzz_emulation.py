@@ -1,6 +1,7 @@
 """CPU: randomised shapes through K1 -> K2 (forward, backward from `out` and from the activation bits) -> K4 (max / avg /
 sum), all from source on the host (tests/emu), against the dense formulation: sentence widths 1..97 incl. the warp
-boundaries, hidden sizes 1..200 incl. unaligned ones, star trees (one row with T-1 neighbours), every slice width."""
+boundaries, hidden sizes 1..200 incl. unaligned ones, star trees (one row with T-1 neighbours), every slice width; and
+randomised configurations of the relation-aware model (K1, K5, K3, K10, K4 from source) against the oracle."""
 import ctypes
 import os
 import random
@@ -14,7 +15,10 @@ from gcn_over_pruned_trees_b200 import _lib, ops, synth
 from oracle import gcn_oracle
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
-NAMES = ('gpt_prune_csr', 'gpt_gcn_aggregate_fwd', 'gpt_gcn_aggregate_bwd', 'gpt_pool3_fwd', 'gpt_pool3_bwd')
+NAMES = ('gpt_prune_csr', 'gpt_gcn_aggregate_fwd', 'gpt_gcn_aggregate_bwd', 'gpt_pool3_fwd', 'gpt_pool3_bwd',
+         'gpt_embed_fwd', 'gpt_embed_bwd', 'gpt_linear_fwd_f32', 'gpt_linear_dgrad_f32', 'gpt_linear_wgrad_f32',
+         'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
+         'gpt_colsum_acc')
 
 
 @pytest.fixture(scope='module', autouse=True)
@@ -93,3 +97,44 @@ def test_random_shapes_k1_k2_k4_from_source_vs_dense(chunk):
             assert torch.equal(torch.isnan(got), torch.isnan(want)), (tag, kind)      # 0/0 of an empty avg pool
             ok = torch.isfinite(want)
             assert not ok.any() or _rel(got[ok], want[ok]) < 1e-5, (tag, kind)
+
+
+@pytest.mark.parametrize('chunk', range(2))
+def test_random_relation_aware_configurations_from_source_vs_oracle(chunk):
+    """hidden 1..33, 1..7 relation slots, 1..3 layers, every switch of the mode, all three poolings: loss and every
+    gradient of one train-mode step (dropout probabilities 0, nothing injected or replaced)."""
+    import weights
+    from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+    rnd = random.Random(2000 + chunk)
+    for trial in range(6):
+        H, D, L = rnd.choice([1, 2, 3, 4, 5, 8, 12, 33]), rnd.choice([1, 2, 3, 7]), rnd.choice([1, 2, 3])
+        mode = rnd.choice(['full_deprel', 'full_deprel', 'diagonal_deprel'])
+        over = dict(adj_type=mode, deprel_emb_dim=D, hidden_dim=H, num_layers=L, prune_k=rnd.choice([-1, 0, 1, 2]),
+                    vocab_size=60, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32',
+                    deprel_max_depth=rnd.choice([1, 2, 3]), deprel_directed=rnd.random() < 0.3,
+                    deprel_self_loop=rnd.random() < 0.8, pooling=rnd.choice(['max', 'avg', 'sum']),
+                    mlp_layers=rnd.choice([1, 2]))
+        if mode == 'full_deprel':                   # the shared Linear needs in_dim == hidden_dim (SURVEY.md 10-3)
+            over.update(emb_dim=H, pos_dim=0, ner_dim=0)
+        else:
+            over.update(emb_dim=rnd.choice([3, 8]), pos_dim=rnd.choice([0, 2]), ner_dim=rnd.choice([0, 3]))
+        opt = synth.tacred_opt(**over)
+        batch = synth.make_batch(10 * chunk + trial, batch_size=rnd.choice([1, 3]), vocab_size=60,
+                                 mean_len=rnd.choice([9, 20]))
+        state = {k: torch.from_numpy(v) for k, v in weights.make_state(opt, 100 + trial).items()}
+        trainer = GCNTrainer(dict(opt))
+        trainer.model.load_state_dict(state)
+        oracle = gcn_oracle.DenseClassifier(opt)
+        oracle.load_state_dict(state)
+        trainer.model.train()
+        oracle.train()
+        loss = trainer.update(batch)
+        loss.backward()
+        ref_loss, _ = oracle.loss(batch)
+        ref_loss.backward()
+        tag = dict(over, chunk=chunk, trial=trial)
+        assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item()), tag
+        got = dict(trainer.model.named_parameters())
+        for key, p in oracle.named_parameters():
+            if p.grad is not None:
+                assert got[key].grad is not None and _rel(got[key].grad, p.grad) <= 1e-4, (tag, key)
