@@ -17,7 +17,12 @@ clip at 5.0, SGD step.
           tensors + loss.item() D2H inside the timed region (wall clock around each step, L2 flushed between)
   roofline      K2 aggregation forward at the large synthetic shape (BASELINE.json configs[4]: 512-token trees,
                 B=4096, H=512 -- the only shape where an HBM fraction means anything), timed live
-  cpu_baseline  the oracle's dense CPU restatement of the reference path, timed on this box's host cores
+  cpu_baseline  the reference's own GCNTrainer (baseline/_ref, unmodified; kind "reference") timed on this box's host
+                cores; the oracle's dense restatement (kind "port") only when baseline/_ref is not installed
+  dp_check      (N > 1) lockstep correctness of the gradient exchange, run before the timed region: replicas
+                bit-identical, parameters equal to a single-process step on the concatenated batch
+  extra         BASELINE.json configs[4] (large512: 512-token trees, B=4096 per GPU, H=512; NCCL all-reduce when N > 1)
+                and configs[3] (semeval_b50: 9-tuple batches, 19 classes) as sub-records, at every N
 """
 import argparse
 import json
@@ -56,18 +61,29 @@ def parse_args():
     ap.add_argument('--no-loader', action='store_true', help='skip the K9 device-loader leg (short profiler passes)')
     ap.add_argument('--roofline-batch', type=int, default=4096)
     ap.add_argument('--cpu-steps', type=int, default=60)
+    ap.add_argument('--no-extra', action='store_true', help='skip the large512 / semeval_b50 legs')
+    ap.add_argument('--no-dp-check', action='store_true')
+    ap.add_argument('--large-batch', type=int, default=4096, help='sentences per GPU of the large512 leg')
+    ap.add_argument('--large-steps', type=int, default=5)
     return ap.parse_args()
 
 
 def workload_config(args, world):
+    """What is computed -- identical for the b200 arm and the reference arm (the driver compares the two dicts)."""
     return {'workload': 'tacred_b50_k%d' % args.prune_k, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world,
             'len': 'clip(Poisson(36),8,96)', 'layers': 2, 'in_dim': 360, 'hidden': 200, 'vocab': VOCAB,
-            'prune_k': args.prune_k, 'gemm': args.gemm, 'parallelism': 'dp%d' % world,
+            'prune_k': args.prune_k, 'parallelism': 'dp%d' % world,
             'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd',
+            'l2': 'GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable'}
+
+
+def engine_config(args, world):
+    """How the b200 arm computes it (not part of `config`: the reference arm has no such keys)."""
+    return {'gemm': args.gemm,
             'engine': 'eager' if args.eager else ('cuda_graph_autograd' if args.autograd_engine else
                                                   'cuda_graph_fused_step'),
             'exchange': 'none' if world == 1 else ('nccl_allreduce' if args.autograd_engine or args.eager else
-                                                   'nvlink_peer_memory_push_reduce (K8)'), 'l2': 'flushed between timed steps (256 MiB fill)'}
+                                                   'nvlink_peer_memory (K8)')}
 
 
 # ------------------------------------------------------------------------------------------------ clocks -------
@@ -119,33 +135,86 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------------------ reference ----
 
+REF_DIR = os.path.join(REPO, 'baseline', '_ref')
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, 'model', 'trainer.py'))
+
+
 def cpu_reference_run(args, steps, warmup):
-    """The oracle's dense CPU restatement of the reference training step, all host threads."""
+    """The reference's own training step on the host cores.  kind "reference": the UNMODIFIED reference from
+    baseline/_ref (tools/install_reference.py) -- its GCNTrainer, its head_to_tree / tree_to_adj, torch CPU kernels, the
+    five calls of train.py:213-227.  kind "port" (only when baseline/_ref is absent): the oracle's restatement."""
     import torch
     from gcn_over_pruned_trees_b200 import synth
-    from oracle import gcn_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
     opt = synth.tacred_opt(vocab_size=VOCAB, prune_k=args.prune_k, cuda=False)
-    model = gcn_oracle.DenseClassifier(opt)
-    model.train()
-    optim = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=opt['lr'])
     batches = [synth.make_batch(1000 + i, batch_size=BATCH, vocab_size=VOCAB) for i in range(min(N_BATCHES, 8))]
+    if reference_available():
+        import contextlib
+        import io
+        sys.path.insert(0, REF_DIR)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                from model import tree as ref_tree
+                from model.trainer import GCNTrainer as RefTrainer
+                if args.prune_k < 0:
+                    ref_tree.Tree.head = None       # the one attribute the reference forgets (SURVEY.md 10-1)
+                trainer = RefTrainer(dict(opt))
+        finally:
+            sys.path.remove(REF_DIR)
+        trainer.model.train()
+        kind = 'reference'
+
+        def step(b):
+            trainer.optimizer.zero_grad()
+            loss = trainer.update(b)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(trainer.model.parameters(), opt['max_grad_norm'])
+            trainer.optimizer.step()
+
+        def adjacency(b):                           # model/gcn.py:96-110, the host section of the reference's forward
+            import numpy as np
+            words, masks, deprel, head, subj_pos, obj_pos = (b[i].numpy() for i in (0, 1, 4, 5, 6, 7))
+            lens = (masks == 0).astype(np.int64).sum(1)
+            maxlen = int(max(lens))
+            trees = [ref_tree.head_to_tree(head[i], words[i], lens[i], opt['prune_k'], subj_pos[i], obj_pos[i], deprel[i])
+                     for i in range(len(lens))]
+            return np.concatenate([ref_tree.tree_to_adj(maxlen, t, directed=False, self_loop=True).reshape(1, maxlen, maxlen)
+                                   for t in trees], axis=0)
+    else:
+        from oracle import gcn_oracle
+        model = gcn_oracle.DenseClassifier(opt)
+        model.train()
+        optim = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=opt['lr'])
+        kind = 'port'
+
+        def step(b):
+            gcn_oracle.train_step(model, optim, b, opt['max_grad_norm'])
+
+        def adjacency(b):
+            return model.gcn_model.adjacency(list(b[:-2]))
     for i in range(warmup):
-        gcn_oracle.train_step(model, optim, batches[i % len(batches)], opt['max_grad_norm'])
+        step(batches[i % len(batches)])
     t0 = time.perf_counter()
     for i in range(steps):
-        gcn_oracle.train_step(model, optim, batches[i % len(batches)], opt['max_grad_norm'])
+        step(batches[i % len(batches)])
     dt = time.perf_counter() - t0
     # the host-side tree + dense adjacency section alone (gcn.py:105-107), single Python thread
     t1 = time.perf_counter()
     n_adj = max(1, min(steps, 10))
     for i in range(n_adj):
-        model.gcn_model.adjacency(list(batches[i % len(batches)][:-2]))
+        adjacency(batches[i % len(batches)])
     adj_ms = (time.perf_counter() - t1) / n_adj * 1e3
     return {'value': BATCH * steps / dt, 'ms_per_step': dt / steps * 1e3, 'cores': cores, 'tree_adj_ms': adj_ms,
-            'sample': '%d steps x %d sentences after %d warm-up, V=%d, train mode' % (steps, BATCH, warmup, VOCAB)}
+            'kind': kind,
+            'sample': '%d steps x %d sentences after %d warm-up, V=%d, train mode (dropout on), %s' % (
+                steps, BATCH, warmup, VOCAB,
+                'unmodified reference GCNTrainer from baseline/_ref, torch CPU' if kind == 'reference' else
+                'oracle port (baseline/_ref not installed)')}
 
 
 def run_reference(args):
@@ -156,9 +225,10 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args, 1), parallelism='cpu'),
-            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
-                             'sample': r['sample'], 'tree_adj_ms_per_batch': r['tree_adj_ms']},
+            'config': workload_config(args, max(args.gpus, 1)),
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'],
+                             'sample': r['sample'] + '; one host process regardless of --gpus',
+                             'tree_adj_ms_per_batch': r['tree_adj_ms']},
             'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -260,6 +330,180 @@ def load_peaks():
             'source': 'fallback (B200_PROFILING.md)'}
 
 
+def dp_lockstep_check(args, rank, world, dev, steps=5):
+    """Correctness of the data-parallel step at this world size, before anything is timed (reduced
+    gradients == single-process gradients on the concatenated batch).  Every rank steps on rows rank::world of the same
+    global batches through FusedTrainStep(data_parallel=True) -- the K8 exchange the timed region uses, same GEMM mode,
+    same vocabulary -- and rank 0 also steps a single-process replica on the full batches.  LOCKSTEP: before every step
+    all ranks load the single-process replica's parameters (free-running trajectories are not comparable at 1e-5: a
+    pre-activation that is zero to within rounding flips a ReLU).  Dropout is off here: the Philox
+    streams are keyed by the sentence's row in the batch, which sharding changes.  Steps 1-2 run eagerly, step 3 is
+    captured and replayed, steps 4-5 are replays: every launch mode of the timed engine is covered."""
+    import torch
+    import torch.distributed as dist
+    from gcn_over_pruned_trees_b200 import synth
+    from gcn_over_pruned_trees_b200.engine import FusedTrainStep
+    from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+    over = dict(vocab_size=VOCAB, prune_k=args.prune_k, cuda=True, input_dropout=0.0, gcn_dropout=0.0,
+                gemm_mode=args.gemm)
+    width = 96
+    batches = [synth.make_batch(300 + i, batch_size=BATCH * world, vocab_size=VOCAB, pad_to=width) for i in range(3)]
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, 'w')
+    torch.manual_seed(11)
+    tr = GCNTrainer(synth.tacred_opt(**over))
+    tr.model.train()
+    eng = FusedTrainStep(tr, data_parallel=True, max_rows=BATCH * 128)
+    ref = ref_eng = None
+    if rank == 0:
+        torch.manual_seed(11)
+        ref = GCNTrainer(synth.tacred_opt(**over))
+        ref.model.train()
+        ref_eng = FusedTrainStep(ref)
+    sys.stdout = _stdout
+    params = list(tr.model.parameters())
+    sizes = [p.numel() for p in params]
+    worst, loss_err, identical = 0.0, 0.0, True
+    for s in range(steps):
+        vec = torch.empty(sum(sizes), device=dev)
+        if rank == 0:
+            vec.copy_(torch.cat([p.detach().reshape(-1) for p in ref.model.parameters()]))
+        dist.broadcast(vec, 0)
+        for p, chunk in zip(params, vec.split(sizes)):
+            p.data.copy_(chunk.view_as(p))                    # in place: the step graphs keep their addresses
+        full = batches[s % 3]
+        shard = tuple(t[rank::world].contiguous() if torch.is_tensor(t) else t[rank::world] for t in full)
+        loss = eng(shard).clone()
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        lo, hi = flat.clone(), flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = identical and bool(torch.equal(lo, hi))   # bitwise: min == max over ranks for every element
+        dist.all_reduce(loss)
+        loss /= world
+        if rank == 0:
+            ref_loss = float(ref_eng(full))
+            for a, b in zip(params, ref.model.parameters()):
+                worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+            loss_err = max(loss_err, abs(float(loss) - ref_loss) / abs(ref_loss))
+    out = torch.tensor([worst, loss_err, 1.0 if identical else 0.0], dtype=torch.float64, device=dev)
+    dist.broadcast(out, 0)
+    worst, loss_err = float(out[0]), float(out[1])
+    ok = identical and worst < 2e-5 and loss_err < 2e-5
+    del eng, ref_eng, tr, ref
+    torch.cuda.empty_cache()
+    return {'world': world, 'steps': steps, 'mode': 'lockstep, dropout off, gemm %s, K8 peer-memory exchange' % args.gemm,
+            'replicas_bit_identical': identical, 'params_rel': worst, 'loss_rel': loss_err,
+            'tolerance': 2e-5, 'ok': ok}
+
+
+def semeval_leg(args, rank, world, dev, flush):
+    """BASELINE.json configs[3]: SemEval-shaped batches (9-tuples without NER, 19 classes, in_dim 330, lengths
+    clip(Poisson(19),5,97); train_semeval.py:195-222's step), 50 sentences per GPU, same engine as the headline."""
+    import torch
+    from gcn_over_pruned_trees_b200 import parallel, synth
+    from gcn_over_pruned_trees_b200.engine import FusedTrainStep, PackedBatch
+    from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+    torch.manual_seed(1234)
+    opt = synth.tacred_opt(vocab_size=VOCAB, prune_k=args.prune_k, cuda=True, gemm_mode=args.gemm, dataset='semeval',
+                           num_class=19)
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, 'w')
+    tr = GCNTrainer(opt)
+    sys.stdout = _stdout
+    tr.model.train()
+    eng = FusedTrainStep(tr, data_parallel=world > 1, max_rows=BATCH * 128)
+    nb = 8
+    host = [synth.make_batch(2000 + rank * nb + i, batch_size=BATCH, vocab_size=VOCAB, dataset='semeval', num_class=19,
+                             mean_len=19, min_len=5, max_len=97) for i in range(nb)]
+    res = [PackedBatch(b, device='cpu').to(dev) for b in host]
+    for _ in range(4):
+        for b in res:
+            eng(b)
+    torch.cuda.synchronize()
+    steps = min(args.steps, 50)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    parallel.barrier()
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(ev):
+        flush.fill_(0.0)
+        a.record()
+        loss = eng(res[i % nb])
+        b.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ms = parallel.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev) / steps
+    out = {'workload': 'semeval_b50_k%d_19cls' % args.prune_k, 'value': BATCH * world / ms * 1e3, 'unit': UNIT,
+           'n_gpus': world, 'ms_per_step': ms, 'steps': steps, 'batch_per_gpu': BATCH, 'in_dim': 330, 'num_class': 19,
+           'len': 'clip(Poisson(19),5,97)', 'loss': float(loss), 'launches_per_step': eng.launches_per_replay(res[0]),
+           'exchange': 'none' if world == 1 else 'nvlink_peer_memory (K8)', 'scaling': 'weak',
+           'projection': 'fp32 FFMA (K=330: row pitch 1320 B is not a multiple of 16 B, no TMA descriptor)'}
+    del eng, tr, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def large512_leg(args, rank, world, dev, peaks):
+    """BASELINE.json configs[4]: every sentence 512 tokens, B=4096 per GPU, 2-layer GCN, 360 -> H=512, k=-1, the whole
+    training step.  N > 1: one NCCL all-reduce of the flat gradient buffer (dense word-embedding gradient included:
+    2M tokens touch the whole vocabulary) -- the exchange north_star names; the step is tens of milliseconds, so it is
+    launched eagerly (~20 launches)."""
+    import torch
+    from gcn_over_pruned_trees_b200 import ops, parallel, synth
+    from gcn_over_pruned_trees_b200.engine import FusedTrainStep
+    from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer
+    B, T, H = args.large_batch, 512, 512
+    torch.manual_seed(1234)
+    opt = synth.tacred_opt(vocab_size=VOCAB, cuda=True, hidden_dim=H, prune_k=-1, gemm_mode=args.gemm)
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, 'w')
+    tr = GCNTrainer(opt)
+    sys.stdout = _stdout
+    tr.model.train()
+    eng = FusedTrainStep(tr, data_parallel='nccl' if world > 1 else False, capture=False)
+    batch = synth.make_batch_torch(5 + rank, B, T, device=dev)
+    inputs, labels = list(batch[:-2]), batch[-2]
+    torch.cuda.reset_peak_memory_stats()
+    with torch.no_grad():
+        for _ in range(3):
+            eng._run(inputs, labels)
+        torch.cuda.synchronize()
+        steps = args.large_steps
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        parallel.barrier()
+        torch.cuda.synchronize()
+        for a, b in ev:                         # one step streams ~35 GB: nothing of it survives in the 126 MB L2
+            a.record()
+            loss, _ = eng._run(inputs, labels)
+            b.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        times = [a.elapsed_time(b) for a, b in ev]
+        ms = parallel.max_over_ranks(sum(times), dev) / steps
+        kernels = None
+        if world == 1:                          # per-entry-point device time (separate instrumented pass)
+            ops.TIMER = ops.KernelTimer()
+            for _ in range(2):
+                eng._run(inputs, labels)
+            summary = ops.TIMER.summary()
+            ops.TIMER = None
+            kernels = {k: {'calls_per_step': c / 2, 'ms_per_call': t / c}
+                       for k, (c, t) in sorted(summary.items(), key=lambda kv: -kv[1][1])}
+    n_rows = B * T
+    flops = 3 * 2 * n_rows * (360 + H) * H           # fwd + dgrad + wgrad of both projections
+    out = {'workload': 'large512: B=%d per GPU x T=512 trees, 360 -> H=512, 2 layers, prune_k=-1, V=%d' % (B, VOCAB),
+           'value': B * world / ms * 1e3, 'unit': UNIT, 'n_gpus': world, 'ms_per_step': ms, 'steps': steps,
+           'step_ms_min': min(times), 'step_ms_max': max(times), 'loss': float(loss), 'scaling': 'weak',
+           'exchange': 'none' if world == 1 else 'nccl_allreduce (one flat fp32 buffer, dense embedding gradient included)',
+           'engine': 'fused step, eager launches', 'gemm': args.gemm,
+           'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9,
+           'projection_tflops_algorithmic': flops / (ms * 1e-3) / 1e12, 'kernels': kernels}
+    del eng, tr, batch, inputs, labels
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch
     from gcn_over_pruned_trees_b200 import _lib, ops, parallel, synth
@@ -279,6 +523,9 @@ def run_b200(args):
     model = trainer.model
     model.train()
     reducer = parallel.GradAllReducer(model.parameters())
+    dp_check = None
+    if world > 1 and not args.no_dp_check and not args.autograd_engine and not args.eager:
+        dp_check = dp_lockstep_check(args, rank, world, dev)
     host = [synth.make_batch(1000 + rank * N_BATCHES + i, batch_size=BATCH, vocab_size=VOCAB) for i in range(N_BATCHES)]
     host = [tuple(t.pin_memory() if torch.is_tensor(t) else t for t in b) for b in host]
     resident = [tuple(t.to(dev) if torch.is_tensor(t) else t for t in b) for b in host]
@@ -334,8 +581,11 @@ def run_b200(args):
     parallel.barrier()
     wall = time.perf_counter() - wall0
     launches += _lib.lib().gpt_launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in events)
+    step_times = sorted(a.elapsed_time(b) for a, b in events)
+    dev_ms = sum(step_times)
     dev_ms = parallel.max_over_ranks(dev_ms, dev)
+    step_ms = {'min': step_times[0], 'median': statistics.median(step_times), 'max': step_times[-1],
+               'of': 'rank 0, CUDA events around each timed step'}
     clocks = sampler.stop() if sampler else None
     ms_per_step = dev_ms / args.steps
     value = BATCH * world * args.steps / (dev_ms * 1e-3)
@@ -370,10 +620,28 @@ def run_b200(args):
                                'ms_per_step': t_s / min(args.steps, 50) * 1e3,
                                'api': 'train_step(pinned 10-tuple as the reference loader emits it: 9 H2D copies)'}
     if world == 1:
-        n_eager = min(args.steps, 30)
+        # the reference's own five-call loop (train.py:213-227) on the new `model` package, nothing else changed:
+        # update() / backward() / optimizer.step() replay captured graphs (engine.FastUpdate), clip_grad_norm_ is torch's
+        n_eager = min(args.steps, 50)
+        host = host_tuples
+        trainer.fast_update = True
+        for _ in range(4):                          # every batch shape: 2 eager steps, capture, one replay
+            for bt in host_tuples:
+                eager_step(bt)
         eager_s = timed_host_loop(eager_step, n_eager)
+        fast = getattr(trainer, '_fast', None)
         e2e['dropin_eager'] = {'value': BATCH * world * n_eager / eager_s, 'ms_per_step': eager_s / n_eager * 1e3,
-                               'api': 'reference call sequence train.py:213-227 on the new model package, eager'}
+                               'api': 'reference call sequence train.py:213-227 (zero_grad, update, backward, '
+                                      'clip_grad_norm_, optimizer.step) on the new model package, pinned host 10-tuples, '
+                                      'loss.item() every step',
+                               'path': 'engine.FastUpdate: 3 CUDA-graph replays per step' if fast is not None
+                                       else 'per-op autograd', 'graph_replays': fast.replays if fast else 0}
+        trainer.fast_update = False                 # the same five calls on the per-op autograd Functions
+        n_auto = min(args.steps, 20)
+        auto_s = timed_host_loop(eager_step, n_auto)
+        trainer.fast_update = True
+        e2e['dropin_autograd'] = {'value': BATCH * world * n_auto / auto_s, 'ms_per_step': auto_s / n_auto * 1e3,
+                                  'api': 'same five calls with GPT_FAST_UPDATE=0: ~115 eager launches per step'}
     # ---- K9: batches assembled on the device from a resident token arena ----------------------
     loader_info = None
     if fused and not args.eager and not args.no_loader:
@@ -423,6 +691,18 @@ def run_b200(args):
                            'algorithmic_bytes_per_batch': int(tokens * 28 + 57 * BATCH * width + 12 * BATCH),
                            'bound': 'launch latency (0.2 MB per batch)'}
 
+    # ---- BASELINE.json configs[3] and configs[4] at this N (sub-records; the headline workload is unchanged) ---------
+    extra = None
+    if fused and not args.eager and not args.no_extra:
+        extra = {}
+        for name, fn in (('semeval_b50', lambda: semeval_leg(args, rank, world, dev, flush)),
+                         ('large512', lambda: large512_leg(args, rank, world, dev, load_peaks()))):
+            try:
+                extra[name] = fn()
+            except Exception as exc:            # keep the headline line; the failure is in the record
+                extra[name] = {'error': repr(exc)}
+                if world > 1:
+                    raise
     if world > 1:
         parallel.barrier()
         torch.distributed.destroy_process_group()
@@ -463,7 +743,7 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(args, args.cpu_steps, 3)
-        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample'],
                'ms_per_step': r['ms_per_step'], 'tree_adj_ms_per_batch': r['tree_adj_ms']}
 
     if loader_info is not None and not args.no_cpu_baseline and world == 1:
@@ -479,9 +759,10 @@ def run_b200(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
+            'engine': engine_config(args, world), 'step_ms': step_ms, 'dp_check': dp_check,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'gpu_launches_per_step': launches / args.steps, 'wall_ms_per_step_incl_flush': wall / args.steps * 1e3,
-            'roofline': roof, 'cpu_baseline': cpu, 'loader': loader_info, 'kernels': kernels}
+            'roofline': roof, 'cpu_baseline': cpu, 'extra': extra, 'loader': loader_info, 'kernels': kernels}
     print(json.dumps(line))
 
 

@@ -761,13 +761,7 @@ AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
 
 template <typename K>
 int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, const CUtensorMap& tm, cudaStream_t st) {
-    static std::unordered_map<const void*, size_t> configured;  // opt in to large dynamic smem once per kernel
-    size_t& have = configured[reinterpret_cast<const void*>(kernel)];
-    if (c.smem > 48 * 1024 && c.smem > have) {
-        cudaError_t a = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-        if (a != cudaSuccess) return (int)a;
-        have = c.smem;
-    }
+    if (int a = gpt_smem_opt_in(kernel, c.smem)) return a;    // large dynamic smem, once per (device, kernel)
     gpt_launch(kernel, dim3(c.grid_x, p.B), dim3(c.nt), c.smem, st, p, tm);
     return gpt_launch_status();
 }

@@ -350,13 +350,7 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
     stages = stages > nkb ? nkb : stages;
     stages = stages < 1 ? 1 : stages;
     const size_t smem = (size_t)stages * stage + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t a = cudaFuncSetAttribute(tf32_gemm_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (a != cudaSuccess) return (int)a;
-        configured = smem;
-    }
+    if (int a = gpt_smem_opt_in(tf32_gemm_kernel<PASSES>, smem)) return a;
     dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles));
     gpt_launch(tf32_gemm_kernel<PASSES>, grid, dim3(kGemmThreads), smem, st, tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
                                                                tmem_cols, stages, ep);

@@ -2,6 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifndef GPT_HOST_EMULATION
+#include <map>
+#include <mutex>
+#include <utility>
+#endif
 
 #define GPT_FULL_MASK 0xffffffffu
 
@@ -65,6 +70,28 @@ static inline cudaError_t gpt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.attrs = attr;
     cfg.numAttrs = g_gpt_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Opt `kernel` in to `smem` bytes of dynamic shared memory.  The attribute belongs to the (device, kernel) pair, so it
+// is remembered per device: a second GPU driven from the same process gets its own call.
+template <typename K>
+static inline int gpt_smem_opt_in(K kernel, size_t smem) {
+    if (smem <= 48 * 1024) return GPT_OK;
+#ifndef GPT_HOST_EMULATION
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> have;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& h = have[std::make_pair(dev, reinterpret_cast<const void*>(kernel))];
+    if (smem > h) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        h = smem;
+    }
+#endif
+    return GPT_OK;
 }
 
 // call once after every <<<>>> launch

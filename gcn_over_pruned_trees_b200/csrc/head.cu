@@ -434,15 +434,9 @@ extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, cons
     if (smem > 200 * 1024) return GPT_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
-    static size_t configured[3] = {0, 0, 0};
-    const int slot = R == 1 ? 0 : (R == 2 ? 1 : 2);
-    if (smem > configured[slot]) {
-        if (R == 1) e = cudaFuncSetAttribute(head_fwd_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else if (R == 2) e = cudaFuncSetAttribute(head_fwd_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else e = cudaFuncSetAttribute(head_fwd_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[slot] = smem;
-    }
+    if (int a = R == 1 ? gpt_smem_opt_in(head_fwd_bwd_kernel<1>, smem)
+                       : (R == 2 ? gpt_smem_opt_in(head_fwd_bwd_kernel<2>, smem) : gpt_smem_opt_in(head_fwd_bwd_kernel<4>, smem)))
+        return a;
     const int groups = (B + R - 1) / R;
     // CTAs per sentence group: a pair of CTAs halves the number of dependent round trips to L2 per layer as long as
     // every CTA has an SM to itself (123 registers x 512 threads = one CTA per SM); wider clusters lose more to the

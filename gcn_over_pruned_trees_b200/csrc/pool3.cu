@@ -181,13 +181,7 @@ extern "C" int gpt_pool3_fwd(const float* h, const uint8_t* flags, int B, int T,
     const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     const size_t smem = pool_fwd_smem(T, H, vec ? 4 : 1);
     if (smem > 200 * 1024) return GPT_ERR_UNSUPPORTED;
-    static size_t configured[2] = {48 * 1024, 48 * 1024};
-    if (smem > configured[vec]) {
-        cudaError_t e = vec ? cudaFuncSetAttribute(pool3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(pool3_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[vec] = smem;
-    }
+    if (int e = vec ? gpt_smem_opt_in(pool3_fwd_kernel<4>, smem) : gpt_smem_opt_in(pool3_fwd_kernel<1>, smem)) return e;
     if (vec) gpt_launch(pool3_fwd_kernel<4>, dim3(B), dim3(kPoolFwdThreads), smem, (cudaStream_t)stream, h, flags, T, H, pool_type, out, argmax);
     else gpt_launch(pool3_fwd_kernel<1>, dim3(B), dim3(kPoolFwdThreads), smem, (cudaStream_t)stream, h, flags, T, H, pool_type, out, argmax);
     return gpt_launch_status();

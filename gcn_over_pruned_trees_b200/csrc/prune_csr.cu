@@ -269,12 +269,7 @@ extern "C" int gpt_prune_csr(const int64_t* head, const int64_t* subj_pos, const
     if (B == 0) return GPT_OK;
     const size_t smem = (size_t)kWarpsPerCta * 6 * (T + 1) * sizeof(int);
     if (smem > 200 * 1024) return GPT_ERR_UNSUPPORTED;  // T <= 2132 per sentence
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t a = cudaFuncSetAttribute(prune_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (a != cudaSuccess) return (int)a;
-        configured = smem;
-    }
+    if (int a = gpt_smem_opt_in(prune_csr_kernel, smem)) return a;
     const int grid = (B + kWarpsPerCta - 1) / kWarpsPerCta;
 #ifdef GPT_HOST_EMULATION   // tests/emu: g++ has no <<<>>>
     gpt_launch(prune_csr_kernel, dim3(grid), dim3(kWarpsPerCta * 32), smem, (cudaStream_t)stream,

@@ -246,12 +246,7 @@ extern "C" int gpt_linear_wgrad_tf32x3(const float* dy, const float* x, const ui
     int rc = tc::make_map_f32(&tm_dy, dy, M, N, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != GPT_OK) return rc;
     if ((rc = tc::make_map_f32(&tm_x, x, M, K, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GPT_OK) return rc;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t a = cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (a != cudaSuccess) return (int)a;
-        configured = smem;
-    }
+    if (int a = gpt_smem_opt_in(wgrad_tf32x3_kernel, smem)) return a;
     wgrad_tf32x3_kernel<<<(unsigned)(n_slices * m_parts), WG_THREADS, smem, (cudaStream_t)stream>>>(
         tm_dy, tm_x, flags, dw, M, N, K, n_slices, rows_per_part, kboxes, tmem_cols, stages);
     return gpt_launch_status();

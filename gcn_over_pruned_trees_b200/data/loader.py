@@ -25,8 +25,14 @@ import random
 import numpy as np
 import torch
 
-from .. import _lib, constant, ops
-from ..engine import PackedBatch
+try:                                    # imported as gcn_over_pruned_trees_b200.data.loader
+    from .. import _lib, constant, ops
+    from ..engine import PackedBatch
+except ImportError:                     # imported as top-level `data.loader` (package dir on PYTHONPATH: train.py:21)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from gcn_over_pruned_trees_b200 import _lib, constant, ops
+    from gcn_over_pruned_trees_b200.engine import PackedBatch
 
 SEMEVAL_LABELS = ['Other', 'Entity-Destination', 'Cause-Effect', 'Member-Collection', 'Entity-Origin',
                   'Message-Topic', 'Component-Whole', 'Instrument-Agency', 'Product-Producer', 'Content-Container']
@@ -74,8 +80,11 @@ def sorted_rows(lens):
 class DataLoader(object):
     """Load data from a json file, keep it on the GPU, emit the reference's batches."""
 
-    def __init__(self, filename, batch_size, opt, vocab, evaluation=False, dataset=None, device=None,
-                 host_word_dropout=False, seed=None, _processed=None):
+    def __init__(self, filename, batch_size, opt, vocab, evaluation=False, bert_embeddings=None, dataset=None,
+                 device=None, host_word_dropout=False, seed=None, _processed=None):
+        if bert_embeddings is not None:         # train.py:79-84 passes the keyword (None unless --use_bert_embeddings)
+            raise NotImplementedError('pre-computed BERT token vectors (data/loader.py:90-104) are outside the built '
+                                      'path (SURVEY.md section 2: out of scope); use the reference loader for them')
         self.batch_size = batch_size
         self.opt = opt
         self.vocab = vocab

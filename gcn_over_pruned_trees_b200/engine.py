@@ -53,19 +53,30 @@ class GraphedTrainStep(object):
             not g.get('maximize', False) for g in opt.param_groups)
         if not (plain_sgd and emb.requires_grad and emb.is_cuda and self.reducer is None):
             return None
-        state = ops.SparseEmbeddingState(emb.data, self.opt['topn'])
-        gcn.sparse_embedding = state
+        # the routing is scoped to this engine's own forward + backward (_fwd_bwd): the reference-compatible sequence
+        # (update / backward / clip / step) on the same trainer keeps receiving a dense emb.weight.grad
         self.emb_weight = emb
-        return state
+        return ops.SparseEmbeddingState(emb.data, self.opt['topn'])
+
+    @staticmethod
+    def capturable(optimizer):
+        """False when optimizer.step() cannot be recorded into a CUDA graph (torch raises mid-capture for Adam /
+        Adamax / Adadelta built with capturable=False, e.g. an optimizer the caller constructed)."""
+        return not any(g.get('capturable', True) is False for g in optimizer.param_groups)
 
     # -- the step itself, used both for eager warm-up and under capture --------------------------------------------
     def _fwd_bwd(self, inputs, labels):
         # grads are re-created by every backward (no zero-fill kernels, no accumulate-adds); under capture they live
         # in the graph's private pool at fixed addresses
         self.trainer.optimizer.zero_grad(set_to_none=True)
-        logits, pooling_output = self.model(inputs)
-        loss = self.trainer._loss(logits, pooling_output, labels)
-        loss.backward()
+        gcn = self.model.gcn_model.gcn
+        gcn.sparse_embedding = self.sparse          # row-sparse word-embedding gradient for this step only
+        try:
+            logits, pooling_output = self.model(inputs)
+            loss = self.trainer._loss(logits, pooling_output, labels)
+            loss.backward()
+        finally:
+            gcn.sparse_embedding = None
         return loss.detach()
 
     def _update(self):
@@ -131,7 +142,9 @@ class GraphedTrainStep(object):
             inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]
             seen = self._seen.get(key, 0)
             self._seen[key] = seen + 1
-            if seen < self.warmup:      # the first steps of a new shape run eagerly (allocates .grad, warms caches)
+            # the first steps of a new shape run eagerly (allocates .grad, warms caches); so does every step when the
+            # optimizer's step() cannot be captured
+            if seen < self.warmup or not self.capturable(self.trainer.optimizer):
                 return self._eager(inputs, labels)
             entry = self._capture(key, inputs, labels)
         else:                           # host (pinned) or device source, straight into the static buffers
@@ -228,6 +241,11 @@ class FlatParameters(object):
     def g(self, p):
         return self.grad_views[id(p)]
 
+    def view_of(self, flat, p):
+        """The slice of another flat buffer of the same layout that corresponds to parameter ``p``."""
+        off = self.offsets[[id(q) for q in self.params].index(id(p))]
+        return flat[off:off + p.numel()].view_as(p)
+
 
 class FusedTrainStep(object):
     """The whole optimisation step as ~22 launches of this library, no ATen kernels, captured once per batch shape.
@@ -239,7 +257,12 @@ class FusedTrainStep(object):
     configuration can run here; everything else stays on GraphedTrainStep (autograd under capture).
     """
 
-    def __init__(self, trainer, max_grad_norm=None, warmup=2, data_parallel=False, max_rows=8192):
+    def __init__(self, trainer, max_grad_norm=None, warmup=2, data_parallel=False, max_rows=8192, capture=True):
+        """data_parallel: False | True / 'peer' (K8: gradients meet in NVLink peer memory inside the step's kernels, the
+        word-embedding gradient travels as live rows -- the exchange for microsecond-scale steps) | 'nccl' (one NCCL
+        all-reduce of ONE flat gradient buffer that also holds the dense [V, E] word-embedding gradient, then K7 on the
+        mean -- the exchange for large batches, where most of the vocabulary is live and a step takes milliseconds).
+        capture=False launches every step eagerly (large shapes: ~20 launches against tens of milliseconds)."""
         from . import ops
         why = self.unsupported_reason(trainer)
         if why:
@@ -252,8 +275,15 @@ class FusedTrainStep(object):
         self.tacred = self.opt['dataset'] == 'tacred'
         self.use_pos = self.opt['pos_dim'] > 0
         self.use_ner = self.opt['ner_dim'] > 0 and self.tacred
+        self.exchange_kind = {False: None, None: None, True: 'peer', 'peer': 'peer', 'nccl': 'nccl'}[data_parallel]
+        self.capture = capture
+        self.dense_emb = self.exchange_kind == 'nccl' and gm.emb.weight.requires_grad
         dense = []
         for name, p in self.model.named_parameters():
+            if p is gm.emb.weight and self.dense_emb:
+                if not any(q is p for _, q in dense):       # registered under two names (gcn.py:45-57,138): once
+                    dense.append((name, p))
+                continue
             if p is gm.emb.weight or p is gm.deprel_emb.weight or not p.requires_grad:
                 continue
             if gm.ner_emb is not None and p is gm.ner_emb.weight and not self.use_ner:
@@ -261,15 +291,26 @@ class FusedTrainStep(object):
             if gm.pos_emb is not None and p is gm.pos_emb.weight and not self.use_pos:
                 continue
             dense.append((name, p))
-        self.flat = FlatParameters(dense)
+        # the flat parameter / gradient buffers and the row-sparse embedding state belong to the trainer: every engine
+        # built on it (train_step's, the fast update path's, a data-parallel one) shares them
+        shared = getattr(trainer, '_fused_state', None)
         emb = gm.emb.weight
+        if shared is None:
+            shared = {'dense_emb': self.dense_emb, 'flat': FlatParameters(dense),
+                      'sparse': ops.SparseEmbeddingState(emb.data, self.opt['topn'])
+                      if (emb.requires_grad and not self.dense_emb) else None}
+            trainer._fused_state = shared
+            self.gcn.rng_state[1] += 1      # the autograd path advances the stream before its first forward
+        elif shared['dense_emb'] != self.dense_emb:
+            raise ValueError('FusedTrainStep: this trainer already has an engine with a different gradient layout '
+                             "(data_parallel='nccl' keeps the word-embedding gradient in the flat buffer)")
+        self.flat = shared['flat']
         self.emb_weight = emb
-        self.sparse = ops.SparseEmbeddingState(emb.data, self.opt['topn']) if emb.requires_grad else None
+        self.sparse = shared['sparse']
         self.mlp = [m for m in gm.out_mlp if isinstance(m, torch.nn.Linear)]
         self.cls = self.model.classifier
         self.partials = torch.zeros(1024, dtype=torch.float32, device=emb.device)
         self.total_norm = torch.zeros((), dtype=torch.float32, device=emb.device)
-        self.gcn.rng_state[1] += 1          # the autograd path advances the stream before its first forward
         self._graphs, self._seen = {}, {}
         self._lr = self.trainer.optimizer.param_groups[0]['lr']
         self.kernels_per_replay = {}
@@ -280,7 +321,11 @@ class FusedTrainStep(object):
         self.capture_stream = torch.cuda.Stream(priority=-1) if os.environ.get('GPT_PRIO', '1') != '0' else None
         self.exchange = None
         self.max_rows = max_rows
-        if data_parallel:                   # collective: every rank constructs its engine at the same point
+        self.world = 1
+        if self.exchange_kind == 'nccl':
+            import torch.distributed as dist
+            self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if self.exchange_kind == 'peer':    # collective: every rank constructs its engine at the same point
             from .parallel import PeerExchange
             self.exchange = PeerExchange(max_rows, emb.shape[1], emb.shape[0], self.flat.grad.numel())
             self.partials = torch.zeros(max(1024, self.exchange.n_partials), dtype=torch.float32, device=emb.device)
@@ -309,9 +354,29 @@ class FusedTrainStep(object):
         return None
 
     # -- the step: the order of calls is the program -----------------------------------------------------------------
-    def _run(self, inputs, labels, update=True):
+    class _Step(object):
+        """What the forward leaves for the backward (all device tensors; kept alive until the step is over)."""
+        pass
+
+    def _fork(self, stream):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        stream.wait_event(ev)
+
+    def _join(self, stream):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        torch.cuda.current_stream().wait_event(ev)
+
+    def _forward(self, inputs, labels, join_side=False, rng=None):
+        """K1 || weight-prep || K5 -> L x (K3, K2) -> K4 -> K6 (head forward + loss rows + the head's data gradients).
+        Independent work runs on two side streams (forked / joined with events, so the same code is what the CUDA graph
+        captures as parallel branches).  Buffers touched by a side stream are allocated here, on the main stream, and
+        kept alive in the returned state.  join_side: also join the L2 prefetch branch before returning (a forward that
+        is captured on its own); otherwise the caller joins it at the end of the step."""
         from . import ops
         opt, gcn, fl = self.opt, self.gcn, self.flat
+        st = self._Step()
         if self.tacred:
             words, masks, pos, ner, deprel, head, subj_pos, obj_pos = inputs
         else:
@@ -320,39 +385,22 @@ class FusedTrainStep(object):
         gm = self.model.gcn_model
         B, T = words.shape
         H = opt['hidden_dim']
-        rng = gcn.rng_state
+        st.rng = rng = gcn.rng_state if rng is None else rng     # {seed, step} of this step's dropout streams
         mode = gcn.gemm_mode
-        use_adj = not opt.get('no_adj', False)
-        ptype = ops.POOL_TYPES[opt['pooling']]
+        st.use_adj = use_adj = not opt.get('no_adj', False)
+        st.ptype = ptype = ops.POOL_TYPES[opt['pooling']]
         p_in, p_gcn = opt['input_dropout'], opt['gcn_dropout']
-        pos_w = gm.pos_emb.weight if self.use_pos else None
-        ner_w = gm.ner_emb.weight if self.use_ner else None
-        # Independent work runs on two side streams (forked / joined with events, so the same code is what the CUDA
-        # graph captures as parallel branches): K1 and the weight preparation beside the embedding stage, every weight
-        # gradient beside the data-gradient chain.  Buffers touched by a side stream are allocated here, on the main
-        # stream, and kept alive in `keep` until the final join.
+        st.pos_w = pos_w = gm.pos_emb.weight if self.use_pos else None
+        st.ner_w = ner_w = gm.ner_emb.weight if self.use_ner else None
+        st.words, st.pos, st.ner, st.B, st.T, st.H = words, pos, ner, B, T, H
         main = torch.cuda.current_stream()
         sa, sb = self.side
-        keep = []
-
-        def fork(stream):
-            ev = torch.cuda.Event()
-            ev.record(main)
-            stream.wait_event(ev)
-
-        def join(stream):
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            main.wait_event(ev)
-
         n_layers = len(gcn.W)
-        fuse_pool = ptype == ops.POOL_TYPES['max'] and ops.aggregate_pool_ok(B, T, H)
-        csr = ops.TreeCSR(B, T, words.device)
-        wss = [ops.weight_prep_buffer(lin.weight.data, mode) for lin in gcn.W]
-        keep += [csr, wss]
-        # forward
-        fork(sa)
-        fork(sb)
+        st.fuse_pool = fuse_pool = ptype == ops.POOL_TYPES['max'] and ops.aggregate_pool_ok(B, T, H)
+        st.csr = csr = ops.TreeCSR(B, T, words.device)
+        st.wss = wss = [ops.weight_prep_buffer(lin.weight.data, mode) for lin in gcn.W]
+        self._fork(sa)
+        self._fork(sb)
         with torch.cuda.stream(sa):
             ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'], out=csr)
         with torch.cuda.stream(sb):
@@ -363,12 +411,13 @@ class FusedTrainStep(object):
         x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
                           None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
         main.wait_event(ev_prep)                 # (the prefetch behind it is joined at the end of the step)
-        xs, acts = [], []
+        st.xs, st.acts = xs, acts = [], []
         h = x
+        pooled = argmax = None
         for l, lin in enumerate(gcn.W):
             y = ops.linear_fwd(h.view(B * T, -1), lin.weight.data, mode, wss[l])
             if l == 0:
-                join(sa)
+                self._join(sa)
             xs.append(h)
             if l == n_layers - 1 and fuse_pool:     # last layer: K2 + K4 in one launch, h itself is never stored
                 pooled, argmax, act, _ = ops.aggregate_fwd_pool(y, csr, lin.bias.data, use_adj)
@@ -379,22 +428,49 @@ class FusedTrainStep(object):
             acts.append(act)
         if not fuse_pool:
             pooled, argmax = ops.pool3_fwd(h, csr, ptype)
-        buf = ops.HeadBuffers(B, H, self.cls.weight.shape[0], len(self.mlp), words.device)
+        st.pooled, st.argmax = pooled, argmax
+        st.buf = buf = ops.HeadBuffers(B, H, self.cls.weight.shape[0], len(self.mlp), words.device)
         ops.head_fwd_bwd(pooled, labels, [m.weight.data for m in self.mlp], [m.bias.data for m in self.mlp],
                          self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=True)
-        # backward
-        keep += [pooled, buf, xs]
-        fork(sa)
-        with torch.cuda.stream(sa):
-            ops.head_wgrad(pooled, buf, [fl.g(m.weight) for m in self.mlp], [fl.g(m.bias) for m in self.mlp],
-                           fl.g(self.cls.weight), fl.g(self.cls.bias))
+        if join_side:
+            self._join(sb)
+        return st
+
+    def _head_wgrad(self, st, into=None):
+        """K6's weight gradients (overwritten, not accumulated) + the scalar loss; ``into``: a flat scratch buffer laid
+        out like the flat gradient buffer instead of the gradient buffer itself."""
+        from . import ops
+        fl = self.flat
+        g = fl.g if into is None else (lambda p: fl.view_of(into, p))
+        ops.head_wgrad(st.pooled, st.buf, [g(m.weight) for m in self.mlp], [g(m.bias) for m in self.mlp],
+                       g(self.cls.weight), g(self.cls.bias))
+
+    def _backward(self, st, head_wgrad=True):
+        """[K6-wgrad || K4-bwd -> L x (K2-bwd -> [K3-wgrad || K3-dgrad])] -> K5-bwd, every gradient ADDED into the flat
+        gradient buffer / the live word-embedding rows (the head's weight gradients are overwritten unless the caller
+        has taken them elsewhere with head_wgrad=False)."""
+        from . import ops
+        opt, gcn, fl = self.opt, self.gcn, self.flat
+        csr, buf, acts, xs, wss = st.csr, st.buf, st.acts, st.xs, st.wss
+        B, T, H = st.B, st.T, st.H
+        words, pos, ner, pos_w, ner_w = st.words, st.pos, st.ner, st.pos_w, st.ner_w
+        rng, mode = st.rng, gcn.gemm_mode
+        p_in, p_gcn = opt['input_dropout'], opt['gcn_dropout']
+        use_adj, ptype, fuse_pool = st.use_adj, st.ptype, st.fuse_pool
+        sa, sb = self.side
+        n_layers = len(gcn.W)
+        keep = []
+        if head_wgrad:
+            self._fork(sa)
+            with torch.cuda.stream(sa):
+                self._head_wgrad(st)
         # K2's backward prologue (g = d * dropscale * [out > 0] / denom) is fused into whatever produces d: K4's backward
         # for the last layer, the dgrad GEMM's epilogue below it; ('dh', .) marks a gradient that still needs it
-        cur = ('pool', None) if fuse_pool else ('g', ops.pool3_bwd_masked(buf.dpooled, argmax, csr, ptype, H, acts[-1], 0.0))
+        cur = ('pool', None) if fuse_pool else ('g', ops.pool3_bwd_masked(buf.dpooled, st.argmax, csr, ptype, H, acts[-1], 0.0))
         for l in range(n_layers - 1, -1, -1):
             lin = gcn.W[l]
             if cur[0] == 'pool':                # K4's backward inside K2's: the [B,T,H] gradient never exists
-                dy = ops.aggregate_bwd_pool(buf.dpooled, argmax, acts[-1], csr, H, use_adj, dbias_out=fl.g(lin.bias))
+                dy = ops.aggregate_bwd_pool(buf.dpooled, st.argmax, acts[-1], csr, H, use_adj, dbias_out=fl.g(lin.bias))
             elif cur[0] == 'g':
                 dy = ops.aggregate_bwd_pre(cur[1], csr, use_adj, dbias_out=fl.g(lin.bias))
             else:
@@ -402,7 +478,7 @@ class FusedTrainStep(object):
                                           act=acts[l], dbias_out=fl.g(lin.bias))
             keep.append(dy)
             side = sb if (n_layers - 1 - l) % 2 == 0 else sa
-            fork(side)
+            self._fork(side)
             with torch.cuda.stream(side):
                 ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True,
                                  flags=csr.flags)
@@ -418,29 +494,51 @@ class FusedTrainStep(object):
         sp = self.sparse
         if sp is not None:
             sp.words = words
+        g_emb = sp.G if sp is not None else (fl.g(self.emb_weight) if self.dense_emb else None)
+        topn = sp.topn if sp is not None else int(min(max(opt['topn'], 0), self.emb_weight.shape[0]))
         ops.embed_bwd(dh, csr.flags, words, pos if self.use_pos else None, ner if self.use_ner else None,
-                      sp.G if sp is not None else None, fl.g(pos_w) if pos_w is not None else None,
+                      g_emb, fl.g(pos_w) if pos_w is not None else None,
                       fl.g(ner_w) if ner_w is not None else None, sp.owner if sp is not None else None,
-                      self.emb_weight.shape[0], self.emb_weight.shape[1], sp.topn if sp is not None else 0, p_in, rng,
-                      0xE0)
-        join(sa)
-        join(sb)
-        del keep
-        self.last_csr = csr
+                      self.emb_weight.shape[0], self.emb_weight.shape[1], topn, p_in, rng, 0xE0)
+        self._join(sa)
+        self._join(sb)
+        st.keep = keep
+
+    def _apply(self, clip=True, advance=True):
+        """K7 (one GPU), K8 (peer-memory exchange) or NCCL all-reduce + K7: clip + SGD; leaves every gradient buffer
+        zeroed and advances the dropout step counter.  clip=False: the caller has already clipped (the reference's own
+        clip_grad_norm_ call, train.py:225)."""
+        from . import ops
+        fl, sp, rng = self.flat, self.sparse, self.gcn.rng_state
         lr = self.trainer.optimizer.param_groups[0]['lr']
-        if not update:
-            pass
+        max_norm = self.max_grad_norm if clip else 0.0
+        counter = rng[1:] if advance else None
+        if self.exchange_kind == 'nccl':                      # one all-reduce (sum) of the flat buffer, K7 on the mean
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(fl.grad)
+            ops.update_sqnorm(fl.grad, None, self.partials)
+            ops.update_apply(fl.param, fl.grad, None, None, self.partials, max_norm, lr, 1.0 / self.world,
+                             self.total_norm, counter)
         elif self.exchange is None:                           # K7
-            ops.update_sqnorm(fl.grad, sp, self.partials)
-            ops.update_apply(fl.param, fl.grad, sp, self.emb_weight.data, self.partials, self.max_grad_norm, lr, 1.0,
-                             self.total_norm, rng[1:])
+            if clip:
+                ops.update_sqnorm(fl.grad, sp, self.partials)
+            ops.update_apply(fl.param, fl.grad, sp, self.emb_weight.data, self.partials, max_norm, lr, 1.0,
+                             self.total_norm if clip else None, counter)
         else:                                                 # K8: exchange over peer memory + K7 on the mean
             ex = self.exchange
             ops.dp_push(ex.ptrs, ex.rank, ex.shape, fl.grad, sp)
             ops.dp_reduce(ex.ptrs, ex.rank, ex.shape, fl.grad, self.partials)
             ops.dp_apply(ex.ptrs[ex.rank], ex.shape, fl.param, fl.grad, self.emb_weight.data, self.partials,
-                         self.max_grad_norm, lr, self.total_norm, rng[1:])
-        return buf.loss, buf.logits
+                         self.max_grad_norm, lr, self.total_norm, counter)
+
+    def _run(self, inputs, labels, update=True):
+        st = self._forward(inputs, labels)
+        self._backward(st)
+        self.last_csr = st.csr
+        if update:
+            self._apply()
+        return st.buf.loss, st.buf.logits
 
     def _capture(self, key, inputs, labels):
         from . import _lib
@@ -472,7 +570,8 @@ class FusedTrainStep(object):
             inputs, labels = unpack_batch(batch, True)[:2]
             seen = self._seen.get(key, 0)
             self._seen[key] = seen + 1
-            if seen < self.warmup:      # first steps of a new shape run eagerly (lazy module loading, smem attributes)
+            # first steps of a new shape run eagerly (lazy module loading, smem attributes)
+            if seen < self.warmup or not self.capture:
                 return self._run(inputs, labels)[0]
             entry = self._capture(key, inputs, labels)
         elif packed is not None:        # one copy: pinned host -> device, or device -> device
@@ -518,3 +617,247 @@ class FusedTrainStep(object):
             batch = batch.as_tuple()
         key = (tuple(batch[0].shape), len(batch) - 2)
         return self.kernels_per_replay.get(key, 0)
+
+
+# ---- the reference's own five-call loop (train.py:213-227), unchanged, on captured graphs ---------------------------
+
+class _PublishedLoss(torch.autograd.Function):
+    """The scalar ``GCNTrainer.update`` returns on the fast path: ``loss.backward()`` (train.py:221, the caller's) replays
+    the step's captured backward, which ADDS this step's gradients -- scaled by the incoming gradient -- into the
+    parameters' ``.grad`` buffers, exactly what autograd's accumulation would have done."""
+
+    @staticmethod
+    def forward(ctx, anchor, fast, entry, generation):
+        ctx.fast, ctx.entry, ctx.generation = fast, entry, generation
+        return entry['loss'].detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.fast._backward(ctx.entry, ctx.generation, grad_out)
+        return None, None, None, None
+
+
+class FastSGD(torch.optim.SGD):
+    """``trainer.optimizer`` on the fast path: same class, same param_groups (update_lr / lr decay keep working), but
+    ``step()`` is one replay of K7's apply over the flat parameter buffer + the live word-embedding rows (which also
+    leaves every gradient buffer zeroed), and ``zero_grad()`` after it is free.  Anything the fast path did not produce
+    (gradients accumulated over several batches, a backward that went through autograd) takes torch's own SGD step over
+    the same buffers."""
+
+    def bind(self, fast):
+        self._fast = fast
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        fast = getattr(self, '_fast', None)
+        if closure is not None or fast is None or not fast.step():
+            out = super().step(closure)
+            if fast is not None:
+                fast.dirty = True
+            return out
+        return None
+
+    def zero_grad(self, set_to_none=True):
+        fast = getattr(self, '_fast', None)
+        if fast is None:
+            return super().zero_grad(set_to_none)
+        fast.zero_grad(set_to_none)
+
+
+class FastUpdate(object):
+    """``update()`` / ``loss.backward()`` / ``clip_grad_norm_`` / ``optimizer.step()`` / ``optimizer.zero_grad()`` as the
+    reference's loop issues them (train.py:213-227), with the forward and the backward of FusedTrainStep captured as two
+    CUDA graphs per batch shape and the SGD update as a third: the caller's five calls cost three replays + the
+    caller's own clip instead of ~115 eager launches.  Same arithmetic, same accumulation semantics:
+
+      * update(batch) touches no gradient; it returns a loss with a grad_fn
+      * loss.backward() adds grad_output x (this step's gradients) into ``p.grad`` -- views into ONE flat buffer for
+        the dense parameters, a dense [V, E] buffer that is zero outside the batch's word rows for emb.weight
+      * clip_grad_norm_(model.parameters(), c) sees and scales exactly those tensors
+      * optimizer.step() applies p -= lr * g (FastSGD), optimizer.zero_grad() clears
+
+    One step's activations are kept per batch shape: backward() of a loss whose shape slot has been overwritten by a
+    newer update() raises instead of using the wrong activations.  GPT_FAST_UPDATE=0 disables the path."""
+
+    def __init__(self, trainer, warmup=2):
+        self.trainer = trainer
+        self.engine = FusedTrainStep(trainer, warmup=warmup)
+        eng = self.engine
+        dev = eng.emb_weight.device
+        self.warmup = warmup
+        self.anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)
+        self.gscale = torch.ones((), dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros_like(eng.flat.grad)            # the head's weight gradients of the newest forward
+        head = list(eng.mlp) + [eng.cls]
+        offs = [eng.flat.offsets[[id(q) for q in eng.flat.params].index(id(p))] for m in head for p in (m.weight, m.bias)]
+        ends = [o + p.numel() for o, (m, p) in zip(offs, [(m, p) for m in head for p in (m.weight, m.bias)])]
+        self.head_lo, self.head_hi = min(offs), max(ends)
+        self.entries, self.seen = {}, {}
+        self.generation = 0
+        self.dirty = False                  # gradient buffers hold something K7 has not cleared
+        self.fast_backwards = 0             # fast backwards since the last step / zero_grad
+        self.mixed = False                  # an autograd backward accumulated into the shared buffers
+        self.last_entry = None
+        self.apply_graphs = {}
+        self.capture_stream = eng.capture_stream
+        self.replays = 0
+        # swap the optimizer for the same class with a graph-replay step(); param_groups (lr!) carry over
+        old = trainer.optimizer
+        new = FastSGD(old.param_groups[0]['params'], lr=old.param_groups[0]['lr'])
+        new.bind(self)
+        trainer.optimizer = new
+        if eng.sparse is not None:
+            eng.emb_weight.register_post_accumulate_grad_hook(self._autograd_touched)
+        for p in eng.flat.params:
+            p.register_post_accumulate_grad_hook(self._autograd_touched)
+
+    def _autograd_touched(self, _p):
+        self.mixed = True
+        self.dirty = True
+
+    @staticmethod
+    def unsupported_reason(trainer):
+        if os.environ.get('GPT_FAST_UPDATE', '1') == '0':
+            return 'GPT_FAST_UPDATE=0'
+        if not isinstance(trainer.optimizer, (FastSGD, torch.optim.SGD)):
+            return 'optimizer is not plain SGD'
+        return FusedTrainStep.unsupported_reason(trainer)
+
+    # -- the two halves; the same code runs eagerly (first steps of a shape) and under capture ---------------------------
+    def _fwd(self, entry):
+        eng = self.engine
+        rng = eng.gcn.rng_state
+        rng[1] += 1                          # new dropout streams for every training forward, as the autograd path
+        entry['rng'].copy_(rng)              # ... frozen for this step's backward
+        st = eng._forward(entry['inputs'], entry['labels'], join_side=True, rng=entry['rng'])
+        eng._head_wgrad(st, into=self.scratch)      # K6's weight gradients (scale 1) + the scalar loss
+        entry['st'], entry['loss'] = st, st.buf.loss
+        eng.last_csr = st.csr
+
+    def _bwd(self, entry):
+        eng = self.engine
+        st = entry['st']
+        lo, hi = self.head_lo, self.head_hi
+        eng.flat.grad[lo:hi].addcmul_(self.scratch[lo:hi], self.gscale)
+        st.buf.dpooled.mul_(self.gscale)
+        eng._backward(st, head_wgrad=False)
+
+    def _graph(self, fn, entry, pool=None):
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=self.capture_stream, pool=pool):
+            fn(entry)
+        return g
+
+    @torch.no_grad()
+    def update(self, batch):
+        fields, labels = batch[:-2], batch[-2]
+        key = (tuple(fields[0].shape), len(fields))
+        entry = self.entries.get(key)
+        if entry is None:
+            dev = self.engine.emb_weight.device
+            proto = tuple(t.to(dev) for t in fields) + (labels.to(dev), None)
+            static = PackedBatch(batch=proto, device=dev)
+            entry = {'packed': static, 'inputs': static.fields, 'labels': static.labels, 'seen': 0, 'gen': -1,
+                     'rng': torch.zeros(2, dtype=torch.int64, device=dev), 'g_fwd': None, 'g_bwd': None}
+            self.entries[key] = entry
+        else:
+            for s_, t in zip(entry['inputs'], fields):
+                s_.copy_(t, non_blocking=True)
+            entry['labels'].copy_(labels, non_blocking=True)
+        self.generation += 1
+        entry['gen'] = self.generation
+        entry['seen'] += 1
+        if entry['g_fwd'] is not None:
+            entry['g_fwd'].replay()
+            self.replays += 1
+        elif entry['seen'] <= self.warmup:
+            self._fwd(entry)
+        else:                                # both halves are captured here, on the caller's thread
+            entry['g_fwd'] = self._graph(self._fwd, entry)
+            entry['g_fwd'].replay()
+            entry['g_bwd'] = self._graph(self._bwd, entry, pool=entry['g_fwd'].pool())
+        with torch.enable_grad():
+            return _PublishedLoss.apply(self.anchor, self, entry, entry['gen'])
+
+    @torch.no_grad()
+    def _backward(self, entry, generation, grad_out):
+        if entry['gen'] != generation:
+            raise RuntimeError('backward() of a loss whose activations have been overwritten: the fast update path keeps '
+                               'one step per batch shape (call backward() before the next update() of the same shape, '
+                               'or set GPT_FAST_UPDATE=0)')
+        entry['gen'] = -1                    # a second backward() of the same loss is refused the same way
+        self.gscale.copy_(grad_out.reshape(()))
+        if entry['g_bwd'] is not None:
+            entry['g_bwd'].replay()
+            self.replays += 1
+        else:
+            self._bwd(entry)
+        self.dirty = True
+        self.fast_backwards += 1
+        self.last_entry = entry
+        self.publish()
+
+    def publish(self):
+        """Point every parameter's .grad at its slice of the shared buffers (a no-op after the first time unless the
+        caller has set them to None)."""
+        eng = self.engine
+        for p in eng.flat.params:
+            g = eng.flat.g(p)
+            if p.grad is not g:
+                p.grad = g
+        if eng.sparse is not None and eng.emb_weight.grad is not eng.sparse.G:
+            eng.emb_weight.grad = eng.sparse.G
+
+    def _published(self):
+        eng = self.engine
+        return all(p.grad is eng.flat.g(p) for p in eng.flat.params) and (
+            eng.sparse is None or eng.emb_weight.grad is eng.sparse.G)
+
+    def step(self):
+        """optimizer.step(): True when K7 did it; False sends FastSGD to torch's own step over the same buffers."""
+        if self.fast_backwards != 1 or self.mixed or not self._published():
+            return False                     # accumulated / foreign gradients: the live-row list of ONE batch is not enough
+        eng = self.engine
+        entry = self.last_entry
+        lr = self.trainer.optimizer.param_groups[0]['lr']
+        key = (id(entry), lr)
+        g = self.apply_graphs.get(key)
+        if g is None:
+            if eng.sparse is not None:
+                eng.sparse.words = entry['inputs'][0]     # the live rows are this batch's words
+            if entry['g_bwd'] is None:       # still warming up: eager
+                eng._apply(clip=False, advance=False)
+            else:
+                g = self.apply_graphs[key] = self._graph(lambda e: eng._apply(clip=False, advance=False), entry,
+                                                         pool=entry['g_fwd'].pool())
+                g.replay()
+        else:
+            g.replay()
+            self.replays += 1
+        self.dirty = False                   # K7 zeroed what it applied and reset the owner marks
+        self.fast_backwards = 0
+        return True
+
+    def zero_grad(self, set_to_none=True):
+        eng = self.engine
+        if self.dirty:
+            eng.flat.grad.zero_()
+            if eng.sparse is not None:
+                eng.sparse.G.zero_()
+                eng.sparse.owner.fill_(0x7fffffff)
+            self.dirty = False
+        self.fast_backwards = 0
+        self.mixed = False
+        for p in self.trainer.optimizer.param_groups[0]['params']:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None and p.grad.data_ptr() not in self._own_ptrs():
+                p.grad.zero_()
+
+    def _own_ptrs(self):
+        eng = self.engine
+        ptrs = {eng.flat.g(p).data_ptr() for p in eng.flat.params}
+        if eng.sparse is not None:
+            ptrs.add(eng.sparse.G.data_ptr())
+        return ptrs

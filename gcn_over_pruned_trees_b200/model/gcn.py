@@ -213,12 +213,13 @@ class GCN(nn.Module):
         out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=rnn_inputs.size(1))
         return out
 
-    def _relation_layers(self, x, csr, deprel, drop_p):
+    def _relation_layers(self, x, csr, deprel, drop_p, rng=None):
         """The layer loop of the relation-aware modes (gcn.py:272-386 + 390-393).  `no_adj` has no effect here, as in the
         reference (these branches re-derive their masks from `adj`, gcn.py:276,308)."""
         opt = self.opt
         emb = self.deprel_emb.weight
         injected = self.injected_masks
+        rng = self.rng_state if rng is None else rng      # the forward's frozen {seed, step} (see forward())
         full = self.adj_type == 'full_deprel'
         if full:
             D, H = opt['deprel_emb_dim'], self.mem_dim
@@ -233,7 +234,7 @@ class GCN(nn.Module):
             last = l == self.layers - 1
             mask = None if injected is None else injected.get('gcn%d' % l)
             cfg = ops.RelationLayerConfig(l, drop_p=0.0 if (last or mask is not None) else drop_p,
-                                          drop_mask=None if last else mask, rng_state=self.rng_state,
+                                          drop_mask=None if last else mask, rng_state=rng,
                                           gemm_mode=self.gemm_mode)
             if not full:
                 x = ops.relation_layer_diag(x, emb, csr, deprel, cfg)
@@ -249,7 +250,7 @@ class GCN(nn.Module):
                 cfg.keep_tokens = tuple(injected['forget_%s%d' % (d, l)].reshape(-1).to(torch.uint8).contiguous()
                                         for d in 'fr')
             elif self.training and opt.get('deprel_keep_prop', 1.0) < 1.0:
-                cfg.keep_tokens = ops.relation_keep_tokens(self.rng_state, B * T, l, opt['deprel_keep_prop'])
+                cfg.keep_tokens = ops.relation_keep_tokens(rng, B * T, l, opt['deprel_keep_prop'])
             x = ops.relation_layer_full(x, wmat, self.W.bias, emb, csr, deprel, cfg, ws)
         return x
 
@@ -262,8 +263,13 @@ class GCN(nn.Module):
             words, masks, pos, deprel, head, subj_pos, obj_pos = inputs
             ner = None
         use_ner = self.opt['ner_dim'] > 0 and self.opt['dataset'] == 'tacred'
+        rng = self.rng_state
         if self.training and self.injected_masks is None:
             self.rng_state[1] += 1         # new dropout streams every training forward (graph-capture safe)
+            # this forward's {seed, step}, frozen: the backward kernels re-derive the Philox masks from it, and another
+            # training forward may advance the live buffer before this one's backward runs (two losses summed before
+            # one backward, activation checkpointing, ...).  A device-side copy: capture-safe.
+            rng = self.rng_state.clone()
         if words.dim() > 2 or self.injected_masks is not None:
             # pre-computed token vectors (BERT path of the loader) or injected test masks: plain lookups
             embs = [words if words.dim() > 2 else self.emb(words)]
@@ -277,20 +283,20 @@ class GCN(nn.Module):
             x = ops.embed_concat(words, pos, ner if use_ner else None, self.emb.weight,
                                  self.pos_emb.weight if self.opt['pos_dim'] > 0 else None,
                                  self.ner_emb.weight if use_ner else None,
-                                 drop_p=self.opt['input_dropout'] if self.training else 0.0, rng_state=self.rng_state,
+                                 drop_p=self.opt['input_dropout'] if self.training else 0.0, rng_state=rng,
                                  subseq=0xE0, flags=None if self.opt.get('rnn', False) else adj.flags,
                                  topn=self.opt['topn'], sparse=self.sparse_embedding)
         if self.opt.get('rnn', False):
             x = self._host_dropout(self.encode_with_rnn(x, masks, words.size(0)), self.rnn_drop, 'rnn')
         drop_p = self.opt['gcn_dropout'] if self.training else 0.0
         if self.adj_type != 'regular':
-            return self._relation_layers(x, adj, deprel, drop_p), adj.pool_mask()
+            return self._relation_layers(x, adj, deprel, drop_p, rng), adj.pool_mask()
         use_adj = not self.opt.get('no_adj', False)
         for l, lin in enumerate(self.W):
             last = l == self.layers - 1
             mask = None if self.injected_masks is None else self.injected_masks.get('gcn%d' % l)
             p = 0.0 if (last or mask is not None) else drop_p
-            x = ops.gcn_layer(x, lin.weight, lin.bias, adj, use_adj=use_adj, drop_p=p, rng_state=self.rng_state,
+            x = ops.gcn_layer(x, lin.weight, lin.bias, adj, use_adj=use_adj, drop_p=p, rng_state=rng,
                               subseq=l, drop_mask=None if last else mask, gemm_mode=self.gemm_mode)
         return x, adj.pool_mask()
 

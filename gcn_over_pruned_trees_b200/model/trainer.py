@@ -5,6 +5,8 @@
 ``{'model': state_dict, 'config': opt}``, ``.update_lr``, ``.get_deprel_emb``; attributes ``model, criterion,
 parameters, optimizer, opt``.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -73,7 +75,12 @@ class GCNTrainer(Trainer):
         if opt['cuda']:
             self.model.cuda()
             self.criterion.cuda()
-        self.optimizer = torch_utils.get_optimizer(opt['optim'], self.parameters, opt['lr'])
+        self.optimizer = torch_utils.get_optimizer(opt['optim'], self.parameters, opt['lr'],
+                                                    capturable=bool(opt['cuda']))
+        # update() / loss.backward() / optimizer.step() on captured graphs where the configuration allows it
+        # (engine.FastUpdate); False, or GPT_FAST_UPDATE=0, keeps every call on the per-op autograd path
+        self.fast_update = os.environ.get('GPT_FAST_UPDATE', '1') != '0'
+        self._fast = None
 
     def _loss(self, logits, pooling_output, labels):
         loss = self.criterion(logits, labels)
@@ -84,9 +91,32 @@ class GCNTrainer(Trainer):
         return loss
 
     def update(self, batch):
+        fast = self._fast_path()
+        if fast is not None:
+            return fast.update(batch)
         inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]
         logits, pooling_output = self.model(inputs)
         return self._loss(logits, pooling_output, labels)
+
+    def _fast_path(self):
+        """engine.FastUpdate when this call can take it: a training-mode forward with autograd on, on a configuration
+        FusedTrainStep covers (regular GCN, plain SGD, CUDA); None otherwise."""
+        if not (self.fast_update and self.opt['cuda'] and self.model.training and torch.is_grad_enabled()):
+            return None
+        if self.model.gcn_model.gcn.injected_masks is not None:
+            return None
+        if self._fast is None:
+            try:
+                from ..engine import FastUpdate
+            except ImportError:
+                from gcn_over_pruned_trees_b200.engine import FastUpdate
+            if FastUpdate.unsupported_reason(self) is not None:
+                self.fast_update = False
+                return None
+            self._fast = FastUpdate(self)
+        elif self._fast.trainer.optimizer is not self.optimizer:
+            return None                     # the caller installed an optimizer of its own
+        return self._fast
 
     def predict(self, batch, unsort=True):
         inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]

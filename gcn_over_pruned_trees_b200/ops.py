@@ -61,6 +61,11 @@ def _dev(t, dtype, name):
         raise _lib.GptError('%s must be a CUDA tensor: the gpt_b200 path has no CPU fallback' % name)
     if t.dtype != dtype:
         raise _lib.GptError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's current stream (_stream()): a tensor of another GPU would be touched
+        # from the wrong device.  Callers select the model's device (torch.cuda.set_device / torch.cuda.device).
+        raise _lib.GptError('%s lives on %s but the current CUDA device is %d' % (name, t.device,
+                                                                                 torch.cuda.current_device()))
     return t if t.is_contiguous() else t.contiguous()
 
 
@@ -98,9 +103,12 @@ class TreeCSR(object):
         """bool [B,T,1], True where the token is not in the pruned tree (the reference's `mask`, gcn.py:262)."""
         return (self.flags & 1).eq(0).unsqueeze(2)
 
-    def check(self):
-        """Raise on sentences the reference cannot process (synchronises; call outside the hot loop)."""
-        bad = (self.err & TREE_ERR_FATAL).nonzero().flatten().tolist()
+    def check(self, symmetric=False):
+        """Raise on sentences the reference cannot process (synchronises; call outside the hot loop).  With
+        ``symmetric`` also on a kept edge whose deprel id is 0: the forward still matches the reference's (asymmetric)
+        matrix, but the backward kernels walk the CSR as its own transpose and would be wrong for that sentence --
+        call it with symmetric=True on training data (the loader never emits id 0, data/loader.py:158-160)."""
+        bad = (self.err & (TREE_ERR_FATAL | (64 if symmetric else 0))).nonzero().flatten().tolist()
         if bad:
             code = int(self.err[bad[0]])
             why = ', '.join(n for bit, n in TREE_ERR_NAMES.items() if code & bit)

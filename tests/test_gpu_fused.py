@@ -146,19 +146,22 @@ def test_k7_grad_scale_is_the_data_parallel_mean():
 # ---------------------------------------------------------------- engine ----------------------------------------------
 
 def _autograd_grads(tr, batch):
+    tr.fast_update = False                  # the per-op autograd Functions, not engine.FastUpdate
     tr.optimizer.zero_grad()
     loss = tr.update(batch)
     loss.backward()
     return loss.detach(), {n: p.grad.detach().clone() for n, p in tr.model.named_parameters() if p.grad is not None}
 
 
+@pytest.mark.parametrize('gemm_mode', ('fp32', 'tf32x3'))
 @pytest.mark.parametrize('over', [dict(), dict(dataset='semeval', num_class=19, ner_dim=0),
                                   dict(dataset='semeval', num_class=10), dict(pooling='avg'),
                                   dict(mlp_layers=1, num_layers=3), dict(prune_k=-1, hidden_dim=64),
                                   dict(topn=300), dict(no_adj=True)])
-def test_fused_step_gradients_match_autograd_path(over):
-    """Same weights, dropout off: FusedTrainStep's hand-ordered backward == autograd over the per-op Functions."""
-    cfg = dict(vocab_size=900, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32')
+def test_fused_step_gradients_match_autograd_path(over, gemm_mode):
+    """Same weights, dropout off: FusedTrainStep's hand-ordered backward == autograd over the per-op Functions, in the
+    FFMA mode and in the 3xTF32 tensor-core mode bench.py runs."""
+    cfg = dict(vocab_size=900, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode=gemm_mode)
     cfg.update(over)
     opt = synth.tacred_opt(**cfg)
     torch.manual_seed(3)
@@ -196,14 +199,17 @@ def test_fused_step_with_dropout_uses_the_same_streams_as_the_autograd_path():
         assert _rel(got[name], g) <= 1e-4, name
 
 
-def test_fused_steps_match_reference_call_sequence():
-    """N fused (graph-replayed) steps == N x [zero_grad, update, backward, clip_grad_norm_, SGD.step] (train.py:213-227)."""
-    over = dict(vocab_size=700, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32')
+@pytest.mark.parametrize('gemm_mode', ('fp32', 'tf32x3'))
+def test_fused_steps_match_reference_call_sequence(gemm_mode):
+    """N fused (graph-replayed) steps == N x [zero_grad, update, backward, clip_grad_norm_, SGD.step] (train.py:213-227),
+    the latter on the per-op autograd path; also in the 3xTF32 mode bench.py runs."""
+    over = dict(vocab_size=700, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode=gemm_mode)
     batches = [synth.make_batch(50 + i, batch_size=50, vocab_size=700, pad_to=64) for i in range(3)]
 
     def run(fused):
         torch.manual_seed(5)
         tr = GCNTrainer(synth.tacred_opt(**over))
+        tr.fast_update = False
         tr.model.train()
         losses = []
         for step in range(9):

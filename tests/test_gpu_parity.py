@@ -372,10 +372,13 @@ def test_model_train_grads_match_oracle_with_injected_masks(golden_adj, name, ge
     assert checked >= 8
 
 
-def test_train_loop_step_runs_and_lowers_loss():
+@pytest.mark.parametrize('fast', (True, False))
+def test_train_loop_step_runs_and_lowers_loss(fast):
+    """train.py:213-227 with dropout on; fast=True: update / backward / step replay captured graphs (engine.FastUpdate)."""
     opt = synth.tacred_opt(vocab_size=500, cuda=True)
     torch.manual_seed(0)
     trainer = GCNTrainer(opt)
+    trainer.fast_update = fast
     batch = synth.make_batch(7, batch_size=50, vocab_size=500)
     trainer.model.train()
     losses = []
@@ -416,6 +419,7 @@ def test_graphed_train_step_matches_eager_steps():
     def run(graphed):
         torch.manual_seed(5)
         tr = GCNTrainer(synth.tacred_opt(**over))
+        tr.fast_update = False              # the eager side of this comparison is the per-op autograd path
         tr.model.train()
         losses = []
         for step in range(9):
