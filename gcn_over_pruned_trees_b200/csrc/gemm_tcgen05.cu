@@ -27,6 +27,7 @@
 // waits on.
 #include "gpt_common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -340,6 +341,8 @@ __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restric
     }
 }
 
+#include "gemm_persist.cuh"   // the large-M path: persistent CTA-pair kernel (uses the helpers above)
+
 template <int PASSES>
 int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
                 int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st, const MaskEpilogue& ep) {
@@ -365,6 +368,10 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
     if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
         (reinterpret_cast<uintptr_t>(b_lo) & 15))
         return GPT_ERR_UNSUPPORTED;
+    {   // large M: persistent CTA-pair kernel with double-buffered accumulators and a TMA-store epilogue
+        const int rc = persist::run(A, B, b_lo, C, M, N, K, st, ep);
+        if (rc != GPT_ERR_UNSUPPORTED) return rc;
+    }
     // N tile: as wide as possible (A is re-read once per N tile) unless that leaves most SMs idle; a narrower tile
     // also makes the stages smaller, i.e. the ring deeper, which is what hides TMA latency when M is small
     const int m_tiles = (M + BM - 1) / BM;
@@ -458,6 +465,12 @@ int transpose(const float* w, float* wt, int N, int K, cudaStream_t st) {
 }
 
 }  // namespace
+
+extern "C" int gpt_gemm_persist_config(int cta_group, long long min_rows) {
+    GPT_CHECK_ARG(cta_group >= 0 && cta_group <= 2 && min_rows >= 0);
+    persist::config() = persist::Config{cta_group, min_rows};
+    return GPT_OK;
+}
 
 extern "C" int gpt_linear_fwd_tf32(const float* x, const float* w, float* y, int M, int N, int K, void* stream) {
     GPT_CHECK_ARG(x && w && y && M >= 0 && N >= 1 && K >= 1);

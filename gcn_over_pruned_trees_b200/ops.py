@@ -143,6 +143,12 @@ def _tf32_ok(*dims):
     return all(d % 4 == 0 for d in dims)
 
 
+def gemm_persist_config(cta_group=2, min_rows=65536):
+    """Which projections take the persistent large-M kernel (csrc/gemm_persist.cuh): cta_group 0 = never, 1 = single-CTA
+    tiles, 2 = CTA pairs; from min_rows rows up.  Process-wide."""
+    _lib.check(_lib.lib().gpt_gemm_persist_config(int(cta_group), int(min_rows)), 'gpt_gemm_persist_config')
+
+
 def weight_prep_buffer(weight, mode):
     N, K = weight.shape
     if mode != 'tf32x3' or not _tf32_ok(N, K):

@@ -161,6 +161,10 @@ int gpt_weight_prep_tf32x3_batch(const float* const* w, float* const* ws, const 
                                  void* stream);
 int gpt_linear_fwd_tf32x3(const float* x, const float* ws, float* y, int M, int N, int K, void* stream);
 int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* dx, int M, int N, int K, void* stream);
+/*     Large M (>= min_rows, default 65 536; BASELINE.json configs[4]) runs the persistent kernel of csrc/gemm_persist.cuh
+ *     behind the same four entry points: CTA pairs (tcgen05.mma.cta_group::2, M = 256), two accumulators in tensor
+ *     memory, TMA-store epilogue.  cta_group: 0 = never, 1 = single-CTA tiles, 2 = pairs (default); process-wide. */
+int gpt_gemm_persist_config(int cta_group, long long min_rows);
 /* dgrad with the previous layer's K2-backward prologue in the epilogue: g = (dy . w) * drop_scale_prev *
  * [out_prev > 0] / denom, act_prev in K2's bit layout over the K columns of dx, rows = B*T sentences of T tokens */
 int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, const uint32_t* act_prev,

@@ -1,0 +1,81 @@
+"""GPU tests of the persistent CTA-pair projection kernel (csrc/gemm_persist.cuh) behind gpt_linear_{fwd,dgrad}_tf32[x3]:
+against float64 matmuls and, bit for bit, against the one-tile-per-CTA kernel it replaces at large M (same products, same
+accumulation order along K: the two kernels must agree exactly).
+
+Tolerances: 3xTF32 <= 1e-5 relative of the largest element (fp32-grade), TF32 <= 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gcn_over_pruned_trees_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+@pytest.fixture(autouse=True)
+def _restore():
+    yield
+    ops.gemm_persist_config(2, 65536)
+
+
+@pytest.mark.parametrize('cg', (1, 2))
+@pytest.mark.parametrize('M,N,K', [(70000, 512, 360), (65536, 512, 512), (66000, 200, 360), (65537, 512, 200),
+                                   (131072 + 77, 64, 36), (70000, 320, 128)])
+def test_persistent_gemm_matches_float64_and_the_small_kernel(M, N, K, cg):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / np.sqrt(K)
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    ref = x.double() @ w.double().t()
+    dref = dy.double() @ w.double()
+    ws = ops.weight_prep(w, 'tf32x3')
+    ops.gemm_persist_config(0, 65536)
+    small = {m: (ops.linear_fwd(x, w, m, ws if m == 'tf32x3' else None),
+                 ops.linear_dgrad(dy, w, m, ws if m == 'tf32x3' else None)) for m in ('tf32', 'tf32x3')}
+    ops.gemm_persist_config(cg, 65536)
+    for mode, tol in (('tf32x3', 1e-5), ('tf32', 2e-3)):
+        y = ops.linear_fwd(x, w, mode, ws if mode == 'tf32x3' else None)
+        dx = ops.linear_dgrad(dy, w, mode, ws if mode == 'tf32x3' else None)
+        torch.cuda.synchronize()
+        assert _rel(y, ref) <= tol, (mode, 'fwd')
+        assert _rel(dx, dref) <= tol, (mode, 'dgrad')
+        assert torch.equal(y, small[mode][0]), (mode, 'fwd vs small kernel')
+        assert torch.equal(dx, small[mode][1]), (mode, 'dgrad vs small kernel')
+
+
+@pytest.mark.parametrize('cg', (1, 2))
+def test_persistent_dgrad_with_k2_prologue_epilogue(cg):
+    """linear_dgrad_masked (K2's backward prologue in the GEMM epilogue) through the persistent kernel == the small one."""
+    B, T, H, N2 = 160, 512, 512, 512
+    batch = synth.make_batch_torch(3, B, T, device=DEV)
+    csr = ops.prune_csr(batch[5], batch[6], batch[7], batch[4], batch[1], -1)
+    y = torch.randn(B * T, H, device=DEV)
+    rng = torch.tensor([5, 9], dtype=torch.int64, device=DEV)
+    _, act = ops.aggregate_fwd(y, csr, torch.zeros(H, device=DEV), drop_p=0.5, rng_state=rng, subseq=0, want_act=True)
+    w = torch.randn(N2, H, device=DEV) / np.sqrt(H)
+    ws = ops.weight_prep(w, 'tf32x3')
+    dnext = torch.randn(B * T, N2, device=DEV)
+    ops.gemm_persist_config(0, 65536)
+    ref = ops.linear_dgrad_masked(dnext, w, ws, act, csr, 0.5)
+    ops.gemm_persist_config(cg, 65536)
+    got = ops.linear_dgrad_masked(dnext, w, ws, act, csr, 0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert float(got.abs().max()) > 0
+
+
+def test_small_batches_keep_the_one_tile_per_cta_kernel():
+    """Below min_rows nothing changes: the TACRED-shape step does not take the persistent kernel."""
+    x = torch.randn(4800, 360, device=DEV)
+    w = torch.randn(200, 360, device=DEV)
+    ops.gemm_persist_config(0, 65536)
+    a = ops.linear_fwd(x, w, 'tf32x3')
+    ops.gemm_persist_config(2, 65536)
+    b = ops.linear_fwd(x, w, 'tf32x3')
+    assert torch.equal(a, b)
