@@ -66,21 +66,10 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {     // acquire at cluster scope
-    uint32_t ok, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > (1u << 26)) __trap();
-    } while (!ok);
-}
+// wait on a barrier whose phase is completed by arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 template <int CG>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     if (CG == 2) {
@@ -274,14 +263,22 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> tensor core reads
                         named_bar(1, 32 * kSplitWarps);
-                        if (t == 0) {
+                        // the arrival travels to the leader CTA: the warps take turns, so that no single thread has one
+                        // remote round trip per k-block on its critical path
+                        if (t == 32u * (it % kSplitWarps)) {
                             if (CG == 2) mbar_arrive_remote(ready_leader + 8 * s);
                             else mbar_arrive(ready0 + 8 * s);
                         }
-                    } else if (t == 0) {
-                        mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
-                        if (CG == 2) mbar_arrive_remote(ready_leader + 8 * s);
-                        else mbar_arrive(ready0 + 8 * s);
+                    } else {
+                        // relay: "stage landed" is forwarded to the leader by warp (it % 8); the named barrier keeps the
+                        // eight warps within one iteration of each other (a parity wait is only meaningful within one
+                        // phase of its barrier)
+                        if ((t & 31u) == 0) mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+                        named_bar(1, 32 * kSplitWarps);
+                        if (t == 32u * (it % kSplitWarps)) {
+                            if (CG == 2) mbar_arrive_remote(ready_leader + 8 * s);
+                            else mbar_arrive(ready0 + 8 * s);
+                        }
                     }
                 }
             }
@@ -406,22 +403,40 @@ int launch(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& 
     const size_t smem = (size_t)stages * stage + 2 * kEpiBuf + 1024;
     if (int a = gpt_smem_opt_in(gemm_persistent_kernel<PASSES, CG>, smem)) return a;
     const int m_blocks = (M + CG * BM - 1) / (CG * BM);
-    int clusters = sm_count() / CG;
-    if (clusters > m_blocks) clusters = m_blocks;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(clusters * CG));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
+    int clusters = sm_count() / CG;
     if (CG == 2) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = 2;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;
+        // a persistent grid must be ONE wave: as many clusters as can be co-resident (a GPC with an odd SM count hosts
+        // one pair fewer), remembered per device
+        static int resident[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64) {
+            if (resident[dev] == 0) {
+                cfg.gridDim = dim3((unsigned)(clusters * CG));
+                cfg.attrs = attr;
+                cfg.numAttrs = na;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, gemm_persistent_kernel<PASSES, CG>, &cfg) != cudaSuccess || n <= 0)
+                    n = clusters;
+                resident[dev] = n;
+                if (getenv("GPT_GEMM_DEBUG")) fprintf(stderr, "gemm_persist<%d,%d>: %d co-resident clusters, %d stages\n", PASSES, CG, n, stages);
+            }
+            if (resident[dev] < clusters) clusters = resident[dev];
+        }
     }
+    if (clusters > m_blocks) clusters = m_blocks;
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
     if (g_gpt_pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;

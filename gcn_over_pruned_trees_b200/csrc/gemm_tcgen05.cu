@@ -27,6 +27,7 @@
 // waits on.
 #include "gpt_common.cuh"
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 
 namespace {

@@ -28,7 +28,8 @@ from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer  # noqa: E402
 def main():
     rank, local_rank, world = parallel.init_from_env('nccl')
     torch.cuda.set_device(local_rank)
-    over = dict(vocab_size=1500, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='fp32')
+    gemm = os.environ.get('GPT_DP_GEMM', 'fp32')          # 'tf32x3' = the mode bench.py runs
+    over = dict(vocab_size=1500, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode=gemm)
     steps = 8
     batches = [synth.make_batch(300 + i, batch_size=50 * world, vocab_size=1500) for i in range(3)]
     torch.manual_seed(11)
@@ -68,12 +69,12 @@ def main():
     ok = identical
     if rank == 0:
         ok = ok and worst < 5e-6 and loss_err < 2e-5
-        line = ('DP_CHECK %s world=%d steps=%d (lockstep) replicas bit-identical: %s; vs full-batch single process: '
-                'params rel %.2e, loss rel %.2e' % ('OK' if ok else 'FAIL', world, steps, identical, worst, loss_err))
+        line = ('DP_CHECK %s world=%d steps=%d gemm=%s (lockstep) replicas bit-identical: %s; vs full-batch single process: '
+                'params rel %.2e, loss rel %.2e' % ('OK' if ok else 'FAIL', world, steps, gemm, identical, worst, loss_err))
         print(line, flush=True)
         out_dir = os.path.join(REPO, 'gpurun_out')
         if os.path.isdir(out_dir):
-            with open(os.path.join(out_dir, 'dp_check_w%d.txt' % world), 'w') as f:
+            with open(os.path.join(out_dir, 'dp_check_w%d_%s.txt' % (world, gemm)), 'w') as f:
                 f.write(line + '\n')
     flag = torch.tensor([1 if ok else 0], device='cuda')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
