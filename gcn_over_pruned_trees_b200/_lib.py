@@ -53,6 +53,8 @@ SIGNATURES = {
     'gpt_head_fwd_bwd': [_p, _p, _p, _p, _c_int, _p, _p, _c_int, _c_int, _c_int, _c_f, _c_int, _p, _p, _p, _p, _p, _p,
                          _p],
     'gpt_head_wgrad': [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _p],
+    'gpt_predict_result_bytes': [_c_int, _c_int],
+    'gpt_predict_tail': [_p, _p, _p, _c_int, _c_int, _p, _p],
     'gpt_dp_region_bytes': [_c_int, _c_int, _c_int, _c_int, _c_ll],
     'gpt_dp_partials': [_c_int, _c_int, _c_int, _c_int, _c_ll],
     'gpt_dp_alloc': [_c_ll, _p, _p],
@@ -102,6 +104,7 @@ def lib():
             fn.restype = _c_int
         handle.gpt_launch_count.restype = ctypes.c_ulonglong
         handle.gpt_dp_region_bytes.restype = ctypes.c_longlong
+        handle.gpt_predict_result_bytes.restype = ctypes.c_longlong
         handle.gpt_error_string.argtypes = [_c_int]
         handle.gpt_error_string.restype = ctypes.c_char_p
         _lib = handle

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, 'libgptb200.so')
 SOURCES = ['api.cu', 'prune_csr.cu', 'aggregate.cu', 'pool3.cu', 'gemm_simt.cu', 'gemm_tcgen05.cu', 'wgrad_tcgen05.cu', 'embed.cu',
-           'head.cu', 'update.cu', 'dp.cu', 'batch.cu', 'deprel.cu']
+           'head.cu', 'predict.cu', 'update.cu', 'dp.cu', 'batch.cu', 'deprel.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC,-O2', '-cudart', 'static']
 

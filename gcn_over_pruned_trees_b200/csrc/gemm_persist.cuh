@@ -121,6 +121,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// TMA load whose completion bytes are credited to an mbarrier that may live in the PEER CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void named_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -145,6 +152,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     const int n_half = n_tile / CG;                                 // rows of W this CTA stages per tile
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_half * BK * 4;
     constexpr uint32_t kLo = PASSES == 3 ? 2u : 1u;
+    constexpr bool kDirect = PASSES == 1;       // TF32: the MMA thread waits on the TMA barrier itself (no splitters, no relay)
     const uint32_t stage_bytes = kLo * (a_bytes + b_bytes);         // [A | A_lo | B | B_lo], every tile 1024-byte aligned
     const uint32_t off_alo = a_bytes, off_b = kLo * a_bytes, off_blo = off_b + b_bytes;
     const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
@@ -181,6 +189,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         // ===== TMA producer (each CTA: its 128 rows of X, its half of the W tile) =====
         if (lane == 0) {
             uint32_t it = 0;
+            // TF32 on a CTA pair: nothing has to touch the landed tiles, so BOTH CTAs' loads credit their bytes to the
+            // leader's full[s] (cp.async.bulk.tensor.cta_group::2) and the MMA thread waits on that barrier directly
+            const uint32_t full_leader = (kDirect && CG == 2) ? map_to_rank(full0, 0) : full0;
             for (int mb = cluster; mb < m_blocks; mb += n_clusters) {
                 const int m0 = (mb * CG + (int)rank) * BM;
                 for (int nb = 0; nb < n_tiles; ++nb) {
@@ -189,10 +200,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         const uint32_t s = it % (uint32_t)STAGES;
                         if (it >= (uint32_t)STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
                         const uint32_t st = tiles + s * stage_bytes;
-                        mbar_expect_tx(full0 + 8 * s, a_bytes + kLo * b_bytes);
-                        tma_load_2d(st, &tm_a, full0 + 8 * s, kb * BK, m0);          // OOB rows / columns arrive as zeros
-                        tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, kb * BK, n0);
-                        if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, kb * BK, n0);
+                        if (kDirect && CG == 2) {
+                            if (leader) mbar_expect_tx(full0 + 8 * s, 2u * (a_bytes + b_bytes));
+                            tma_load_2d_pair(st, &tm_a, full_leader + 8 * s, kb * BK, m0);
+                            tma_load_2d_pair(st + off_b, &tm_b, full_leader + 8 * s, kb * BK, n0);
+                        } else {
+                            mbar_expect_tx(full0 + 8 * s, a_bytes + kLo * b_bytes);
+                            tma_load_2d(st, &tm_a, full0 + 8 * s, kb * BK, m0);      // OOB rows / columns arrive as zeros
+                            tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, kb * BK, n0);
+                            if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, kb * BK, n0);
+                        }
                     }
                 }
             }
@@ -211,7 +228,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                     const uint32_t acc = tmem_base + a * kAccCols;
                     for (int kb = 0; kb < nkb; ++kb, ++it) {
                         const uint32_t s = it % (uint32_t)STAGES;
-                        mbar_wait_cluster(ready0 + 8 * s, (it / STAGES) & 1);
+                        mbar_wait_cluster((kDirect ? full0 : ready0) + 8 * s, (it / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t st = tiles + s * stage_bytes;
                         const uint64_t a_desc = make_kmajor_desc(st), b_desc = make_kmajor_desc(st + off_b);
@@ -232,7 +249,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             }
         }
     } else if (warp >= 2 + kEpiWarps) {
-        // ===== splitters (3xTF32) / relay (TF32): make the landed stage consumable and tell the leader =====
+        // ===== splitters (3xTF32 only): rewrite the landed X tile as hi, write lo, tell the leader =====
         const uint32_t t = threadIdx.x - 32 * (2 + kEpiWarps);     // 0..255
         const uint32_t ready_leader = CG == 2 ? map_to_rank(ready0, 0) : ready0;
         uint32_t it = 0;
@@ -265,16 +282,6 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         named_bar(1, 32 * kSplitWarps);
                         // the arrival travels to the leader CTA: the warps take turns, so that no single thread has one
                         // remote round trip per k-block on its critical path
-                        if (t == 32u * (it % kSplitWarps)) {
-                            if (CG == 2) mbar_arrive_remote(ready_leader + 8 * s);
-                            else mbar_arrive(ready0 + 8 * s);
-                        }
-                    } else {
-                        // relay: "stage landed" is forwarded to the leader by warp (it % 8); the named barrier keeps the
-                        // eight warps within one iteration of each other (a parity wait is only meaningful within one
-                        // phase of its barrier)
-                        if ((t & 31u) == 0) mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
-                        named_bar(1, 32 * kSplitWarps);
                         if (t == 32u * (it % kSplitWarps)) {
                             if (CG == 2) mbar_arrive_remote(ready_leader + 8 * s);
                             else mbar_arrive(ready0 + 8 * s);

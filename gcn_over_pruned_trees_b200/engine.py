@@ -257,14 +257,16 @@ class FusedTrainStep(object):
     configuration can run here; everything else stays on GraphedTrainStep (autograd under capture).
     """
 
-    def __init__(self, trainer, max_grad_norm=None, warmup=2, data_parallel=False, max_rows=8192, capture=True):
+    def __init__(self, trainer, max_grad_norm=None, warmup=2, data_parallel=False, max_rows=8192, capture=True,
+                 training=True):
         """data_parallel: False | True / 'peer' (K8: gradients meet in NVLink peer memory inside the step's kernels, the
         word-embedding gradient travels as live rows -- the exchange for microsecond-scale steps) | 'nccl' (one NCCL
         all-reduce of ONE flat gradient buffer that also holds the dense [V, E] word-embedding gradient, then K7 on the
         mean -- the exchange for large batches, where most of the vocabulary is live and a step takes milliseconds).
-        capture=False launches every step eagerly (large shapes: ~20 launches against tens of milliseconds)."""
+        capture=False launches every step eagerly (large shapes: ~20 launches against tens of milliseconds).
+        training=False: forward only (FusedPredict) -- the parameters stay where they are, no gradient buffers."""
         from . import ops
-        why = self.unsupported_reason(trainer)
+        why = self.unsupported_reason(trainer, training)
         if why:
             raise ValueError('FusedTrainStep: ' + why)
         self.trainer, self.model, self.opt = trainer, trainer.model, trainer.opt
@@ -275,6 +277,16 @@ class FusedTrainStep(object):
         self.tacred = self.opt['dataset'] == 'tacred'
         self.use_pos = self.opt['pos_dim'] > 0
         self.use_ner = self.opt['ner_dim'] > 0 and self.tacred
+        self.mlp = [m for m in gm.out_mlp if isinstance(m, torch.nn.Linear)]
+        self.cls = self.model.classifier
+        self.emb_weight = gm.emb.weight
+        self.side = (torch.cuda.Stream(), torch.cuda.Stream())
+        # the step is captured on a high-priority stream: when a side branch (weight gradients, K1) and the chain of
+        # data-dependent kernels compete for SMs, the chain goes first
+        self.capture_stream = torch.cuda.Stream(priority=-1) if os.environ.get('GPT_PRIO', '1') != '0' else None
+        self.flat = self.sparse = self.exchange = None
+        if not training:
+            return
         self.exchange_kind = {False: None, None: None, True: 'peer', 'peer': 'peer', 'nccl': 'nccl'}[data_parallel]
         self.capture = capture
         self.dense_emb = self.exchange_kind == 'nccl' and gm.emb.weight.requires_grad
@@ -315,11 +327,6 @@ class FusedTrainStep(object):
         self._lr = self.trainer.optimizer.param_groups[0]['lr']
         self.kernels_per_replay = {}
         self.replays = 0
-        self.side = (torch.cuda.Stream(), torch.cuda.Stream())
-        # the step is captured on a high-priority stream: when a side branch (weight gradients, K1) and the chain of
-        # data-dependent kernels compete for SMs, the chain goes first
-        self.capture_stream = torch.cuda.Stream(priority=-1) if os.environ.get('GPT_PRIO', '1') != '0' else None
-        self.exchange = None
         self.max_rows = max_rows
         self.world = 1
         if self.exchange_kind == 'nccl':
@@ -331,7 +338,9 @@ class FusedTrainStep(object):
             self.partials = torch.zeros(max(1024, self.exchange.n_partials), dtype=torch.float32, device=emb.device)
 
     @staticmethod
-    def unsupported_reason(trainer):
+    def unsupported_reason(trainer, training=True):
+        """Why this trainer cannot run on the fused kernels (None: it can).  training=False asks for the forward only
+        (FusedPredict): the optimizer and the loss's extra terms do not matter then."""
         opt = trainer.opt
         o = trainer.optimizer
         plain_sgd = isinstance(o, torch.optim.SGD) and len(o.param_groups) == 1 and all(
@@ -339,13 +348,13 @@ class FusedTrainStep(object):
             not g.get('maximize', False) for g in o.param_groups)
         if not opt.get('cuda', False):
             return 'needs a CUDA device'
-        if not plain_sgd:
+        if training and not plain_sgd:
             return 'optimizer is not plain SGD'
         if opt.get('rnn', False):
             return 'C-GCN encoder (cuDNN LSTM) runs under autograd'
         if opt.get('adj_type', 'regular') != 'regular':
             return 'relation-aware layers (csrc/deprel.cu) run under autograd'
-        if opt.get('conv_l2', 0) > 0:
+        if training and opt.get('conv_l2', 0) > 0:
             return 'conv_l2 > 0'
         if opt['hidden_dim'] % 4 != 0 or opt['mlp_layers'] > 4:
             return 'head shape outside K6'
@@ -368,7 +377,7 @@ class FusedTrainStep(object):
         ev.record(stream)
         torch.cuda.current_stream().wait_event(ev)
 
-    def _forward(self, inputs, labels, join_side=False, rng=None):
+    def _forward(self, inputs, labels, join_side=False, rng=None, train=True):
         """K1 || weight-prep || K5 -> L x (K3, K2) -> K4 -> K6 (head forward + loss rows + the head's data gradients).
         Independent work runs on two side streams (forked / joined with events, so the same code is what the CUDA graph
         captures as parallel branches).  Buffers touched by a side stream are allocated here, on the main stream, and
@@ -389,7 +398,7 @@ class FusedTrainStep(object):
         mode = gcn.gemm_mode
         st.use_adj = use_adj = not opt.get('no_adj', False)
         st.ptype = ptype = ops.POOL_TYPES[opt['pooling']]
-        p_in, p_gcn = opt['input_dropout'], opt['gcn_dropout']
+        p_in, p_gcn = (opt['input_dropout'], opt['gcn_dropout']) if train else (0.0, 0.0)
         st.pos_w = pos_w = gm.pos_emb.weight if self.use_pos else None
         st.ner_w = ner_w = gm.ner_emb.weight if self.use_ner else None
         st.words, st.pos, st.ner, st.B, st.T, st.H = words, pos, ner, B, T, H
@@ -407,7 +416,8 @@ class FusedTrainStep(object):
             ops.weight_prep_all([lin.weight.data for lin in gcn.W], mode, wss)    # one launch: the first GEMM waits for it
             ev_prep = torch.cuda.Event()
             ev_prep.record(sb)
-            ops.l2_prefetch(fl.param)            # every dense weight: first touches later in the step hit L2
+            if fl is not None:
+                ops.l2_prefetch(fl.param)        # every dense weight: first touches later in the step hit L2
         x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
                           None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
         main.wait_event(ev_prep)                 # (the prefetch behind it is joined at the end of the step)
@@ -431,7 +441,7 @@ class FusedTrainStep(object):
         st.pooled, st.argmax = pooled, argmax
         st.buf = buf = ops.HeadBuffers(B, H, self.cls.weight.shape[0], len(self.mlp), words.device)
         ops.head_fwd_bwd(pooled, labels, [m.weight.data for m in self.mlp], [m.bias.data for m in self.mlp],
-                         self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=True)
+                         self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=train)
         if join_side:
             self._join(sb)
         return st
@@ -861,3 +871,84 @@ class FastUpdate(object):
         if eng.sparse is not None:
             ptrs.add(eng.sparse.G.data_ptr())
         return ptrs
+
+
+class FusedPredict(object):
+    """``GCNTrainer.predict`` (/root/reference/model/trainer.py:112-124) on the fused kernels: the eval-mode forward of
+    FusedTrainStep (K1 || K5 -> L x (K3, K2) -> K4 -> K6) + K11 (mean CE, softmax, argmax, un-sort by orig_idx) captured as
+    one CUDA graph per batch shape, ONE device-to-host copy of a packed result.  The reference runs the model, three ATen
+    tails, two .cpu() copies and a Python sort of B tuples."""
+
+    def __init__(self, trainer, warmup=1):
+        self.trainer = trainer
+        self.engine = FusedTrainStep(trainer, training=False)
+        self.warmup = warmup
+        self.entries = {}
+        self.replays = 0
+        self._sig = None
+
+    def _signature(self):
+        return tuple(p.data_ptr() for p in self.trainer.model.parameters())
+
+    def _run(self, entry):
+        from . import ops
+        st = self.engine._forward(entry['inputs'], entry['labels'], join_side=True, train=False)
+        ops.predict_tail(st.buf.logits, entry['labels'], entry['dest'], entry['result'])
+        self.engine.last_csr = st.csr
+
+    @torch.no_grad()
+    def predict(self, batch, unsort=True):
+        import numpy as np
+        from . import ops
+        fields, labels, orig_idx = batch[:-2], batch[-2], batch[-1]
+        B, T = fields[0].shape
+        C = self.engine.cls.weight.shape[0]
+        sig = self._signature()
+        if sig != self._sig:                 # the parameters moved (a training engine re-homed them): re-capture
+            self.entries.clear()
+            self._sig = sig
+        key = (B, T, len(fields))
+        entry = self.entries.get(key)
+        dev = self.engine.emb_weight.device
+        if entry is None:
+            proto = tuple(t.to(dev) for t in fields) + (labels.to(dev), None)
+            static = PackedBatch(batch=proto, device=dev)
+            nbytes = ops.predict_result_bytes(B, C)
+            entry = {'packed': static, 'inputs': static.fields, 'labels': static.labels, 'seen': 0, 'graph': None,
+                     'dest': torch.zeros(B, dtype=torch.int32, device=dev),
+                     'dest_host': torch.zeros(B, dtype=torch.int32).pin_memory(),
+                     'result': torch.zeros(nbytes, dtype=torch.uint8, device=dev),
+                     'result_host': torch.zeros(nbytes, dtype=torch.uint8).pin_memory()}
+            self.entries[key] = entry
+        else:
+            for s_, t in zip(entry['inputs'], fields):
+                s_.copy_(t, non_blocking=True)
+            entry['labels'].copy_(labels, non_blocking=True)
+        # where each batch row goes: sorted(zip(orig_idx, ...)) of the reference = ascending orig_idx
+        if unsort:
+            order = sorted(range(B), key=orig_idx.__getitem__)
+            dest = entry['dest_host'].numpy()
+            dest[order] = np.arange(B, dtype=np.int32)
+        else:
+            entry['dest_host'].numpy()[:] = np.arange(B, dtype=np.int32)
+        entry['dest'].copy_(entry['dest_host'], non_blocking=True)
+        entry['seen'] += 1
+        if entry['graph'] is not None:
+            entry['graph'].replay()
+            self.replays += 1
+        elif entry['seen'] <= self.warmup:
+            self._run(entry)
+        else:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=self.engine.capture_stream):
+                self._run(entry)
+            entry['graph'] = g
+            g.replay()
+        entry['result_host'].copy_(entry['result'], non_blocking=True)        # the one device-to-host copy
+        torch.cuda.current_stream().synchronize()
+        raw = entry['result_host'].numpy()
+        probs = raw[:B * C * 4].view(np.float32).reshape(B, C)
+        preds = raw[B * C * 4:B * C * 4 + B * 4].view(np.int32)
+        loss = float(raw[B * C * 4 + B * 4:].view(np.float32)[0])
+        return preds.tolist(), probs.tolist(), loss

@@ -98,6 +98,23 @@ class GCNTrainer(Trainer):
         logits, pooling_output = self.model(inputs)
         return self._loss(logits, pooling_output, labels)
 
+    def _predict_path(self, batch):
+        if not (self.fast_update and self.opt['cuda']) or batch[0].dim() != 2:
+            return None
+        if self.model.gcn_model.gcn.injected_masks is not None:
+            return None
+        fp = getattr(self, '_fused_predict', None)
+        if fp is None:
+            try:
+                from ..engine import FusedPredict, FusedTrainStep
+            except ImportError:
+                from gcn_over_pruned_trees_b200.engine import FusedPredict, FusedTrainStep
+            if FusedTrainStep.unsupported_reason(self, training=False) is not None:
+                self._fused_predict = False
+                return None
+            fp = self._fused_predict = FusedPredict(self)
+        return fp or None
+
     def _fast_path(self):
         """engine.FastUpdate when this call can take it: a training-mode forward with autograd on, on a configuration
         FusedTrainStep covers (regular GCN, plain SGD, CUDA); None otherwise."""
@@ -119,9 +136,12 @@ class GCNTrainer(Trainer):
         return self._fast
 
     def predict(self, batch, unsort=True):
+        self.model.eval()
+        fused = self._predict_path(batch)
+        if fused is not None:           # one graph replay + one device-to-host copy (engine.FusedPredict, K11)
+            return fused.predict(batch, unsort)
         inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]
         orig_idx = batch[-1]
-        self.model.eval()
         with torch.no_grad():
             logits, _ = self.model(inputs)
             loss = self.criterion(logits, labels)

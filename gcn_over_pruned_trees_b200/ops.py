@@ -709,6 +709,17 @@ def head_wgrad(pooled, buf, dws, dbs, dwc, dbc):
     return buf.loss
 
 
+def predict_tail(logits, labels, dest, result):
+    """K11: softmax + argmax + mean CE + un-sort (model/trainer.py:118-123) -> packed ``result`` (uint8 device buffer of
+    gpt_predict_result_bytes(B, C) bytes: probs f32 [B,C] | predictions i32 [B] | loss f32)."""
+    B, C = logits.shape
+    _call('gpt_predict_tail', _ptr(logits), _ptr(labels), _ptr(dest), B, C, _ptr(result), _stream())
+
+
+def predict_result_bytes(B, C):
+    return int(_lib.lib().gpt_predict_result_bytes(int(B), int(C)))
+
+
 # ---- K7: clip + SGD ---------------------------------------------------------------------------------------------------
 
 def update_partials(n, n_rows):

@@ -191,6 +191,15 @@ int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner, const floa
 int gpt_embed_rows_sgd(const int64_t* words, int32_t* owner, float* g_emb, float* emb_w, int n_rows, int E, int topn,
                        const float* total_sq, float max_norm, float lr, void* stream);
 
+/* K11. eval-side tail of GCNTrainer.predict (model/trainer.py:112-124) in one launch: mean CrossEntropy (:118), softmax
+ *     (:119), argmax with numpy's first-maximum rule (:120) and the un-sort to the loader's original order (:121-123).
+ *     dest[b] = position of batch row b in the original order (NULL: keep the batch order).  result: one packed device
+ *     buffer of gpt_predict_result_bytes(B, C) bytes, [ probs f32 [B,C] | predictions i32 [B] | loss f32 ], rows already in
+ *     the original order -- the host needs a single device-to-host copy. */
+long long gpt_predict_result_bytes(int B, int C);
+int gpt_predict_tail(const float* logits, const int64_t* labels, const int32_t* dest, int B, int C, void* result,
+                     void* stream);
+
 /* K6. classifier head for one batch of pooled vectors [B,3H] (K4 output): out_mlp (model/gcn.py:64-68,122: n_mlp x
  *     Linear+ReLU, w[0] [H,3H], w[l>0] [H,H]), classifier (model/gcn.py:21,29: wc [C,H]), and the loss of
  *     model/trainer.py:94-100 without the conv_l2 term: CrossEntropy(mean) + pooling_l2 * mean_b sum_h pooled[b,h<H]^2.

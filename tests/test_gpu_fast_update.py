@@ -218,3 +218,68 @@ def test_graphed_engine_leaves_the_reference_sequence_with_a_dense_embedding_gra
     tr.optimizer.step()
     assert not torch.equal(tr.model.gcn_model.emb.weight, emb0)
     assert float(tr._graphed.sparse.G.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------- K11 / FusedPredict ----------------------------------
+
+@pytest.mark.parametrize('B,C', [(50, 42), (1, 42), (20, 19), (333, 10), (64, 200)])
+def test_k11_predict_tail_matches_torch(B, C):
+    """softmax / np.argmax (first maximum) / mean CE / un-sort of model/trainer.py:118-123 in one launch."""
+    g = torch.Generator().manual_seed(B * 31 + C)
+    logits = torch.randn(B, C, generator=g) * 3
+    logits[0, :] = 1.25                                  # a full tie: numpy picks column 0
+    if B > 2:
+        logits[2, 5 % C] = logits[2, C - 1] = 9.0        # a two-way tie: the lower column wins
+    labels = torch.randint(0, C, (B,), generator=g)
+    orig_idx = torch.randperm(B, generator=g).tolist()
+    order = sorted(range(B), key=orig_idx.__getitem__)
+    dest = torch.empty(B, dtype=torch.int32)
+    dest[order] = torch.arange(B, dtype=torch.int32)
+    result = torch.zeros(ops.predict_result_bytes(B, C), dtype=torch.uint8, device=DEV)
+    ops.predict_tail(logits.to(DEV), labels.to(DEV), dest.to(DEV), result)
+    raw = result.cpu().numpy()
+    probs = raw[:B * C * 4].view(np.float32).reshape(B, C)
+    preds = raw[B * C * 4:B * C * 4 + B * 4].view(np.int32)
+    loss = float(raw[B * C * 4 + B * 4:].view(np.float32)[0])
+    ref_probs = torch.softmax(logits, 1).numpy()
+    ref_preds = np.argmax(logits.numpy(), axis=1)
+    _, ref_preds_u, ref_probs_u = [list(t) for t in zip(*sorted(zip(orig_idx, ref_preds.tolist(), ref_probs.tolist())))]
+    assert preds.tolist() == ref_preds_u
+    assert np.abs(probs - np.array(ref_probs_u)).max() <= 1e-6
+    ref_loss = float(torch.nn.functional.cross_entropy(logits, labels))
+    assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss)
+
+
+@pytest.mark.parametrize('gemm_mode', ('fp32', 'tf32x3'))
+def test_fused_predict_equals_the_per_op_predict(gemm_mode):
+    """GCNTrainer.predict on one graph replay + one D2H copy == the same call on the per-op path (model forward, ATen
+    softmax / argmax, two copies, Python sort): same labels, probabilities <= 1e-5, loss <= 1e-5; before and after the
+    training engines have re-homed the parameters; unsort=False; repeated shapes (replays)."""
+    from gcn_over_pruned_trees_b200.engine import FusedPredict
+    opt = synth.tacred_opt(vocab_size=700, cuda=True, gemm_mode=gemm_mode)
+    torch.manual_seed(17)
+    tr = GCNTrainer(dict(opt))
+    batches = [synth.make_batch(90 + i, batch_size=bs, vocab_size=700) for i, bs in enumerate((50, 50, 37, 1))]
+    batches.append(batches[0])
+
+    def both(b, unsort=True):
+        tr.fast_update = False
+        ref = tr.predict(b, unsort)
+        tr.fast_update = True
+        got = tr.predict(b, unsort)
+        assert got[0] == ref[0]
+        assert np.abs(np.array(got[1]) - np.array(ref[1])).max() <= 1e-5 * np.abs(np.array(ref[1])).max()
+        assert abs(got[2] - ref[2]) <= 1e-5 * abs(ref[2])
+        assert isinstance(got[0][0], int) and isinstance(got[1][0][0], float) and isinstance(got[2], float)
+
+    for b in batches:
+        both(b)
+    both(batches[0], unsort=False)
+    assert isinstance(tr._fused_predict, FusedPredict) and tr._fused_predict.replays >= 1
+    tr.model.train()
+    for _ in range(3):                                   # FastUpdate / FusedTrainStep move the parameters into one buffer
+        _five_calls(tr, batches[0])
+    tr.train_step(batches[2])
+    for b in batches[:3]:
+        both(b)
+    assert not tr.model.training                         # predict() leaves the model in eval mode, as the reference does
