@@ -73,6 +73,7 @@ def workload_config(args, world):
     return {'workload': 'tacred_b50_k%d' % args.prune_k, 'batch_per_gpu': BATCH, 'global_batch': BATCH * world,
             'len': 'clip(Poisson(36),8,96)', 'layers': 2, 'in_dim': 360, 'hidden': 200, 'vocab': VOCAB,
             'prune_k': args.prune_k, 'parallelism': 'dp%d' % world,
+            'sharding': 'rows r::N of one length-sorted global batch per step',
             'step': 'zero_grad+fwd+loss+bwd+allreduce+clip5+sgd',
             'l2': 'GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable'}
 
@@ -415,8 +416,9 @@ def semeval_leg(args, rank, world, dev, flush):
     tr.model.train()
     eng = FusedTrainStep(tr, data_parallel=world > 1, max_rows=BATCH * 128)
     nb = 8
-    host = [synth.make_batch(2000 + rank * nb + i, batch_size=BATCH, vocab_size=VOCAB, dataset='semeval', num_class=19,
-                             mean_len=19, min_len=5, max_len=97) for i in range(nb)]
+    host = [parallel.shard_batch(synth.make_batch(2000 + i, batch_size=BATCH * world, vocab_size=VOCAB, dataset='semeval',
+                                                  num_class=19, mean_len=19, min_len=5, max_len=97), rank, world)
+            for i in range(nb)]
     res = [PackedBatch(b, device='cpu').to(dev) for b in host]
     for _ in range(4):
         for b in res:
@@ -526,7 +528,11 @@ def run_b200(args):
     dp_check = None
     if world > 1 and not args.no_dp_check and not args.autograd_engine and not args.eager:
         dp_check = dp_lockstep_check(args, rank, world, dev)
-    host = [synth.make_batch(1000 + rank * N_BATCHES + i, batch_size=BATCH, vocab_size=VOCAB) for i in range(N_BATCHES)]
+    # N ranks: every step is ONE global batch of 50 x N sentences, length-sorted as the loader sorts it, and rank r takes rows
+    # r::N (parallel.shard_batch) -- the ranks' shards then have near-equal widths and no rank waits for a
+    # straggler with a longer batch.  N = 1: the same 50-sentence batches as before.
+    host = [parallel.shard_batch(synth.make_batch(1000 + i, batch_size=BATCH * world, vocab_size=VOCAB), rank, world)
+            for i in range(N_BATCHES)]
     host = [tuple(t.pin_memory() if torch.is_tensor(t) else t for t in b) for b in host]
     resident = [tuple(t.to(dev) if torch.is_tensor(t) else t for t in b) for b in host]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)

@@ -120,6 +120,7 @@ __global__ void dp_init_kernel(const DpLayout L, unsigned char* base) {
 __global__ void __launch_bounds__(kDpThreads)
 dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restrict__ flat_g, float* __restrict__ G,
                int* __restrict__ owner, const long long* __restrict__ words, int n_rows, int topn, int dense_blocks) {
+    GPT_PDL_ENTER();        // launched with programmatic serialization: the grid is resident before the backward's tail ends
     unsigned char* self = P.base[rank];
     const unsigned long long step = *reinterpret_cast<const unsigned long long*>(self + L.off_step);
     const int par = (int)(step & 1ull);
@@ -216,6 +217,9 @@ __device__ __forceinline__ void dp_entry(const int* s_off, int W, int e, int* r,
 __global__ void __launch_bounds__(kDpThreads, 4)
 dp_reduce_kernel(const DpLayout L, const DpPeers P, int rank, int signal, float* __restrict__ flat_g,
                  int dense_blocks, float* __restrict__ partials) {
+    // griddepcontrol.wait returns once the push grid has COMPLETED and its stores (peer stores included) are performed:
+    // the guarantee the flag protocol below relies on, with or without the programmatic-launch attribute
+    GPT_PDL_ENTER();
     __shared__ float s_red[kDpWarps];
     __shared__ int s_off[kDpMaxWorld + 1], s_n[kDpMaxWorld];
     unsigned char* self = P.base[rank];
@@ -341,6 +345,7 @@ dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __res
                 float* __restrict__ flat_g, float* __restrict__ emb_w, int dense_blocks,
                 const float* __restrict__ partials, int n_partials, float max_norm, float lr,
                 float* __restrict__ total_norm, unsigned long long* __restrict__ step_counter) {
+    GPT_PDL_ENTER();
     __shared__ float s_red[kDpWarps];
     __shared__ float s_coef;
     __shared__ int s_off[kDpMaxWorld + 1];
@@ -524,8 +529,8 @@ extern "C" int gpt_dp_push(void* const* regions, int rank, int W, int cap_rows, 
     int rb = (n_rows + kDpWarps - 1) / kDpWarps;
     if (rb > kDpMaxBlocks - 296) rb = kDpMaxBlocks - 296;      // one warp per token slot
     (void)r;
-    dp_push_kernel<<<d + rb, kDpThreads, 0, (cudaStream_t)stream>>>(
-        L, P, rank, flat_g, g_emb, owner, reinterpret_cast<const long long*>(words), n_rows, topn, d);
+    gpt_launch(dp_push_kernel, dim3(d + rb), dim3(kDpThreads), 0, (cudaStream_t)stream,
+               L, P, rank, flat_g, g_emb, owner, reinterpret_cast<const long long*>(words), n_rows, topn, d);
     return gpt_launch_status();
 }
 
@@ -564,7 +569,8 @@ extern "C" int gpt_dp_reduce(void* const* regions, int rank, int signal, int W, 
     }
     int d, r;
     plan(L, &d, &r);
-    dp_reduce_kernel<<<d + r, kDpThreads, 0, (cudaStream_t)stream>>>(L, P, rank, signal, flat_g, d, partials);
+    gpt_launch(dp_reduce_kernel, dim3(d + r), dim3(kDpThreads), 0, (cudaStream_t)stream, L, P, rank, signal, flat_g, d,
+               partials);
     return gpt_launch_status();
 }
 
@@ -578,8 +584,8 @@ extern "C" int gpt_dp_apply(void* region, int W, int cap_rows, int E, int V, lon
     const DpLayout L = make_layout(W, cap_rows, E, V, n_flat);
     int d, r;
     plan(L, &d, &r);
-    dp_apply_kernel<<<d + r, kDpThreads, 0, (cudaStream_t)stream>>>(
-        L, reinterpret_cast<unsigned char*>(region), param, flat_g, emb_w, d, partials, d + r, max_norm, lr,
-        total_norm, reinterpret_cast<unsigned long long*>(step_counter));
+    gpt_launch(dp_apply_kernel, dim3(d + r), dim3(kDpThreads), 0, (cudaStream_t)stream,
+               L, reinterpret_cast<unsigned char*>(region), param, flat_g, emb_w, d, partials, d + r, max_norm, lr,
+               total_norm, reinterpret_cast<unsigned long long*>(step_counter));
     return gpt_launch_status();
 }

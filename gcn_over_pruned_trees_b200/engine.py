@@ -40,6 +40,21 @@ class GraphedTrainStep(object):
         self._seen = {}
         self.replays = 0
         self.kernels_per_replay = {}
+        # Eager warm-up steps and the capture run on ONE side stream of this engine, never on the legacy default stream:
+        # autograd creates a parameter's AccumulateGrad node on the stream that is current at that moment and keeps it
+        # while any graph references it; a node that lives on the legacy stream makes the backward recorded under capture
+        # synchronise the legacy stream with the capturing one -- cudaErrorStreamCaptureImplicit, seen intermittently
+        # (torch's whole-network capture recipe: warm up on a side stream).
+        self._stream = torch.cuda.Stream() if trainer.opt.get('cuda', False) else None
+
+    def _on_side_stream(self, fn, *args):
+        if self._stream is None:
+            return fn(*args)
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            out = fn(*args)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        return out
 
     def _make_sparse_state(self):
         """Row-sparse word-embedding update (csrc/embed.cu) when it is arithmetic-identical to the dense one: a
@@ -114,7 +129,7 @@ class GraphedTrainStep(object):
         torch.cuda.synchronize()
         n0 = _lib.lib().gpt_launch_count()
         g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
+        with torch.cuda.graph(g1, stream=self._stream):
             loss = self._fwd_bwd(static_in, static_lab)
             if self.reducer is None:
                 self._update()
@@ -122,7 +137,7 @@ class GraphedTrainStep(object):
         entry['grads'] = [p.grad for p in self.reducer.params if p.grad is not None] if self.reducer else None
         if self.reducer is not None:
             g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, pool=g1.pool()):
+            with torch.cuda.graph(g2, pool=g1.pool(), stream=self._stream):
                 self._update()
             entry['g2'] = g2
         self.kernels_per_replay[key] = int(_lib.lib().gpt_launch_count() - n0)
@@ -145,7 +160,7 @@ class GraphedTrainStep(object):
             # the first steps of a new shape run eagerly (allocates .grad, warms caches); so does every step when the
             # optimizer's step() cannot be captured
             if seen < self.warmup or not self.capturable(self.trainer.optimizer):
-                return self._eager(inputs, labels)
+                return self._on_side_stream(self._eager, inputs, labels)
             entry = self._capture(key, inputs, labels)
         else:                           # host (pinned) or device source, straight into the static buffers
             for s, t in zip(entry['inputs'], fields):

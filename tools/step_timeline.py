@@ -9,18 +9,22 @@ import torch
 from torch.profiler import ProfilerActivity, profile
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gcn_over_pruned_trees_b200 import synth  # noqa: E402
+from gcn_over_pruned_trees_b200 import parallel, synth  # noqa: E402
 from gcn_over_pruned_trees_b200.engine import FusedTrainStep, PackedBatch  # noqa: E402
 from gcn_over_pruned_trees_b200.model.trainer import GCNTrainer  # noqa: E402
 
 
 def main():
+    # under torchrun: the data-parallel step (K8 exchange over NVLink peer memory); rank 0 prints its own timeline
+    rank, local_rank, world = parallel.init_from_env('nccl')
+    torch.cuda.set_device(local_rank)
     torch.manual_seed(0)
+    sys.stdout = open(os.devnull, 'w') if rank else sys.stdout
     tr = GCNTrainer(synth.tacred_opt(vocab_size=50000, cuda=True, gemm_mode='tf32x3', prune_k=1))
     tr.model.train()
-    eng = FusedTrainStep(tr)
-    batches = [PackedBatch(synth.make_batch(1000 + i, batch_size=50, vocab_size=50000), device='cpu').to('cuda')
-               for i in range(4)]
+    eng = FusedTrainStep(tr, data_parallel=world > 1, max_rows=6400)
+    batches = [PackedBatch(parallel.shard_batch(synth.make_batch(1000 + i, batch_size=50 * world, vocab_size=50000), rank,
+                                                world), device='cpu').to('cuda') for i in range(4)]
     flush = torch.empty(64 << 20, dtype=torch.float32, device='cuda')
     for _ in range(6):
         for b in batches:
@@ -45,7 +49,11 @@ def main():
         d = e.time_range.end - e.time_range.start
         end = max(end, s + d)
         print('%-58s %9.1f %9.1f' % (e.name.replace('(anonymous namespace)::', '')[:58], s, d))
-    print('replay span %.1f us, sum of kernel durations %.1f us' % (end, sum(e.time_range.end - e.time_range.start for e in last)))
+    print('replay span %.1f us, sum of kernel durations %.1f us (world %d)' % (
+        end, sum(e.time_range.end - e.time_range.start for e in last), world))
+    if world > 1:
+        parallel.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
