@@ -438,13 +438,19 @@ dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __res
     }
 }
 
+// Grid of the reduce / apply kernels: ONE wave.  dp_reduce_kernel keeps 4 CTAs per SM resident (launch bounds), so at most
+// 4 x 148 CTAs in total -- a grid sized for the region's capacity (1005 CTAs at W = 8) ran as a full wave plus a tail wave
+// of mostly idle CTAs, and both kernels are chains of dependent memory latencies: the second wave doubled them.  Both
+// loops are grid-stride, so fewer CTAs only means more entries per warp.
+constexpr int kDpWaveBlocks = 4 * 148;
+
 void plan(const DpLayout& L, int* dense_blocks, int* row_blocks) {
-    long long db = (L.n_flat / 4 + kDpThreads - 1) / kDpThreads;       // one float4 per thread while that fits
+    long long db = (L.n_flat / 4 + 2 * kDpThreads - 1) / (2 * kDpThreads);     // two float4 per thread while that fits
     if (db < 1) db = 1;
-    if (db > 296) db = 296;
+    if (db > 148) db = 148;
     const int per_block = kDpWarps * dp_chunk(L.W);
     long long rb = ((long long)L.W * L.cap_rows + per_block - 1) / per_block;
-    if (rb > kDpMaxBlocks - 296) rb = kDpMaxBlocks - 296;
+    if (rb > kDpWaveBlocks - db) rb = kDpWaveBlocks - db;
     *dense_blocks = (int)db;
     *row_blocks = (int)rb;
 }
