@@ -39,6 +39,9 @@ SIGNATURES = {
     'gpt_linear_wgrad_rows_f32': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_wgrad_tf32x3': [_p, _p, _p, _p, _c_ll, _c_int, _c_int, _p],
     'gpt_gemm_persist_config': [_c_int, _c_ll],
+    'gpt_weight_prep_bf16': [_p, _p, _c_int, _c_int, _p],
+    'gpt_linear_fwd_bf16': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
+    'gpt_linear_dgrad_bf16': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_fwd_tf32': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_tf32': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_weight_prep_tf32x3': [_p, _p, _c_int, _c_int, _p],

@@ -88,6 +88,24 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t 
             : "memory");
     }
 }
+template <int CG>
+__device__ __forceinline__ void umma16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+            : "memory");
+    }
+}
 // arrive (once every MMA issued so far by this thread has completed) on the barrier at this offset in every CTA of the pair
 template <int CG>
 __device__ __forceinline__ void commit_all(uint32_t bar) {
@@ -150,7 +168,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     const int m_blocks = (M + CG * BM - 1) / (CG * BM);
     const int nkb = (K + BK - 1) / BK;
     const int n_half = n_tile / CG;                                 // rows of W this CTA stages per tile
-    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_half * BK * 4;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_half * BK * (PASSES == 0 ? 2 : 4);
     constexpr uint32_t kLo = PASSES == 3 ? 2u : 1u;
     constexpr bool kDirect = PASSES == 1;       // TF32: the MMA thread waits on the TMA barrier itself (no splitters, no relay)
     const uint32_t stage_bytes = kLo * (a_bytes + b_bytes);         // [A | A_lo | B | B_lo], every tile 1024-byte aligned
@@ -217,7 +235,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
         if (leader && lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) |
+            const uint32_t fmt = PASSES == 0 ? 1u : 2u;          // operand format: BF16 (kind::f16) or TF32
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_tile >> 3) << 17) |
                                    ((uint32_t)((CG * BM) >> 4) << 24);
             uint32_t it = 0, tile_it = 0;
             for (int mb = cluster; mb < m_blocks; mb += n_clusters) {
@@ -231,6 +250,14 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         mbar_wait_cluster((kDirect ? full0 : ready0) + 8 * s, (it / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t st = tiles + s * stage_bytes;
+                        if (PASSES == 0) {
+                            const uint64_t a16 = make_kmajor_desc_sw64(st), b16 = make_kmajor_desc_sw64(st + off_b);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma16<CG>(acc, a16 + 2 * k, b16 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            commit_all<CG>(empty0 + 8 * s);
+                            continue;
+                        }
                         const uint64_t a_desc = make_kmajor_desc(st), b_desc = make_kmajor_desc(st + off_b);
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k)
@@ -257,6 +284,17 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             for (int nb = 0; nb < n_tiles; ++nb) {
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)STAGES;
+                    if (PASSES == 0) {          // bf16 operands: round the landed fp32 X tile to bf16, in place
+                        mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+                        tile_to_bf16_inplace<32 * kSplitWarps>(tiles + s * stage_bytes, BM, t,
+                                                               [] { named_bar(1, 32 * kSplitWarps); });
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar(1, 32 * kSplitWarps);
+                        if (t == 32u * (it % kSplitWarps)) {
+                            if (CG == 2) mbar_arrive_remote(ready_leader + 8 * s);
+                            else mbar_arrive(ready0 + 8 * s);
+                        }
+                    }
                     if (PASSES == 3) {
                         mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
                         const uint32_t src = tiles + s * stage_bytes + t * 16u, dst = src + off_alo;
@@ -402,7 +440,7 @@ inline int sm_count() {
 template <int PASSES, int CG>
 int launch(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, const CUtensorMap& tm_c, int M,
            int N, int K, int n_tile, int n_tiles, cudaStream_t st, const MaskEpilogue& ep) {
-    const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)(n_tile / CG) * BK * 4);
+    const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)(n_tile / CG) * BK * (PASSES == 0 ? 2 : 4));
     const size_t budget = 227 * 1024 - 1024 /*alignment*/ - 2 * kEpiBuf - 512 /*static*/;
     int stages = (int)(budget / stage);
     stages = stages > kMaxStages ? kMaxStages : stages;
@@ -497,6 +535,25 @@ inline int run(const float* A, const float* B, const float* b_lo, float* C, int 
     }
     if (b_lo != nullptr) return launch<3, 1>(tm_a, tm_b, tm_b_lo, tm_c, M, N, K, n_tile, n_tiles, st, ep);
     return launch<1, 1>(tm_a, tm_b, tm_b_lo, tm_c, M, N, K, n_tile, n_tiles, st, ep);
+}
+
+// the same for bf16 operands: B16 is bf16 [N, K] (kind::f16, one pass)
+inline int run_bf16(const float* A, const void* B16, float* C, int M, int N, int K, cudaStream_t st, const MaskEpilogue& ep) {
+    const int cg = mode();
+    if (cg != 1 && cg != 2) return GPT_ERR_UNSUPPORTED;
+    if (M < min_rows() || N % 4 != 0 || K % 8 != 0 || (reinterpret_cast<uintptr_t>(C) & 15)) return GPT_ERR_UNSUPPORTED;
+    const int n_tiles = (N + 255) / 256;
+    const int gran = n_tiles > 1 ? 32 : 16 * cg;
+    int n_tile = ((N + n_tiles - 1) / n_tiles + gran - 1) / gran * gran;
+    if (n_tile < 16 * cg) n_tile = 16 * cg;
+    if (n_tile > 256) return GPT_ERR_UNSUPPORTED;
+    alignas(64) CUtensorMap tm_a, tm_b, tm_c;
+    int rc = make_map(&tm_a, A, M, K, BM);
+    if (rc != GPT_OK) return rc;
+    if ((rc = make_map_bf16(&tm_b, B16, N, K, n_tile / cg)) != GPT_OK) return rc;
+    if ((rc = make_store_map(&tm_c, C, M, N)) != GPT_OK) return rc;
+    if (cg == 2) return launch<0, 2>(tm_a, tm_b, tm_b, tm_c, M, N, K, n_tile, n_tiles, st, ep);
+    return launch<0, 1>(tm_a, tm_b, tm_b, tm_c, M, N, K, n_tile, n_tiles, st, ep);
 }
 
 }  // namespace persist

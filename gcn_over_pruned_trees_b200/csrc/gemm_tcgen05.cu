@@ -19,6 +19,9 @@
 // bits are ignored, for A and for B), so with  a = a_hi + a_lo,  a_hi = trunc_tf32(a),  a_lo = a - a_hi (exact):
 //   PASSES = 1:  A.B ~ A_hi.B_hi                                   one TF32 pass, ~1e-3 relative
 //   PASSES = 3:  A.B ~ A_hi.B_hi + A_lo.B_hi + A_hi.B_lo           "3xTF32": fp32-grade (~1e-6), the parity mode
+//   PASSES = 0:  A.B ~ bf16(A).bf16(B), fp32 accumulation           kind::f16 with bf16 operands (the reduced-precision
+//                mode north_star asks for; ~4e-3 relative per product): the landed fp32 X tile is rounded to bf16 in
+//                shared memory by the same warps (in place: [128 x 32] bf16, 64-byte rows, SWIZZLE_64B), W arrives as bf16
 // For PASSES = 3 hi is *rounded* to TF32 (|lo| <= 2^-12 |a|, zero-mean), which makes the truncation the tensor core
 // applies to lo and the dropped lo.lo term ~2^-23 each.  B_hi / B_lo (the weight) are precomputed by a tiny kernel
 // and arrive by TMA; A_hi / A_lo are produced in shared memory by the four epilogue warps, which are idle during the
@@ -27,6 +30,7 @@
 // waits on.
 #include "gpt_common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
 
@@ -108,6 +112,57 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// K-major SWIZZLE_64B descriptor (bf16 tiles of 32 elements = 64-byte rows): 8-row groups 512 B apart, layout type 4
+__device__ __forceinline__ uint64_t make_kmajor_desc_sw64(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (bf16 operands, fp32 accumulator), K = 16 per instruction
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {      // round to nearest even, lo in the low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// The landed fp32 tile [rows x 32] (128-byte rows, 128B swizzle: 16-byte chunk j of row r at j ^ (r % 8)) -> bf16 tile
+// [rows x 32] at the same base (64-byte rows, 64B swizzle: 16-byte chunk c of row r at c ^ ((r / 2) % 4)).  In place:
+// every thread reads its items, ALL threads pass `sync`, then they write.  item = (row, bf16 chunk c = 8 elements).
+template <int NTHREADS, typename Sync>
+__device__ __forceinline__ void tile_to_bf16_inplace(uint32_t tile, int rows, uint32_t t, Sync sync) {
+    constexpr int kMaxItems = (128 * 4 + NTHREADS - 1) / NTHREADS;
+    float4 a[kMaxItems], b[kMaxItems];
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) {
+        const uint32_t item = t + (uint32_t)i * NTHREADS;
+        const uint32_t r = item >> 2, c = item & 3u;
+        if ((int)r < rows) {
+            const uint32_t base = tile + r * 128u, sw = r & 7u;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a[i].x), "=f"(a[i].y), "=f"(a[i].z), "=f"(a[i].w) : "r"(base + (((2u * c) ^ sw) << 4)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b[i].x), "=f"(b[i].y), "=f"(b[i].z), "=f"(b[i].w) : "r"(base + (((2u * c + 1u) ^ sw) << 4)));
+        }
+    }
+    sync();
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) {
+        const uint32_t item = t + (uint32_t)i * NTHREADS;
+        const uint32_t r = item >> 2, c = item & 3u;
+        if ((int)r < rows)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(tile + r * 64u + ((c ^ ((r >> 1) & 3u)) << 4)), "r"(pack_bf16(a[i].x, a[i].y)),
+                           "r"(pack_bf16(a[i].z, a[i].w)), "r"(pack_bf16(b[i].x, b[i].y)), "r"(pack_bf16(b[i].z, b[i].w))
+                         : "memory");
+    }
+}
+
 template <int PASSES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -123,7 +178,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // is served by L2 instead of HBM
     const int m0 = (int)(blockIdx.x / n_tiles) * BM, n0 = (int)(blockIdx.x % n_tiles) * n_tile;
     const int nkb = (K + BK - 1) / BK;
-    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_tile * BK * 4;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_tile * BK * (PASSES == 0 ? 2 : 4);
     // stage layout: [A | A_lo | B | B_lo] (the lo tiles only for PASSES == 3); every tile is 1024-byte aligned
     const uint32_t stage_bytes = (PASSES == 3 ? 2u : 1u) * (a_bytes + b_bytes);
     const uint32_t off_alo = a_bytes, off_b = (PASSES == 3 ? 2u : 1u) * a_bytes, off_blo = off_b + b_bytes;
@@ -172,14 +227,24 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9,
             // 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) |
+            // kind::f16 with bf16 operands: A = B = BF16 (format 1)
+            const uint32_t fmt = PASSES == 0 ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_tile >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
-                // PASSES == 3: the splitters arrive after the TMA bytes have landed and A_lo is written
-                mbar_wait((PASSES == 3 ? split0 : full0) + 8 * s, (kb / STAGES) & 1);
+                // PASSES == 3 / 0: the splitters arrive after the TMA bytes have landed and A_lo / bf16(A) is written
+                mbar_wait((PASSES != 1 ? split0 : full0) + 8 * s, (kb / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t st = tiles + (uint32_t)s * stage_bytes;
+                if (PASSES == 0) {
+                    const uint64_t a16 = make_kmajor_desc_sw64(st), b16 = make_kmajor_desc_sw64(st + off_b);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)      // 16 bf16 = 32 bytes per instruction
+                        umma_bf16(tmem_base, a16 + 2 * k, b16 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);
+                    continue;
+                }
                 const uint64_t a_desc = make_kmajor_desc(st), b_desc = make_kmajor_desc(st + off_b);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes inside the swizzle atom = +2 in the address field
@@ -196,6 +261,19 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             umma_commit(done);                          // accumulator complete
         }
     } else {
+        if (PASSES == 0) {
+            // ===== converters: the landed fp32 X tile -> bf16 (in place) =====
+            const uint32_t t = threadIdx.x - 64;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                tile_to_bf16_inplace<32 * kSplitWarps>(tiles + (uint32_t)s * stage_bytes, BM, t, [] {
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSplitWarps) : "memory");
+                });
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(split0 + 8 * s);
+            }
+        }
         if (PASSES == 3) {
             // ===== splitters: A -> A_hi (in place), A_lo = A - A_hi, element-wise in the swizzled tile =====
             const uint32_t t = threadIdx.x - 64;       // 0..255: 16-byte chunk t, t + 256, ... of the A tile
@@ -332,6 +410,20 @@ int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_ro
     return r == CUDA_SUCCESS ? GPT_OK : GPT_ERR_DRIVER;
 }
 
+// row-major bf16 [rows, cols] -> boxes of [box_rows x 32] elements (64-byte rows), 64-byte swizzle, zero fill
+int make_map_bf16(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return GPT_ERR_DRIVER;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GPT_OK : GPT_ERR_DRIVER;
+}
+
 __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
                                   size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,7 +439,7 @@ __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restric
 template <int PASSES>
 int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
                 int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st, const MaskEpilogue& ep) {
-    const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * 4);
+    const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * (PASSES == 0 ? 2 : 4));
     int stages = (int)((200 * 1024) / stage);
     const int nkb = (K + BK - 1) / BK;
     stages = stages > kMaxStages ? kMaxStages : stages;
@@ -466,6 +558,71 @@ int transpose(const float* w, float* wt, int N, int K, cudaStream_t st) {
 }
 
 }  // namespace
+
+namespace {
+
+// C[M,N] = bf16(A[M,K]) . B16[N,K]^T with B16 already bf16 (gpt_weight_prep_bf16); fp32 accumulation
+int run_bf16_gemm(const float* A, const void* B16, float* C, int M, int N, int K, cudaStream_t st) {
+    if (M == 0) return GPT_OK;
+    if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B16) & 15))
+        return GPT_ERR_UNSUPPORTED;              // TMA: 16-byte aligned bases and row pitches (bf16 rows: K % 8)
+    const MaskEpilogue ep{nullptr, nullptr, 1.f, 1};
+    {
+        const int rc = persist::run_bf16(A, B16, C, M, N, K, st, ep);
+        if (rc != GPT_ERR_UNSUPPORTED) return rc;
+    }
+    const int m_tiles = (M + BM - 1) / BM;
+    int cap = 256;
+    while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
+    const int n_tiles = (N + cap - 1) / cap;
+    int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+    if (n_tile < 16) n_tile = 16;
+    int tmem_cols = 32;
+    while (tmem_cols < n_tile) tmem_cols <<= 1;
+    alignas(64) CUtensorMap tm_a, tm_b;
+    int rc = make_map(&tm_a, A, M, K, BM);
+    if (rc != GPT_OK) return rc;
+    if ((rc = make_map_bf16(&tm_b, B16, N, K, n_tile)) != GPT_OK) return rc;
+    return launch_gemm<0>(tm_a, tm_b, tm_b, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep);
+}
+
+// w [N,K] fp32 -> ws16 = [ bf16(w) [N,K] | bf16(w^T) [K,N] ]  (2*N*K bf16 = N*K floats of workspace)
+__global__ void weight_prep_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws, int N, int K) {
+    __shared__ float t[32][33];
+    const size_t nk = (size_t)N * K;
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        if (x < K && y0 + j < N) {
+            const float v = w[(size_t)(y0 + j) * K + x];
+            ws[(size_t)(y0 + j) * K + x] = __float2bfloat16_rn(v);
+            t[j][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (ox < N && oy0 + j < K) ws[nk + (size_t)(oy0 + j) * N + ox] = __float2bfloat16_rn(t[threadIdx.x][j]);
+}
+
+}  // namespace
+
+extern "C" int gpt_weight_prep_bf16(const float* w, void* ws, int N, int K, void* stream) {
+    GPT_CHECK_ARG(w && ws && N >= 1 && K >= 1);
+    weight_prep_bf16_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(ws), N, K);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_linear_fwd_bf16(const float* x, const void* ws, float* y, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(x && ws && y && M >= 0 && N >= 1 && K >= 1);
+    return run_bf16_gemm(x, ws, y, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_linear_dgrad_bf16(const float* dy, const void* ws, float* dx, int M, int N, int K, void* stream) {
+    GPT_CHECK_ARG(dy && ws && dx && M >= 0 && N >= 1 && K >= 1);
+    const __nv_bfloat16* wt = reinterpret_cast<const __nv_bfloat16*>(ws) + (size_t)N * K;     // bf16(w^T) [K, N]
+    return run_bf16_gemm(dy, wt, dx, M, K, N, (cudaStream_t)stream);
+}
 
 extern "C" int gpt_gemm_persist_config(int cta_group, long long min_rows) {
     GPT_CHECK_ARG(cta_group >= 0 && cta_group <= 2 && min_rows >= 0);

@@ -149,20 +149,28 @@ def gemm_persist_config(cta_group=2, min_rows=65536):
     _lib.check(_lib.lib().gpt_gemm_persist_config(int(cta_group), int(min_rows)), 'gpt_gemm_persist_config')
 
 
+def _bf16_ok(*dims):
+    return all(d % 8 == 0 for d in dims)
+
+
 def weight_prep_buffer(weight, mode):
     N, K = weight.shape
+    if mode == 'bf16' and _bf16_ok(N, K):
+        return torch.empty((2, N * K), dtype=torch.bfloat16, device=weight.device)      # [bf16(w) | bf16(w^T)]
     if mode != 'tf32x3' or not _tf32_ok(N, K):
         return None
     return torch.empty((4, N * K), dtype=torch.float32, device=weight.device)
 
 
 def weight_prep(weight, mode, out=None):
-    """Per-step operand preparation of the 3xTF32 projection: [w_hi | w_lo | w^T_hi | w^T_lo]; None otherwise."""
+    """Per-step operand preparation: 3xTF32 -> [w_hi | w_lo | w^T_hi | w^T_lo] (fp32); bf16 -> [bf16(w) | bf16(w^T)];
+    None for the modes / shapes that read the weight as it is."""
     N, K = weight.shape
     ws = weight_prep_buffer(weight, mode) if out is None else out
     if ws is None:
         return None
-    _call('gpt_weight_prep_tf32x3', _ptr(weight), _ptr(ws), N, K, _stream())
+    _call('gpt_weight_prep_bf16' if ws.dtype == torch.bfloat16 else 'gpt_weight_prep_tf32x3', _ptr(weight), _ptr(ws), N,
+          K, _stream())
     return ws
 
 
@@ -170,10 +178,10 @@ def weight_prep_all(weights, mode, outs):
     """weight_prep for every layer in one launch; layers whose shape has no tensor-core path (out is None) are skipped."""
     import ctypes
     todo = [(w, o) for w, o in zip(weights, outs) if o is not None]
-    if mode != 'tf32x3' or not todo:
+    if mode not in ('tf32x3', 'bf16') or not todo:
         return
     n = len(todo)
-    if n > 8:
+    if n > 8 or mode == 'bf16':
         for w, o in todo:
             weight_prep(w, mode, out=o)
         return
@@ -183,20 +191,23 @@ def weight_prep_all(weights, mode, outs):
 
 
 def linear_fwd(x2d, weight, mode='fp32', ws=None):
-    """y = x W^T.  'tf32x3': tcgen05/TMEM GEMM fed by TMA, 3xTF32 (fp32-grade); 'tf32': one TF32 pass; 'fp32': FFMA.
-    The tensor-core modes fall back to FFMA when the shape cannot be described to TMA (row pitch % 16 B != 0)."""
+    """y = x W^T.  'tf32x3': tcgen05/TMEM GEMM fed by TMA, 3xTF32 (fp32-grade); 'tf32': one TF32 pass; 'bf16': operands
+    rounded to bf16 (kind::f16), fp32 accumulation; 'fp32': FFMA.  The tensor-core modes fall back to FFMA when the shape
+    cannot be described to TMA (row pitch % 16 B != 0)."""
     M, K = x2d.shape
     N = weight.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     if mode not in GEMM_MODES:
         raise _lib.GptError('unknown gemm mode %r' % mode)
-    if mode == 'tf32x3' and ws is None:
+    if mode in ('tf32x3', 'bf16') and ws is None:
         ws = weight_prep(weight, mode)
     if mode == 'tf32' and _tf32_ok(K):
         _call('gpt_linear_fwd_tf32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
     elif mode == 'tf32x3' and ws is not None:
         _call('gpt_linear_fwd_tf32x3', _ptr(x2d), _ptr(ws), _ptr(y), M, N, K, _stream())
-    elif mode in ('fp32', 'tf32', 'tf32x3'):
+    elif mode == 'bf16' and ws is not None:
+        _call('gpt_linear_fwd_bf16', _ptr(x2d), _ptr(ws), _ptr(y), M, N, K, _stream())
+    elif mode in ('fp32', 'tf32', 'tf32x3', 'bf16'):
         _call('gpt_linear_fwd_f32', _ptr(x2d), _ptr(weight), _ptr(y), M, N, K, _stream())
     else:
         raise _lib.GptError('gemm mode %r not built' % mode)
@@ -207,13 +218,15 @@ def linear_dgrad(dy, weight, mode='fp32', ws=None):
     M, N = dy.shape
     K = weight.shape[1]
     dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-    if mode == 'tf32x3' and ws is None:
+    if mode in ('tf32x3', 'bf16') and ws is None:
         ws = weight_prep(weight, mode)
     if mode == 'tf32' and _tf32_ok(N, K):
         wt = torch.empty((K, N), dtype=torch.float32, device=dy.device)
         _call('gpt_linear_dgrad_tf32', _ptr(dy), _ptr(weight), _ptr(dx), _ptr(wt), M, N, K, _stream())
     elif mode == 'tf32x3' and ws is not None:
         _call('gpt_linear_dgrad_tf32x3', _ptr(dy), _ptr(ws), _ptr(dx), M, N, K, _stream())
+    elif mode == 'bf16' and ws is not None:
+        _call('gpt_linear_dgrad_bf16', _ptr(dy), _ptr(ws), _ptr(dx), M, N, K, _stream())
     else:
         _call('gpt_linear_dgrad_f32', _ptr(dy), _ptr(weight), _ptr(dx), M, N, K, _stream())
     return dx
@@ -234,7 +247,7 @@ def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False, flags=None):
     M, N = dy.shape
     K = x2d.shape[1]
     dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
-    if accumulate and mode == 'tf32x3' and wgrad_tc_ok(M, N, K):
+    if accumulate and mode in ('tf32x3', 'bf16') and wgrad_tc_ok(M, N, K):      # (the weight gradient stays 3xTF32)
         # long reductions: tensor cores (3xTF32), the row range split over the SMs
         _call('gpt_linear_wgrad_tf32x3', _ptr(dy), _ptr(x2d), _ptr(flags), _ptr(dw), M, N, K, _stream())
         return dw
@@ -826,7 +839,7 @@ def linear_dgrad_masked(dy, weight, ws, act_prev, csr, p_drop_prev):
     """K3 dgrad (3xTF32) writing g of the previous layer instead of dx; None when the shape is not TMA-describable."""
     M, N = dy.shape
     K = weight.shape[1]
-    if ws is None or not _tf32_ok(N, K):
+    if ws is None or ws.dtype != torch.float32 or not _tf32_ok(N, K):
         return None
     g = torch.empty((M, K), dtype=torch.float32, device=dy.device)
     _call('gpt_linear_dgrad_tf32x3_masked', _ptr(dy), _ptr(ws), _ptr(g), _ptr(act_prev), _ptr(csr.denom),

@@ -165,6 +165,14 @@ int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* dx, int M, 
  *     behind the same four entry points: CTA pairs (tcgen05.mma.cta_group::2, M = 256), two accumulators in tensor
  *     memory, TMA-store epilogue.  cta_group: 0 = never, 1 = single-CTA tiles, 2 = pairs (default); process-wide. */
 int gpt_gemm_persist_config(int cta_group, long long min_rows);
+/* K3, bf16 operands (GPT_GEMM_BF16; north_star's reduced-precision mode): tcgen05.mma kind::f16 with A and B rounded to
+ *     bfloat16 (round-to-nearest-even), fp32 accumulation in TMEM -- ~4e-3 relative per product, logits within ~3e-2 of
+ *     the fp32 path (tolerance written in tests/test_gpu_bf16.py).  X stays fp32 in HBM and is rounded in shared memory
+ *     after the TMA load; gpt_weight_prep_bf16 writes ws = bf16 [2*N*K] ([bf16(w) | bf16(w^T)]) once per step.
+ *     Needs K % 8 == 0 (fwd) / N % 8 == 0 (dgrad).  The weight gradient of this mode stays 3xTF32. */
+int gpt_weight_prep_bf16(const float* w, void* ws, int N, int K, void* stream);
+int gpt_linear_fwd_bf16(const float* x, const void* ws, float* y, int M, int N, int K, void* stream);
+int gpt_linear_dgrad_bf16(const float* dy, const void* ws, float* dx, int M, int N, int K, void* stream);
 /* dgrad with the previous layer's K2-backward prologue in the epilogue: g = (dy . w) * drop_scale_prev *
  * [out_prev > 0] / denom, act_prev in K2's bit layout over the K columns of dx, rows = B*T sentences of T tokens */
 int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, const uint32_t* act_prev,
