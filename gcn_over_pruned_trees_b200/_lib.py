@@ -51,6 +51,9 @@ SIGNATURES = {
     'gpt_embed_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p],
     'gpt_embed_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p,
                       _c_u32, _p],
+    'gpt_embed_bwd_grouped_workspace': [_c_int, _c_int],
+    'gpt_embed_bwd_grouped': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p,
+                              _c_u32, _p, _p],
     'gpt_embed_rows_sqnorm': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_embed_rows_sgd': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _p],
     'gpt_head_fwd_bwd': [_p, _p, _p, _p, _c_int, _p, _p, _c_int, _c_int, _c_int, _c_f, _c_int, _p, _p, _p, _p, _p, _p,
@@ -108,6 +111,7 @@ def lib():
         handle.gpt_launch_count.restype = ctypes.c_ulonglong
         handle.gpt_dp_region_bytes.restype = ctypes.c_longlong
         handle.gpt_predict_result_bytes.restype = ctypes.c_longlong
+        handle.gpt_embed_bwd_grouped_workspace.restype = ctypes.c_longlong
         handle.gpt_error_string.argtypes = [_c_int]
         handle.gpt_error_string.restype = ctypes.c_char_p
         _lib = handle

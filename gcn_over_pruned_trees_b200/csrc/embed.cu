@@ -161,6 +161,195 @@ embed_bwd_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned
     }
 }
 
+// ---- word-embedding gradient of LARGE batches: group the token rows by word, then one plain sum per word -----------------
+// At the large shape (2 M tokens over a 50 k vocabulary) the scatter above is 157 M 16-byte reductions into a 60 MB
+// table: 10.2 ms, bound by L2 reduction throughput, not by the 3 GB of dX it reads.  Grouped: a counting sort of the live
+// token rows by word id (count -> scan -> fill; integer atomics on 50 k counters), then one warp per word adds its ~40
+// rows of dX in registers (dropout mask re-derived per row, as above) and touches G[w] once: the kernel streams dX at HBM
+// speed and issues no floating-point atomic at all.  (The order of a word's rows inside its group depends on the fill's
+// atomics, like the order of the reductions it replaces.)
+__global__ void __launch_bounds__(256)
+emb_group_zero_kernel(int* __restrict__ count, int n) {
+    GPT_PDL_ENTER();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) count[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+emb_group_count_kernel(const long long* __restrict__ words, const unsigned char* __restrict__ flags, int n_rows, int topn,
+                       int* __restrict__ count) {
+    GPT_PDL_ENTER();
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+        if (flags != nullptr && flags[row] == 0) continue;
+        const long long w = words[row];
+        if (w != 0 && w < topn) atomicAdd(count + w, 1);
+    }
+}
+
+// start[w] = number of live rows of words < w (start[V] = total); cursor[w] = start[w].  One CTA.
+__global__ void __launch_bounds__(1024)
+emb_group_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, int* __restrict__ cursor) {
+    GPT_PDL_ENTER();
+    __shared__ int s_sum[1024];
+    const int per = (V + 1023) / 1024, lo = threadIdx.x * per, hi = min(V, lo + per);
+    int t = 0;
+    for (int i = lo; i < hi; ++i) t += count[i];
+    s_sum[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {            // inclusive scan of the per-thread totals
+        const int v = threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_sum[threadIdx.x] - t;
+    for (int i = lo; i < hi; ++i) {
+        start[i] = run;
+        cursor[i] = run;
+        run += count[i];
+    }
+    if (threadIdx.x == 1023) start[V] = s_sum[1023];
+}
+
+__global__ void __launch_bounds__(256)
+emb_group_fill_kernel(const long long* __restrict__ words, const unsigned char* __restrict__ flags, int n_rows, int topn,
+                      int* __restrict__ cursor, int* __restrict__ rows_sorted) {
+    GPT_PDL_ENTER();
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+        if (flags != nullptr && flags[row] == 0) continue;
+        const long long w = words[row];
+        if (w != 0 && w < topn) rows_sorted[atomicAdd(cursor + w, 1)] = row;
+    }
+}
+
+// one warp per word: G[w] += sum over the word's rows of mask(row) * dX[row, :E];  owner[w] = its smallest row.
+// Lane l serves the 8-column groups l and l + 32 (E <= 512); needs E % 4 == 0 and (E + Dp + Dn) % 4 == 0 (16-byte loads).
+__global__ void __launch_bounds__(256)
+emb_group_sum_kernel(const EmbParams p, const float* __restrict__ dx, const int* __restrict__ start,
+                     const int* __restrict__ rows_sorted, float* __restrict__ g_emb, int* __restrict__ owner) {
+    GPT_PDL_ENTER();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int D = p.E + p.Dp + p.Dn;
+    const bool drop = p.thresh16 > 0;
+    unsigned long long seed = 0, step = 0;
+    if (drop) { seed = p.rng[0]; step = p.rng[1]; }
+    const int ng = (p.E + 7) >> 3;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < p.V; w += warps) {
+        const int s0 = start[w], n = start[w + 1] - s0;
+        if (n == 0) continue;                                           // warp-uniform
+        float acc[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
+        int min_row = 0x7fffffff;
+        for (int i = 0; i < n; ++i) {
+            const int row = rows_sorted[s0 + i];
+            min_row = min(min_row, row);
+            const float* dr = dx + (size_t)row * D;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int g = lane + 32 * u;
+                if (g >= ng) break;
+                const int c = g * 8;
+                const float4 a = *reinterpret_cast<const float4*>(dr + c);
+                const float4 b = c + 4 < p.E ? *reinterpret_cast<const float4*>(dr + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                if (drop) {
+                    const Philox4 q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step,
+                                                 (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+                    const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                        v[k] = bits >= p.thresh16 ? v[k] * p.drop_scale : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[u][k] += v[k];
+            }
+        }
+        float* gr = g_emb + (size_t)w * p.E;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int g = lane + 32 * u;
+            if (g >= ng) break;
+            const int c = g * 8;
+            float4* q0 = reinterpret_cast<float4*>(gr + c);
+            float4 t = *q0;
+            t.x += acc[u][0]; t.y += acc[u][1]; t.z += acc[u][2]; t.w += acc[u][3];
+            *q0 = t;
+            if (c + 4 < p.E) {
+                float4* q1 = reinterpret_cast<float4*>(gr + c + 4);
+                float4 t1 = *q1;
+                t1.x += acc[u][4]; t1.y += acc[u][5]; t1.z += acc[u][6]; t1.w += acc[u][7];
+                *q1 = t1;
+            }
+        }
+        if (lane == 0 && owner != nullptr) owner[w] = min(owner[w], min_row);
+    }
+}
+
+// The POS / NER columns of dX (the last Dp + Dn of every row) for large batches: a thread serves one 8-column group of
+// one row, so every thread of the CTA is busy (the scatter kernel's row loop leaves 120 of its 128 threads idle on these
+// 60 columns); gradients meet in shared memory (ids < kSmallIds) and every touched entry is flushed once per CTA.
+__global__ void __launch_bounds__(256)
+emb_small_tables_kernel(const EmbParams p, const float* __restrict__ dx, const unsigned char* __restrict__ flags,
+                        float* __restrict__ g_pos, float* __restrict__ g_ner) {
+    GPT_PDL_ENTER();
+    extern __shared__ float s_small[];                   // [kSmallIds][Dp] then [kSmallIds][Dn]
+    float* s_pos = s_small;
+    float* s_ner = s_small + kSmallIds * p.Dp;
+    for (int i = threadIdx.x; i < kSmallIds * (p.Dp + p.Dn); i += blockDim.x) s_small[i] = 0.f;
+    __syncthreads();
+    const int D = p.E + p.Dp + p.Dn;
+    const int g0 = p.E >> 3, tpr = ((D + 7) >> 3) - g0;              // 8-column groups that hold small-table columns
+    const int rows_per_pass = blockDim.x / tpr;
+    const int lr = threadIdx.x / tpr, g = g0 + threadIdx.x % tpr;
+    const bool drop = p.thresh16 > 0;
+    unsigned long long seed = 0, step = 0;
+    if (drop) { seed = p.rng[0]; step = p.rng[1]; }
+    if (lr < rows_per_pass) {
+        for (long long row = (long long)blockIdx.x * rows_per_pass + lr; row < p.n_rows;
+             row += (long long)gridDim.x * rows_per_pass) {
+            if (flags != nullptr && flags[row] == 0) continue;
+            const long long ps = p.pos_w ? p.pos[row] : 0;
+            const long long nr = p.ner_w ? p.ner[row] : 0;
+            const float* dr = dx + (size_t)row * D;
+            Philox4 q{0, 0, 0, 0};
+            if (drop)
+                q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step, (uint32_t)seed,
+                               (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+            const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int cc = g * 8 + k;
+                if (cc < p.E || cc >= D) continue;
+                float u = dr[cc];
+                if (drop) {
+                    const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                    u = bits >= p.thresh16 ? u * p.drop_scale : 0.f;
+                }
+                if (u == 0.f) continue;
+                if (cc < p.E + p.Dp) {
+                    if (g_pos) {
+                        if (ps < kSmallIds) atomicAdd(s_pos + (int)ps * p.Dp + (cc - p.E), u);
+                        else atomicAdd(g_pos + (size_t)ps * p.Dp + (cc - p.E), u);
+                    }
+                } else if (g_ner) {
+                    if (nr < kSmallIds) atomicAdd(s_ner + (int)nr * p.Dn + (cc - p.E - p.Dp), u);
+                    else atomicAdd(g_ner + (size_t)nr * p.Dn + (cc - p.E - p.Dp), u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSmallIds * p.Dp; i += blockDim.x)
+        if (g_pos && s_pos[i] != 0.f) atomicAdd(g_pos + i, s_pos[i]);
+    for (int i = threadIdx.x; i < kSmallIds * p.Dn; i += blockDim.x)
+        if (g_ner && s_ner[i] != 0.f) atomicAdd(g_ner + i, s_ner[i]);
+}
+
 __global__ void __launch_bounds__(kEmbThreads)
 rows_sqnorm_kernel(const long long* __restrict__ words, const int* __restrict__ owner, const float* __restrict__ g,
                    int n_rows, int E, int topn, float* __restrict__ sq) {
@@ -257,6 +446,53 @@ extern "C" int gpt_embed_bwd(const float* dx, const uint8_t* flags, const int64_
     gpt_launch(embed_bwd_kernel<false>, dim3(n_rows), dim3(kEmbThreads), 0, st, p, dx, flags, g_emb, g_pos, g_ner, owner,
                tn);
     return gpt_launch_status();
+}
+
+extern "C" long long gpt_embed_bwd_grouped_workspace(int n_rows, int V) {      // int32 entries
+    return 3ll * V + 1 + n_rows;
+}
+
+// The same gradients as gpt_embed_bwd for large batches, without floating-point atomics on the word table: the live rows
+// are grouped by word (workspace: gpt_embed_bwd_grouped_workspace(n_rows, V) int32) and each word's rows are summed by one
+// warp; the POS / NER columns go through the shared-memory path of gpt_embed_bwd.  GPT_ERR_UNSUPPORTED when the row
+// widths do not allow 16-byte loads (the caller falls back to gpt_embed_bwd).
+extern "C" int gpt_embed_bwd_grouped(const float* dx, const uint8_t* flags, const int64_t* words, const int64_t* pos,
+                                     const int64_t* ner, float* g_emb, float* g_pos, float* g_ner, int32_t* owner,
+                                     int n_rows, int V, int E, int Dp, int Dn, int topn, float drop_p,
+                                     const uint64_t* rng_state, uint32_t subseq, int32_t* workspace, void* stream) {
+    EmbParams p{};
+    int rc = fill_params(p, words, pos, ner, dx, Dp > 0 ? dx : nullptr, Dn > 0 ? dx : nullptr, n_rows, V, E, Dp, Dn,
+                         drop_p, rng_state, subseq);
+    if (rc != GPT_OK || dx == nullptr || g_emb == nullptr || workspace == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
+    if (n_rows == 0) return GPT_OK;
+    const int D = E + Dp + Dn;
+    if (E % 4 != 0 || D % 4 != 0 || E > 512 || (reinterpret_cast<uintptr_t>(dx) & 15) || (reinterpret_cast<uintptr_t>(g_emb) & 15))
+        return GPT_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)kSmallIds * (Dp + Dn) * sizeof(float);
+    if (smem > 48 * 1024) return GPT_ERR_UNSUPPORTED;
+    const cudaStream_t st = (cudaStream_t)stream;
+    const int tn = topn < V ? topn : V;
+    int* count = workspace;
+    int* start = workspace + V;             // [V + 1]
+    int* cursor = start + V + 1;            // [V]
+    int* rows_sorted = cursor + V;          // [n_rows]
+    const long long* w64 = reinterpret_cast<const long long*>(words);
+    gpt_launch(emb_group_zero_kernel, dim3(64), dim3(256), 0, st, count, V);
+    if ((rc = gpt_launch_status()) != GPT_OK) return rc;
+    gpt_launch(emb_group_count_kernel, dim3(148 * 8), dim3(256), 0, st, w64, flags, n_rows, tn, count);
+    if ((rc = gpt_launch_status()) != GPT_OK) return rc;
+    gpt_launch(emb_group_scan_kernel, dim3(1), dim3(1024), 0, st, (const int*)count, V, start, cursor);
+    if ((rc = gpt_launch_status()) != GPT_OK) return rc;
+    gpt_launch(emb_group_fill_kernel, dim3(148 * 8), dim3(256), 0, st, w64, flags, n_rows, tn, cursor, rows_sorted);
+    if ((rc = gpt_launch_status()) != GPT_OK) return rc;
+    gpt_launch(emb_group_sum_kernel, dim3(148 * 8), dim3(256), 0, st, p, dx, (const int*)start, (const int*)rows_sorted,
+               g_emb, owner);
+    if ((rc = gpt_launch_status()) != GPT_OK) return rc;
+    if ((g_pos != nullptr || g_ner != nullptr) && Dp + Dn > 0) {     // the POS / NER columns: every thread busy
+        gpt_launch(emb_small_tables_kernel, dim3(148 * 4), dim3(256), smem, st, p, dx, flags, g_pos, g_ner);
+        rc = gpt_launch_status();
+    }
+    return rc;
 }
 
 extern "C" int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner, const float* g_emb, int n_rows, int E,

@@ -636,9 +636,8 @@ class _EmbedConcat(torch.autograd.Function):
         else:
             g_emb = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev) if want_emb else None
             owner, ret_emb = None, g_emb
-        _call('gpt_embed_bwd', _ptr(dx), _ptr(flags), _ptr(words), _ptr(pos if Dp else None),
-              _ptr(ner if Dn else None), _ptr(g_emb), _ptr(g_pos), _ptr(g_ner), _ptr(owner), n_rows, V, E, Dp, Dn,
-              topn, drop_p, _ptr(rng_state if drop_p > 0 else None), subseq, _stream())
+        embed_bwd(dx, flags, words, pos if Dp else None, ner if Dn else None, g_emb, g_pos, g_ner, owner, V, E, topn,
+                  drop_p, rng_state, subseq)
         return None, None, None, ret_emb, g_pos, g_ner, None, None, None, None, None, None
 
 
@@ -673,10 +672,22 @@ def embed_fwd(words, pos, ner, emb_w, pos_w, ner_w, drop_p, rng_state, subseq):
     return x
 
 
+EMBED_GROUPED_MIN_ROWS = int(_os.environ.get('GPT_EMBED_GROUPED_MIN_ROWS', 65536))
+
+
 def embed_bwd(dx, flags, words, pos, ner, g_emb, g_pos, g_ner, owner, V, E, topn, drop_p, rng_state, subseq):
-    """K5 backward: scatter-add into caller-zeroed tables (any of g_emb / g_pos / g_ner may be None)."""
+    """K5 backward: scatter-add into caller-zeroed tables (any of g_emb / g_pos / g_ner may be None).  Large batches group
+    the token rows by word first and sum each word's rows once (no floating-point atomics on the word table)."""
     Dp = g_pos.shape[1] if g_pos is not None else 0
     Dn = g_ner.shape[1] if g_ner is not None else 0
+    n_rows = words.numel()
+    if g_emb is not None and n_rows >= EMBED_GROUPED_MIN_ROWS and E % 4 == 0 and (E + Dp + Dn) % 4 == 0 and E <= 512 \
+            and Dp + Dn <= 192:
+        ws = torch.empty(int(_lib.lib().gpt_embed_bwd_grouped_workspace(n_rows, V)), dtype=torch.int32, device=dx.device)
+        _call('gpt_embed_bwd_grouped', _ptr(dx), _ptr(flags), _ptr(words), _ptr(pos if Dp else None),
+              _ptr(ner if Dn else None), _ptr(g_emb), _ptr(g_pos), _ptr(g_ner), _ptr(owner), n_rows, V, E, Dp, Dn,
+              int(topn), float(drop_p), _ptr(rng_state if drop_p > 0 else None), int(subseq), _ptr(ws), _stream())
+        return
     _call('gpt_embed_bwd', _ptr(dx), _ptr(flags), _ptr(words), _ptr(pos if Dp else None), _ptr(ner if Dn else None),
           _ptr(g_emb), _ptr(g_pos), _ptr(g_ner), _ptr(owner), words.numel(), V, E, Dp, Dn, int(topn), float(drop_p),
           _ptr(rng_state if drop_p > 0 else None), int(subseq), _stream())

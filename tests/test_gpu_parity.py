@@ -622,3 +622,38 @@ def test_device_resident_bilstm_equals_the_packed_sequence_path(layers, monkeypa
     for n, p in model.rnn.named_parameters():
         assert float((ga[n] - p.grad).abs().max()) <= 1e-4 * max(1.0, float(p.grad.abs().max())), n
     assert float((x1.grad - x2.grad).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize('n,V,E,Dp,Dn,p,topn', [(70_001, 500, 300, 30, 30, 0.5, 500), (131_072, 3000, 300, 30, 0, 0.0, 2000),
+                                                (66_000, 50, 64, 8, 8, 0.3, 50), (65_536, 800, 300, 0, 0, 0.5, 800)])
+def test_k5_grouped_backward_equals_the_scatter_backward(n, V, E, Dp, Dn, p, topn):
+    """Large batches: rows grouped by word and summed once per word (no fp atomics on the word table) == the scatter
+    kernel: same dropout masks (re-derived per row from {seed, step}), unobservable rows skipped, padding row and rows
+    >= topn untouched, owner = the word's first live row, gradients ADDED to what the buffers hold."""
+    g = torch.Generator(device=DEV).manual_seed(n + V)
+    words = torch.randint(0, V, (n,), device=DEV, generator=g)
+    pos = torch.randint(0, 47, (n,), device=DEV, generator=g) if Dp else None
+    ner = torch.randint(0, 15, (n,), device=DEV, generator=g) if Dn else None
+    flags = (torch.rand(n, device=DEV, generator=g) < 0.6).to(torch.uint8)
+    dx = torch.randn(n, E + Dp + Dn, device=DEV, generator=g)
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device=DEV)
+    outs = []
+    for min_rows in (1 << 30, 65536):                        # scatter, then grouped
+        ops.EMBED_GROUPED_MIN_ROWS = min_rows
+        G = torch.full((V, E), 0.25, device=DEV)            # not zero: both paths must accumulate
+        gp = torch.zeros(47, Dp, device=DEV) if Dp else None
+        gn = torch.zeros(15, Dn, device=DEV) if Dn else None
+        owner = torch.full((V,), 0x7fffffff, dtype=torch.int32, device=DEV)
+        ops.embed_bwd(dx, flags, words, pos, ner, G, gp, gn, owner, V, E, topn, p, rng, 0xE0)
+        torch.cuda.synchronize()
+        outs.append((G, gp, gn, owner))
+    ops.EMBED_GROUPED_MIN_ROWS = 65536
+    (G0, gp0, gn0, o0), (G1, gp1, gn1, o1) = outs
+    assert torch.equal(o0, o1)
+    assert float((G0 - 0.25).abs().max()) > 0 and torch.equal(G0[0], torch.full((E,), 0.25, device=DEV))
+    assert torch.equal(G1[topn:], G0[topn:]) and torch.equal(G1[0], G0[0])
+    assert _rel(G1.double().cpu(), G0.double().cpu()) < 2e-5      # ~n/V fp32 additions per entry, in a different order
+    if Dp:
+        assert _rel(gp1.double().cpu(), gp0.double().cpu()) < 2e-5
+    if Dn:
+        assert _rel(gn1.double().cpu(), gn0.double().cpu()) < 2e-5
