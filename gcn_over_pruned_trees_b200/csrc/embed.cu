@@ -69,6 +69,55 @@ embed_fwd_kernel(const EmbParams p, float* __restrict__ x) {
     }
 }
 
+// The same rows for LARGE batches (>= 64 K token rows): one CTA per row means 2 M CTAs of 45 busy threads at the large
+// shape -- 3.2 ms, bound by the rate at which CTAs can be launched, for 3 GB of output.  Here a resident grid walks
+// (row, 8-column group) items with every thread busy; same Philox stream, bit-identical output.
+__global__ void __launch_bounds__(256)
+embed_fwd_rows_kernel(const EmbParams p, float* __restrict__ x) {
+    GPT_PDL_ENTER();
+    const int D = p.E + p.Dp + p.Dn, ng = (D + 7) >> 3;
+    const bool drop = p.thresh16 > 0;
+    unsigned long long seed = 0, step = 0;
+    if (drop) { seed = p.rng[0]; step = p.rng[1]; }
+    const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const long long total = (long long)p.n_rows * ng;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+         it += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(it / ng), g = (int)(it - (long long)row * ng);
+        const long long w = p.words[row];
+        const long long ps = p.pos_w ? p.pos[row] : 0;
+        const long long nr = p.ner_w ? p.ner[row] : 0;
+        Philox4 q{0, 0, 0, 0};
+        if (drop)
+            q = philox4x32((uint32_t)g | (p.subseq << 20), (uint32_t)row, 0x454d4245u, (uint32_t)step, (uint32_t)seed,
+                           (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+        const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            float u = 0.f;
+            if (c < p.E) u = p.emb_w[(size_t)w * p.E + c];
+            else if (c < p.E + p.Dp) u = p.pos_w[(size_t)ps * p.Dp + (c - p.E)];
+            else if (c < D) u = p.ner_w[(size_t)nr * p.Dn + (c - p.E - p.Dp)];
+            if (drop) {
+                const uint32_t bits = (r4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                u = bits >= p.thresh16 ? u * p.drop_scale : 0.f;
+            }
+            v[k] = u;
+        }
+        float* xr = x + (size_t)row * D + g * 8;
+        if (vec && g * 8 + 7 < D) {
+            reinterpret_cast<float4*>(xr)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(xr)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (g * 8 + k < D) xr[k] = v[k];
+        }
+    }
+}
+
 // scatter dX (after the same dropout mask) into the tables; word rows additionally record their first token.
 // MULTI = false: one CTA per token row (TACRED-sized batches: thousands of short CTAs).  MULTI = true (>= 64 K rows):
 // a CTA walks many rows and first collects the gradients of the small tables -- 47 POS and 15 NER rows, i.e. millions of
@@ -419,6 +468,10 @@ extern "C" int gpt_embed_fwd(const int64_t* words, const int64_t* pos, const int
     int rc = fill_params(p, words, pos, ner, emb_w, pos_w, ner_w, n_rows, V, E, Dp, Dn, drop_p, rng_state, subseq);
     if (rc != GPT_OK || x == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
     if (n_rows == 0) return GPT_OK;
+    if (n_rows >= 65536) {
+        gpt_launch(embed_fwd_rows_kernel, dim3(148 * 8), dim3(256), 0, (cudaStream_t)stream, p, x);
+        return gpt_launch_status();
+    }
     gpt_launch(embed_fwd_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream, p, x);
     return gpt_launch_status();
 }

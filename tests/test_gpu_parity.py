@@ -657,3 +657,32 @@ def test_k5_grouped_backward_equals_the_scatter_backward(n, V, E, Dp, Dn, p, top
         assert _rel(gp1.double().cpu(), gp0.double().cpu()) < 2e-5
     if Dn:
         assert _rel(gn1.double().cpu(), gn0.double().cpu()) < 2e-5
+
+
+def test_k5_large_batch_forward_and_grouped_backward_share_one_dropout_stream():
+    """>= 64 K rows: the resident-grid forward (every thread one 8-column group) and the grouped backward re-derive the
+    same Philox mask per (row, column group): d(table) == scatter of (r * keep * scale), keep rate 0.5."""
+    V, E, n = 900, 300, 70_003
+    g = torch.Generator(device=DEV).manual_seed(9)
+    words = torch.randint(0, V, (1, n), device=DEV, generator=g)
+    pos = torch.randint(0, 47, (1, n), device=DEV, generator=g)
+    ner = torch.randint(0, 15, (1, n), device=DEV, generator=g)
+    emb = (torch.rand(V, E, device=DEV, generator=g) + 0.5).requires_grad_()
+    pw = (torch.rand(47, 30, device=DEV, generator=g) + 0.5).requires_grad_()
+    nw = (torch.rand(15, 30, device=DEV, generator=g) + 0.5).requires_grad_()
+    rng = torch.tensor([4321, 11], dtype=torch.int64, device=DEV)
+    x = ops.embed_concat(words, pos, ner, emb, pw, nw, drop_p=0.5, rng_state=rng, subseq=0xE0)
+    keep = x != 0
+    assert abs(keep[0][words[0] != 0].float().mean().item() - 0.5) < 0.01
+    scale = ops.drop_scale(0.5)
+    full = torch.cat([emb.detach()[words], pw.detach()[pos], nw.detach()[ner]], 2)
+    assert torch.equal(x, torch.where(keep, full * scale, torch.zeros_like(full)))
+    r = torch.randn(x.shape, device=DEV, generator=g)
+    (x * r).sum().backward()
+    want = torch.zeros(V, E, device=DEV, dtype=torch.float64)
+    want.index_put_((words.flatten(),), (r * keep * scale)[0, :, :E].double(), accumulate=True)
+    want[0] = 0
+    assert _rel(emb.grad.double().cpu(), want.cpu()) < 1e-5
+    wantp = torch.zeros(47, 30, device=DEV, dtype=torch.float64)
+    wantp.index_put_((pos.flatten(),), (r * keep * scale)[0, :, E:E + 30].double(), accumulate=True)
+    assert _rel(pw.grad.double().cpu(), wantp.cpu()) < 1e-5
