@@ -269,7 +269,9 @@ dp_reduce_kernel(const DpLayout L, const DpPeers P, int rank, int signal, float*
         const unsigned wmask = (1u << W) - 1u;
         // lane = (entry j of the chunk, rank q): one instruction fetches, for every entry, the slot every rank holds
         // for its word
-        const int Wp = dp_pow2(W), chunk = dp_chunk(W);
+        const int Wp = dp_pow2(W);
+        int chunk = 1;                              // entries per warp and pass: as few as the grid allows (see dp_apply_kernel)
+        while (chunk < dp_chunk(W) && (long long)chunk * row_blocks * kDpWarps < total) chunk <<= 1;
         const int jl = lane / Wp, ql = lane - jl * Wp;
         const int stride = row_blocks * kDpWarps * chunk;
         for (int base = (((int)blockIdx.x - dense_blocks) * kDpWarps + warp) * chunk; base < total; base += stride) {
@@ -387,11 +389,17 @@ dp_apply_kernel(const DpLayout L, unsigned char* __restrict__ self, float* __res
         const int E = L.E, E4 = E >> 2;
         const bool vec = (E & 3) == 0 && E4 <= 32 * kDpRowVec;
         const int total = s_off[W];
-        const int stride = row_blocks * kDpWarps * kDpChunk;
-        for (int base = (((int)blockIdx.x - dense_blocks) * kDpWarps + warp) * kDpChunk; base < total; base += stride) {
+        // entries per warp and pass: as few as the grid allows (1 when there are more warps than entries).  A warp serves
+        // its live entries one after the other -- each a round trip to HBM for the embedding row -- so a chunk of 8 with
+        // 3 live entries is 3 dependent latencies where spreading the entries over idle warps costs one.
+        const int warps_total = row_blocks * kDpWarps;
+        int chunk = 1;
+        while (chunk < kDpChunk && (long long)chunk * warps_total < total) chunk <<= 1;
+        const int stride = warps_total * chunk;
+        for (int base = (((int)blockIdx.x - dense_blocks) * kDpWarps + warp) * chunk; base < total; base += stride) {
             const int e = base + lane;
             int r = 0, i = 0, w = -1;                            // w < 0: not live, or folded into a lower rank's entry
-            if (lane < kDpChunk && e < total) {
+            if (lane < chunk && e < total) {
                 dp_entry(s_off, W, e, &r, &i);
                 w = dp_ids(L, self, par, r)[i];
             }
@@ -589,8 +597,11 @@ extern "C" int gpt_dp_apply(void* region, int W, int cap_rows, int E, int V, lon
     if (rc != GPT_OK) return rc;
     const DpLayout L = make_layout(W, cap_rows, E, V, n_flat);
     int d, r;
-    plan(L, &d, &r);
-    gpt_launch(dp_apply_kernel, dim3(d + r), dim3(kDpThreads), 0, (cudaStream_t)stream,
+    plan(L, &d, &r);                            // the reduce kernel's grid: that many partial sums to add
+    // apply keeps 6 CTAs per SM resident: its own, wider single wave (more warps = fewer entries per warp)
+    long long ra = ((long long)L.W * L.cap_rows + kDpWarps - 1) / kDpWarps;
+    if (ra > 6 * 148 - d) ra = 6 * 148 - d;
+    gpt_launch(dp_apply_kernel, dim3(d + (int)ra), dim3(kDpThreads), 0, (cudaStream_t)stream,
                L, reinterpret_cast<unsigned char*>(region), param, flat_g, emb_w, d, partials, d + r, max_norm, lr,
                total_norm, reinterpret_cast<unsigned long long*>(step_counter));
     return gpt_launch_status();
