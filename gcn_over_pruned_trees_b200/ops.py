@@ -237,8 +237,10 @@ WGRAD_TC_MIN_ROWS = int(_os.environ.get('GPT_WGRAD_TC_MIN_ROWS', 32768))   # bel
 
 
 def wgrad_tc_ok(M, N, K):
-    """Shapes csrc/wgrad_tcgen05.cu takes: TMA-describable, accumulator fits tensor memory, reduction long enough."""
-    return M >= WGRAD_TC_MIN_ROWS and K % 4 == 0 and N % 4 == 0 and K <= 512
+    """Shapes csrc/wgrad_tcgen05.cu takes: TMA-describable, accumulator fits tensor memory, and enough work for its
+    persistent CTAs -- a long reduction (the regular layers of large batches) or many 128-row slices of dW (the shared
+    [D*H, in] projection of the relation-aware layers: 79 slices at D = 50, H = 200)."""
+    return (M >= WGRAD_TC_MIN_ROWS or (M >= 1024 and N >= 2048)) and K % 4 == 0 and N % 4 == 0 and K <= 512
 
 
 def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False, flags=None):
@@ -246,11 +248,17 @@ def linear_wgrad(dy, x2d, mode='fp32', out=None, accumulate=False, flags=None):
     with ``flags`` (K1's per-row flags) only rows that carry a gradient are read."""
     M, N = dy.shape
     K = x2d.shape[1]
-    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
-    if accumulate and mode in ('tf32x3', 'bf16') and wgrad_tc_ok(M, N, K):      # (the weight gradient stays 3xTF32)
-        # long reductions: tensor cores (3xTF32), the row range split over the SMs
+    if mode in ('tf32x3', 'bf16') and wgrad_tc_ok(M, N, K):
+        # tensor cores (3xTF32), the row range / the slices of dW split over the SMs; the kernel adds into dw
+        if out is None:
+            dw = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
+        else:
+            dw = out
+            if not accumulate:
+                dw.zero_()
         _call('gpt_linear_wgrad_tf32x3', _ptr(dy), _ptr(x2d), _ptr(flags), _ptr(dw), M, N, K, _stream())
         return dw
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
     if accumulate and flags is not None:
         _call('gpt_linear_wgrad_rows_f32', _ptr(dy), _ptr(x2d), _ptr(flags), _ptr(dw), M, N, K, _stream())
         return dw
