@@ -429,7 +429,11 @@ extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, cons
     p.prefetch = getenv("GPT_HEAD_NOPF") == nullptr;
     p.logits = logits; p.loss_rows = loss_rows; p.acts = acts; p.dacts = dacts; p.dlogits = dlogits; p.dpooled = dpooled;
     // sentences per CTA: 1 while a wave of CTAs fits the machine, then 2 / 4 so that weights are streamed less often
-    const int R = B <= 296 ? 1 : (B <= 1184 ? 2 : 4);
+    int R = B <= 296 ? 1 : (B <= 1184 ? 2 : 4);
+    if (const char* e0 = getenv("GPT_HEAD_R")) {                        // tuning knob (tools/head_bench.py)
+        const int r = atoi(e0);
+        if (r == 1 || r == 2 || r == 4) R = r;
+    }
     const size_t smem = head_smem_bytes(R, H, C, n_mlp);
     if (smem > 200 * 1024) return GPT_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -440,7 +444,9 @@ extern "C" int gpt_head_fwd_bwd(const float* pooled, const int64_t* labels, cons
     const int groups = (B + R - 1) / R;
     // CTAs per sentence group: a pair of CTAs halves the number of dependent round trips to L2 per layer as long as
     // every CTA has an SM to itself (123 registers x 512 threads = one CTA per SM); wider clusters lose more to the
-    // cluster barriers than they gain (tools/head_bench.py: B=50: cs 1 / 2 / 4 -> 33 / 24 / 37 us)
+    // cluster barriers than they gain (tools/head_bench.py: B=50: cs 1 / 2 / 4 -> 33 / 24 / 37 us; two sentences per CTA
+    // with cs = 4 -- the same 100 CTAs, a quarter of the weights each -- also lands on 24.7 us: the layer chain, not the
+    // weight stream, is what bounds it)
     int cs = (R == 1 && groups * 2 <= 148) ? 2 : 1;
     if (const char* e2 = getenv("GPT_HEAD_CS")) cs = atoi(e2) > 0 ? atoi(e2) : cs;   // tuning knob (tools/head_bench.py)
     cudaLaunchConfig_t cfg{};
