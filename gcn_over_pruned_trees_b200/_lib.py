@@ -69,6 +69,7 @@ SIGNATURES = {
     'gpt_dp_free': [_p],
     'gpt_dp_region_init': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p],
     'gpt_dp_push': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _p],
+    'gpt_dp_push_multicast': [_p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _p],
     'gpt_dp_signal': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p],
     'gpt_dp_reduce': [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p],
     'gpt_dp_apply': [_p, _c_int, _c_int, _c_int, _c_int, _c_ll, _p, _p, _p, _p, _c_f, _c_f, _p, _p, _p],

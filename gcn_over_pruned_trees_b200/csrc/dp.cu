@@ -101,6 +101,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// NVSwitch multicast: one store to the multicast mapping of the exchange regions lands in the region of EVERY rank (the
+// switch replicates it), so a rank's contribution leaves its GPU once instead of W - 1 times.  Plain data movement (no
+// in-switch arithmetic): the rank-ordered adds stay local and replicas stay bit-identical.
+__device__ __forceinline__ void mc_st_f4(float* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st_f(float* p, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st_i(int* p, int v) {
+    asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void dp_init_kernel(const DpLayout L, unsigned char* base) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)gridDim.x * blockDim.x;
     int* slot = reinterpret_cast<int*>(base + L.off_slot);
@@ -118,8 +132,9 @@ __global__ void dp_init_kernel(const DpLayout L, unsigned char* base) {
 
 // ---- push ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kDpThreads)
-dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restrict__ flat_g, float* __restrict__ G,
-               int* __restrict__ owner, const long long* __restrict__ words, int n_rows, int topn, int dense_blocks) {
+dp_push_kernel(const DpLayout L, const DpPeers P, unsigned char* __restrict__ mc, int rank,
+               const float* __restrict__ flat_g, float* __restrict__ G, int* __restrict__ owner,
+               const long long* __restrict__ words, int n_rows, int topn, int dense_blocks) {
     GPT_PDL_ENTER();        // launched with programmatic serialization: the grid is resident before the backward's tail ends
     unsigned char* self = P.base[rank];
     const unsigned long long step = *reinterpret_cast<const unsigned long long*>(self + L.off_step);
@@ -130,7 +145,8 @@ dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restr
         const float4* g4 = reinterpret_cast<const float4*>(flat_g);
         for (long long i = (long long)blockIdx.x * kDpThreads + tid; i < n4; i += (long long)dense_blocks * kDpThreads) {
             const float4 v = g4[i];
-            for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(dp_dense(L, P.base[q], par, rank))[i] = v;
+            if (mc != nullptr) mc_st_f4(dp_dense(L, mc, par, rank) + 4 * i, v);
+            else for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(dp_dense(L, P.base[q], par, rank))[i] = v;
         }
     } else {
         const int row_blocks = gridDim.x - dense_blocks;
@@ -139,8 +155,10 @@ dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restr
         for (int i = ((int)blockIdx.x - dense_blocks) * kDpWarps + warp; i < n_rows; i += row_blocks * kDpWarps) {
             const long long w = words[i];
             const bool live = w != 0 && w < topn && owner[w] == i;          // warp-uniform
-            if (lane == 0)
-                for (int q = 0; q < W; ++q) dp_ids(L, P.base[q], par, rank)[i] = live ? (int)w : -1;
+            if (lane == 0) {
+                if (mc != nullptr) mc_st_i(dp_ids(L, mc, par, rank) + i, live ? (int)w : -1);
+                else for (int q = 0; q < W; ++q) dp_ids(L, P.base[q], par, rank)[i] = live ? (int)w : -1;
+            }
             if (!live) continue;
             float* gr = G + (size_t)w * E;
             if ((E & 3) == 0) {
@@ -148,36 +166,48 @@ dp_push_kernel(const DpLayout L, const DpPeers P, int rank, const float* __restr
 #pragma unroll
                 for (int j = 0; j < kDpRowVec; ++j)
                     v[j] = lane + 32 * j < E4 ? reinterpret_cast<float4*>(gr)[lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int q = 0; q < W; ++q) {
-                    float4* dst = reinterpret_cast<float4*>(dp_rows(L, P.base[q], par, rank) + (size_t)i * E);
+                if (mc != nullptr) {
+                    float* dst = dp_rows(L, mc, par, rank) + (size_t)i * E;
 #pragma unroll
                     for (int j = 0; j < kDpRowVec; ++j)
-                        if (lane + 32 * j < E4) dst[lane + 32 * j] = v[j];
+                        if (lane + 32 * j < E4) mc_st_f4(dst + 4 * (lane + 32 * j), v[j]);
+                } else {
+                    for (int q = 0; q < W; ++q) {
+                        float4* dst = reinterpret_cast<float4*>(dp_rows(L, P.base[q], par, rank) + (size_t)i * E);
+#pragma unroll
+                        for (int j = 0; j < kDpRowVec; ++j)
+                            if (lane + 32 * j < E4) dst[lane + 32 * j] = v[j];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < kDpRowVec; ++j)
                     if (lane + 32 * j < E4) reinterpret_cast<float4*>(gr)[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int c = lane + 32 * kDpRowVec; c < E4; c += 32) {      // rows wider than 384 floats
                     const float4 u = reinterpret_cast<float4*>(gr)[c];
-                    for (int q = 0; q < W; ++q)
+                    if (mc != nullptr) mc_st_f4(dp_rows(L, mc, par, rank) + (size_t)i * E + 4 * c, u);
+                    else for (int q = 0; q < W; ++q)
                         reinterpret_cast<float4*>(dp_rows(L, P.base[q], par, rank) + (size_t)i * E)[c] = u;
                     reinterpret_cast<float4*>(gr)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {
                 for (int c = lane; c < E; c += 32) {
                     const float u = gr[c];
-                    for (int q = 0; q < W; ++q) dp_rows(L, P.base[q], par, rank)[(size_t)i * E + c] = u;
+                    if (mc != nullptr) mc_st_f(dp_rows(L, mc, par, rank) + (size_t)i * E + c, u);
+                    else for (int q = 0; q < W; ++q) dp_rows(L, P.base[q], par, rank)[(size_t)i * E + c] = u;
                     gr[c] = 0.f;
                 }
             }
             if (lane == 0) {
-                for (int q = 0; q < W; ++q) dp_slot(L, P.base[q], par, rank)[w] = i;
+                if (mc != nullptr) mc_st_i(dp_slot(L, mc, par, rank) + w, i);
+                else for (int q = 0; q < W; ++q) dp_slot(L, P.base[q], par, rank)[w] = i;
                 owner[w] = 0x7fffffff;
             }
         }
     }
-    if (blockIdx.x == 0 && tid == 0)
-        for (int q = 0; q < W; ++q) dp_nrows(L, P.base[q], par)[rank] = n_rows;
+    if (blockIdx.x == 0 && tid == 0) {
+        if (mc != nullptr) mc_st_i(dp_nrows(L, mc, par) + rank, n_rows);
+        else for (int q = 0; q < W; ++q) dp_nrows(L, P.base[q], par)[rank] = n_rows;
+    }
     // no fence here: the flags are raised by the NEXT kernel in stream order (dp_signal_kernel, or CTA 0 of
     // dp_reduce_kernel), i.e. after this grid has completed and its stores have drained
 }
@@ -523,9 +553,9 @@ extern "C" int gpt_dp_region_init(void* region, int W, int cap_rows, int E, int 
     return gpt_launch_status();
 }
 
-extern "C" int gpt_dp_push(void* const* regions, int rank, int W, int cap_rows, int E, int V, long long n_flat,
-                           const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words, int n_rows,
-                           int topn, void* stream) {
+static int dp_push_impl(void* const* regions, void* multicast, int rank, int W, int cap_rows, int E, int V, long long n_flat,
+                        const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words, int n_rows,
+                        int topn, void* stream) {
     GPT_CHECK_ARG(regions && flat_g && rank >= 0 && rank < W && n_rows >= 0);
     GPT_CHECK_ARG(n_rows == 0 || (g_emb && owner && words));
     int rc = check_layout(W, cap_rows, E, V, n_flat);
@@ -544,8 +574,24 @@ extern "C" int gpt_dp_push(void* const* regions, int rank, int W, int cap_rows, 
     if (rb > kDpMaxBlocks - 296) rb = kDpMaxBlocks - 296;      // one warp per token slot
     (void)r;
     gpt_launch(dp_push_kernel, dim3(d + rb), dim3(kDpThreads), 0, (cudaStream_t)stream,
-               L, P, rank, flat_g, g_emb, owner, reinterpret_cast<const long long*>(words), n_rows, topn, d);
+               L, P, reinterpret_cast<unsigned char*>(multicast), rank, flat_g, g_emb, owner,
+               reinterpret_cast<const long long*>(words), n_rows, topn, d);
     return gpt_launch_status();
+}
+
+extern "C" int gpt_dp_push(void* const* regions, int rank, int W, int cap_rows, int E, int V, long long n_flat,
+                           const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words, int n_rows,
+                           int topn, void* stream) {
+    return dp_push_impl(regions, nullptr, rank, W, cap_rows, E, V, n_flat, flat_g, g_emb, owner, words, n_rows, topn, stream);
+}
+
+// the same push through an NVSwitch multicast mapping of the W regions (multimem.st): every byte leaves the GPU once
+extern "C" int gpt_dp_push_multicast(void* const* regions, void* multicast, int rank, int W, int cap_rows, int E, int V,
+                                     long long n_flat, const float* flat_g, float* g_emb, int32_t* owner,
+                                     const int64_t* words, int n_rows, int topn, void* stream) {
+    GPT_CHECK_ARG(multicast != nullptr && (reinterpret_cast<uintptr_t>(multicast) & 15) == 0);
+    return dp_push_impl(regions, multicast, rank, W, cap_rows, E, V, n_flat, flat_g, g_emb, owner, words, n_rows, topn,
+                        stream);
 }
 
 static int dp_peers(void* const* regions, int W, DpPeers* P) {

@@ -167,7 +167,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
-                 int n_tiles, int tmem_cols, int STAGES, const MaskEpilogue ep) {
+                 int n_tiles, int tmem_cols, int STAGES, const MaskEpilogue ep, int kb_per_split) {
     GPT_PDL_TRIGGER();
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 1];
@@ -177,7 +177,13 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // N tiles of one M tile are neighbours in launch order: they run at the same time and the second read of the A tile
     // is served by L2 instead of HBM
     const int m0 = (int)(blockIdx.x / n_tiles) * BM, n0 = (int)(blockIdx.x % n_tiles) * n_tile;
-    const int nkb = (K + BK - 1) / BK;
+    // split-K (blockIdx.y): a long reduction over few output tiles (the relation-aware layers' data gradient: 3 000 x 200
+    // outputs reduced over D*H = 10 000) is cut into ranges of kb_per_split k-blocks; the partial tiles meet in C through
+    // vector reductions (the launcher zeroes C first)
+    const int nkb_all = (K + BK - 1) / BK;
+    const int kb0 = (int)blockIdx.y * kb_per_split;
+    const int nkb = min(kb_per_split, nkb_all - kb0);
+    const bool split_k = gridDim.y > 1;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_tile * BK * (PASSES == 0 ? 2 : 4);
     // stage layout: [A | A_lo | B | B_lo] (the lo tiles only for PASSES == 3); every tile is 1024-byte aligned
     const uint32_t stage_bytes = (PASSES == 3 ? 2u : 1u) * (a_bytes + b_bytes);
@@ -217,9 +223,9 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (kb >= STAGES) mbar_wait(empty0 + 8 * s, ((kb / STAGES) - 1) & 1);
                 const uint32_t st = tiles + (uint32_t)s * stage_bytes;
                 mbar_expect_tx(full0 + 8 * s, a_bytes + (PASSES == 3 ? 2u : 1u) * b_bytes);
-                tma_load_2d(st, &tm_a, full0 + 8 * s, kb * BK, m0);      // OOB rows / columns arrive as zeros
-                tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, kb * BK, n0);
-                if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, kb * BK, n0);
+                tma_load_2d(st, &tm_a, full0 + 8 * s, (kb0 + kb) * BK, m0);      // OOB rows / columns arrive as zeros
+                tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, (kb0 + kb) * BK, n0);
+                if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, (kb0 + kb) * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -348,7 +354,17 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 for (int j = 0; j < 32; j += 4) {
                     const int c = n0 + c0 + j;
                     if (c0 + j >= n_tile) break;        // n_tile is a multiple of 16, not of 32: stay inside this tile
-                    if (vec_ok && c + 3 < N) {
+                    if (split_k) {
+                        if (vec_ok && c + 3 < N) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + c0 + j),
+                                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (c + i < N) atomicAdd(crow + c0 + j + i, __uint_as_float(v[j + i]));
+                        }
+                    } else if (vec_ok && c + 3 < N) {
                         *reinterpret_cast<float4*>(crow + c0 + j) =
                             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                         __uint_as_float(v[j + 3]));
@@ -438,18 +454,25 @@ __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restric
 
 template <int PASSES>
 int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
-                int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st, const MaskEpilogue& ep) {
+                int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st, const MaskEpilogue& ep, int splits = 1) {
     const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)n_tile * BK * (PASSES == 0 ? 2 : 4));
     int stages = (int)((200 * 1024) / stage);
-    const int nkb = (K + BK - 1) / BK;
+    const int nkb_all = (K + BK - 1) / BK;
+    int kb_per_split = (nkb_all + splits - 1) / splits;
+    splits = (nkb_all + kb_per_split - 1) / kb_per_split;
+    const int nkb = kb_per_split;
     stages = stages > kMaxStages ? kMaxStages : stages;
     stages = stages > nkb ? nkb : stages;
     stages = stages < 1 ? 1 : stages;
     const size_t smem = (size_t)stages * stage + 1024;
     if (int a = gpt_smem_opt_in(tf32_gemm_kernel<PASSES>, smem)) return a;
-    dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles));
+    if (splits > 1) {               // the partial tiles are ADDED into C
+        const cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles), (unsigned)splits);
     gpt_launch(tf32_gemm_kernel<PASSES>, grid, dim3(kGemmThreads), smem, st, tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
-                                                               tmem_cols, stages, ep);
+                                                               tmem_cols, stages, ep, kb_per_split);
     return gpt_launch_status();
 }
 
@@ -468,8 +491,17 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
     // N tile: as wide as possible (A is re-read once per N tile) unless that leaves most SMs idle; a narrower tile
     // also makes the stages smaller, i.e. the ring deeper, which is what hides TMA latency when M is small
     const int m_tiles = (M + BM - 1) / BM;
-    int cap = 256;
-    while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
+    const int nkb_all = (K + BK - 1) / BK;
+    int cap = 256, splits = 1;
+    if (nkb_all >= 64 && (long)m_tiles * ((N + 255) / 256) < 74) {
+        // long reduction, few output tiles: keep the N tile wide (the X tile is loaded and split once per N tile) and
+        // fill the machine by splitting K instead
+        splits = 148 / (m_tiles * ((N + 255) / 256));
+        if (splits > nkb_all / 8) splits = nkb_all / 8;
+        if (splits < 1) splits = 1;
+    } else {
+        while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
+    }
     const int n_tiles = (N + cap - 1) / cap;
     int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;   // UMMA N: multiple of 16 at M = 128, <= 256
     if (n_tile < 16) n_tile = 16;
@@ -480,8 +512,8 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
     if (rc != GPT_OK) return rc;
     if ((rc = make_map(&tm_b, B, N, K, n_tile)) != GPT_OK) return rc;
     if ((rc = make_map(&tm_b_lo, b_lo ? b_lo : B, N, K, n_tile)) != GPT_OK) return rc;
-    if (b_lo != nullptr) return launch_gemm<3>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep);
-    return launch_gemm<1>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep);
+    if (b_lo != nullptr) return launch_gemm<3>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep, splits);
+    return launch_gemm<1>(tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles, tmem_cols, st, ep, splits);
 }
 
 // w [N,K] -> ws = [w_hi | w_lo | wt_hi | wt_lo]  (wt = w^T [K,N]); hi = round_tf32, lo = w - hi

@@ -556,7 +556,7 @@ class FusedTrainStep(object):
                              self.total_norm if clip else None, counter)
         else:                                                 # K8: exchange over peer memory + K7 on the mean
             ex = self.exchange
-            ops.dp_push(ex.ptrs, ex.rank, ex.shape, fl.grad, sp)
+            ops.dp_push(ex.ptrs, ex.rank, ex.shape, fl.grad, sp, multicast=ex.multicast)
             ops.dp_reduce(ex.ptrs, ex.rank, ex.shape, fl.grad, self.partials)
             ops.dp_apply(ex.ptrs[ex.rank], ex.shape, fl.param, fl.grad, self.emb_weight.data, self.partials,
                          self.max_grad_norm, lr, self.total_norm, counter)

@@ -779,26 +779,40 @@ def update_apply(flat_param, flat_grad, sparse, emb_weight, partials, max_norm, 
 # ---- K8: data-parallel exchange over peer memory -----------------------------------------------------------------
 
 class ExchangeRegion(object):
-    """One rank's exchange region (csrc/dp.cu): cudaMalloc'ed by the library, shareable through its cudaIpc handle."""
+    """One rank's exchange region (csrc/dp.cu): cudaMalloc'ed by the library and shareable through its cudaIpc handle, or
+    (``buffer``) a caller-owned device allocation -- e.g. torch symmetric memory, which also comes with an NVSwitch
+    multicast mapping."""
 
-    def __init__(self, world, cap_rows, E, V, n_flat):
+    def __init__(self, world, cap_rows, E, V, n_flat, buffer=None):
         import ctypes
         self.shape = (int(world), int(cap_rows), int(E), int(V), int(n_flat))
-        nbytes = _lib.lib().gpt_dp_region_bytes(*self.shape)
-        if nbytes <= 0:
-            raise _lib.GptError('bad exchange layout %r' % (self.shape,))
-        ptr = ctypes.c_void_p()
-        handle = ctypes.create_string_buffer(64)
-        _lib.check(_lib.lib().gpt_dp_alloc(nbytes, ctypes.byref(ptr), handle), 'gpt_dp_alloc')
-        self.ptr, self.handle, self.nbytes = ptr.value, handle.raw, nbytes
+        nbytes = self.bytes_for(*self.shape)
+        self.buffer = buffer
+        if buffer is not None:
+            if buffer.numel() * buffer.element_size() < nbytes or buffer.data_ptr() % 256:
+                raise _lib.GptError('exchange buffer too small or misaligned')
+            self.ptr, self.handle = buffer.data_ptr(), None
+        else:
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(_lib.lib().gpt_dp_alloc(nbytes, ctypes.byref(ptr), handle), 'gpt_dp_alloc')
+            self.ptr, self.handle = ptr.value, handle.raw
+        self.nbytes = nbytes
         self.n_partials = int(_lib.lib().gpt_dp_partials(*self.shape))
         _call('gpt_dp_region_init', self.ptr, *self.shape, _stream())
         torch.cuda.current_stream().synchronize()
 
+    @staticmethod
+    def bytes_for(world, cap_rows, E, V, n_flat):
+        nbytes = _lib.lib().gpt_dp_region_bytes(int(world), int(cap_rows), int(E), int(V), int(n_flat))
+        if nbytes <= 0:
+            raise _lib.GptError('bad exchange layout %r' % ((world, cap_rows, E, V, n_flat),))
+        return int(nbytes)
+
     def free(self):
-        if self.ptr:
+        if self.ptr and self.buffer is None:
             _lib.lib().gpt_dp_free(self.ptr)
-            self.ptr = None
+        self.ptr = self.buffer = None
 
 
 def open_peer_region(handle):
@@ -809,13 +823,18 @@ def open_peer_region(handle):
     return ptr.value
 
 
-def dp_push(region_ptrs, rank, shape, flat_grad, sparse):
+def dp_push(region_ptrs, rank, shape, flat_grad, sparse, multicast=None):
+    """multicast: the NVSwitch multicast address of the W regions (one multimem.st reaches every rank) or None (one store
+    per peer)."""
     import ctypes
     arr = (ctypes.c_void_p * len(region_ptrs))(*region_ptrs)
     n_rows = sparse.words.numel() if sparse is not None else 0
-    _call('gpt_dp_push', arr, rank, *shape, _ptr(flat_grad), _ptr(sparse.G if sparse else None),
-          _ptr(sparse.owner if sparse else None), _ptr(sparse.words if sparse else None), n_rows,
-          sparse.topn if sparse else 0, _stream())
+    tail = (_ptr(flat_grad), _ptr(sparse.G if sparse else None), _ptr(sparse.owner if sparse else None),
+            _ptr(sparse.words if sparse else None), n_rows, sparse.topn if sparse else 0, _stream())
+    if multicast:
+        _call('gpt_dp_push_multicast', arr, int(multicast), rank, *shape, *tail)
+    else:
+        _call('gpt_dp_push', arr, rank, *shape, *tail)
 
 
 def dp_signal(region_ptrs, rank, shape):

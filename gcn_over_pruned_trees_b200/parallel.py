@@ -121,13 +121,49 @@ class PeerExchange(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.world > 8:
             raise ValueError('PeerExchange is a single-node (<= 8 GPU) exchange')
-        self.region = ops.ExchangeRegion(self.world, cap_rows, emb_dim, vocab, n_flat)
+        self.multicast = None           # NVSwitch multicast address of the W regions, when the fabric offers one
+        self.symm = None
+        self.region = None
+        if self.world > 1 and os.environ.get('GPT_DP_SYMM', '1') != '0':
+            self._try_symmetric_memory(cap_rows, emb_dim, vocab, n_flat, group)
+        if self.region is None:
+            # cudaMalloc + cudaIpc: every rank allocates, the 64-byte handles travel through the process group once
+            self.region = ops.ExchangeRegion(self.world, cap_rows, emb_dim, vocab, n_flat)
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, self.region.handle, group=group)
+            self.ptrs = [self.region.ptr if r == self.rank else ops.open_peer_region(handles[r])
+                         for r in range(self.world)]
         self.shape = self.region.shape
         self.n_partials = self.region.n_partials
-        handles = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(handles, self.region.handle, group=group)
-        self.ptrs = [self.region.ptr if r == self.rank else ops.open_peer_region(handles[r])
-                     for r in range(self.world)]
         if self.world > 1:
             dist.barrier(group=group)
+
+    def _try_symmetric_memory(self, cap_rows, emb_dim, vocab, n_flat, group):
+        """Regions in torch symmetric memory (plumbing: cuMemCreate + fabric handles + cuMulticast*): same peer pointers
+        as the cudaIpc path, plus a multicast address when the devices sit behind an NVSwitch.  Collective; every rank
+        must reach the same verdict, so the outcome is agreed on with an all-reduce before it is used."""
+        from . import ops
+        ok, buf, hdl = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = ops.ExchangeRegion.bytes_for(self.world, cap_rows, emb_dim, vocab, n_flat)
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=torch.device('cuda', torch.cuda.current_device()))
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or ptrs[self.rank] != buf.data_ptr():
+                ok = 0
+        except Exception:               # no symmetric-memory support in this build / on this fabric
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) != 1:
+            return
+        self.symm = (buf, hdl)
+        self.ptrs = ptrs
+        self.region = ops.ExchangeRegion(self.world, cap_rows, emb_dim, vocab, n_flat, buffer=buf)
+        mc = int(hdl.multicast_ptr) if getattr(hdl, 'has_multicast_support', False) else 0
+        use = torch.tensor([1 if (mc and os.environ.get('GPT_DP_MULTICAST', '1') != '0') else 0], dtype=torch.int32,
+                           device='cuda')
+        dist.all_reduce(use, op=dist.ReduceOp.MIN, group=group)
+        self.multicast = mc if int(use) == 1 else None

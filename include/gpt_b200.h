@@ -194,6 +194,16 @@ int gpt_embed_bwd(const float* dx, const uint8_t* flags, const int64_t* words, c
 /* Row-sparse tail of clip_grad_norm_ + SGD for the word embedding (train.py:224-227), touching only the rows the
  *     batch used: sq += sum |G[w]|^2 over touched rows;  then  W[w] -= lr * min(1, max_norm/(sqrt(*total_sq)+1e-6)) *
  *     G[w], G[w] = 0, owner[w] = INT_MAX.  total_sq must hold the squared global gradient norm of ALL parameters. */
+/*     The same gradients for LARGE batches without floating-point atomics on the word table: the live token rows are
+ *     grouped by word (counting sort: count -> scan -> fill, int32 workspace of gpt_embed_bwd_grouped_workspace(n_rows, V)
+ *     entries) and one warp per word sums its rows of dX (dropout mask re-derived per row) and adds the result to g_emb[w]
+ *     once; the POS / NER columns are collected in shared memory per CTA.  5.5 -> 1.4 ms at 2 M tokens.  Needs E % 4 == 0,
+ *     (E + Dp + Dn) % 4 == 0, E <= 512, else GPT_ERR_UNSUPPORTED (use gpt_embed_bwd). */
+long long gpt_embed_bwd_grouped_workspace(int n_rows, int V);
+int gpt_embed_bwd_grouped(const float* dx, const uint8_t* flags, const int64_t* words, const int64_t* pos,
+                          const int64_t* ner, float* g_emb, float* g_pos, float* g_ner, int32_t* owner, int n_rows, int V,
+                          int E, int Dp, int Dn, int topn, float drop_p, const uint64_t* rng_state, uint32_t subseq,
+                          int32_t* workspace, void* stream);
 int gpt_embed_rows_sqnorm(const int64_t* words, const int32_t* owner, const float* g_emb, int n_rows, int E, int topn,
                           float* sq, void* stream);
 int gpt_embed_rows_sgd(const int64_t* words, int32_t* owner, float* g_emb, float* emb_w, int n_rows, int E, int topn,
@@ -266,6 +276,12 @@ int gpt_dp_region_init(void* region, int W, int cap_rows, int E, int V, long lon
 int gpt_dp_push(void* const* regions /* host array of W device pointers */, int rank, int W, int cap_rows, int E, int V,
                 long long n_flat, const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words, int n_rows,
                 int topn, void* stream);
+/*     The same push through an NVSwitch multicast mapping of the W regions (`multicast`: e.g. the multicast_ptr of torch
+ *     symmetric memory holding the regions): multimem.st, every byte leaves the GPU once instead of W - 1 times; plain
+ *     data movement, the rank-ordered adds of gpt_dp_reduce stay local. */
+int gpt_dp_push_multicast(void* const* regions, void* multicast, int rank, int W, int cap_rows, int E, int V,
+                          long long n_flat, const float* flat_g, float* g_emb, int32_t* owner, const int64_t* words,
+                          int n_rows, int topn, void* stream);
 int gpt_dp_signal(void* const* regions, int rank, int W, int cap_rows, int E, int V, long long n_flat, void* stream);
 int gpt_dp_reduce(void* const* regions, int rank, int signal, int W, int cap_rows, int E, int V, long long n_flat,
                   float* flat_g, float* partials, void* stream);

@@ -79,3 +79,24 @@ def test_small_batches_keep_the_one_tile_per_cta_kernel():
     ops.gemm_persist_config(2, 65536)
     b = ops.linear_fwd(x, w, 'tf32x3')
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('M,N,K', [(3000, 200, 10000), (700, 512, 4096), (128, 64, 2048), (2750, 200, 360)])
+def test_split_k_of_long_reductions_in_the_one_tile_kernel(M, N, K):
+    """Few output tiles, long reduction (the relation-aware layers' data gradient: [3000, D*H = 10000] x [10000, 200]): the
+    K range is split over CTAs and the partial tiles meet in C through vector reductions; the last shape takes the
+    unsplit path."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / np.sqrt(K)
+    ref = x.double() @ w.double().t()
+    y = torch.full((M, N), 7.0, device=DEV)                 # stale contents must not leak into the sums
+    for mode, tol in (('tf32x3', 1e-5), ('tf32', 2e-3)):
+        ws = ops.weight_prep(w, mode)
+        y = ops.linear_fwd(x, w, mode, ws)
+        assert _rel(y, ref) <= tol, mode
+    dy = torch.randn(M, N, device=DEV, generator=g)          # and as the data gradient: reduction over N
+    if N >= 2048 // 4:
+        ws = ops.weight_prep(w, 'tf32x3')
+        dx = ops.linear_dgrad(dy, w, 'tf32x3', ws)
+        assert _rel(dx, dy.double() @ w.double()) <= 1e-5
