@@ -40,6 +40,7 @@ constexpr int BM = 128;        // rows per CTA tile (UMMA M)
 constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
 constexpr int kMaxStages = 8;   // ring depth is chosen at launch: as many stages as fit in shared memory
+constexpr int kMaxChainKb = 32; // split-K: k-blocks per accumulator chain (bounds the round-toward-zero bias, run_tf32_gemm)
 constexpr int kSplitWarps = 8;          // warps 2..9: operand split (3xTF32) during the main loop, then the epilogue
 constexpr int kGemmThreads = 64 + 32 * kSplitWarps;
 
@@ -498,6 +499,10 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
         // fill the machine by splitting K instead
         splits = 148 / (m_tiles * ((N + 255) / 256));
         if (splits > nkb_all / 8) splits = nkb_all / 8;
+        // the tensor core accumulates round-toward-zero (~1.8e-8 relative per addition, wgrad_tcgen05.cu): at most
+        // kMaxChainKb k-blocks (x 4 K-steps x 3 passes = 384 additions, <= 7e-6) go into one accumulator chain; a second
+        // wave of CTAs costs less than the fp32 grade of the result
+        if (splits < (nkb_all + kMaxChainKb - 1) / kMaxChainKb) splits = (nkb_all + kMaxChainKb - 1) / kMaxChainKb;
         if (splits < 1) splits = 1;
     } else {
         while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;

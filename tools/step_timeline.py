@@ -23,6 +23,10 @@ def main():
     tr = GCNTrainer(synth.tacred_opt(vocab_size=50000, cuda=True, gemm_mode='tf32x3', prune_k=1))
     tr.model.train()
     eng = FusedTrainStep(tr, data_parallel=world > 1, max_rows=6400)
+    if eng.exchange is not None:
+        print('exchange: regions in %s, push through %s' % (
+            'torch symmetric memory' if eng.exchange.symm is not None else 'cudaMalloc + cudaIpc',
+            'NVSwitch multicast (multimem.st)' if eng.exchange.multicast else 'one store per peer'))
     batches = [PackedBatch(parallel.shard_batch(synth.make_batch(1000 + i, batch_size=50 * world, vocab_size=50000), rank,
                                                 world), device='cpu').to('cuda') for i in range(4)]
     flush = torch.empty(64 << 20, dtype=torch.float32, device='cuda')
