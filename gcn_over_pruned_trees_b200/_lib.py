@@ -85,6 +85,15 @@ SIGNATURES = {
     'gpt_edge_keep_dense': [_p, _c_int, _c_int, _c_u32, _c_int, _c_f, _p, _p],
     'gpt_relation_keep_tokens': [_p, _c_int, _c_u32, _c_f, _p, _p, _p],
     'gpt_colsum_acc': [_p, _c_ll, _c_int, _p, _p],
+    'gpt_live_rows': [_p, _c_int, _p, _p, _p, _p, _p],
+    'gpt_gather_rows': [_p, _p, _p, _c_int, _c_int, _p, _p],
+    'gpt_scatter_rows': [_p, _p, _c_int, _c_int, _p, _p],
+    'gpt_linear_fwd_tf32x3_rows': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_linear_dgrad_tf32x3_rows': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_linear_wgrad_tf32x3_rows': [_p, _p, _p, _p, _c_ll, _c_int, _c_int, _p, _p],
+    'gpt_relmix_fwd_rows': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p],
+    'gpt_relmix_bwd_rows': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p],
+    'gpt_colsum_acc_rows': [_p, _c_ll, _c_int, _p, _p, _p],
     'gpt_update_partials': [_c_ll, _c_int],
     'gpt_update_sqnorm': [_p, _c_ll, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_update_apply': [_p, _p, _c_ll, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _c_f, _c_f, _c_f, _p, _p, _p],

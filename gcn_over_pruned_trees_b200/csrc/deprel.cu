@@ -70,8 +70,13 @@ struct MixParams {
     float* S;
     float* dZ;                    // bwd: [N, D*H]
     float* dE;                    // bwd: [85, D], caller-zeroed, atomically accumulated
+    const int* perm;              // optional: the observable rows, compacted (gpt_live_rows) -- Z / dZ are then indexed by
+    const int* count;             //   the compact position i < *count, everything per token by n = perm[i]
     int N, D, H, deep;
 };
+
+// rows this launch walks: every token row, or only the compacted observable ones
+__device__ __forceinline__ int mix_rows(const MixParams& p) { return p.perm != nullptr ? min(*p.count, p.N) : p.N; }
 
 __device__ __forceinline__ void load_relation_vectors(const MixParams& p, int n, int rf, float* ef, float* er, float* es) {
     const bool forget_f = p.deep || (p.keep_f != nullptr && p.keep_f[n] == 0);
@@ -90,7 +95,9 @@ __global__ void __launch_bounds__(kThreads) relmix_fwd_kernel(const MixParams p)
     float* es = sm + 2 * p.D;
     GPT_PDL_ENTER();
     const size_t DH = (size_t)p.D * p.H;
-    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+    const int rows = mix_rows(p);
+    for (int i = blockIdx.x; i < rows; i += gridDim.x) {
+        const int n = p.perm != nullptr ? p.perm[i] : i;
         if (!observable(p.flags[n])) {                 // CTA-uniform
             for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
                 p.F[(size_t)n * p.H + h] = 0.f;
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(kThreads) relmix_fwd_kernel(const MixParams p)
         load_relation_vectors(p, n, rel_id(p.deprel[n]), ef, er, es);
         __syncthreads();
         for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
-            const float* __restrict__ z = p.Z + (size_t)n * DH + h;
+            const float* __restrict__ z = p.Z + (size_t)i * DH + h;
             const float* __restrict__ b = p.bias + h;
             float f = 0.f, r = 0.f, s = 0.f;
             for (int d = 0; d < p.D; ++d) {
@@ -134,8 +141,10 @@ __global__ void __launch_bounds__(kThreads) relmix_bwd_kernel(const MixParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int d = threadIdx.x; d < p.D; d += blockDim.x) acc84[d] = 0.f;
     __syncthreads();
-    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
-        float* __restrict__ dz = p.dZ + (size_t)n * DH;
+    const int rows = mix_rows(p);
+    for (int i = blockIdx.x; i < rows; i += gridDim.x) {
+        const int n = p.perm != nullptr ? p.perm[i] : i;
+        float* __restrict__ dz = p.dZ + (size_t)i * DH;
         if (!observable(p.flags[n])) {                 // CTA-uniform; the projection's gradients read every row
             for (size_t i = threadIdx.x; i < DH; i += blockDim.x) dz[i] = 0.f;
             continue;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) relmix_bwd_kernel(const MixParams p)
             gs[h] = p.S[(size_t)n * p.H + h];
         }
         __syncthreads();
-        const float* __restrict__ z = p.Z + (size_t)n * DH;
+        const float* __restrict__ z = p.Z + (size_t)i * DH;
         for (int d = warp; d < p.D; d += nwarps) {             // a relation slot d always belongs to the same warp
             const float a = ef[d], b = er[d], c = es[d];
             float sf = 0.f, sr = 0.f, ss = 0.f;
@@ -176,6 +185,250 @@ __global__ void __launch_bounds__(kThreads) relmix_bwd_kernel(const MixParams p)
     if (!p.deep)
         for (int d = warp; d < p.D; d += nwarps)
             if (lane == 0 && acc84[d] != 0.f) atomicAdd(p.dE + (size_t)kRevBound * p.D + d, acc84[d]);
+}
+
+// ---- relation mix, 128-bit path (H % 4 == 0, 16-byte aligned rows): warps over the relation slots, lanes over the columns ----
+constexpr int kMixThreads = 256;
+__device__ __forceinline__ float4 f4_fma(float a, float4 v, float4 acc) {
+    return make_float4(fmaf(a, v.x, acc.x), fmaf(a, v.y, acc.y), fmaf(a, v.z, acc.z), fmaf(a, v.w, acc.w));
+}
+// volatile: ptxas keeps these in program order, so a batch of loads is in flight before its first consumer
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+#ifdef GPT_HOST_EMULATION
+    return *p;
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
+__device__ __forceinline__ float f4_dot(float4 a, float4 b, float acc) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
+}
+
+// smem: ef, er, es [D] | part [warps][3][H]: warp w sums the slots d = w, w + warps, ...; the partial rows meet in shared memory
+__global__ void __launch_bounds__(kMixThreads) relmix_fwd4_kernel(const MixParams p) {
+    extern __shared__ float sm[];
+    float* ef = sm;
+    float* er = sm + p.D;
+    float* es = sm + 2 * p.D;
+    float4* part = reinterpret_cast<float4*>(sm + ((3 * p.D + 3) & ~3));
+    GPT_PDL_ENTER();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5, hq = p.H >> 2;
+    const size_t DH = (size_t)p.D * p.H;
+    const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(p.bias);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int rows = mix_rows(p);
+    for (int i = blockIdx.x; i < rows; i += gridDim.x) {
+        const int n = p.perm != nullptr ? p.perm[i] : i;
+        float4* __restrict__ F4 = reinterpret_cast<float4*>(p.F + (size_t)n * p.H);
+        float4* __restrict__ R4 = reinterpret_cast<float4*>(p.R + (size_t)n * p.H);
+        float4* __restrict__ S4 = reinterpret_cast<float4*>(p.S + (size_t)n * p.H);
+        if (!observable(p.flags[n])) {                 // CTA-uniform
+            for (int c = threadIdx.x; c < hq; c += blockDim.x) F4[c] = R4[c] = S4[c] = zero;
+            continue;
+        }
+        load_relation_vectors(p, n, rel_id(p.deprel[n]), ef, er, es);
+        __syncthreads();
+        const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.Z + (size_t)i * DH);
+        for (int c = lane; c < hq; c += 32) {
+            float4 f = zero, r = zero, s = zero;
+#pragma unroll 4
+            for (int d = warp; d < p.D; d += nw) {
+                const float4 z = z4[(size_t)d * hq + c], b = bias4[(size_t)d * hq + c];
+                const float4 v = make_float4(z.x + b.x, z.y + b.y, z.z + b.z, z.w + b.w);
+                f = f4_fma(ef[d], v, f);
+                r = f4_fma(er[d], v, r);
+                s = f4_fma(es[d], v, s);
+            }
+            part[(size_t)(warp * 3 + 0) * hq + c] = f;
+            part[(size_t)(warp * 3 + 1) * hq + c] = r;
+            part[(size_t)(warp * 3 + 2) * hq + c] = s;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 3 * hq; idx += blockDim.x) {
+            const int which = idx / hq, c = idx - which * hq;
+            float4 acc = zero;
+            for (int w = 0; w < nw; ++w) {
+                const float4 v = part[(size_t)(w * 3 + which) * hq + c];
+                acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+            }
+            (which == 0 ? F4 : which == 1 ? R4 : S4)[c] = acc;
+        }
+        __syncthreads();                                       // ef/er/es and part are rewritten for the next row
+    }
+}
+
+// smem: ef, er, es [D] | acc84 [D] | dF, dR, dS [H]
+__global__ void __launch_bounds__(kMixThreads, 3) relmix_bwd4_kernel(const MixParams p) {
+    extern __shared__ float sm[];
+    float* ef = sm;
+    float* er = sm + p.D;
+    float* es = sm + 2 * p.D;
+    float* acc84 = sm + 3 * p.D;
+    float4* gf = reinterpret_cast<float4*>(sm + ((4 * p.D + 3) & ~3));
+    const int hq = p.H >> 2;
+    float4* gr = gf + hq;
+    float4* gs = gr + hq;
+    GPT_PDL_ENTER();
+    const size_t DH = (size_t)p.D * p.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(p.bias);
+    for (int d = threadIdx.x; d < p.D; d += blockDim.x) acc84[d] = 0.f;
+    __syncthreads();
+    const int rows = mix_rows(p);
+    for (int i = blockIdx.x; i < rows; i += gridDim.x) {
+        const int n = p.perm != nullptr ? p.perm[i] : i;
+        float4* __restrict__ dz4 = reinterpret_cast<float4*>(p.dZ + (size_t)i * DH);
+        if (!observable(p.flags[n])) {                 // CTA-uniform; the projection's gradients read every row
+            for (size_t k = threadIdx.x; k < DH / 4; k += blockDim.x) dz4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const int rf = rel_id(p.deprel[n]);
+        const bool forget_f = p.deep || (p.keep_f != nullptr && p.keep_f[n] == 0);
+        const bool forget_r = p.deep || (p.keep_r != nullptr && p.keep_r[n] == 0);
+        load_relation_vectors(p, n, rf, ef, er, es);
+        for (int c = threadIdx.x; c < hq; c += blockDim.x) {
+            gf[c] = reinterpret_cast<const float4*>(p.F + (size_t)n * p.H)[c];
+            gr[c] = reinterpret_cast<const float4*>(p.R + (size_t)n * p.H)[c];
+            gs[c] = reinterpret_cast<const float4*>(p.S + (size_t)n * p.H)[c];
+        }
+        __syncthreads();
+        const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.Z + (size_t)i * DH);
+        // U relation slots x 2 column groups per lane: every load of Z is issued before the first store of dZ (the stores
+        // would otherwise fence the loads behind them -- one round trip to memory per slot)
+        constexpr int U = 4;
+        for (int db = warp; db < p.D; db += nw * U) {          // a relation slot d always belongs to the same warp
+            float sf[U], sr[U], ss[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sf[u] = sr[u] = ss[u] = 0.f;
+            for (int q0 = lane; q0 < hq; q0 += 64) {
+                float4 zv[U][2];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int d = db + u * nw, q = q0 + 32 * j;
+                        if (d < p.D && q < hq) zv[u][j] = ld_stream_f4(z4 + (size_t)d * hq + q);
+                    }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int d = db + u * nw;
+                    if (d >= p.D) break;                       // warp-uniform
+                    const float a = ef[d], b = er[d], c = es[d];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int q = q0 + 32 * j;
+                        if (q >= hq) break;
+                        const float4 z = zv[u][j], bb = bias4[(size_t)d * hq + q];
+                        const float4 v = make_float4(z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w);
+                        const float4 x = gf[q], y = gr[q], w = gs[q];
+                        sf[u] = f4_dot(x, v, sf[u]);
+                        sr[u] = f4_dot(y, v, sr[u]);
+                        ss[u] = f4_dot(w, v, ss[u]);
+                        dz4[(size_t)d * hq + q] =
+                            make_float4(fmaf(a, x.x, fmaf(b, y.x, c * w.x)), fmaf(a, x.y, fmaf(b, y.y, c * w.y)),
+                                        fmaf(a, x.z, fmaf(b, y.z, c * w.z)), fmaf(a, x.w, fmaf(b, y.w, c * w.w)));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int d = db + u * nw;
+                if (d >= p.D) break;
+                const float tf = warp_sum_f(sf[u]), tr = warp_sum_f(sr[u]), ts = warp_sum_f(ss[u]);
+                if (lane == 0 && !p.deep) {
+                    if (!forget_f && rf != 0) atomicAdd(p.dE + (size_t)rf * p.D + d, tf);      // row 0 is padding_idx
+                    if (!forget_r) atomicAdd(p.dE + (size_t)(rf + kFwdBound) * p.D + d, tr);
+                    acc84[d] += ts;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!p.deep)
+        for (int d = warp; d < p.D; d += nw)
+            if (lane == 0 && acc84[d] != 0.f) atomicAdd(p.dE + (size_t)kRevBound * p.D + d, acc84[d]);
+}
+
+// ---- the observable rows of a batch, compacted -----------------------------------------------------------------------
+// At prune_k = 1 three quarters of a TACRED-shaped batch's token rows are outside every pruned tree: nothing downstream
+// reads what the relation-aware layers compute for them, and their [D*H]-wide projections are the step's largest cost.
+// One CTA lists the rows with flags != 0 in ascending order:  perm[0 .. count) = their ids, inv[n] = position of row n
+// or -1, live[i] = (i < count) -- the K1-style row flags of the COMPACT arrays, which the weight-gradient kernels take --
+// and count itself stays on the device: the step is captured into a CUDA graph, so every consumer gets its row count from
+// this buffer, never from the host.
+__global__ void __launch_bounds__(1024) live_rows_kernel(const unsigned char* __restrict__ flags, int N,
+                                                         int* __restrict__ perm, int* __restrict__ inv,
+                                                         unsigned char* __restrict__ live, int* __restrict__ count) {
+    __shared__ int s_wcnt[32];
+    __shared__ int s_base;
+    GPT_PDL_ENTER();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int n = base + tid;
+        const bool ob = n < N && observable(flags[n]);
+        const unsigned m = __ballot_sync(GPT_FULL_MASK, ob);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < nw; ++w) {
+            const int c = s_wcnt[w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        const int b0 = s_base;
+        if (n < N) {
+            const int pos = b0 + before + __popc(m & ((1u << lane) - 1u));
+            if (ob) perm[pos] = n;
+            inv[n] = ob ? pos : -1;
+        }
+        __syncthreads();
+        if (tid == 0) s_base = b0 + total;
+        __syncthreads();
+    }
+    const int total = s_base;
+    for (int i = tid; i < N; i += blockDim.x) live[i] = i < total ? 1 : 0;
+    if (tid == 0) count[0] = total;
+}
+
+// out[i, :] = x[perm[i], :] for i < *count (the other rows of `out` are never read)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ perm,
+                                                          const int* __restrict__ count, int N, int K,
+                                                          float* __restrict__ out) {
+    GPT_PDL_ENTER();
+    const int rows = min(*count, N);
+    const bool vec = (K % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    for (int i = blockIdx.x; i < rows; i += gridDim.x) {
+        const size_t src = (size_t)perm[i] * K, dst = (size_t)i * K;
+        if (vec) {
+            for (int k = threadIdx.x; k < K / 4; k += blockDim.x)
+                reinterpret_cast<float4*>(out + dst)[k] = reinterpret_cast<const float4*>(x + src)[k];
+        } else {
+            for (int k = threadIdx.x; k < K; k += blockDim.x) out[dst + k] = x[src + k];
+        }
+    }
+}
+
+// dx[n, :] = inv[n] >= 0 ? dxc[inv[n], :] : 0 for every token row n
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ dxc, const int* __restrict__ inv, int N,
+                                                           int K, float* __restrict__ dx) {
+    GPT_PDL_ENTER();
+    const bool vec = (K % 4 == 0) && (((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dxc)) & 15) == 0);
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+        const int pos = inv[n];
+        const size_t src = (size_t)(pos < 0 ? 0 : pos) * K, dst = (size_t)n * K;
+        if (vec) {
+            for (int k = threadIdx.x; k < K / 4; k += blockDim.x)
+                reinterpret_cast<float4*>(dx + dst)[k] =
+                    pos < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(dxc + src)[k];
+        } else {
+            for (int k = threadIdx.x; k < K; k += blockDim.x) dx[dst + k] = pos < 0 ? 0.f : dxc[src + k];
+        }
+    }
 }
 
 // ---- diagonal mode: elementwise relation gates -----------------------------------------------------------------------
@@ -382,19 +635,21 @@ __global__ void token_keep_kernel(const unsigned long long* __restrict__ rng, in
 
 // out[c] += sum_r a[r, c]   (bias gradient of the shared projection: column sums of dZ)
 __global__ void __launch_bounds__(256) colsum_acc_kernel(const float* __restrict__ a, long long rows, int cols, int chunk,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, const int* __restrict__ count) {
     GPT_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
+    if (count != nullptr && *count < rows) rows = *count;       // only the compacted observable rows (gpt_live_rows)
     const long long r0 = (long long)blockIdx.y * chunk;
     const long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
+    if (r0 >= r1) return;
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += a[(size_t)r * cols + c];
     atomicAdd(out + c, s);
 }
 
-inline unsigned row_grid(long long rows) {
-    long long cap = 148LL * 16;            // resident CTAs of 128 threads per SM x SM count: one wave, grid-stride beyond
+inline unsigned row_grid(long long rows, int threads = kThreads) {
+    long long cap = 148LL * (2048 / threads);   // resident CTAs per SM x SM count: one wave, grid-stride beyond
     if (const char* e = getenv("GPT_K10_MAX_CTAS")) {      // tuning / test knob: CTAs per launch
         const long long v = atoll(e);
         if (v > 0) cap = v;
@@ -404,31 +659,90 @@ inline unsigned row_grid(long long rows) {
 
 }  // namespace
 
-extern "C" int gpt_relmix_fwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
-                              const uint8_t* keep_f, const uint8_t* keep_r, int N, int D, int H, int deep, float* F,
-                              float* R, float* S, void* stream) {
+static bool mix_vec_ok(const MixParams& p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.Z) | reinterpret_cast<uintptr_t>(p.bias) | reinterpret_cast<uintptr_t>(p.F) |
+                        reinterpret_cast<uintptr_t>(p.R) | reinterpret_cast<uintptr_t>(p.S) | reinterpret_cast<uintptr_t>(p.dZ);
+    return p.H % 4 == 0 && (a & 15) == 0;
+}
+
+// perm / count: NULL = every token row; else the compact row list of gpt_live_rows (Z is then [count, D*H], compact)
+extern "C" int gpt_relmix_fwd_rows(const float* Z, const float* bias, const float* E, const int64_t* deprel,
+                                   const uint8_t* flags, const uint8_t* keep_f, const uint8_t* keep_r, const int32_t* perm,
+                                   const int32_t* count, int N, int D, int H, int deep, float* F, float* R, float* S,
+                                   void* stream) {
     GPT_CHECK_ARG(Z && bias && E && deprel && flags && F && R && S && N >= 0 && D >= 1 && H >= 1);
+    GPT_CHECK_ARG((perm == nullptr) == (count == nullptr));
     if (N == 0) return GPT_OK;
-    if ((size_t)3 * D * sizeof(float) > 48 * 1024) return GPT_ERR_UNSUPPORTED;
     MixParams p{};
     p.Z = Z; p.bias = bias; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags;
     p.keep_f = keep_f; p.keep_r = keep_r; p.F = F; p.R = R; p.S = S; p.N = N; p.D = D; p.H = H; p.deep = deep;
+    p.perm = perm; p.count = count;
+    const size_t smem4 = ((size_t)((3 * D + 3) & ~3) + (size_t)(kMixThreads / 32) * 3 * H) * sizeof(float);
+    if (mix_vec_ok(p) && smem4 <= 48 * 1024) {
+        gpt_launch(relmix_fwd4_kernel, dim3(row_grid(N, kMixThreads)), dim3(kMixThreads), smem4, (cudaStream_t)stream, p);
+        return gpt_launch_status();
+    }
+    if ((size_t)3 * D * sizeof(float) > 48 * 1024) return GPT_ERR_UNSUPPORTED;
     gpt_launch(relmix_fwd_kernel, dim3(row_grid(N)), dim3(kThreads), (size_t)3 * D * sizeof(float), (cudaStream_t)stream, p);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_relmix_fwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                              const uint8_t* keep_f, const uint8_t* keep_r, int N, int D, int H, int deep, float* F,
+                              float* R, float* S, void* stream) {
+    return gpt_relmix_fwd_rows(Z, bias, E, deprel, flags, keep_f, keep_r, nullptr, nullptr, N, D, H, deep, F, R, S, stream);
+}
+
+extern "C" int gpt_relmix_bwd_rows(const float* Z, const float* bias, const float* E, const int64_t* deprel,
+                                   const uint8_t* flags, const uint8_t* keep_f, const uint8_t* keep_r, const int32_t* perm,
+                                   const int32_t* count, const float* dF, const float* dR, const float* dS, int N, int D,
+                                   int H, int deep, float* dZ, float* dE, void* stream) {
+    GPT_CHECK_ARG(Z && bias && E && deprel && flags && dF && dR && dS && dZ && dE && N >= 0 && D >= 1 && H >= 1);
+    GPT_CHECK_ARG((perm == nullptr) == (count == nullptr));
+    if (N == 0) return GPT_OK;
+    MixParams p{};
+    p.Z = Z; p.bias = bias; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags;
+    p.keep_f = keep_f; p.keep_r = keep_r; p.F = const_cast<float*>(dF); p.R = const_cast<float*>(dR);
+    p.S = const_cast<float*>(dS); p.dZ = dZ; p.dE = dE; p.N = N; p.D = D; p.H = H; p.deep = deep;
+    p.perm = perm; p.count = count;
+    const size_t smem4 = ((size_t)((4 * D + 3) & ~3) + (size_t)3 * H) * sizeof(float);
+    if (mix_vec_ok(p) && smem4 <= 48 * 1024) {
+        gpt_launch(relmix_bwd4_kernel, dim3(row_grid(N, kMixThreads)), dim3(kMixThreads), smem4, (cudaStream_t)stream, p);
+        return gpt_launch_status();
+    }
+    const size_t smem = ((size_t)4 * D + 3 * H) * sizeof(float);
+    if (smem > 48 * 1024) return GPT_ERR_UNSUPPORTED;
+    gpt_launch(relmix_bwd_kernel, dim3(row_grid(N)), dim3(kThreads), smem, (cudaStream_t)stream, p);
     return gpt_launch_status();
 }
 
 extern "C" int gpt_relmix_bwd(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
                               const uint8_t* keep_f, const uint8_t* keep_r, const float* dF, const float* dR,
                               const float* dS, int N, int D, int H, int deep, float* dZ, float* dE, void* stream) {
-    GPT_CHECK_ARG(Z && bias && E && deprel && flags && dF && dR && dS && dZ && dE && N >= 0 && D >= 1 && H >= 1);
+    return gpt_relmix_bwd_rows(Z, bias, E, deprel, flags, keep_f, keep_r, nullptr, nullptr, dF, dR, dS, N, D, H, deep, dZ, dE,
+                               stream);
+}
+
+// flags [N] -> perm [N], inv [N], live [N], count [1] (see live_rows_kernel)
+extern "C" int gpt_live_rows(const uint8_t* flags, int N, int32_t* perm, int32_t* inv, uint8_t* live, int32_t* count,
+                             void* stream) {
+    GPT_CHECK_ARG(flags && perm && inv && live && count && N >= 0);
+    gpt_launch(live_rows_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, flags, N, perm, inv, live, count);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_gather_rows(const float* x, const int32_t* perm, const int32_t* count, int N, int K, float* out,
+                               void* stream) {
+    GPT_CHECK_ARG(x && perm && count && out && N >= 0 && K >= 1);
     if (N == 0) return GPT_OK;
-    const size_t smem = ((size_t)4 * D + 3 * H) * sizeof(float);
-    if (smem > 48 * 1024) return GPT_ERR_UNSUPPORTED;
-    MixParams p{};
-    p.Z = Z; p.bias = bias; p.E = E; p.deprel = reinterpret_cast<const long long*>(deprel); p.flags = flags;
-    p.keep_f = keep_f; p.keep_r = keep_r; p.F = const_cast<float*>(dF); p.R = const_cast<float*>(dR);
-    p.S = const_cast<float*>(dS); p.dZ = dZ; p.dE = dE; p.N = N; p.D = D; p.H = H; p.deep = deep;
-    gpt_launch(relmix_bwd_kernel, dim3(row_grid(N)), dim3(kThreads), smem, (cudaStream_t)stream, p);
+    gpt_launch(gather_rows_kernel, dim3(row_grid(N, 256)), dim3(256), 0, (cudaStream_t)stream, x, perm, count, N, K, out);
+    return gpt_launch_status();
+}
+
+extern "C" int gpt_scatter_rows(const float* dxc, const int32_t* inv, int N, int K, float* dx, void* stream) {
+    GPT_CHECK_ARG(dxc && inv && dx && N >= 0 && K >= 1);
+    if (N == 0) return GPT_OK;
+    gpt_launch(scatter_rows_kernel, dim3(row_grid(N, 256)), dim3(256), 0, (cudaStream_t)stream, dxc, inv, N, K, dx);
     return gpt_launch_status();
 }
 
@@ -523,13 +837,18 @@ extern "C" int gpt_relation_keep_tokens(const void* rng_state, int N, unsigned l
     return gpt_launch_status();
 }
 
-extern "C" int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* stream) {
+// out[c] += sum over rows r < min(rows, *count) of a[r, c]   (count == NULL: every row)
+extern "C" int gpt_colsum_acc_rows(const float* a, long long rows, int cols, const int32_t* count, float* out, void* stream) {
     GPT_CHECK_ARG(a && out && rows >= 0 && cols >= 1);
     if (rows == 0) return GPT_OK;
     const int chunk = 64;
     const long long row_blocks = (rows + chunk - 1) / chunk;
     GPT_CHECK_ARG(row_blocks <= 65535);
     gpt_launch(colsum_acc_kernel, dim3((unsigned)((cols + 255) / 256), (unsigned)row_blocks), dim3(256), 0,
-               (cudaStream_t)stream, a, rows, cols, chunk, out);
+               (cudaStream_t)stream, a, rows, cols, chunk, out, count);
     return gpt_launch_status();
+}
+
+extern "C" int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* stream) {
+    return gpt_colsum_acc_rows(a, rows, cols, nullptr, out, stream);
 }

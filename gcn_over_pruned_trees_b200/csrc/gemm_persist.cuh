@@ -150,11 +150,30 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Static tile schedule of one cluster: its q-th tile.  Many row blocks (the large shapes): a cluster owns whole row blocks
+// and walks their N tiles back to back, so the second read of the block's X rows is an L2 hit.  Few row blocks and many N
+// tiles (the relation-aware layers: ~1 000 live rows x D*H = 10 000 columns): tiles are dealt round-robin, or most
+// clusters would have nothing to do.
+struct TileSched {
+    int m_blocks, n_tiles, cluster, n_clusters, flat;
+    __device__ __forceinline__ bool get(int q, int& mb, int& nb) const {
+        if (flat) {
+            const int t = cluster + q * n_clusters;
+            mb = t / n_tiles;
+            nb = t - mb * n_tiles;
+            return t < m_blocks * n_tiles;
+        }
+        mb = cluster + (q / n_tiles) * n_clusters;
+        nb = q % n_tiles;
+        return mb < m_blocks;
+    }
+};
+
 template <int PASSES, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                        const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ CUtensorMap tm_c,
-                       int M, int N, int K, int n_tile, int n_tiles, int STAGES, const MaskEpilogue ep) {
+                       int M, int N, int K, int n_tile, int n_tiles, int STAGES, const MaskEpilogue ep, int flat) {
     GPT_PDL_TRIGGER();
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 4];
@@ -165,7 +184,6 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     const bool leader = rank == 0;
     const int cluster = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
     const int n_clusters = CG == 2 ? (int)n_clusters_x() : (int)gridDim.x;
-    const int m_blocks = (M + CG * BM - 1) / (CG * BM);
     const int nkb = (K + BK - 1) / BK;
     const int n_half = n_tile / CG;                                 // rows of W this CTA stages per tile
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)n_half * BK * (PASSES == 0 ? 2 : 4);
@@ -202,6 +220,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_holder;
     GPT_PDL_WAIT();
+    // the row count may live on the device (gpt_live_rows): row blocks beyond it are not scheduled at all
+    const int m_rows = ep.m_live != nullptr ? min(M, *ep.m_live) : M;
+    const TileSched sched{(m_rows + CG * BM - 1) / (CG * BM), n_tiles, cluster, n_clusters, flat};
+    int mb, nb;
 
     if (warp == 0) {
         // ===== TMA producer (each CTA: its 128 rows of X, its half of the W tile) =====
@@ -210,24 +232,22 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             // TF32 on a CTA pair: nothing has to touch the landed tiles, so BOTH CTAs' loads credit their bytes to the
             // leader's full[s] (cp.async.bulk.tensor.cta_group::2) and the MMA thread waits on that barrier directly
             const uint32_t full_leader = (kDirect && CG == 2) ? map_to_rank(full0, 0) : full0;
-            for (int mb = cluster; mb < m_blocks; mb += n_clusters) {
+            for (int q = 0; sched.get(q, mb, nb); ++q) {
                 const int m0 = (mb * CG + (int)rank) * BM;
-                for (int nb = 0; nb < n_tiles; ++nb) {
-                    const int n0 = nb * n_tile + (int)rank * n_half;
-                    for (int kb = 0; kb < nkb; ++kb, ++it) {
-                        const uint32_t s = it % (uint32_t)STAGES;
-                        if (it >= (uint32_t)STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
-                        const uint32_t st = tiles + s * stage_bytes;
-                        if (kDirect && CG == 2) {
-                            if (leader) mbar_expect_tx(full0 + 8 * s, 2u * (a_bytes + b_bytes));
-                            tma_load_2d_pair(st, &tm_a, full_leader + 8 * s, kb * BK, m0);
-                            tma_load_2d_pair(st + off_b, &tm_b, full_leader + 8 * s, kb * BK, n0);
-                        } else {
-                            mbar_expect_tx(full0 + 8 * s, a_bytes + kLo * b_bytes);
-                            tma_load_2d(st, &tm_a, full0 + 8 * s, kb * BK, m0);      // OOB rows / columns arrive as zeros
-                            tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, kb * BK, n0);
-                            if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, kb * BK, n0);
-                        }
+                const int n0 = nb * n_tile + (int)rank * n_half;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)STAGES;
+                    if (it >= (uint32_t)STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+                    const uint32_t st = tiles + s * stage_bytes;
+                    if (kDirect && CG == 2) {
+                        if (leader) mbar_expect_tx(full0 + 8 * s, 2u * (a_bytes + b_bytes));
+                        tma_load_2d_pair(st, &tm_a, full_leader + 8 * s, kb * BK, m0);
+                        tma_load_2d_pair(st + off_b, &tm_b, full_leader + 8 * s, kb * BK, n0);
+                    } else {
+                        mbar_expect_tx(full0 + 8 * s, a_bytes + kLo * b_bytes);
+                        tma_load_2d(st, &tm_a, full0 + 8 * s, kb * BK, m0);      // OOB rows / columns arrive as zeros
+                        tma_load_2d(st + off_b, &tm_b, full0 + 8 * s, kb * BK, n0);
+                        if (PASSES == 3) tma_load_2d(st + off_blo, &tm_b_lo, full0 + 8 * s, kb * BK, n0);
                     }
                 }
             }
@@ -239,8 +259,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_tile >> 3) << 17) |
                                    ((uint32_t)((CG * BM) >> 4) << 24);
             uint32_t it = 0, tile_it = 0;
-            for (int mb = cluster; mb < m_blocks; mb += n_clusters) {
-                for (int nb = 0; nb < n_tiles; ++nb, ++tile_it) {
+            {
+                for (int q = 0; sched.get(q, mb, nb); ++q, ++tile_it) {
                     const uint32_t a = tile_it & 1u;
                     if (tile_it >= 2) mbar_wait_cluster(tempty0 + 8 * a, ((tile_it >> 1) - 1) & 1);
                     tc_fence_after();
@@ -280,8 +300,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         const uint32_t t = threadIdx.x - 32 * (2 + kEpiWarps);     // 0..255
         const uint32_t ready_leader = CG == 2 ? map_to_rank(ready0, 0) : ready0;
         uint32_t it = 0;
-        for (int mb = cluster; mb < m_blocks; mb += n_clusters) {
-            for (int nb = 0; nb < n_tiles; ++nb) {
+        {
+            for (int q = 0; sched.get(q, mb, nb); ++q) {
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)STAGES;
                     if (PASSES == 0) {          // bf16 operands: round the landed fp32 X tile to bf16, in place
@@ -336,17 +356,22 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         const uint32_t tempty_leader = CG == 2 ? map_to_rank(tempty0, 0) : tempty0;
         const uint32_t row_off = (uint32_t)r_loc * 128u, sw = (uint32_t)(r_loc & 7);
         uint32_t tile_it = 0, chunk_it = 0;
-        for (int mb = cluster; mb < m_blocks; mb += n_clusters) {
-            const int m0 = (mb * CG + (int)rank) * BM;
-            const int row = m0 + r_loc;
+        {
+            int last_mb = -1, m0 = 0;
             float ep_inv = 0.f;
             const uint32_t* ep_words = nullptr;
-            if (ep.act != nullptr && row < M) {
-                const int bb = row / ep.T, tt = row - bb * ep.T;
-                ep_inv = __frcp_rn(ep.denom[row]);
-                ep_words = ep.act + ((size_t)bb * ((N + 31) / 32)) * ep.T + tt;
-            }
-            for (int nb = 0; nb < n_tiles; ++nb, ++tile_it) {
+            for (int q = 0; sched.get(q, mb, nb); ++q, ++tile_it) {
+                if (mb != last_mb) {
+                    last_mb = mb;
+                    m0 = (mb * CG + (int)rank) * BM;
+                    const int row = m0 + r_loc;
+                    ep_words = nullptr;
+                    if (ep.act != nullptr && row < M) {
+                        const int bb = row / ep.T, tt = row - bb * ep.T;
+                        ep_inv = __frcp_rn(ep.denom[row]);
+                        ep_words = ep.act + ((size_t)bb * ((N + 31) / 32)) * ep.T + tt;
+                    }
+                }
                 const uint32_t a = tile_it & 1u;
                 mbar_wait(tfull0 + 8 * a, (tile_it >> 1) & 1);
                 tc_fence_after();
@@ -480,7 +505,10 @@ int launch(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& 
             if (resident[dev] < clusters) clusters = resident[dev];
         }
     }
-    if (clusters > m_blocks) clusters = m_blocks;
+    // few row blocks (or a row count only the device knows): the tiles are dealt round-robin over the clusters (TileSched)
+    const int flat = (ep.m_live != nullptr || m_blocks < clusters) ? 1 : 0;
+    const long long work = flat ? (long long)m_blocks * n_tiles : m_blocks;
+    if (clusters > work) clusters = (int)work;
     cfg.gridDim = dim3((unsigned)(clusters * CG));
     if (g_gpt_pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -490,7 +518,7 @@ int launch(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& 
     cfg.attrs = attr;
     cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_persistent_kernel<PASSES, CG>, tm_a, tm_b, tm_b_lo, tm_c, M, N, K, n_tile,
-                                       n_tiles, stages, ep);
+                                       n_tiles, stages, ep, flat);
     if (e != cudaSuccess) return (int)e;
     return gpt_launch_status();
 }
@@ -517,7 +545,11 @@ inline int run(const float* A, const float* B, const float* b_lo, float* C, int 
                const MaskEpilogue& ep) {
     const int cg = mode();
     if (cg != 1 && cg != 2) return GPT_ERR_UNSUPPORTED;
-    if (M < min_rows() || N % 4 != 0 || K % 4 != 0 || (reinterpret_cast<uintptr_t>(C) & 15)) return GPT_ERR_UNSUPPORTED;
+    // large M -- or a wide output whose live row count is on the device (the relation-aware layers' shared projection: the
+    // static schedule then simply stops at the last live row block, and CTA pairs halve W's L2 -> SMEM traffic)
+    const bool wide_live = ep.m_live != nullptr && N >= 2048 && M >= 256;
+    if ((M < min_rows() && !wide_live) || N % 4 != 0 || K % 4 != 0 || (reinterpret_cast<uintptr_t>(C) & 15))
+        return GPT_ERR_UNSUPPORTED;
     const int n_tiles = (N + 255) / 256;
     const int gran = n_tiles > 1 ? 32 : 16 * cg;                 // a tile that has a neighbour ends on a store-box edge
     int n_tile = ((N + n_tiles - 1) / n_tiles + gran - 1) / gran * gran;

@@ -52,6 +52,10 @@ struct MaskEpilogue {
     const float* denom;      // [B*T]
     float scale;             // dropout scale of the previous layer's forward
     int T;
+    // Unrelated to the mask, carried here because every launcher already passes this struct: an optional device-side row
+    // count (gpt_live_rows).  Row tiles at or beyond *m_live leave at once -- the relation-aware layers project only the
+    // compacted observable rows of a batch, and inside a captured step the host never knows how many there are.
+    const int* m_live;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,8 +172,26 @@ template <int PASSES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int K, int n_tile,
-                 int n_tiles, int tmem_cols, int STAGES, const MaskEpilogue ep, int kb_per_split) {
+                 int n_tiles, int tmem_cols, int STAGES, const MaskEpilogue ep, int kb_per_split, int sm_count) {
     GPT_PDL_TRIGGER();
+    if (ep.m_live != nullptr) {     // CTA-uniform, before any barrier or tensor-memory state exists
+        GPT_PDL_WAIT();
+        const int m_live = *ep.m_live;
+        if ((int)(blockIdx.x / n_tiles) * BM >= m_live) return;
+        if (gridDim.y > 1) {
+            // split-K with a device-side row count: the host launched the finest split it allows (gridDim.y ranges); the
+            // number actually used is chosen here, so that the live row tiles x splits fill the SMs once -- every CTA
+            // streams its K range through one SM's L2 port, so idle SMs are lost bandwidth -- but never more k-blocks per
+            // accumulator chain than kMaxChainKb
+            const int nkb_all = (K + BK - 1) / BK;
+            const int live_tiles = ((m_live + BM - 1) / BM) * n_tiles;
+            int splits = sm_count / live_tiles;
+            splits = max(splits, (nkb_all + kMaxChainKb - 1) / kMaxChainKb);
+            splits = max(1, min(splits, (int)gridDim.y));
+            kb_per_split = (nkb_all + splits - 1) / splits;
+            if ((int)blockIdx.y * kb_per_split >= nkb_all) return;
+        }
+    }
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_holder;
@@ -471,9 +493,12 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
         const cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles), (unsigned)splits);
     gpt_launch(tf32_gemm_kernel<PASSES>, grid, dim3(kGemmThreads), smem, st, tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
-                                                               tmem_cols, stages, ep, kb_per_split);
+                                                               tmem_cols, stages, ep, kb_per_split, sms);
     return gpt_launch_status();
 }
 
@@ -494,7 +519,7 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
     const int m_tiles = (M + BM - 1) / BM;
     const int nkb_all = (K + BK - 1) / BK;
     int cap = 256, splits = 1;
-    if (nkb_all >= 64 && (long)m_tiles * ((N + 255) / 256) < 74) {
+    if (nkb_all >= 64 && (ep.m_live != nullptr || (long)m_tiles * ((N + 255) / 256) < 74)) {
         // long reduction, few output tiles: keep the N tile wide (the X tile is loaded and split once per N tile) and
         // fill the machine by splitting K instead
         splits = 148 / (m_tiles * ((N + 255) / 256));
@@ -503,6 +528,9 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
         // kMaxChainKb k-blocks (x 4 K-steps x 3 passes = 384 additions, <= 7e-6) go into one accumulator chain; a second
         // wave of CTAs costs less than the fp32 grade of the result
         if (splits < (nkb_all + kMaxChainKb - 1) / kMaxChainKb) splits = (nkb_all + kMaxChainKb - 1) / kMaxChainKb;
+        // device-side row count: how many row tiles are live is not known here; launch the finest split (8 k-blocks per
+        // range) and let the kernel choose (tf32_gemm_kernel)
+        if (ep.m_live != nullptr) splits = nkb_all / 8;
         if (splits < 1) splits = 1;
     } else {
         while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
@@ -713,6 +741,23 @@ extern "C" int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* 
     GPT_CHECK_ARG(dy && ws && dx && M >= 0 && N >= 1 && K >= 1);
     const size_t nk = (size_t)N * K;
     return run_tf32_gemm(dy, ws + 2 * nk, ws + 3 * nk, dx, M, K, N, (cudaStream_t)stream);
+}
+
+// the same two projections over the first *m_live rows only (device-side count, gpt_live_rows); rows beyond it are not
+// computed and the corresponding rows of the output keep whatever they held
+extern "C" int gpt_linear_fwd_tf32x3_rows(const float* x, const float* ws, float* y, int M, int N, int K,
+                                          const int32_t* m_live, void* stream) {
+    GPT_CHECK_ARG(x && ws && y && m_live && M >= 0 && N >= 1 && K >= 1);
+    return run_tf32_gemm(x, ws, ws + (size_t)N * K, y, M, N, K, (cudaStream_t)stream,
+                         MaskEpilogue{nullptr, nullptr, 1.f, 1, m_live});
+}
+
+extern "C" int gpt_linear_dgrad_tf32x3_rows(const float* dy, const float* ws, float* dx, int M, int N, int K,
+                                            const int32_t* m_live, void* stream) {
+    GPT_CHECK_ARG(dy && ws && dx && m_live && M >= 0 && N >= 1 && K >= 1);
+    const size_t nk = (size_t)N * K;
+    return run_tf32_gemm(dy, ws + 2 * nk, ws + 3 * nk, dx, M, K, N, (cudaStream_t)stream,
+                         MaskEpilogue{nullptr, nullptr, 1.f, 1, m_live});
 }
 
 extern "C" int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, const uint32_t* act_prev,

@@ -43,7 +43,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
                     const unsigned char* __restrict__ flags, float* __restrict__ dW, long long M, int N, int K,
-                    int n_slices, long long rows_per_part, int kboxes, int tmem_cols, int STAGES) {
+                    int n_slices, long long rows_per_part, int kboxes, int tmem_cols, int STAGES,
+                    const int* __restrict__ m_live) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * WG_MAX_STAGES + 2];
     __shared__ uint32_t tmem_base_holder;
@@ -51,6 +52,13 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = (int)(blockIdx.x % n_slices) * WG_NSLICE;
     const long long part = blockIdx.x / n_slices;
+    if (m_live != nullptr) {
+        // device-side row count: the row ranges are cut here, over the live rows only (the host cut them over all M rows)
+        const long long live = *m_live < M ? *m_live : M;
+        const long long parts = gridDim.x / n_slices;
+        M = live;
+        rows_per_part = ((live + WG_ROWS - 1) / WG_ROWS + parts - 1) / parts * WG_ROWS;
+    }
     const long long m_begin = part * rows_per_part;
     const long long m_end = m_begin + rows_per_part < M ? m_begin + rows_per_part : M;
     const int nkb = m_end > m_begin ? (int)((m_end - m_begin + WG_ROWS - 1) / WG_ROWS) : 0;
@@ -217,8 +225,9 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
 // dw[N,K] += dy[M,N]^T . x[M,K] over the rows with flags[m] != 0 (flags == NULL: every row).  GPT_ERR_UNSUPPORTED when
 // the shape cannot be described to TMA / does not fit tensor memory (K > 512, K or N not a multiple of 4): callers fall
 // back to gpt_linear_wgrad_rows_f32.
-extern "C" int gpt_linear_wgrad_tf32x3(const float* dy, const float* x, const uint8_t* flags, float* dw, long long M,
-                                       int N, int K, void* stream) {
+// m_live: optional device-side row count (gpt_live_rows): only rows m < *m_live are read
+extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, const uint8_t* flags, float* dw, long long M,
+                                            int N, int K, const int32_t* m_live, void* stream) {
     GPT_CHECK_ARG(dy && x && dw && M >= 0 && N >= 1 && K >= 1);
     if (M == 0) return GPT_OK;
     if (K % 4 != 0 || N % 4 != 0 || K > 512 || M > 0x7fffffffLL - 64 || (reinterpret_cast<uintptr_t>(dy) & 15) ||
@@ -231,13 +240,20 @@ extern "C" int gpt_linear_wgrad_tf32x3(const float* dy, const float* x, const ui
     int stages = (int)((220 * 1024) / stage);
     stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
     if (stages < 2) return GPT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)stages * stage + 1024;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_slices = (N + WG_NSLICE - 1) / WG_NSLICE;
     long long m_parts = sms / n_slices;
     if (m_parts < 1) m_parts = 1;
+    // When one CTA per SM would leave a quarter of the SMs without one (79 slices of a [D*H = 10 000, K] gradient on 148
+    // SMs), run TWO CTAs per SM with a two-stage ring each: twice the row ranges, every SM's tensor core fed by two
+    // independent pipelines.  Needs both accumulators in tensor memory (2 x <= 256 columns) and both rings in shared memory.
+    if (n_slices * m_parts * 4 < 3LL * sms && tmem_cols <= 256 && 2 * (2 * stage + 1024) + 2048 <= 227 * 1024) {
+        stages = 2;
+        m_parts = 2LL * sms / n_slices;
+    }
+    const size_t smem = (size_t)stages * stage + 1024;
     const long long blocks16 = (M + WG_ROWS - 1) / WG_ROWS;
     if (m_parts > blocks16) m_parts = blocks16;
     const long long rows_per_part = ((blocks16 + m_parts - 1) / m_parts) * WG_ROWS;
@@ -248,6 +264,11 @@ extern "C" int gpt_linear_wgrad_tf32x3(const float* dy, const float* x, const ui
     if ((rc = tc::make_map_f32(&tm_x, x, M, K, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GPT_OK) return rc;
     if (int a = gpt_smem_opt_in(wgrad_tf32x3_kernel, smem)) return a;
     wgrad_tf32x3_kernel<<<(unsigned)(n_slices * m_parts), WG_THREADS, smem, (cudaStream_t)stream>>>(
-        tm_dy, tm_x, flags, dw, M, N, K, n_slices, rows_per_part, kboxes, tmem_cols, stages);
+        tm_dy, tm_x, flags, dw, M, N, K, n_slices, rows_per_part, kboxes, tmem_cols, stages, m_live);
     return gpt_launch_status();
+}
+
+extern "C" int gpt_linear_wgrad_tf32x3(const float* dy, const float* x, const uint8_t* flags, float* dw, long long M,
+                                       int N, int K, void* stream) {
+    return gpt_linear_wgrad_tf32x3_rows(dy, x, flags, dw, M, N, K, nullptr, stream);
 }

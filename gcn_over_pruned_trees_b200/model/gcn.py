@@ -227,6 +227,9 @@ class GCN(nn.Module):
             # the projection GEMM wants the [D*H, in] matrix whose row d*H+h is weight_l[d, :, h]
             wmat = self.W.weight.reshape(D, -1, H).permute(0, 2, 1).reshape(D * H, -1).contiguous()
             ws = ops.weight_prep(wmat.detach(), self.gemm_mode)
+            # only rows some pool can see are projected and mixed (a quarter of a TACRED-shaped batch at prune_k = 1): the
+            # reference computes all of them and masks the rest away in pool() (gcn.py:116-120, 262)
+            live = ops.LiveRows(csr.flags) if os.environ.get('GPT_K10_COMPACT', '1') != '0' else None
         else:
             x = ops.linear(x, self.preprocessor.weight, self.preprocessor.bias, self.gemm_mode)    # gcn.py:255-257
         B, T = csr.B, csr.T
@@ -235,7 +238,7 @@ class GCN(nn.Module):
             mask = None if injected is None else injected.get('gcn%d' % l)
             cfg = ops.RelationLayerConfig(l, drop_p=0.0 if (last or mask is not None) else drop_p,
                                           drop_mask=None if last else mask, rng_state=rng,
-                                          gemm_mode=self.gemm_mode)
+                                          gemm_mode=self.gemm_mode, live=live if full else None)
             if not full:
                 x = ops.relation_layer_diag(x, emb, csr, deprel, cfg)
                 continue

@@ -400,10 +400,11 @@ def linear(x, weight, bias=None, gemm_mode='fp32'):
 class RelationLayerConfig(object):
     """Per-layer switches of the relation-aware modes (all host scalars except the optional test masks)."""
     __slots__ = ('layer', 'deep', 'directed', 'self_loop', 'edge_keep', 'keep_edges', 'keep_tokens', 'drop_p',
-                 'drop_mask', 'rng_state', 'gemm_mode')
+                 'drop_mask', 'rng_state', 'gemm_mode', 'live')
 
     def __init__(self, layer, deep=False, directed=False, self_loop=True, edge_keep=1.0, keep_edges=None,
-                 keep_tokens=None, drop_p=0.0, drop_mask=None, rng_state=None, gemm_mode='fp32'):
+                 keep_tokens=None, drop_p=0.0, drop_mask=None, rng_state=None, gemm_mode='fp32', live=None):
+        self.live = live                    # None or the batch's LiveRows: project / mix only the observable rows
         self.layer, self.deep, self.directed, self.self_loop = int(layer), bool(deep), bool(directed), bool(self_loop)
         self.edge_keep = float(edge_keep)
         self.keep_edges = keep_edges        # None or (uint8 [B,T,T] parent->child matrix, uint8 [B,T,T] child->parent)
@@ -426,6 +427,67 @@ def relation_keep_tokens(rng_state, n_rows, layer, keep_prop):
     _call('gpt_relation_keep_tokens', _ptr(rng_state), int(n_rows), int(layer), float(keep_prop), _ptr(kf), _ptr(kr),
           _stream())
     return kf, kr
+
+
+class LiveRows(object):
+    """The observable rows of a batch (flags != 0: inside a pruned tree, or a subject / object token), compacted on the
+    device by ``gpt_live_rows``: ``perm`` int32 [N] (ascending row ids, first ``count`` entries), ``inv`` int32 [N],
+    ``live`` uint8 [N] (``i < count``), ``count`` int32 [1].  The count never comes to the host (graph capture)."""
+    __slots__ = ('N', 'perm', 'inv', 'live', 'count')
+
+    def __init__(self, flags):
+        flags = _dev(flags, torch.uint8, 'flags')
+        self.N = N = flags.numel()
+        self.perm = torch.empty((N,), dtype=torch.int32, device=flags.device)
+        self.inv = torch.empty((N,), dtype=torch.int32, device=flags.device)
+        self.live = torch.empty((N,), dtype=torch.uint8, device=flags.device)
+        self.count = torch.empty((1,), dtype=torch.int32, device=flags.device)
+        _call('gpt_live_rows', _ptr(flags), N, _ptr(self.perm), _ptr(self.inv), _ptr(self.live), _ptr(self.count), _stream())
+
+    def gather(self, x2d):
+        """[N,K] -> compact [N,K]: row i < count is x2d[perm[i]]; the rest is never read."""
+        out = torch.empty_like(x2d)
+        _call('gpt_gather_rows', _ptr(x2d), _ptr(self.perm), _ptr(self.count), self.N, x2d.shape[1], _ptr(out), _stream())
+        return out
+
+    def scatter(self, xc):
+        """compact [N,K] -> [N,K] with zeros on the rows that are not observable."""
+        out = torch.empty_like(xc)
+        _call('gpt_scatter_rows', _ptr(xc), _ptr(self.inv), self.N, xc.shape[1], _ptr(out), _stream())
+        return out
+
+
+def _linear_fwd_rows(xc, weight, mode, ws, live):
+    M, K = xc.shape
+    N = weight.shape[0]
+    if mode == 'tf32x3' and ws is not None and M < 65536:
+        y = torch.empty((M, N), dtype=torch.float32, device=xc.device)
+        _call('gpt_linear_fwd_tf32x3_rows', _ptr(xc), _ptr(ws), _ptr(y), M, N, K, _ptr(live.count), _stream())
+        return y
+    return linear_fwd(xc, weight, mode, ws)          # every row: the ones beyond count are scratch
+
+
+def _linear_dgrad_rows(dyc, weight, mode, ws, live):
+    M, N = dyc.shape
+    K = weight.shape[1]
+    if mode == 'tf32x3' and ws is not None and M < 65536:
+        dx = torch.empty((M, K), dtype=torch.float32, device=dyc.device)
+        _call('gpt_linear_dgrad_tf32x3_rows', _ptr(dyc), _ptr(ws), _ptr(dx), M, N, K, _ptr(live.count), _stream())
+        return dx
+    return linear_dgrad(dyc, weight, mode, ws)
+
+
+def _linear_wgrad_rows(dyc, xc, mode, live):
+    """dw = dyc^T xc over the compact rows i < count (the rows beyond hold scratch: `live.live` masks them)."""
+    M, N = dyc.shape
+    K = xc.shape[1]
+    dw = torch.zeros((N, K), dtype=torch.float32, device=dyc.device)
+    if mode in ('tf32x3', 'bf16') and wgrad_tc_ok(M, N, K):
+        _call('gpt_linear_wgrad_tf32x3_rows', _ptr(dyc), _ptr(xc), _ptr(live.live), _ptr(dw), M, N, K, _ptr(live.count),
+              _stream())
+    else:
+        _call('gpt_linear_wgrad_rows_f32', _ptr(dyc), _ptr(xc), _ptr(live.live), _ptr(dw), M, N, K, _stream())
+    return dw
 
 
 def _agg3_fwd(F, R, S, csr, cfg):
@@ -469,35 +531,51 @@ class _RelationLayerFull(torch.autograd.Function):
         N = B * T
         if emb.shape[0] != 85 or wmat.shape != (D * H, K) or bias.numel() != D * H:
             raise _lib.GptError('full_deprel layer: inconsistent shapes')
-        Z = linear_fwd(x.view(N, K), wmat, cfg.gemm_mode, ws)
+        live = cfg.live
+        # with `live`: xs / Z are COMPACT (row i < count belongs to token perm[i]); F, R, S and out stay per token
+        xs = x.view(N, K) if live is None else live.gather(x.view(N, K))
+        Z = linear_fwd(xs, wmat, cfg.gemm_mode, ws) if live is None else _linear_fwd_rows(xs, wmat, cfg.gemm_mode, ws, live)
         F, R, S = (torch.empty((N, H), dtype=torch.float32, device=x.device) for _ in range(3))
         kf, kr = cfg.keep_tokens if cfg.keep_tokens is not None else (None, None)
-        _call('gpt_relmix_fwd', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr), N, D,
-              H, int(cfg.deep), _ptr(F), _ptr(R), _ptr(S), _stream())
+        _call('gpt_relmix_fwd_rows', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
+              _ptr(None if live is None else live.perm), _ptr(None if live is None else live.count), N, D, H,
+              int(cfg.deep), _ptr(F), _ptr(R), _ptr(S), _stream())
         out = _agg3_fwd(F, R, S, csr, cfg)
         ctx.csr, ctx.cfg, ctx.dims = csr, cfg, (B, T, K, D, H)
-        ctx.save_for_backward(x, wmat, bias, emb, deprel, Z, out, ws)
+        ctx.save_for_backward(xs, wmat, bias, emb, deprel, Z, out, ws)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, wmat, bias, emb, deprel, Z, out, ws = ctx.saved_tensors
+        xs, wmat, bias, emb, deprel, Z, out, ws = ctx.saved_tensors
         csr, cfg = ctx.csr, ctx.cfg
+        live = cfg.live
         B, T, K, D, H = ctx.dims
         N = B * T
         gout = _dev(gout, torch.float32, 'grad_out')
         dF, dR, dS = _agg3_bwd(gout, out, csr, cfg)
-        dZ = torch.empty((N, D * H), dtype=torch.float32, device=gout.device)
+        dZ = torch.empty((N, D * H), dtype=torch.float32, device=gout.device)     # compact, like Z, when `live`
         dE = torch.zeros_like(emb)
         kf, kr = cfg.keep_tokens if cfg.keep_tokens is not None else (None, None)
-        _call('gpt_relmix_bwd', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
-              _ptr(dF), _ptr(dR), _ptr(dS), N, D, H, int(cfg.deep), _ptr(dZ), _ptr(dE), _stream())
+        cnt = None if live is None else live.count
+        _call('gpt_relmix_bwd_rows', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
+              _ptr(None if live is None else live.perm), _ptr(cnt), _ptr(dF), _ptr(dR), _ptr(dS), N, D, H, int(cfg.deep),
+              _ptr(dZ), _ptr(dE), _stream())
         dbias = None
         if ctx.needs_input_grad[2]:
             dbias = torch.zeros((D * H,), dtype=torch.float32, device=gout.device)
-            _call('gpt_colsum_acc', _ptr(dZ), N, D * H, _ptr(dbias), _stream())
-        dx = linear_dgrad(dZ, wmat, cfg.gemm_mode, ws).view(B, T, K) if ctx.needs_input_grad[0] else None
-        dw = linear_wgrad(dZ, x.view(N, K), cfg.gemm_mode) if ctx.needs_input_grad[1] else None
+            _call('gpt_colsum_acc_rows', _ptr(dZ), N, D * H, _ptr(cnt), _ptr(dbias), _stream())
+        dx = dw = None
+        if live is None:
+            if ctx.needs_input_grad[0]:
+                dx = linear_dgrad(dZ, wmat, cfg.gemm_mode, ws).view(B, T, K)
+            if ctx.needs_input_grad[1]:
+                dw = linear_wgrad(dZ, xs, cfg.gemm_mode)
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = live.scatter(_linear_dgrad_rows(dZ, wmat, cfg.gemm_mode, ws, live)).view(B, T, K)
+            if ctx.needs_input_grad[1]:
+                dw = _linear_wgrad_rows(dZ, xs, cfg.gemm_mode, live)
         return dx, dw, dbias, (dE if ctx.needs_input_grad[3] else None), None, None, None, None
 
 

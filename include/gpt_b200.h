@@ -350,6 +350,38 @@ int gpt_relation_keep_tokens(const void* rng_state, int N, unsigned layer, float
 /* out[c] += sum_r a[r,c] (bias gradient of the shared projection); out is caller-zeroed */
 int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* stream);
 
+/* K10 over the OBSERVABLE rows only.  The reference computes every [B,T] position of every layer (gcn.py:296-386) although
+ * only rows inside a pruned tree, or subject / object tokens, ever reach a pool (gcn.py:116-120, 262); at prune_k = 1 that is
+ * a quarter of a TACRED-shaped batch.  gpt_live_rows lists the rows with flags != 0 (gpt_prune_csr) in ascending order:
+ * perm int32 [N] (first *count entries), inv int32 [N] (position of row n in perm, or -1), live uint8 [N] (i < count: the
+ * row flags of the compact arrays, which the weight-gradient entry points take), count int32 [1] -- which stays on the
+ * device: a captured step never learns it on the host, so every consumer below takes the POINTER.
+ *   gpt_gather_rows       out[i,:] = x[perm[i],:]  for i < *count           (x, out float [N,K]; other rows of out untouched)
+ *   gpt_scatter_rows      dx[n,:] = inv[n] >= 0 ? dxc[inv[n],:] : 0        for every n < N
+ *   gpt_linear_{fwd,dgrad}_tf32x3_rows, gpt_linear_wgrad_tf32x3_rows:  the projections of gpt_linear_*_tf32x3 over the first
+ *                         *m_live rows (row tiles beyond leave at once; output rows beyond keep what they held)
+ *   gpt_relmix_{fwd,bwd}_rows   Z / dZ compact [count, D*H], everything per token (deprel, flags, keep_*, F/R/S, dF/dR/dS)
+ *                         addressed through perm; perm == count == NULL is gpt_relmix_{fwd,bwd}.  Rows with flags == 0 are
+ *                         not written in the compact form (nothing reads them: the aggregation gathers kept rows only)
+ *   gpt_colsum_acc_rows   gpt_colsum_acc over rows r < *count */
+int gpt_live_rows(const uint8_t* flags, int N, int32_t* perm, int32_t* inv, uint8_t* live, int32_t* count, void* stream);
+int gpt_gather_rows(const float* x, const int32_t* perm, const int32_t* count, int N, int K, float* out, void* stream);
+int gpt_scatter_rows(const float* dxc, const int32_t* inv, int N, int K, float* dx, void* stream);
+int gpt_linear_fwd_tf32x3_rows(const float* x, const float* ws, float* y, int M, int N, int K, const int32_t* m_live,
+                               void* stream);
+int gpt_linear_dgrad_tf32x3_rows(const float* dy, const float* ws, float* dx, int M, int N, int K, const int32_t* m_live,
+                                 void* stream);
+int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, const uint8_t* flags, float* dw, long long M, int N, int K,
+                                 const int32_t* m_live, void* stream);
+int gpt_relmix_fwd_rows(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                        const uint8_t* keep_f, const uint8_t* keep_r, const int32_t* perm, const int32_t* count, int N, int D,
+                        int H, int deep, float* F, float* R, float* S, void* stream);
+int gpt_relmix_bwd_rows(const float* Z, const float* bias, const float* E, const int64_t* deprel, const uint8_t* flags,
+                        const uint8_t* keep_f, const uint8_t* keep_r, const int32_t* perm, const int32_t* count,
+                        const float* dF, const float* dR, const float* dS, int N, int D, int H, int deep, float* dZ, float* dE,
+                        void* stream);
+int gpt_colsum_acc_rows(const float* a, long long rows, int cols, const int32_t* count, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

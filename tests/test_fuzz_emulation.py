@@ -18,7 +18,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu
 NAMES = ('gpt_prune_csr', 'gpt_gcn_aggregate_fwd', 'gpt_gcn_aggregate_bwd', 'gpt_pool3_fwd', 'gpt_pool3_bwd',
          'gpt_embed_fwd', 'gpt_embed_bwd', 'gpt_linear_fwd_f32', 'gpt_linear_dgrad_f32', 'gpt_linear_wgrad_f32',
          'gpt_relmix_fwd', 'gpt_relmix_bwd', 'gpt_diagmix_fwd', 'gpt_diagmix_bwd', 'gpt_agg3_fwd', 'gpt_agg3_bwd',
-         'gpt_colsum_acc')
+         'gpt_colsum_acc', 'gpt_live_rows', 'gpt_gather_rows', 'gpt_scatter_rows', 'gpt_relmix_fwd_rows', 'gpt_relmix_bwd_rows',
+       'gpt_colsum_acc_rows', 'gpt_linear_wgrad_rows_f32')
 
 
 @pytest.fixture(scope='module', autouse=True)

@@ -100,3 +100,49 @@ def test_split_k_of_long_reductions_in_the_one_tile_kernel(M, N, K):
         ws = ops.weight_prep(w, 'tf32x3')
         dx = ops.linear_dgrad(dy, w, 'tf32x3', ws)
         assert _rel(dx, dy.double() @ w.double()) <= 1e-5
+
+
+@pytest.mark.parametrize('cg', (1, 2))
+@pytest.mark.parametrize('live', (0, 1, 257, 1000, 3000))
+def test_wide_projection_with_a_device_side_row_count(cg, live):
+    """gpt_linear_fwd_tf32x3_rows on a wide output (the relation-aware layers' [rows, D*H] projection): the persistent
+    kernel deals the tiles round-robin over the clusters and stops at the last live row block -- same bits as the
+    one-tile kernel on the live rows, nothing written past the last live block."""
+    M, N, K = 3000, 2560, 200
+    g = torch.Generator(device=DEV).manual_seed(live + cg)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / np.sqrt(K)
+    ws = ops.weight_prep(w, 'tf32x3')
+    count = torch.tensor([live], dtype=torch.int32, device=DEV)
+    out = []
+    for mode in (0, cg):
+        ops.gemm_persist_config(mode, 65536)
+        y = torch.full((M, N), 7.0, device=DEV)
+        ops._call('gpt_linear_fwd_tf32x3_rows', x.data_ptr(), ws.data_ptr(), y.data_ptr(), M, N, K, count.data_ptr(),
+                  ops._stream())
+        out.append(y)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0][:live], out[1][:live])
+    if live:
+        assert _rel(out[1][:live], x[:live].double() @ w.double().t()) <= 1e-5
+    block = 128 * cg
+    touched = min(M, (live + block - 1) // block * block)
+    assert bool((out[1][touched:] == 7.0).all())
+
+
+@pytest.mark.parametrize('live', (0, 130, 1000, 2900))
+def test_split_k_data_gradient_with_a_device_side_row_count(live):
+    """gpt_linear_dgrad_tf32x3_rows (reduction over D*H = 10 000): the number of K ranges is chosen on the device from the
+    live row tiles; 3xTF32 tolerance 1e-5."""
+    M, N, K = 3000, 10000, 200
+    g = torch.Generator(device=DEV).manual_seed(live)
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / np.sqrt(N)
+    ws = ops.weight_prep(w, 'tf32x3')
+    count = torch.tensor([live], dtype=torch.int32, device=DEV)
+    dx = torch.empty((M, K), device=DEV)
+    ops._call('gpt_linear_dgrad_tf32x3_rows', dy.data_ptr(), ws.data_ptr(), dx.data_ptr(), M, N, K, count.data_ptr(),
+              ops._stream())
+    torch.cuda.synchronize()
+    if live:
+        assert _rel(dx[:live], dy[:live].double() @ w.double()) <= 1e-5

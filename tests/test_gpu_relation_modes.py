@@ -230,3 +230,67 @@ def test_relation_mode_checkpoint_round_trip(golden_adj, tmp_path):
     sd = b.model.state_dict()
     assert sd['gcn_model.deprel_emb.weight'].data_ptr() == sd['gcn_model.gcn.deprel_emb.weight'].data_ptr()
     assert tuple(sd['gcn_model.gcn.W.weight'].shape) == (8 * 64, 64)
+
+
+@pytest.mark.parametrize('frac', (0.0, 0.27, 1.0))
+def test_live_row_compaction_and_row_limited_projections(frac):
+    """gpt_live_rows / gather / scatter and the projections that take their row count from the device
+    (gpt_linear_{fwd,dgrad,wgrad}_tf32x3_rows): the rows beyond the count hold NaN scratch here and must never leak.
+    3xTF32 tolerance 1e-5 relative of the largest element, against float64."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    N, K, DH = 3000, 200, 2560
+    flags = (torch.rand(N, device=DEV, generator=g) < frac).to(torch.uint8) * 3
+    live = ops.LiveRows(flags)
+    idx = flags.nonzero().flatten()
+    cnt = int(live.count)
+    assert cnt == idx.numel()
+    assert torch.equal(live.perm[:cnt].long(), idx)
+    expect_inv = torch.full((N,), -1, dtype=torch.int32, device=DEV)
+    expect_inv[idx] = torch.arange(cnt, dtype=torch.int32, device=DEV)
+    assert torch.equal(live.inv, expect_inv)
+    assert torch.equal(live.live, (torch.arange(N, device=DEV) < cnt).to(torch.uint8))
+
+    x = torch.randn(N, K, device=DEV, generator=g)
+    xc = live.gather(x)
+    assert torch.equal(xc[:cnt], x[idx])
+    xc[cnt:] = float('nan')
+    w = torch.randn(DH, K, device=DEV, generator=g) / np.sqrt(K)
+    ws = ops.weight_prep(w, 'tf32x3')
+    y = ops._linear_fwd_rows(xc, w, 'tf32x3', ws, live)
+    dy = torch.randn(N, DH, device=DEV, generator=g)
+    dy[cnt:] = float('nan')
+    dxc = ops._linear_dgrad_rows(dy, w, 'tf32x3', ws, live)
+    dx = live.scatter(dxc)
+    dw = ops._linear_wgrad_rows(dy, xc, 'tf32x3', live)
+    torch.cuda.synchronize()
+    dead = flags == 0
+    assert not bool(dx[dead].ne(0).any()) and torch.equal(dx[idx], dxc[:cnt])
+    if cnt == 0:
+        assert not bool(dw.ne(0).any())
+        return
+    assert _rel(y[:cnt].cpu(), (xc[:cnt].double() @ w.double().t()).cpu()) <= 1e-5
+    assert _rel(dxc[:cnt].cpu(), (dy[:cnt].double() @ w.double()).cpu()) <= 1e-5
+    assert _rel(dw.cpu(), (dy[:cnt].double().t() @ xc[:cnt].double()).cpu()) <= 1e-5
+    db = torch.zeros(DH, device=DEV)
+    ops._call('gpt_colsum_acc_rows', dy.data_ptr(), N, DH, live.count.data_ptr(), db.data_ptr(), ops._stream())
+    assert _rel(db.cpu(), dy[:cnt].double().sum(0).cpu()) <= 1e-5
+
+
+def test_full_deprel_compacted_rows_equal_all_rows(golden_adj, monkeypatch):
+    """The layer over the observable rows only == the layer over every row (GPT_K10_COMPACT=0): logits, loss and every
+    gradient, 1e-5 / 1e-4 (the two differ in summation order only)."""
+    res = []
+    for compact in ('1', '0'):
+        monkeypatch.setenv('GPT_K10_COMPACT', compact)
+        opt, batch, trainer, _ = _setup(golden_adj, 'full_k1_d8', 'tf32x3')
+        trainer.model.train()
+        masks = _injected_masks(opt, batch, seed=5, edges=True, forget=True)
+        trainer.model.gcn_model.gcn.injected_masks = {k: v.to(DEV) for k, v in masks.items()}
+        loss = trainer.update(batch)
+        loss.backward()
+        res.append((loss.item(), {n: p.grad.detach().cpu().numpy() for n, p in trainer.model.named_parameters()
+                                  if p.grad is not None}))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
+    assert len(res[0][1]) == len(res[1][1]) >= 8
+    for n, g in res[1][1].items():
+        assert _rel(res[0][1][n], g) <= 1e-4, n
