@@ -88,7 +88,7 @@ SIGNATURES = {
     'gpt_live_rows': [_p, _c_int, _p, _p, _p, _p, _p],
     'gpt_gather_rows': [_p, _p, _p, _c_int, _c_int, _p, _p],
     'gpt_scatter_rows': [_p, _p, _c_int, _c_int, _p, _p],
-    'gpt_linear_fwd_tf32x3_rows': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
+    'gpt_linear_fwd_tf32x3_rows': [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_linear_dgrad_tf32x3_rows': [_p, _p, _p, _c_int, _c_int, _c_int, _p, _p],
     'gpt_linear_wgrad_tf32x3_rows': [_p, _p, _p, _p, _c_ll, _c_int, _c_int, _p, _p],
     'gpt_relmix_fwd_rows': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p],

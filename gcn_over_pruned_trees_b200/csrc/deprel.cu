@@ -110,10 +110,9 @@ __global__ void __launch_bounds__(kThreads) relmix_fwd_kernel(const MixParams p)
         __syncthreads();
         for (int h = threadIdx.x; h < p.H; h += blockDim.x) {
             const float* __restrict__ z = p.Z + (size_t)i * DH + h;
-            const float* __restrict__ b = p.bias + h;
             float f = 0.f, r = 0.f, s = 0.f;
             for (int d = 0; d < p.D; ++d) {
-                const float v = z[(size_t)d * p.H] + b[(size_t)d * p.H];
+                const float v = z[(size_t)d * p.H] + (p.bias != nullptr ? p.bias[(size_t)d * p.H + h] : 0.f);
                 f = fmaf(ef[d], v, f);
                 r = fmaf(er[d], v, r);
                 s = fmaf(es[d], v, s);
@@ -164,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) relmix_bwd_kernel(const MixParams p)
             const float a = ef[d], b = er[d], c = es[d];
             float sf = 0.f, sr = 0.f, ss = 0.f;
             for (int h = lane; h < p.H; h += 32) {
-                const float v = z[(size_t)d * p.H + h] + p.bias[(size_t)d * p.H + h];
+                const float v = z[(size_t)d * p.H + h] + (p.bias != nullptr ? p.bias[(size_t)d * p.H + h] : 0.f);
                 const float x = gf[h], y = gr[h], w = gs[h];
                 sf = fmaf(x, v, sf);
                 sr = fmaf(y, v, sr);
@@ -218,6 +217,7 @@ __global__ void __launch_bounds__(kMixThreads) relmix_fwd4_kernel(const MixParam
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5, hq = p.H >> 2;
     const size_t DH = (size_t)p.D * p.H;
     const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(p.bias);
+    const bool has_b = p.bias != nullptr;       // else the projection's epilogue already added it to Z
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     const int rows = mix_rows(p);
     for (int i = blockIdx.x; i < rows; i += gridDim.x) {
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kMixThreads) relmix_fwd4_kernel(const MixParam
             float4 f = zero, r = zero, s = zero;
 #pragma unroll 4
             for (int d = warp; d < p.D; d += nw) {
-                const float4 z = z4[(size_t)d * hq + c], b = bias4[(size_t)d * hq + c];
+                const float4 z = z4[(size_t)d * hq + c], b = has_b ? bias4[(size_t)d * hq + c] : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 v = make_float4(z.x + b.x, z.y + b.y, z.z + b.z, z.w + b.w);
                 f = f4_fma(ef[d], v, f);
                 r = f4_fma(er[d], v, r);
@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(kMixThreads, 3) relmix_bwd4_kernel(const MixPa
     const size_t DH = (size_t)p.D * p.H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(p.bias);
+    const bool has_b = p.bias != nullptr;       // else the projection's epilogue already added it to Z
     for (int d = threadIdx.x; d < p.D; d += blockDim.x) acc84[d] = 0.f;
     __syncthreads();
     const int rows = mix_rows(p);
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kMixThreads, 3) relmix_bwd4_kernel(const MixPa
                     for (int j = 0; j < 2; ++j) {
                         const int q = q0 + 32 * j;
                         if (q >= hq) break;
-                        const float4 z = zv[u][j], bb = bias4[(size_t)d * hq + q];
+                        const float4 z = zv[u][j], bb = has_b ? bias4[(size_t)d * hq + q] : make_float4(0.f, 0.f, 0.f, 0.f);
                         const float4 v = make_float4(z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w);
                         const float4 x = gf[q], y = gr[q], w = gs[q];
                         sf[u] = f4_dot(x, v, sf[u]);
@@ -349,6 +350,276 @@ __global__ void __launch_bounds__(kMixThreads, 3) relmix_bwd4_kernel(const MixPa
     }
     if (!p.deep)
         for (int d = warp; d < p.D; d += nw)
+            if (lane == 0 && acc84[d] != 0.f) atomicAdd(p.dE + (size_t)kRevBound * p.D + d, acc84[d]);
+}
+
+// ---- relation mix over the compacted rows: rows streamed through shared memory by bulk copies ---------------------------
+// One row is 40 KB of Z (D = 50, H = 200) behind a chain of dependent loads: perm[i] -> deprel[n], keep[n] -> E rows (and,
+// backward, the dF / dR / dS rows).  With one row per CTA and per-thread loads that chain and the load round trips, not
+// the 40 KB, are the row's time (ncu: every sample on a long-scoreboard stall, 10 % of DRAM bandwidth).  Here a CTA walks
+// rows i, i + grid, ... and a NINTH warp runs one row ahead of the eight compute warps: it fetches the next row's vectors
+// into the other half of a double buffer and brings the next row of Z in with ONE bulk copy (cp.async.bulk, completion on
+// an mbarrier) -- 2 x 40 KB per CTA and two CTAs per SM keep ~160 KB per SM in flight without a register being spent on it.
+constexpr int kPipeThreads = kMixThreads + 32;
+
+struct RowMeta {
+    int n, rf, forget_f, forget_r;
+};
+
+#ifdef GPT_HOST_EMULATION
+// host build (tests/emu): the staging copy is done by the fetch warp's lanes, synchronously; the row barrier orders it
+__device__ inline void stage_init(unsigned long long*, int) {}
+__device__ inline void stage_expect(unsigned long long*, int, int) {}
+__device__ inline void stage_row(float* dst, const float* src, int n_floats, unsigned long long*, int lane) {
+    for (int k = lane; k < n_floats; k += 32) dst[k] = src[k];
+}
+__device__ inline void stage_wait(unsigned long long*, unsigned) {}
+#else
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_init(unsigned long long* bars, int lane) {
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_addr(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_addr(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+// one elected lane: expect `total_floats` on the barrier (the sum over every copy of this phase) ...
+__device__ __forceinline__ void stage_expect(unsigned long long* bar, int total_floats, int lane) {
+    if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_addr(bar)), "r"((uint32_t)total_floats * 4u)
+                     : "memory");
+}
+// ... and one bulk copy global -> shared per call (16-byte aligned, a multiple of 16 bytes)
+__device__ __forceinline__ void stage_row(float* dst, const float* src, int n_floats, unsigned long long* bar, int lane) {
+    if (lane == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sm_addr(dst)), "l"(src), "r"((uint32_t)n_floats * 4u), "r"(sm_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void stage_wait(unsigned long long* bar, unsigned parity) {
+    uint32_t ok, spins = 0;
+    const uint32_t b = sm_addr(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();      // a lost copy must fail the launch, never hang the GPU
+    } while (!ok);
+}
+#endif
+
+// The fetch warp resolves perm[i] -> deprel[n], keep[n] for 32 of its CTA's rows at once (lane l: the l-th next row), so
+// that two of the three dependent round trips of a row's prologue are paid once per 32 rows, not once per row.
+__device__ __forceinline__ void pipe_resolve(const MixParams& p, int i0, int rows, RowMeta* table, int lane) {
+    const long long i = (long long)i0 + (long long)lane * gridDim.x;
+    if (i < rows) {
+        const int n = p.perm[i];
+        const int rf = rel_id(p.deprel[n]);
+        const bool forget_f = p.deep || (p.keep_f != nullptr && p.keep_f[n] == 0);
+        const bool forget_r = p.deep || (p.keep_r != nullptr && p.keep_r[n] == 0);
+        table[lane] = RowMeta{n, rf, forget_f ? 1 : 0, forget_r ? 1 : 0};
+    }
+    __syncwarp();
+}
+
+// warp `kMixThreads / 32`: the three relation vectors of a resolved row -> buffer.  Two rounds of loads are issued before
+// the first store (a store to shared memory orders the loads behind it: one round trip to L2 per round otherwise).
+__device__ __forceinline__ void pipe_prefetch(const MixParams& p, const RowMeta m, float* e3, RowMeta* meta, int lane) {
+    const float* __restrict__ Ef = p.E + (size_t)m.rf * p.D;
+    const float* __restrict__ Er = p.E + (size_t)(m.rf + kFwdBound) * p.D;
+    const float* __restrict__ Es = p.E + (size_t)kRevBound * p.D;
+    for (int d0 = lane; d0 < p.D; d0 += 64) {
+        float v[2][3];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int d = d0 + 32 * j;
+            v[j][0] = (d < p.D && !m.forget_f) ? Ef[d] : 1.f;
+            v[j][1] = (d < p.D && !m.forget_r) ? Er[d] : 1.f;
+            v[j][2] = (d < p.D && !p.deep) ? Es[d] : 1.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int d = d0 + 32 * j;
+            if (d < p.D) {
+                e3[d] = v[j][0];
+                e3[p.D + d] = v[j][1];
+                e3[2 * p.D + d] = v[j][2];
+            }
+        }
+    }
+    if (lane == 0) *meta = m;
+}
+
+// backward: the row's incoming gradients dF, dR, dS [H] each -> g3 [3H], three more bulk copies on the same barrier phase
+__device__ __forceinline__ void stage_grads(const MixParams& p, int n, float* g3, unsigned long long* bar, int lane) {
+    stage_row(g3, p.F + (size_t)n * p.H, p.H, bar, lane);
+    stage_row(g3 + p.H, p.R + (size_t)n * p.H, p.H, bar, lane);
+    stage_row(g3 + 2 * p.H, p.S + (size_t)n * p.H, p.H, bar, lane);
+}
+
+// smem: 2 x Z row [D*H] | 2 x e [3D] | part [8][3][H]
+__global__ void __launch_bounds__(kPipeThreads, 2) relmix_fwd_pipe_kernel(const MixParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ RowMeta s_meta[2];
+    __shared__ RowMeta s_rows[32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const int e_len = (3 * p.D + 3) & ~3, hq = p.H >> 2, DH = p.D * p.H;
+    constexpr int NW = kMixThreads / 32;
+    float* z_buf = sm;
+    float* e_buf = sm + 2 * DH;
+    float4* part = reinterpret_cast<float4*>(e_buf + 2 * e_len);
+    GPT_PDL_ENTER();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool fetcher = warp == NW;
+    const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(p.bias);
+    const bool has_b = p.bias != nullptr;       // else the projection's epilogue already added it to Z
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int rows = mix_rows(p);
+    if ((int)blockIdx.x >= rows) return;
+    if (fetcher) {
+        stage_init(s_bar, lane);
+        stage_expect(&s_bar[0], DH, lane);
+        stage_row(z_buf, p.Z + (size_t)blockIdx.x * DH, DH, &s_bar[0], lane);
+        pipe_resolve(p, blockIdx.x, rows, s_rows, lane);
+        pipe_prefetch(p, s_rows[0], e_buf, &s_meta[0], lane);
+    }
+    __syncthreads();
+    int k = 0;
+    for (int i = blockIdx.x; i < rows; i += gridDim.x, ++k) {
+        const int cur = k & 1;
+        if (fetcher) {
+            const int nxt = i + (int)gridDim.x;
+            if (nxt < rows) {   // the other buffers were last read before the previous row's barrier
+                stage_expect(&s_bar[cur ^ 1], DH, lane);
+                stage_row(z_buf + (cur ^ 1) * DH, p.Z + (size_t)nxt * DH, DH, &s_bar[cur ^ 1], lane);
+                if (((k + 1) & 31) == 0) pipe_resolve(p, nxt, rows, s_rows, lane);
+                pipe_prefetch(p, s_rows[(k + 1) & 31], e_buf + (cur ^ 1) * e_len, &s_meta[cur ^ 1], lane);
+            }
+        } else {
+            const float* ef = e_buf + cur * e_len;
+            const float* er = ef + p.D;
+            const float* es = er + p.D;
+            stage_wait(&s_bar[cur], (unsigned)(k >> 1) & 1u);
+            const float4* z4 = reinterpret_cast<const float4*>(z_buf + cur * DH);
+            for (int q = lane; q < hq; q += 32) {
+                float4 f = zero, r = zero, s = zero;
+#pragma unroll 4
+                for (int d = warp; d < p.D; d += NW) {
+                    const float4 z = z4[d * hq + q], bb = has_b ? bias4[(size_t)d * hq + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v = make_float4(z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w);
+                    f = f4_fma(ef[d], v, f);
+                    r = f4_fma(er[d], v, r);
+                    s = f4_fma(es[d], v, s);
+                }
+                part[(warp * 3 + 0) * hq + q] = f;
+                part[(warp * 3 + 1) * hq + q] = r;
+                part[(warp * 3 + 2) * hq + q] = s;
+            }
+        }
+        __syncthreads();     // the warps' partial rows are complete (and the next row's vectors are in place)
+        if (!fetcher) {
+            const int n = s_meta[cur].n;
+            float4* __restrict__ F4 = reinterpret_cast<float4*>(p.F + (size_t)n * p.H);
+            float4* __restrict__ R4 = reinterpret_cast<float4*>(p.R + (size_t)n * p.H);
+            float4* __restrict__ S4 = reinterpret_cast<float4*>(p.S + (size_t)n * p.H);
+            for (int idx = threadIdx.x; idx < 3 * hq; idx += kMixThreads) {
+                const int which = idx / hq, c = idx - which * hq;
+                float4 acc = zero;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const float4 v = part[(w * 3 + which) * hq + c];
+                    acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+                }
+                (which == 0 ? F4 : which == 1 ? R4 : S4)[c] = acc;
+            }
+        }
+        __syncthreads();     // `part` is free again
+    }
+}
+
+// smem: 2 x Z row [D*H] | acc84 [D] | 2 x { e [3D] | dF, dR, dS [3H] }
+__global__ void __launch_bounds__(kPipeThreads, 2) relmix_bwd_pipe_kernel(const MixParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ RowMeta s_meta[2];
+    __shared__ RowMeta s_rows[32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const int e_len = (3 * p.D + 3) & ~3, hq = p.H >> 2, acc_len = (p.D + 3) & ~3, DH = p.D * p.H;
+    constexpr int NW = kMixThreads / 32;
+    float* z_buf = sm;
+    float* acc84 = sm + 2 * DH;
+    float* bufs = acc84 + acc_len;
+    const int buf_len = e_len + 3 * p.H;
+    GPT_PDL_ENTER();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool fetcher = warp == NW;
+    const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(p.bias);
+    const bool has_b = p.bias != nullptr;       // else the projection's epilogue already added it to Z
+    const int rows = mix_rows(p);
+    if ((int)blockIdx.x >= rows) return;
+    for (int d = threadIdx.x; d < p.D; d += blockDim.x) acc84[d] = 0.f;
+    if (fetcher) {
+        stage_init(s_bar, lane);
+        stage_expect(&s_bar[0], DH + 3 * p.H, lane);
+        stage_row(z_buf, p.Z + (size_t)blockIdx.x * DH, DH, &s_bar[0], lane);
+        pipe_resolve(p, blockIdx.x, rows, s_rows, lane);
+        stage_grads(p, s_rows[0].n, bufs + e_len, &s_bar[0], lane);
+        pipe_prefetch(p, s_rows[0], bufs, &s_meta[0], lane);
+    }
+    __syncthreads();
+    int k = 0;
+    for (int i = blockIdx.x; i < rows; i += gridDim.x, ++k) {
+        const int cur = k & 1;
+        if (fetcher) {
+            const int nxt = i + (int)gridDim.x;
+            if (nxt < rows) {
+                float* nb = bufs + (cur ^ 1) * buf_len;
+                stage_expect(&s_bar[cur ^ 1], DH + 3 * p.H, lane);
+                stage_row(z_buf + (cur ^ 1) * DH, p.Z + (size_t)nxt * DH, DH, &s_bar[cur ^ 1], lane);
+                if (((k + 1) & 31) == 0) pipe_resolve(p, nxt, rows, s_rows, lane);
+                stage_grads(p, s_rows[(k + 1) & 31].n, nb + e_len, &s_bar[cur ^ 1], lane);
+                pipe_prefetch(p, s_rows[(k + 1) & 31], nb, &s_meta[cur ^ 1], lane);
+            }
+        } else {
+            const float* ef = bufs + cur * buf_len;
+            const float* er = ef + p.D;
+            const float* es = er + p.D;
+            const float4* gf = reinterpret_cast<const float4*>(ef + e_len);
+            const float4* gr = gf + hq;
+            const float4* gs = gr + hq;
+            const RowMeta m = s_meta[cur];
+            stage_wait(&s_bar[cur], (unsigned)(k >> 1) & 1u);
+            const float4* z4 = reinterpret_cast<const float4*>(z_buf + cur * DH);
+            float4* __restrict__ dz4 = reinterpret_cast<float4*>(p.dZ + (size_t)i * DH);
+#pragma unroll 2
+            for (int d = warp; d < p.D; d += NW) {             // a relation slot d always belongs to the same warp
+                const float a = ef[d], b = er[d], c = es[d];
+                float sf = 0.f, sr = 0.f, ss = 0.f;
+                for (int q = lane; q < hq; q += 32) {
+                    const float4 z = z4[d * hq + q], bb = has_b ? bias4[(size_t)d * hq + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v = make_float4(z.x + bb.x, z.y + bb.y, z.z + bb.z, z.w + bb.w);
+                    const float4 x = gf[q], y = gr[q], w = gs[q];
+                    sf = f4_dot(x, v, sf);
+                    sr = f4_dot(y, v, sr);
+                    ss = f4_dot(w, v, ss);
+                    dz4[(size_t)d * hq + q] =
+                        make_float4(fmaf(a, x.x, fmaf(b, y.x, c * w.x)), fmaf(a, x.y, fmaf(b, y.y, c * w.y)),
+                                    fmaf(a, x.z, fmaf(b, y.z, c * w.z)), fmaf(a, x.w, fmaf(b, y.w, c * w.w)));
+                }
+                sf = warp_sum_f(sf);
+                sr = warp_sum_f(sr);
+                ss = warp_sum_f(ss);
+                if (lane == 0 && !p.deep) {
+                    if (!m.forget_f && m.rf != 0) atomicAdd(p.dE + (size_t)m.rf * p.D + d, sf);   // row 0 is padding_idx
+                    if (!m.forget_r) atomicAdd(p.dE + (size_t)(m.rf + kFwdBound) * p.D + d, sr);
+                    acc84[d] += ss;
+                }
+            }
+        }
+        __syncthreads();     // this row's buffers are free AND the next row's vectors have landed
+    }
+    if (!p.deep && !fetcher)
+        for (int d = warp; d < p.D; d += NW)
             if (lane == 0 && acc84[d] != 0.f) atomicAdd(p.dE + (size_t)kRevBound * p.D + d, acc84[d]);
 }
 
@@ -659,6 +930,17 @@ inline unsigned row_grid(long long rows, int threads = kThreads) {
 
 }  // namespace
 
+constexpr size_t kPipeSmemMax = 110 * 1024;     // two CTAs per SM
+// pipelined row walkers: two resident CTAs per SM, so that a CTA sees several rows and its prefetch warp has work to hide
+static unsigned pipe_grid(long long rows) {
+    long long cap = 148LL * 2;
+    if (const char* e = getenv("GPT_K10_MAX_CTAS")) {
+        const long long v = atoll(e);
+        if (v > 0) cap = v;
+    }
+    return (unsigned)(rows < 1 ? 1 : (rows < cap ? rows : cap));
+}
+
 static bool mix_vec_ok(const MixParams& p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p.Z) | reinterpret_cast<uintptr_t>(p.bias) | reinterpret_cast<uintptr_t>(p.F) |
                         reinterpret_cast<uintptr_t>(p.R) | reinterpret_cast<uintptr_t>(p.S) | reinterpret_cast<uintptr_t>(p.dZ);
@@ -670,7 +952,7 @@ extern "C" int gpt_relmix_fwd_rows(const float* Z, const float* bias, const floa
                                    const uint8_t* flags, const uint8_t* keep_f, const uint8_t* keep_r, const int32_t* perm,
                                    const int32_t* count, int N, int D, int H, int deep, float* F, float* R, float* S,
                                    void* stream) {
-    GPT_CHECK_ARG(Z && bias && E && deprel && flags && F && R && S && N >= 0 && D >= 1 && H >= 1);
+    GPT_CHECK_ARG(Z && E && deprel && flags && F && R && S && N >= 0 && D >= 1 && H >= 1);    // bias NULL: already in Z
     GPT_CHECK_ARG((perm == nullptr) == (count == nullptr));
     if (N == 0) return GPT_OK;
     MixParams p{};
@@ -678,6 +960,12 @@ extern "C" int gpt_relmix_fwd_rows(const float* Z, const float* bias, const floa
     p.keep_f = keep_f; p.keep_r = keep_r; p.F = F; p.R = R; p.S = S; p.N = N; p.D = D; p.H = H; p.deep = deep;
     p.perm = perm; p.count = count;
     const size_t smem4 = ((size_t)((3 * D + 3) & ~3) + (size_t)(kMixThreads / 32) * 3 * H) * sizeof(float);
+    const size_t smem_pipe = smem4 + ((size_t)((3 * D + 3) & ~3) + 2 * (size_t)D * H) * sizeof(float);
+    if (perm != nullptr && mix_vec_ok(p) && smem_pipe <= kPipeSmemMax) {
+        if (int a = gpt_smem_opt_in(relmix_fwd_pipe_kernel, smem_pipe)) return a;
+        gpt_launch(relmix_fwd_pipe_kernel, dim3(pipe_grid(N)), dim3(kPipeThreads), smem_pipe, (cudaStream_t)stream, p);
+        return gpt_launch_status();
+    }
     if (mix_vec_ok(p) && smem4 <= 48 * 1024) {
         gpt_launch(relmix_fwd4_kernel, dim3(row_grid(N, kMixThreads)), dim3(kMixThreads), smem4, (cudaStream_t)stream, p);
         return gpt_launch_status();
@@ -697,7 +985,7 @@ extern "C" int gpt_relmix_bwd_rows(const float* Z, const float* bias, const floa
                                    const uint8_t* flags, const uint8_t* keep_f, const uint8_t* keep_r, const int32_t* perm,
                                    const int32_t* count, const float* dF, const float* dR, const float* dS, int N, int D,
                                    int H, int deep, float* dZ, float* dE, void* stream) {
-    GPT_CHECK_ARG(Z && bias && E && deprel && flags && dF && dR && dS && dZ && dE && N >= 0 && D >= 1 && H >= 1);
+    GPT_CHECK_ARG(Z && E && deprel && flags && dF && dR && dS && dZ && dE && N >= 0 && D >= 1 && H >= 1);
     GPT_CHECK_ARG((perm == nullptr) == (count == nullptr));
     if (N == 0) return GPT_OK;
     MixParams p{};
@@ -706,6 +994,13 @@ extern "C" int gpt_relmix_bwd_rows(const float* Z, const float* bias, const floa
     p.S = const_cast<float*>(dS); p.dZ = dZ; p.dE = dE; p.N = N; p.D = D; p.H = H; p.deep = deep;
     p.perm = perm; p.count = count;
     const size_t smem4 = ((size_t)((4 * D + 3) & ~3) + (size_t)3 * H) * sizeof(float);
+    const size_t smem_pipe =
+        (2 * (size_t)D * H + (size_t)((D + 3) & ~3) + 2 * ((size_t)((3 * D + 3) & ~3) + 3 * H)) * sizeof(float);
+    if (perm != nullptr && mix_vec_ok(p) && smem_pipe <= kPipeSmemMax) {
+        if (int a = gpt_smem_opt_in(relmix_bwd_pipe_kernel, smem_pipe)) return a;
+        gpt_launch(relmix_bwd_pipe_kernel, dim3(pipe_grid(N)), dim3(kPipeThreads), smem_pipe, (cudaStream_t)stream, p);
+        return gpt_launch_status();
+    }
     if (mix_vec_ok(p) && smem4 <= 48 * 1024) {
         gpt_launch(relmix_bwd4_kernel, dim3(row_grid(N, kMixThreads)), dim3(kMixThreads), smem4, (cudaStream_t)stream, p);
         return gpt_launch_status();

@@ -178,6 +178,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_holder;
+    __shared__ __align__(16) float s_bias[kAccCols];    // the tile's column bias (one copy: the epilogue's own barriers order it)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
@@ -361,6 +362,15 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             float ep_inv = 0.f;
             const uint32_t* ep_words = nullptr;
             for (int q = 0; sched.get(q, mb, nb); ++q, ++tile_it) {
+                if (ep.bias != nullptr) {
+                    // the tile's bias -> shared memory while the MMAs of the tile are still running (every epilogue warp is
+                    // past the last chunk barrier of the previous tile, i.e. past its last read of s_bias)
+                    for (int c = (int)et; c < n_tile; c += 32 * kEpiWarps) {
+                        const int col = nb * n_tile + c;
+                        s_bias[c] = col < N ? __ldg(ep.bias + col) : 0.f;
+                    }
+                    named_bar(2, 32 * kEpiWarps);
+                }
                 if (mb != last_mb) {
                     last_mb = mb;
                     m0 = (mb * CG + (int)rank) * BM;
@@ -398,6 +408,17 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         if (lane == 0) {
                             if (CG == 2) mbar_arrive_remote(tempty_leader + 8 * a);
                             else mbar_arrive(tempty0 + 8 * a);
+                        }
+                    }
+                    if (ep.bias != nullptr) {
+                        const float4* b4 = reinterpret_cast<const float4*>(&s_bias[c0]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = b4[j];
+                            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + b.x);
+                            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
                         }
                     }
                     if (ep_words != nullptr) {          // g = (dx * (bit * scale)) * (1 / denom), as K2 forms it
@@ -466,7 +487,7 @@ template <int PASSES, int CG>
 int launch(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, const CUtensorMap& tm_c, int M,
            int N, int K, int n_tile, int n_tiles, cudaStream_t st, const MaskEpilogue& ep) {
     const size_t stage = (size_t)(PASSES == 3 ? 2 : 1) * (BM * BK * 4 + (size_t)(n_tile / CG) * BK * (PASSES == 0 ? 2 : 4));
-    const size_t budget = 227 * 1024 - 1024 /*alignment*/ - 2 * kEpiBuf - 512 /*static*/;
+    const size_t budget = 227 * 1024 - 1024 /*alignment*/ - 2 * kEpiBuf - 1536 /*static: barriers + the bias tile*/;
     int stages = (int)(budget / stage);
     stages = stages > kMaxStages ? kMaxStages : stages;
     if (stages < 2) return GPT_ERR_UNSUPPORTED;

@@ -56,6 +56,9 @@ struct MaskEpilogue {
     // count (gpt_live_rows).  Row tiles at or beyond *m_live leave at once -- the relation-aware layers project only the
     // compacted observable rows of a batch, and inside a captured step the host never knows how many there are.
     const int* m_live;
+    // optional column bias added to the accumulator before it is stored (y = x W^T + b; never with split-K): the relation
+    // mix reads every projected element once per direction, and a bias left for it to add doubles its L2 traffic
+    const float* bias;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -361,6 +364,19 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ep.bias != nullptr) {            // N % 4 == 0 and n0 + c0 is a multiple of 16: aligned 128-bit loads
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int c = n0 + c0 + j;
+                    if (c + 3 < N) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
+                        v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+                        v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+                        v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+                    }
+                }
+            }
             if (ep_words != nullptr) {                      // g = (dx * (bit * scale)) * (1 / denom), as K2 forms it
                 const int cg = n0 + c0, wi = cg >> 5, sh = cg & 31, nw = (N + 31) / 32;
                 unsigned long long bits = wi < nw ? (unsigned long long)ep_words[(size_t)wi * ep.T] : 0ull;
@@ -489,6 +505,7 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
     stages = stages < 1 ? 1 : stages;
     const size_t smem = (size_t)stages * stage + 1024;
     if (int a = gpt_smem_opt_in(tf32_gemm_kernel<PASSES>, smem)) return a;
+    if (splits > 1 && ep.bias != nullptr) return GPT_ERR_UNSUPPORTED;     // every K range would add it
     if (splits > 1) {               // the partial tiles are ADDED into C
         const cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
@@ -745,11 +762,12 @@ extern "C" int gpt_linear_dgrad_tf32x3(const float* dy, const float* ws, float* 
 
 // the same two projections over the first *m_live rows only (device-side count, gpt_live_rows); rows beyond it are not
 // computed and the corresponding rows of the output keep whatever they held
-extern "C" int gpt_linear_fwd_tf32x3_rows(const float* x, const float* ws, float* y, int M, int N, int K,
-                                          const int32_t* m_live, void* stream) {
+extern "C" int gpt_linear_fwd_tf32x3_rows(const float* x, const float* ws, const float* bias, float* y, int M, int N,
+                                          int K, const int32_t* m_live, void* stream) {
     GPT_CHECK_ARG(x && ws && y && m_live && M >= 0 && N >= 1 && K >= 1);
+    if (bias != nullptr && (N % 4 != 0 || (reinterpret_cast<uintptr_t>(bias) & 15))) return GPT_ERR_UNSUPPORTED;
     return run_tf32_gemm(x, ws, ws + (size_t)N * K, y, M, N, K, (cudaStream_t)stream,
-                         MaskEpilogue{nullptr, nullptr, 1.f, 1, m_live});
+                         MaskEpilogue{nullptr, nullptr, 1.f, 1, m_live, bias});
 }
 
 extern "C" int gpt_linear_dgrad_tf32x3_rows(const float* dy, const float* ws, float* dx, int M, int N, int K,
@@ -757,7 +775,7 @@ extern "C" int gpt_linear_dgrad_tf32x3_rows(const float* dy, const float* ws, fl
     GPT_CHECK_ARG(dy && ws && dx && m_live && M >= 0 && N >= 1 && K >= 1);
     const size_t nk = (size_t)N * K;
     return run_tf32_gemm(dy, ws + 2 * nk, ws + 3 * nk, dx, M, K, N, (cudaStream_t)stream,
-                         MaskEpilogue{nullptr, nullptr, 1.f, 1, m_live});
+                         MaskEpilogue{nullptr, nullptr, 1.f, 1, m_live, nullptr});
 }
 
 extern "C" int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, const uint32_t* act_prev,

@@ -457,14 +457,17 @@ class LiveRows(object):
         return out
 
 
-def _linear_fwd_rows(xc, weight, mode, ws, live):
+def _linear_fwd_rows(xc, weight, mode, ws, live, bias=None):
+    """-> (y, bias_added): over the live rows; the tensor-core path adds ``bias`` in its epilogue."""
     M, K = xc.shape
     N = weight.shape[0]
     if mode == 'tf32x3' and ws is not None and M < 65536:
+        fuse = bias is not None and N % 4 == 0 and bias.data_ptr() % 16 == 0
         y = torch.empty((M, N), dtype=torch.float32, device=xc.device)
-        _call('gpt_linear_fwd_tf32x3_rows', _ptr(xc), _ptr(ws), _ptr(y), M, N, K, _ptr(live.count), _stream())
-        return y
-    return linear_fwd(xc, weight, mode, ws)          # every row: the ones beyond count are scratch
+        _call('gpt_linear_fwd_tf32x3_rows', _ptr(xc), _ptr(ws), _ptr(bias if fuse else None), _ptr(y), M, N, K,
+              _ptr(live.count), _stream())
+        return y, fuse
+    return linear_fwd(xc, weight, mode, ws), False          # every row: the ones beyond count are scratch
 
 
 def _linear_dgrad_rows(dyc, weight, mode, ws, live):
@@ -534,14 +537,18 @@ class _RelationLayerFull(torch.autograd.Function):
         live = cfg.live
         # with `live`: xs / Z are COMPACT (row i < count belongs to token perm[i]); F, R, S and out stay per token
         xs = x.view(N, K) if live is None else live.gather(x.view(N, K))
-        Z = linear_fwd(xs, wmat, cfg.gemm_mode, ws) if live is None else _linear_fwd_rows(xs, wmat, cfg.gemm_mode, ws, live)
+        if live is None:
+            Z, biased = linear_fwd(xs, wmat, cfg.gemm_mode, ws), False
+        else:
+            Z, biased = _linear_fwd_rows(xs, wmat, cfg.gemm_mode, ws, live, bias.reshape(-1))
+        mix_bias = None if biased else bias       # `biased`: Z already holds x W^T + b, the mix must not add it again
         F, R, S = (torch.empty((N, H), dtype=torch.float32, device=x.device) for _ in range(3))
         kf, kr = cfg.keep_tokens if cfg.keep_tokens is not None else (None, None)
-        _call('gpt_relmix_fwd_rows', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
+        _call('gpt_relmix_fwd_rows', _ptr(Z), _ptr(mix_bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
               _ptr(None if live is None else live.perm), _ptr(None if live is None else live.count), N, D, H,
               int(cfg.deep), _ptr(F), _ptr(R), _ptr(S), _stream())
         out = _agg3_fwd(F, R, S, csr, cfg)
-        ctx.csr, ctx.cfg, ctx.dims = csr, cfg, (B, T, K, D, H)
+        ctx.csr, ctx.cfg, ctx.dims, ctx.biased = csr, cfg, (B, T, K, D, H), biased
         ctx.save_for_backward(xs, wmat, bias, emb, deprel, Z, out, ws)
         return out
 
@@ -558,7 +565,8 @@ class _RelationLayerFull(torch.autograd.Function):
         dE = torch.zeros_like(emb)
         kf, kr = cfg.keep_tokens if cfg.keep_tokens is not None else (None, None)
         cnt = None if live is None else live.count
-        _call('gpt_relmix_bwd_rows', _ptr(Z), _ptr(bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags), _ptr(kf), _ptr(kr),
+        _call('gpt_relmix_bwd_rows', _ptr(Z), _ptr(None if ctx.biased else bias), _ptr(emb), _ptr(deprel), _ptr(csr.flags),
+              _ptr(kf), _ptr(kr),
               _ptr(None if live is None else live.perm), _ptr(cnt), _ptr(dF), _ptr(dR), _ptr(dS), N, D, H, int(cfg.deep),
               _ptr(dZ), _ptr(dE), _stream())
         dbias = None

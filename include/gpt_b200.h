@@ -359,7 +359,10 @@ int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* s
  *   gpt_gather_rows       out[i,:] = x[perm[i],:]  for i < *count           (x, out float [N,K]; other rows of out untouched)
  *   gpt_scatter_rows      dx[n,:] = inv[n] >= 0 ? dxc[inv[n],:] : 0        for every n < N
  *   gpt_linear_{fwd,dgrad}_tf32x3_rows, gpt_linear_wgrad_tf32x3_rows:  the projections of gpt_linear_*_tf32x3 over the first
- *                         *m_live rows (row tiles beyond leave at once; output rows beyond keep what they held)
+ *                         *m_live rows (row tiles beyond leave at once; output rows beyond keep what they held); the
+ *                         forward takes an optional column bias (float [N], 16-byte aligned, N % 4 == 0) added in its
+ *                         epilogue -- gpt_relmix_*_rows are then called with bias == NULL (the mix reads every projected
+ *                         element once per direction: a bias left for it to add doubles its L2 traffic)
  *   gpt_relmix_{fwd,bwd}_rows   Z / dZ compact [count, D*H], everything per token (deprel, flags, keep_*, F/R/S, dF/dR/dS)
  *                         addressed through perm; perm == count == NULL is gpt_relmix_{fwd,bwd}.  Rows with flags == 0 are
  *                         not written in the compact form (nothing reads them: the aggregation gathers kept rows only)
@@ -367,8 +370,8 @@ int gpt_colsum_acc(const float* a, long long rows, int cols, float* out, void* s
 int gpt_live_rows(const uint8_t* flags, int N, int32_t* perm, int32_t* inv, uint8_t* live, int32_t* count, void* stream);
 int gpt_gather_rows(const float* x, const int32_t* perm, const int32_t* count, int N, int K, float* out, void* stream);
 int gpt_scatter_rows(const float* dxc, const int32_t* inv, int N, int K, float* dx, void* stream);
-int gpt_linear_fwd_tf32x3_rows(const float* x, const float* ws, float* y, int M, int N, int K, const int32_t* m_live,
-                               void* stream);
+int gpt_linear_fwd_tf32x3_rows(const float* x, const float* ws, const float* bias, float* y, int M, int N, int K,
+                               const int32_t* m_live, void* stream);
 int gpt_linear_dgrad_tf32x3_rows(const float* dy, const float* ws, float* dx, int M, int N, int K, const int32_t* m_live,
                                  void* stream);
 int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, const uint8_t* flags, float* dw, long long M, int N, int K,

@@ -7,7 +7,7 @@ unsigned long long g_gpt_launches = 0;
 int g_gpt_pdl = 0;
 
 namespace {
-alignas(16) thread_local float sm[48 * 1024 / 4];   // the kernels' `extern __shared__ float sm[]`: one block runs at a time
+alignas(16) thread_local float sm[160 * 1024 / 4];   // the kernels' `extern __shared__ float sm[]`: one block runs at a time
 }
 
 #include "../../gcn_over_pruned_trees_b200/csrc/deprel.cu"

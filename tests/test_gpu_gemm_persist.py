@@ -113,18 +113,19 @@ def test_wide_projection_with_a_device_side_row_count(cg, live):
     x = torch.randn(M, K, device=DEV, generator=g)
     w = torch.randn(N, K, device=DEV, generator=g) / np.sqrt(K)
     ws = ops.weight_prep(w, 'tf32x3')
+    bias = torch.randn(N, device=DEV, generator=g)           # added in the epilogue of either kernel
     count = torch.tensor([live], dtype=torch.int32, device=DEV)
     out = []
     for mode in (0, cg):
         ops.gemm_persist_config(mode, 65536)
         y = torch.full((M, N), 7.0, device=DEV)
-        ops._call('gpt_linear_fwd_tf32x3_rows', x.data_ptr(), ws.data_ptr(), y.data_ptr(), M, N, K, count.data_ptr(),
-                  ops._stream())
+        ops._call('gpt_linear_fwd_tf32x3_rows', x.data_ptr(), ws.data_ptr(), bias.data_ptr(), y.data_ptr(), M, N, K,
+                  count.data_ptr(), ops._stream())
         out.append(y)
     torch.cuda.synchronize()
     assert torch.equal(out[0][:live], out[1][:live])
     if live:
-        assert _rel(out[1][:live], x[:live].double() @ w.double().t()) <= 1e-5
+        assert _rel(out[1][:live], x[:live].double() @ w.double().t() + bias.double()) <= 1e-5
     block = 128 * cg
     touched = min(M, (live + block - 1) // block * block)
     assert bool((out[1][touched:] == 7.0).all())

@@ -256,7 +256,9 @@ def test_live_row_compaction_and_row_limited_projections(frac):
     xc[cnt:] = float('nan')
     w = torch.randn(DH, K, device=DEV, generator=g) / np.sqrt(K)
     ws = ops.weight_prep(w, 'tf32x3')
-    y = ops._linear_fwd_rows(xc, w, 'tf32x3', ws, live)
+    bias = torch.randn(DH, device=DEV, generator=g)
+    y, biased = ops._linear_fwd_rows(xc, w, 'tf32x3', ws, live, bias)     # the bias rides in the projection's epilogue
+    assert biased
     dy = torch.randn(N, DH, device=DEV, generator=g)
     dy[cnt:] = float('nan')
     dxc = ops._linear_dgrad_rows(dy, w, 'tf32x3', ws, live)
@@ -268,7 +270,7 @@ def test_live_row_compaction_and_row_limited_projections(frac):
     if cnt == 0:
         assert not bool(dw.ne(0).any())
         return
-    assert _rel(y[:cnt].cpu(), (xc[:cnt].double() @ w.double().t()).cpu()) <= 1e-5
+    assert _rel(y[:cnt].cpu(), (xc[:cnt].double() @ w.double().t() + bias.double()).cpu()) <= 1e-5
     assert _rel(dxc[:cnt].cpu(), (dy[:cnt].double() @ w.double()).cpu()) <= 1e-5
     assert _rel(dw.cpu(), (dy[:cnt].double().t() @ xc[:cnt].double()).cpu()) <= 1e-5
     db = torch.zeros(DH, device=DEV)
