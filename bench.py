@@ -554,6 +554,12 @@ def run_b200(args):
     else:
         graphed = GraphedTrainStep(trainer, reducer=reducer)
     step = eager_step if args.eager else graphed
+    engine_info = engine_config(args, world)
+    ex = getattr(graphed, 'exchange', None)
+    if ex is not None:      # how the K8 regions are mapped on this box (parallel.PeerExchange)
+        engine_info['exchange'] += ': regions in %s, push through %s' % (
+            'torch symmetric memory' if ex.symm is not None else 'cudaMalloc + cudaIpc',
+            'an NVSwitch multicast mapping (multimem.st)' if ex.multicast else 'one store per peer')
     host_tuples, resident_tuples = host, resident
     if fused and not args.eager:    # loader batches packed into one contiguous buffer each: one copy per step
         from gcn_over_pruned_trees_b200.engine import PackedBatch
@@ -765,7 +771,7 @@ def run_b200(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
-            'engine': engine_config(args, world), 'step_ms': step_ms, 'dp_check': dp_check,
+            'engine': engine_info, 'step_ms': step_ms, 'dp_check': dp_check,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'gpu_launches_per_step': launches / args.steps, 'wall_ms_per_step_incl_flush': wall / args.steps * 1e3,
             'roofline': roof, 'cpu_baseline': cpu, 'extra': extra, 'loader': loader_info, 'kernels': kernels}

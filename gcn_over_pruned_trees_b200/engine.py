@@ -87,8 +87,7 @@ class GraphedTrainStep(object):
         gcn = self.model.gcn_model.gcn
         gcn.sparse_embedding = self.sparse          # row-sparse word-embedding gradient for this step only
         try:
-            logits, pooling_output = self.model(inputs)
-            loss = self.trainer._loss(logits, pooling_output, labels)
+            loss = self.trainer._forward_loss(inputs, labels)
             loss.backward()
         finally:
             gcn.sparse_embedding = None

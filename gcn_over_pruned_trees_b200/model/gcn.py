@@ -44,6 +44,19 @@ class GCNClassifier(nn.Module):
         outputs, pooling_output = self.gcn_model(inputs)
         return self.classifier(outputs), pooling_output
 
+    def loss_fused(self, inputs, labels, pooling_l2):
+        """Training-time ``CrossEntropy(classifier(out_mlp(pooled))) + pooling_l2 * mean_b |h_out_b|^2`` (gcn.py:122 +
+        trainer.py:94-100) with the whole head -- forward, loss and every gradient of it -- in K6's two launches instead
+        of ~45 ATen kernels, still under autograd (ops.head_loss).  Returns (loss, logits); None when K6 does not take
+        the configuration."""
+        mlp = [m for m in self.gcn_model.out_mlp if isinstance(m, nn.Linear)]
+        H = self.opt['hidden_dim']
+        if H % 4 != 0 or len(mlp) > 4 or not labels.is_cuda:
+            return None
+        pooled = self.gcn_model.pooled(inputs)
+        wb = [t for m in mlp for t in (m.weight, m.bias)]
+        return ops.head_loss(pooled, labels, float(pooling_l2), self.classifier.weight, self.classifier.bias, *wb)
+
     def get_deprel_emb(self):
         return self.gcn_model.get_deprel_embedding()
 
@@ -98,7 +111,8 @@ class GCNRelationModel(nn.Module):
         else:
             print("Finetune all embeddings.")
 
-    def forward(self, inputs):
+    def pooled(self, inputs):
+        """[B, 3H]: the sentence / subject / object pools of the last GCN layer (gcn.py:96-121 up to the cat)."""
         if self.opt['dataset'] == 'tacred':
             words, masks, pos, ner, deprel, head, subj_pos, obj_pos = inputs
         else:
@@ -108,7 +122,10 @@ class GCNRelationModel(nn.Module):
         self.last_csr = csr
         h, _ = self.gcn(csr, inputs)
         # K4: sentence / subject / object pools in one pass
-        pooled = ops.pool3(h, csr, self.opt['pooling'])
+        return ops.pool3(h, csr, self.opt['pooling'])
+
+    def forward(self, inputs):
+        pooled = self.pooled(inputs)
         h_out = pooled[:, :self.opt['hidden_dim']]
         return self.out_mlp(pooled), h_out
 

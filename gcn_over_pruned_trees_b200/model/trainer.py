@@ -81,6 +81,8 @@ class GCNTrainer(Trainer):
         # (engine.FastUpdate); False, or GPT_FAST_UPDATE=0, keeps every call on the per-op autograd path
         self.fast_update = os.environ.get('GPT_FAST_UPDATE', '1') != '0'
         self._fast = None
+        # per-op path: classifier head + loss through K6 (ops.head_loss) instead of nn.Linear / CrossEntropyLoss kernels
+        self.fused_head = os.environ.get('GPT_FUSED_HEAD', '1') != '0'
 
     def _loss(self, logits, pooling_output, labels):
         loss = self.criterion(logits, labels)
@@ -95,6 +97,18 @@ class GCNTrainer(Trainer):
         if fast is not None:
             return fast.update(batch)
         inputs, labels = unpack_batch(batch, self.opt['cuda'])[:2]
+        return self._forward_loss(inputs, labels)
+
+    def _forward_loss(self, inputs, labels):
+        """Forward + loss of the per-op path (also what engine.GraphedTrainStep captures)."""
+        if self.fused_head and self.opt['cuda'] and self.model.training and torch.is_grad_enabled():
+            # the head and its loss in K6's two launches (still autograd: the caller's loss.backward() works as before)
+            fused = self.model.loss_fused(inputs, labels, self.opt.get('pooling_l2', 0))
+            if fused is not None:
+                loss = fused[0]
+                if self.opt.get('conv_l2', 0) > 0:
+                    loss = loss + self.model.conv_l2() * self.opt['conv_l2']
+                return loss
         logits, pooling_output = self.model(inputs)
         return self._loss(logits, pooling_output, labels)
 

@@ -827,6 +827,40 @@ def head_wgrad(pooled, buf, dws, dbs, dwc, dbc):
     return buf.loss
 
 
+class _HeadLoss(torch.autograd.Function):
+    """K6 under autograd: loss = mean CE(classifier(out_mlp(pooled)), labels) + pooling_l2 * mean_b |pooled[b, :H]|^2.
+    The forward runs K6's two launches, which already produce d loss / d pooled and every weight / bias gradient of the
+    head; the backward only scales them by the incoming gradient (one multi-tensor launch)."""
+
+    @staticmethod
+    def forward(ctx, pooled, labels, pooling_l2, wc, bc, *wb):
+        pooled = _dev(pooled, torch.float32, 'pooled')
+        labels = _dev(labels, torch.int64, 'labels')
+        weights = [_dev(w.detach(), torch.float32, 'out_mlp weight') for w in wb[0::2]]
+        biases = [_dev(b.detach(), torch.float32, 'out_mlp bias') for b in wb[1::2]]
+        wc_, bc_ = _dev(wc.detach(), torch.float32, 'classifier.weight'), _dev(bc.detach(), torch.float32, 'classifier.bias')
+        B, H, C = pooled.shape[0], pooled.shape[1] // 3, wc_.shape[0]
+        buf = HeadBuffers(B, H, C, len(weights), pooled.device)
+        head_fwd_bwd(pooled, labels, weights, biases, wc_, bc_, pooling_l2, buf, train=True)
+        dws, dbs = [torch.empty_like(w) for w in weights], [torch.empty_like(b) for b in biases]
+        dwc, dbc = torch.empty_like(wc_), torch.empty_like(bc_)
+        loss = head_wgrad(pooled, buf, dws, dbs, dwc, dbc)
+        ctx.n = len(weights)
+        ctx.save_for_backward(buf.dpooled, dwc, dbc, *[t for pair in zip(dws, dbs) for t in pair])
+        ctx.mark_non_differentiable(buf.logits)
+        return loss, buf.logits
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits):
+        grads = torch._foreach_mul(list(ctx.saved_tensors), gloss)
+        return (grads[0], None, None, grads[1], grads[2]) + tuple(grads[3:])
+
+
+def head_loss(pooled, labels, pooling_l2, wc, bc, *wb):
+    """(loss, logits) of the classifier head on pooled [B,3H]; wb = out_mlp's (weight, bias) pairs in order."""
+    return _HeadLoss.apply(pooled, labels, pooling_l2, wc, bc, *wb)
+
+
 def predict_tail(logits, labels, dest, result):
     """K11: softmax + argmax + mean CE + un-sort (model/trainer.py:118-123) -> packed ``result`` (uint8 device buffer of
     gpt_predict_result_bytes(B, C) bytes: probs f32 [B,C] | predictions i32 [B] | loss f32)."""
