@@ -878,6 +878,121 @@ __global__ void __launch_bounds__(kThreads) agg3_bwd_kernel(const Agg3Params p) 
     }
 }
 
+// ---- the same aggregation, one WARP per token row and 128-bit columns (H % 4 == 0) ------------------------------------
+// A row moves a few KB behind a chain of dependent loads (flags -> rowptr -> col / val -> the neighbours' rows): what
+// matters is how many rows are in flight, so a 128-thread CTA serves four rows at once and a lane holds four columns.
+constexpr int kAggWarps = kThreads / 32;
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__global__ void __launch_bounds__(kThreads) agg3_fwd4_kernel(const Agg3Params p) {
+    GPT_PDL_ENTER();
+    const int N = p.B * p.T, hq = p.H >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool philox_drop = p.drop_mask == nullptr && p.drop_p > 0.f && p.rng != nullptr;
+    const float scale = philox_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = blockIdx.x * kAggWarps + warp; n < N; n += gridDim.x * kAggWarps) {
+        float4* __restrict__ out4 = reinterpret_cast<float4*>(p.out + (size_t)n * p.H);
+        if (!observable(p.flags[n])) {                 // warp-uniform
+            for (int q = lane; q < hq; q += 32) out4[q] = zero;
+            continue;
+        }
+        const int b = n / p.T, i = n - b * p.T;
+        const int e0 = p.rowptr[(size_t)b * (p.T + 1) + i], e1 = p.rowptr[(size_t)b * (p.T + 1) + i + 1];
+        const int* __restrict__ col = p.col + (size_t)b * p.cap;
+        const unsigned char* __restrict__ val = p.val + (size_t)b * p.cap;
+        const float dn = p.denom[n];
+        for (int q = lane; q < hq; q += 32) {
+            float4 acc = p.self_loop ? reinterpret_cast<const float4*>(p.S + (size_t)n * p.H)[q] : zero;
+            for (int e = e0; e < e1; ++e) {
+                const int j = col[e], v = val[e];
+                if (is_fwd(v)) {
+                    if (edge_kept(p.keep_f, p.rng, p.edge_keep, p.layer, 0u, b, i, j, p.T))
+                        acc = f4_add(acc, reinterpret_cast<const float4*>(p.F + ((size_t)b * p.T + j) * p.H)[q]);
+                } else if (is_rev(v) && !p.directed) {
+                    if (edge_kept(p.keep_r, p.rng, p.edge_keep, p.layer, 1u, b, i, j, p.T))
+                        acc = f4_add(acc, reinterpret_cast<const float4*>(p.R + ((size_t)b * p.T + j) * p.H)[q]);
+                }
+            }
+            float o[4] = {fmaxf(acc.x / dn, 0.f), fmaxf(acc.y / dn, 0.f), fmaxf(acc.z / dn, 0.f), fmaxf(acc.w / dn, 0.f)};
+            const size_t idx0 = (size_t)n * p.H + 4 * q;
+            if (p.drop_mask != nullptr) {
+                const float4 m = reinterpret_cast<const float4*>(p.drop_mask + idx0)[0];
+                o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
+            } else if (philox_drop) {
+                const unsigned long long seed = p.rng[0], step = p.rng[1];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {           // the element's own stream, as the scalar kernel draws it
+                    const size_t idx = idx0 + c;
+                    const Philox4 r = philox4x32((uint32_t)idx, (uint32_t)(idx >> 32), 0xD7090000u | p.layer, (uint32_t)step,
+                                                 (uint32_t)seed, (uint32_t)(seed >> 32));
+                    o[c] = (u01(r.x) >= p.drop_p) ? o[c] * scale : 0.f;
+                }
+            }
+            out4[q] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+__device__ __forceinline__ float4 upstream4(const Agg3Params& p, size_t idx0, float scale, float inv_dn) {
+    const float4 o = reinterpret_cast<const float4*>(p.outp + idx0)[0];
+    const float4 g = reinterpret_cast<const float4*>(p.gout + idx0)[0];
+    float4 m = make_float4(scale, scale, scale, scale);
+    if (p.drop_mask != nullptr) m = reinterpret_cast<const float4*>(p.drop_mask + idx0)[0];
+    return make_float4(o.x == 0.f ? 0.f : g.x * m.x * inv_dn, o.y == 0.f ? 0.f : g.y * m.y * inv_dn,
+                       o.z == 0.f ? 0.f : g.z * m.z * inv_dn, o.w == 0.f ? 0.f : g.w * m.w * inv_dn);
+}
+
+__global__ void __launch_bounds__(kThreads) agg3_bwd4_kernel(const Agg3Params p) {
+    GPT_PDL_ENTER();
+    const int N = p.B * p.T, hq = p.H >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool philox_drop = p.drop_mask == nullptr && p.drop_p > 0.f && p.rng != nullptr;
+    const float scale = philox_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = blockIdx.x * kAggWarps + warp; n < N; n += gridDim.x * kAggWarps) {
+        float4* __restrict__ dF4 = reinterpret_cast<float4*>(p.dF + (size_t)n * p.H);
+        float4* __restrict__ dR4 = reinterpret_cast<float4*>(p.dR + (size_t)n * p.H);
+        float4* __restrict__ dS4 = reinterpret_cast<float4*>(p.dS + (size_t)n * p.H);
+        if (!observable(p.flags[n])) {                 // warp-uniform
+            for (int q = lane; q < hq; q += 32) dF4[q] = dR4[q] = dS4[q] = zero;
+            continue;
+        }
+        const int b = n / p.T, j = n - b * p.T;
+        const int e0 = p.rowptr[(size_t)b * (p.T + 1) + j], e1 = p.rowptr[(size_t)b * (p.T + 1) + j + 1];
+        const int* __restrict__ col = p.col + (size_t)b * p.cap;
+        const unsigned char* __restrict__ val = p.val + (size_t)b * p.cap;
+        const float inv_self = 1.f / p.denom[n];
+        for (int q = lane; q < hq; q += 32) {
+            float4 df = zero, dr = zero;
+            for (int e = e0; e < e1; ++e) {
+                const int i = col[e], v = val[e];
+                const size_t nb = ((size_t)b * p.T + i) * p.H + 4 * q;
+                if (is_rev(v)) {            // i is j's parent: its row gathered F_j through entry [i, j] of the parent->child matrix
+                    if (edge_kept(p.keep_f, p.rng, p.edge_keep, p.layer, 0u, b, i, j, p.T))
+                        df = f4_add(df, upstream4(p, nb, scale, 1.f / p.denom[(size_t)b * p.T + i]));
+                } else if (is_fwd(v) && !p.directed) {   // i is a child of j: its row gathered R_j through entry [i, j]
+                    if (edge_kept(p.keep_r, p.rng, p.edge_keep, p.layer, 1u, b, i, j, p.T))
+                        dr = f4_add(dr, upstream4(p, nb, scale, 1.f / p.denom[(size_t)b * p.T + i]));
+                }
+            }
+            dF4[q] = df;
+            dR4[q] = dr;
+            dS4[q] = p.self_loop ? upstream4(p, (size_t)n * p.H + 4 * q, scale, inv_self) : zero;
+        }
+    }
+}
+
+static bool agg3_vec_ok(const Agg3Params& p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.F) | reinterpret_cast<uintptr_t>(p.R) | reinterpret_cast<uintptr_t>(p.S) |
+                        reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.gout) |
+                        reinterpret_cast<uintptr_t>(p.outp) | reinterpret_cast<uintptr_t>(p.dF) |
+                        reinterpret_cast<uintptr_t>(p.dR) | reinterpret_cast<uintptr_t>(p.dS) |
+                        reinterpret_cast<uintptr_t>(p.drop_mask);
+    return p.H % 4 == 0 && (a & 15) == 0;
+}
+
 // dense [B,T,T] copy of the Philox edge-keep decisions of one layer and direction (tests feed it to the oracle)
 __global__ void edge_keep_dense_kernel(const unsigned long long* __restrict__ rng, int B, int T, unsigned layer, unsigned dir,
                                        float keep_prob, unsigned char* __restrict__ out) {
@@ -1089,6 +1204,11 @@ extern "C" int gpt_agg3_fwd(const float* F, const float* R, const float* S, cons
     if (rc != GPT_OK) return rc;
     if (B == 0) return GPT_OK;
     p.F = F; p.R = R; p.S = S; p.out = out;
+    if (agg3_vec_ok(p)) {
+        const long long rows = (long long)B * T;
+        gpt_launch(agg3_fwd4_kernel, dim3(row_grid((rows + kAggWarps - 1) / kAggWarps)), dim3(kThreads), 0, (cudaStream_t)stream, p);
+        return gpt_launch_status();
+    }
     gpt_launch(agg3_fwd_kernel, dim3(row_grid((long long)B * T)), dim3(kThreads), 0, (cudaStream_t)stream, p);
     return gpt_launch_status();
 }
@@ -1105,6 +1225,11 @@ extern "C" int gpt_agg3_bwd(const float* gout, const float* out, const int32_t* 
     if (rc != GPT_OK) return rc;
     if (B == 0) return GPT_OK;
     p.gout = gout; p.outp = out; p.dF = dF; p.dR = dR; p.dS = dS;
+    if (agg3_vec_ok(p)) {
+        const long long rows = (long long)B * T;
+        gpt_launch(agg3_bwd4_kernel, dim3(row_grid((rows + kAggWarps - 1) / kAggWarps)), dim3(kThreads), 0, (cudaStream_t)stream, p);
+        return gpt_launch_status();
+    }
     gpt_launch(agg3_bwd_kernel, dim3(row_grid((long long)B * T)), dim3(kThreads), 0, (cudaStream_t)stream, p);
     return gpt_launch_status();
 }
