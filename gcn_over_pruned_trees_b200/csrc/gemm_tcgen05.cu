@@ -491,6 +491,18 @@ __global__ void tf32_split_kernel(const float* __restrict__ in, float* __restric
 
 #include "gemm_persist.cuh"   // the large-M path: persistent CTA-pair kernel (uses the helpers above)
 
+inline int sm_count_host() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 template <int PASSES>
 int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_b_lo, float* C, int M, int N,
                 int K, int n_tile, int n_tiles, int tmem_cols, cudaStream_t st, const MaskEpilogue& ep, int splits = 1) {
@@ -510,9 +522,7 @@ int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensor
         const cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count_host();
     dim3 grid((unsigned)(((M + BM - 1) / BM) * n_tiles), (unsigned)splits);
     gpt_launch(tf32_gemm_kernel<PASSES>, grid, dim3(kGemmThreads), smem, st, tm_a, tm_b, tm_b_lo, C, M, N, K, n_tile, n_tiles,
                                                                tmem_cols, stages, ep, kb_per_split, sms);
@@ -550,7 +560,9 @@ int run_tf32_gemm(const float* A, const float* B, const float* b_lo, float* C, i
         if (ep.m_live != nullptr) splits = nkb_all / 8;
         if (splits < 1) splits = 1;
     } else {
-        while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
+        // halve the tile while the grid still fits ONE wave (one CTA per SM at these shared-memory sizes): 168 tiles on 148
+        // SMs run as two waves -- the first layer's data gradient (N = 360) took 18.8 us that way against 13.3 for 112 tiles
+        while (cap > 64 && (long)m_tiles * ((N + cap / 2 - 1) / (cap / 2)) <= sm_count_host()) cap >>= 1;
     }
     const int n_tiles = (N + cap - 1) / cap;
     int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;   // UMMA N: multiple of 16 at M = 128, <= 256
@@ -655,7 +667,7 @@ int run_bf16_gemm(const float* A, const void* B16, float* C, int M, int N, int K
     }
     const int m_tiles = (M + BM - 1) / BM;
     int cap = 256;
-    while (cap > 64 && (long)m_tiles * ((N + cap - 1) / cap) < 148) cap >>= 1;
+    while (cap > 64 && (long)m_tiles * ((N + cap / 2 - 1) / (cap / 2)) <= sm_count_host()) cap >>= 1;
     const int n_tiles = (N + cap - 1) / cap;
     int n_tile = ((N + n_tiles - 1) / n_tiles + 15) / 16 * 16;
     if (n_tile < 16) n_tile = 16;

@@ -255,6 +255,9 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     }
     const size_t smem = (size_t)stages * stage + 1024;
     const long long blocks16 = (M + WG_ROWS - 1) / WG_ROWS;
+    // every row range ends with a flush of its [128, K] partial tile into dW (vector reductions): a range of fewer than
+    // 16 blocks spends more on the flush than on the rows (the TACRED-sized batches: a few hundred blocks in all)
+    if (m_parts > blocks16 / 16) m_parts = blocks16 / 16 > 0 ? blocks16 / 16 : 1;
     if (m_parts > blocks16) m_parts = blocks16;
     const long long rows_per_part = ((blocks16 + m_parts - 1) / m_parts) * WG_ROWS;
     m_parts = (M + rows_per_part - 1) / rows_per_part;

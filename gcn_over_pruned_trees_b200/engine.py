@@ -303,6 +303,11 @@ class FusedTrainStep(object):
         # data-dependent kernels compete for SMs, the chain goes first
         self.capture_stream = torch.cuda.Stream(priority=-1) if os.environ.get('GPT_PRIO', '1') != '0' else None
         self.flat = self.sparse = self.exchange = None
+        # measured at the TACRED shape and OFF by default: the chain gets shorter (first layer's data gradient 18.8 -> 10.5 us
+        # once the FFMA weight gradient no longer shares the SMs with it) but gather + tensor-core weight gradient are two
+        # dependent launches on the side branch (7 + 5 us of edge latency) and the two weight gradients contend for tensor
+        # memory: the tail moves from 131 to 139 us, the step from 140 to 147
+        self.tc_wgrad_small = os.environ.get('GPT_TC_WGRAD_SMALL', '0') != '0'
         if not training:
             return
         self.exchange_kind = {False: None, None: None, True: 'peer', 'peer': 'peer', 'nccl': 'nccl'}[data_parallel]
@@ -426,10 +431,19 @@ class FusedTrainStep(object):
         st.fuse_pool = fuse_pool = ptype == ops.POOL_TYPES['max'] and ops.aggregate_pool_ok(B, T, H)
         st.csr = csr = ops.TreeCSR(B, T, words.device)
         st.wss = wss = [ops.weight_prep_buffer(lin.weight.data, mode) for lin in gcn.W]
+        # weight gradient of TACRED-sized batches on the tensor cores: over the rows that carry a gradient only, compacted
+        # (ops.LiveRows: a quarter of the token rows at prune_k = 1) -- an FFMA kernel over the live rows otherwise
+        st.live = live = None
+        if (train and self.tc_wgrad_small and mode == 'tf32x3' and B * T < ops.WGRAD_TC_MIN_ROWS and
+                all(ops.wgrad_rows_tc_ok(*lin.weight.shape) for lin in gcn.W)):
+            st.live = live = ops.LiveRows(n_rows=B * T, device=words.device)
+        st.xc = xc = []
         self._fork(sa)
         self._fork(sb)
         with torch.cuda.stream(sa):
             ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'], out=csr)
+            if live is not None:
+                live.run(csr.flags)
         with torch.cuda.stream(sb):
             ops.weight_prep_all([lin.weight.data for lin in gcn.W], mode, wss)    # one launch: the first GEMM waits for it
             ev_prep = torch.cuda.Event()
@@ -447,6 +461,12 @@ class FusedTrainStep(object):
             if l == 0:
                 self._join(sa)
             xs.append(h)
+            if live is not None:        # the layer input's live rows, packed: off the chain, read by the backward only
+                h2d = h.view(B * T, -1)
+                buf_c = torch.empty_like(h2d)
+                self._fork(sa)
+                with torch.cuda.stream(sa):
+                    xc.append(live.gather(h2d, out=buf_c))
             if l == n_layers - 1 and fuse_pool:     # last layer: K2 + K4 in one launch, h itself is never stored
                 pooled, argmax, act, _ = ops.aggregate_fwd_pool(y, csr, lin.bias.data, use_adj)
                 acts.append(act)
@@ -460,6 +480,8 @@ class FusedTrainStep(object):
         st.buf = buf = ops.HeadBuffers(B, H, self.cls.weight.shape[0], len(self.mlp), words.device)
         ops.head_fwd_bwd(pooled, labels, [m.weight.data for m in self.mlp], [m.bias.data for m in self.mlp],
                          self.cls.weight.data, self.cls.bias.data, opt.get('pooling_l2', 0) or 0.0, buf, train=train)
+        if live is not None:
+            self._join(sa)
         if join_side:
             self._join(sb)
         return st
@@ -506,10 +528,15 @@ class FusedTrainStep(object):
                                           act=acts[l], dbias_out=fl.g(lin.bias))
             keep.append(dy)
             side = sb if (n_layers - 1 - l) % 2 == 0 else sa
+            dyc = torch.empty_like(dy) if st.live is not None else None
+            keep.append(dyc)
             self._fork(side)
             with torch.cuda.stream(side):
-                ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True,
-                                 flags=csr.flags)
+                if st.live is not None:
+                    ops.linear_wgrad_live_acc(st.live.gather(dy, out=dyc), st.xc[l], st.live, fl.g(lin.weight))
+                else:
+                    ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True,
+                                     flags=csr.flags)
             g = None
             if l > 0 and mode == 'tf32x3':
                 g = ops.linear_dgrad_masked(dy, lin.weight.data, wss[l], acts[l - 1], csr, p_gcn)

@@ -432,21 +432,30 @@ def relation_keep_tokens(rng_state, n_rows, layer, keep_prop):
 class LiveRows(object):
     """The observable rows of a batch (flags != 0: inside a pruned tree, or a subject / object token), compacted on the
     device by ``gpt_live_rows``: ``perm`` int32 [N] (ascending row ids, first ``count`` entries), ``inv`` int32 [N],
-    ``live`` uint8 [N] (``i < count``), ``count`` int32 [1].  The count never comes to the host (graph capture)."""
+    ``live`` uint8 [N] (``i < count``), ``count`` int32 [1].  The count never comes to the host (graph capture).
+    ``flags=None`` only allocates (on the current stream); ``run(flags)`` launches."""
     __slots__ = ('N', 'perm', 'inv', 'live', 'count')
 
-    def __init__(self, flags):
-        flags = _dev(flags, torch.uint8, 'flags')
-        self.N = N = flags.numel()
-        self.perm = torch.empty((N,), dtype=torch.int32, device=flags.device)
-        self.inv = torch.empty((N,), dtype=torch.int32, device=flags.device)
-        self.live = torch.empty((N,), dtype=torch.uint8, device=flags.device)
-        self.count = torch.empty((1,), dtype=torch.int32, device=flags.device)
-        _call('gpt_live_rows', _ptr(flags), N, _ptr(self.perm), _ptr(self.inv), _ptr(self.live), _ptr(self.count), _stream())
+    def __init__(self, flags=None, n_rows=None, device=None):
+        if flags is not None:
+            flags = _dev(flags, torch.uint8, 'flags')
+            n_rows, device = flags.numel(), flags.device
+        self.N = N = int(n_rows)
+        self.perm = torch.empty((N,), dtype=torch.int32, device=device)
+        self.inv = torch.empty((N,), dtype=torch.int32, device=device)
+        self.live = torch.empty((N,), dtype=torch.uint8, device=device)
+        self.count = torch.empty((1,), dtype=torch.int32, device=device)
+        if flags is not None:
+            self.run(flags)
 
-    def gather(self, x2d):
+    def run(self, flags):
+        _call('gpt_live_rows', _ptr(flags), self.N, _ptr(self.perm), _ptr(self.inv), _ptr(self.live), _ptr(self.count),
+              _stream())
+        return self
+
+    def gather(self, x2d, out=None):
         """[N,K] -> compact [N,K]: row i < count is x2d[perm[i]]; the rest is never read."""
-        out = torch.empty_like(x2d)
+        out = torch.empty_like(x2d) if out is None else out
         _call('gpt_gather_rows', _ptr(x2d), _ptr(self.perm), _ptr(self.count), self.N, x2d.shape[1], _ptr(out), _stream())
         return out
 
@@ -455,6 +464,19 @@ class LiveRows(object):
         out = torch.empty_like(xc)
         _call('gpt_scatter_rows', _ptr(xc), _ptr(self.inv), self.N, xc.shape[1], _ptr(out), _stream())
         return out
+
+
+def wgrad_rows_tc_ok(N, K):
+    """Shapes the tensor-core weight gradient over compacted rows takes (csrc/wgrad_tcgen05.cu)."""
+    return K % 4 == 0 and N % 4 == 0 and K <= 512
+
+
+def linear_wgrad_live_acc(dyc, xc, live, out):
+    """out += dyc^T xc over the compact rows i < count (3xTF32 on the tensor cores)."""
+    M, N = dyc.shape
+    _call('gpt_linear_wgrad_tf32x3_rows', _ptr(dyc), _ptr(xc), _ptr(live.live), _ptr(out), M, N, xc.shape[1],
+          _ptr(live.count), _stream())
+    return out
 
 
 def _linear_fwd_rows(xc, weight, mode, ws, live, bias=None):

@@ -486,3 +486,23 @@ def test_k2_backward_prologue_fused_into_its_producers(T, H, k):
         dy = ops.aggregate_bwd_pre(g.view(B, T, H), csr, dbias_out=db)
         assert torch.equal(dy, dy_ref)
         assert _rel(db, db_ref) <= 1e-5
+
+
+def test_tensor_core_weight_gradient_over_compacted_rows_at_tacred_size(monkeypatch):
+    """GPT_TC_WGRAD_SMALL=1 (off by default): the layers' weight gradients from ops.LiveRows-compacted rows
+    on the tensor cores == the FFMA kernel over the live rows, 1e-5 relative, and the fused step still trains."""
+    grads = []
+    for on in ('0', '1'):
+        monkeypatch.setenv('GPT_TC_WGRAD_SMALL', on)
+        torch.manual_seed(2)
+        tr = GCNTrainer(synth.tacred_opt(vocab_size=900, cuda=True, input_dropout=0.0, gcn_dropout=0.0, gemm_mode='tf32x3'))
+        tr.model.train()
+        batch = tuple(t.cuda() if torch.is_tensor(t) else t for t in synth.make_batch(31, batch_size=50, vocab_size=900))
+        eng = FusedTrainStep(tr, capture=False)
+        inputs, labels = batch[:8], batch[8]
+        eng._backward(eng._forward(inputs, labels))
+        torch.cuda.synchronize()
+        gcn = tr.model.gcn_model.gcn
+        grads.append([eng.flat.g(lin.weight).clone() for lin in gcn.W])
+    for a, b in zip(*grads):
+        assert float((a - b).abs().max() / a.abs().max()) <= 1e-5
