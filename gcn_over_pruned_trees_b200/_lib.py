@@ -28,6 +28,8 @@ SIGNATURES = {
     'gpt_gcn_aggregate_bwd_pool': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_gcn_aggregate_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_int, _p],
     'gpt_gcn_aggregate_bwd_pre': [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _p],
+    'gpt_gcn_aggregate_bwd_pre_c': [_p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _p],
+    'gpt_gcn_aggregate_bwd_pool_c': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_pool3_bwd_masked': [_p, _p, _p, _p, _p, _c_f, _c_int, _c_int, _c_int, _c_int, _p, _p],
     'gpt_linear_dgrad_tf32x3_masked': [_p, _p, _p, _p, _p, _c_f, _c_int, _c_int, _c_int, _c_int, _p],
     'gpt_pool3_fwd': [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p],

@@ -59,6 +59,10 @@ struct AggParams {
     // [tma_rows x HS] floats, tma_rows divides T) instead of one cp.async per 16 bytes issued by every thread -- in the
     // cp.async version 17 % of all instructions of the forward kernel were address arithmetic for those copies
     int tma_rows;
+    // bwd, optional: every stored row of dy is stored a second time at its position in the batch's compact row list
+    // (gpt_live_rows: inv[b*T + i] >= 0), so that the weight gradient can read the live rows as one dense block
+    const int* inv;
+    float* out_c;
 };
 
 #ifdef GPT_HOST_EMULATION   // tests/emu: the same accessors on a host array instead of PTX
@@ -696,8 +700,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 3) aggregate_bwd_kernel(co
             gather4<HS>(tile_lane, col_s, T, mx, acc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (rows[q] < T && col_ok)
+                if (rows[q] < T && col_ok) {
                     store4<ALIGNED>(out_lane + (uint32_t)rows[q] * (uint32_t)H, unpack(acc[q]), c_lane, H);
+                    if (p.out_c != nullptr) {           // CTA-uniform
+                        const int pos = p.inv[(size_t)b * T + rows[q]];
+                        if (pos >= 0) store4<ALIGNED>(p.out_c + (size_t)pos * H + c_lane, unpack(acc[q]), c_lane, H);
+                    }
+                }
         }
         if (p.dbias != nullptr) *reinterpret_cast<float4*>(red + (warp * RPW + sub) * HS + cl) = unpack(csum);
         __syncthreads();  // tile buffer free for the refill; red[] complete
@@ -898,32 +907,56 @@ extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const 
 
 // K2 backward of the LAST layer fused with K4's backward (max pooling): the incoming gradient is d(pooled) [B,3H] +
 // argmax [B,3H]; g = scatter(d pooled) * [out > 0] / denom is formed in shared memory, never in HBM.
+extern "C" int gpt_gcn_aggregate_bwd_pool_c(const float* dpooled, const int32_t* argmax, const uint32_t* act_mask,
+                                            const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
+                                            float* dbias, const int32_t* inv, float* dy_compact, int B, int T, int H,
+                                            int use_adj, void* stream);
+
 extern "C" int gpt_gcn_aggregate_bwd_pool(const float* dpooled, const int32_t* argmax, const uint32_t* act_mask,
                                           const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
                                           float* dbias, int B, int T, int H, int use_adj, void* stream) {
+    return gpt_gcn_aggregate_bwd_pool_c(dpooled, argmax, act_mask, rowptr, col, denom, dy, dbias, nullptr, nullptr, B, T, H,
+                                        use_adj, stream);
+}
+
+extern "C" int gpt_gcn_aggregate_bwd_pool_c(const float* dpooled, const int32_t* argmax, const uint32_t* act_mask,
+                                            const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
+                                            float* dbias, const int32_t* inv, float* dy_compact, int B, int T, int H,
+                                            int use_adj, void* stream) {
     GPT_CHECK_ARG(dpooled && argmax && act_mask && rowptr && col && denom && dy);
+    GPT_CHECK_ARG((inv == nullptr) == (dy_compact == nullptr));
     GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1);
     if (B == 0) return GPT_OK;
     if (B > 65535) return GPT_ERR_UNSUPPORTED;
     AggParams p{};
     p.y = dpooled; p.act_in = act_mask; p.rowptr = rowptr; p.col = col; p.denom = denom; p.out = dy; p.dbias = dbias;
     p.pool_g = dpooled; p.pool_arg_in = argmax;
+    p.inv = inv; p.out_c = dy_compact;
     p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
     set_dropout(p, 0.f);
     return dispatch(false, p, 0, (cudaStream_t)stream);
 }
 
-extern "C" int gpt_gcn_aggregate_bwd_pre(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom,
-                                         float* dy, float* dbias, int B, int T, int H, int use_adj, int force_vec,
-                                         void* stream) {
-    GPT_CHECK_ARG(g && rowptr && col && denom && dy);
+// inv / dy_compact (both or neither): also store every live row of dy at inv[row] of dy_compact (see AggParams)
+extern "C" int gpt_gcn_aggregate_bwd_pre_c(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom,
+                                           float* dy, float* dbias, const int32_t* inv, float* dy_compact, int B, int T,
+                                           int H, int use_adj, int force_vec, void* stream) {
+    GPT_CHECK_ARG(g && rowptr && col && denom && dy && (inv == nullptr) == (dy_compact == nullptr));
     GPT_CHECK_ARG(B >= 0 && T >= 1 && H >= 1);
     if (B == 0) return GPT_OK;
     if (B > 65535) return GPT_ERR_UNSUPPORTED;
     AggParams p{};
     p.y = g; p.rowptr = rowptr; p.col = col; p.denom = denom; p.out = dy; p.dbias = dbias;
+    p.inv = inv; p.out_c = dy_compact;
     p.B = B; p.T = T; p.H = H; p.cap = 3 * T; p.use_adj = use_adj;
     p.pre_scaled = 1;
     set_dropout(p, 0.f);
     return dispatch(false, p, force_vec, (cudaStream_t)stream);
+}
+
+extern "C" int gpt_gcn_aggregate_bwd_pre(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom,
+                                         float* dy, float* dbias, int B, int T, int H, int use_adj, int force_vec,
+                                         void* stream) {
+    return gpt_gcn_aggregate_bwd_pre_c(g, rowptr, col, denom, dy, dbias, nullptr, nullptr, B, T, H, use_adj, force_vec,
+                                       stream);
 }

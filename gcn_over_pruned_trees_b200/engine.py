@@ -442,6 +442,8 @@ class FusedTrainStep(object):
         self._fork(sb)
         with torch.cuda.stream(sa):
             ops.prune_csr(head, subj_pos, obj_pos, deprel, masks, opt['prune_k'], out=csr)
+            ev_csr = torch.cuda.Event()
+            ev_csr.record(sa)                    # the chain waits for the CSR only, not for what follows on this branch
             if live is not None:
                 live.run(csr.flags)
         with torch.cuda.stream(sb):
@@ -459,7 +461,7 @@ class FusedTrainStep(object):
         for l, lin in enumerate(gcn.W):
             y = ops.linear_fwd(h.view(B * T, -1), lin.weight.data, mode, wss[l])
             if l == 0:
-                self._join(sa)
+                main.wait_event(ev_csr)
             xs.append(h)
             if live is not None:        # the layer input's live rows, packed: off the chain, read by the backward only
                 h2d = h.view(B * T, -1)
@@ -519,21 +521,29 @@ class FusedTrainStep(object):
         cur = ('pool', None) if fuse_pool else ('g', ops.pool3_bwd_masked(buf.dpooled, st.argmax, csr, ptype, H, acts[-1], 0.0))
         for l in range(n_layers - 1, -1, -1):
             lin = gcn.W[l]
+            # with st.live (tensor-core weight gradient over the live rows) K2's backward stores dy's live rows a second time,
+            # compactly: no gather launch between it and the weight gradient
+            live = st.live
+            dyc = torch.empty((B * T, H), dtype=torch.float32, device=words.device) if live is not None else None
+            compact_done = live is not None
             if cur[0] == 'pool':                # K4's backward inside K2's: the [B,T,H] gradient never exists
-                dy = ops.aggregate_bwd_pool(buf.dpooled, st.argmax, acts[-1], csr, H, use_adj, dbias_out=fl.g(lin.bias))
+                dy = ops.aggregate_bwd_pool(buf.dpooled, st.argmax, acts[-1], csr, H, use_adj, dbias_out=fl.g(lin.bias),
+                                            live=live, compact_out=dyc)
             elif cur[0] == 'g':
-                dy = ops.aggregate_bwd_pre(cur[1], csr, use_adj, dbias_out=fl.g(lin.bias))
+                dy = ops.aggregate_bwd_pre(cur[1], csr, use_adj, dbias_out=fl.g(lin.bias), live=live, compact_out=dyc)
             else:
                 dy, _ = ops.aggregate_bwd(cur[1], None, csr, use_adj, 0.0 if l == n_layers - 1 else p_gcn, None,
                                           act=acts[l], dbias_out=fl.g(lin.bias))
+                compact_done = False
             keep.append(dy)
-            side = sb if (n_layers - 1 - l) % 2 == 0 else sa
-            dyc = torch.empty_like(dy) if st.live is not None else None
             keep.append(dyc)
+            side = sb if (n_layers - 1 - l) % 2 == 0 else sa
             self._fork(side)
             with torch.cuda.stream(side):
-                if st.live is not None:
-                    ops.linear_wgrad_live_acc(st.live.gather(dy, out=dyc), st.xc[l], st.live, fl.g(lin.weight))
+                if live is not None:
+                    if not compact_done:
+                        live.gather(dy, out=dyc)
+                    ops.linear_wgrad_live_acc(dyc, st.xc[l], live, fl.g(lin.weight))
                 else:
                     ops.linear_wgrad(dy, xs[l].view(B * T, -1), mode, out=fl.g(lin.weight), accumulate=True,
                                      flags=csr.flags)

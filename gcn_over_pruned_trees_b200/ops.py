@@ -274,12 +274,14 @@ def aggregate_pool_ok(B, T, H):
     return bool(_lib.lib().gpt_gcn_aggregate_fwd_pool_supported(int(B), int(T), int(H)))
 
 
-def aggregate_bwd_pool(dpooled, argmax, act, csr, H, use_adj=True, dbias_out=None):
-    """K4 backward (max) + K2 backward of the last layer in one launch: d(pooled) [B,3H] -> dy [B*T, H]."""
+def aggregate_bwd_pool(dpooled, argmax, act, csr, H, use_adj=True, dbias_out=None, live=None, compact_out=None):
+    """K4 backward (max) + K2 backward of the last layer in one launch: d(pooled) [B,3H] -> dy [B*T, H].  With ``live``
+    (LiveRows) and ``compact_out`` [B*T, H] the live rows of dy are also stored compactly (row inv[n] of compact_out)."""
     B, T = csr.B, csr.T
     dy = torch.empty((B * T, H), dtype=torch.float32, device=dpooled.device)
-    _call('gpt_gcn_aggregate_bwd_pool', _ptr(dpooled), _ptr(argmax), _ptr(act), _ptr(csr.rowptr), _ptr(csr.col),
-          _ptr(csr.denom), _ptr(dy), _ptr(dbias_out), B, T, H, int(bool(use_adj)), _stream())
+    _call('gpt_gcn_aggregate_bwd_pool_c', _ptr(dpooled), _ptr(argmax), _ptr(act), _ptr(csr.rowptr), _ptr(csr.col),
+          _ptr(csr.denom), _ptr(dy), _ptr(dbias_out), _ptr(live.inv if live is not None else None),
+          _ptr(compact_out if live is not None else None), B, T, H, int(bool(use_adj)), _stream())
     return dy
 
 
@@ -1027,12 +1029,13 @@ def linear_dgrad_masked(dy, weight, ws, act_prev, csr, p_drop_prev):
     return g
 
 
-def aggregate_bwd_pre(g, csr, use_adj=True, dbias_out=None, force_vec=0):
+def aggregate_bwd_pre(g, csr, use_adj=True, dbias_out=None, force_vec=0, live=None, compact_out=None):
     B, T = csr.B, csr.T
     H = g.shape[-1]
     dy = torch.empty((B * T, H), dtype=torch.float32, device=g.device)
-    _call('gpt_gcn_aggregate_bwd_pre', _ptr(g), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom), _ptr(dy),
-          _ptr(dbias_out), B, T, H, int(bool(use_adj)), int(force_vec), _stream())
+    _call('gpt_gcn_aggregate_bwd_pre_c', _ptr(g), _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.denom), _ptr(dy),
+          _ptr(dbias_out), _ptr(live.inv if live is not None else None),
+          _ptr(compact_out if live is not None else None), B, T, H, int(bool(use_adj)), int(force_vec), _stream())
     return dy
 
 

@@ -113,6 +113,15 @@ int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* a
  * dbias += 2 * sum_i g_i.  One shared-memory pass and one barrier per slice less than gpt_gcn_aggregate_bwd. */
 int gpt_gcn_aggregate_bwd_pre(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
                               float* dbias, int B, int T, int H, int use_adj, int force_vec, void* stream);
+/* The two calls above with a second, compact copy of dy: every row n with inv[n] >= 0 (gpt_live_rows) is also stored at
+ * dy_compact[inv[n], :], so that the tensor-core weight gradient (gpt_linear_wgrad_tf32x3_rows) reads the live rows as one
+ * dense block without a gather launch in between.  inv == dy_compact == NULL: exactly the calls above. */
+int gpt_gcn_aggregate_bwd_pool_c(const float* dpooled, const int32_t* argmax, const uint32_t* act_mask,
+                                 const int32_t* rowptr, const int32_t* col, const float* denom, float* dy, float* dbias,
+                                 const int32_t* inv, float* dy_compact, int B, int T, int H, int use_adj, void* stream);
+int gpt_gcn_aggregate_bwd_pre_c(const float* g, const int32_t* rowptr, const int32_t* col, const float* denom, float* dy,
+                                float* dbias, const int32_t* inv, float* dy_compact, int B, int T, int H, int use_adj,
+                                int force_vec, void* stream);
 
 /* K4. three masked pools + cat (model/gcn.py:116-121, 473-483): out float [B,3H] = [h_out, subj_out, obj_out];
  * argmax int32 [B,3H] (token index or -1) is required for GPT_POOL_MAX. */

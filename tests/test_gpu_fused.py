@@ -506,3 +506,27 @@ def test_tensor_core_weight_gradient_over_compacted_rows_at_tacred_size(monkeypa
         grads.append([eng.flat.g(lin.weight).clone() for lin in gcn.W])
     for a, b in zip(*grads):
         assert float((a - b).abs().max() / a.abs().max()) <= 1e-5
+
+
+def test_k2_backward_also_stores_the_live_rows_compactly():
+    """gpt_gcn_aggregate_bwd_{pre,pool}_c: dy unchanged, and dy's live rows (gpt_live_rows) also at their compact position."""
+    B, T, H = 23, 61, 200
+    batch = synth.make_batch(9, batch_size=B, vocab_size=500, pad_to=T)
+    dev = [t.cuda() if torch.is_tensor(t) else t for t in batch]
+    csr = ops.prune_csr(dev[5], dev[6], dev[7], dev[4], dev[1], 1)
+    live = ops.LiveRows(csr.flags)
+    cnt = int(live.count)
+    idx = csr.flags.view(-1).nonzero().flatten()
+    g = torch.randn(B, T, H, device=DEV) * csr.flags.view(B, T, 1).ne(0)
+    ref = ops.aggregate_bwd_pre(g, csr)
+    dyc = torch.full((B * T, H), float('nan'), device=DEV)
+    got = ops.aggregate_bwd_pre(g, csr, live=live, compact_out=dyc)
+    assert torch.equal(got, ref) and torch.equal(dyc[:cnt], ref[idx]) and bool(dyc[cnt:].isnan().all())
+    # the pooled variant: act bits and argmax rows from a forward of the last layer
+    y = torch.randn(B * T, H, device=DEV)
+    pooled, argmax, act, _ = ops.aggregate_fwd_pool(y, csr, torch.zeros(H, device=DEV))
+    dpooled = torch.randn(B, 3 * H, device=DEV)
+    ref = ops.aggregate_bwd_pool(dpooled, argmax, act, csr, H)
+    dyc.fill_(float('nan'))
+    got = ops.aggregate_bwd_pool(dpooled, argmax, act, csr, H, live=live, compact_out=dyc)
+    assert torch.equal(got, ref) and torch.equal(dyc[:cnt], ref[idx]) and bool(dyc[cnt:].isnan().all())

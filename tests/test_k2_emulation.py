@@ -16,7 +16,8 @@ from gcn_over_pruned_trees_b200 import _lib, ops, synth
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
 NAMES = ('gpt_prune_csr', 'gpt_linear_fwd_f32', 'gpt_linear_dgrad_f32', 'gpt_linear_wgrad_f32', 'gpt_pool3_fwd',
          'gpt_pool3_bwd', 'gpt_gcn_aggregate_fwd', 'gpt_gcn_aggregate_bwd', 'gpt_gcn_aggregate_bwd_pre',
-         'gpt_gcn_aggregate_fwd_pool', 'gpt_gcn_aggregate_fwd_pool_supported', 'gpt_gcn_aggregate_bwd_pool')
+         'gpt_gcn_aggregate_fwd_pool', 'gpt_gcn_aggregate_fwd_pool_supported', 'gpt_gcn_aggregate_bwd_pool',
+         'gpt_gcn_aggregate_bwd_pool_c', 'gpt_gcn_aggregate_bwd_pre_c')
 
 
 @pytest.fixture(scope='module', autouse=True)
