@@ -21,6 +21,7 @@
 //               into dW with vector reductions (red.global.add.v4.f32); the partial sums of all CTAs meet in L2.
 //               Short accumulation chains keep the tensor core's round-toward-zero accumulation below 1e-5 relative
 #include "tcgen05_util.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -40,36 +41,107 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
+// ---- CTA pair (cta_group::2) helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+            : "memory");
+    } else {
+        umma_tf32(tmem_d, a_desc, b_desc, idesc, acc);
+    }
+}
+// arrive, once every MMA issued so far by this thread has completed, on the barrier at this offset in every CTA of the pair
+template <int CG>
+__device__ __forceinline__ void commit_cg(uint32_t bar) {
+    if (CG == 2) {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(bar), "h"((unsigned short)3)
+            : "memory");
+    } else {
+        umma_commit(bar);
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t holder, uint32_t cols) {
+    if (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        tmem_alloc(holder, cols);
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t base, uint32_t cols) {
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+    else tmem_dealloc(base, cols);
+}
+
+// CG = 2: a CTA PAIR owns 256 rows of dW (two neighbouring n-slices, one per CTA) over one row range.  Each CTA stages and
+// splits its own 128 columns of dY and only HALF of X's columns; tcgen05.mma.cta_group::2 (M = 256) reads both halves, so
+// per CTA the shared-memory traffic of X -- landing, splitting into hi / lo, operand reads of the three passes -- is halved.
+// That traffic, not the tensor core, bounds the single-CTA kernel (ncu: 53 % tensor-pipe activity at the large shape).
+// kboxes is then the number of 32-column boxes of X THIS CTA stages per chunk-half (see the launcher).
+template <int CG>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
                     const unsigned char* __restrict__ flags, float* __restrict__ dW, long long M, int N, int K,
-                    int n_slices, long long rows_per_part, int kboxes, int tmem_cols, int STAGES,
+                    int n_units, long long rows_per_part, int kboxes, int tmem_cols, int STAGES,
                     const int* __restrict__ m_live) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[3 * WG_MAX_STAGES + 2];
+    __shared__ __align__(8) unsigned long long bars[4 * WG_MAX_STAGES + 2];
     __shared__ uint32_t tmem_base_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = (int)(blockIdx.x % n_slices) * WG_NSLICE;
-    const long long part = blockIdx.x / n_slices;
+    const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+    const bool leader = rank == 0;
+    const int unit = (int)(blockIdx.x / CG);                 // a CTA (CG = 1) or a CTA pair: (n-slice unit, row range)
+    const int n0 = ((unit % n_units) * CG + (int)rank) * WG_NSLICE;
+    const long long part = unit / n_units;
     if (m_live != nullptr) {
         // device-side row count: the row ranges are cut here, over the live rows only (the host cut them over all M rows)
         const long long live = *m_live < M ? *m_live : M;
-        const long long parts = gridDim.x / n_slices;
+        const long long parts = (gridDim.x / CG) / n_units;
         M = live;
         rows_per_part = ((live + WG_ROWS - 1) / WG_ROWS + parts - 1) / parts * WG_ROWS;
     }
     const long long m_begin = part * rows_per_part;
     const long long m_end = m_begin + rows_per_part < M ? m_begin + rows_per_part : M;
     const int nkb = m_end > m_begin ? (int)((m_end - m_begin + WG_ROWS - 1) / WG_ROWS) : 0;
-    // stage: [dY hi: 4 boxes | dY lo: 4 boxes | X hi: kboxes | X lo: kboxes]
-    const uint32_t a_bytes = WG_ABOXES * WG_BOX_BYTES, b_bytes = (uint32_t)kboxes * WG_BOX_BYTES;
+    // X boxes: kboxes in all (even when CG = 2), accumulated in chunks of <= 8 boxes = 256 tensor-memory columns; of every
+    // chunk this CTA stages 1/CG: chunk c holds nb_c boxes, this CTA its boxes [rank * nb_c / CG, (rank + 1) * nb_c / CG)
+    constexpr int kChunk = 8 / CG;                            // boxes of a full chunk staged by one CTA
+    const int kb_mine = kboxes / CG;
+    // stage: [dY hi: 4 boxes | dY lo: 4 boxes | X hi: kb_mine | X lo: kb_mine]
+    const uint32_t a_bytes = WG_ABOXES * WG_BOX_BYTES, b_bytes = (uint32_t)kb_mine * WG_BOX_BYTES;
     const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);
     const uint32_t off_alo = a_bytes, off_b = 2u * a_bytes, off_blo = off_b + b_bytes;
     const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
     const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[WG_MAX_STAGES]);
-    const uint32_t split0 = smem_addr(&bars[2 * WG_MAX_STAGES]), done = smem_addr(&bars[3 * WG_MAX_STAGES]);
-    const uint32_t drained = smem_addr(&bars[3 * WG_MAX_STAGES + 1]);
+    const uint32_t split0 = smem_addr(&bars[2 * WG_MAX_STAGES]), ready0 = smem_addr(&bars[3 * WG_MAX_STAGES]);
+    const uint32_t done = smem_addr(&bars[4 * WG_MAX_STAGES]), drained = smem_addr(&bars[4 * WG_MAX_STAGES + 1]);
 
     if (warp == 0 && lane == 0) {
         prefetch_map(&tm_dy);
@@ -78,19 +150,21 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
             mbar_init(split0 + 8 * s, 32 * WG_SPLIT_WARPS);
+            mbar_init(ready0 + 8 * s, 1);                     // CG = 2, leader: the peer's operands of stage s are split
         }
         mbar_init(done, 1);
-        mbar_init(drained, 32 * WG_SPLIT_WARPS);
+        mbar_init(drained, 32 * WG_SPLIT_WARPS * CG);         // CG = 2: the flush warps of both CTAs arrive on the leader's
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_addr(&tmem_base_holder), (uint32_t)tmem_cols);
+    if (warp == 1) tmem_alloc_cg<CG>(smem_addr(&tmem_base_holder), (uint32_t)tmem_cols);
     fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();       // the peer's barriers exist before anything arrives on them
     fence_after();
     const uint32_t tmem_base = tmem_base_holder;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: this CTA's 128 columns of dY and its share of X's columns =====
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
@@ -101,13 +175,17 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < WG_ABOXES; ++j)   // columns past N / rows past M arrive as zeros
                     tma_load_2d(st + (uint32_t)j * WG_BOX_BYTES, &tm_dy, full0 + 8 * s, n0 + 32 * j, row);
-                for (int j = 0; j < kboxes; ++j)
-                    tma_load_2d(st + off_b + (uint32_t)j * WG_BOX_BYTES, &tm_x, full0 + 8 * s, 32 * j, row);
+                for (int jl = 0; jl < kb_mine; ++jl) {
+                    const int c = jl / kChunk, j = jl - c * kChunk;
+                    const int nb_c = kboxes - 8 * c < 8 ? kboxes - 8 * c : 8;
+                    const int box = 8 * c + (int)rank * (nb_c / CG) + j;       // columns past K arrive as zeros
+                    tma_load_2d(st + off_b + (uint32_t)jl * WG_BOX_BYTES, &tm_x, full0 + 8 * s, 32 * box, row);
+                }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && leader) {
+            // ===== MMA issuer (the leader drives the tensor cores of both SMs) =====
             const int nchunks = (kboxes + 7) / 8;      // <= 256 accumulator columns per instruction
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
@@ -117,6 +195,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                     fence_after();
                 }
                 mbar_wait(split0 + 8 * s, (kb / STAGES) & 1);
+                if (CG == 2) mbar_wait(ready0 + 8 * s, (kb / STAGES) & 1);
                 fence_after();
                 const uint32_t st = tiles + (uint32_t)s * stage_bytes;
 #pragma unroll
@@ -125,32 +204,41 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                     const uint32_t b_base = st + (pass == 2 ? off_blo : off_b);
                     for (int c = 0; c < nchunks; ++c) {
                         const int nb = kboxes - 8 * c < 8 ? kboxes - 8 * c : 8;
-                        const uint32_t idesc = make_idesc_tf32(WG_NSLICE, 32 * nb, true, true);
+                        const uint32_t idesc = make_idesc_tf32(WG_NSLICE * CG, 32 * nb, true, true);
 #pragma unroll
                         for (int k8 = 0; k8 < WG_ROWS / 8; ++k8) {   // 8 rows = two 4-row atoms (SBO 512 B); next K-step: +1024 B
                             const uint64_t a_desc = make_desc(a_base + (uint32_t)k8 * 1024u, WG_BOX_BYTES, 512u, kLayoutSw128Base32);
-                            const uint64_t b_desc = make_desc(b_base + (uint32_t)c * 8u * WG_BOX_BYTES + (uint32_t)k8 * 1024u,
+                            const uint64_t b_desc = make_desc(b_base + (uint32_t)(c * kChunk) * WG_BOX_BYTES + (uint32_t)k8 * 1024u,
                                                               WG_BOX_BYTES, 512u, kLayoutSw128Base32);
-                            umma_tf32(tmem_base + (uint32_t)c * 256u, a_desc, b_desc, idesc,
-                                      (in_group | pass | k8) != 0 ? 1u : 0u);
+                            umma_tf32_cg<CG>(tmem_base + (uint32_t)c * 256u, a_desc, b_desc, idesc,
+                                             (in_group | pass | k8) != 0 ? 1u : 0u);
                         }
                     }
                 }
-                umma_commit(empty0 + 8 * s);
-                if (in_group == WG_FLUSH - 1 || kb == nkb - 1) umma_commit(done);   // accumulator of this group complete
+                commit_cg<CG>(empty0 + 8 * s);
+                if (in_group == WG_FLUSH - 1 || kb == nkb - 1) commit_cg<CG>(done);   // accumulator of this group complete
+            }
+        } else if (lane == 0 && CG == 2) {
+            // ===== peer CTA: tell the leader when this CTA's operands of a stage are split =====
+            const uint32_t ready_leader = map_to_rank(ready0, 0);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(split0 + 8 * s, (kb / STAGES) & 1);
+                mbar_arrive_remote(ready_leader + 8 * s);
             }
         }
     } else {
         // ===== splitters (+ the accumulator flushes) =====
         // thread u: 16-byte chunk (u & 127) of the boxes u >> 7, (u >> 7) + 2, ...; the chunk's row is (u & 127) / 8
         const uint32_t u = threadIdx.x - 64, t = u & 127u;
-        const int j0 = (int)(u >> 7), nboxes = WG_ABOXES + kboxes;
+        const int j0 = (int)(u >> 7), nboxes = WG_ABOXES + kb_mine;
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;              // warps 2..5: first half of the accumulator columns, 6..9: second
         const int cols = 32 * kboxes, c_begin = half * ((kboxes + 1) / 2) * 32;
         const int c_end = half == 0 ? ((kboxes + 1) / 2) * 32 : cols;
         const int n = n0 + q * 32 + lane;
         float* wrow = dW + (size_t)n * K;
+        const uint32_t drained_leader = CG == 2 ? map_to_rank(drained, 0) : drained;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             const long long row = m_begin + (long long)kb * WG_ROWS + (t >> 3);
@@ -210,14 +298,16 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                     }
                 }
                 fence_before();
-                mbar_arrive(drained);
+                if (CG == 2) mbar_arrive_remote(drained_leader);
+                else mbar_arrive(drained);
             }
         }
     }
 
     fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    if (CG == 2) cluster_sync_all();        // the peer may still be signalling barriers in this CTA / reading its operands
+    if (warp == 1) tmem_dealloc_cg<CG>(tmem_base, (uint32_t)tmem_cols);
 }
 
 }  // namespace
@@ -233,6 +323,55 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     if (K % 4 != 0 || N % 4 != 0 || K > 512 || M > 0x7fffffffLL - 64 || (reinterpret_cast<uintptr_t>(dy) & 15) ||
         (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dw) & 15))
         return GPT_ERR_UNSUPPORTED;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_slices = (N + WG_NSLICE - 1) / WG_NSLICE;
+    const long long blocks16 = (M + WG_ROWS - 1) / WG_ROWS;
+    alignas(64) CUtensorMap tm_dy, tm_x;
+    int rc = tc::make_map_f32(&tm_dy, dy, M, N, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != GPT_OK) return rc;
+    if ((rc = tc::make_map_f32(&tm_x, x, M, K, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GPT_OK) return rc;
+
+    // Long reductions over >= 2 n-slices: CTA pairs (cta_group::2, see the kernel) -- X is staged and split once per pair
+    static const bool pair_ok = [] { const char* e = getenv("GPT_WGRAD_PAIR"); return e == nullptr || atoi(e) != 0; }();
+    // (measured at 2 097 152 rows x 512 columns of dY: K = 512  6.29 -> 5.09 ms -- the single-CTA ring has room for two
+    // stages there, the pair's for four; K = 360  4.26 -> 4.47 ms: three stages were enough, the pair only adds signalling)
+    if (pair_ok && n_slices >= 2 && M >= 32768 && K > 416) {
+        const int kboxes = ((K + 31) / 32 + 1) / 2 * 2;          // even: every chunk is halved between the two CTAs
+        int tmem_cols = 32;
+        while (tmem_cols < 32 * kboxes) tmem_cols <<= 1;
+        const size_t stage = 2 * (size_t)(WG_ABOXES + kboxes / 2) * WG_BOX_BYTES;
+        int stages = (int)((220 * 1024) / stage);
+        stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
+        const size_t smem = (size_t)stages * stage + 1024;
+        const int n_pairs = (n_slices + 1) / 2;
+        long long m_parts = (sms / 2) / n_pairs;
+        if (m_parts < 1) m_parts = 1;
+        if (m_parts > blocks16 / 16) m_parts = blocks16 / 16 > 0 ? blocks16 / 16 : 1;
+        const long long rows_per_part = ((blocks16 + m_parts - 1) / m_parts) * WG_ROWS;
+        m_parts = (M + rows_per_part - 1) / rows_per_part;
+        if (tmem_cols <= 512 && stages >= 2) {
+            if (int a = gpt_smem_opt_in(wgrad_tf32x3_kernel<2>, smem)) return a;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(n_pairs * m_parts * 2));
+            cfg.blockDim = dim3(WG_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tf32x3_kernel<2>, tm_dy, tm_x, flags, dw, M, N, K, n_pairs,
+                                                     rows_per_part, kboxes, tmem_cols, stages, m_live);
+            if (e != cudaSuccess) return (int)e;
+            return gpt_launch_status();
+        }
+    }
+
     const int kboxes = (K + 31) / 32;
     int tmem_cols = 32;
     while (tmem_cols < 32 * kboxes) tmem_cols <<= 1;
@@ -240,10 +379,6 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     int stages = (int)((220 * 1024) / stage);
     stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
     if (stages < 2) return GPT_ERR_UNSUPPORTED;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_slices = (N + WG_NSLICE - 1) / WG_NSLICE;
     long long m_parts = sms / n_slices;
     if (m_parts < 1) m_parts = 1;
     // When one CTA per SM would leave a quarter of the SMs without one (79 slices of a [D*H = 10 000, K] gradient on 148
@@ -254,19 +389,14 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
         m_parts = 2LL * sms / n_slices;
     }
     const size_t smem = (size_t)stages * stage + 1024;
-    const long long blocks16 = (M + WG_ROWS - 1) / WG_ROWS;
     // every row range ends with a flush of its [128, K] partial tile into dW (vector reductions): a range of fewer than
     // 16 blocks spends more on the flush than on the rows (the TACRED-sized batches: a few hundred blocks in all)
     if (m_parts > blocks16 / 16) m_parts = blocks16 / 16 > 0 ? blocks16 / 16 : 1;
     if (m_parts > blocks16) m_parts = blocks16;
     const long long rows_per_part = ((blocks16 + m_parts - 1) / m_parts) * WG_ROWS;
     m_parts = (M + rows_per_part - 1) / rows_per_part;
-    alignas(64) CUtensorMap tm_dy, tm_x;
-    int rc = tc::make_map_f32(&tm_dy, dy, M, N, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc != GPT_OK) return rc;
-    if ((rc = tc::make_map_f32(&tm_x, x, M, K, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GPT_OK) return rc;
-    if (int a = gpt_smem_opt_in(wgrad_tf32x3_kernel, smem)) return a;
-    wgrad_tf32x3_kernel<<<(unsigned)(n_slices * m_parts), WG_THREADS, smem, (cudaStream_t)stream>>>(
+    if (int a = gpt_smem_opt_in(wgrad_tf32x3_kernel<1>, smem)) return a;
+    wgrad_tf32x3_kernel<1><<<(unsigned)(n_slices * m_parts), WG_THREADS, smem, (cudaStream_t)stream>>>(
         tm_dy, tm_x, flags, dw, M, N, K, n_slices, rows_per_part, kboxes, tmem_cols, stages, m_live);
     return gpt_launch_status();
 }

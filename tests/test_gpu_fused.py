@@ -280,7 +280,9 @@ def test_k3_wgrad_over_live_rows(M, N, K, frac):
 
 
 @pytest.mark.parametrize('M,N,K,frac', [(40000, 512, 360, 1.0), (33000, 200, 360, 0.4), (65536 + 5, 512, 512, 0.7),
-                                        (32768, 64, 100, 1.0), (50000, 200, 200, 0.0)])
+                                        (32768, 64, 100, 1.0), (50000, 200, 200, 0.0),
+                                        # CTA pairs (cta_group::2, K > 416): odd slice count, K not a multiple of 64, ragged M
+                                        (40001, 320, 512, 0.5), (33333, 200, 420, 1.0), (70000, 512, 448, 0.3)])
 def test_k3_wgrad_on_tensor_cores_is_fp32_grade(M, N, K, frac):
     """csrc/wgrad_tcgen05.cu (MN-major operands straight from HBM, 3xTF32): dw += dy^T x over the live rows, against
     fp64 at the fp32 parity tolerance (1e-5 relative); rows with flags == 0 may hold anything."""
