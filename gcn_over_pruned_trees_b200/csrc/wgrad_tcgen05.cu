@@ -13,7 +13,9 @@
 //                          range of token rows; grid = n_slices x m_parts <= one CTA per SM, the four n-slices of one
 //                          row range are neighbours in launch order so that X is read from HBM once and from L2 thrice
 //   warp 0      TMA producer: per 16-row block, 4 boxes of dY (128 columns) + ceil(K/32) boxes of X into a ring
-//   warps 2..9  splitters: every landed fp32 element v -> hi = round_tf32(v) in place, lo = v - hi next to it; rows
+//   warps 2..9  splitters: every landed fp32 element v -> hi = round_tf32(v) in place, lo = v - hi into one of two lo
+//               buffers behind the ring (a stage is held ~3 us, from the TMA issue to the end of its MMAs; a lo buffer
+//               only from the split to the end of the MMAs -- the shared memory saved makes the ring twice as deep); rows
 //               whose K1 flag is 0 (no gradient) are written as zeros, so dead rows are never accumulated
 //   warp 1      one thread issues, per block, hi.hi + lo.hi + hi.lo as tcgen05.mma.kind::tf32 (M = 128, N <= 256 per
 //               instruction, K = 8 rows) into the fp32 accumulator in tensor memory
@@ -31,7 +33,8 @@ constexpr int WG_ROWS = 16;                 // token rows per ring stage (two UM
 constexpr int WG_BOX_BYTES = WG_ROWS * 128;  // one TMA box: 16 rows x 32 fp32
 constexpr int WG_NSLICE = 128;              // dW rows per CTA (UMMA M)
 constexpr int WG_ABOXES = WG_NSLICE / 32;
-constexpr int WG_MAX_STAGES = 4;
+constexpr int WG_MAX_STAGES = 8;
+constexpr int WG_LO = 2;                      // lo buffers (see the kernel): written just before the MMAs that read them
 constexpr int WG_SPLIT_WARPS = 8;             // splitter / epilogue warps (warps 2..9)
 constexpr int WG_THREADS = 64 + 32 * WG_SPLIT_WARPS;
 constexpr int WG_FLUSH = 64;                  // k-blocks (x16 rows) accumulated in tensor memory between two flushes
@@ -111,7 +114,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                     int n_units, long long rows_per_part, int kboxes, int tmem_cols, int STAGES,
                     const int* __restrict__ m_live) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[4 * WG_MAX_STAGES + 2];
+    __shared__ __align__(8) unsigned long long bars[4 * WG_MAX_STAGES + 2 + WG_LO];
     __shared__ uint32_t tmem_base_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,14 +137,19 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
     // chunk this CTA stages 1/CG: chunk c holds nb_c boxes, this CTA its boxes [rank * nb_c / CG, (rank + 1) * nb_c / CG)
     constexpr int kChunk = 8 / CG;                            // boxes of a full chunk staged by one CTA
     const int kb_mine = kboxes / CG;
-    // stage: [dY hi: 4 boxes | dY lo: 4 boxes | X hi: kb_mine | X lo: kb_mine]
+    // ring of STAGES stages [dY: 4 boxes | X: kb_mine boxes]: the landed fp32 values, rewritten in place as their hi parts;
+    // behind it WG_LO buffers of the same shape for the lo parts.  A stage is held from the TMA issue to the end of its MMAs
+    // (~3 us: what the ring's depth has to cover), a lo buffer only from the split to the end of the MMAs -- two are enough,
+    // and the shared memory they do not take makes the ring twice as deep
     const uint32_t a_bytes = WG_ABOXES * WG_BOX_BYTES, b_bytes = (uint32_t)kb_mine * WG_BOX_BYTES;
-    const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);
-    const uint32_t off_alo = a_bytes, off_b = 2u * a_bytes, off_blo = off_b + b_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t off_b = a_bytes;
     const uint32_t tiles = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    const uint32_t lo_tiles = tiles + (uint32_t)STAGES * stage_bytes;
     const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[WG_MAX_STAGES]);
     const uint32_t split0 = smem_addr(&bars[2 * WG_MAX_STAGES]), ready0 = smem_addr(&bars[3 * WG_MAX_STAGES]);
     const uint32_t done = smem_addr(&bars[4 * WG_MAX_STAGES]), drained = smem_addr(&bars[4 * WG_MAX_STAGES + 1]);
+    const uint32_t lo_empty0 = smem_addr(&bars[4 * WG_MAX_STAGES + 2]);
 
     if (warp == 0 && lane == 0) {
         prefetch_map(&tm_dy);
@@ -152,6 +160,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
             mbar_init(split0 + 8 * s, 32 * WG_SPLIT_WARPS);
             mbar_init(ready0 + 8 * s, 1);                     // CG = 2, leader: the peer's operands of stage s are split
         }
+        for (int l = 0; l < WG_LO; ++l) mbar_init(lo_empty0 + 8 * l, 1);
         mbar_init(done, 1);
         mbar_init(drained, 32 * WG_SPLIT_WARPS * CG);         // CG = 2: the flush warps of both CTAs arrive on the leader's
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -198,10 +207,11 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                 if (CG == 2) mbar_wait(ready0 + 8 * s, (kb / STAGES) & 1);
                 fence_after();
                 const uint32_t st = tiles + (uint32_t)s * stage_bytes;
+                const uint32_t lo = lo_tiles + (uint32_t)(kb % WG_LO) * stage_bytes;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {   // hi.hi, lo.hi, hi.lo
-                    const uint32_t a_base = st + (pass == 1 ? off_alo : 0u);
-                    const uint32_t b_base = st + (pass == 2 ? off_blo : off_b);
+                    const uint32_t a_base = pass == 1 ? lo : st;
+                    const uint32_t b_base = (pass == 2 ? lo : st) + off_b;
                     for (int c = 0; c < nchunks; ++c) {
                         const int nb = kboxes - 8 * c < 8 ? kboxes - 8 * c : 8;
                         const uint32_t idesc = make_idesc_tf32(WG_NSLICE * CG, 32 * nb, true, true);
@@ -216,6 +226,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                     }
                 }
                 commit_cg<CG>(empty0 + 8 * s);
+                commit_cg<CG>(lo_empty0 + 8 * (kb % WG_LO));
                 if (in_group == WG_FLUSH - 1 || kb == nkb - 1) commit_cg<CG>(done);   // accumulator of this group complete
             }
         } else if (lane == 0 && CG == 2) {
@@ -244,15 +255,16 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
             const long long row = m_begin + (long long)kb * WG_ROWS + (t >> 3);
             const bool live = row < m_end && (flags == nullptr || flags[row] != 0);
             mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+            if (kb >= WG_LO) mbar_wait(lo_empty0 + 8 * (kb % WG_LO), ((kb / WG_LO) - 1) & 1);   // its last readers are done
             const uint32_t st = tiles + (uint32_t)s * stage_bytes + t * 16u;
+            const uint32_t lo_off = lo_tiles + (uint32_t)(kb % WG_LO) * stage_bytes - (tiles + (uint32_t)s * stage_bytes);
             for (int jb = j0; jb < nboxes; jb += 8) {   // four boxes per round: the loads are in flight together
                 float4 v[4];
                 uint32_t src[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int j = jb + 2 * i;
-                    src[i] = st + (j < WG_ABOXES ? (uint32_t)j * WG_BOX_BYTES
-                                                 : off_b + (uint32_t)(j - WG_ABOXES) * WG_BOX_BYTES);
+                    src[i] = st + (uint32_t)j * WG_BOX_BYTES;         // dY boxes, then X boxes: one contiguous stage
                     if (j < nboxes)
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src[i]));
@@ -261,7 +273,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_cons
                 for (int i = 0; i < 4; ++i) {
                     const int j = jb + 2 * i;
                     if (j >= nboxes) break;
-                    const uint32_t dst = src[i] + (j < WG_ABOXES ? off_alo : b_bytes);
+                    const uint32_t dst = src[i] + lo_off;
                     const float4 w = live ? v[i] : make_float4(0.f, 0.f, 0.f, 0.f);   // dead rows never accumulate
                     const float4 h = make_float4(tf32_hi(w.x), tf32_hi(w.y), tf32_hi(w.z), tf32_hi(w.w));
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src[i]), "f"(h.x), "f"(h.y), "f"(h.z),
@@ -333,18 +345,21 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     if (rc != GPT_OK) return rc;
     if ((rc = tc::make_map_f32(&tm_x, x, M, K, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GPT_OK) return rc;
 
-    // Long reductions over >= 2 n-slices: CTA pairs (cta_group::2, see the kernel) -- X is staged and split once per pair
+    // Long reductions over >= 2 n-slices CAN run on CTA pairs (cta_group::2, see the kernel): X staged and split once per
+    // pair.  Measured at 2 097 152 rows x 512 columns of dY: with the old ring (hi and lo halves in every stage: two
+    // stages at K = 512) the pair was 19 % faster (6.29 -> 5.09 ms); with the deep ring + two just-in-time lo buffers both
+    // forms run the same 5.1-5.2 ms (K = 360: 4.31 single, 4.43-4.64 pair) at 63 % tensor-pipe activity, and the single
+    // CTAs place more freely next to the step's other kernels.  So pairs are opt-in: GPT_WGRAD_PAIR_MIN_K=<K>.
     static const bool pair_ok = [] { const char* e = getenv("GPT_WGRAD_PAIR"); return e == nullptr || atoi(e) != 0; }();
-    // (measured at 2 097 152 rows x 512 columns of dY: K = 512  6.29 -> 5.09 ms -- the single-CTA ring has room for two
-    // stages there, the pair's for four; K = 360  4.26 -> 4.47 ms: three stages were enough, the pair only adds signalling)
-    if (pair_ok && n_slices >= 2 && M >= 32768 && K > 416) {
+    static const int pair_min_k = [] { const char* e = getenv("GPT_WGRAD_PAIR_MIN_K"); return e ? atoi(e) : (1 << 30); }();
+    if (pair_ok && n_slices >= 2 && M >= 32768 && K >= pair_min_k) {
         const int kboxes = ((K + 31) / 32 + 1) / 2 * 2;          // even: every chunk is halved between the two CTAs
         int tmem_cols = 32;
         while (tmem_cols < 32 * kboxes) tmem_cols <<= 1;
-        const size_t stage = 2 * (size_t)(WG_ABOXES + kboxes / 2) * WG_BOX_BYTES;
-        int stages = (int)((220 * 1024) / stage);
+        const size_t stage = (size_t)(WG_ABOXES + kboxes / 2) * WG_BOX_BYTES;      // + WG_LO buffers of the same size
+        int stages = (int)((220 * 1024) / stage) - WG_LO;
         stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
-        const size_t smem = (size_t)stages * stage + 1024;
+        const size_t smem = (size_t)(stages + WG_LO) * stage + 1024;
         const int n_pairs = (n_slices + 1) / 2;
         long long m_parts = (sms / 2) / n_pairs;
         if (m_parts < 1) m_parts = 1;
@@ -375,8 +390,8 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     const int kboxes = (K + 31) / 32;
     int tmem_cols = 32;
     while (tmem_cols < 32 * kboxes) tmem_cols <<= 1;
-    const size_t stage = 2 * (size_t)(WG_ABOXES + kboxes) * WG_BOX_BYTES;
-    int stages = (int)((220 * 1024) / stage);
+    const size_t stage = (size_t)(WG_ABOXES + kboxes) * WG_BOX_BYTES;              // + WG_LO buffers of the same size
+    int stages = (int)((220 * 1024) / stage) - WG_LO;
     stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
     if (stages < 2) return GPT_ERR_UNSUPPORTED;
     long long m_parts = sms / n_slices;
@@ -384,11 +399,12 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     // When one CTA per SM would leave a quarter of the SMs without one (79 slices of a [D*H = 10 000, K] gradient on 148
     // SMs), run TWO CTAs per SM with a two-stage ring each: twice the row ranges, every SM's tensor core fed by two
     // independent pipelines.  Needs both accumulators in tensor memory (2 x <= 256 columns) and both rings in shared memory.
-    if (n_slices * m_parts * 4 < 3LL * sms && tmem_cols <= 256 && 2 * (2 * stage + 1024) + 2048 <= 227 * 1024) {
-        stages = 2;
+    if (n_slices * m_parts * 4 < 3LL * sms && tmem_cols <= 256 && 2 * ((2 + WG_LO) * stage + 1024) + 2048 <= 227 * 1024) {
+        stages = (int)((110 * 1024) / stage) - WG_LO;
+        stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
         m_parts = 2LL * sms / n_slices;
     }
-    const size_t smem = (size_t)stages * stage + 1024;
+    const size_t smem = (size_t)(stages + WG_LO) * stage + 1024;
     // every row range ends with a flush of its [128, K] partial tile into dW (vector reductions): a range of fewer than
     // 16 blocks spends more on the flush than on the rows (the TACRED-sized batches: a few hundred blocks in all)
     if (m_parts > blocks16 / 16) m_parts = blocks16 / 16 > 0 ? blocks16 / 16 : 1;

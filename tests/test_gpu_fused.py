@@ -285,7 +285,8 @@ def test_k3_wgrad_over_live_rows(M, N, K, frac):
                                         (40001, 320, 512, 0.5), (33333, 200, 420, 1.0), (70000, 512, 448, 0.3)])
 def test_k3_wgrad_on_tensor_cores_is_fp32_grade(M, N, K, frac):
     """csrc/wgrad_tcgen05.cu (MN-major operands straight from HBM, 3xTF32): dw += dy^T x over the live rows, against
-    fp64 at the fp32 parity tolerance (1e-5 relative); rows with flags == 0 may hold anything."""
+    fp64 at the fp32 parity tolerance (1e-5 relative); rows with flags == 0 may hold anything.  (The CTA-pair form of the
+    kernel is opt-in per process -- GPT_WGRAD_PAIR_MIN_K, tests/test_gpu_multi-style subprocess below.)"""
     assert ops.wgrad_tc_ok(M, N, K)
     g = torch.Generator().manual_seed(M + N + K)
     flags = None
@@ -532,3 +533,30 @@ def test_k2_backward_also_stores_the_live_rows_compactly():
     dyc.fill_(float('nan'))
     got = ops.aggregate_bwd_pool(dpooled, argmax, act, csr, H, live=live, compact_out=dyc)
     assert torch.equal(got, ref) and torch.equal(dyc[:cnt], ref[idx]) and bool(dyc[cnt:].isnan().all())
+
+
+def test_k3_wgrad_cta_pair_form_in_a_subprocess():
+    """GPT_WGRAD_PAIR_MIN_K=100 (read once per process): the cta_group::2 form of the weight gradient on odd slice counts,
+    K not a multiple of 64 and ragged M, against float64."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from gcn_over_pruned_trees_b200 import ops\n"
+        "for M, N, K, frac in [(40001, 320, 512, 0.5), (33333, 200, 420, 1.0), (70000, 512, 448, 0.3), (40000, 512, 360, 1.0)]:\n"
+        "    g = torch.Generator().manual_seed(M)\n"
+        "    dy = torch.randn(M, N, generator=g).cuda(); x = torch.randn(M, K, generator=g).cuda()\n"
+        "    flags = (torch.rand(M, generator=g) < frac).to(torch.uint8).cuda() * 3\n"
+        "    live = (flags != 0)[:, None]\n"
+        "    ref = (dy * live).double().t() @ (x * live).double()\n"
+        "    dy[~live[:, 0]] = float('nan')\n"
+        "    dw = torch.zeros(N, K, device='cuda')\n"
+        "    ops.linear_wgrad(dy, x, 'tf32x3', out=dw, accumulate=True, flags=flags)\n"
+        "    rel = float((dw.double() - ref).abs().max() / ref.abs().max())\n"
+        "    assert rel <= 1e-5, (M, N, K, rel)\n"
+        "print('PAIR OK')\n")
+    env = dict(os.environ, GPT_WGRAD_PAIR_MIN_K='100',
+               PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'PAIR OK' in out.stdout, out.stdout + out.stderr
