@@ -14,7 +14,29 @@ gradient all-reduce (backward | all-reduce | clip + update).
 """
 import os
 
+import contextlib
+import gc
+
 import torch
+
+
+@contextlib.contextmanager
+def _graph_capture(graph, **kw):
+    """torch.cuda.graph with Python's cyclic collector held off for the duration of the capture.  A collection that runs in
+    the MIDDLE of a capture can finalise objects of an earlier engine (flat buffers, side streams, other CUDA graphs and
+    their private pools): their release calls into the CUDA runtime and invalidates the capture
+    (cudaErrorStreamCaptureInvalidated, seen when an eager FusedTrainStep of an earlier test became garbage during a later
+    GraphedTrainStep capture).  Everything collectable is collected first -- twice, finalisers can free more."""
+    gc.collect()
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, **kw):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 from .model.trainer import unpack_batch
 
@@ -128,7 +150,7 @@ class GraphedTrainStep(object):
         torch.cuda.synchronize()
         n0 = _lib.lib().gpt_launch_count()
         g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1, stream=self._stream):
+        with _graph_capture(g1, stream=self._stream):
             loss = self._fwd_bwd(static_in, static_lab)
             if self.reducer is None:
                 self._update()
@@ -136,7 +158,7 @@ class GraphedTrainStep(object):
         entry['grads'] = [p.grad for p in self.reducer.params if p.grad is not None] if self.reducer else None
         if self.reducer is not None:
             g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, pool=g1.pool(), stream=self._stream):
+            with _graph_capture(g2, pool=g1.pool(), stream=self._stream):
                 self._update()
             entry['g2'] = g2
         self.kernels_per_replay[key] = int(_lib.lib().gpt_launch_count() - n0)
@@ -612,7 +634,7 @@ class FusedTrainStep(object):
         torch.cuda.synchronize()
         n0 = _lib.lib().gpt_launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self.capture_stream):
+        with _graph_capture(g, stream=self.capture_stream):
             entry['loss'], entry['logits'] = self._run(entry['inputs'], entry['labels'])
         entry['graph'] = g
         self.kernels_per_replay[key] = int(_lib.lib().gpt_launch_count() - n0)
@@ -810,7 +832,7 @@ class FastUpdate(object):
     def _graph(self, fn, entry, pool=None):
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=self.capture_stream, pool=pool):
+        with _graph_capture(g, stream=self.capture_stream, pool=pool):
             fn(entry)
         return g
 
@@ -996,7 +1018,7 @@ class FusedPredict(object):
         else:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(g, stream=self.engine.capture_stream):
+            with _graph_capture(g, stream=self.engine.capture_stream):
                 self._run(entry)
             entry['graph'] = g
             g.replay()
