@@ -345,13 +345,15 @@ extern "C" int gpt_linear_wgrad_tf32x3_rows(const float* dy, const float* x, con
     if (rc != GPT_OK) return rc;
     if ((rc = tc::make_map_f32(&tm_x, x, M, K, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GPT_OK) return rc;
 
-    // Long reductions over >= 2 n-slices CAN run on CTA pairs (cta_group::2, see the kernel): X staged and split once per
-    // pair.  Measured at 2 097 152 rows x 512 columns of dY: with the old ring (hi and lo halves in every stage: two
+    // Long reductions over >= 2 n-slices run on CTA pairs (cta_group::2, see the kernel): X staged and split once per pair.
+    // Measured at 2 097 152 rows x 512 columns of dY.  Stand-alone: with the old ring (hi and lo halves in every stage: two
     // stages at K = 512) the pair was 19 % faster (6.29 -> 5.09 ms); with the deep ring + two just-in-time lo buffers both
-    // forms run the same 5.1-5.2 ms (K = 360: 4.31 single, 4.43-4.64 pair) at 63 % tensor-pipe activity, and the single
-    // CTAs place more freely next to the step's other kernels.  So pairs are opt-in: GPT_WGRAD_PAIR_MIN_K=<K>.
+    // forms run 5.1-5.2 ms at K = 512 (4.31 single, 4.43-4.64 pair at K = 360), 63 % tensor-pipe activity.  INSIDE the large
+    // step, where the weight gradients share the SMs with the data-gradient chain, the pair form wins: 38.5 ms (single),
+    // 38.0 (pairs at K = 512 only), 37.1 (pairs for both layers) -- half the shared-memory traffic per SM leaves more of
+    // the SM to its neighbours.  GPT_WGRAD_PAIR=0 / GPT_WGRAD_PAIR_MIN_K=<K> select the single-CTA form.
     static const bool pair_ok = [] { const char* e = getenv("GPT_WGRAD_PAIR"); return e == nullptr || atoi(e) != 0; }();
-    static const int pair_min_k = [] { const char* e = getenv("GPT_WGRAD_PAIR_MIN_K"); return e ? atoi(e) : (1 << 30); }();
+    static const int pair_min_k = [] { const char* e = getenv("GPT_WGRAD_PAIR_MIN_K"); return e ? atoi(e) : 0; }();
     if (pair_ok && n_slices >= 2 && M >= 32768 && K >= pair_min_k) {
         const int kboxes = ((K + 31) / 32 + 1) / 2 * 2;          // even: every chunk is halved between the two CTAs
         int tmem_cols = 32;

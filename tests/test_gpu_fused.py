@@ -285,8 +285,8 @@ def test_k3_wgrad_over_live_rows(M, N, K, frac):
                                         (40001, 320, 512, 0.5), (33333, 200, 420, 1.0), (70000, 512, 448, 0.3)])
 def test_k3_wgrad_on_tensor_cores_is_fp32_grade(M, N, K, frac):
     """csrc/wgrad_tcgen05.cu (MN-major operands straight from HBM, 3xTF32): dw += dy^T x over the live rows, against
-    fp64 at the fp32 parity tolerance (1e-5 relative); rows with flags == 0 may hold anything.  (The CTA-pair form of the
-    kernel is opt-in per process -- GPT_WGRAD_PAIR_MIN_K, tests/test_gpu_multi-style subprocess below.)"""
+    fp64 at the fp32 parity tolerance (1e-5 relative); rows with flags == 0 may hold anything.  (>= 2 n-slices: the CTA-pair
+    form; the single-CTA form of the same shapes runs in a subprocess below -- the switch is read once per process.)"""
     assert ops.wgrad_tc_ok(M, N, K)
     g = torch.Generator().manual_seed(M + N + K)
     flags = None
@@ -535,9 +535,9 @@ def test_k2_backward_also_stores_the_live_rows_compactly():
     assert torch.equal(got, ref) and torch.equal(dyc[:cnt], ref[idx]) and bool(dyc[cnt:].isnan().all())
 
 
-def test_k3_wgrad_cta_pair_form_in_a_subprocess():
-    """GPT_WGRAD_PAIR_MIN_K=100 (read once per process): the cta_group::2 form of the weight gradient on odd slice counts,
-    K not a multiple of 64 and ragged M, against float64."""
+def test_k3_wgrad_single_cta_form_in_a_subprocess():
+    """GPT_WGRAD_PAIR=0 (read once per process): the single-CTA form of the weight gradient on the shapes that take CTA
+    pairs by default (odd slice counts, K not a multiple of 64, ragged M), against float64."""
     import os
     import subprocess
     import sys
@@ -555,8 +555,8 @@ def test_k3_wgrad_cta_pair_form_in_a_subprocess():
         "    ops.linear_wgrad(dy, x, 'tf32x3', out=dw, accumulate=True, flags=flags)\n"
         "    rel = float((dw.double() - ref).abs().max() / ref.abs().max())\n"
         "    assert rel <= 1e-5, (M, N, K, rel)\n"
-        "print('PAIR OK')\n")
-    env = dict(os.environ, GPT_WGRAD_PAIR_MIN_K='100',
+        "print('SINGLE OK')\n")
+    env = dict(os.environ, GPT_WGRAD_PAIR='0',
                PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and 'PAIR OK' in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and 'SINGLE OK' in out.stdout, out.stdout + out.stderr
