@@ -238,3 +238,29 @@ def test_in_kernel_dropout_rate_and_backward_consistency(emulated, golden_adj):
     dF2, dR2, dS2 = ops._agg3_bwd(gout, ops._agg3_fwd(F, R, S, csr, cfg_m), csr, cfg_m)
     for a, b in ((dF, dF2), (dR, dR2), (dS, dS2)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('n_rows,frac', [(1, 1.0), (37, 0.0), (300, 0.3), (2500, 0.6)])
+def test_emulated_live_row_compaction_gather_scatter_and_column_sums(emulated, n_rows, frac):
+    """gpt_live_rows / gpt_gather_rows / gpt_scatter_rows / gpt_colsum_acc_rows from source on the CPU against numpy
+    (several 1024-row rounds of the single-CTA scan, empty and full lists, K not a multiple of 4)."""
+    g = torch.Generator().manual_seed(n_rows)
+    flags = (torch.rand(n_rows, generator=g) < frac).to(torch.uint8) * 5
+    live = ops.LiveRows(flags)
+    idx = flags.nonzero().flatten()
+    cnt = int(live.count)
+    assert cnt == idx.numel()
+    assert torch.equal(live.perm[:cnt].long(), idx)
+    inv = torch.full((n_rows,), -1, dtype=torch.int32)
+    inv[idx] = torch.arange(cnt, dtype=torch.int32)
+    assert torch.equal(live.inv, inv)
+    assert torch.equal(live.live, (torch.arange(n_rows) < cnt).to(torch.uint8))
+    for K in (8, 7):
+        x = torch.randn(n_rows, K, generator=g)
+        xc = live.gather(x, out=torch.full((n_rows, K), 9.0))
+        assert torch.equal(xc[:cnt], x[idx]) and bool((xc[cnt:] == 9.0).all())
+        back = live.scatter(xc)
+        assert torch.equal(back[idx], x[idx]) and not bool(back[flags == 0].ne(0).any())
+        s = torch.zeros(K)
+        ops._call('gpt_colsum_acc_rows', xc.data_ptr(), n_rows, K, live.count.data_ptr(), s.data_ptr(), None)
+        assert torch.allclose(s, x[idx].sum(0), rtol=1e-5, atol=1e-5)
