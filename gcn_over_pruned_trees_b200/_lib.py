@@ -51,6 +51,8 @@ SIGNATURES = {
     'gpt_linear_fwd_tf32x3': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_linear_dgrad_tf32x3': [_p, _p, _p, _c_int, _c_int, _c_int, _p],
     'gpt_embed_fwd': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p],
+    'gpt_embed_fwd_prep': [_p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p, _c_u32, _p, _p, _p, _p,
+                           _c_int, _p],
     'gpt_embed_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _p,
                       _c_u32, _p],
     'gpt_embed_bwd_grouped_workspace': [_c_int, _c_int],

@@ -15,6 +15,7 @@
 //   rows_sgd       : W[w] -= lr * clip * G[w] ; G[w] = 0 ; owner[w] = INT_MAX      (G stays all-zero between steps)
 // which is arithmetic-identical to clip_grad_norm_ + SGD over the dense tensor (train.py:224-227).
 #include "gpt_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -72,17 +73,14 @@ embed_fwd_kernel(const EmbParams p, float* __restrict__ x) {
 // The same rows for LARGE batches (>= 64 K token rows): one CTA per row means 2 M CTAs of 45 busy threads at the large
 // shape -- 3.2 ms, bound by the rate at which CTAs can be launched, for 3 GB of output.  Here a resident grid walks
 // (row, 8-column group) items with every thread busy; same Philox stream, bit-identical output.
-__global__ void __launch_bounds__(256)
-embed_fwd_rows_kernel(const EmbParams p, float* __restrict__ x) {
-    GPT_PDL_ENTER();
+__device__ __forceinline__ void embed_rows_body(const EmbParams& p, float* __restrict__ x, unsigned block, unsigned n_blocks) {
     const int D = p.E + p.Dp + p.Dn, ng = (D + 7) >> 3;
     const bool drop = p.thresh16 > 0;
     unsigned long long seed = 0, step = 0;
     if (drop) { seed = p.rng[0]; step = p.rng[1]; }
     const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const long long total = (long long)p.n_rows * ng;
-    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-         it += (long long)gridDim.x * blockDim.x) {
+    for (long long it = (long long)block * blockDim.x + threadIdx.x; it < total; it += (long long)n_blocks * blockDim.x) {
         const int row = (int)(it / ng), g = (int)(it - (long long)row * ng);
         const long long w = p.words[row];
         const long long ps = p.pos_w ? p.pos[row] : 0;
@@ -114,6 +112,69 @@ embed_fwd_rows_kernel(const EmbParams p, float* __restrict__ x) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (g * 8 + k < D) xr[k] = v[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+embed_fwd_rows_kernel(const EmbParams p, float* __restrict__ x) {
+    GPT_PDL_ENTER();
+    embed_rows_body(p, x, blockIdx.x, gridDim.x);
+}
+
+// The FRONT of a training step in one launch: the embedding rows (blocks [0, embed_blocks)) and, in the blocks behind them,
+// the per-step operand preparation of every GCN layer's weight for the 3xTF32 projections -- w -> [w_hi | w_lo | w^T_hi |
+// w^T_lo], hi = round_tf32, lo = w - hi, 32 x 32 tiles through shared memory (what gpt_weight_prep_tf32x3_batch does in a
+// launch of its own).  As separate root nodes of the captured step the two kernels start ~6 us apart and the first
+// projection waits for the later one across streams: it began at 17.7 us of the replay; behind this kernel, 12 us.
+struct FrontPrep {
+    const float* w[8];
+    float* ws[8];
+    int N[8], K[8];
+    int tile0[9];            // first tile of layer l in the flat tile index; tile0[n_layers] = number of tiles
+    int n_layers;
+};
+
+__device__ __forceinline__ float front_tf32_hi(float v) {     // round to nearest TF32 (ties away), as tc::tf32_hi
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+
+__global__ void __launch_bounds__(256)
+embed_fwd_rows_prep_kernel(const EmbParams p, float* __restrict__ x, const FrontPrep f, int embed_blocks) {
+    GPT_PDL_ENTER();
+    if ((int)blockIdx.x < embed_blocks) {
+        embed_rows_body(p, x, blockIdx.x, (unsigned)embed_blocks);
+        return;
+    }
+    __shared__ float th[32][33], tl[32][33];
+    const int tile = (int)blockIdx.x - embed_blocks;
+    int l = 0;
+    while (l + 1 < f.n_layers && tile >= f.tile0[l + 1]) ++l;
+    const float* __restrict__ w = f.w[l];
+    float* __restrict__ ws = f.ws[l];
+    const int N = f.N[l], K = f.K[l];
+    const int tiles_x = (K + 31) / 32, t = tile - f.tile0[l];
+    const int bx = t % tiles_x, by = t / tiles_x;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t nk = (size_t)N * K;
+    const int xk = bx * 32 + tx, y0 = by * 32;
+    for (int j = ty; j < 32; j += 8) {
+        if (xk < K && y0 + j < N) {
+            const size_t i = (size_t)(y0 + j) * K + xk;
+            const float v = w[i], h = front_tf32_hi(v);
+            ws[i] = h;
+            ws[nk + i] = v - h;
+            th[j][tx] = h;
+            tl[j][tx] = v - h;
+        }
+    }
+    __syncthreads();
+    const int ox = by * 32 + tx, oy0 = bx * 32;
+    for (int j = ty; j < 32; j += 8) {
+        if (ox < N && oy0 + j < K) {
+            const size_t o = (size_t)(oy0 + j) * N + ox;
+            ws[2 * nk + o] = th[tx][j];
+            ws[3 * nk + o] = tl[tx][j];
         }
     }
 }
@@ -468,11 +529,43 @@ extern "C" int gpt_embed_fwd(const int64_t* words, const int64_t* pos, const int
     int rc = fill_params(p, words, pos, ner, emb_w, pos_w, ner_w, n_rows, V, E, Dp, Dn, drop_p, rng_state, subseq);
     if (rc != GPT_OK || x == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
     if (n_rows == 0) return GPT_OK;
-    if (n_rows >= 65536) {
-        gpt_launch(embed_fwd_rows_kernel, dim3(148 * 8), dim3(256), 0, (cudaStream_t)stream, p, x);
+    static const int rows_min = [] { const char* e = getenv("GPT_EMBED_ROWS_MIN"); return e ? atoi(e) : 65536; }();
+    if (n_rows >= rows_min) {
+        const long long items = (long long)n_rows * ((E + Dp + Dn + 7) / 8);
+        long long blocks = (items + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        gpt_launch(embed_fwd_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p, x);
         return gpt_launch_status();
     }
     gpt_launch(embed_fwd_kernel, dim3(n_rows), dim3(kEmbThreads), 0, (cudaStream_t)stream, p, x);
+    return gpt_launch_status();
+}
+
+// gpt_embed_fwd (resident-grid form) and gpt_weight_prep_tf32x3_batch in ONE launch (see embed_fwd_rows_prep_kernel)
+extern "C" int gpt_embed_fwd_prep(const int64_t* words, const int64_t* pos, const int64_t* ner, const float* emb_w,
+                                  const float* pos_w, const float* ner_w, float* x, int n_rows, int V, int E, int Dp, int Dn,
+                                  float drop_p, const uint64_t* rng_state, uint32_t subseq, const float* const* w,
+                                  float* const* ws, const int* wN, const int* wK, int n_layers, void* stream) {
+    EmbParams p{};
+    int rc = fill_params(p, words, pos, ner, emb_w, pos_w, ner_w, n_rows, V, E, Dp, Dn, drop_p, rng_state, subseq);
+    if (rc != GPT_OK || x == nullptr) return rc != GPT_OK ? rc : GPT_ERR_BAD_ARG;
+    GPT_CHECK_ARG(w && ws && wN && wK && n_layers >= 1 && n_layers <= 8);
+    FrontPrep f{};
+    f.n_layers = n_layers;
+    int tiles = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        GPT_CHECK_ARG(w[l] && ws[l] && wN[l] >= 1 && wK[l] >= 1);
+        f.w[l] = w[l]; f.ws[l] = ws[l]; f.N[l] = wN[l]; f.K[l] = wK[l];
+        f.tile0[l] = tiles;
+        tiles += ((wK[l] + 31) / 32) * ((wN[l] + 31) / 32);
+    }
+    f.tile0[n_layers] = tiles;
+    const long long items = (long long)n_rows * ((E + Dp + Dn + 7) / 8);
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    gpt_launch(embed_fwd_rows_prep_kernel, dim3((unsigned)(blocks + tiles)), dim3(256), 0, (cudaStream_t)stream, p, x, f,
+               (int)blocks);
     return gpt_launch_status();
 }
 

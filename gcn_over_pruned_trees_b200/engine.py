@@ -330,6 +330,7 @@ class FusedTrainStep(object):
         # dependent launches on the side branch (7 + 5 us of edge latency) and the two weight gradients contend for tensor
         # memory: the tail moves from 131 to 139 us, the step from 140 to 147
         self.tc_wgrad_small = os.environ.get('GPT_TC_WGRAD_SMALL', '0') != '0'
+        self.fused_front = os.environ.get('GPT_FUSED_FRONT', '1') != '0'     # K5 forward + weight preparation in one launch
         if not training:
             return
         self.exchange_kind = {False: None, None: None, True: 'peer', 'peer': 'peer', 'nccl': 'nccl'}[data_parallel]
@@ -468,15 +469,25 @@ class FusedTrainStep(object):
             ev_csr.record(sa)                    # the chain waits for the CSR only, not for what follows on this branch
             if live is not None:
                 live.run(csr.flags)
+        emb_args = (words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
+                    None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
+        # the operand preparation rides in the embedding launch (one root node of the graph instead of two, and a
+        # programmatic edge to the first projection instead of an event across streams) when every layer has a 3xTF32
+        # workspace; otherwise it is a launch of its own on the side stream
+        x = None
+        if self.fused_front and mode == 'tf32x3':
+            x = ops.embed_fwd_prep(*emb_args, [lin.weight.data for lin in gcn.W], wss)
         with torch.cuda.stream(sb):
-            ops.weight_prep_all([lin.weight.data for lin in gcn.W], mode, wss)    # one launch: the first GEMM waits for it
-            ev_prep = torch.cuda.Event()
-            ev_prep.record(sb)
+            ev_prep = None
+            if x is None:
+                ops.weight_prep_all([lin.weight.data for lin in gcn.W], mode, wss)    # one launch: the first GEMM waits for it
+                ev_prep = torch.cuda.Event()
+                ev_prep.record(sb)
             if fl is not None:
                 ops.l2_prefetch(fl.param)        # every dense weight: first touches later in the step hit L2
-        x = ops.embed_fwd(words, pos if self.use_pos else None, ner if self.use_ner else None, self.emb_weight.data,
-                          None if pos_w is None else pos_w.data, None if ner_w is None else ner_w.data, p_in, rng, 0xE0)
-        main.wait_event(ev_prep)                 # (the prefetch behind it is joined at the end of the step)
+        if x is None:
+            x = ops.embed_fwd(*emb_args)
+            main.wait_event(ev_prep)             # (the prefetch behind it is joined at the end of the step)
         st.xs, st.acts = xs, acts = [], []
         h = x
         pooled = argmax = None

@@ -790,6 +790,26 @@ def embed_fwd(words, pos, ner, emb_w, pos_w, ner_w, drop_p, rng_state, subseq):
     return x
 
 
+def embed_fwd_prep(words, pos, ner, emb_w, pos_w, ner_w, drop_p, rng_state, subseq, weights, outs):
+    """embed_fwd + weight_prep_all(weights, 'tf32x3', outs) in one launch (the front of engine.FusedTrainStep's graph).
+    Returns None when some layer has no 3xTF32 workspace (the caller makes the two calls)."""
+    import ctypes
+    n = len(weights)
+    if n == 0 or n > 8 or any(o is None or o.dtype != torch.float32 for o in outs):
+        return None
+    V, E = emb_w.shape
+    Dp = pos_w.shape[1] if pos_w is not None else 0
+    Dn = ner_w.shape[1] if ner_w is not None else 0
+    x = torch.empty(words.shape + (E + Dp + Dn,), dtype=torch.float32, device=words.device)
+    _call('gpt_embed_fwd_prep', _ptr(words), _ptr(pos if Dp else None), _ptr(ner if Dn else None), _ptr(emb_w),
+          _ptr(pos_w), _ptr(ner_w), _ptr(x), words.numel(), V, E, Dp, Dn, float(drop_p),
+          _ptr(rng_state if drop_p > 0 else None), int(subseq),
+          (ctypes.c_void_p * n)(*[_ptr(w) for w in weights]), (ctypes.c_void_p * n)(*[_ptr(o) for o in outs]),
+          (ctypes.c_int * n)(*[w.shape[0] for w in weights]), (ctypes.c_int * n)(*[w.shape[1] for w in weights]), n,
+          _stream())
+    return x
+
+
 EMBED_GROUPED_MIN_ROWS = int(_os.environ.get('GPT_EMBED_GROUPED_MIN_ROWS', 65536))
 
 

@@ -193,6 +193,13 @@ int gpt_linear_dgrad_tf32x3_masked(const float* dy, const float* ws, float* g, c
 int gpt_embed_fwd(const int64_t* words, const int64_t* pos, const int64_t* ner, const float* emb_w, const float* pos_w,
                   const float* ner_w, float* x, int n_rows, int V, int E, int Dp, int Dn, float drop_p,
                   const uint64_t* rng_state, uint32_t subseq, void* stream);
+/* gpt_embed_fwd and gpt_weight_prep_tf32x3_batch in ONE launch -- the front of a captured training step: as two root nodes
+ * of the graph they start microseconds apart and the first projection waits for the later one across streams.  w / ws /
+ * wN / wK: host arrays of n_layers (<= 8) entries, as gpt_weight_prep_tf32x3_batch takes them. */
+int gpt_embed_fwd_prep(const int64_t* words, const int64_t* pos, const int64_t* ner, const float* emb_w, const float* pos_w,
+                       const float* ner_w, float* x, int n_rows, int V, int E, int Dp, int Dn, float drop_p,
+                       const uint64_t* rng_state, uint32_t subseq, const float* const* w, float* const* ws, const int* wN,
+                       const int* wK, int n_layers, void* stream);
 /* K5 backward: scatter-add dx (re-applying the same dropout mask) into the gradient tables (all accumulated with
  *     atomics, caller zeroes them; any of g_emb/g_pos/g_ner may be NULL).  Rows with flags == 0 are skipped (their
  *     gradient is exactly zero), word id 0 (padding_idx) and ids >= topn (model/gcn.py:83-86) get no gradient.

@@ -560,3 +560,28 @@ def test_k3_wgrad_single_cta_form_in_a_subprocess():
                PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and 'SINGLE OK' in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize('drop_p', (0.0, 0.5))
+def test_front_kernel_equals_embedding_forward_plus_weight_preparation(drop_p):
+    """gpt_embed_fwd_prep (K5 forward + the 3xTF32 operand preparation of every layer in one launch) == gpt_embed_fwd and
+    gpt_weight_prep_tf32x3_batch, bit for bit (same Philox stream, same rounding)."""
+    g = torch.Generator(device=DEV).manual_seed(4)
+    B, T, V = 50, 67, 3000
+    words = torch.randint(0, V, (B, T), device=DEV, generator=g)
+    pos = torch.randint(0, 40, (B, T), device=DEV, generator=g)
+    ner = torch.randint(0, 20, (B, T), device=DEV, generator=g)
+    emb, pw, nw = (torch.randn(n, d, device=DEV, generator=g) for n, d in ((V, 300), (47, 30), (24, 30)))
+    weights = [torch.randn(200, 360, device=DEV, generator=g), torch.randn(200, 200, device=DEV, generator=g),
+               torch.randn(36, 100, device=DEV, generator=g)]
+    rng = torch.tensor([12345, 7], dtype=torch.int64, device=DEV)
+    ref_x = ops.embed_fwd(words, pos, ner, emb, pw, nw, drop_p, rng, 0xE0)
+    ref_ws = [ops.weight_prep_buffer(w, 'tf32x3') for w in weights]
+    ops.weight_prep_all(weights, 'tf32x3', ref_ws)
+    outs = [torch.full_like(o, float('nan')) for o in ref_ws]
+    x = ops.embed_fwd_prep(words, pos, ner, emb, pw, nw, drop_p, rng, 0xE0, weights, outs)
+    torch.cuda.synchronize()
+    assert torch.equal(x, ref_x)
+    for a, b in zip(outs, ref_ws):
+        assert torch.equal(a, b)
+    assert ops.embed_fwd_prep(words, pos, ner, emb, pw, nw, drop_p, rng, 0xE0, weights, [None] + outs[1:]) is None
