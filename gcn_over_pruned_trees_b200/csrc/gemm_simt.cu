@@ -172,6 +172,9 @@ wgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
     __shared__ __align__(16) float Bs[BK][BN + 4];   // [slab row][k]
     __shared__ int s_rows[kRowWin];
     __shared__ int s_wcnt[kGemmThreads / 32];
+    // launched with the programmatic attribute (gpt_launch): behind a kernel of its own stream the grid is resident before
+    // that kernel has drained; behind an event of another stream the attribute changes nothing
+    GPT_PDL_ENTER();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * BM, k0 = blockIdx.y * BN;
     const int r_begin = blockIdx.z * rows_per_cta, r_end = min(M, r_begin + rows_per_cta);
@@ -329,11 +332,7 @@ extern "C" int gpt_linear_wgrad_rows_f32(const float* dy, const float* x, const 
     splits = (M + rows_per_cta - 1) / rows_per_cta;
     dim3 grid((N + BM - 1) / BM, (K + BN - 1) / BN, splits);
     if (grid.y > 65535 || grid.z > 65535) return GPT_ERR_UNSUPPORTED;
-#ifdef GPT_HOST_EMULATION
     gpt_launch(wgrad_rows_kernel, grid, dim3(kGemmThreads), 0, (cudaStream_t)stream, dy, x, flags, dw, M, N, K,
                rows_per_cta);
-#else
-    wgrad_rows_kernel<<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(dy, x, flags, dw, M, N, K, rows_per_cta);
-#endif
     return gpt_launch_status();
 }
