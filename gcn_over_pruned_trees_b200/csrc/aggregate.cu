@@ -86,6 +86,15 @@ __device__ __forceinline__ void add_pk(Pack4& a, const Pack4 b) {
     asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.lo) : "l"(b.lo));
     asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.hi) : "l"(b.hi));
 }
+__device__ __forceinline__ void mul_pk(Pack4& a, const float s) {   // all four lanes times one scalar
+    unsigned long long s2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(s2) : "f"(s));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a.lo) : "l"(s2));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a.hi) : "l"(s2));
+}
+// The value is what it was, but the compiler no longer knows where it came from: it is kept in registers instead of
+// being recomputed at every use.
+#define GPT_OPAQUE(ptr) asm volatile("" : "+l"(ptr))
 __device__ __forceinline__ float4 unpack(const Pack4 a) {
     float4 v;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(a.lo));
@@ -131,6 +140,12 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
+// 128-bit store to global memory through a pointer whose address space the compiler cannot see (GPT_OPAQUE)
+__device__ __forceinline__ void stg128(void* gptr, const float4 v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(gptr)), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 #endif
 
@@ -144,8 +159,9 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 //   perm [..]             row ids sorted by row length (longest first), padded with T
 //   col  [4T+4]           16-bit column indices (3T used; the tail is slack so that padded slots read in bounds)
 //   pool [NT/32][3][HS]x2 forward with fused pooling: per-warp partial (max, argmax) of the three pools
-//   actb [T][8]           forward, when the activation mask is written: one byte per (row, lane of the row's group)
+//   actb [T+1][8]         forward, when the activation mask is written: one byte per (row, lane of the row's group)
 //                         holding that lane's 4 activation bits; packed into the row's 32-bit word after the slice
+//                         (row T takes the stores of the padded slots, so that the store needs no branch)
 struct Layout {
     size_t tile, red, bits, bias, meta, perm, col, actb, pool, total;  // byte offsets
 };
@@ -161,14 +177,14 @@ __host__ __device__ inline Layout make_layout(int T, int H, int lpr, int nt, int
     size_t o = 0;
     L.tile = o; o += (size_t)nbuf * tile_floats(T, lpr) * 4;
     L.red = o;  o += fwd ? 0 : (size_t)groups * hs * 4;
-    L.bits = o; o += bits ? (size_t)(fwd ? 1 : nbuf) * bits_stride(T, lpr) * 4 : 0;
+    L.bits = o; o += bits ? (size_t)(fwd ? 1 : nbuf) * bits_stride(T, lpr) * 4 + (fwd ? 16 : 0) : 0;  // fwd: + row T
     L.bias = o; o += fwd ? (size_t)((H + hs - 1) / hs) * hs * 4 : 0;
     L.meta = o; o += (size_t)((T + 2) / 2 * 2) * 8;
     L.perm = o; o += (size_t)perm_len(T, groups) * 2;
     o = (o + 3) / 4 * 4;
     L.col = o;  o += (size_t)(4 * T + 4) * 2;
     o = (o + 7) / 8 * 8;
-    L.actb = o; o += actb ? (size_t)T * 8 : 0;
+    L.actb = o; o += actb ? (size_t)(T + 1) * 8 : 0;
     L.pool = o; o += pool ? (size_t)(nt / 32) * 3 * hs * 8 : 0;   // per-warp (value, argmax) partials of the fused pools
     L.total = (o + 15) / 16 * 16;
     return L;
@@ -297,7 +313,10 @@ enum { DROP_NONE = 0, DROP_PHILOX = 1, DROP_MASK = 2 };
 // (/root/reference/model/gcn.py:116-121, K4) fall out of the same pass: each thread keeps (max, argmax) of its 4 columns
 // over the rows it serves, lane groups meet by shuffles, warps in shared memory.  Ties keep the smallest row, an empty
 // pool yields -1e12 / -1, exactly as pool3_fwd_kernel.  p.out may then be null: the layer output itself is not stored.
-template <int LPR, int NT, bool ALIGNED, int DROP, bool POOL = false>
+// ACT: the activation bit mask is written (LPR == 8 only).  A template parameter, and the store itself free of
+// branches: with a run-time test around it the four rows a lane group has in flight became four separate convergence
+// regions, each with its own exposed shared-memory latency (1.73 ms against 1.54 ms without the mask at the large shape).
+template <int LPR, int NT, bool ALIGNED, int DROP, bool POOL = false, bool ACT = POOL>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? 2 : 3)) aggregate_fwd_kernel(const AggParams p, const __grid_constant__ CUtensorMap tm) {
     GPT_PDL_TRIGGER();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -305,7 +324,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? 2 : 3)) aggregate_
     const int T = p.T, H = p.H;
     const int b = blockIdx.y;
     const int nsl = (H + HS - 1) / HS;
-    const bool write_act = (p.act_out != nullptr) && (LPR == 8);
+    constexpr bool write_act = ACT && (LPR == 8);
     const Layout L = make_layout(T, H, LPR, NT, p.nbuf, true, DROP == DROP_PHILOX, write_act, POOL);
     float* tile0 = reinterpret_cast<float*>(smem_raw + L.tile);
     uint32_t* keepw = reinterpret_cast<uint32_t*>(smem_raw + L.bits);
@@ -417,14 +436,22 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? 2 : 3)) aggregate_
 
         const int c_lane = col0 + cl;
         const bool col_ok = c_lane < H;  // lanes past H stay in the loops (warp-wide ops inside) but never store
-        const float4 bias2 = lds128(bias_s + (uint32_t)c_lane * 4u);  // 2*bias, zero past H
+        const Pack4 bias2 = lds_pk(bias_s + (uint32_t)c_lane * 4u);  // 2*bias, zero past H
         const uint32_t tile_lane = tile_s0 + (uint32_t)(it & 1) * tile_bytes + (uint32_t)cl * 4u;
-        float* const out_lane = p.out + (size_t)b * T * H + c_lane;
+        // the lane's column of row 0 of this sentence; opaque to the compiler, which otherwise re-derives the 64-bit
+        // address from the kernel parameters for every row (6 instructions per row instead of one IMAD.WIDE)
+        char* out_lane = reinterpret_cast<char*>(p.out + (size_t)b * T * H + c_lane);
+        GPT_OPAQUE(out_lane);
+        const uint32_t row_bytes = (uint32_t)H * 4u;
         const float* const mask_lane = (DROP == DROP_MASK) ? p.drop_mask + (size_t)b * T * H + c_lane : nullptr;
         uint32_t* const act_sl = write_act ? p.act_out + act_index(b, T, H, sl) : nullptr;
+        const uint32_t actb_lane = actb_s + (uint32_t)(lane % LPR);
+        const uint32_t keep_lane = keep_s + (uint32_t)(cl >> 5) * 4u;
+        const bool store_out = !POOL || p.out != nullptr;
 
         // LPR lanes per node, four nodes in flight per lane group, taken in length-sorted order.  The loop is
-        // warp-uniform; slots past T map to the zero row / empty meta entry and are never stored.
+        // warp-uniform; slots past T map to the zero row / empty meta entry (and to the pad rows of the keep-words
+        // and of the activation bytes) and are never stored.  No branch inside: the four rows' epilogues interleave.
         for (int base0 = warp * RPW * 4; base0 < T; base0 += GROUPS * 4) {
             const uint2 pr = lds64(perm_s + (uint32_t)(base0 + sub * 4) * 2u);
             const int rows[4] = {(int)(pr.x & 0xffffu), (int)(pr.x >> 16), (int)(pr.y & 0xffffu), (int)(pr.y >> 16)};
@@ -436,33 +463,43 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? 2 : 3)) aggregate_
                 const uint2 m = lds64(meta_s + (uint32_t)rows[q] * 8u);
                 mx[q] = m.x;
                 inv[q] = __uint_as_float(m.y);  // 0 for unobservable rows -> output 0
+                // kept elements are scaled by 1/(1-p): folded into the row's 1/denom (relu commutes with a positive scale)
+                if (DROP == DROP_PHILOX) inv[q] *= dscale;
                 // the separate W(h) self term (the CSR row holds the 84-diagonal a second time)
                 acc[q] = lds_pk(tile_lane + (uint32_t)rows[q] * (HS * 4));
             }
             gather4<HS>(tile_lane, col_s, T, mx, acc);
+            uint32_t kw[4] = {0u, 0u, 0u, 0u};
+            if (DROP == DROP_PHILOX) {      // the four rows' keep-words, requested together
+#pragma unroll
+                for (int q = 0; q < 4; ++q) kw[q] = lds32(keep_lane + (uint32_t)rows[q] * (WPR * 4)) >> (cl & 31);
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int i = rows[q];
+                add_pk(acc[q], bias2);
+                mul_pk(acc[q], inv[q]);
                 const float4 a = unpack(acc[q]);
-                float res[4] = {fmaxf((a.x + bias2.x) * inv[q], 0.f), fmaxf((a.y + bias2.y) * inv[q], 0.f),
-                                fmaxf((a.z + bias2.z) * inv[q], 0.f), fmaxf((a.w + bias2.w) * inv[q], 0.f)};
+                float res[4] = {fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)};
                 const bool live = (i < T) && col_ok;
                 if (DROP == DROP_PHILOX) {
-                    const uint32_t kw = lds32(keep_s + (uint32_t)((i < T ? i : 0) * WPR + (cl >> 5)) * 4u) >> (cl & 31);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) res[v] = ((kw >> v) & 1u) ? res[v] * dscale : 0.f;
+                    for (int v = 0; v < 4; ++v) res[v] = ((kw[q] >> v) & 1u) ? res[v] : 0.f;
                 }
-                const uint32_t off = (uint32_t)i * (uint32_t)H;
                 if (DROP == DROP_MASK) {
                     if (live) {
-                        const float* m = mask_lane + off;
+                        const float* m = mask_lane + (uint32_t)i * (uint32_t)H;
 #pragma unroll
                         for (int v = 0; v < 4; ++v)
                             if (c_lane + v < H) res[v] *= m[v];
                     }
                 }
-                if (live && p.out != nullptr)
-                    store4<ALIGNED>(out_lane + off, make_float4(res[0], res[1], res[2], res[3]), c_lane, H);
+                if (live && store_out) {
+                    char* const dst = out_lane + (size_t)(uint32_t)i * (size_t)row_bytes;
+                    const float4 r4 = make_float4(res[0], res[1], res[2], res[3]);
+                    if (ALIGNED) stg128(dst, r4);   // H % 4 == 0 keeps the vector inside the row
+                    else store4<false>(reinterpret_cast<float*>(dst), r4, c_lane, H);
+                }
                 if (POOL && live) {
                     const unsigned f = p.flags[(size_t)b * T + i];       // bit0 in tree, bit1 subject, bit2 object
 #pragma unroll
@@ -479,10 +516,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? 2 : 3)) aggregate_
                         }
                     }
                 }
-                if (write_act && i < T) {  // CTA-uniform; LPR == 8: this lane's 4 activation bits, packed after the slice
+                if (write_act) {
+                    // LPR == 8: this lane's 4 activation bits, packed into the row's word after the slice.  Slots past T
+                    // write row T of actb; columns past H hold zeros (tile and bias are zero there), so do their bits.
                     const uint32_t nib = (res[0] > 0.f ? 1u : 0u) | (res[1] > 0.f ? 2u : 0u) | (res[2] > 0.f ? 4u : 0u) |
                                          (res[3] > 0.f ? 8u : 0u);
-                    sts_u8(actb_s + (uint32_t)i * 8u + (uint32_t)(lane % LPR), col_ok ? nib : 0u);
+                    sts_u8(actb_lane + (uint32_t)i * 8u, nib);
                 }
             }
         }
@@ -682,7 +721,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 3) aggregate_bwd_kernel(co
         const int c_lane = col0 + cl;
         const bool col_ok = c_lane < H;
         const uint32_t tile_lane = tile_s + (uint32_t)cl * 4u;
-        float* const out_lane = p.out + base + c_lane;
+        char* out_lane = reinterpret_cast<char*>(p.out + base + c_lane);
+        GPT_OPAQUE(out_lane);       // (see the forward: one IMAD.WIDE per stored row instead of a re-derived address)
+        const uint32_t row_bytes = (uint32_t)H * 4u;
         Pack4 csum;
         csum.lo = 0ull;
         csum.hi = 0ull;
@@ -700,13 +741,19 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 3) aggregate_bwd_kernel(co
             gather4<HS>(tile_lane, col_s, T, mx, acc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (rows[q] < T && col_ok) {
-                    store4<ALIGNED>(out_lane + (uint32_t)rows[q] * (uint32_t)H, unpack(acc[q]), c_lane, H);
-                    if (p.out_c != nullptr) {           // CTA-uniform
+                if (rows[q] < T && col_ok) {            // (a predicated store, no branch)
+                    char* const dst = out_lane + (size_t)(uint32_t)rows[q] * (size_t)row_bytes;
+                    if (ALIGNED) stg128(dst, unpack(acc[q]));
+                    else store4<false>(reinterpret_cast<float*>(dst), unpack(acc[q]), c_lane, H);
+                }
+            if (p.out_c != nullptr) {                   // CTA-uniform: the live rows a second time, in compact order
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (rows[q] < T && col_ok) {
                         const int pos = p.inv[(size_t)b * T + rows[q]];
                         if (pos >= 0) store4<ALIGNED>(p.out_c + (size_t)pos * H + c_lane, unpack(acc[q]), c_lane, H);
                     }
-                }
+            }
         }
         if (p.dbias != nullptr) *reinterpret_cast<float4*>(red + (warp * RPW + sub) * HS + cl) = unpack(csum);
         __syncthreads();  // tile buffer free for the refill; red[] complete
@@ -778,13 +825,23 @@ int launch_kernel(K kernel, const AggConfig& c, const AggParams& p, const CUtens
 template <int LPR, int NT, bool ALIGNED>
 int launch(bool fwd, const AggConfig& c, const AggParams& p, const CUtensorMap& tm, cudaStream_t st) {
     if (!fwd) return launch_kernel(aggregate_bwd_kernel<LPR, NT, ALIGNED>, c, p, tm, st);
+    if (p.pool_out != nullptr) {
+        if (LPR == 8 && NT == 256 && p.act_out != nullptr && p.drop_mask == nullptr && !(p.rng != nullptr && p.thresh16 > 0))
+            return launch_kernel(aggregate_fwd_kernel<8, 256, ALIGNED, DROP_NONE, true>, c, p, tm, st);
+        return GPT_ERR_UNSUPPORTED;
+    }
+    if (LPR == 8 && p.act_out != nullptr) {     // with the activation bit mask (its layout is that of 8 lanes per row)
+        constexpr int L8 = 8;                   // (the other widths name the same kernels: nothing more is instantiated)
+        if (p.drop_mask != nullptr)
+            return launch_kernel(aggregate_fwd_kernel<L8, NT, ALIGNED, DROP_MASK, false, true>, c, p, tm, st);
+        if (p.rng != nullptr && p.thresh16 > 0)
+            return launch_kernel(aggregate_fwd_kernel<L8, NT, ALIGNED, DROP_PHILOX, false, true>, c, p, tm, st);
+        return launch_kernel(aggregate_fwd_kernel<L8, NT, ALIGNED, DROP_NONE, false, true>, c, p, tm, st);
+    }
+    if (p.act_out != nullptr) return GPT_ERR_UNSUPPORTED;   // pick_config chooses 8 lanes per row whenever a mask is asked for
     if (p.drop_mask != nullptr) return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_MASK>, c, p, tm, st);
     if (p.rng != nullptr && p.thresh16 > 0)
         return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_PHILOX>, c, p, tm, st);
-    if (p.pool_out != nullptr) {
-        if (LPR == 8 && NT == 256) return launch_kernel(aggregate_fwd_kernel<8, 256, ALIGNED, DROP_NONE, true>, c, p, tm, st);
-        return GPT_ERR_UNSUPPORTED;
-    }
     return launch_kernel(aggregate_fwd_kernel<LPR, NT, ALIGNED, DROP_NONE>, c, p, tm, st);
 }
 

@@ -32,6 +32,13 @@ inline void add_pk(Pack4& a, const Pack4 b) {
     for (int i = 0; i < 4; ++i) x[i] += y[i];
     std::memcpy(&a, x, 16);
 }
+inline void mul_pk(Pack4& a, const float s) {
+    float x[4];
+    std::memcpy(x, &a, 16);
+    for (int i = 0; i < 4; ++i) x[i] *= s;
+    std::memcpy(&a, x, 16);
+}
+#define GPT_OPAQUE(ptr) ((void)(ptr))
 inline float4 unpack(const Pack4 a) {
     float4 v;
     std::memcpy(&v, &a, 16);
@@ -65,4 +72,5 @@ inline uint32_t lds_u16(uint32_t a) {
 inline void sts_u8(uint32_t a, uint32_t v) { *emu::smem_ptr(a) = (unsigned char)v; }
 inline void sts128(uint32_t a, const float4 v) { std::memcpy(emu::smem_ptr(a), &v, 16); }
 inline void sts_f32(uint32_t a, float v) { std::memcpy(emu::smem_ptr(a), &v, 4); }
+inline void stg128(void* gptr, const float4 v) { std::memcpy(gptr, &v, 16); }
 inline void fence_mbar_init() {}
