@@ -681,6 +681,40 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 3) aggregate_bwd_kernel(co
                 }
             }
             __syncthreads();
+        } else if (!p.pre_scaled && use_act && p.drop_mask == nullptr) {
+            // the path the model takes ([out > 0] from the forward's bit mask, in-kernel dropout): a thread keeps its
+            // column group and walks rows; the factor dropscale * bit is selected, not converted and multiplied (four
+            // I2F per item were a quarter-rate pipe's worth of the whole pass)
+            const int cc = (tid % LPR) * 4;
+            if (col0 + cc < H) {
+                constexpr int RSTEP = NT / LPR;     // rows between a thread's consecutive items
+                for (int row0 = tid / LPR; row0 < T; row0 += 4 * RSTEP) {
+                    // four items loaded, then computed, then stored: the loads are in flight together (the accessors
+                    // are ordered among themselves, so a plain unrolled loop would expose one latency per item)
+                    float4 g[4];
+                    float inv[4];
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = min(row0 + j * RSTEP, T);       // past T: the zero row / the empty meta entry
+                        g[j] = lds128(tile_s + (uint32_t)(row * HS + cc) * 4u);
+                        inv[j] = __uint_as_float(lds32(meta_s + (uint32_t)row * 8u + 4u));
+                        w[j] = lds32(actw_s + (uint32_t)min(row, T - 1) * 4u) >> cc;  // LPR == 8: cc < 32
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // same association order on every path: (gout * m) * inv
+                        g[j].x = g[j].x * ((w[j] & 1u) ? ds : 0.f) * inv[j];
+                        g[j].y = g[j].y * ((w[j] & 2u) ? ds : 0.f) * inv[j];
+                        g[j].z = g[j].z * ((w[j] & 4u) ? ds : 0.f) * inv[j];
+                        g[j].w = g[j].w * ((w[j] & 8u) ? ds : 0.f) * inv[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (row0 + j * RSTEP < T) sts128(tile_s + (uint32_t)((row0 + j * RSTEP) * HS + cc) * 4u, g[j]);
+                }
+            }
+            __syncthreads();
         } else if (!p.pre_scaled) {
 #pragma unroll 2
         for (int q = tid; q < T * LPR; q += NT) {
