@@ -293,7 +293,7 @@ def aggregation_roofline(args, peaks):
     bytes_bwd = 2 * B * T * H * 4 + B * T * H // 8 + 4 * (B * (T + 1)) + 4 * nnz + 4 * B * T
     peak = peaks['hbm_gbs']
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
-    tpath = os.path.join(REPO, 'profiles', 'r01_k2_fwd_traffic.json')
+    tpath = os.path.join(REPO, 'profiles', 'r02_k2_fwd_traffic.json')
     if os.path.exists(tpath) and B == 4096:
         t = json.load(open(tpath))
         traffic = t['dram_bytes_read'] + t['dram_bytes_write']
@@ -302,7 +302,7 @@ def aggregation_roofline(args, peaks):
     del y, out, gout, act
     torch.cuda.empty_cache()
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9  # noqa: E731
-    return {'bound': 'hbm', 'kernel': 'aggregate_fwd_kernel<8,512,1,1> (K2 forward as the training step runs it: '
+    return {'bound': 'hbm', 'kernel': 'aggregate_fwd_kernel<8,512,1,1,0,1> (K2 forward as the training step runs it: '
                                       'dropout 0.5 + activation bit mask)',
             'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peaks['source'],
             'traffic': traffic,
