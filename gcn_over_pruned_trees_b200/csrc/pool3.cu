@@ -34,11 +34,17 @@ pool3_fwd_kernel(const float* __restrict__ h, const unsigned char* __restrict__ 
     int* s_list = reinterpret_cast<int*>(smem_raw);           // [T]  t | flags << 16
     float* s_val = reinterpret_cast<float*>(s_list + ((T + 3) & ~3));   // [G][3][H]
     int* s_arg = reinterpret_cast<int*>(s_val + (size_t)G * 3 * H);     // [G][3][H]
+    // the sentence's flags, fetched by the whole CTA at once (one exposed global latency instead of one per 32 tokens
+    // in warp 0's compaction loop below); parked in the first partial-result slot, which is not written before the
+    // second barrier
+    unsigned char* s_flags = reinterpret_cast<unsigned char*>(s_val);
+    for (int t = tid; t < T; t += kPoolFwdThreads) s_flags[t] = flags[(size_t)b * T + t];
+    __syncthreads();
     if (tid < 32) {
         int n = 0, c0 = 0, c1 = 0, c2 = 0;
         for (int base = 0; base < T; base += 32) {
             const int t = base + tid;
-            const unsigned f = t < T ? flags[(size_t)b * T + t] : 0u;
+            const unsigned f = t < T ? s_flags[t] : 0u;
             const unsigned m = __ballot_sync(GPT_FULL_MASK, f != 0);
             if (f != 0) s_list[n + __popc(m & ((1u << tid) - 1u))] = t | (int)(f << 16);
             n += __popc(m);
@@ -116,7 +122,8 @@ pool3_fwd_kernel(const float* __restrict__ h, const unsigned char* __restrict__ 
 size_t pool_fwd_smem(int T, int H, int V) {
     const int cols = H / V;
     const int G = cols < kPoolFwdThreads ? kPoolFwdThreads / cols : 1;
-    return (size_t)((T + 3) & ~3) * 4 + (size_t)G * 3 * H * 8;
+    const size_t partials = (size_t)G * 3 * H * 8;      // the flags (T bytes) are staged in the same space first
+    return (size_t)((T + 3) & ~3) * 4 + (partials > (size_t)T ? partials : (size_t)((T + 15) & ~15));
 }
 
 __global__ void __launch_bounds__(kPoolThreads)
