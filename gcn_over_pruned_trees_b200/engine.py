@@ -947,17 +947,21 @@ class FastUpdate(object):
             self.dirty = False
         self.fast_backwards = 0
         self.mixed = False
+        own = None if set_to_none else self._own_ptrs()
         for p in self.trainer.optimizer.param_groups[0]['params']:
             if set_to_none:
                 p.grad = None
-            elif p.grad is not None and p.grad.data_ptr() not in self._own_ptrs():
+            elif p.grad is not None and p.grad.data_ptr() not in own:
                 p.grad.zero_()
 
     def _own_ptrs(self):
-        eng = self.engine
-        ptrs = {eng.flat.g(p).data_ptr() for p in eng.flat.params}
-        if eng.sparse is not None:
-            ptrs.add(eng.sparse.G.data_ptr())
+        ptrs = getattr(self, '_own_ptr_set', None)
+        if ptrs is None:                     # the shared buffers live as long as the engine: computed once
+            eng = self.engine
+            ptrs = {eng.flat.g(p).data_ptr() for p in eng.flat.params}
+            if eng.sparse is not None:
+                ptrs.add(eng.sparse.G.data_ptr())
+            self._own_ptr_set = ptrs
         return ptrs
 
 
