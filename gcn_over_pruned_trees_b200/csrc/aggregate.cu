@@ -317,7 +317,7 @@ enum { DROP_NONE = 0, DROP_PHILOX = 1, DROP_MASK = 2 };
 // branches: with a run-time test around it the four rows a lane group has in flight became four separate convergence
 // regions, each with its own exposed shared-memory latency (1.73 ms against 1.54 ms without the mask at the large shape).
 template <int LPR, int NT, bool ALIGNED, int DROP, bool POOL = false, bool ACT = POOL>
-__global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? 2 : 3)) aggregate_fwd_kernel(const AggParams p, const __grid_constant__ CUtensorMap tm) {
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : (POOL ? (NT == 128 ? 4 : 2) : 3)) aggregate_fwd_kernel(const AggParams p, const __grid_constant__ CUtensorMap tm) {
     GPT_PDL_TRIGGER();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int HS = 4 * LPR, RPW = 32 / LPR, GROUPS = (NT / 32) * RPW, WPR = (HS + 31) / 32;
@@ -832,6 +832,18 @@ AggConfig pick_config(const AggParams& p, bool fwd, int force_vec) {
         if (smem > 54 * 1024) continue;                       // want >= 4 CTAs per SM
         if (lpr > 8 && (long)slices(lpr) * B < 2 * 148) continue;  // and enough CTAs to fill the machine
         c.lpr = lpr; c.nt = 256; c.nbuf = 1; c.grid_x = slices(lpr); c.smem = smem;
+        if (fwd && p.pool_out != nullptr && lpr == 8) {
+            // The fused-pool form holds 24 (max, argmax) registers more: 128 per thread, two 256-thread CTAs per SM.
+            // A batch of 50 sentences x 7 slices is 350 CTAs against 296 places: a second, nearly empty wave (11 us
+            // against 6 for the plain form in the step's timeline).  CTAs of 128 threads fit four to an SM: one wave.
+            const char* e_nt = getenv("GPT_AGG_POOL_NT");          // tuning / test knob: 128 or 256
+            const int force_nt = e_nt ? atoi(e_nt) : 0;
+            const long ctas = (long)c.grid_x * B;
+            if (force_nt == 128 || (force_nt != 256 && ctas > 2 * 148 && ctas <= 4 * 148)) {
+                c.nt = 128;
+                c.smem = bytes(lpr, 128, 1);
+            }
+        }
         return c;
     }
     c.lpr = 8; c.nt = 512;
@@ -910,6 +922,11 @@ int dispatch(bool fwd, AggParams& p, int force_vec, cudaStream_t st) {
         }
     }
     if (c.nt == 512) return aligned ? launch<8, 512, true>(fwd, c, p, tm, st) : launch<8, 512, false>(fwd, c, p, tm, st);
+    if (c.nt == 128) {      // fused-pool forward only (pick_config)
+        if (!fwd || p.pool_out == nullptr || p.act_out == nullptr || c.lpr != 8) return GPT_ERR_UNSUPPORTED;
+        return aligned ? launch_kernel(aggregate_fwd_kernel<8, 128, true, DROP_NONE, true>, c, p, tm, st)
+                       : launch_kernel(aggregate_fwd_kernel<8, 128, false, DROP_NONE, true>, c, p, tm, st);
+    }
     if (aligned) {
         if (c.lpr == 32) return launch<32, 256, true>(fwd, c, p, tm, st);
         if (c.lpr == 16) return launch<16, 256, true>(fwd, c, p, tm, st);
@@ -975,7 +992,7 @@ extern "C" int gpt_gcn_aggregate_fwd_pool_supported(int B, int T, int H) {
     p.act_out = reinterpret_cast<uint32_t*>(1);      // only null-ness is looked at by pick_config
     p.pool_out = reinterpret_cast<float*>(1);
     const AggConfig c = pick_config(p, true, 0);
-    return (c.nt == 256 && c.lpr == 8) ? 1 : 0;
+    return ((c.nt == 256 || c.nt == 128) && c.lpr == 8) ? 1 : 0;
 }
 
 extern "C" int gpt_gcn_aggregate_bwd(const float* gout, const float* out, const uint32_t* act_mask,

@@ -143,6 +143,24 @@ def test_k2_source_last_layer_fused_with_the_three_max_pools_both_directions():
     assert torch.equal(dy, dy_ref)
 
 
+def test_k2_source_fused_pool_forward_in_128_thread_ctas(monkeypatch):
+    """The 128-thread form of the fused-pool forward (chosen when the 256-thread form would need a second wave of CTAs,
+    e.g. 50 sentences x 7 slices) == the 256-thread form, bit for bit, ragged widths included."""
+    batch = synth.make_batch(36, batch_size=9)
+    csr = _csr_of(batch, 1)
+    B, T = batch[0].shape
+    g = torch.Generator().manual_seed(5)
+    for H in (64, 200, 72):
+        y = torch.randn(B * T, H, generator=g)
+        bias = torch.randn(H, generator=g)
+        monkeypatch.setenv('GPT_AGG_POOL_NT', '256')
+        ref = ops.aggregate_fwd_pool(y, csr, bias, want_out=True)
+        monkeypatch.setenv('GPT_AGG_POOL_NT', '128')
+        got = ops.aggregate_fwd_pool(y, csr, bias, want_out=True)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize('k', (-1, 1))
 def test_k2_source_persistent_double_buffered_path_512_tokens(k, monkeypatch):
     """Large sentence tiles (the shape the roofline number is quoted on): the 512-thread CTA walks the sentence's column
