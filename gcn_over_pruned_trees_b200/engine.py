@@ -319,7 +319,7 @@ class FusedTrainStep(object):
         # the side branches (K1, weight preparation, every weight gradient) run at the same priority as the chain: with
         # default-priority side streams the live-row weight gradients were starved by the data-gradient chain and ended
         # 10 us after it (34 us for a 17 us kernel); at equal priority both ends meet (147 -> 142 us per step)
-        _sp = -1 if os.environ.get('GPT_SIDE_PRIO', '1') == '1' else 0
+        _sp = -int(os.environ.get('GPT_SIDE_PRIO', '1'))      # 0: default priority, 1: the chain's, 2: above the chain
         self.side = (torch.cuda.Stream(priority=_sp), torch.cuda.Stream(priority=_sp))
         # the step is captured on a high-priority stream: when a side branch (weight gradients, K1) and the chain of
         # data-dependent kernels compete for SMs, the chain goes first
