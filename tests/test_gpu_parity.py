@@ -19,6 +19,13 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
+@pytest.fixture(params=['warp_per_sentence', 'cta_per_sentence'])
+def k1_form(request, monkeypatch):
+    """Both forms of K1 (one warp / one CTA per sentence) on every K1 case; the library reads the threshold per call."""
+    monkeypatch.setenv('GPT_K1_BLOCK_MIN_T', '1' if request.param == 'cta_per_sentence' else '1000000')
+    return request.param
+
+
 def _csr_of(batch, k, dataset='tacred'):
     off = 4 if dataset == 'tacred' else 3
     deprel, head, subj_pos, obj_pos = [t.to(DEV) for t in batch[off:off + 4]]
@@ -39,7 +46,7 @@ def _rel(a, b):
 # ---------------------------------------------------------------- K1 ------------------------------------------
 
 @pytest.mark.parametrize('split', cases.SPLITS)
-def test_k1_bundled_sample_matches_reference(golden_adj, split):
+def test_k1_bundled_sample_matches_reference(golden_adj, split, k1_form):
     batch = cases.batch_from_npz(golden_adj, split)
     for k in cases.PRUNE_KS:
         csr = _csr_of(batch, k)
@@ -55,7 +62,7 @@ def test_k1_bundled_sample_matches_reference(golden_adj, split):
 
 
 @pytest.mark.parametrize('seed', cases.SYNTH_ADJ_SEEDS + (1, 2, 3))
-def test_k1_synthetic_matches_oracle(seed):
+def test_k1_synthetic_matches_oracle(seed, k1_form):
     batch = synth.make_batch(seed, batch_size=50)
     for k in cases.PRUNE_KS + (7,):
         csr = _csr_of(batch, k)
@@ -69,7 +76,7 @@ def test_k1_synthetic_matches_oracle(seed):
                 assert np.all(np.diff(seg) > 0)
 
 
-def test_k1_subj_obj_flags():
+def test_k1_subj_obj_flags(k1_form):
     batch = synth.make_batch(4, batch_size=20)
     csr = _csr_of(batch, 1)
     f = csr.flags.cpu().numpy()
@@ -78,7 +85,7 @@ def test_k1_subj_obj_flags():
 
 
 @pytest.mark.parametrize('name', sorted(cases.EDGE_TREES))
-def test_k1_edge_trees(golden_adj, name):
+def test_k1_edge_trees(golden_adj, name, k1_form):
     head, subj, obj, deprel = cases.EDGE_TREES[name]
     n, width = len(head), len(head) + 3           # padded on purpose
     pad = lambda a, fill=0: torch.tensor([list(a) + [fill] * (width - n)], dtype=torch.int64, device=DEV)
@@ -93,7 +100,7 @@ def test_k1_edge_trees(golden_adj, name):
         assert csr.to_dense().numpy()[0, n:, :].sum() == 0
 
 
-def test_k1_512_token_sentences(golden_adj):
+def test_k1_512_token_sentences(golden_adj, k1_form):
     import hashlib
     batch = synth.make_batch(900, batch_size=6, fixed_len=512)
     for k in (-1, 1):
@@ -102,7 +109,7 @@ def test_k1_512_token_sentences(golden_adj):
         assert sha == bytes(golden_adj['synth512/k%d/sha' % k]).decode()
 
 
-def test_k1_malformed_trees_are_flagged_not_hung():
+def test_k1_malformed_trees_are_flagged_not_hung(k1_form):
     def run(head, subj, obj, k, deprel=None):
         n = len(head)
         t = lambda a: torch.tensor([a], dtype=torch.int64, device=DEV)

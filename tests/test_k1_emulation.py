@@ -37,6 +37,14 @@ def _csr_of(batch, k):
     return ops.prune_csr(batch[5], batch[6], batch[7], batch[4], batch[1], k)
 
 
+@pytest.fixture(autouse=True, params=['warp_per_sentence', 'cta_per_sentence'])
+def k1_form(request, monkeypatch):
+    """Every case below runs through both forms of K1: one warp per sentence (the default below 256 tokens) and one CTA
+    per sentence (the default from 256 tokens up); gpt_prune_csr reads the threshold on every call."""
+    monkeypatch.setenv('GPT_K1_BLOCK_MIN_T', '1' if request.param == 'cta_per_sentence' else '1000000')
+    return request.param
+
+
 def _oracle_adj(batch, k):
     lens = synth.batch_lengths(batch).numpy()
     return tree_oracle.batch_adjacency(batch[5].numpy(), batch[6].numpy(), batch[7].numpy(), batch[4].numpy(), lens,
