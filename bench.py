@@ -297,6 +297,30 @@ def aggregation_roofline(args, peaks):
     if os.path.exists(tpath) and B == 4096:
         t = json.load(open(tpath))
         traffic = t['dram_bytes_read'] + t['dram_bytes_write']
+    # K1 and K4 forward at the same shape (SURVEY.md 8d names them as HBM-bound kernels too); never lets the K2 record down
+    k1k4 = {}
+    try:
+        def _avg_ms(fn, reps=10, warm=3):
+            for _ in range(warm):
+                fn()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            torch.cuda.synchronize()
+            for a, b in evs:
+                a.record()
+                fn()
+                b.record()
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs) / reps
+        t_k1 = _avg_ms(lambda: ops.prune_csr(batch[5], batch[6], batch[7], batch[4], batch[1], -1))
+        k1_bytes = B * T * 33 + 4 * B * (T + 1) + 5 * nnz + 5 * B * T + 8 * B
+        t_k4 = _avg_ms(lambda: ops.pool3_fwd(out, csr, ops.POOL_TYPES['max']))
+        k4_bytes = B * T * H * 4 + B * 3 * H * 8 + B * T
+        k1k4 = {'k1_prune_csr_ms': t_k1, 'k1_bytes_per_launch': k1_bytes, 'k1_gbs': k1_bytes / (t_k1 * 1e-3) / 1e9,
+                'k1_frac': k1_bytes / (t_k1 * 1e-3) / 1e9 / peak,
+                'k4_pool3_fwd_ms': t_k4, 'k4_bytes_per_launch': k4_bytes, 'k4_gbs': k4_bytes / (t_k4 * 1e-3) / 1e9,
+                'k4_frac': k4_bytes / (t_k4 * 1e-3) / 1e9 / peak}
+    except Exception as exc:
+        k1k4 = {'k1_k4_error': repr(exc)}
     bytes_train = bytes_fwd + B * T * H // 8             # + the 1-bit activation mask the backward reads
     ach = bytes_train / (results['fwd_train'] * 1e-3) / 1e9
     del y, out, gout, act
@@ -317,7 +341,7 @@ def aggregation_roofline(args, peaks):
                       'bwd_bytes_per_launch': bytes_bwd,
                       'bwd_pre_scaled_ms': results['bwd_pre'],
                       'bwd_pre_scaled_gbs': gbs(bytes_bwd_pre, results['bwd_pre']),
-                      'bwd_pre_scaled_frac': gbs(bytes_bwd_pre, results['bwd_pre']) / peak}}
+                      'bwd_pre_scaled_frac': gbs(bytes_bwd_pre, results['bwd_pre']) / peak, **k1k4}}
 
 
 def load_peaks():
